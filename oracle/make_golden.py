@@ -1,0 +1,96 @@
+"""Generate tests/golden/*.npz by running the REAL reference code (imported from
+/root/reference through oracle/refstubs) on the seeded synthetic inputs of
+temporalstereo_b200.synth.  Run in the build container only:
+
+    python oracle/make_golden.py
+
+Inputs are not stored (they are re-derived from the seeds); only reference outputs are.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_import  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+from temporalstereo_b200 import synth  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+torch.set_num_threads(1)            # the reference is thread-count sensitive
+
+
+def save(name, **arrs):
+    np.savez_compressed(os.path.join(OUT, name), **{k: np.asarray(v, dtype=np.float32) for k, v in arrs.items()})
+    print("wrote", name, {k: tuple(np.shape(v)) for k, v in arrs.items()})
+
+
+def op_inputs(seed, B, C, H, W, S):
+    rng = np.random.RandomState(seed)
+    L = torch.from_numpy(rng.standard_normal((B, C, H, W)).astype(np.float32))
+    R = torch.from_numpy(rng.standard_normal((B, C, H, W)).astype(np.float32))
+    smp = torch.from_numpy(rng.uniform(-3.0, W / 2.0, (B, S, H, W)).astype(np.float32))
+    return L, R, smp
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ref_import.setup()
+    from architecture.modeling.aggregation.utils.block_cost import block_cost as ref_block_cost
+    from architecture.modeling.layers.inverse_warp import project_to_3d as ref_project
+
+    # ---- a1/a2/a3: block_cost, both branches, odd sizes exercise floor pooling ----
+    with torch.no_grad():
+        for tag, (B, C, H, W, S) in {"a": (2, 16, 10, 14, 5), "b": (1, 8, 9, 13, 8)}.items():
+            L, R, smp = op_inputs(10, B, C, H, W, S)
+            save(f"block_cost_warp_{tag}.npz", out=ref_block_cost(L, R, smp, 3).numpy(), shape=[B, C, H, W, S])
+            save(f"block_cost_shift_{tag}.npz", out=ref_block_cost(L, R, S, 3).numpy(), shape=[B, C, H, W, S])
+
+        # ---- a18: project_to_3d ----
+        st = synth.synthetic_temporal_state(64, 96, B=2)
+        K8 = st["K"].clone(); K8[:, :2] /= 8.0
+        T = torch.bmm(st["T_now"], st["inv_T_prev"])
+        depth = 0.54 * K8[:, 0, 0].view(-1, 1, 1, 1) / (st["cost_memory"]["disp_sample"] + 1e-5)
+        o = ref_project(depth, K8, torch.inverse(K8), T)
+        save("project_to_3d.npz", flow=o["optical_flow"].numpy(), tri=o["triangular_depth"].numpy())
+
+        # ---- a15: whole aggregation, single frame ----
+        sd = synth.synthetic_state_dict(seed=0)
+        agg = ref_import.build_reference_aggregation()
+        agg.load_state_dict(sd, strict=True)
+        H, W = 96, 160
+        lf, rf, li, ri = synth.synthetic_frame(H, W, B=1, seed=1)
+        disps, costs, samples, offs, ranges, info = agg(lf, rf, li, ri, prev_info={})
+        arrs = {}
+        for i, t in enumerate(disps): arrs[f"disp{i}"] = t.numpy()
+        for i, t in enumerate(costs): arrs[f"cost{i}"] = t.numpy()
+        for i, t in enumerate(samples): arrs[f"sample{i}"] = t.numpy()
+        for i, t in enumerate(offs): arrs[f"off{i}"] = t.numpy()
+        arrs["mem_sample"] = info["cost_memory"]["disp_sample"].numpy()
+        arrs["mem_cost"] = info["cost_memory"]["cost_volume"].numpy()
+        save("agg_single_96x160.npz", **arrs)
+
+        # ---- a17 + a15: temporal (update_map through the reference with the CPU splat
+        #      restatement, then aggregation with memory + local map) ----
+        tm = ref_import.build_reference_temporal(O.softsplat_softmax)
+        st = synth.synthetic_temporal_state(H, W, B=1)
+        prev = dict(prev_disp=st["prev_disp"], cost_memory=st["cost_memory"], local_map=st["local_map"])
+        batch = {"baseline": st["baseline"], ("color_aug", 0, "l"): li, ("K", 0): st["K"],
+                 ("inv_T", -1, "l"): st["inv_T_prev"], ("T", 0, "l"): st["T_now"]}
+        _, prev = tm.update_map(batch, prev, 0)
+        save("update_map_96x160.npz", mem_sample=prev["cost_memory"]["disp_sample"].numpy(),
+             mem_cost=prev["cost_memory"]["cost_volume"].numpy(), local_map=prev["local_map"].numpy())
+        disps, costs, samples, offs, ranges, info = agg(lf, rf, li, ri, prev_info=prev)
+        arrs = {}
+        for i, t in enumerate(disps): arrs[f"disp{i}"] = t.numpy()
+        for i, t in enumerate(costs): arrs[f"cost{i}"] = t.numpy()
+        for i, t in enumerate(samples): arrs[f"sample{i}"] = t.numpy()
+        for i, t in enumerate(offs): arrs[f"off{i}"] = t.numpy()
+        save("agg_temporal_96x160.npz", **arrs)
+
+
+if __name__ == "__main__":
+    main()
