@@ -1,0 +1,177 @@
+/*
+ * tstereo.h — C ABI of libtstereo.so, the B200 (sm_100a) cost-volume stereo engine.
+ *
+ * Drop-in boundary for the per-frame hot path of youmi-zym/TemporalStereo.
+ * Every entry point takes plain device pointers + sizes + a cudaStream_t (as void*),
+ * launches asynchronously on that stream and returns 0 or a negative TSTEREO_E_* code;
+ * tstereo_last_error() returns the message of the calling thread's last failure.
+ * No torch types cross this boundary.  All tensors are fp32, contiguous NCHW / NCDHW
+ * unless an entry point takes explicit element strides.
+ *
+ * "ref:" lines cite the reference interface each symbol replaces (paths relative to
+ * the reference repository root).
+ */
+#ifndef TSTEREO_H_
+#define TSTEREO_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSTEREO_VERSION 100            /* 0.1.0 */
+
+#define TSTEREO_OK            0
+#define TSTEREO_E_ARG        -1        /* bad size / null pointer / unsupported variant */
+#define TSTEREO_E_CUDA       -2        /* CUDA runtime error at launch                  */
+
+#define TSTEREO_ACT_NONE 0
+#define TSTEREO_ACT_SILU 1
+#define TSTEREO_ACT_RELU 2
+
+int         tstereo_version(void);
+const char* tstereo_last_error(void);
+
+/* ---------------------------------------------------------------- cost volume (a1-a3)
+ * ref: architecture/modeling/aggregation/utils/block_cost.py:16-83 (block_cost),
+ *      :6-13 (groupwise_correlation), architecture/modeling/layers/inverse_warp_3d.py:4-58.
+ * left/right [B,C,H,W]; C % 8 == 0; H,W >= 4; three pooled scales (block_cost_scale = 3).
+ * scratch: >= tstereo_block_cost_scratch_floats(B,C,H,W,D) floats.
+ */
+long long tstereo_block_cost_scratch_floats(int B, int C, int H, int W, int D);
+
+/* int branch (block_cost.py:34-45): out [B, C + 3C/8, D, H, W] =
+ *   [ -(L - R_d)^2 , g0, g1, g2 ],  R_d[x] = R[x-d] (0 for x<d), d = 0..D-1 */
+int tstereo_block_cost_shift(const float* left, const float* right, float* out, float* scratch,
+                             int B, int C, int H, int W, int D, void* stream);
+
+/* tensor branch (block_cost.py:47-58): samples [B,S,H,W];
+ * out [B, 2C + 3C/8, S, H, W] = [ L broadcast, R warped to x - sample, g0, g1, g2 ] */
+int tstereo_block_cost_warp(const float* left, const float* right, const float* samples, float* out,
+                            float* scratch, int B, int C, int H, int W, int S, void* stream);
+
+/* ---------------------------------------------------------------- convolutions (a4-a7, a9, a12, a13)
+ * ref: architecture/modeling/layers/basic_layers.py:194-235 (Conv3d), :340-388 (ConvTranspose3d),
+ *      architecture/modeling/aggregation/TemporalStereo/module.py:111-184 (separable pairs).
+ * Activations are 5-D views [B, C, D, H, W] with element strides (sB, sC, sD) and a contiguous
+ * H*W plane (2-D convs use D = 1).  Weights are pre-packed by the host with eval-mode BatchNorm
+ * folded in: w[Cin][taps][CoutP] (CoutP = Cout rounded up to 4), bias[Cout] (may be NULL).
+ */
+
+/* (1,3,3) / 3x3 convolution over (H,W): stride 1|2, dilation 1|2, padding = dilation. */
+int tstereo_conv_hw3(const float* in, long long isB, long long isC, long long isD,
+                     float* out, long long osB, long long osC, long long osD,
+                     const float* w, const float* bias,
+                     int B, int Cin, int Cout, int D, int Hin, int Win, int Hout, int Wout,
+                     int stride, int dilation, int act, void* stream);
+
+/* (k,1,1) convolution along D: k = 3|5, stride 1|2, dilation 1|2, padding = dilation*(k/2).
+ * transposed != 0: ConvTranspose (3,1,1) stride 2, padding 1, output_padding 1 (Dout = 2*Din). */
+int tstereo_conv_d(const float* in, long long isB, long long isC, long long isD,
+                   float* out, long long osB, long long osC, long long osD,
+                   const float* w, const float* bias,
+                   int B, int Cin, int Cout, int Din, int Dout, int HW,
+                   int k, int stride, int dilation, int transposed, int act, void* stream);
+
+/* Transposed (1,k,k) / kxk convolution over (H,W), stride 2, padding 1:
+ * k = 3 with output_padding 1 (module.py:149-184) or k = 4 (module.py:452-457); Hout = 2*Hin. */
+int tstereo_deconv_hw(const float* in, long long isB, long long isC, long long isD,
+                      float* out, long long osB, long long osC, long long osD,
+                      const float* w, const float* bias,
+                      int B, int Cin, int Cout, int D, int Hin, int Win,
+                      int k, int act, void* stream);
+
+/* out = act( trilinear_align_corners(a -> (D,H,W)) + skip )   (module.py:285-295)
+ * a [B,C,Da,Ha,Wa], skip/out [B,C,D,H,W] contiguous; skip may be NULL. */
+int tstereo_resize_add_act(const float* a, const float* skip, float* out,
+                           int B, int C, int Da, int Ha, int Wa, int D, int H, int W,
+                           int act, void* stream);
+
+/* avg_pool3d and max_pool3d, kernel 5, stride 1, padding 2 (module.py:416-417).
+ * x [B,C,D,H,W] view with strides; results written to two channel slices (strided views). D <= 24. */
+int tstereo_pool5(const float* x, long long xsB, long long xsC,
+                  float* avg, float* mx, long long osB, long long osC,
+                  int B, int C, int D, int H, int W, void* stream);
+
+/* ---------------------------------------------------------------- memory merge (a8)
+ * ref: coarse.py:84-105, fine.py:104-122.  vol [B,C,D,H,W], samples [B,D,H,W],
+ * mem_sample / mem_cost [B,M,H,W] (NULL = zeros), past_conv folded to w[C], b[C] (+SiLU).
+ * Stable sort of the D+M candidates per pixel; out_vol [B,C,D+M,H,W] (strided view:
+ * osB, osC; plane stride H*W), out_samples [B,D+M,H,W].  D+M <= 32. */
+int tstereo_merge_memory(const float* vol, const float* samples,
+                         const float* mem_sample, const float* mem_cost,
+                         const float* past_w, const float* past_b,
+                         float* out_vol, long long osB, long long osC, float* out_samples,
+                         int B, int C, int D, int M, int H, int W, void* stream);
+
+/* ---------------------------------------------------------------- heads + regression (a10, a11, a14)
+ * ref: module.py:356-398 (PredictionHeads), coarse.py:69-75 (predict_disp), fine.py:78-86.
+ * feat [B,2C,D,H,W]: channels [0,C) = cost-head features, [C,2C) = offset-head features
+ * (both after the (3,1,1) conv + BN + SiLU).  w [2][C][9].
+ * cost, off [B,D,H,W]; off = clamp(tanh(x/100),-1,1)*delta. */
+int tstereo_heads(const float* feat, const float* w, float* cost, float* off,
+                  int B, int C, int D, int H, int W, float delta, void* stream);
+
+/* top-2 over D -> softmax -> gather(sample+off) -> sum.  disp [B,1,H,W];
+ * top_disp / top_cost [B,2,H,W] may be NULL.  Ties: lowest index first. */
+int tstereo_predict_disp(const float* cost, const float* samples, const float* off,
+                         float* disp, float* top_disp, float* top_cost,
+                         int B, int D, int H, int W, void* stream);
+
+/* low = disp - r, high = disp + r, samples[:, c_off + k] = |high-low|*{0,3,4,5,8}/8 + min(low,high)
+ * samples is [B, S_total, H, W]; low/high [B,1,H,W]. */
+int tstereo_range_samples(const float* disp, float radius, float* low, float* high,
+                          float* samples, int S_total, int c_off,
+                          int B, int H, int W, void* stream);
+
+/* ---------------------------------------------------------------- up-sampling (a12, a13, a16, a20)
+ * ConvexUpsample tail (module.py:318-353): m [B,64,H,W] (mask.0+BN+SiLU output),
+ * w [36][64], b [36], disp [B,1,H,W] -> out [B,1,2H,2W]. */
+int tstereo_convex_upsample(const float* m, const float* w, const float* b, const float* disp,
+                            float* out, int B, int H, int W, void* stream);
+
+/* UNet.upsample (module.py:468-483): logits [B,9,H,W], disp [B,1,h,w] -> full [B,1,H,W]. */
+int tstereo_unet_upsample(const float* logits, const float* disp, float* full,
+                          int B, int H, int W, int h, int w, void* stream);
+
+/* Bilinear align_corners resize of (in * mul / div): in [B,C,Hi,Wi] ->
+ * out[:, c_off : c_off+C] of a [B, C_total, Ho, Wo] tensor.
+ * (coarse.py:92-95, fine.py:91, precise.py:100-103, projects/TemporalStereo/TemporalStereo.py:305-309) */
+int tstereo_bilinear_resize(const float* in, float* out, float mul, float div,
+                            int B, int C, int Hi, int Wi, int Ho, int Wo,
+                            int C_total, int c_off, void* stream);
+
+/* ---------------------------------------------------------------- temporal warp (a17-a19)
+ * ref: projects/TemporalStereo/TemporalStereo.py:326-461 (update_map),
+ *      architecture/modeling/layers/inverse_warp.py:92-178 (project_to_3d),
+ *      architecture/modeling/layers/softsplat.py:8-53, 334-360 (softmax splatting).
+ *
+ * pose_prep: per batch item, T = T_now @ inv_T_prev, down_K = K with rows 0,1 / factor,
+ * inv(down_K), P = (down_K @ T)[:3,:].  params [B,24] = invK(9) | P(12) | focal | baseline | pad. */
+int tstereo_pose_prep(const float* K, const float* T_now, const float* inv_T_prev,
+                      const float* baseline, float factor, float* params, int B, void* stream);
+
+/* disparity -> depth -> 3-D -> new camera -> (flow of channel 0, new disparity of every channel).
+ * disp [B,C,h,w]; flow [B,2,h,w] (may be NULL); new_disp [B,C_total,h,w] at c_off (may be NULL). */
+int tstereo_reproject_disp(const float* disp, const float* params, float* flow, float* new_disp,
+                           int C_total, int c_off, int B, int C, int h, int w, void* stream);
+
+/* project_to_3d drop-in (inverse_warp.py:92-178): depth [B,C,h,w] -> optical_flow [B,2C,h,w]
+ * (x,y pairs per channel; may be NULL) and triangular_depth [B,C,h,w] (may be NULL).
+ * params from tstereo_pose_prep (factor 1, inv_T_prev = identity reproduces K @ T). */
+int tstereo_project_to_3d(const float* depth, const float* params, float* flow, float* tri,
+                          int B, int C, int h, int w, void* stream);
+
+/* metric = clamp(pd[:, :1] - mean(pd[:, :1]), -50, 50) over the whole local batch.
+ * pd [B,C,h,w]; metric [B,1,h,w]; scratch >= 1024 floats. */
+int tstereo_splat_metric(const float* pd, float* metric, float* scratch,
+                         int B, int C, int h, int w, void* stream);
+
+/* FunctionSoftsplat(x, flow, metric, 'softmax'): x [B,C,h,w], flow [B,2,h,w], metric [B,1,h,w],
+ * acc scratch [B,C+1,h,w] (zeroed by the call), out [B,C,h,w]. */
+int tstereo_softsplat(const float* x, const float* flow, const float* metric, float* acc,
+                      float* out, int B, int C, int h, int w, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* TSTEREO_H_ */

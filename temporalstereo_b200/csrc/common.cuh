@@ -1,0 +1,76 @@
+// Shared helpers for libtstereo.so kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdarg>
+#include "../../include/tstereo.h"
+
+namespace tstereo {
+
+void set_error(const char* fmt, ...);
+
+inline int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return TSTEREO_E_CUDA;
+    }
+    return TSTEREO_OK;
+}
+
+#define TS_REQUIRE(cond, ...)                 \
+    do {                                      \
+        if (!(cond)) {                        \
+            tstereo::set_error(__VA_ARGS__);  \
+            return TSTEREO_E_ARG;             \
+        }                                     \
+    } while (0)
+
+__host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ inline long long cdivll(long long a, long long b) { return (a + b - 1) / b; }
+
+// x * sigmoid(x); full-precision expf so the result tracks the fp32 reference to ~1 ulp.
+__device__ __forceinline__ float silu_f(float x) { return __fdiv_rn(x, 1.0f + expf(-x)); }
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+    if (act == TSTEREO_ACT_SILU) return silu_f(x);
+    if (act == TSTEREO_ACT_RELU) return fmaxf(x, 0.0f);
+    return x;
+}
+
+// 4-byte cp.async with zero fill when !valid (src must still be a legal address).
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc, bool valid) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    int sz = valid ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(s), "l"(gsrc), "r"(sz));
+}
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// ATen's align_corners source index: scale = (in-1)/(out-1) in float, src = scale*dst
+// (aten/src/ATen/native/UpSample.h area_pixel_compute_scale / guard_index_and_lambda).
+struct LerpIdx {
+    int i0, i1;
+    float w0, w1;
+};
+__device__ __forceinline__ float ac_scale(int in_size, int out_size) {
+    return out_size > 1 ? __fdiv_rn((float)(in_size - 1), (float)(out_size - 1)) : 0.0f;
+}
+__device__ __forceinline__ LerpIdx ac_index(float scale, int dst, int in_size) {
+    float src = __fmul_rn(scale, (float)dst);
+    int i0 = min((int)floorf(src), in_size - 1);
+    float l = fminf(fmaxf(src - (float)i0, 0.0f), 1.0f);
+    LerpIdx r;
+    r.i0 = i0;
+    r.i1 = min(i0 + 1, in_size - 1);
+    r.w1 = l;
+    r.w0 = 1.0f - l;
+    return r;
+}
+
+}  // namespace tstereo

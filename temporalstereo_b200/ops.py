@@ -1,0 +1,297 @@
+"""Tensor-level wrappers of the C ABI (include/tstereo.h).
+
+Each function checks device / dtype / contiguity, allocates the outputs, and launches the kernel on
+torch's *current* CUDA stream.  PyTorch is only the allocator and stream provider here; all
+arithmetic happens inside libtstereo.so.  Names and argument meaning follow the reference operators
+they replace (cited per function, paths relative to the reference repository).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+ACT = {None: 0, "none": 0, "SiLU": 1, "silu": 1, "ReLU": 2, "relu": 2}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(*ts: Optional[torch.Tensor]) -> None:
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise TypeError("libtstereo ops need CUDA tensors (there is no CPU fallback)")
+        if t.dtype != torch.float32:
+            raise TypeError(f"libtstereo ops are fp32-only, got {t.dtype}")
+        if not t.is_contiguous():
+            raise ValueError("libtstereo ops need contiguous tensors")
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _view5(t: torch.Tensor) -> Tuple[int, int, int]:
+    """(sB, sC, sD) element strides of a [B,C,D,H,W] (or [B,C,H,W]) view whose (H,W) plane is dense."""
+    if t.dtype != torch.float32 or not t.is_cuda:
+        raise TypeError("libtstereo ops need fp32 CUDA tensors")
+    if t.dim() == 4:
+        B, Cc, H, W = t.shape
+        sB, sC, sH, sW = t.stride()
+        sD = 0
+    else:
+        B, Cc, D, H, W = t.shape
+        sB, sC, sD, sH, sW = t.stride()
+    if W > 1 and sW != 1 or H > 1 and sH != W:
+        raise ValueError("the (H, W) plane of a libtstereo activation view must be dense")
+    return sB, sC, sD
+
+
+# --------------------------------------------------------------------------- cost volume
+def block_cost(left: torch.Tensor, right: torch.Tensor, disp_sample, block_cost_scale: int = 3) -> torch.Tensor:
+    """Drop-in for `block_cost(left, right, disp_sample, block_cost_scale)`
+    (architecture/modeling/aggregation/utils/block_cost.py:16-83): int `disp_sample` -> shifted
+    difference volume, tensor `disp_sample` [B,S,H,W] -> [L, warp(R)] concat volume; both followed by
+    the three pooled group-wise terms."""
+    _chk(left, right)
+    if block_cost_scale != 3:
+        raise ValueError("libtstereo block_cost implements block_cost_scale = 3 (every shipped config)")
+    B, Cc, H, W = left.shape
+    assert right.shape == left.shape, "left / right feature shapes differ"
+    G = Cc // 8
+    if isinstance(disp_sample, int):
+        D = disp_sample
+        out = torch.empty((B, Cc + 3 * G, D, H, W), device=left.device, dtype=torch.float32)
+        n = _lib.load().tstereo_block_cost_scratch_floats(B, Cc, H, W, D)
+        scratch = torch.empty((max(int(n), 1),), device=left.device, dtype=torch.float32)
+        _lib.call("tstereo_block_cost_shift", _p(left), _p(right), _p(out), _p(scratch), B, Cc, H, W, D, _stream())
+    else:
+        _chk(disp_sample)
+        S = disp_sample.shape[1]
+        assert disp_sample.shape == (B, S, H, W)
+        out = torch.empty((B, 2 * Cc + 3 * G, S, H, W), device=left.device, dtype=torch.float32)
+        n = _lib.load().tstereo_block_cost_scratch_floats(B, Cc, H, W, S)
+        scratch = torch.empty((max(int(n), 1),), device=left.device, dtype=torch.float32)
+        _lib.call("tstereo_block_cost_warp", _p(left), _p(right), _p(disp_sample), _p(out), _p(scratch),
+                  B, Cc, H, W, S, _stream())
+    return out
+
+
+# --------------------------------------------------------------------------- convolutions
+def conv_hw3(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], cout: int, stride: int = 1,
+             dilation: int = 1, act=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(1,3,3) / 3x3 conv, padding = dilation, packed weights w[Cin][9][CoutP]
+    (layers/basic_layers.py:194-235 with eval-mode BN folded)."""
+    five = x.dim() == 5
+    B, Cin = x.shape[:2]
+    D = x.shape[2] if five else 1
+    Hin, Win = x.shape[-2:]
+    Hout, Wout = (Hin - 1) // stride + 1, (Win - 1) // stride + 1
+    if out is None:
+        shape = (B, cout, D, Hout, Wout) if five else (B, cout, Hout, Wout)
+        out = torch.empty(shape, device=x.device, dtype=torch.float32)
+    isB, isC, isD = _view5(x)
+    osB, osC, osD = _view5(out)
+    _chk(w, bias)
+    _lib.call("tstereo_conv_hw3", _p(x), isB, isC, isD, _p(out), osB, osC, osD, _p(w), _p(bias),
+              B, Cin, cout, D, Hin, Win, Hout, Wout, stride, dilation, ACT[act], _stream())
+    return out
+
+
+def conv_d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], cout: int, k: int = 3, stride: int = 1,
+           dilation: int = 1, transposed: bool = False, act=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(k,1,1) conv along D (or its stride-2 transposed form), packed weights w[Cin][k][CoutP]."""
+    B, Cin, Din, H, W = x.shape
+    Dout = 2 * Din if transposed else (Din - 1) // stride + 1
+    if out is None:
+        out = torch.empty((B, cout, Dout, H, W), device=x.device, dtype=torch.float32)
+    isB, isC, isD = _view5(x)
+    osB, osC, osD = _view5(out)
+    _chk(w, bias)
+    _lib.call("tstereo_conv_d", _p(x), isB, isC, isD, _p(out), osB, osC, osD, _p(w), _p(bias),
+              B, Cin, cout, Din, Dout, H * W, k, stride, dilation, int(transposed), ACT[act], _stream())
+    return out
+
+
+def deconv_hw(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], cout: int, k: int = 3, act=None,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Transposed (1,k,k)/kxk conv, stride 2, padding 1 (k=3: output_padding 1), w[Cin][k*k][CoutP]."""
+    five = x.dim() == 5
+    B, Cin = x.shape[:2]
+    D = x.shape[2] if five else 1
+    Hin, Win = x.shape[-2:]
+    if out is None:
+        shape = (B, cout, D, 2 * Hin, 2 * Win) if five else (B, cout, 2 * Hin, 2 * Win)
+        out = torch.empty(shape, device=x.device, dtype=torch.float32)
+    isB, isC, isD = _view5(x)
+    osB, osC, osD = _view5(out)
+    _chk(w, bias)
+    _lib.call("tstereo_deconv_hw", _p(x), isB, isC, isD, _p(out), osB, osC, osD, _p(w), _p(bias),
+              B, Cin, cout, D, Hin, Win, k, ACT[act], _stream())
+    return out
+
+
+def resize_add_act(a: torch.Tensor, size, skip: Optional[torch.Tensor] = None, act=None) -> torch.Tensor:
+    """act(F.interpolate(a, size, 'trilinear', align_corners=True) + skip) (module.py:285-295)."""
+    _chk(a, skip)
+    B, Cc, Da, Ha, Wa = a.shape
+    D, H, W = size
+    out = torch.empty((B, Cc, D, H, W), device=a.device, dtype=torch.float32)
+    if skip is not None:
+        assert tuple(skip.shape) == tuple(out.shape)
+    _lib.call("tstereo_resize_add_act", _p(a), _p(skip), _p(out), B, Cc, Da, Ha, Wa, D, H, W, ACT[act], _stream())
+    return out
+
+
+def pool5(x: torch.Tensor, avg: torch.Tensor, mx: torch.Tensor) -> None:
+    """avg_pool3d / max_pool3d, kernel 5, stride 1, padding 2, written into two views (module.py:416-417)."""
+    B, Cc, D, H, W = x.shape
+    xsB, xsC, xsD = _view5(x)
+    osB, osC, osD = _view5(avg)
+    assert (xsD == H * W or D == 1) and (osD == H * W or D == 1) and _view5(mx) == (osB, osC, osD)
+    _lib.call("tstereo_pool5", _p(x), xsB, xsC, _p(avg), _p(mx), osB, osC, B, Cc, D, H, W, _stream())
+
+
+def merge_memory(vol: torch.Tensor, samples: torch.Tensor, mem_sample: Optional[torch.Tensor],
+                 mem_cost: Optional[torch.Tensor], past_w: torch.Tensor, past_b: torch.Tensor, M: int = 2,
+                 out_vol: Optional[torch.Tensor] = None):
+    """Temporal memory merge (coarse.py:84-105, fine.py:104-122): returns (volume [B,C,D+M,H,W], samples)."""
+    _chk(vol, samples, mem_sample, mem_cost, past_w, past_b)
+    B, Cc, D, H, W = vol.shape
+    if out_vol is None:
+        out_vol = torch.empty((B, Cc, D + M, H, W), device=vol.device, dtype=torch.float32)
+    osB, osC, osD = _view5(out_vol)
+    assert osD == H * W
+    out_s = torch.empty((B, D + M, H, W), device=vol.device, dtype=torch.float32)
+    _lib.call("tstereo_merge_memory", _p(vol), _p(samples), _p(mem_sample), _p(mem_cost), _p(past_w), _p(past_b),
+              _p(out_vol), osB, osC, _p(out_s), B, Cc, D, M, H, W, _stream())
+    return out_vol, out_s
+
+
+def heads(feat: torch.Tensor, w: torch.Tensor, delta: float):
+    """Final (1,3,3) C->1 convs of both prediction heads + tanh offset squashing (module.py:380-398)."""
+    _chk(feat, w)
+    B, C2, D, H, W = feat.shape
+    cost = torch.empty((B, D, H, W), device=feat.device, dtype=torch.float32)
+    off = torch.empty_like(cost)
+    _lib.call("tstereo_heads", _p(feat), _p(w), _p(cost), _p(off), B, C2 // 2, D, H, W, float(delta), _stream())
+    return cost, off
+
+
+def predict_disp(cost: torch.Tensor, samples: torch.Tensor, off: torch.Tensor, want_top: bool = False):
+    """top-2 soft-argmin (coarse.py:69-75): disp [B,1,H,W] (+ top-2 disparities / costs)."""
+    _chk(cost, samples, off)
+    B, D, H, W = cost.shape
+    disp = torch.empty((B, 1, H, W), device=cost.device, dtype=torch.float32)
+    td = tc = None
+    if want_top:
+        td = torch.empty((B, 2, H, W), device=cost.device, dtype=torch.float32)
+        tc = torch.empty_like(td)
+    _lib.call("tstereo_predict_disp", _p(cost), _p(samples), _p(off), _p(disp), _p(td), _p(tc), B, D, H, W, _stream())
+    return disp, td, tc
+
+
+def range_samples(disp: torch.Tensor, radius: float, samples: torch.Tensor, c_off: int = 0):
+    """low/high = disp -/+ radius and the 5 range candidates written at channel c_off of `samples`
+    (aggregation/TemporalStereo/TemporalStereo.py:103-110, fine.py:78-86)."""
+    _chk(disp, samples)
+    B, _, H, W = disp.shape
+    low = torch.empty_like(disp)
+    high = torch.empty_like(disp)
+    _lib.call("tstereo_range_samples", _p(disp), float(radius), _p(low), _p(high), _p(samples), samples.shape[1],
+              c_off, B, H, W, _stream())
+    return low, high
+
+
+def convex_upsample(m: torch.Tensor, w: torch.Tensor, b: torch.Tensor, disp: torch.Tensor) -> torch.Tensor:
+    """ConvexUpsample tail (module.py:318-353) given the 64-channel mask features."""
+    _chk(m, w, b, disp)
+    B, _, H, W = disp.shape
+    assert m.shape == (B, 64, H, W)
+    out = torch.empty((B, 1, 2 * H, 2 * W), device=disp.device, dtype=torch.float32)
+    _lib.call("tstereo_convex_upsample", _p(m), _p(w), _p(b), _p(disp), _p(out), B, H, W, _stream())
+    return out
+
+
+def unet_upsample(logits: torch.Tensor, disp: torch.Tensor) -> torch.Tensor:
+    """UNet.upsample (module.py:468-483)."""
+    _chk(logits, disp)
+    B, nine, H, W = logits.shape
+    assert nine == 9
+    h, w = disp.shape[-2:]
+    out = torch.empty((B, 1, H, W), device=disp.device, dtype=torch.float32)
+    _lib.call("tstereo_unet_upsample", _p(logits), _p(disp), _p(out), B, H, W, h, w, _stream())
+    return out
+
+
+def bilinear_resize(x: torch.Tensor, size, mul: float = 1.0, div: float = 1.0, out: Optional[torch.Tensor] = None,
+                    c_off: int = 0) -> torch.Tensor:
+    """F.interpolate(x * mul / div, size, 'bilinear', align_corners=True), optionally into a channel slice."""
+    _chk(x, out)
+    B, Cc, Hi, Wi = x.shape
+    Ho, Wo = size
+    if out is None:
+        out = torch.empty((B, Cc, Ho, Wo), device=x.device, dtype=torch.float32)
+    _lib.call("tstereo_bilinear_resize", _p(x), _p(out), float(mul), float(div), B, Cc, Hi, Wi, Ho, Wo,
+              out.shape[1], c_off, _stream())
+    return out
+
+
+# --------------------------------------------------------------------------- temporal warp
+def pose_prep(K: torch.Tensor, T_now: torch.Tensor, inv_T_prev: torch.Tensor, baseline: torch.Tensor,
+              factor: float) -> torch.Tensor:
+    _chk(K, T_now, inv_T_prev, baseline)
+    B = K.shape[0]
+    assert K.shape == (B, 4, 4) and T_now.shape == (B, 4, 4) and inv_T_prev.shape == (B, 4, 4)
+    assert baseline.numel() == B
+    params = torch.empty((B, 24), device=K.device, dtype=torch.float32)
+    _lib.call("tstereo_pose_prep", _p(K), _p(T_now), _p(inv_T_prev), _p(baseline), float(factor), _p(params), B,
+              _stream())
+    return params
+
+
+def reproject_disp(disp: torch.Tensor, params: torch.Tensor, want_flow: bool = True, want_disp: bool = True,
+                   out: Optional[torch.Tensor] = None, c_off: int = 0):
+    _chk(disp, params, out)
+    B, Cc, h, w = disp.shape
+    flow = torch.empty((B, 2, h, w), device=disp.device, dtype=torch.float32) if want_flow else None
+    if want_disp and out is None:
+        out = torch.empty((B, Cc, h, w), device=disp.device, dtype=torch.float32)
+    ct = out.shape[1] if out is not None else Cc
+    _lib.call("tstereo_reproject_disp", _p(disp), _p(params), _p(flow), _p(out if want_disp else None), ct, c_off,
+              B, Cc, h, w, _stream())
+    return flow, out
+
+
+def project_depth(depth: torch.Tensor, params: torch.Tensor):
+    """Kernel behind the `project_to_3d` drop-in: (optical_flow [B,2C,h,w], triangular_depth [B,C,h,w])."""
+    _chk(depth, params)
+    B, Cc, h, w = depth.shape
+    flow = torch.empty((B, 2 * Cc, h, w), device=depth.device, dtype=torch.float32)
+    tri = torch.empty_like(depth)
+    _lib.call("tstereo_project_to_3d", _p(depth), _p(params), _p(flow), _p(tri), B, Cc, h, w, _stream())
+    return flow, tri
+
+
+def splat_metric(pd: torch.Tensor) -> torch.Tensor:
+    _chk(pd)
+    B, Cc, h, w = pd.shape
+    metric = torch.empty((B, 1, h, w), device=pd.device, dtype=torch.float32)
+    scratch = torch.empty((1024,), device=pd.device, dtype=torch.float32)
+    _lib.call("tstereo_splat_metric", _p(pd), _p(metric), _p(scratch), B, Cc, h, w, _stream())
+    return metric
+
+
+def softsplat(x: torch.Tensor, flow: torch.Tensor, metric: torch.Tensor) -> torch.Tensor:
+    _chk(x, flow, metric)
+    B, Cc, h, w = x.shape
+    assert flow.shape == (B, 2, h, w) and metric.shape == (B, 1, h, w)
+    acc = torch.empty((B, Cc + 1, h, w), device=x.device, dtype=torch.float32)
+    out = torch.empty_like(x)
+    _lib.call("tstereo_softsplat", _p(x), _p(flow), _p(metric), _p(acc), _p(out), B, Cc, h, w, _stream())
+    return out
