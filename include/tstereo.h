@@ -30,6 +30,8 @@ extern "C" {
 
 int         tstereo_version(void);
 const char* tstereo_last_error(void);
+/* number of kernels this library has launched in the process so far (bench.py's gpu_launches) */
+long long   tstereo_launch_count(void);
 
 /* ---------------------------------------------------------------- cost volume (a1-a3)
  * ref: architecture/modeling/aggregation/utils/block_cost.py:16-83 (block_cost),

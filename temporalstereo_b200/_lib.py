@@ -18,6 +18,7 @@ P, I, F, LL = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 SIGNATURES = {
     "tstereo_version": (I, []),
     "tstereo_last_error": (C.c_char_p, []),
+    "tstereo_launch_count": (LL, []),
     "tstereo_block_cost_scratch_floats": (LL, [I, I, I, I, I]),
     "tstereo_block_cost_shift": (I, [P, P, P, P, I, I, I, I, I, P]),
     "tstereo_block_cost_warp": (I, [P, P, P, P, P, I, I, I, I, I, P]),

@@ -8,8 +8,10 @@
 namespace tstereo {
 
 void set_error(const char* fmt, ...);
+void count_launch();
 
 inline int check_launch(const char* what) {
+    count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("%s: %s", what, cudaGetErrorString(e));

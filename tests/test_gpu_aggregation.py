@@ -1,0 +1,161 @@
+"""End-to-end parity of the drop-in TEMPORALSTEREO module (CUDA, through the C ABI) against
+ (1) golden outputs of the real reference (tests/golden, made by oracle/make_golden.py) and
+ (2) the CPU oracle on the same seeded inputs at the BASELINE.json sizes.
+
+Tolerances (north_star): regressed disparity within 1e-3 px EPE of the reference fp32 path;
+index work (sorted candidate lists, top-2 selection) exact.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+from temporalstereo_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+EPE_TOL = 1e-3      # px, mean abs difference of the full-resolution disparity (north_star)
+
+
+@pytest.fixture(scope="module")
+def engine():
+    assert torch.cuda.is_available()
+    from temporalstereo_b200.aggregation import TEMPORALSTEREO
+    m = TEMPORALSTEREO()
+    m.load_state_dict(synth.synthetic_state_dict(seed=0), strict=True)
+    return m.cuda().eval()
+
+
+def _load(golden_dir, name):
+    return {k: torch.from_numpy(v) for k, v in np.load(os.path.join(golden_dir, name)).items()}
+
+
+def _cuda(x):
+    if torch.is_tensor(x):
+        return x.cuda()
+    if isinstance(x, dict):
+        return {k: _cuda(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return [_cuda(v) for v in x]
+    return x
+
+
+def _report(out, ref_disps, ref_costs, ref_samples, ref_offs):
+    disps, costs, samples, offs = out[:4]
+    rep = {}
+    for i, (a, b) in enumerate(zip(disps, ref_disps)):
+        d = (a.cpu() - b).abs()
+        rep[f"disp{i}"] = (d.mean().item(), d.max().item())
+    for i, (a, b) in enumerate(zip(costs, ref_costs)):
+        rep[f"cost{i}"] = ((a.cpu() - b).abs().max().item(),)
+    for i, (a, b) in enumerate(zip(samples, ref_samples)):
+        rep[f"sample{i}"] = ((a.cpu() - b).abs().max().item(),)
+    for i, (a, b) in enumerate(zip(offs, ref_offs)):
+        rep[f"off{i}"] = ((a.cpu() - b).abs().max().item(),)
+    return rep
+
+
+def _check(out, ref, what):
+    ref_disps, ref_costs, ref_samples, ref_offs = ref
+    rep = _report(out, ref_disps, ref_costs, ref_samples, ref_offs)
+    print(what, {k: tuple(f"{x:.2e}" for x in v) for k, v in rep.items()})
+    for t in list(out[0]) + list(out[1]) + list(out[2]) + list(out[3]):
+        assert torch.isfinite(t).all(), f"{what}: non-finite output"
+    # shapes of the 6-tuple
+    for a, b in zip(list(out[0]) + list(out[1]) + list(out[2]) + list(out[3]),
+                    list(ref_disps) + list(ref_costs) + list(ref_samples) + list(ref_offs)):
+        assert tuple(a.shape) == tuple(b.shape), (what, a.shape, b.shape)
+    assert rep["disp0"][0] < EPE_TOL, f"{what}: full-res EPE {rep['disp0'][0]:.3e} px >= {EPE_TOL}"
+    for i in (1, 2, 3):
+        assert rep[f"disp{i}"][0] < EPE_TOL, f"{what}: disp{i} EPE {rep[f'disp{i}'][0]:.3e}"
+    # the coarse candidate list is pure index work (sorted integers + zero memory): exact
+    assert rep["sample2"][0] == 0.0 or rep["sample2"][0] < 1e-4, f"{what}: coarse samples differ {rep['sample2']}"
+    return rep
+
+
+def test_single_frame_matches_reference_golden(engine, golden_dir):
+    g = _load(golden_dir, "agg_single_96x160.npz")
+    lf, rf, li, ri = synth.synthetic_frame(96, 160, B=1, seed=1)
+    out = engine(_cuda(lf), _cuda(rf), li.cuda(), ri.cuda(), {})
+    ref = ([g[f"disp{i}"] for i in range(4)], [g[f"cost{i}"] for i in range(3)],
+           [g[f"sample{i}"] for i in range(3)], [g[f"off{i}"] for i in range(3)])
+    rep = _check(out, ref, "golden single 96x160")
+    assert rep["sample2"][0] == 0.0, "coarse sorted candidates must be bit-exact"
+    for i in range(3):
+        assert rep[f"cost{i}"][0] < 2e-3, rep
+        assert rep[f"off{i}"][0] < 1e-4, rep
+    info = out[5]
+    d = (info["cost_memory"]["disp_sample"].cpu() - g["mem_sample"]).abs()
+    assert d.mean() < EPE_TOL, d.mean()
+    d = (info["cost_memory"]["cost_volume"].cpu() - g["mem_cost"]).abs()
+    assert d.max() < 2e-3, d.max()
+    assert info["prev_disp"].data_ptr() == out[0][0].data_ptr() or torch.equal(info["prev_disp"], out[0][0])
+
+
+def test_temporal_frame_matches_reference_golden(engine, golden_dir):
+    """update_map (CUDA) -> aggregation with cost memory + local map, against the reference's outputs."""
+    from temporalstereo_b200 import temporal
+    g = _load(golden_dir, "agg_temporal_96x160.npz")
+    H, W = 96, 160
+    lf, rf, li, ri = synth.synthetic_frame(H, W, B=1, seed=1)
+    st = synth.synthetic_temporal_state(H, W, B=1)
+    prev = _cuda(dict(prev_disp=st["prev_disp"], cost_memory=st["cost_memory"], local_map=st["local_map"]))
+    prev = temporal.update_map(prev, st["K"].cuda(), st["T_now"].cuda(), st["inv_T_prev"].cuda(),
+                               st["baseline"].cuda(), H, W, True, 3)
+    out = engine(_cuda(lf), _cuda(rf), li.cuda(), ri.cuda(), prev)
+    ref = ([g[f"disp{i}"] for i in range(4)], [g[f"cost{i}"] for i in range(3)],
+           [g[f"sample{i}"] for i in range(3)], [g[f"off{i}"] for i in range(3)])
+    assert out[2][1].shape[1] == 10 and out[2][2].shape[1] == 14      # 3 local-map + 5 + 2 memory; 12 + 2
+    _check(out, ref, "golden temporal 96x160")
+
+
+@pytest.mark.parametrize("H,W,B", [(320, 576, 1), (544, 960, 1), (64, 96, 3)])
+def test_single_frame_vs_oracle(engine, H, W, B):
+    """BASELINE configs C1 (320x576) and C2 (540x960 -> 544x960), plus a batched ragged case."""
+    sd = synth.synthetic_state_dict(seed=0)
+    lf, rf, li, ri = synth.synthetic_frame(H, W, B=B, seed=3)
+    with torch.no_grad():
+        want = O.aggregation_forward(sd, lf, rf, li, ri, {})
+    out = engine(_cuda(lf), _cuda(rf), li.cuda(), ri.cuda(), {})
+    _check(out, want[:4], f"oracle single {H}x{W} B={B}")
+    # top-2 index work: the stored memory is top-2 (sample+offset)/2 resized; compare as EPE
+    d = (out[5]["cost_memory"]["disp_sample"].cpu() - want[5]["cost_memory"]["disp_sample"]).abs().mean()
+    assert d < EPE_TOL, d
+
+
+def test_sequence_vs_oracle(engine):
+    """BASELINE config C3 shape (KITTI 384x1248, T=2, pose warp on): two frames carrying prev_info."""
+    from temporalstereo_b200 import temporal
+    H, W = 384, 1248
+    sd = synth.synthetic_state_dict(seed=0)
+    st = synth.synthetic_temporal_state(H, W, B=1)
+    ref_prev, dev_prev = {}, {}
+    for t in range(2):
+        lf, rf, li, ri = synth.synthetic_frame(H, W, B=1, seed=10 + t)
+        if t > 0:
+            with torch.no_grad():
+                ref_prev = O.update_map(ref_prev, st["K"], st["T_now"], st["inv_T_prev"], st["baseline"], H, W, True, 3)
+            dev_prev = temporal.update_map(dev_prev, st["K"].cuda(), st["T_now"].cuda(), st["inv_T_prev"].cuda(),
+                                           st["baseline"].cuda(), H, W, True, 3)
+        with torch.no_grad():
+            want = O.aggregation_forward(sd, lf, rf, li, ri, ref_prev)
+        out = engine(_cuda(lf), _cuda(rf), li.cuda(), ri.cuda(), dev_prev)
+        ref_prev, dev_prev = want[5], out[5]
+        _check(out, want[:4], f"oracle sequence frame {t}")
+
+
+def test_idempotent_and_batch_independent(engine):
+    """Size-independent properties: same input -> bit-identical output (no atomics on the aggregation
+    path); a batch of 2 equals the two frames run separately."""
+    lf, rf, li, ri = synth.synthetic_frame(128, 192, B=2, seed=5)
+    a = engine(_cuda(lf), _cuda(rf), li.cuda(), ri.cuda(), {})
+    b = engine(_cuda(lf), _cuda(rf), li.cuda(), ri.cuda(), {})
+    for x, y in zip(a[0] + a[1], b[0] + b[1]):
+        assert torch.equal(x, y)
+    for i in range(2):
+        one = engine([t[i:i + 1].cuda() for t in lf], [t[i:i + 1].cuda() for t in rf], li[i:i + 1].cuda(),
+                     ri[i:i + 1].cuda(), {})
+        for x, y in zip(a[0] + a[1], one[0] + one[1]):
+            assert torch.equal(x[i:i + 1], y)

@@ -1,0 +1,422 @@
+"""Per-operator parity of the CUDA kernels (through the C ABI) against the CPU oracle.
+
+Every test feeds the same seeded inputs to oracle/oracle.py (or the torch fp32 CPU op the oracle
+itself calls) and to libtstereo.so, at sizes the oracle finishes in well under a second, including
+odd / ragged sizes (floor pooling, tile tails, W not a multiple of 32).  Index work (sort order,
+top-2 selection) must be exact; floating point is compared with the tolerance written per test.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import oracle as O
+from temporalstereo_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+
+@pytest.fixture(scope="module")
+def ops():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from temporalstereo_b200 import ops as _ops
+    return _ops
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    rng = np.random.RandomState(seed)
+    return torch.from_numpy((scale * rng.standard_normal(shape)).astype(np.float32))
+
+
+def pack(w):
+    """[Cout, Cin, taps...] -> [Cin][taps][CoutP] (the layout include/tstereo.h documents)."""
+    cout, cin = w.shape[:2]
+    w = w.reshape(cout, cin, -1)
+    coutp = (cout + 3) // 4 * 4
+    p = torch.zeros(cin, w.shape[2], coutp)
+    p[:, :, :cout] = w.permute(1, 2, 0)
+    return p.contiguous()
+
+
+def close(got, want, atol, rtol=0.0, what=""):
+    got = got.detach().cpu()
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    assert torch.isfinite(got).all(), f"{what}: non-finite output"
+    torch.testing.assert_close(got, want, atol=atol, rtol=rtol, msg=lambda m: f"{what}: {m}")
+
+
+# --------------------------------------------------------------------------- cost volume (a1-a3)
+def _load(golden_dir, name):
+    return {k: torch.from_numpy(v) for k, v in np.load(os.path.join(golden_dir, name)).items()}
+
+
+def _op_inputs(seed, B, C, H, W, S):
+    rng = np.random.RandomState(seed)
+    L = torch.from_numpy(rng.standard_normal((B, C, H, W)).astype(np.float32))
+    R = torch.from_numpy(rng.standard_normal((B, C, H, W)).astype(np.float32))
+    smp = torch.from_numpy(rng.uniform(-3.0, W / 2.0, (B, S, H, W)).astype(np.float32))
+    return L, R, smp
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_block_cost_golden(ops, golden_dir, tag):
+    """Against outputs of the real reference block_cost (tests/golden, odd sizes)."""
+    g = _load(golden_dir, f"block_cost_warp_{tag}.npz")
+    B, C, H, W, S = [int(v) for v in g["shape"]]
+    L, R, smp = _op_inputs(10, B, C, H, W, S)
+    out = ops.block_cost(L.cuda(), R.cuda(), smp.cuda())
+    # the [L, warp(R)] half is a copy + one bilinear blend; group terms are sums of 8 squares
+    close(out[:, :C], g["out"][:, :C], 0.0, what="L broadcast (bit-exact)")
+    close(out, g["out"], 2e-5, what="block_cost warp")
+    g = _load(golden_dir, f"block_cost_shift_{tag}.npz")
+    out = ops.block_cost(L.cuda(), R.cuda(), S)
+    close(out[:, :C], g["out"][:, :C], 0.0, what="-(L-R_d)^2 (bit-exact)")
+    close(out, g["out"], 2e-5, what="block_cost shift")
+
+
+@pytest.mark.parametrize("B,C,H,W,S", [(1, 32, 34, 60, 5), (2, 16, 17, 45, 7), (1, 128, 24, 40, 5), (1, 8, 4, 4, 2),
+                                        (1, 16, 33, 70, 3)])
+def test_block_cost_warp_vs_oracle(ops, B, C, H, W, S):
+    L, R, smp = _op_inputs(3, B, C, H, W, S)
+    smp[:, 0] = torch.round(smp[:, 0])          # integer candidates: exact taps
+    smp[:, -1] = smp[:, -1] + W                 # fully out-of-range candidates -> zeros
+    want = O.block_cost(L, R, smp, 3)
+    out = ops.block_cost(L.cuda(), R.cuda(), smp.cuda())
+    close(out[:, :C], want[:, :C], 0.0, what="L half")
+    close(out[:, C:2 * C], want[:, C:2 * C], 1e-5, what="warped R half")
+    close(out[:, 2 * C:], want[:, 2 * C:], 5e-5, rtol=1e-5, what="group terms")
+
+
+@pytest.mark.parametrize("B,C,H,W,D", [(1, 256, 20, 36, 12), (2, 16, 9, 13, 20), (1, 8, 6, 5, 8), (1, 64, 34, 60, 16)])
+def test_block_cost_shift_vs_oracle(ops, B, C, H, W, D):
+    L, R, _ = _op_inputs(4, B, C, H, W, 1)
+    want = O.block_cost(L, R, D, 3)
+    out = ops.block_cost(L.cuda(), R.cuda(), D)
+    close(out[:, :C], want[:, :C], 0.0, what="difference half")
+    close(out[:, C:], want[:, C:], 5e-5, rtol=1e-5, what="group terms")
+
+
+def test_block_cost_rejects_bad_arguments(ops):
+    from temporalstereo_b200._lib import TStereoError
+    L = torch.zeros(1, 12, 8, 8, device="cuda")
+    with pytest.raises(TStereoError):
+        ops.block_cost(L, L, 4)                  # C not a multiple of 8 (reference asserts, block_cost.py:9)
+    with pytest.raises(TypeError):
+        ops.block_cost(L.cpu(), L.cpu(), 4)      # no CPU fallback
+
+
+# --------------------------------------------------------------------------- convolutions (a4-a7)
+HW3_CASES = [
+    # B, Cin, Cout, D, H, W, stride, dil, act, bias
+    (1, 44, 32, 3, 17, 30, 1, 1, "SiLU", True),
+    (1, 304, 8, 2, 20, 37, 1, 1, "SiLU", True),
+    (2, 16, 16, 2, 9, 33, 1, 1, None, False),
+    (1, 32, 64, 3, 17, 31, 2, 1, "SiLU", True),
+    (1, 8, 16, 5, 34, 60, 2, 1, "SiLU", True),
+    (1, 32, 32, 2, 17, 30, 1, 2, "SiLU", True),
+    (1, 8, 8, 3, 12, 70, 1, 2, "SiLU", True),
+    (1, 16, 16, 2, 11, 19, 1, 2, None, True),
+    (1, 3, 32, 1, 32, 48, 2, 1, "ReLU", True),
+    (1, 64, 64, 1, 9, 15, 1, 1, "ReLU", True),
+    (1, 128, 36, 1, 10, 12, 1, 1, None, True),
+    (1, 64, 9, 1, 10, 40, 1, 1, None, True),
+    (1, 8, 8, 2, 70, 40, 1, 1, "SiLU", True),
+    (1, 16, 32, 2, 8, 12, 2, 1, None, True),
+]
+
+
+@pytest.mark.parametrize("B,Cin,Cout,D,H,W,stride,dil,act,bias", HW3_CASES)
+def test_conv_hw3(ops, B, Cin, Cout, D, H, W, stride, dil, act, bias):
+    x = rnd(B, Cin, D, H, W, seed=1)
+    w = rnd(Cout, Cin, 1, 3, 3, seed=2, scale=(2.0 / (9 * Cin)) ** 0.5)
+    b = rnd(Cout, seed=3, scale=0.1) if bias else None
+    want = O._act(F.conv3d(x, w, b, (1, stride, stride), (0, dil, dil), (1, dil, dil)), act)
+    got = ops.conv_hw3(x.cuda(), pack(w).cuda(), None if b is None else b.cuda(), Cout, stride, dil, act)
+    close(got, want, 2e-5, rtol=1e-5, what="conv_hw3")
+
+
+def test_conv_hw3_2d_and_strided_views(ops):
+    """4-D input (Conv2d) written into a channel slice of a wider tensor (the concat targets)."""
+    x = rnd(2, 24, 13, 21, seed=5)
+    w = rnd(16, 24, 3, 3, seed=6, scale=0.1)
+    want = F.relu(F.conv2d(x, w, None, 1, 1))
+    buf = torch.full((2, 40, 13, 21), 7.0, device="cuda")
+    ops.conv_hw3(x.cuda(), pack(w).cuda(), None, 16, 1, 1, "ReLU", out=buf[:, 8:24])
+    close(buf[:, 8:24], want, 2e-5, what="conv2d into slice")
+    assert (buf[:, :8] == 7).all() and (buf[:, 24:] == 7).all(), "wrote outside the channel slice"
+    # channel-sliced *input* view
+    xin = torch.zeros(2, 40, 13, 21)
+    xin[:, 8:32] = x
+    got = ops.conv_hw3(xin.cuda()[:, 8:32], pack(w).cuda(), None, 16, 1, 1, "ReLU")
+    close(got, want, 2e-5, what="conv2d from slice")
+
+
+D_CASES = [
+    # B, Cin, Cout, Din, HW(h,w), k, stride, dil, transposed, act
+    (1, 32, 32, 12, (9, 14), 3, 1, 1, False, "SiLU"),
+    (1, 64, 64, 12, (7, 9), 3, 2, 1, False, "SiLU"),
+    (1, 16, 16, 5, (11, 13), 3, 2, 1, False, "SiLU"),
+    (1, 16, 16, 3, (11, 13), 3, 2, 1, False, None),
+    (2, 8, 8, 5, (20, 33), 3, 1, 2, False, "SiLU"),
+    (1, 32, 32, 14, (9, 14), 5, 1, 1, False, "SiLU"),
+    (1, 16, 32, 7, (9, 14), 3, 1, 1, False, "SiLU"),
+    (1, 64, 64, 3, (5, 8), 3, 1, 1, True, None),
+    (1, 16, 8, 2, (12, 19), 3, 1, 1, True, None),
+    (1, 32, 32, 6, (600, 1), 3, 1, 1, True, None),
+]
+
+
+@pytest.mark.parametrize("B,Cin,Cout,Din,hw,k,stride,dil,transposed,act", D_CASES)
+def test_conv_d(ops, B, Cin, Cout, Din, hw, k, stride, dil, transposed, act):
+    H, W = hw
+    x = rnd(B, Cin, Din, H, W, seed=7)
+    b = rnd(Cout, seed=9, scale=0.1)
+    if transposed:
+        w = rnd(Cin, Cout, 3, 1, 1, seed=8, scale=0.1)
+        want = O._act(F.conv_transpose3d(x, w, b, (2, 1, 1), (1, 0, 0), (1, 0, 0)), act)
+        pw = pack(w.transpose(0, 1).contiguous())
+    else:
+        w = rnd(Cout, Cin, k, 1, 1, seed=8, scale=0.1)
+        want = O._act(F.conv3d(x, w, b, (stride, 1, 1), (dil * (k // 2), 0, 0), (dil, 1, 1)), act)
+        pw = pack(w)
+    got = ops.conv_d(x.cuda(), pw.cuda(), b.cuda(), Cout, k, stride, dil, transposed, act)
+    close(got, want, 2e-5, rtol=1e-5, what="conv_d")
+
+
+@pytest.mark.parametrize("B,Cin,Cout,D,H,W,k,act", [
+    (1, 64, 64, 3, 9, 15, 3, None), (1, 64, 32, 2, 17, 30, 3, None), (2, 16, 8, 2, 5, 7, 3, None),
+    (1, 32, 32, 1, 17, 30, 4, "ReLU"), (1, 32, 9, 1, 20, 70, 4, None), (1, 16, 16, 2, 6, 65, 3, None)])
+def test_deconv_hw(ops, B, Cin, Cout, D, H, W, k, act):
+    x = rnd(B, Cin, D, H, W, seed=11)
+    w = rnd(Cin, Cout, 1, k, k, seed=12, scale=0.1)
+    b = rnd(Cout, seed=13, scale=0.1)
+    op = (0, 1, 1) if k == 3 else (0, 0, 0)
+    want = O._act(F.conv_transpose3d(x, w, b, (1, 2, 2), (0, 1, 1), op), act)
+    got = ops.deconv_hw(x.cuda(), pack(w.transpose(0, 1).contiguous()).cuda(), b.cuda(), Cout, k, act)
+    close(got, want, 2e-5, rtol=1e-5, what="deconv_hw")
+
+
+@pytest.mark.parametrize("src,dst", [((6, 18, 30), (6, 17, 30)), ((4, 10, 16), (3, 9, 15)), ((6, 18, 30), (5, 17, 30)),
+                                     ((12, 34, 60), (12, 34, 60)), ((2, 4, 6), (5, 9, 13))])
+def test_resize_add_act(ops, src, dst):
+    a = rnd(2, 5, *src, seed=14)
+    skip = rnd(2, 5, *dst, seed=15)
+    want = F.silu(F.interpolate(a, size=dst, mode="trilinear", align_corners=True) + skip)
+    got = ops.resize_add_act(a.cuda(), dst, skip.cuda(), "SiLU")
+    close(got, want, 2e-6, what="resize_add_act")
+    got = ops.resize_add_act(a.cuda(), dst, None, None)
+    close(got, F.interpolate(a, size=dst, mode="trilinear", align_corners=True), 2e-6, what="resize only")
+
+
+@pytest.mark.parametrize("B,C,D,H,W", [(1, 4, 14, 34, 60), (2, 3, 7, 9, 33), (1, 2, 3, 5, 4), (1, 1, 1, 1, 1)])
+def test_pool5(ops, B, C, D, H, W):
+    x = rnd(B, C, D, H, W, seed=16)
+    cat = torch.zeros(B, 3 * C, D, H, W, device="cuda")
+    cat[:, :C] = x.cuda()
+    ops.pool5(cat[:, :C], cat[:, C:2 * C], cat[:, 2 * C:])
+    close(cat[:, C:2 * C], F.avg_pool3d(x, 5, 1, 2), 1e-6, what="avg_pool3d 5^3")
+    close(cat[:, 2 * C:], F.max_pool3d(x, 5, 1, 2), 0.0, what="max_pool3d 5^3 (exact)")
+
+
+# --------------------------------------------------------------------------- memory merge (a8)
+def _past_conv_sd(C, seed):
+    rng = np.random.RandomState(seed)
+    f = lambda *s: torch.from_numpy(rng.standard_normal(s).astype(np.float32))
+    return {"m.past_conv.weight": f(C, 1, 1, 1, 1), "m.past_conv.norm.weight": 1 + 0.1 * f(C),
+            "m.past_conv.norm.bias": 0.1 * f(C), "m.past_conv.norm.running_mean": 0.1 * f(C),
+            "m.past_conv.norm.running_var": 1 + 0.1 * f(C).abs()}
+
+
+def _fold_past(sd):
+    s = sd["m.past_conv.norm.weight"] / torch.sqrt(sd["m.past_conv.norm.running_var"] + 1e-5)
+    w = sd["m.past_conv.weight"].reshape(-1) * s
+    b = (0 - sd["m.past_conv.norm.running_mean"]) * s + sd["m.past_conv.norm.bias"]
+    return w.contiguous(), b.contiguous()
+
+
+@pytest.mark.parametrize("with_memory", [False, True])
+@pytest.mark.parametrize("B,C,D,H,W", [(1, 32, 12, 9, 14), (2, 16, 8, 7, 33)])
+def test_merge_memory(ops, with_memory, B, C, D, H, W):
+    vol = rnd(B, C, D, H, W, seed=17)
+    if D == 12:   # the coarse level's constant integer candidates: ties with the zero memory samples
+        samples = torch.linspace(0, D - 1, D).view(1, D, 1, 1).expand(B, D, H, W).contiguous()
+    else:
+        samples = rnd(B, D, H, W, seed=18, scale=5.0)
+        samples[:, 3] = samples[:, 1]            # exact ties inside the candidate list
+    sd = _past_conv_sd(C, 19)
+    prev = {}
+    ms = mc = None
+    if with_memory:
+        ms = rnd(B, 2, H, W, seed=20, scale=4.0)
+        ms[:, 1] = samples[:, 2]                 # tie between a memory sample and a candidate
+        mc = rnd(B, 2, H, W, seed=21)
+        prev = {"cost_memory": {"disp_sample": ms, "cost_volume": mc}, "use_past_cost": True}
+    want_vol, want_s = O.merge_memory(vol, samples, sd, "m", prev, 2, coarse=False)
+    pw, pb = _fold_past(sd)
+    got_vol, got_s = ops.merge_memory(vol.cuda(), samples.cuda(), None if ms is None else ms.cuda(),
+                                      None if mc is None else mc.cuda(), pw.cuda(), pb.cuda(), 2)
+    close(got_s, want_s, 0.0, what="sorted samples (exact)")
+    # planes coming from the volume are pure gathers -> exact; memory planes go through SiLU
+    close(got_vol, want_vol, 2e-6, what="permuted volume")
+    # the permutation itself: every plane taken from the input volume must match bit-for-bit
+    src = torch.cat([samples, ms if ms is not None else torch.zeros(B, 2, H, W)], 1)
+    order = torch.sort(src, dim=1, stable=True)[1]
+    from_vol = (order < D).unsqueeze(1).expand_as(want_vol)
+    assert torch.equal(got_vol.cpu()[from_vol], want_vol[from_vol]), "gathered planes differ: sort order mismatch"
+
+
+# --------------------------------------------------------------------------- heads + regression (a10, a11, a14)
+def test_heads(ops):
+    B, C, D, H, W = 2, 16, 7, 9, 33
+    feat = rnd(B, 2 * C, D, H, W, seed=22)
+    wc = rnd(1, C, 1, 3, 3, seed=23, scale=3.0)
+    wo = rnd(1, C, 1, 3, 3, seed=24, scale=30.0)     # large: exercises the tanh squashing
+    want_cost = F.conv3d(feat[:, :C], wc, None, 1, (0, 1, 1)).squeeze(1)
+    want_off = torch.tanh(F.conv3d(feat[:, C:], wo, None, 1, (0, 1, 1)).squeeze(1) / 100).clamp(-1, 1) * 1.0
+    w = torch.stack([wc.reshape(C, 9), wo.reshape(C, 9)]).contiguous()
+    cost, off = ops.heads(feat.cuda(), w.cuda(), 1.0)
+    close(cost, want_cost, 5e-5, rtol=1e-5, what="cost head")
+    close(off, want_off, 5e-6, what="offset head")
+
+
+@pytest.mark.parametrize("B,D,H,W", [(1, 14, 9, 14), (2, 5, 7, 33), (1, 2, 3, 5), (1, 22, 4, 40)])
+def test_predict_disp(ops, B, D, H, W):
+    cost = rnd(B, D, H, W, seed=25, scale=2.0)
+    samples = rnd(B, D, H, W, seed=26, scale=10.0)
+    off = rnd(B, D, H, W, seed=27, scale=0.3)
+    want, want_td, want_tc = O.predict_disp(cost, samples, off, 2)
+    disp, td, tc = ops.predict_disp(cost.cuda(), samples.cuda(), off.cuda(), True)
+    close(tc, want_tc, 0.0, what="top-2 costs (exact)")
+    close(td, want_td, 0.0, what="top-2 disparities (exact: index work)")
+    close(disp, want, 2e-6, what="regressed disparity")
+
+
+def test_predict_disp_ties(ops):
+    """Equal costs: ties resolve to the lowest index first, and the selected *values* equal torch.topk's."""
+    cost = torch.tensor([1.0, 3.0, 3.0, 2.0, 3.0]).view(1, 5, 1, 1).repeat(1, 1, 2, 3).contiguous()
+    samples = torch.arange(5.0).view(1, 5, 1, 1).repeat(1, 1, 2, 3).contiguous()
+    off = torch.zeros_like(cost)
+    disp, td, tc = ops.predict_disp(cost.cuda(), samples.cuda(), off.cuda(), True)
+    assert torch.equal(tc.cpu(), torch.full((1, 2, 2, 3), 3.0))
+    assert torch.equal(td.cpu()[:, 0], torch.full((1, 2, 3), 1.0)) and torch.equal(td.cpu()[:, 1], torch.full((1, 2, 3), 2.0))
+    # all-equal costs (e.g. a constant volume): indices 0 and 1
+    cost = torch.zeros(1, 4, 2, 2)
+    disp, td, tc = ops.predict_disp(cost.cuda(), torch.arange(4.0).view(1, 4, 1, 1).expand(1, 4, 2, 2).contiguous().cuda(),
+                                    cost.cuda(), True)
+    assert torch.equal(td.cpu()[:, 0], torch.zeros(1, 2, 2)) and torch.equal(td.cpu()[:, 1], torch.ones(1, 2, 2))
+    close(disp, torch.full((1, 1, 2, 2), 0.5), 0.0, what="tie regression")
+
+
+def test_range_samples(ops):
+    disp = rnd(2, 1, 9, 14, seed=28, scale=20.0)
+    want = O.range_samples(disp - 4.0, disp + 4.0)
+    buf = torch.full((2, 8, 9, 14), -1.0, device="cuda")
+    low, high = ops.range_samples(disp.cuda(), 4.0, buf, 3)
+    close(buf[:, 3:], want, 0.0, what="range candidates (exact)")
+    close(low, disp - 4.0, 0.0, what="low")
+    close(high, disp + 4.0, 0.0, what="high")
+    assert (buf[:, :3] == -1).all()
+
+
+# --------------------------------------------------------------------------- up-sampling (a12, a13, a16, a20)
+def test_convex_upsample(ops):
+    B, H, W = 2, 9, 33
+    m = rnd(B, 64, H, W, seed=29)
+    w = rnd(36, 64, 1, 1, seed=30, scale=0.3)
+    b = rnd(36, seed=31, scale=0.1)
+    disp = rnd(B, 1, H, W, seed=32, scale=10.0)
+    logits = F.conv2d(m, w, b)
+    mm = torch.softmax(logits.view(B, 1, 9, 2, 2, H, W), 2)
+    u = F.unfold(disp * 2, (3, 3), padding=1).view(B, 1, 9, 1, 1, H, W)
+    want = (mm * u).sum(2).permute(0, 1, 4, 2, 5, 3).reshape(B, 1, 2 * H, 2 * W)
+    got = ops.convex_upsample(m.cuda(), w.reshape(36, 64).contiguous().cuda(), b.cuda(), disp.cuda())
+    close(got, want, 2e-5, what="convex_upsample")
+
+
+@pytest.mark.parametrize("h,w", [(9, 14), (24, 40), (5, 33)])
+def test_unet_upsample(ops, h, w):
+    B, H, W = 2, 4 * h, 4 * w
+    logits = rnd(B, 9, H, W, seed=33, scale=2.0)
+    disp = rnd(B, 1, h, w, seed=34, scale=10.0)
+    want = O.unet_upsample(logits, disp)
+    got = ops.unet_upsample(logits.cuda(), disp.cuda())
+    close(got, want, 2e-5, what="unet_upsample")
+
+
+@pytest.mark.parametrize("src,dst", [((24, 40), (12, 20)), ((12, 20), (6, 10)), ((6, 10), (96, 160)), ((7, 9), (7, 9))])
+def test_bilinear_resize(ops, src, dst):
+    x = rnd(2, 3, *src, seed=35, scale=5.0)
+    want = F.interpolate(x * dst[1] / src[1], size=dst, mode="bilinear", align_corners=True)
+    got = ops.bilinear_resize(x.cuda(), dst, mul=dst[1], div=src[1])
+    close(got, want, 2e-6, rtol=1e-6, what="bilinear_resize")
+    buf = torch.zeros(2, 5, *dst, device="cuda")
+    ops.bilinear_resize(x.cuda(), dst, out=buf, c_off=2)
+    close(buf[:, 2:], F.interpolate(x, size=dst, mode="bilinear", align_corners=True), 2e-6, what="into slice")
+    assert (buf[:, :2] == 0).all()
+
+
+# --------------------------------------------------------------------------- temporal warp (a17-a19)
+def test_project_to_3d_golden(golden_dir):
+    from temporalstereo_b200 import temporal
+    g = _load(golden_dir, "project_to_3d.npz")
+    st = synth.synthetic_temporal_state(64, 96, B=2)
+    K8 = st["K"].clone(); K8[:, :2] /= 8.0
+    T = torch.bmm(st["T_now"], st["inv_T_prev"])
+    depth = 0.54 * K8[:, 0, 0].view(-1, 1, 1, 1) / (st["cost_memory"]["disp_sample"] + 1e-5)
+    out = temporal.project_to_3d(depth.cuda(), K8.cuda(), None, T.cuda())
+    close(out["optical_flow"], g["flow"], 2e-4, rtol=1e-5, what="optical_flow vs reference")
+    close(out["triangular_depth"], g["tri"], 1e-5, rtol=1e-6, what="triangular_depth vs reference")
+
+
+def test_softsplat_vs_oracle():
+    from temporalstereo_b200 import temporal
+    B, C, h, w = 2, 4, 12, 20
+    x = rnd(B, C, h, w, seed=36)
+    flow = rnd(B, 2, h, w, seed=37, scale=2.5)
+    flow[0, :, 0, 0] = torch.tensor([-30.0, 4.0])      # lands outside: contributes nowhere
+    flow[0, :, 1, 1] = torch.tensor([1.0, -1.0])       # exactly on a pixel centre
+    metric = rnd(B, 1, h, w, seed=38, scale=3.0)
+    want = O.softsplat_softmax(x, flow, metric)
+    got = temporal.FunctionSoftsplat(x.cuda(), flow.cuda(), metric.cuda(), "softmax")
+    # float atomics: summation order differs from the oracle's index_add_
+    close(got, want, 2e-5, rtol=1e-5, what="softmax splat")
+    holes = (want == 0).all(1)
+    assert torch.equal((got.cpu() == 0).all(1), holes), "hole pattern (pixels nobody splats to) differs"
+
+
+@pytest.mark.parametrize("first_frame", [False, True])
+def test_update_map_vs_oracle(golden_dir, first_frame):
+    from temporalstereo_b200 import temporal
+    H, W = 96, 160
+    st = synth.synthetic_temporal_state(H, W, B=2)
+    prev = dict(prev_disp=st["prev_disp"], cost_memory=st["cost_memory"], local_map=st["local_map"])
+    if first_frame:
+        prev.pop("local_map")
+    want = O.update_map(dict(prev), st["K"], st["T_now"], st["inv_T_prev"], st["baseline"], H, W, True, 3)
+    dev = {k: (v.cuda() if torch.is_tensor(v) else {a: b.cuda() for a, b in v.items()}) for k, v in prev.items()}
+    got = temporal.update_map(dev, st["K"].cuda(), st["T_now"].cuda(), st["inv_T_prev"].cuda(), st["baseline"].cuda(),
+                              H, W, True, 3)
+    close(got["cost_memory"]["disp_sample"], want["cost_memory"]["disp_sample"], 2e-4, rtol=1e-5, what="warped samples")
+    close(got["cost_memory"]["cost_volume"], want["cost_memory"]["cost_volume"], 2e-4, rtol=1e-5, what="warped costs")
+    close(got["local_map"], want["local_map"], 2e-4, rtol=1e-5, what="local map")
+    assert got["local_map_size"] == 3 and got["use_past_cost"] is True
+
+
+def test_update_map_golden(golden_dir):
+    """Against the real reference's update_map (with the CPU splat restatement), B=1."""
+    from temporalstereo_b200 import temporal
+    gm = _load(golden_dir, "update_map_96x160.npz")
+    H, W = 96, 160
+    st = synth.synthetic_temporal_state(H, W, B=1)
+    dev = dict(prev_disp=st["prev_disp"].cuda(), local_map=st["local_map"].cuda(),
+               cost_memory={k: v.cuda() for k, v in st["cost_memory"].items()})
+    got = temporal.update_map(dev, st["K"].cuda(), st["T_now"].cuda(), st["inv_T_prev"].cuda(), st["baseline"].cuda(),
+                              H, W, True, 3)
+    close(got["cost_memory"]["disp_sample"], gm["mem_sample"], 2e-4, rtol=1e-5, what="warped samples")
+    close(got["cost_memory"]["cost_volume"], gm["mem_cost"], 2e-4, rtol=1e-5, what="warped costs")
+    close(got["local_map"], gm["local_map"], 2e-4, rtol=1e-5, what="local map")
