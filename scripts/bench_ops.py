@@ -1,0 +1,61 @@
+"""Micro-benchmarks of individual libtstereo ops at the C2 (544x960) shapes, CUDA-event timed.
+    python scripts/bench_ops.py [block_cost] [conv] [--batch B]"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from temporalstereo_b200 import ops
+
+B = 1
+if "--batch" in sys.argv:
+    B = int(sys.argv[sys.argv.index("--batch") + 1])
+which = [a for a in sys.argv[1:] if not a.startswith("--") and not a.isdigit()] or ["block_cost"]
+H, W = 544, 960
+dev = "cuda"
+flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+
+
+def timeit(fn, reps=10, warm=3):
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+if "block_cost" in which:
+    tot_b, tot_t = 0, 0
+    for name, C, s, S, warp in (("coarse", 256, 16, 12, False), ("fine", 128, 8, 5, True), ("precise", 128, 4, 5, True),
+                                ("fine-temporal", 128, 8, 8, True)):
+        h, w = H // s, W // s
+        L = torch.randn(B, C, h, w, device=dev); R = torch.randn(B, C, h, w, device=dev)
+        smp = (torch.rand(B, S, h, w, device=dev) * 30) if warp else S
+        planes = (2 * C if warp else C) + 3 * C // 8
+        nbytes = 4 * B * (2 * C * h * w + (S * h * w if warp else 0) + planes * S * h * w)
+        med, best = timeit(lambda: ops.block_cost(L, R, smp))
+        print(f"block_cost {name:14s} B={B} {nbytes/1e6:8.2f} MB  median {med:8.1f} us  best {best:8.1f} us  "
+              f"{nbytes/med/1e3:7.1f} GB/s ({100*nbytes/med/1e3/6553.9:.1f}% of measured HBM peak)")
+        if name != "fine-temporal":
+            tot_b += nbytes; tot_t += med
+    print(f"block_cost total (coarse+fine+precise): {tot_b/1e6:.1f} MB in {tot_t:.1f} us -> {tot_b/tot_t/1e3:.1f} GB/s "
+          f"({100*tot_b/tot_t/1e3/6553.9:.1f}%)")
+
+if "conv" in which:
+    def pack(cout, cin, taps):
+        return torch.randn(cin, taps, (cout + 3) // 4 * 4, device=dev) * 0.05
+    cases = [("coarse.init3d.0.conv.0", 352, 32, 12, 34, 60, 1, 1), ("fine.init3d.0.conv.0", 304, 16, 5, 68, 120, 1, 1),
+             ("precise.init3d.0.conv.0", 304, 8, 5, 136, 240, 1, 1), ("coarse.fuse", 128, 32, 14, 34, 60, 1, 1),
+             ("unet.concat", 64, 32, 1, 272, 480, 1, 1), ("unet.conv2.1", 32, 32, 1, 272, 480, 1, 1),
+             ("unet.fuse.0", 128, 32, 1, 136, 240, 1, 1), ("coarse.mask0", 256, 64, 1, 34, 60, 1, 1),
+             ("hourglass 64->64 s1", 64, 64, 6, 17, 30, 1, 1)]
+    for name, cin, cout, D, h, w, st, dl in cases:
+        x = torch.randn(B, cin, D, h, w, device=dev)
+        wt = pack(cout, cin, 9); bias = torch.randn(cout, device=dev)
+        med, best = timeit(lambda: ops.conv_hw3(x, wt, bias, cout, st, dl, "SiLU"))
+        fl = 2 * B * cin * cout * 9 * D * h * w
+        print(f"conv_hw3 {name:26s} B={B} {fl/1e9:6.2f} GFLOP median {med:8.1f} us best {best:8.1f} -> {fl/med/1e6:7.2f} TFLOP/s")
