@@ -30,6 +30,8 @@ extern "C" {
 
 int         tstereo_version(void);
 const char* tstereo_last_error(void);
+/* hash of the sources the library was built from (temporalstereo_b200/build.py:source_id) */
+const char* tstereo_build_id(void);
 /* number of kernels this library has launched in the process so far (bench.py's gpu_launches) */
 long long   tstereo_launch_count(void);
 

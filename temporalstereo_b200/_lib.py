@@ -18,6 +18,7 @@ P, I, F, LL = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 SIGNATURES = {
     "tstereo_version": (I, []),
     "tstereo_last_error": (C.c_char_p, []),
+    "tstereo_build_id": (C.c_char_p, []),
     "tstereo_launch_count": (LL, []),
     "tstereo_block_cost_scratch_floats": (LL, [I, I, I, I, I]),
     "tstereo_block_cost_shift": (I, [P, P, P, P, I, I, I, I, I, P]),
@@ -44,6 +45,16 @@ SIGNATURES = {
 _lib = None
 
 
+def _built_id(path: str) -> str:
+    """Build id baked into a libtstereo.so, read from the file bytes (no dlopen of a stale library)."""
+    try:
+        data = open(path, "rb").read()
+    except OSError:
+        return ""
+    i = data.find(b"TSTEREO_BUILD_ID=")
+    return data[i + 17:i + 33].decode(errors="replace") if i >= 0 else ""
+
+
 class TStereoError(RuntimeError):
     """A libtstereo entry point returned a negative TSTEREO_E_* code."""
 
@@ -53,6 +64,14 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
+    default = "TSTEREO_LIB" not in os.environ
+    if default:
+        from . import build as _build
+        want = _build.source_id()
+        if not os.path.exists(LIB_PATH) or _built_id(LIB_PATH) != want:
+            _build.build()                      # stale or missing: recompile in-tree (nvcc needs no GPU)
+        if _built_id(LIB_PATH) != want:
+            raise ImportError(f"{LIB_PATH} is stale and could not be rebuilt")
     if not os.path.exists(LIB_PATH):
         raise ImportError(
             f"{LIB_PATH} not found: build it with `python -m temporalstereo_b200.build` "

@@ -34,6 +34,19 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found (set NVCC=/path/to/nvcc)")
 
 
+def source_id() -> str:
+    """sha1 over every source that goes into libtstereo.so; baked into the library as
+    tstereo_build_id() so a stale .so is detected at load time (_lib.load)."""
+    import hashlib
+    h = hashlib.sha1()
+    files = sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh")))
+    files.append(os.path.join(ROOT, "include", "tstereo.h"))
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
 def _stale(target: str, deps) -> bool:
     if not os.path.exists(target):
         return True
@@ -48,11 +61,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
     hdrs = sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [os.path.join(ROOT, "include", "tstereo.h")]
     jobs = []
     objs = []
+    sid = source_id()
+    idfile = os.path.join(OBJ, "build_id.txt")
+    if not os.path.exists(idfile) or open(idfile).read() != sid:
+        force = True                                # any source changed: rebuild everything (cheap, parallel)
     for s in srcs:
         o = os.path.join(OBJ, os.path.basename(s)[:-3] + ".o")
         objs.append(o)
         if force or _stale(o, [s] + hdrs):
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            cmd = [nvcc] + NVCC_FLAGS + [f'-DTSTEREO_BUILD_ID="{sid}"'] + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             jobs.append(cmd)
 
     def run(cmd):
@@ -68,6 +85,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
                     print(log, file=sys.stderr)
     if force or jobs or _stale(LIB, objs):
         run([nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+    with open(idfile, "w") as f:
+        f.write(sid)
     return LIB
 
 

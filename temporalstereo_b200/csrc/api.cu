@@ -18,5 +18,11 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 extern "C" {
 int tstereo_version(void) { return TSTEREO_VERSION; }
 const char* tstereo_last_error(void) { return tstereo::g_err; }
+#ifndef TSTEREO_BUILD_ID
+#define TSTEREO_BUILD_ID "unknown"
+#endif
+// the "TSTEREO_BUILD_ID=" prefix lets the loader read the id from the file without dlopen()ing a stale library
+static const char g_build_id[] = "TSTEREO_BUILD_ID=" TSTEREO_BUILD_ID;
+const char* tstereo_build_id(void) { return g_build_id + 17; }
 long long tstereo_launch_count(void) { return tstereo::g_launches.load(std::memory_order_relaxed); }
 }
