@@ -6,14 +6,14 @@
 //
 // HBM-bound streaming kernel: the output is ~6x the input bytes (C2 precise: 34 MB in, 198 MB out).
 //
-//  * main kernel.  thread = ONE pixel, one group of 8 channels, SC disparity candidates.
-//    lane layout inside a warp is 8 columns x 4 rows, a 256-thread CTA covers 32 columns x 8 rows,
-//    so every global access of a warp is four fully used 32 B sectors and a CTA writes whole 128 B
-//    lines.  Per pixel the warp coordinate / tap weights are computed once per candidate and reused
-//    for the 8 channels; the left feature is loaded once and reused for the SC candidates.
+//  * main kernel.  thread = FOUR consecutive pixels of a row, one group of 8 channels, one
+//    disparity candidate.  A warp is 8 threads (32 px = 128 B) x 4 rows, a 128-thread CTA covers
+//    64 px x 8 rows.  The left features and every output plane move as 16 B vectors (one 128 B line
+//    per warp row); only the right-feature taps are scalar gathers.  Per pixel the warp coordinate /
+//    tap weights are computed once and reused for the 8 channels.
 //    avg_pool(L) - avg_pool(R_d) == avg_pool(L - R_d), so the 2x2 and 4x4 pooled differences are
-//    warp-shuffle reductions of the per-pixel difference (xor 1, 8 | xor 2, 16) — no second pass over
-//    the features, no shared memory.  The thread writes L, R_d (or -(L-R_d)^2), the full-resolution
+//    in-thread sums along x plus warp shuffles along y (xor 8, xor 16) — no second pass over the
+//    features, no shared memory.  The thread writes L, R_d (or -(L-R_d)^2), the full-resolution
 //    group term g0 and the small pooled terms G1, G2 (scratch, L2 resident).
 //  * resize kernel: bilinear align_corners up-sampling of G1, G2 into the last 2*C/8 planes,
 //    four output columns per thread.
@@ -21,40 +21,42 @@
 
 namespace tstereo {
 
-template <bool WARP, int SC>
-__global__ void __launch_bounds__(256)
+// VEC: W % 4 == 0 and 16 B aligned bases -> float4 loads / stores; otherwise scalar with tail guards.
+template <bool WARP, bool VEC>
+__global__ void __launch_bounds__(128)
 block_cost_main_kernel(const float* __restrict__ L, const float* __restrict__ R,
                        const float* __restrict__ smp, float* __restrict__ out,
                        float* __restrict__ g1, float* __restrict__ g2,
-                       int C, int H, int W, int D, int nchunk) {
+                       int C, int H, int W, int D) {
     const int G = C >> 3;
     int z = blockIdx.z;
-    const int chunk = z % nchunk;
-    z /= nchunk;
+    const int d = z % D;
+    z /= D;
     const int g = z % G;
     const int b = z / G;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int x = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
-    const int y = blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
-    const size_t HW = (size_t)H * W;
+    const int x = (blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7)) * 4;       // first of the 4 pixels
+    const int y = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+    const int HW = H * W;
     const int outC = (WARP ? 2 * C : C) + 3 * G;
-    const bool pin = (x < W) && (y < H);
-    const int d0 = chunk * SC;
+    const bool rowin = y < H;
+    bool pin[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) pin[k] = rowin && (x + k < W);
 
-    // per-candidate horizontal taps (x0 = -2: nothing to sample)
-    int x0[SC];
-    float w0[SC], w1[SC];
-    // vertical taps (warp branch only; same for every candidate)
+    // horizontal taps per pixel: offset of tap 0 inside the row, weights, validity bits
+    int x0[4];
+    float w0[4], w1[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        x0[k] = -2;                       // -2: neither tap is inside the image
+        w0[k] = 0.f;
+        w1[k] = 0.f;
+    }
     int ylo = y;
     float wy0 = 1.f, wy1 = 0.f;
-#pragma unroll
-    for (int s = 0; s < SC; ++s) {
-        x0[s] = -2;
-        w0[s] = 0.f;
-        w1[s] = 0.f;
-    }
-    if (pin) {
-        if (WARP) {
+    if (WARP) {
+        if (rowin) {
             // The y coordinate goes through the same normalise / un-normalise round trip
             // (inverse_warp_3d.py:46, grid_sampler_unnormalize); for some (H, y) it lands a few
             // 1e-6 px off the integer, which blends two rows.
@@ -65,110 +67,153 @@ block_cost_main_kernel(const float* __restrict__ L, const float* __restrict__ R,
             ylo = (int)fy;
             wy0 = __fsub_rn(fy + 1.0f, iy);
             wy1 = __fsub_rn(iy, fy);
+            const float* sp = smp + ((size_t)(b * D + d) * H + y) * W + x;
+            float dsp[4];
+            if (VEC) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(sp));
+                dsp[0] = t.x; dsp[1] = t.y; dsp[2] = t.z; dsp[3] = t.w;
+            } else {
 #pragma unroll
-            for (int s = 0; s < SC; ++s) {
-                if (d0 + s < D) {
+                for (int k = 0; k < 4; ++k) dsp[k] = pin[k] ? __ldg(sp + k) : 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (pin[k]) {
                     // same op sequence as inverse_warp_3d.py:40-47 + ATen grid_sampler_unnormalize
-                    const float dsp = __ldg(smp + ((size_t)(b * D + d0 + s) * H + y) * W + x);
-                    const float gx = __fadd_rn((float)x, -dsp);
+                    const float gx = __fadd_rn((float)(x + k), -dsp[k]);
                     const float gn = __fsub_rn(__fmul_rn(__fdiv_rn(gx, Wm1), 2.0f), 1.0f);
                     const float ix = __fmul_rn(__fdiv_rn(__fadd_rn(gn, 1.0f), 2.0f), Wm1);
                     const float fx = floorf(ix);
                     if (fx >= -1.0f && fx <= Wm1) {
-                        x0[s] = (int)fx;
-                        w0[s] = __fsub_rn(fx + 1.0f, ix);
-                        w1[s] = __fsub_rn(ix, fx);
+                        x0[k] = (int)fx;
+                        w0[k] = __fsub_rn(fx + 1.0f, ix);
+                        w1[k] = __fsub_rn(ix, fx);
                     }
                 }
             }
-        } else {
-#pragma unroll
-            for (int s = 0; s < SC; ++s)
-                if (d0 + s < D && x - (d0 + s) >= 0) x0[s] = x - (d0 + s);
         }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (pin[k] && x + k - d >= 0) x0[k] = x + k - d;
     }
     // rows to blend (warp branch): r = 0 -> (ylo, wy0), r = 1 -> (ylo + 1, wy1); zero-weight or
     // out-of-image rows are skipped exactly like grid_sample's zeros padding
-    int rbeg = 0, rend = 1;
-    if (WARP) {
-        rbeg = (ylo >= 0 && wy0 != 0.f) ? 0 : 1;
-        rend = (ylo + 1 < H && wy1 != 0.f) ? 2 : 1;
+    const bool row0 = WARP ? (rowin && ylo >= 0 && wy0 != 0.f) : rowin;
+    const bool row1 = WARP ? (rowin && ylo + 1 < H && wy1 != 0.f) : false;
+    bool v0[4], v1[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        v0[k] = (unsigned)x0[k] < (unsigned)W;
+        v1[k] = (unsigned)(x0[k] + 1) < (unsigned)W;
     }
 
-    float a0[SC], a1[SC], a2[SC];
-#pragma unroll
-    for (int s = 0; s < SC; ++s) a0[s] = a1[s] = a2[s] = 0.f;
+    float a0[4] = {0.f, 0.f, 0.f, 0.f};
+    float a1[2] = {0.f, 0.f};
+    float a2 = 0.f;
 
-    const size_t pix = (size_t)y * W + x;
+    const int pix = y * W + x;
     const float* Lp = L + ((size_t)b * C + g * 8) * HW + pix;
-    const float* Rb = R + ((size_t)b * C + g * 8) * HW;
-    float* o1 = out + (((size_t)b * outC + g * 8) * D + d0) * HW + pix;   // first half, plane (ch, d0)
-    const size_t second = (size_t)C * D * HW;                             // offset of the R half (WARP)
-    const size_t chs = (size_t)D * HW;                                     // channel stride in `out`
+    const float* Rp = R + ((size_t)b * C + g * 8) * HW + (WARP ? ylo : y) * W;
+    float* o1 = out + (((size_t)b * outC + g * 8) * D + d) * HW + pix;   // first half, plane (ch, d)
+    const size_t second = (size_t)C * D * HW;                            // offset of the R half (WARP)
+    const size_t chs = (size_t)D * HW;                                    // channel stride in `out`
 
-#pragma unroll 1
+#pragma unroll 2
     for (int c = 0; c < 8; ++c) {
-        const float l = pin ? __ldg(Lp + (size_t)c * HW) : 0.f;
-        const float* Rp = Rb + (size_t)c * HW;
-        float rv[SC];
+        float l[4] = {0.f, 0.f, 0.f, 0.f}, rv[4] = {0.f, 0.f, 0.f, 0.f};
+        if (VEC) {
+            if (pin[0]) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(Lp));
+                l[0] = t.x; l[1] = t.y; l[2] = t.z; l[3] = t.w;
+            }
+        } else {
 #pragma unroll
-        for (int s = 0; s < SC; ++s) rv[s] = 0.f;
+            for (int k = 0; k < 4; ++k)
+                if (pin[k]) l[k] = __ldg(Lp + k);
+        }
         if (WARP) {
-#pragma unroll 1
-            for (int r = rbeg; r < rend; ++r) {
-                const float* rr = Rp + (ylo + r) * W;
-                const float wy = r ? wy1 : wy0;
+            if (row0) {
 #pragma unroll
-                for (int s = 0; s < SC; ++s) {
-                    const bool v0 = (unsigned)x0[s] < (unsigned)W, v1 = (unsigned)(x0[s] + 1) < (unsigned)W;
-                    const float ra = v0 ? __ldg(rr + x0[s]) : 0.f;
-                    const float rb = v1 ? __ldg(rr + x0[s] + 1) : 0.f;
-                    rv[s] = fmaf(wy, fmaf(rb, w1[s], __fmul_rn(ra, w0[s])), rv[s]);
+                for (int k = 0; k < 4; ++k) {
+                    const float ra = v0[k] ? __ldg(Rp + x0[k]) : 0.f;
+                    const float rb = v1[k] ? __ldg(Rp + x0[k] + 1) : 0.f;
+                    rv[k] = wy0 * fmaf(rb, w1[k], __fmul_rn(ra, w0[k]));
+                }
+            }
+            if (row1) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float ra = v0[k] ? __ldg(Rp + W + x0[k]) : 0.f;
+                    const float rb = v1[k] ? __ldg(Rp + W + x0[k] + 1) : 0.f;
+                    rv[k] = fmaf(wy1, fmaf(rb, w1[k], __fmul_rn(ra, w0[k])), rv[k]);
                 }
             }
         } else {
 #pragma unroll
-            for (int s = 0; s < SC; ++s)
-                if (x0[s] >= 0) rv[s] = __ldg(Rp + y * W + x0[s]);
+            for (int k = 0; k < 4; ++k)
+                if (v0[k]) rv[k] = __ldg(Rp + x0[k]);
         }
+        float e[4];
 #pragma unroll
-        for (int s = 0; s < SC; ++s) {
-            const bool live = pin && (d0 + s < D);
-            float* op = o1 + (size_t)c * chs + (size_t)s * HW;
-            const float e = live ? (l - rv[s]) : 0.f;
-            if (live) {
+        for (int k = 0; k < 4; ++k) {
+            e[k] = l[k] - rv[k];                 // 0 outside the image (l = rv = 0)
+            a0[k] = fmaf(e[k], e[k], a0[k]);
+        }
+        if (VEC) {
+            if (pin[0]) {
                 if (WARP) {
-                    op[0] = l;
-                    op[second] = rv[s];
+                    *reinterpret_cast<float4*>(o1) = make_float4(l[0], l[1], l[2], l[3]);
+                    *reinterpret_cast<float4*>(o1 + second) = make_float4(rv[0], rv[1], rv[2], rv[3]);
                 } else {
-                    op[0] = -(e * e);
+                    *reinterpret_cast<float4*>(o1) = make_float4(-(e[0] * e[0]), -(e[1] * e[1]), -(e[2] * e[2]), -(e[3] * e[3]));
                 }
             }
-            a0[s] = fmaf(e, e, a0[s]);
-            float s2 = e + __shfl_xor_sync(0xffffffffu, e, 1);
-            s2 += __shfl_xor_sync(0xffffffffu, s2, 8);
-            const float m1 = s2 * 0.25f;
-            a1[s] = fmaf(m1, m1, a1[s]);
-            float s4 = s2 + __shfl_xor_sync(0xffffffffu, s2, 2);
-            s4 += __shfl_xor_sync(0xffffffffu, s4, 16);
-            const float m2 = s4 * 0.0625f;
-            a2[s] = fmaf(m2, m2, a2[s]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (pin[k]) {
+                    if (WARP) {
+                        o1[k] = l[k];
+                        o1[second + k] = rv[k];
+                    } else {
+                        o1[k] = -(e[k] * e[k]);
+                    }
+                }
         }
+        // 2x2 pooled difference: x pairs in-thread, y pairs across lanes (xor 8); 4x4: + xor 16
+        float pa = e[0] + e[1], pb = e[2] + e[3];
+        pa += __shfl_xor_sync(0xffffffffu, pa, 8);
+        pb += __shfl_xor_sync(0xffffffffu, pb, 8);
+        const float ma = pa * 0.25f, mb = pb * 0.25f;
+        a1[0] = fmaf(ma, ma, a1[0]);
+        a1[1] = fmaf(mb, mb, a1[1]);
+        float q = pa + pb;
+        q += __shfl_xor_sync(0xffffffffu, q, 16);
+        const float mq = q * 0.0625f;
+        a2 = fmaf(mq, mq, a2);
+        Lp += HW;
+        Rp += HW;
+        o1 += chs;
     }
 
     const int base = WARP ? 2 * C : C;
     const int H1 = H >> 1, W1 = W >> 1, H2 = H >> 2, W2 = W >> 2;
-    const bool cell1 = ((x | y) & 1) == 0 && x + 1 < W && y + 1 < H;
-    const bool cell2 = ((x | y) & 3) == 0 && x + 3 < W && y + 3 < H;
+    float* og = out + (((size_t)b * outC + base + g) * D + d) * HW + pix;
+    if (VEC) {
+        if (pin[0]) *reinterpret_cast<float4*>(og) = make_float4(-a0[0], -a0[1], -a0[2], -a0[3]);
+    } else {
 #pragma unroll
-    for (int s = 0; s < SC; ++s) {
-        const int d = d0 + s;
-        if (d >= D) break;
-        if (pin) out[(((size_t)b * outC + base + g) * D + d) * HW + pix] = -a0[s];
-        const size_t pl = ((size_t)b * G + g) * D + d;
-        if (cell1) g1[(pl * H1 + (y >> 1)) * W1 + (x >> 1)] = -a1[s];
-        if (cell2) g2[(pl * H2 + (y >> 2)) * W2 + (x >> 2)] = -a2[s];
+        for (int k = 0; k < 4; ++k)
+            if (pin[k]) og[k] = -a0[k];
     }
+    const size_t pl = ((size_t)b * G + g) * D + d;
+    if ((y & 1) == 0 && y + 1 < H) {
+        float* p1 = g1 + (pl * H1 + (y >> 1)) * W1 + (x >> 1);
+        if (x + 1 < W) p1[0] = -a1[0];
+        if (x + 3 < W) p1[1] = -a1[1];
+    }
+    if ((y & 3) == 0 && y + 3 < H && x + 3 < W) g2[(pl * H2 + (y >> 2)) * W2 + (x >> 2)] = -a2;
 }
 
 // out planes [base+G+g] and [base+2G+g] <- bilinear_align_corners(G1), (G2)   (block_cost.py:74)
@@ -230,14 +275,6 @@ static inline float host_ac_scale(int in_size, int out_size) {
     return out_size > 1 ? (float)(in_size - 1) / (float)(out_size - 1) : 0.0f;   // IEEE fp32 divide == __fdiv_rn
 }
 
-template <bool WARP, int SC>
-static void launch_main(const float* L, const float* R, const float* smp, float* out, float* g1, float* g2, int B,
-                        int C, int H, int W, int D, cudaStream_t st) {
-    const int nchunk = cdiv(D, SC);
-    dim3 grid(cdiv(W, 32), cdiv(H, 8), B * (C / 8) * nchunk);
-    block_cost_main_kernel<WARP, SC><<<grid, 256, 0, st>>>(L, R, smp, out, g1, g2, C, H, W, D, nchunk);
-}
-
 static int block_cost_launch(bool warp, const float* L, const float* R, const float* smp, float* out,
                              float* scratch, int B, int C, int H, int W, int D, cudaStream_t st) {
     TS_REQUIRE(L && R && out && scratch, "block_cost: null pointer");
@@ -245,26 +282,18 @@ static int block_cost_launch(bool warp, const float* L, const float* R, const fl
     TS_REQUIRE(B > 0 && D > 0 && C > 0 && C % 8 == 0, "block_cost: C=%d must be a positive multiple of 8 (B=%d D=%d)", C, B, D);
     TS_REQUIRE(H >= 4 && W >= 4, "block_cost: H=%d W=%d must be >= 4 for the three pooled scales", H, W);
     const int G = C / 8;
-    // candidates per thread: the chunk size that wastes the fewest slots (5 -> 5, 8 -> 4+4, 12 -> 6+6, 16 -> 4x4, 20 -> 4x5)
-    int SC = 4, waste = cdiv(D, 4) * 4 - D;
-    for (int c = 5; c <= 6; ++c) {
-        const int w = cdiv(D, c) * c - D;
-        if (w < waste || (w == waste && cdiv(D, c) < cdiv(D, SC))) {
-            SC = c;
-            waste = w;
-        }
-    }
-    TS_REQUIRE((long long)B * G * cdiv(D, SC) <= 65535, "block_cost: B*C/8*chunks = %lld exceeds grid.z",
-               (long long)B * G * cdiv(D, SC));
-    TS_REQUIRE((long long)B * G * D <= 65535 && H <= 65535, "block_cost: B*C/8*D = %lld exceeds grid.z", (long long)B * G * D);
+    TS_REQUIRE((long long)B * G * D <= 65535 && H <= 65535 * 8, "block_cost: B*C/8*D = %lld exceeds grid.z", (long long)B * G * D);
+    TS_REQUIRE((long long)H * W < (1ll << 30), "block_cost: plane too large");
     const int H1 = H / 2, W1 = W / 2;
     float* g1 = scratch;
     float* g2 = scratch + (size_t)B * G * D * H1 * W1;
-#define TS_BC(WP, S_) launch_main<WP, S_>(L, R, smp, out, g1, g2, B, C, H, W, D, st)
+    const bool vec = (W % 4 == 0) && (((size_t)L | (size_t)out | (size_t)(smp ? smp : L)) & 15) == 0;
+    dim3 grid(cdiv(W, 64), cdiv(H, 8), B * G * D);
+#define TS_BC(WP, VC) block_cost_main_kernel<WP, VC><<<grid, 128, 0, st>>>(L, R, smp, out, g1, g2, C, H, W, D)
     if (warp) {
-        if (SC == 4) TS_BC(true, 4); else if (SC == 5) TS_BC(true, 5); else TS_BC(true, 6);
+        if (vec) TS_BC(true, true); else TS_BC(true, false);
     } else {
-        if (SC == 4) TS_BC(false, 4); else if (SC == 5) TS_BC(false, 5); else TS_BC(false, 6);
+        if (vec) TS_BC(false, true); else TS_BC(false, false);
     }
 #undef TS_BC
     int rc = check_launch("block_cost_main");
