@@ -21,6 +21,26 @@
 
 namespace tstereo {
 
+// Predicated read-only loads / stores as single instructions (no branch, so ptxas can hoist the next
+// channel's loads above the current channel's arithmetic and stores).
+__device__ __forceinline__ float ldg_if(const float* p, bool pred) {
+    float v;
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\tmov.f32 %0, 0f00000000;\n\t@q ld.global.nc.f32 %0, [%1];\n\t}"
+        : "=f"(v) : "l"(p), "r"((int)pred));
+    return v;
+}
+__device__ __forceinline__ float4 ldg4_if(const float* p, bool pred) {
+    float4 v;
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\tmov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\t"
+        "mov.f32 %2, 0f00000000;\n\tmov.f32 %3, 0f00000000;\n\t@q ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];\n\t}"
+        : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "r"((int)pred));
+    return v;
+}
+__device__ __forceinline__ void stg4_if(float* p, float a, float b, float c, float d, bool pred) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t@q st.global.v4.f32 [%0], {%1,%2,%3,%4};\n\t}"
+                 :: "l"(p), "f"(a), "f"(b), "f"(c), "f"(d), "r"((int)pred));
+}
+
 // VEC: W % 4 == 0 and 16 B aligned bases -> float4 loads / stores; otherwise scalar with tail guards.
 template <bool WARP, bool VEC>
 __global__ void __launch_bounds__(128)
@@ -119,40 +139,46 @@ block_cost_main_kernel(const float* __restrict__ L, const float* __restrict__ R,
     const size_t second = (size_t)C * D * HW;                            // offset of the R half (WARP)
     const size_t chs = (size_t)D * HW;                                    // channel stride in `out`
 
+    // taps that are actually read: inside the image AND on a blended row
+    bool t00[4], t01[4], t10[4], t11[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        t00[k] = v0[k] && row0;
+        t01[k] = v1[k] && row0;
+        t10[k] = v0[k] && row1;
+        t11[k] = v1[k] && row1;
+    }
+    const bool two_rows = WARP && __any_sync(0xffffffffu, row1);     // warp-uniform
+    const int r1off = row1 ? W : 0;                                    // keeps unread addresses in range
+
 #pragma unroll 2
     for (int c = 0; c < 8; ++c) {
         float l[4] = {0.f, 0.f, 0.f, 0.f}, rv[4] = {0.f, 0.f, 0.f, 0.f};
         if (VEC) {
-            if (pin[0]) {
-                const float4 t = __ldg(reinterpret_cast<const float4*>(Lp));
-                l[0] = t.x; l[1] = t.y; l[2] = t.z; l[3] = t.w;
-            }
+            const float4 t = ldg4_if(Lp, pin[0]);
+            l[0] = t.x; l[1] = t.y; l[2] = t.z; l[3] = t.w;
         } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (pin[k]) l[k] = __ldg(Lp + k);
+            for (int k = 0; k < 4; ++k) l[k] = ldg_if(Lp + k, pin[k]);
         }
         if (WARP) {
-            if (row0) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float ra = v0[k] ? __ldg(Rp + x0[k]) : 0.f;
-                    const float rb = v1[k] ? __ldg(Rp + x0[k] + 1) : 0.f;
-                    rv[k] = wy0 * fmaf(rb, w1[k], __fmul_rn(ra, w0[k]));
-                }
+            for (int k = 0; k < 4; ++k) {
+                const float ra = ldg_if(Rp + x0[k], t00[k]);
+                const float rb = ldg_if(Rp + x0[k] + 1, t01[k]);
+                rv[k] = wy0 * fmaf(rb, w1[k], __fmul_rn(ra, w0[k]));      // wy0 * 0 == 0 when row 0 is skipped
             }
-            if (row1) {
+            if (two_rows) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const float ra = v0[k] ? __ldg(Rp + W + x0[k]) : 0.f;
-                    const float rb = v1[k] ? __ldg(Rp + W + x0[k] + 1) : 0.f;
+                    const float ra = ldg_if(Rp + r1off + x0[k], t10[k]);
+                    const float rb = ldg_if(Rp + r1off + x0[k] + 1, t11[k]);
                     rv[k] = fmaf(wy1, fmaf(rb, w1[k], __fmul_rn(ra, w0[k])), rv[k]);
                 }
             }
         } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (v0[k]) rv[k] = __ldg(Rp + x0[k]);
+            for (int k = 0; k < 4; ++k) rv[k] = ldg_if(Rp + x0[k], t00[k]);
         }
         float e[4];
 #pragma unroll
@@ -161,13 +187,11 @@ block_cost_main_kernel(const float* __restrict__ L, const float* __restrict__ R,
             a0[k] = fmaf(e[k], e[k], a0[k]);
         }
         if (VEC) {
-            if (pin[0]) {
-                if (WARP) {
-                    *reinterpret_cast<float4*>(o1) = make_float4(l[0], l[1], l[2], l[3]);
-                    *reinterpret_cast<float4*>(o1 + second) = make_float4(rv[0], rv[1], rv[2], rv[3]);
-                } else {
-                    *reinterpret_cast<float4*>(o1) = make_float4(-(e[0] * e[0]), -(e[1] * e[1]), -(e[2] * e[2]), -(e[3] * e[3]));
-                }
+            if (WARP) {
+                stg4_if(o1, l[0], l[1], l[2], l[3], pin[0]);
+                stg4_if(o1 + second, rv[0], rv[1], rv[2], rv[3], pin[0]);
+            } else {
+                stg4_if(o1, -(e[0] * e[0]), -(e[1] * e[1]), -(e[2] * e[2]), -(e[3] * e[3]), pin[0]);
             }
         } else {
 #pragma unroll
