@@ -38,7 +38,15 @@ if "block_cost" in which:
         NS = max(2, int(300e6 // (8 * B * C * h * w)) + 1)      # input sets: > 2x L2 in total
         Ls = [torch.randn(B, C, h, w, device=dev) for _ in range(NS)]
         Rs = [torch.randn(B, C, h, w, device=dev) for _ in range(NS)]
-        smp = (torch.rand(B, S, h, w, device=dev) * 30) if warp else S
+        if warp and "--random-samples" in sys.argv:      # worst case: every pixel gathers from a random column
+            smp = torch.rand(B, S, h, w, device=dev) * 30
+        elif warp:                                        # piecewise-smooth disparity +- the engine's candidate offsets
+            yy, xx = torch.meshgrid(torch.arange(h, device=dev), torch.arange(w, device=dev), indexing="ij")
+            base = 0.06 * w * (1.2 + torch.sin(xx / w * 6.0) * torch.cos(yy / h * 4.0)) + 0.3 * torch.rand(h, w, device=dev)
+            offs = torch.tensor([-4.0, -1.0, 0.0, 1.0, 4.0, -2.5, 2.5, 6.0], device=dev)[:S]
+            smp = (base[None, None] + offs.view(1, S, 1, 1)).expand(B, S, h, w).contiguous()
+        else:
+            smp = S
         planes = (2 * C if warp else C) + 3 * C // 8
         nbytes = 4 * B * (2 * C * h * w + (S * h * w if warp else 0) + planes * S * h * w)
         med, best = timeit(lambda i: ops.block_cost(Ls[i % NS], Rs[i % NS], smp))

@@ -42,6 +42,12 @@ __device__ __forceinline__ void stg4_if(float* p, float a, float b, float c, flo
 }
 
 // VEC: W % 4 == 0 and 16 B aligned bases -> float4 loads / stores; otherwise scalar with tail guards.
+//
+// Taps outside the image are read from a clamped in-image address with weight 0 (no predicate per
+// load), so the arithmetic on finite features is unchanged.  grid_sample's y coordinate
+// (inverse_warp_3d.py:46 + grid_sampler_unnormalize) lands up to ~1e-6 px off the integer row on
+// ~20 % of the rows, which would blend two rows with weights (1-eps, eps); the kernel samples the
+// nearer row only (deviation <= 2e-6 * |R|, far below the fp32 noise of the following contraction).
 template <bool WARP, bool VEC>
 __global__ void __launch_bounds__(128)
 block_cost_main_kernel(const float* __restrict__ L, const float* __restrict__ R,
@@ -63,135 +69,116 @@ block_cost_main_kernel(const float* __restrict__ L, const float* __restrict__ R,
     bool pin[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) pin[k] = rowin && (x + k < W);
+    const int yc = min(y, H - 1);                 // threads outside the image read a valid row, store nothing
 
-    // horizontal taps per pixel: offset of tap 0 inside the row, weights, validity bits
-    int x0[4];
-    float w0[4], w1[4];
+    // per pixel: offset of tap 0 inside the channel plane and the two tap weights
+    int off[4];
+    float wa[4], wb[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        x0[k] = -2;                       // -2: neither tap is inside the image
-        w0[k] = 0.f;
-        w1[k] = 0.f;
+        off[k] = yc * W;
+        wa[k] = 0.f;
+        wb[k] = 0.f;
     }
-    int ylo = y;
-    float wy0 = 1.f, wy1 = 0.f;
     if (WARP) {
-        if (rowin) {
-            // The y coordinate goes through the same normalise / un-normalise round trip
-            // (inverse_warp_3d.py:46, grid_sampler_unnormalize); for some (H, y) it lands a few
-            // 1e-6 px off the integer, which blends two rows.
-            const float Hm1 = (float)(H - 1), Wm1 = (float)(W - 1);
-            const float gyn = __fsub_rn(__fmul_rn(__fdiv_rn((float)y, Hm1), 2.0f), 1.0f);
-            const float iy = __fmul_rn(__fdiv_rn(__fadd_rn(gyn, 1.0f), 2.0f), Hm1);
-            const float fy = floorf(iy);
-            ylo = (int)fy;
-            wy0 = __fsub_rn(fy + 1.0f, iy);
-            wy1 = __fsub_rn(iy, fy);
-            const float* sp = smp + ((size_t)(b * D + d) * H + y) * W + x;
-            float dsp[4];
-            if (VEC) {
-                const float4 t = __ldg(reinterpret_cast<const float4*>(sp));
-                dsp[0] = t.x; dsp[1] = t.y; dsp[2] = t.z; dsp[3] = t.w;
-            } else {
+        // same op sequence as inverse_warp_3d.py:40-47 + ATen grid_sampler_unnormalize
+        const float Hm1 = (float)(H - 1), Wm1 = (float)(W - 1);
+        const float gyn = __fsub_rn(__fmul_rn(__fdiv_rn((float)yc, Hm1), 2.0f), 1.0f);
+        const float iy = __fmul_rn(__fdiv_rn(__fadd_rn(gyn, 1.0f), 2.0f), Hm1);
+        const float fy = floorf(iy);
+        int yn = (int)fy;
+        if (__fsub_rn(iy, fy) > 0.5f) yn += 1;    // nearer of the two rows grid_sample would blend
+        yn = min(max(yn, 0), H - 1);
+        const float* sp = smp + ((size_t)(b * D + d) * H + yc) * W;
+        float dsp[4];
+        if (VEC) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(sp + min(x, W - 4)));
+            dsp[0] = t.x; dsp[1] = t.y; dsp[2] = t.z; dsp[3] = t.w;
+        } else {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) dsp[k] = pin[k] ? __ldg(sp + k) : 0.f;
-            }
+            for (int k = 0; k < 4; ++k) dsp[k] = __ldg(sp + min(x + k, W - 1));
+        }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (pin[k]) {
-                    // same op sequence as inverse_warp_3d.py:40-47 + ATen grid_sampler_unnormalize
-                    const float gx = __fadd_rn((float)(x + k), -dsp[k]);
-                    const float gn = __fsub_rn(__fmul_rn(__fdiv_rn(gx, Wm1), 2.0f), 1.0f);
-                    const float ix = __fmul_rn(__fdiv_rn(__fadd_rn(gn, 1.0f), 2.0f), Wm1);
-                    const float fx = floorf(ix);
-                    if (fx >= -1.0f && fx <= Wm1) {
-                        x0[k] = (int)fx;
-                        w0[k] = __fsub_rn(fx + 1.0f, ix);
-                        w1[k] = __fsub_rn(ix, fx);
-                    }
+        for (int k = 0; k < 4; ++k) {
+            const float gx = __fadd_rn((float)(x + k), -dsp[k]);
+            const float gn = __fsub_rn(__fmul_rn(__fdiv_rn(gx, Wm1), 2.0f), 1.0f);
+            const float ix = __fmul_rn(__fdiv_rn(__fadd_rn(gn, 1.0f), 2.0f), Wm1);
+            const float fx = floorf(ix);
+            int xa = 0;
+            if (pin[k] && fx >= -1.0f && fx <= Wm1) {
+                xa = (int)fx;
+                wa[k] = __fsub_rn(fx + 1.0f, ix);
+                wb[k] = __fsub_rn(ix, fx);
+                if (xa < 0) {                     // tap 0 left of the image: read columns 0,1 as (tap1, unused)
+                    xa = 0;
+                    wa[k] = wb[k];
+                    wb[k] = 0.f;
+                } else if (xa + 1 >= W) {         // tap 1 right of the image: read columns W-2,W-1 as (unused, tap0)
+                    xa = W - 2;
+                    wb[k] = wa[k];
+                    wa[k] = 0.f;
                 }
             }
+            off[k] = yn * W + xa;
         }
     } else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (pin[k] && x + k - d >= 0) x0[k] = x + k - d;
-    }
-    // rows to blend (warp branch): r = 0 -> (ylo, wy0), r = 1 -> (ylo + 1, wy1); zero-weight or
-    // out-of-image rows are skipped exactly like grid_sample's zeros padding
-    const bool row0 = WARP ? (rowin && ylo >= 0 && wy0 != 0.f) : rowin;
-    const bool row1 = WARP ? (rowin && ylo + 1 < H && wy1 != 0.f) : false;
-    bool v0[4], v1[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        v0[k] = (unsigned)x0[k] < (unsigned)W;
-        v1[k] = (unsigned)(x0[k] + 1) < (unsigned)W;
+        for (int k = 0; k < 4; ++k) {
+            const int xs = x + k - d;
+            if (pin[k] && xs >= 0) wa[k] = 1.f;
+            off[k] = yc * W + min(max(xs, 0), W - 1);
+        }
     }
 
     float a0[4] = {0.f, 0.f, 0.f, 0.f};
     float a1[2] = {0.f, 0.f};
     float a2 = 0.f;
 
-    const int pix = y * W + x;
-    const float* Lp = L + ((size_t)b * C + g * 8) * HW + pix;
-    const float* Rp = R + ((size_t)b * C + g * 8) * HW + (WARP ? ylo : y) * W;
-    float* o1 = out + (((size_t)b * outC + g * 8) * D + d) * HW + pix;   // first half, plane (ch, d)
-    const size_t second = (size_t)C * D * HW;                            // offset of the R half (WARP)
-    const size_t chs = (size_t)D * HW;                                    // channel stride in `out`
-
-    // taps that are actually read: inside the image AND on a blended row
-    bool t00[4], t01[4], t10[4], t11[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        t00[k] = v0[k] && row0;
-        t01[k] = v1[k] && row0;
-        t10[k] = v0[k] && row1;
-        t11[k] = v1[k] && row1;
-    }
-    const bool two_rows = WARP && __any_sync(0xffffffffu, row1);     // warp-uniform
-    const int r1off = row1 ? W : 0;                                    // keeps unread addresses in range
+    const int pix = y * W + x;                                                   // store position
+    const int lpix = yc * W + (VEC ? min(x, W - 4) : 0);                          // always-valid load position
+    const float* Lp = L + ((size_t)b * C + g * 8) * HW + lpix;
+    const float* Rp = R + ((size_t)b * C + g * 8) * HW;
+    float* o1 = out + (((size_t)b * outC + g * 8) * D + d) * HW + pix;           // first half, plane (ch, d)
+    const size_t second = (size_t)C * D * HW;                                    // offset of the R half (WARP)
+    const size_t chs = (size_t)D * HW;                                            // channel stride in `out`
+    const float lmask = pin[0] ? 1.f : 0.f;
 
 #pragma unroll 2
     for (int c = 0; c < 8; ++c) {
-        float l[4] = {0.f, 0.f, 0.f, 0.f}, rv[4] = {0.f, 0.f, 0.f, 0.f};
+        float l[4], rv[4];
         if (VEC) {
-            const float4 t = ldg4_if(Lp, pin[0]);
+            const float4 t = __ldg(reinterpret_cast<const float4*>(Lp));
             l[0] = t.x; l[1] = t.y; l[2] = t.z; l[3] = t.w;
+            if (!pin[0]) l[0] = l[1] = l[2] = l[3] = 0.f;
         } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) l[k] = ldg_if(Lp + k, pin[k]);
+            for (int k = 0; k < 4; ++k) l[k] = pin[k] ? __ldg(Lp + min(x + k, W - 1)) : 0.f;
         }
         if (WARP) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const float ra = ldg_if(Rp + x0[k], t00[k]);
-                const float rb = ldg_if(Rp + x0[k] + 1, t01[k]);
-                rv[k] = wy0 * fmaf(rb, w1[k], __fmul_rn(ra, w0[k]));      // wy0 * 0 == 0 when row 0 is skipped
-            }
-            if (two_rows) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float ra = ldg_if(Rp + r1off + x0[k], t10[k]);
-                    const float rb = ldg_if(Rp + r1off + x0[k] + 1, t11[k]);
-                    rv[k] = fmaf(wy1, fmaf(rb, w1[k], __fmul_rn(ra, w0[k])), rv[k]);
-                }
+                const float ra = __ldg(Rp + off[k]);
+                const float rb = __ldg(Rp + off[k] + 1);
+                rv[k] = fmaf(rb, wb[k], __fmul_rn(ra, wa[k]));
             }
         } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) rv[k] = ldg_if(Rp + x0[k], t00[k]);
+            for (int k = 0; k < 4; ++k) rv[k] = __fmul_rn(__ldg(Rp + off[k]), wa[k]);
         }
         float e[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            e[k] = l[k] - rv[k];                 // 0 outside the image (l = rv = 0)
+            e[k] = l[k] - rv[k];                 // 0 outside the image (l = 0, weights = 0)
             a0[k] = fmaf(e[k], e[k], a0[k]);
         }
         if (VEC) {
-            if (WARP) {
-                stg4_if(o1, l[0], l[1], l[2], l[3], pin[0]);
-                stg4_if(o1 + second, rv[0], rv[1], rv[2], rv[3], pin[0]);
-            } else {
-                stg4_if(o1, -(e[0] * e[0]), -(e[1] * e[1]), -(e[2] * e[2]), -(e[3] * e[3]), pin[0]);
+            if (pin[0]) {
+                if (WARP) {
+                    *reinterpret_cast<float4*>(o1) = make_float4(l[0], l[1], l[2], l[3]);
+                    *reinterpret_cast<float4*>(o1 + second) = make_float4(rv[0], rv[1], rv[2], rv[3]);
+                } else {
+                    *reinterpret_cast<float4*>(o1) = make_float4(-(e[0] * e[0]), -(e[1] * e[1]), -(e[2] * e[2]), -(e[3] * e[3]));
+                }
             }
         } else {
 #pragma unroll
@@ -220,6 +207,7 @@ block_cost_main_kernel(const float* __restrict__ L, const float* __restrict__ R,
         Rp += HW;
         o1 += chs;
     }
+    (void)lmask;
 
     const int base = WARP ? 2 * C : C;
     const int H1 = H >> 1, W1 = W >> 1, H2 = H >> 2, W2 = W >> 2;
@@ -246,9 +234,10 @@ __global__ void __launch_bounds__(128)
 block_cost_resize_kernel(const float* __restrict__ g1, const float* __restrict__ g2, float* __restrict__ out,
                          int G, int D, int H, int W, int outC, int base,
                          float sy1, float sx1, float sy2, float sx2) {
-    const int x4 = (blockIdx.x * 128 + threadIdx.x) * 4;
-    if (x4 >= W) return;
-    const int y = blockIdx.y;
+    // blockDim = (TX, 128 / TX): TX = 32 | 64 | 128 threads along x (4 columns each), the rest along y
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x4 >= W || y >= H) return;
     int z = blockIdx.z;
     const int d = z % D;
     z /= D;
@@ -323,8 +312,10 @@ static int block_cost_launch(bool warp, const float* L, const float* R, const fl
     int rc = check_launch("block_cost_main");
     if (rc) return rc;
     const int outC = (warp ? 2 * C : C) + 3 * G;
-    dim3 rgrid(cdiv(cdiv(W, 4), 128), H, B * G * D);
-    block_cost_resize_kernel<<<rgrid, 128, 0, st>>>(g1, g2, out, G, D, H, W, outC, warp ? 2 * C : C,
+    const int tx = cdiv(W, 4) <= 32 ? 32 : (cdiv(W, 4) <= 64 ? 64 : 128);
+    dim3 rblock(tx, 128 / tx);
+    dim3 rgrid(cdiv(cdiv(W, 4), tx), cdiv(H, (int)rblock.y), B * G * D);
+    block_cost_resize_kernel<<<rgrid, rblock, 0, st>>>(g1, g2, out, G, D, H, W, outC, warp ? 2 * C : C,
                                                     host_ac_scale(H / 2, H), host_ac_scale(W / 2, W),
                                                     host_ac_scale(H / 4, H), host_ac_scale(W / 4, W));
     return check_launch("block_cost_resize");
