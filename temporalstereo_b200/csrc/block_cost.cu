@@ -143,7 +143,11 @@ block_cost_main_kernel(const float* __restrict__ L, const float* __restrict__ R,
     const size_t chs = (size_t)D * HW;                                            // channel stride in `out`
     const float lmask = pin[0] ? 1.f : 0.f;
 
-#pragma unroll 2
+#ifndef TS_BC_UNROLL
+#define TS_BC_UNROLL 8
+#endif
+    constexpr int kUnroll = TS_BC_UNROLL;     // channels whose loads are in flight together
+#pragma unroll kUnroll
     for (int c = 0; c < 8; ++c) {
         float l[4], rv[4];
         if (VEC) {
@@ -229,7 +233,8 @@ block_cost_main_kernel(const float* __restrict__ L, const float* __restrict__ R,
 }
 
 // out planes [base+G+g] and [base+2G+g] <- bilinear_align_corners(G1), (G2)   (block_cost.py:74)
-// thread = 4 consecutive output columns of one row of one (b, g, d) plane.
+// thread = 4 consecutive output columns of one row; the align_corners index / weight math is done
+// once per thread and reused for all D candidate planes of the (b, g) group.
 __global__ void __launch_bounds__(128)
 block_cost_resize_kernel(const float* __restrict__ g1, const float* __restrict__ g2, float* __restrict__ out,
                          int G, int D, int H, int W, int outC, int base,
@@ -238,49 +243,68 @@ block_cost_resize_kernel(const float* __restrict__ g1, const float* __restrict__
     const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x4 >= W || y >= H) return;
-    int z = blockIdx.z;
-    const int d = z % D;
-    z /= D;
-    const int g = z % G;
-    const int b = z / G;
+    const int g = blockIdx.z % G;
+    const int b = blockIdx.z / G;
     const int H1 = H >> 1, W1 = W >> 1, H2 = H >> 2, W2 = W >> 2;
-    const size_t HW = (size_t)H * W;
-    const size_t pl = ((size_t)b * G + g) * D + d;
-    const float* p1 = g1 + pl * (size_t)H1 * W1;
-    const float* p2 = g2 + pl * (size_t)H2 * W2;
-    float* o1 = out + (((size_t)b * outC + base + G + g) * D + d) * HW + (size_t)y * W + x4;
-    float* o2 = out + (((size_t)b * outC + base + 2 * G + g) * D + d) * HW + (size_t)y * W + x4;
+    const int HW = H * W, P1 = H1 * W1, P2 = H2 * W2;
     const LerpIdx iy1 = ac_index(sy1, y, H1), iy2 = ac_index(sy2, y, H2);
-    const float* r10 = p1 + (size_t)iy1.i0 * W1;
-    const float* r11 = p1 + (size_t)iy1.i1 * W1;
-    const float* r20 = p2 + (size_t)iy2.i0 * W2;
-    const float* r21 = p2 + (size_t)iy2.i1 * W2;
-    float v1[4], v2[4];
+    // per column: offsets of the 4 source texels (relative to the plane) and the x weight
+    int o1a[4], o1b[4], o2a[4], o2b[4];       // row i0: (a, a + d1), row i1: (b, b + d1)
+    int d1[4], d2[4];
+    float wx1[4], wx2[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int x = min(x4 + k, W - 1);
-        const LerpIdx ix1 = ac_index(sx1, x, W1), ix2 = ac_index(sx2, x, W2);
-        {
-            const float t0 = ix1.w0 * __ldg(r10 + ix1.i0) + ix1.w1 * __ldg(r10 + ix1.i1);
-            const float t1 = ix1.w0 * __ldg(r11 + ix1.i0) + ix1.w1 * __ldg(r11 + ix1.i1);
-            v1[k] = iy1.w0 * t0 + iy1.w1 * t1;
-        }
-        {
-            const float t0 = ix2.w0 * __ldg(r20 + ix2.i0) + ix2.w1 * __ldg(r20 + ix2.i1);
-            const float t1 = ix2.w0 * __ldg(r21 + ix2.i0) + ix2.w1 * __ldg(r21 + ix2.i1);
-            v2[k] = iy2.w0 * t0 + iy2.w1 * t1;
-        }
+        const LerpIdx i1 = ac_index(sx1, x, W1), i2 = ac_index(sx2, x, W2);
+        o1a[k] = iy1.i0 * W1 + i1.i0;
+        o1b[k] = iy1.i1 * W1 + i1.i0;
+        d1[k] = i1.i1 - i1.i0;
+        wx1[k] = i1.w1;
+        o2a[k] = iy2.i0 * W2 + i2.i0;
+        o2b[k] = iy2.i1 * W2 + i2.i0;
+        d2[k] = i2.i1 - i2.i0;
+        wx2[k] = i2.w1;
     }
-    if ((W & 3) == 0) {
-        *reinterpret_cast<float4*>(o1) = make_float4(v1[0], v1[1], v1[2], v1[3]);
-        *reinterpret_cast<float4*>(o2) = make_float4(v2[0], v2[1], v2[2], v2[3]);
-    } else {
+    const size_t pl = ((size_t)b * G + g) * D;
+    const float* p1 = g1 + pl * P1;
+    const float* p2 = g2 + pl * P2;
+    float* q1 = out + (((size_t)b * outC + base + G + g) * D) * HW + (size_t)y * W + x4;
+    float* q2 = out + (((size_t)b * outC + base + 2 * G + g) * D) * HW + (size_t)y * W + x4;
+    const bool vec = (W & 3) == 0;
+    for (int d = 0; d < D; ++d) {
+        float v1[4], v2[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (x4 + k < W) {
-                o1[k] = v1[k];
-                o2[k] = v2[k];
+        for (int k = 0; k < 4; ++k) {
+            {
+                const float a0 = __ldg(p1 + o1a[k]), a1 = __ldg(p1 + o1a[k] + d1[k]);
+                const float b0 = __ldg(p1 + o1b[k]), b1 = __ldg(p1 + o1b[k] + d1[k]);
+                const float t0 = (1.0f - wx1[k]) * a0 + wx1[k] * a1;
+                const float t1 = (1.0f - wx1[k]) * b0 + wx1[k] * b1;
+                v1[k] = iy1.w0 * t0 + iy1.w1 * t1;
             }
+            {
+                const float a0 = __ldg(p2 + o2a[k]), a1 = __ldg(p2 + o2a[k] + d2[k]);
+                const float b0 = __ldg(p2 + o2b[k]), b1 = __ldg(p2 + o2b[k] + d2[k]);
+                const float t0 = (1.0f - wx2[k]) * a0 + wx2[k] * a1;
+                const float t1 = (1.0f - wx2[k]) * b0 + wx2[k] * b1;
+                v2[k] = iy2.w0 * t0 + iy2.w1 * t1;
+            }
+        }
+        if (vec) {
+            *reinterpret_cast<float4*>(q1) = make_float4(v1[0], v1[1], v1[2], v1[3]);
+            *reinterpret_cast<float4*>(q2) = make_float4(v2[0], v2[1], v2[2], v2[3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (x4 + k < W) {
+                    q1[k] = v1[k];
+                    q2[k] = v2[k];
+                }
+        }
+        p1 += P1;
+        p2 += P2;
+        q1 += HW;
+        q2 += HW;
     }
 }
 
@@ -314,7 +338,7 @@ static int block_cost_launch(bool warp, const float* L, const float* R, const fl
     const int outC = (warp ? 2 * C : C) + 3 * G;
     const int tx = cdiv(W, 4) <= 32 ? 32 : (cdiv(W, 4) <= 64 ? 64 : 128);
     dim3 rblock(tx, 128 / tx);
-    dim3 rgrid(cdiv(cdiv(W, 4), tx), cdiv(H, (int)rblock.y), B * G * D);
+    dim3 rgrid(cdiv(cdiv(W, 4), tx), cdiv(H, (int)rblock.y), B * G);
     block_cost_resize_kernel<<<rgrid, rblock, 0, st>>>(g1, g2, out, G, D, H, W, outC, warp ? 2 * C : C,
                                                     host_ac_scale(H / 2, H), host_ac_scale(W / 2, W),
                                                     host_ac_scale(H / 4, H), host_ac_scale(W / 4, W));
