@@ -269,36 +269,46 @@ def main():
         ms_e2e = float(t.item())
     fps_e2e = world * B * a.steps / (ms_e2e * 1e-3)
 
-    # ---- roofline of the cost-volume kernels (the three block_cost calls of one step), timed alone
+    # ---- roofline of the cost-volume operator (block_cost: the path north_star sets the HBM target on).
+    #      Dominant launch = the precise-level volume (198 of the 329 MB/frame); the three-level total
+    #      is reported beside it.  Candidates are the engine's own pattern: a piecewise-smooth disparity
+    #      +- {4,1,0} (a trained network regresses smooth maps; random-init weights do not).
     peak, peak_src = peaks()
-    lcat = torch.randn(B, 128, H // 4, W // 4, device=dev)
-    rcat = torch.randn(B, 128, H // 4, W // 4, device=dev)
-    smp4 = torch.rand(B, 5, H // 4, W // 4, device=dev) * 40
-    l8, r8 = sets[0][1], sets[0][4]
-    smp8 = torch.rand(B, 5, H // 8, W // 8, device=dev) * 20
-    l16, r16 = sets[0][2], sets[0][5]
 
-    def cost_volumes():
-        ops.block_cost(l16, r16, 12)
-        ops.block_cost(l8, r8, smp8)
-        ops.block_cost(lcat, rcat, smp4)
+    def smooth_samples(h, w, S):
+        yy, xx = torch.meshgrid(torch.arange(h, device=dev), torch.arange(w, device=dev), indexing="ij")
+        base = 0.06 * w * (1.2 + torch.sin(xx / w * 6.0) * torch.cos(yy / h * 4.0)) + 0.3 * torch.rand(h, w, device=dev)
+        offs = torch.tensor([-4.0, -1.0, 0.0, 1.0, 4.0], device=dev)[:S]
+        return (base[None, None] + offs.view(1, S, 1, 1)).expand(B, S, h, w).contiguous()
 
-    def vol_bytes(C, h, w, S, planes):
-        return 4 * B * (2 * C * h * w + S * h * w + planes * S * h * w)
+    nrot = max(2, -(-2 * L2_BYTES // (8 * B * 128 * (H // 4) * (W // 4))))
+    lcat = [torch.randn(B, 128, H // 4, W // 4, device=dev) for _ in range(nrot)]
+    rcat = [torch.randn(B, 128, H // 4, W // 4, device=dev) for _ in range(nrot)]
+    smp4, smp8 = smooth_samples(H // 4, W // 4, 5), smooth_samples(H // 8, W // 8, 5)
 
-    alg_bytes = (4 * B * (2 * 256 * (H // 16) * (W // 16) + 352 * 12 * (H // 16) * (W // 16))
-                 + vol_bytes(128, H // 8, W // 8, 5, 304) + vol_bytes(128, H // 4, W // 4, 5, 304))
-    for _ in range(3):
-        cost_volumes()
-    torch.cuda.synchronize()
-    reps = max(5, min(a.steps, 20))
-    e0.record()
-    for _ in range(reps):
-        cost_volumes()
-    e1.record()
-    torch.cuda.synchronize()
-    cv_ms = e0.elapsed_time(e1) / reps
-    achieved = alg_bytes / (cv_ms * 1e-3) / 1e9
+    def timed(fn, reps):
+        for i in range(3):
+            fn(i)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(reps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    def vol_bytes(C, h, w, S, planes, warp=True):
+        return 4 * B * (2 * C * h * w + (S * h * w if warp else 0) + planes * S * h * w)
+
+    reps = max(10, min(a.steps, 50))
+    b_p = vol_bytes(128, H // 4, W // 4, 5, 304)
+    b_f = vol_bytes(128, H // 8, W // 8, 5, 304)
+    b_c = vol_bytes(256, H // 16, W // 16, 12, 352, warp=False)
+    ms_p = timed(lambda i: ops.block_cost(lcat[i % nrot], rcat[i % nrot], smp4), reps)
+    ms_f = timed(lambda i: ops.block_cost(sets[i % nsets][1], sets[i % nsets][4], smp8), reps)
+    ms_c = timed(lambda i: ops.block_cost(sets[i % nsets][2], sets[i % nsets][5], 12), reps)
+    achieved = b_p / (ms_p * 1e-3) / 1e9
+    cv_ms, alg_bytes = ms_p + ms_f + ms_c, b_p + b_f + b_c
 
     result = {
         "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
@@ -312,9 +322,13 @@ def main():
         "e2e": {"value": fps_e2e, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": B * H * W * 4,
                 "ms_per_step": ms_e2e / a.steps},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "block_cost (3 cost volumes of one step: main + resize kernels)",
+        "roofline": {"bound": "hbm",
+                     "kernel": "block_cost_warp at the precise level (block_cost_main_kernel<1,1> + block_cost_resize_kernel)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes": alg_bytes, "ms": cv_ms,
+                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes": b_p, "ms": ms_p,
+                     "all_three_levels": {"algorithmic_bytes": alg_bytes, "ms": cv_ms,
+                                          "achieved": alg_bytes / (cv_ms * 1e-3) / 1e9,
+                                          "frac": alg_bytes / (cv_ms * 1e-3) / 1e9 / peak},
                      "share_of_step": cv_ms / (ms / a.steps)},
     }
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
