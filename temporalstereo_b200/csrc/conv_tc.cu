@@ -1,0 +1,351 @@
+// Tensor-core (tcgen05, sm_100a) implicit-GEMM 3x3 convolution over (H,W), stride 1, dilation 1|2 —
+// the weight contractions of the aggregation.
+//
+// ref: architecture/modeling/layers/basic_layers.py:194-235 (Conv3d: conv -> BN -> act) as used by the
+//      (1,3,3) halves of aggregation/TemporalStereo/module.py:111-147 and the 2-D convs of :300-353, 424-492.
+//
+// Precision: plain TF32 moves the regressed disparity by 0.7 px, so every product is
+// error-compensated "3xTF32": a = a_hi + a_lo (both exactly representable in tf32), and
+// D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi with fp32 accumulation in TMEM (~21 operand bits).
+//
+// GEMM view of one (b, d) plane:  M = padded-linear pixel position q = y*PW + x with pitch PW = W + DIL
+// (the DIL zero columns after each row serve as right padding of row y and left padding of row y+1),
+// N = Cout (rounded up to 16), K = 8-channel chunks x 9 taps.  A tap (ky,kx) is the SAME staged tile
+// read at a start-address offset of (ky*DIL*PW + kx*DIL) positions, because the tile is staged K-major
+// with 16 B per (position, 4 channels):  smem A[part][khalf][position][4 ch]  — UMMA canonical K-major
+// SWIZZLE_NONE layout with SBO = 128 B (8 positions x 16 B, dense) and LBO = NPOS*16 B.
+//
+//  warps 0-7 : producers — global NCHW fp32 -> registers (4 channel loads per K-half) -> hi/lo split ->
+//              one 16 B st.shared per (position, K-half, part); thread 0 also bulk-copies the chunk's
+//              pre-split weights (cp.async.bulk + mbarrier complete_tx).  Afterwards: epilogue
+//              (tcgen05.ld -> bias -> activation -> coalesced NCHW stores).
+//  warp 8    : TMEM alloc/dealloc; one elected lane issues MT x 9 x 3 tcgen05.mma per chunk and
+//              tcgen05.commit's the stage back to the producers.
+#include "common.cuh"
+#include <cstdint>
+
+namespace tstereo {
+namespace tc {
+
+constexpr int NPROD = 256;             // producer threads (8 warps)
+constexpr int NTHREADS = NPROD + 32;   // + MMA warp
+constexpr int MAX_STAGES = 4;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, M = 128
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;      // descriptor version (Blackwell)
+    return d;                    // base_offset 0, lbo_mode 0, layout_type 0 = SWIZZLE_NONE
+}
+__device__ __forceinline__ uint32_t f2tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+struct Params {
+    const float* in;
+    long long isB, isC, isD;
+    float* out;
+    long long osB, osC, osD;
+    const float* wpack;     // [nchunk][part 2][tap 9][khalf 2][N][4]
+    const float* bias;      // [Cout] or null
+    int Cin, Cout, D, H, W;
+    int dil, PW, MT, NPOS, halo, nchunk, stages, act;
+    int tiles_per_plane;
+};
+
+template <int N>
+__global__ void __launch_bounds__(NTHREADS, 1) conv_hw3_tc_kernel(const Params p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    // layout: [stages] x { A: part(2) x khalf(2) x NPOS x 16 B | B: 2 x 9 x 2 x N x 16 B } | pos table | barriers
+    const uint32_t a_bytes = 4u * p.NPOS * 16u;
+    const uint32_t b_bytes = 2u * 9u * 2u * N * 16u;
+    const uint32_t stage_bytes = a_bytes + b_bytes;
+    int* pos_tbl = reinterpret_cast<int*>(smem + (size_t)p.stages * stage_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes + (((size_t)p.NPOS * 4 + 15) & ~(size_t)15));
+    uint64_t* full = bars;                       // [stages]
+    uint64_t* empty = bars + MAX_STAGES;         // [stages]
+    uint64_t* accum_full = bars + 2 * MAX_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int plane = blockIdx.y;
+    const int b = plane / p.D, d = plane % p.D;
+    const int q0 = blockIdx.x * p.MT * 128;                   // first padded-linear output position of this CTA
+    const float* in_pl = p.in + (long long)b * p.isB + (long long)d * p.isD;
+    uint32_t ncols = 32;                                       // TMEM columns: MT * N rounded up to a power of two
+    while (ncols < (uint32_t)(p.MT * N)) ncols <<= 1;
+
+    if (tid == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full[s], NPROD + 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(accum_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == NPROD / 32) {   // MMA warp allocates TMEM
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // position table: offset of padded-linear position (q0 - halo + i) inside the plane, or -1 (zero)
+    for (int i = tid; i < p.NPOS; i += NTHREADS) {
+        const int q = q0 - p.halo + i;
+        int off = -1;
+        if (q >= 0) {
+            const int y = q / p.PW, x = q - y * p.PW;
+            if (y < p.H && x < p.W) off = y * p.W + x;
+        }
+        pos_tbl[i] = off;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < NPROD / 32) {
+        // ===================== producers =====================
+        for (int k = 0; k < p.nchunk; ++k) {
+            const int s = k % p.stages;
+            const uint32_t ph = (uint32_t)(k / p.stages) & 1u;
+            mbar_wait(&empty[s], ph ^ 1u);
+            uint8_t* st_base = smem + (size_t)s * stage_bytes;
+            if (tid == 0) {
+                mbar_arrive_expect_tx(&full[s], b_bytes);
+                bulk_g2s(st_base + a_bytes, p.wpack + (size_t)k * (b_bytes / 4), b_bytes, &full[s]);
+            }
+            const uint32_t a_hi = smem_u32(st_base);                        // part 0 (hi): khalf 0, khalf 1
+            const uint32_t a_lo = a_hi + 2u * p.NPOS * 16u;                // part 1 (lo)
+            const uint32_t half = (uint32_t)p.NPOS * 16u;
+            const int c0 = k * 8;
+            const float* src = in_pl + (long long)c0 * p.isC;
+#pragma unroll 2
+            for (int i = tid; i < p.NPOS; i += NPROD) {
+                const int off = pos_tbl[i];
+                float v[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) v[c] = (off >= 0 && c0 + c < p.Cin) ? __ldg(src + (long long)c * p.isC + off) : 0.f;
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    hi[c] = f2tf32(v[c]);
+                    lo[c] = f2tf32(v[c] - __uint_as_float(hi[c]));
+                }
+                const uint32_t o = (uint32_t)i * 16u;
+                sts128(a_hi + o, hi[0], hi[1], hi[2], hi[3]);
+                sts128(a_hi + half + o, hi[4], hi[5], hi[6], hi[7]);
+                sts128(a_lo + o, lo[0], lo[1], lo[2], lo[3]);
+                sts128(a_lo + half + o, lo[4], lo[5], lo[6], lo[7]);
+            }
+            fence_proxy_async();          // generic-proxy st.shared -> visible to the tensor core (async proxy)
+            mbar_arrive(&full[s]);
+        }
+        // ===================== epilogue =====================
+        mbar_wait(accum_full, 0);
+        tc_fence_after();
+        const int quarter = warp & 3;                 // TMEM lanes this warp may read
+        const size_t HWp = (size_t)p.H * p.W;
+        float* out_pl = p.out + (long long)b * p.osB + (long long)d * p.osD;
+        for (int j = warp >> 2; j < p.MT; j += 2) {
+            const int q = q0 + j * 128 + quarter * 32 + lane;
+            const int y = q / p.PW, x = q - y * p.PW;
+            const bool ok = (y < p.H) && (x < p.W);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(j * N);
+#pragma unroll
+            for (int c0 = 0; c0 < N; c0 += 16) {
+                uint32_t r[16];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                      "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                    : "r"(taddr + (uint32_t)c0));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (ok) {
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        const int co = c0 + c;
+                        if (co < p.Cout) {
+                            const float bv = p.bias ? __ldg(p.bias + co) : 0.f;
+                            out_pl[(long long)co * p.osC + (size_t)y * p.W + x] = apply_act(__uint_as_float(r[c]) + bv, p.act);
+                        }
+                    }
+                }
+            }
+        }
+        (void)HWp;
+        tc_fence_before();
+    } else {
+        // ===================== MMA issuer =====================
+        // instruction descriptor: D fp32, A/B tf32, both K-major, N, M = 128
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t a_lbo = (uint32_t)p.NPOS * 16u, b_lbo = (uint32_t)N * 16u;
+        for (int k = 0; k < p.nchunk; ++k) {
+            const int s = k % p.stages;
+            const uint32_t ph = (uint32_t)(k / p.stages) & 1u;
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t st_base = smem_u32(smem + (size_t)s * stage_bytes);
+                const uint32_t a_part[2] = {st_base, st_base + 2u * p.NPOS * 16u};
+                const uint32_t b_base = st_base + a_bytes;
+                for (int j = 0; j < p.MT; ++j) {
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(j * N);
+                    const uint32_t a_row0 = (uint32_t)(p.halo + j * 128) * 16u;
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) {
+                        const int ky = t / 3 - 1, kx = t % 3 - 1;
+                        const int toff = (ky * p.dil * p.PW + kx * p.dil) * 16;
+#pragma unroll
+                        for (int term = 0; term < 3; ++term) {
+                            const int pa = (term == 0) ? 1 : 0;      // lo*hi, hi*lo, hi*hi (small terms first)
+                            const int pb = (term == 1) ? 1 : 0;
+                            const uint64_t ad = make_desc(a_part[pa] + a_row0 + toff, a_lbo, 128u);
+                            const uint64_t bd = make_desc(b_base + (uint32_t)((pb * 9 + t) * 2 * N * 16), b_lbo, 128u);
+                            tc_mma_tf32(d_tmem, ad, bd, idesc, (k | t | term) != 0 ? 1u : 0u);
+                        }
+                    }
+                }
+                tc_commit(&empty[s]);                         // stage free once these MMAs have read it
+                if (k == p.nchunk - 1) tc_commit(accum_full);  // accumulators complete
+            }
+            __syncwarp();
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == NPROD / 32) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+    }
+}
+
+}  // namespace tc
+}  // namespace tstereo
+
+using namespace tstereo;
+
+extern "C" {
+
+long long tstereo_conv_hw3_tc_wpack_floats(int Cin, int Cout) {
+    const long long N = (Cout + 15) / 16 * 16, nchunk = (Cin + 7) / 8;
+    return nchunk * 2 * 9 * 2 * N * 4;
+}
+
+int tstereo_conv_hw3_tc(const float* in, long long isB, long long isC, long long isD,
+                        float* out, long long osB, long long osC, long long osD,
+                        const float* wpack, const float* bias,
+                        int B, int Cin, int Cout, int D, int H, int W,
+                        int dilation, int act, void* stream) {
+    TS_REQUIRE(in && out && wpack, "conv_hw3_tc: null pointer");
+    TS_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && Cout <= 64 && D > 0 && H > 0 && W > 0, "conv_hw3_tc: bad sizes (Cout <= 64)");
+    TS_REQUIRE(dilation == 1 || dilation == 2, "conv_hw3_tc: dilation %d unsupported", dilation);
+    TS_REQUIRE((long long)B * D <= 65535, "conv_hw3_tc: B*D exceeds grid.y");
+    TS_REQUIRE((((size_t)wpack) & 15) == 0, "conv_hw3_tc: packed weights must be 16-byte aligned");
+    const int N = (Cout + 15) / 16 * 16;
+    tc::Params p;
+    p.in = in; p.isB = isB; p.isC = isC; p.isD = isD;
+    p.out = out; p.osB = osB; p.osC = osC; p.osD = osD;
+    p.wpack = wpack; p.bias = bias;
+    p.Cin = Cin; p.Cout = Cout; p.D = D; p.H = H; p.W = W;
+    p.dil = dilation; p.act = act;
+    p.PW = W + dilation;
+    p.halo = dilation * p.PW + dilation;
+    p.nchunk = (Cin + 7) / 8;
+    const long long total_pos = (long long)H * p.PW;
+    // tile count: MT x 128 positions per CTA; TMEM holds MT*N <= 512 columns; shared memory must hold >= 2 stages.
+    const int planes = B * D;
+    int best_mt = 1, best_stages = 2;
+    double best_cost = 1e30;
+    for (int mt = 1; mt <= 512 / N && mt <= 16; ++mt) {
+        const long long npos = (long long)mt * 128 + 2 * p.halo;
+        const size_t stage = (size_t)npos * 64 + (size_t)576 * N;
+        const size_t fixed = (size_t)((npos * 4 + 15) & ~15ll) + 128;
+        int stages = (int)((227 * 1024 - fixed) / stage);
+        if (stages < 2) continue;
+        if (stages > tc::MAX_STAGES) stages = tc::MAX_STAGES;
+        const long long tiles = (total_pos + mt * 128 - 1) / (mt * 128);
+        const long long ctas = tiles * planes;
+        const long long waves = (ctas + 147) / 148;
+        // cost model: waves x per-CTA work (outputs + halo re-staging); fewer, fuller waves win
+        const double cost = (double)waves * ((double)mt * 128 + 2.0 * p.halo * 0.6);
+        if (cost < best_cost) {
+            best_cost = cost;
+            best_mt = mt;
+            best_stages = stages;
+        }
+    }
+    TS_REQUIRE(best_cost < 1e29, "conv_hw3_tc: row pitch %d too wide for the shared-memory tile", p.PW);
+    p.MT = best_mt;
+    p.stages = best_stages;
+    p.NPOS = best_mt * 128 + 2 * p.halo;
+    p.tiles_per_plane = (int)((total_pos + best_mt * 128 - 1) / (best_mt * 128));
+    const size_t smem_bytes = (size_t)p.stages * ((size_t)p.NPOS * 64 + (size_t)576 * N) + (size_t)((p.NPOS * 4 + 15) & ~15) + 128;
+    dim3 grid(p.tiles_per_plane, planes);
+    cudaStream_t st = (cudaStream_t)stream;
+#define TS_TC(NN)                                                                                                   \
+    {                                                                                                               \
+        auto kern = tc::conv_hw3_tc_kernel<NN>;                                                                     \
+        static bool attr_done = false;                                                                              \
+        if (!attr_done) {                                                                                           \
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);    \
+            if (e != cudaSuccess) {                                                                                 \
+                set_error("conv_hw3_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));                          \
+                return TSTEREO_E_CUDA;                                                                              \
+            }                                                                                                       \
+            attr_done = true;                                                                                       \
+        }                                                                                                           \
+        kern<<<grid, tc::NTHREADS, smem_bytes, st>>>(p);                                                            \
+    }
+    if (N == 16) TS_TC(16) else if (N == 32) TS_TC(32) else if (N == 48) TS_TC(48) else TS_TC(64)
+#undef TS_TC
+    return check_launch("conv_hw3_tc");
+}
+
+}  // extern "C"

@@ -103,6 +103,47 @@ def conv_hw3(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], cou
     return out
 
 
+def tf32_split(w: torch.Tensor):
+    """w = hi + lo with both parts exactly representable in tf32 (10 mantissa bits), rounding to
+    nearest / ties away like cvt.rna.tf32.f32."""
+    def rna(t):
+        i = t.contiguous().view(torch.int32)
+        return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+    hi = rna(w)
+    return hi, rna(w - hi)
+
+
+def pack_conv_hw3_tc(w: torch.Tensor) -> torch.Tensor:
+    """[Cout, Cin, 9] (BN folded) -> the tcgen05 B-operand image [ceil(Cin/8)][part 2][tap 9][khalf 2][N][4]."""
+    cout, cin, taps = w.shape
+    assert taps == 9
+    N, nch = (cout + 15) // 16 * 16, (cin + 7) // 8
+    full = torch.zeros((N, nch * 8, 9), device=w.device, dtype=torch.float32)
+    full[:cout, :cin] = w
+    hi, lo = tf32_split(full)
+    parts = torch.stack([hi, lo])                                     # [2, N, nch*8, 9]
+    parts = parts.view(2, N, nch, 2, 4, 9)                            # [part, n, chunk, khalf, i, tap]
+    return parts.permute(2, 0, 5, 3, 1, 4).contiguous().view(-1)      # [chunk, part, tap, khalf, n, i]
+
+
+def conv_hw3_tc(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Tensor], cout: int, dilation: int = 1,
+                act=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Stride-1 (1,3,3) / 3x3 conv on the tensor cores (tcgen05, 3xTF32), padding = dilation."""
+    five = x.dim() == 5
+    B, Cin = x.shape[:2]
+    D = x.shape[2] if five else 1
+    H, W = x.shape[-2:]
+    if out is None:
+        out = torch.empty((B, cout, D, H, W) if five else (B, cout, H, W), device=x.device, dtype=torch.float32)
+    isB, isC, isD = _view5(x)
+    osB, osC, osD = _view5(out)
+    _chk(wpack, bias)
+    assert wpack.numel() == _lib.load().tstereo_conv_hw3_tc_wpack_floats(Cin, cout)
+    _lib.call("tstereo_conv_hw3_tc", _p(x), isB, isC, isD, _p(out), osB, osC, osD, _p(wpack), _p(bias),
+              B, Cin, cout, D, H, W, dilation, ACT[act], _stream())
+    return out
+
+
 def conv_d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], cout: int, k: int = 3, stride: int = 1,
            dilation: int = 1, transposed: bool = False, act=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """(k,1,1) conv along D (or its stride-2 transposed form), packed weights w[Cin][k][CoutP]."""

@@ -420,3 +420,45 @@ def test_update_map_golden(golden_dir):
     close(got["cost_memory"]["disp_sample"], gm["mem_sample"], 2e-4, rtol=1e-5, what="warped samples")
     close(got["cost_memory"]["cost_volume"], gm["mem_cost"], 2e-4, rtol=1e-5, what="warped costs")
     close(got["local_map"], gm["local_map"], 2e-4, rtol=1e-5, what="local map")
+
+
+# --------------------------------------------------------------------------- tensor-core conv (tcgen05, 3xTF32)
+TC_CASES = [
+    # B, Cin, Cout, D, H, W, dil, act, bias
+    (1, 8, 16, 1, 8, 16, 1, None, False),
+    (1, 16, 8, 2, 9, 20, 1, "SiLU", True),
+    (1, 44, 32, 3, 17, 30, 1, "SiLU", True),
+    (2, 304, 8, 2, 20, 37, 1, "SiLU", True),
+    (1, 128, 32, 2, 34, 60, 1, None, True),
+    (1, 64, 64, 1, 9, 15, 1, "ReLU", True),
+    (1, 32, 32, 2, 17, 30, 2, "SiLU", True),
+    (1, 13, 36, 1, 10, 12, 1, None, True),
+    (1, 64, 32, 1, 40, 240, 1, "ReLU", True),
+    (1, 8, 8, 5, 136, 240, 2, "SiLU", True),
+]
+
+
+@pytest.mark.parametrize("B,Cin,Cout,D,H,W,dil,act,bias", TC_CASES)
+def test_conv_hw3_tc(ops, B, Cin, Cout, D, H, W, dil, act, bias):
+    """tcgen05 implicit-GEMM conv with error-compensated 3xTF32 operands == fp32 conv to ~1e-6 relative."""
+    x = rnd(B, Cin, D, H, W, seed=41)
+    w = rnd(Cout, Cin, 1, 3, 3, seed=42, scale=(2.0 / (9 * Cin)) ** 0.5)
+    b = rnd(Cout, seed=43, scale=0.1) if bias else None
+    want = O._act(F.conv3d(x.double(), w.double(), None if b is None else b.double(), 1, (0, dil, dil), (1, dil, dil)), act).float()
+    wp = ops.pack_conv_hw3_tc(w.reshape(Cout, Cin, 9).cuda())
+    got = ops.conv_hw3_tc(x.cuda(), wp, None if b is None else b.cuda(), Cout, dil, act)
+    close(got, want, 1e-5, rtol=1e-5, what="conv_hw3_tc")
+
+
+def test_conv_hw3_tc_views(ops):
+    """2-D input, channel-sliced input and output views (the concat buffers)."""
+    x = rnd(2, 24, 13, 21, seed=45)
+    w = rnd(16, 24, 3, 3, seed=46, scale=0.1)
+    want = F.relu(F.conv2d(x, w, None, 1, 1))
+    wp = ops.pack_conv_hw3_tc(w.reshape(16, 24, 9).cuda())
+    buf = torch.full((2, 40, 13, 21), 7.0, device="cuda")
+    xin = torch.zeros(2, 40, 13, 21)
+    xin[:, 8:32] = x
+    ops.conv_hw3_tc(xin.cuda()[:, 8:32], wp, None, 16, 1, "ReLU", out=buf[:, 8:24])
+    close(buf[:, 8:24], want, 1e-5, rtol=1e-5, what="tc conv2d slices")
+    assert (buf[:, :8] == 7).all() and (buf[:, 24:] == 7).all()
