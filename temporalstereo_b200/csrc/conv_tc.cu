@@ -97,38 +97,49 @@ struct Params {
     const float* wpack;     // [nchunk][part 2][tap 9][khalf 2][N][4]
     const float* bias;      // [Cout] or null
     int Cin, Cout, D, H, W;
-    int dil, PW, MT, NPOS, halo, nchunk, stages, act;
+    int dil, PW, NPOS, halo, nchunk, stages, act;
     int tiles_per_plane;
 };
 
-template <int N>
+// The tensor core accumulates into TMEM with truncation: measured on B200 the error of one long
+// accumulation grows linearly with K with a bias towards zero (rms 3e-5 at K = 9*352, 20x the fp32 FMA
+// chain; scripts/diag_tc.py).  So every 8-channel chunk (27 MMAs) accumulates from zero into one of two
+// TMEM buffers and the producer warps add it into fp32 REGISTER accumulators (round-to-nearest) while
+// the tensor core works on the next chunk in the other buffer.
+template <int N, int MT>
 __global__ void __launch_bounds__(NTHREADS, 1) conv_hw3_tc_kernel(const Params p) {
+    constexpr int TOTAL = N * MT;          // accumulator columns of one buffer
+    constexpr int JT = (MT + 1) / 2;       // M-tiles per reader thread (tiles j = half + 2*jj)
+    static_assert(JT * N <= 64, "register accumulators limited to 64 per thread");
     extern __shared__ __align__(128) uint8_t smem[];
     // layout: [stages] x { A: part(2) x khalf(2) x NPOS x 16 B | B: 2 x 9 x 2 x N x 16 B } | pos table | barriers
     const uint32_t a_bytes = 4u * p.NPOS * 16u;
-    const uint32_t b_bytes = 2u * 9u * 2u * N * 16u;
+    constexpr uint32_t b_bytes = 2u * 9u * 2u * N * 16u;
     const uint32_t stage_bytes = a_bytes + b_bytes;
     int* pos_tbl = reinterpret_cast<int*>(smem + (size_t)p.stages * stage_bytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes + (((size_t)p.NPOS * 4 + 15) & ~(size_t)15));
-    uint64_t* full = bars;                       // [stages]
-    uint64_t* empty = bars + MAX_STAGES;         // [stages]
-    uint64_t* accum_full = bars + 2 * MAX_STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 1);
+    uint64_t* full = bars;                       // [stages]   producers -> MMA
+    uint64_t* empty = bars + MAX_STAGES;         // [stages]   MMA -> producers
+    uint64_t* acc_full = bars + 2 * MAX_STAGES;  // [2]        MMA -> readers (chunk accumulated)
+    uint64_t* acc_empty = acc_full + 2;          // [2]        readers -> MMA (buffer drained)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int plane = blockIdx.y;
     const int b = plane / p.D, d = plane % p.D;
-    const int q0 = blockIdx.x * p.MT * 128;                   // first padded-linear output position of this CTA
+    const int q0 = blockIdx.x * MT * 128;                     // first padded-linear output position of this CTA
     const float* in_pl = p.in + (long long)b * p.isB + (long long)d * p.isD;
-    uint32_t ncols = 32;                                       // TMEM columns: MT * N rounded up to a power of two
-    while (ncols < (uint32_t)(p.MT * N)) ncols <<= 1;
+    constexpr uint32_t ncols = (2 * TOTAL <= 32) ? 32 : (2 * TOTAL <= 64) ? 64 : (2 * TOTAL <= 128) ? 128 : (2 * TOTAL <= 256) ? 256 : 512;
 
     if (tid == 0) {
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(&full[s], NPROD + 1);
             mbar_init(&empty[s], 1);
         }
-        mbar_init(accum_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], NPROD);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == NPROD / 32) {   // MMA warp allocates TMEM
@@ -151,7 +162,42 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_hw3_tc_kernel(const Params p
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < NPROD / 32) {
-        // ===================== producers =====================
+        // ===================== producers / accumulator readers =====================
+        const int quarter = warp & 3;                 // TMEM lanes this warp may read
+        const int half = warp >> 2;                   // which M-tiles it drains
+        float acc[JT][N];
+#pragma unroll
+        for (int jj = 0; jj < JT; ++jj)
+#pragma unroll
+            for (int n = 0; n < N; ++n) acc[jj][n] = 0.f;
+
+        auto drain = [&](int kk) {
+            const int bf = kk & 1;
+            mbar_wait(&acc_full[bf], (uint32_t)(kk >> 1) & 1u);
+            tc_fence_after();
+#pragma unroll
+            for (int jj = 0; jj < JT; ++jj) {
+                const int j = half + 2 * jj;
+                if (j < MT) {
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(bf * TOTAL + j * N);
+#pragma unroll
+                    for (int c0 = 0; c0 < N; c0 += 16) {
+                        uint32_t r[16];
+                        asm volatile(
+                            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                            : "r"(taddr + (uint32_t)c0));
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) acc[jj][c0 + c] += __uint_as_float(r[c]);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&acc_empty[bf]);
+        };
+
         for (int k = 0; k < p.nchunk; ++k) {
             const int s = k % p.stages;
             const uint32_t ph = (uint32_t)(k / p.stages) & 1u;
@@ -163,7 +209,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_hw3_tc_kernel(const Params p
             }
             const uint32_t a_hi = smem_u32(st_base);                        // part 0 (hi): khalf 0, khalf 1
             const uint32_t a_lo = a_hi + 2u * p.NPOS * 16u;                // part 1 (lo)
-            const uint32_t half = (uint32_t)p.NPOS * 16u;
+            const uint32_t khalf = (uint32_t)p.NPOS * 16u;
             const int c0 = k * 8;
             const float* src = in_pl + (long long)c0 * p.isC;
 #pragma unroll 2
@@ -180,63 +226,54 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_hw3_tc_kernel(const Params p
                 }
                 const uint32_t o = (uint32_t)i * 16u;
                 sts128(a_hi + o, hi[0], hi[1], hi[2], hi[3]);
-                sts128(a_hi + half + o, hi[4], hi[5], hi[6], hi[7]);
+                sts128(a_hi + khalf + o, hi[4], hi[5], hi[6], hi[7]);
                 sts128(a_lo + o, lo[0], lo[1], lo[2], lo[3]);
-                sts128(a_lo + half + o, lo[4], lo[5], lo[6], lo[7]);
+                sts128(a_lo + khalf + o, lo[4], lo[5], lo[6], lo[7]);
             }
             fence_proxy_async();          // generic-proxy st.shared -> visible to the tensor core (async proxy)
             mbar_arrive(&full[s]);
+            if (k >= 1) drain(k - 1);     // overlaps with the MMAs of chunk k
         }
-        // ===================== epilogue =====================
-        mbar_wait(accum_full, 0);
-        tc_fence_after();
-        const int quarter = warp & 3;                 // TMEM lanes this warp may read
-        const size_t HWp = (size_t)p.H * p.W;
+        drain(p.nchunk - 1);
+
+        // ===================== epilogue: bias + activation from the register accumulators =====================
         float* out_pl = p.out + (long long)b * p.osB + (long long)d * p.osD;
-        for (int j = warp >> 2; j < p.MT; j += 2) {
-            const int q = q0 + j * 128 + quarter * 32 + lane;
-            const int y = q / p.PW, x = q - y * p.PW;
-            const bool ok = (y < p.H) && (x < p.W);
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(j * N);
 #pragma unroll
-            for (int c0 = 0; c0 < N; c0 += 16) {
-                uint32_t r[16];
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                      "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                    : "r"(taddr + (uint32_t)c0));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (ok) {
+        for (int jj = 0; jj < JT; ++jj) {
+            const int j = half + 2 * jj;
+            if (j < MT) {
+                const int q = q0 + j * 128 + quarter * 32 + lane;
+                const int y = q / p.PW, x = q - y * p.PW;
+                if (y < p.H && x < p.W) {
+                    float* o = out_pl + (size_t)y * p.W + x;
 #pragma unroll
-                    for (int c = 0; c < 16; ++c) {
-                        const int co = c0 + c;
-                        if (co < p.Cout) {
-                            const float bv = p.bias ? __ldg(p.bias + co) : 0.f;
-                            out_pl[(long long)co * p.osC + (size_t)y * p.W + x] = apply_act(__uint_as_float(r[c]) + bv, p.act);
+                    for (int n = 0; n < N; ++n)
+                        if (n < p.Cout) {
+                            const float bv = p.bias ? __ldg(p.bias + n) : 0.f;
+                            o[(long long)n * p.osC] = apply_act(acc[jj][n] + bv, p.act);
                         }
-                    }
                 }
             }
         }
-        (void)HWp;
-        tc_fence_before();
     } else {
         // ===================== MMA issuer =====================
         // instruction descriptor: D fp32, A/B tf32, both K-major, N, M = 128
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
         const uint32_t a_lbo = (uint32_t)p.NPOS * 16u, b_lbo = (uint32_t)N * 16u;
         for (int k = 0; k < p.nchunk; ++k) {
             const int s = k % p.stages;
             const uint32_t ph = (uint32_t)(k / p.stages) & 1u;
+            const int bf = k & 1, u = k >> 1;
             mbar_wait(&full[s], ph);
+            if (u >= 1) mbar_wait(&acc_empty[bf], (uint32_t)(u - 1) & 1u);
             tc_fence_after();
             if (lane == 0) {
                 const uint32_t st_base = smem_u32(smem + (size_t)s * stage_bytes);
                 const uint32_t a_part[2] = {st_base, st_base + 2u * p.NPOS * 16u};
                 const uint32_t b_base = st_base + a_bytes;
-                for (int j = 0; j < p.MT; ++j) {
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(j * N);
+#pragma unroll 1
+                for (int j = 0; j < MT; ++j) {
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(bf * TOTAL + j * N);
                     const uint32_t a_row0 = (uint32_t)(p.halo + j * 128) * 16u;
 #pragma unroll
                     for (int t = 0; t < 9; ++t) {
@@ -248,12 +285,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_hw3_tc_kernel(const Params p
                             const int pb = (term == 1) ? 1 : 0;
                             const uint64_t ad = make_desc(a_part[pa] + a_row0 + toff, a_lbo, 128u);
                             const uint64_t bd = make_desc(b_base + (uint32_t)((pb * 9 + t) * 2 * N * 16), b_lbo, 128u);
-                            tc_mma_tf32(d_tmem, ad, bd, idesc, (k | t | term) != 0 ? 1u : 0u);
+                            tc_mma_tf32(d_tmem, ad, bd, idesc, (t | term) != 0 ? 1u : 0u);
                         }
                     }
                 }
-                tc_commit(&empty[s]);                         // stage free once these MMAs have read it
-                if (k == p.nchunk - 1) tc_commit(accum_full);  // accumulators complete
+                tc_commit(&empty[s]);        // stage free once these MMAs have read it
+                tc_commit(&acc_full[bf]);    // chunk accumulated
             }
             __syncwarp();
         }
@@ -299,39 +336,38 @@ int tstereo_conv_hw3_tc(const float* in, long long isB, long long isC, long long
     p.halo = dilation * p.PW + dilation;
     p.nchunk = (Cin + 7) / 8;
     const long long total_pos = (long long)H * p.PW;
-    // tile count: MT x 128 positions per CTA; TMEM holds MT*N <= 512 columns; shared memory must hold >= 2 stages.
+    // M-tiles per CTA: MT in {1,2,4,8} with ceil(MT/2)*N <= 64 register accumulators per thread; shared memory must
+    // hold >= 2 stages.  Cost model: waves x (outputs + halo re-staging) per CTA — fewer, fuller waves win.
     const int planes = B * D;
-    int best_mt = 1, best_stages = 2;
+    int best_mt = 0, best_stages = 2;
     double best_cost = 1e30;
-    for (int mt = 1; mt <= 512 / N && mt <= 16; ++mt) {
+    for (int mt = 1; mt <= 8; mt *= 2) {
+        if (((mt + 1) / 2) * N > 64) continue;
         const long long npos = (long long)mt * 128 + 2 * p.halo;
         const size_t stage = (size_t)npos * 64 + (size_t)576 * N;
         const size_t fixed = (size_t)((npos * 4 + 15) & ~15ll) + 128;
+        if (fixed + 2 * stage > 227 * 1024) continue;
         int stages = (int)((227 * 1024 - fixed) / stage);
-        if (stages < 2) continue;
         if (stages > tc::MAX_STAGES) stages = tc::MAX_STAGES;
         const long long tiles = (total_pos + mt * 128 - 1) / (mt * 128);
-        const long long ctas = tiles * planes;
-        const long long waves = (ctas + 147) / 148;
-        // cost model: waves x per-CTA work (outputs + halo re-staging); fewer, fuller waves win
-        const double cost = (double)waves * ((double)mt * 128 + 2.0 * p.halo * 0.6);
+        const long long waves = (tiles * planes + 147) / 148;
+        const double cost = (double)waves * ((double)mt * 128 + 2.0 * p.halo * 0.6 + 96.0);
         if (cost < best_cost) {
             best_cost = cost;
             best_mt = mt;
             best_stages = stages;
         }
     }
-    TS_REQUIRE(best_cost < 1e29, "conv_hw3_tc: row pitch %d too wide for the shared-memory tile", p.PW);
-    p.MT = best_mt;
+    TS_REQUIRE(best_mt > 0, "conv_hw3_tc: row pitch %d too wide for the shared-memory tile", p.PW);
     p.stages = best_stages;
     p.NPOS = best_mt * 128 + 2 * p.halo;
     p.tiles_per_plane = (int)((total_pos + best_mt * 128 - 1) / (best_mt * 128));
     const size_t smem_bytes = (size_t)p.stages * ((size_t)p.NPOS * 64 + (size_t)576 * N) + (size_t)((p.NPOS * 4 + 15) & ~15) + 128;
     dim3 grid(p.tiles_per_plane, planes);
     cudaStream_t st = (cudaStream_t)stream;
-#define TS_TC(NN)                                                                                                   \
-    {                                                                                                               \
-        auto kern = tc::conv_hw3_tc_kernel<NN>;                                                                     \
+#define TS_TC(NN, MM)                                                                                               \
+    if (N == NN && best_mt == MM) {                                                                                 \
+        auto kern = tc::conv_hw3_tc_kernel<NN, MM>;                                                                 \
         static bool attr_done = false;                                                                              \
         if (!attr_done) {                                                                                           \
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);    \
@@ -343,7 +379,10 @@ int tstereo_conv_hw3_tc(const float* in, long long isB, long long isC, long long
         }                                                                                                           \
         kern<<<grid, tc::NTHREADS, smem_bytes, st>>>(p);                                                            \
     }
-    if (N == 16) TS_TC(16) else if (N == 32) TS_TC(32) else if (N == 48) TS_TC(48) else TS_TC(64)
+    TS_TC(16, 1) TS_TC(16, 2) TS_TC(16, 4) TS_TC(16, 8)
+    TS_TC(32, 1) TS_TC(32, 2) TS_TC(32, 4)
+    TS_TC(48, 1) TS_TC(48, 2)
+    TS_TC(64, 1) TS_TC(64, 2)
 #undef TS_TC
     return check_launch("conv_hw3_tc");
 }
