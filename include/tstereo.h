@@ -70,7 +70,7 @@ int tstereo_conv_hw3(const float* in, long long isB, long long isC, long long is
 
 /* Tensor-core form of tstereo_conv_hw3 for stride 1, Cout <= 64: tcgen05 implicit GEMM with
  * error-compensated 3xTF32 operands (fp32-equivalent results).  wpack holds the weights
- * split into tf32 hi/lo parts in the MMA's shared-memory layout: [ceil(Cin/8)][part 2][tap 9][khalf 2][N][4]
+ * split into tf32 hi/lo parts in the MMA's shared-memory layout: [ceil(Cin/8)][tap 9][khalf 2][part 2][N][4]
  * with N = Cout rounded up to 16 (tstereo_conv_hw3_tc_wpack_floats floats, 16-byte aligned). */
 long long tstereo_conv_hw3_tc_wpack_floats(int Cin, int Cout);
 int tstereo_conv_hw3_tc(const float* in, long long isB, long long isC, long long isD,

@@ -36,10 +36,11 @@ class _Node(nn.Module):
 
 
 class _Packed:
-    __slots__ = ("w", "b", "cout")
+    __slots__ = ("w", "b", "cout", "wtc")
 
-    def __init__(self, w, b, cout):
+    def __init__(self, w, b, cout, wtc=None):
         self.w, self.b, self.cout = w, b, cout
+        self.wtc = wtc          # tcgen05 (3xTF32) operand image of a 3x3 conv, or None
 
 
 def _level_cfg(node, defaults: dict) -> dict:
@@ -85,6 +86,9 @@ class TEMPORALSTEREO(nn.Module):
         self.weight_init()
         self._pk: Optional[Dict[str, _Packed]] = None
         self._const: Dict[tuple, torch.Tensor] = {}
+        # stride-1 3x3 contractions on tcgen05 with error-compensated 3xTF32 operands (fp32-equivalent);
+        # False keeps every contraction on the fp32 FMA pipe
+        self.tensor_cores = True
         self.register_load_state_dict_post_hook(lambda m, _k: m.invalidate())
         super().train(False)
 
@@ -173,7 +177,10 @@ class TEMPORALSTEREO(nn.Module):
         coutp = (cout + 3) // 4 * 4
         packed = torch.zeros((cin, w.shape[2], coutp), device=w.device, dtype=torch.float32)
         packed[:, :, :cout] = w.permute(1, 2, 0)
-        return _Packed(packed.contiguous(), None if bias is None else bias.contiguous(), cout)
+        wtc = None
+        if w.shape[2] == 9 and not transposed and cout <= 64 and cin >= 8 and w.is_cuda and self.tensor_cores:
+            wtc = ops.pack_conv_hw3_tc(w)
+        return _Packed(packed.contiguous(), None if bias is None else bias.contiguous(), cout, wtc)
 
     def _pack(self) -> Dict[str, _Packed]:
         sd = dict(self.state_dict(keep_vars=True))
@@ -227,10 +234,16 @@ class TEMPORALSTEREO(nn.Module):
         return pk
 
     # ------------------------------------------------------------------ building blocks
+    def _hw3(self, x, k: _Packed, stride=1, dil=1, act=None, out=None):
+        """3x3 conv over (H,W): tensor cores for stride 1, fp32 FMA kernel otherwise."""
+        if k.wtc is not None and stride == 1 and self.tensor_cores:
+            return ops.conv_hw3_tc(x, k.wtc, k.b, k.cout, dil, act, out=out)
+        return ops.conv_hw3(x, k.w, k.b, k.cout, stride, dil, act, out=out)
+
     def _sep(self, x, p, stride=1, dil=1, act0="SiLU", act1="SiLU", out=None):
         """'DepthwiseConv3D': (1,3,3) conv then (3,1,1) conv, BN folded (reference module.py:111-147)."""
         a, b = self._pk[p + ".conv.0"], self._pk[p + ".conv.1"]
-        y = ops.conv_hw3(x, a.w, a.b, a.cout, stride, dil, act0)
+        y = self._hw3(x, a, stride, dil, act0)
         return ops.conv_d(y, b.w, b.b, b.cout, 3, stride, dil, False, act1, out=out)
 
     def _sep_t(self, x, p):
@@ -300,13 +313,13 @@ class TEMPORALSTEREO(nn.Module):
         vol = self._sep(cat, f"{lvl}.fuse.conv_fuse", act0=None, act1=None)
         disp, cost, off, _, _ = self._heads_predict(vol, samples, f"{lvl}.pred_heads", float(cfg["delta"]))
         m0, m3 = self._pk[f"{lvl}.convex_upsample.mask.0"], self._pk[f"{lvl}.convex_upsample.mask.3"]
-        mfeat = ops.conv_hw3(left, m0.w, m0.b, m0.cout, 1, 1, "SiLU")
+        mfeat = self._hw3(left, m0, 1, 1, "SiLU")
         up = ops.convex_upsample(mfeat, m3.w, m3.b, disp)
         return up, cost, off, samples
 
     def _conv2d(self, x, p, stride=1, act="ReLU", out=None):
         k = self._pk[p]
-        return ops.conv_hw3(x, k.w, k.b, k.cout, stride, 1, act, out=out)
+        return self._hw3(x, k, stride, 1, act, out=out)
 
     # ------------------------------------------------------------------ forward
     @torch.no_grad()

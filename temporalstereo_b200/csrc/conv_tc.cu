@@ -6,7 +6,10 @@
 //
 // Precision: plain TF32 moves the regressed disparity by 0.7 px, so every product is
 // error-compensated "3xTF32": a = a_hi + a_lo (both exactly representable in tf32), and
-// D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi with fp32 accumulation in TMEM (~21 operand bits).
+// D += A_hi*B_hi + A_hi*B_lo + A_lo*B_hi (~21 operand bits).  The kernel is bound by the shared-memory
+// reads of the A operand (4 KB per M=128,K=8 MMA, ~44 cycles each, measured), so the two A_hi terms are ONE
+// MMA of width 2N against [B_hi | B_lo] (two accumulator column blocks, summed when drained): 18 instead
+// of 27 MMAs per (chunk, M-tile).
 //
 // GEMM view of one (b, d) plane:  M = padded-linear pixel position q = y*PW + x with pitch PW = W + DIL
 // (the DIL zero columns after each row serve as right padding of row y and left padding of row y+1),
@@ -94,7 +97,7 @@ struct Params {
     long long isB, isC, isD;
     float* out;
     long long osB, osC, osD;
-    const float* wpack;     // [nchunk][part 2][tap 9][khalf 2][N][4]
+    const float* wpack;     // [nchunk][tap 9][khalf 2][part 2][N][4]  (rows n' = part*N + n of a 2N x 8 K-major matrix)
     const float* bias;      // [Cout] or null
     int Cin, Cout, D, H, W;
     int dil, PW, NPOS, halo, nchunk, stages, act;
@@ -108,11 +111,11 @@ struct Params {
 // the tensor core works on the next chunk in the other buffer.
 template <int N, int MT>
 __global__ void __launch_bounds__(NTHREADS, 1) conv_hw3_tc_kernel(const Params p) {
-    constexpr int TOTAL = N * MT;          // accumulator columns of one buffer
+    constexpr int TOTAL = 2 * N * MT;      // accumulator columns of one buffer: per M-tile [A*B_hi | A_hi*B_lo]
     constexpr int JT = (MT + 1) / 2;       // M-tiles per reader thread (tiles j = half + 2*jj)
     static_assert(JT * N <= 64, "register accumulators limited to 64 per thread");
     extern __shared__ __align__(128) uint8_t smem[];
-    // layout: [stages] x { A: part(2) x khalf(2) x NPOS x 16 B | B: 2 x 9 x 2 x N x 16 B } | pos table | barriers
+    // layout: [stages] x { A: part(2) x khalf(2) x NPOS x 16 B | B: tap(9) x khalf(2) x 2N x 16 B } | pos table | barriers
     const uint32_t a_bytes = 4u * p.NPOS * 16u;
     constexpr uint32_t b_bytes = 2u * 9u * 2u * N * 16u;
     const uint32_t stage_bytes = a_bytes + b_bytes;
@@ -179,9 +182,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_hw3_tc_kernel(const Params p
             for (int jj = 0; jj < JT; ++jj) {
                 const int j = half + 2 * jj;
                 if (j < MT) {
-                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(bf * TOTAL + j * N);
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(bf * TOTAL + j * 2 * N);
 #pragma unroll
-                    for (int c0 = 0; c0 < N; c0 += 16) {
+                    for (int c0 = 0; c0 < 2 * N; c0 += 16) {
                         uint32_t r[16];
                         asm volatile(
                             "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -190,7 +193,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_hw3_tc_kernel(const Params p
                             : "r"(taddr + (uint32_t)c0));
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                        for (int c = 0; c < 16; ++c) acc[jj][c0 + c] += __uint_as_float(r[c]);
+                        for (int c = 0; c < 16; ++c) acc[jj][(c0 + c) % N] += __uint_as_float(r[c]);
                     }
                 }
             }
@@ -258,8 +261,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_hw3_tc_kernel(const Params p
     } else {
         // ===================== MMA issuer =====================
         // instruction descriptor: D fp32, A/B tf32, both K-major, N, M = 128
-        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
-        const uint32_t a_lbo = (uint32_t)p.NPOS * 16u, b_lbo = (uint32_t)N * 16u;
+        constexpr uint32_t idesc_n = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+        constexpr uint32_t idesc_2n = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(2 * N >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t a_lbo = (uint32_t)p.NPOS * 16u, b_lbo = 2u * N * 16u;
         for (int k = 0; k < p.nchunk; ++k) {
             const int s = k % p.stages;
             const uint32_t ph = (uint32_t)(k / p.stages) & 1u;
@@ -273,20 +277,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_hw3_tc_kernel(const Params p
                 const uint32_t b_base = st_base + a_bytes;
 #pragma unroll 1
                 for (int j = 0; j < MT; ++j) {
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(bf * TOTAL + j * N);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(bf * TOTAL + j * 2 * N);
                     const uint32_t a_row0 = (uint32_t)(p.halo + j * 128) * 16u;
 #pragma unroll
                     for (int t = 0; t < 9; ++t) {
                         const int ky = t / 3 - 1, kx = t % 3 - 1;
                         const int toff = (ky * p.dil * p.PW + kx * p.dil) * 16;
-#pragma unroll
-                        for (int term = 0; term < 3; ++term) {
-                            const int pa = (term == 0) ? 1 : 0;      // lo*hi, hi*lo, hi*hi (small terms first)
-                            const int pb = (term == 1) ? 1 : 0;
-                            const uint64_t ad = make_desc(a_part[pa] + a_row0 + toff, a_lbo, 128u);
-                            const uint64_t bd = make_desc(b_base + (uint32_t)((pb * 9 + t) * 2 * N * 16), b_lbo, 128u);
-                            tc_mma_tf32(d_tmem, ad, bd, idesc, (t | term) != 0 ? 1u : 0u);
-                        }
+                        const uint64_t bd = make_desc(b_base + (uint32_t)(t * 2 * 2 * N * 16), b_lbo, 128u);
+                        // [D1 | D2] (+)= A_hi * [B_hi | B_lo]   (first MMA of the chunk overwrites both blocks)
+                        tc_mma_tf32(d_tmem, make_desc(a_part[0] + a_row0 + toff, a_lbo, 128u), bd, idesc_2n, t != 0 ? 1u : 0u);
+                        // D1 += A_lo * B_hi
+                        tc_mma_tf32(d_tmem, make_desc(a_part[1] + a_row0 + toff, a_lbo, 128u), bd, idesc_n, 1u);
                     }
                 }
                 tc_commit(&empty[s]);        // stage free once these MMAs have read it

@@ -114,7 +114,8 @@ def tf32_split(w: torch.Tensor):
 
 
 def pack_conv_hw3_tc(w: torch.Tensor) -> torch.Tensor:
-    """[Cout, Cin, 9] (BN folded) -> the tcgen05 B-operand image [ceil(Cin/8)][part 2][tap 9][khalf 2][N][4]."""
+    """[Cout, Cin, 9] (BN folded) -> the tcgen05 B-operand image [ceil(Cin/8)][tap 9][khalf 2][part 2][N][4]:
+    per (chunk, tap) a K-major 2N x 8 matrix whose rows are [tf32 hi part | tf32 lo part] of the weights."""
     cout, cin, taps = w.shape
     assert taps == 9
     N, nch = (cout + 15) // 16 * 16, (cin + 7) // 8
@@ -123,7 +124,7 @@ def pack_conv_hw3_tc(w: torch.Tensor) -> torch.Tensor:
     hi, lo = tf32_split(full)
     parts = torch.stack([hi, lo])                                     # [2, N, nch*8, 9]
     parts = parts.view(2, N, nch, 2, 4, 9)                            # [part, n, chunk, khalf, i, tap]
-    return parts.permute(2, 0, 5, 3, 1, 4).contiguous().view(-1)      # [chunk, part, tap, khalf, n, i]
+    return parts.permute(2, 5, 3, 0, 1, 4).contiguous().view(-1)      # [chunk, tap, khalf, part, n, i]
 
 
 def conv_hw3_tc(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Tensor], cout: int, dilation: int = 1,
