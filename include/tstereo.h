@@ -68,16 +68,22 @@ int tstereo_conv_hw3(const float* in, long long isB, long long isC, long long is
                      int B, int Cin, int Cout, int D, int Hin, int Win, int Hout, int Wout,
                      int stride, int dilation, int act, void* stream);
 
-/* Tensor-core form of tstereo_conv_hw3 for stride 1, Cout <= 64: tcgen05 implicit GEMM with
- * error-compensated 3xTF32 operands (fp32-equivalent results).  wpack holds the weights
- * split into tf32 hi/lo parts in the MMA's shared-memory layout: [ceil(Cin/8)][tap 9][khalf 2][part 2][N][4]
- * with N = Cout rounded up to 16 (tstereo_conv_hw3_tc_wpack_floats floats, 16-byte aligned). */
-long long tstereo_conv_hw3_tc_wpack_floats(int Cin, int Cout);
+/* Tensor-core forms (tcgen05 implicit GEMM, error-compensated 3xTF32 operands: fp32-equivalent results,
+ * DESIGN.md section 3) of tstereo_conv_hw3 (stride 1 only) and tstereo_conv_d, for Cout <= 64.
+ * wpack holds the weights split into tf32 hi/lo parts in the MMA's shared-memory layout:
+ * [ceil(Cin/8)][tap][khalf 2][part 2][N][4] with N = Cout rounded up to 16, taps = 9 (hw3: ky*3+kx) or k (d);
+ * tstereo_conv_tc_wpack_floats(Cin, Cout, taps) floats, 16-byte aligned. */
+long long tstereo_conv_tc_wpack_floats(int Cin, int Cout, int taps);
 int tstereo_conv_hw3_tc(const float* in, long long isB, long long isC, long long isD,
                         float* out, long long osB, long long osC, long long osD,
                         const float* wpack, const float* bias,
                         int B, int Cin, int Cout, int D, int H, int W,
                         int dilation, int act, void* stream);
+int tstereo_conv_d_tc(const float* in, long long isB, long long isC, long long isD,
+                      float* out, long long osB, long long osC, long long osD,
+                      const float* wpack, const float* bias,
+                      int B, int Cin, int Cout, int Din, int Dout, int H, int W,
+                      int k, int stride, int dilation, int transposed, int act, void* stream);
 
 /* (k,1,1) convolution along D: k = 3|5, stride 1|2, dilation 1|2, padding = dilation*(k/2).
  * transposed != 0: ConvTranspose (3,1,1) stride 2, padding 1, output_padding 1 (Dout = 2*Din). */

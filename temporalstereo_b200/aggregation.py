@@ -178,8 +178,10 @@ class TEMPORALSTEREO(nn.Module):
         packed = torch.zeros((cin, w.shape[2], coutp), device=w.device, dtype=torch.float32)
         packed[:, :, :cout] = w.permute(1, 2, 0)
         wtc = None
-        if w.shape[2] == 9 and not transposed and cout <= 64 and cin >= 8 and w.is_cuda and self.tensor_cores:
-            wtc = ops.pack_conv_hw3_tc(w)
+        is_hw = conv.endswith(".conv.0") or ".refinement." in conv or ".mask." in conv     # (1,k,k) / 2-D kernels
+        tc_ok = (w.shape[2] == 9 and not transposed) if is_hw else w.shape[2] in (3, 5)
+        if tc_ok and cout <= 64 and cin >= 8 and w.is_cuda and self.tensor_cores:
+            wtc = ops.pack_conv_tc(w)
         return _Packed(packed.contiguous(), None if bias is None else bias.contiguous(), cout, wtc)
 
     def _pack(self) -> Dict[str, _Packed]:
@@ -207,7 +209,10 @@ class TEMPORALSTEREO(nn.Module):
             cp = (2 * c + 3) // 4 * 4
             wp = torch.zeros((w.shape[0], w.shape[1], cp), device=w.device)
             wp[:, :, :2 * c] = w
-            pk[p + ".stem"] = _Packed(wp.contiguous(), torch.cat([a.b, b.b]).contiguous(), 2 * c)
+            wtc = None
+            if self.tensor_cores and w.is_cuda and 2 * c <= 64 and w.shape[0] >= 8:
+                wtc = ops.pack_conv_tc(w.permute(2, 0, 1).contiguous())            # [Cin][k][2C] -> [2C][Cin][k]
+            pk[p + ".stem"] = _Packed(wp.contiguous(), torch.cat([a.b, b.b]).contiguous(), 2 * c, wtc)
             w1 = torch.stack([sd[f"{p}.cost_head.1.weight"].detach().float().reshape(c, 9),
                               sd[f"{p}.off_head.1.weight"].detach().float().reshape(c, 9)])
             pk[p + ".final"] = _Packed(w1.contiguous(), None, 2)
@@ -240,17 +245,23 @@ class TEMPORALSTEREO(nn.Module):
             return ops.conv_hw3_tc(x, k.wtc, k.b, k.cout, dil, act, out=out)
         return ops.conv_hw3(x, k.w, k.b, k.cout, stride, dil, act, out=out)
 
+    def _d(self, x, k: _Packed, ksz=3, stride=1, dil=1, transposed=False, act=None, out=None):
+        """(k,1,1) conv along D: tensor cores when a tcgen05 operand image exists."""
+        if k.wtc is not None and self.tensor_cores:
+            return ops.conv_d_tc(x, k.wtc, k.b, k.cout, ksz, stride, dil, transposed, act, out=out)
+        return ops.conv_d(x, k.w, k.b, k.cout, ksz, stride, dil, transposed, act, out=out)
+
     def _sep(self, x, p, stride=1, dil=1, act0="SiLU", act1="SiLU", out=None):
         """'DepthwiseConv3D': (1,3,3) conv then (3,1,1) conv, BN folded (reference module.py:111-147)."""
         a, b = self._pk[p + ".conv.0"], self._pk[p + ".conv.1"]
         y = self._hw3(x, a, stride, dil, act0)
-        return ops.conv_d(y, b.w, b.b, b.cout, 3, stride, dil, False, act1, out=out)
+        return self._d(y, b, 3, stride, dil, False, act1, out=out)
 
     def _sep_t(self, x, p):
         """'DepthwiseConvTranspose3D' k3 s2 p1 op1, no activation (reference module.py:149-184)."""
         a, b = self._pk[p + ".conv.0"], self._pk[p + ".conv.1"]
         y = ops.deconv_hw(x, a.w, a.b, a.cout, 3, None)
-        return ops.conv_d(y, b.w, b.b, b.cout, 3, 2, 1, True, None)
+        return self._d(y, b, 3, 2, 1, True, None)
 
     def _hourglass(self, x, p):
         """ResidualBlock3D (reference module.py:271-297)."""
@@ -272,7 +283,7 @@ class TEMPORALSTEREO(nn.Module):
 
     def _heads_predict(self, vol, samples, p, delta, want_top=False):
         st, fin = self._pk[p + ".stem"], self._pk[p + ".final"]
-        feat = ops.conv_d(vol, st.w, st.b, st.cout, 3, 1, 1, False, "SiLU")
+        feat = self._d(vol, st, 3, 1, 1, False, "SiLU")
         cost, off = ops.heads(feat, fin.w, delta)
         disp, td, tc = ops.predict_disp(cost, samples, off, want_top)
         return disp, cost, off, td, tc
@@ -308,7 +319,7 @@ class TEMPORALSTEREO(nn.Module):
         cat = torch.empty((B, 4 * C, D + 2, H, W), device=left.device, dtype=torch.float32)
         _, samples = ops.merge_memory(vol, samples, ms, mv, pc.w, pc.b, 2, out_vol=cat[:, :C])
         c5 = self._pk[f"{lvl}.fuse.conv_5x5"]
-        ops.conv_d(cat[:, :C], c5.w, c5.b, c5.cout, 5, 1, 1, False, "SiLU", out=cat[:, C:2 * C])
+        self._d(cat[:, :C], c5, 5, 1, 1, False, "SiLU", out=cat[:, C:2 * C])
         ops.pool5(cat[:, :C], cat[:, 2 * C:3 * C], cat[:, 3 * C:])
         vol = self._sep(cat, f"{lvl}.fuse.conv_fuse", act0=None, act1=None)
         disp, cost, off, _, _ = self._heads_predict(vol, samples, f"{lvl}.pred_heads", float(cfg["delta"]))

@@ -1,29 +1,35 @@
-// Tensor-core (tcgen05, sm_100a) implicit-GEMM 3x3 convolution over (H,W), stride 1, dilation 1|2 —
-// the weight contractions of the aggregation.
+// Tensor-core (tcgen05, sm_100a) implicit-GEMM convolutions — the weight contractions of the aggregation
+// (SURVEY.md §8 rows a4-a7, a9, a10, a12, a13):
+//   * tstereo_conv_hw3_tc : (1,3,3) / 3x3 conv over (H,W), stride 1, dilation 1|2
+//   * tstereo_conv_d_tc   : (k,1,1) conv along D, k = 3|5, stride 1|2, dilation 1|2, or transposed stride 2
 //
-// ref: architecture/modeling/layers/basic_layers.py:194-235 (Conv3d: conv -> BN -> act) as used by the
-//      (1,3,3) halves of aggregation/TemporalStereo/module.py:111-147 and the 2-D convs of :300-353, 424-492.
+// ref: architecture/modeling/layers/basic_layers.py:194-235 (Conv3d: conv -> BN -> act), :340-388 (ConvTranspose3d)
+//      as used by the separable pairs of aggregation/TemporalStereo/module.py:111-184 and the 2-D convs of
+//      :300-353, 424-492.
 //
 // Precision: plain TF32 moves the regressed disparity by 0.7 px, so every product is
 // error-compensated "3xTF32": a = a_hi + a_lo (both exactly representable in tf32), and
 // D += A_hi*B_hi + A_hi*B_lo + A_lo*B_hi (~21 operand bits).  The kernel is bound by the shared-memory
 // reads of the A operand (4 KB per M=128,K=8 MMA, ~44 cycles each, measured), so the two A_hi terms are ONE
-// MMA of width 2N against [B_hi | B_lo] (two accumulator column blocks, summed when drained): 18 instead
-// of 27 MMAs per (chunk, M-tile).
+// MMA of width 2N against [B_hi | B_lo] (two accumulator column blocks, summed when drained): 2 MMAs per
+// (tap, chunk, M-tile).
 //
-// GEMM view of one (b, d) plane:  M = padded-linear pixel position q = y*PW + x with pitch PW = W + DIL
-// (the DIL zero columns after each row serve as right padding of row y and left padding of row y+1),
-// N = Cout (rounded up to 16), K = 8-channel chunks x 9 taps.  A tap (ky,kx) is the SAME staged tile
-// read at a start-address offset of (ky*DIL*PW + kx*DIL) positions, because the tile is staged K-major
-// with 16 B per (position, 4 channels):  smem A[part][khalf][position][4 ch]  — UMMA canonical K-major
-// SWIZZLE_NONE layout with SBO = 128 B (8 positions x 16 B, dense) and LBO = NPOS*16 B.
+// GEMM view:  M = 128 x MT pixel positions of one output plane, N = Cout (rounded up to 16),
+// K = 8-channel chunks x taps.  A is staged K-major with 16 B per (position, 4 channels):
+// smem A[part][khalf][position][4 ch] — UMMA canonical K-major SWIZZLE_NONE layout with SBO = 128 B
+// (8 positions x 16 B, dense) and LBO = NPOS*16 B — so a tap is just a start-address offset into the staged
+// positions:
+//   hw3: positions are padded-linear q = y*PW + x with pitch PW = W + DIL (the DIL zero columns after each
+//        row are the right padding of row y and the left padding of row y+1); tap (ky,kx) = offset
+//        ky*DIL*PW + kx*DIL inside ONE staged tile with a halo of DIL*PW + DIL positions on both sides;
+//   d  : every valid tap stages its own input plane (MT*128 positions each); tap t = offset t*MT*128.
 //
-//  warps 0-7 : producers — global NCHW fp32 -> registers (4 channel loads per K-half) -> hi/lo split ->
+//  warps 0-7 : producers — global NCDHW fp32 -> registers (4 channel loads per K-half) -> hi/lo split ->
 //              one 16 B st.shared per (position, K-half, part); thread 0 also bulk-copies the chunk's
-//              pre-split weights (cp.async.bulk + mbarrier complete_tx).  Afterwards: epilogue
-//              (tcgen05.ld -> bias -> activation -> coalesced NCHW stores).
-//  warp 8    : TMEM alloc/dealloc; one elected lane issues MT x 9 x 3 tcgen05.mma per chunk and
-//              tcgen05.commit's the stage back to the producers.
+//              pre-split weights (cp.async.bulk + mbarrier complete_tx).  They also drain the per-chunk
+//              TMEM accumulators into fp32 registers and run the epilogue (bias, activation, NCDHW stores).
+//  warp 8    : TMEM alloc/dealloc; one elected lane issues the tcgen05.mma's of a chunk and
+//              tcgen05.commit's the stage back to the producers and the accumulator buffer to the readers.
 #include "common.cuh"
 #include <cstdint>
 
@@ -33,6 +39,8 @@ namespace tc {
 constexpr int NPROD = 256;             // producer threads (8 warps)
 constexpr int NTHREADS = NPROD + 32;   // + MMA warp
 constexpr int MAX_STAGES = 4;
+constexpr int MAX_TAPS = 9;
+constexpr size_t SMEM_MAX = 227 * 1024;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -92,32 +100,37 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+enum Mode { MODE_HW3 = 0, MODE_D = 1 };
+
 struct Params {
     const float* in;
     long long isB, isC, isD;
     float* out;
     long long osB, osC, osD;
-    const float* wpack;     // [nchunk][tap 9][khalf 2][part 2][N][4]  (rows n' = part*N + n of a 2N x 8 K-major matrix)
+    const float* wpack;     // [nchunk][tap T][khalf 2][part 2][N][4]  (rows n' = part*N + n of a 2N x 8 K-major matrix)
     const float* bias;      // [Cout] or null
-    int Cin, Cout, D, H, W;
+    int mode, T;            // T = taps stored in wpack (9 | k)
+    int Cin, Cout, H, W;
+    int Din, Dout;          // planes of the input / output (hw3: equal)
     int dil, PW, NPOS, halo, nchunk, stages, act;
+    int k_d, stride_d, transposed;   // MODE_D
     int tiles_per_plane;
 };
 
 // The tensor core accumulates into TMEM with truncation: measured on B200 the error of one long
 // accumulation grows linearly with K with a bias towards zero (rms 3e-5 at K = 9*352, 20x the fp32 FMA
-// chain; scripts/diag_tc.py).  So every 8-channel chunk (27 MMAs) accumulates from zero into one of two
-// TMEM buffers and the producer warps add it into fp32 REGISTER accumulators (round-to-nearest) while
-// the tensor core works on the next chunk in the other buffer.
+// chain; scripts/diag_tc.py).  So every 8-channel chunk accumulates from zero into one of two TMEM buffers
+// and the producer warps add it into fp32 REGISTER accumulators (round-to-nearest) while the tensor core
+// works on the next chunk in the other buffer.
 template <int N, int MT>
-__global__ void __launch_bounds__(NTHREADS, 1) conv_hw3_tc_kernel(const Params p) {
+__global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const Params p) {
     constexpr int TOTAL = 2 * N * MT;      // accumulator columns of one buffer: per M-tile [A*B_hi | A_hi*B_lo]
     constexpr int JT = (MT + 1) / 2;       // M-tiles per reader thread (tiles j = half + 2*jj)
     static_assert(JT * N <= 64, "register accumulators limited to 64 per thread");
     extern __shared__ __align__(128) uint8_t smem[];
-    // layout: [stages] x { A: part(2) x khalf(2) x NPOS x 16 B | B: tap(9) x khalf(2) x 2N x 16 B } | pos table | barriers
+    // layout: [stages] x { A: part(2) x khalf(2) x NPOS x 16 B | B: tap(T) x khalf(2) x 2N x 16 B } | pos table | barriers | taps
     const uint32_t a_bytes = 4u * p.NPOS * 16u;
-    constexpr uint32_t b_bytes = 2u * 9u * 2u * N * 16u;
+    const uint32_t b_bytes = (uint32_t)p.T * 2u * 2u * N * 16u;
     const uint32_t stage_bytes = a_bytes + b_bytes;
     int* pos_tbl = reinterpret_cast<int*>(smem + (size_t)p.stages * stage_bytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes + (((size_t)p.NPOS * 4 + 15) & ~(size_t)15));
@@ -126,12 +139,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_hw3_tc_kernel(const Params p
     uint64_t* acc_full = bars + 2 * MAX_STAGES;  // [2]        MMA -> readers (chunk accumulated)
     uint64_t* acc_empty = acc_full + 2;          // [2]        readers -> MMA (buffer drained)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    int* tap_tbl = reinterpret_cast<int*>(tmem_slot + 2);   // [0] = ntap, [1] = staged positions, (a_off, w_tap) pairs, input planes
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int plane = blockIdx.y;
-    const int b = plane / p.D, d = plane % p.D;
-    const int q0 = blockIdx.x * MT * 128;                     // first padded-linear output position of this CTA
-    const float* in_pl = p.in + (long long)b * p.isB + (long long)d * p.isD;
+    const int b = plane / p.Dout, dout = plane % p.Dout;
+    const int q0 = blockIdx.x * MT * 128;                     // first output position of this CTA
+    const float* in_b = p.in + (long long)b * p.isB;
     constexpr uint32_t ncols = (2 * TOTAL <= 32) ? 32 : (2 * TOTAL <= 64) ? 64 : (2 * TOTAL <= 128) ? 128 : (2 * TOTAL <= 256) ? 256 : 512;
 
     if (tid == 0) {
@@ -144,18 +158,56 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_hw3_tc_kernel(const Params p
             mbar_init(&acc_empty[i], NPROD);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // tap list: (offset of the tap's first row inside the staged positions, weight tap index)
+        int nt = 0;
+        if (p.mode == MODE_HW3) {
+            for (int t = 0; t < 9; ++t) {
+                const int ky = t / 3 - 1, kx = t % 3 - 1;
+                tap_tbl[2 + 2 * nt] = p.halo + ky * p.dil * p.PW + kx * p.dil;
+                tap_tbl[3 + 2 * nt] = t;
+                ++nt;
+            }
+            tap_tbl[1] = p.NPOS;
+        } else {
+            for (int kd = 0; kd < p.k_d; ++kd) {
+                int din;
+                if (p.transposed) {                 // dout = din*2 - 1 + kd
+                    const int t2 = dout + 1 - kd;
+                    din = (t2 >= 0 && (t2 & 1) == 0) ? (t2 >> 1) : -1;
+                } else {
+                    din = dout * p.stride_d - p.dil * (p.k_d / 2) + kd * p.dil;
+                }
+                if (din >= 0 && din < p.Din) {
+                    tap_tbl[2 + 2 * nt] = nt * MT * 128;
+                    tap_tbl[3 + 2 * nt] = kd;
+                    tap_tbl[2 + 2 * MAX_TAPS + nt] = din;
+                    ++nt;
+                }
+            }
+            tap_tbl[1] = nt * MT * 128;
+        }
+        tap_tbl[0] = nt;
     }
     if (warp == NPROD / 32) {   // MMA warp allocates TMEM
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ncols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // position table: offset of padded-linear position (q0 - halo + i) inside the plane, or -1 (zero)
-    for (int i = tid; i < p.NPOS; i += NTHREADS) {
-        const int q = q0 - p.halo + i;
+    __syncthreads();
+    const int ntap = tap_tbl[0];
+    const int npos = tap_tbl[1];               // staged positions actually used (<= p.NPOS)
+    // position table: element offset (relative to in_b + c*isC) of staged position i, or -1 (zero)
+    const int HW = p.H * p.W;
+    for (int i = tid; i < npos; i += NTHREADS) {
         int off = -1;
-        if (q >= 0) {
-            const int y = q / p.PW, x = q - y * p.PW;
-            if (y < p.H && x < p.W) off = y * p.W + x;
+        if (p.mode == MODE_HW3) {
+            const int q = q0 - p.halo + i;
+            if (q >= 0) {
+                const int y = q / p.PW, x = q - y * p.PW;
+                if (y < p.H && x < p.W) off = dout * (int)p.isD + y * p.W + x;
+            }
+        } else {
+            const int t = i / (MT * 128), q = q0 + (i - t * MT * 128);
+            if (q < HW) off = tap_tbl[2 + 2 * MAX_TAPS + t] * (int)p.isD + q;
         }
         pos_tbl[i] = off;
     }
@@ -164,7 +216,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_hw3_tc_kernel(const Params p
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < NPROD / 32) {
+    if (ntap == 0) {
+        // no input plane contributes (cannot happen for the supported k / stride / padding combinations)
+    } else if (warp < NPROD / 32) {
         // ===================== producers / accumulator readers =====================
         const int quarter = warp & 3;                 // TMEM lanes this warp may read
         const int half = warp >> 2;                   // which M-tiles it drains
@@ -214,9 +268,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_hw3_tc_kernel(const Params p
             const uint32_t a_lo = a_hi + 2u * p.NPOS * 16u;                // part 1 (lo)
             const uint32_t khalf = (uint32_t)p.NPOS * 16u;
             const int c0 = k * 8;
-            const float* src = in_pl + (long long)c0 * p.isC;
+            const float* src = in_b + (long long)c0 * p.isC;
 #pragma unroll 2
-            for (int i = tid; i < p.NPOS; i += NPROD) {
+            for (int i = tid; i < npos; i += NPROD) {
                 const int off = pos_tbl[i];
                 float v[8];
 #pragma unroll
@@ -240,7 +294,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_hw3_tc_kernel(const Params p
         drain(p.nchunk - 1);
 
         // ===================== epilogue: bias + activation from the register accumulators =====================
-        float* out_pl = p.out + (long long)b * p.osB + (long long)d * p.osD;
+        float* out_pl = p.out + (long long)b * p.osB + (long long)dout * p.osD;
 #pragma unroll
         for (int jj = 0; jj < JT; ++jj) {
             const int j = half + 2 * jj;
@@ -260,7 +314,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_hw3_tc_kernel(const Params p
         }
     } else {
         // ===================== MMA issuer =====================
-        // instruction descriptor: D fp32, A/B tf32, both K-major, N, M = 128
+        // instruction descriptor: D fp32, A/B tf32, both K-major, N (or 2N), M = 128
         constexpr uint32_t idesc_n = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
         constexpr uint32_t idesc_2n = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(2 * N >> 3) << 17) | ((128u >> 4) << 24);
         const uint32_t a_lbo = (uint32_t)p.NPOS * 16u, b_lbo = 2u * N * 16u;
@@ -278,16 +332,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_hw3_tc_kernel(const Params p
 #pragma unroll 1
                 for (int j = 0; j < MT; ++j) {
                     const uint32_t d_tmem = tmem_base + (uint32_t)(bf * TOTAL + j * 2 * N);
-                    const uint32_t a_row0 = (uint32_t)(p.halo + j * 128) * 16u;
-#pragma unroll
-                    for (int t = 0; t < 9; ++t) {
-                        const int ky = t / 3 - 1, kx = t % 3 - 1;
-                        const int toff = (ky * p.dil * p.PW + kx * p.dil) * 16;
-                        const uint64_t bd = make_desc(b_base + (uint32_t)(t * 2 * 2 * N * 16), b_lbo, 128u);
+#pragma unroll 1
+                    for (int t = 0; t < ntap; ++t) {
+                        const uint32_t aoff = (uint32_t)(tap_tbl[2 + 2 * t] + j * 128) * 16u;
+                        const uint64_t bd = make_desc(b_base + (uint32_t)(tap_tbl[3 + 2 * t] * 2 * 2 * N * 16), b_lbo, 128u);
                         // [D1 | D2] (+)= A_hi * [B_hi | B_lo]   (first MMA of the chunk overwrites both blocks)
-                        tc_mma_tf32(d_tmem, make_desc(a_part[0] + a_row0 + toff, a_lbo, 128u), bd, idesc_2n, t != 0 ? 1u : 0u);
+                        tc_mma_tf32(d_tmem, make_desc(a_part[0] + aoff, a_lbo, 128u), bd, idesc_2n, t != 0 ? 1u : 0u);
                         // D1 += A_lo * B_hi
-                        tc_mma_tf32(d_tmem, make_desc(a_part[1] + a_row0 + toff, a_lbo, 128u), bd, idesc_n, 1u);
+                        tc_mma_tf32(d_tmem, make_desc(a_part[1] + aoff, a_lbo, 128u), bd, idesc_n, 1u);
                     }
                 }
                 tc_commit(&empty[s]);        // stage free once these MMAs have read it
@@ -304,6 +356,64 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_hw3_tc_kernel(const Params p
     }
 }
 
+// shared memory of a launch: stages x (A + B) + position table + barriers / tap table
+static size_t smem_need(int stages, long long npos, int T, int N) {
+    return (size_t)stages * ((size_t)npos * 64 + (size_t)T * 64 * N) + (size_t)((npos * 4 + 15) & ~15ll) + 384;
+}
+
+// picks MT in {1,2,4,8} (ceil(MT/2)*N <= 64 register accumulators per thread) and the stage count; launches.
+static int launch(Params& p, int N, long long positions_per_plane, int planes, int halo, int taps_staged, cudaStream_t st,
+                  const char* what) {
+    int best_mt = 0, best_stages = 2;
+    double best_cost = 1e30;
+    for (int mt = 1; mt <= 8; mt *= 2) {
+        if (((mt + 1) / 2) * N > 64) continue;
+        const long long npos = (long long)taps_staged * mt * 128 + 2 * halo;
+        if (smem_need(2, npos, p.T, N) > SMEM_MAX) continue;
+        int stages = 2;
+        while (stages < MAX_STAGES && smem_need(stages + 1, npos, p.T, N) <= SMEM_MAX) ++stages;
+        const long long tiles = (positions_per_plane + mt * 128 - 1) / (mt * 128);
+        const long long waves = (tiles * planes + 147) / 148;
+        // cost model: waves x (outputs + halo re-staging + fixed per-CTA cost); fewer, fuller waves win
+        const double cost = (double)waves * ((double)mt * 128 + 2.0 * halo * 0.6 + 96.0);
+        if (cost < best_cost) {
+            best_cost = cost;
+            best_mt = mt;
+            best_stages = stages;
+        }
+    }
+    TS_REQUIRE(best_mt > 0, "%s: tile does not fit shared memory (row pitch %d)", what, p.PW);
+    p.stages = best_stages;
+    p.halo = halo;
+    p.NPOS = taps_staged * best_mt * 128 + 2 * halo;
+    p.tiles_per_plane = (int)((positions_per_plane + best_mt * 128 - 1) / (best_mt * 128));
+    const size_t smem_bytes = smem_need(p.stages, p.NPOS, p.T, N);
+    dim3 grid(p.tiles_per_plane, planes);
+    bool launched = false;
+#define TS_TC(NN, MM)                                                                                               \
+    if (N == NN && best_mt == MM) {                                                                                 \
+        auto kern = conv_tc_kernel<NN, MM>;                                                                         \
+        static bool attr_done = false;                                                                              \
+        if (!attr_done) {                                                                                           \
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX); \
+            if (e != cudaSuccess) {                                                                                 \
+                set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));                             \
+                return TSTEREO_E_CUDA;                                                                              \
+            }                                                                                                       \
+            attr_done = true;                                                                                       \
+        }                                                                                                           \
+        kern<<<grid, NTHREADS, smem_bytes, st>>>(p);                                                                \
+        launched = true;                                                                                            \
+    }
+    TS_TC(16, 1) TS_TC(16, 2) TS_TC(16, 4) TS_TC(16, 8)
+    TS_TC(32, 1) TS_TC(32, 2) TS_TC(32, 4)
+    TS_TC(48, 1) TS_TC(48, 2)
+    TS_TC(64, 1) TS_TC(64, 2)
+#undef TS_TC
+    TS_REQUIRE(launched, "%s: no kernel instance for N=%d MT=%d", what, N, best_mt);
+    return check_launch(what);
+}
+
 }  // namespace tc
 }  // namespace tstereo
 
@@ -311,9 +421,9 @@ using namespace tstereo;
 
 extern "C" {
 
-long long tstereo_conv_hw3_tc_wpack_floats(int Cin, int Cout) {
+long long tstereo_conv_tc_wpack_floats(int Cin, int Cout, int taps) {
     const long long N = (Cout + 15) / 16 * 16, nchunk = (Cin + 7) / 8;
-    return nchunk * 2 * 9 * 2 * N * 4;
+    return nchunk * taps * 2 * 2 * N * 4;
 }
 
 int tstereo_conv_hw3_tc(const float* in, long long isB, long long isC, long long isD,
@@ -326,66 +436,48 @@ int tstereo_conv_hw3_tc(const float* in, long long isB, long long isC, long long
     TS_REQUIRE(dilation == 1 || dilation == 2, "conv_hw3_tc: dilation %d unsupported", dilation);
     TS_REQUIRE((long long)B * D <= 65535, "conv_hw3_tc: B*D exceeds grid.y");
     TS_REQUIRE((((size_t)wpack) & 15) == 0, "conv_hw3_tc: packed weights must be 16-byte aligned");
-    const int N = (Cout + 15) / 16 * 16;
-    tc::Params p;
+    TS_REQUIRE((long long)D * isD + (long long)H * W < (1ll << 31), "conv_hw3_tc: plane offsets exceed 32 bits");
+    tc::Params p = {};
     p.in = in; p.isB = isB; p.isC = isC; p.isD = isD;
     p.out = out; p.osB = osB; p.osC = osC; p.osD = osD;
     p.wpack = wpack; p.bias = bias;
-    p.Cin = Cin; p.Cout = Cout; p.D = D; p.H = H; p.W = W;
+    p.mode = tc::MODE_HW3; p.T = 9;
+    p.Cin = Cin; p.Cout = Cout; p.H = H; p.W = W; p.Din = D; p.Dout = D;
     p.dil = dilation; p.act = act;
     p.PW = W + dilation;
-    p.halo = dilation * p.PW + dilation;
     p.nchunk = (Cin + 7) / 8;
-    const long long total_pos = (long long)H * p.PW;
-    // M-tiles per CTA: MT in {1,2,4,8} with ceil(MT/2)*N <= 64 register accumulators per thread; shared memory must
-    // hold >= 2 stages.  Cost model: waves x (outputs + halo re-staging) per CTA — fewer, fuller waves win.
-    const int planes = B * D;
-    int best_mt = 0, best_stages = 2;
-    double best_cost = 1e30;
-    for (int mt = 1; mt <= 8; mt *= 2) {
-        if (((mt + 1) / 2) * N > 64) continue;
-        const long long npos = (long long)mt * 128 + 2 * p.halo;
-        const size_t stage = (size_t)npos * 64 + (size_t)576 * N;
-        const size_t fixed = (size_t)((npos * 4 + 15) & ~15ll) + 128;
-        if (fixed + 2 * stage > 227 * 1024) continue;
-        int stages = (int)((227 * 1024 - fixed) / stage);
-        if (stages > tc::MAX_STAGES) stages = tc::MAX_STAGES;
-        const long long tiles = (total_pos + mt * 128 - 1) / (mt * 128);
-        const long long waves = (tiles * planes + 147) / 148;
-        const double cost = (double)waves * ((double)mt * 128 + 2.0 * p.halo * 0.6 + 96.0);
-        if (cost < best_cost) {
-            best_cost = cost;
-            best_mt = mt;
-            best_stages = stages;
-        }
+    return tc::launch(p, (Cout + 15) / 16 * 16, (long long)H * p.PW, B * D, dilation * p.PW + dilation, 1,
+                      (cudaStream_t)stream, "conv_hw3_tc");
+}
+
+int tstereo_conv_d_tc(const float* in, long long isB, long long isC, long long isD,
+                      float* out, long long osB, long long osC, long long osD,
+                      const float* wpack, const float* bias,
+                      int B, int Cin, int Cout, int Din, int Dout, int H, int W,
+                      int k, int stride, int dilation, int transposed, int act, void* stream) {
+    TS_REQUIRE(in && out && wpack, "conv_d_tc: null pointer");
+    TS_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && Cout <= 64 && Din > 0 && Dout > 0 && H > 0 && W > 0, "conv_d_tc: bad sizes (Cout <= 64)");
+    TS_REQUIRE(k == 3 || k == 5, "conv_d_tc: k=%d unsupported", k);
+    if (transposed) {
+        TS_REQUIRE(k == 3 && Dout == 2 * Din, "conv_d_tc: transposed needs k=3, Dout=2*Din (got k=%d Din=%d Dout=%d)", k, Din, Dout);
+    } else {
+        TS_REQUIRE((stride == 1 || stride == 2) && (dilation == 1 || dilation == 2), "conv_d_tc: bad stride/dilation");
+        TS_REQUIRE(Dout == (Din - 1) / stride + 1, "conv_d_tc: Dout=%d inconsistent with Din=%d stride=%d", Dout, Din, stride);
     }
-    TS_REQUIRE(best_mt > 0, "conv_hw3_tc: row pitch %d too wide for the shared-memory tile", p.PW);
-    p.stages = best_stages;
-    p.NPOS = best_mt * 128 + 2 * p.halo;
-    p.tiles_per_plane = (int)((total_pos + best_mt * 128 - 1) / (best_mt * 128));
-    const size_t smem_bytes = (size_t)p.stages * ((size_t)p.NPOS * 64 + (size_t)576 * N) + (size_t)((p.NPOS * 4 + 15) & ~15) + 128;
-    dim3 grid(p.tiles_per_plane, planes);
-    cudaStream_t st = (cudaStream_t)stream;
-#define TS_TC(NN, MM)                                                                                               \
-    if (N == NN && best_mt == MM) {                                                                                 \
-        auto kern = tc::conv_hw3_tc_kernel<NN, MM>;                                                                 \
-        static bool attr_done = false;                                                                              \
-        if (!attr_done) {                                                                                           \
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);    \
-            if (e != cudaSuccess) {                                                                                 \
-                set_error("conv_hw3_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));                          \
-                return TSTEREO_E_CUDA;                                                                              \
-            }                                                                                                       \
-            attr_done = true;                                                                                       \
-        }                                                                                                           \
-        kern<<<grid, tc::NTHREADS, smem_bytes, st>>>(p);                                                            \
-    }
-    TS_TC(16, 1) TS_TC(16, 2) TS_TC(16, 4) TS_TC(16, 8)
-    TS_TC(32, 1) TS_TC(32, 2) TS_TC(32, 4)
-    TS_TC(48, 1) TS_TC(48, 2)
-    TS_TC(64, 1) TS_TC(64, 2)
-#undef TS_TC
-    return check_launch("conv_hw3_tc");
+    TS_REQUIRE((long long)B * Dout <= 65535, "conv_d_tc: B*Dout exceeds grid.y");
+    TS_REQUIRE((((size_t)wpack) & 15) == 0, "conv_d_tc: packed weights must be 16-byte aligned");
+    TS_REQUIRE((long long)Din * isD + (long long)H * W < (1ll << 31), "conv_d_tc: plane offsets exceed 32 bits");
+    tc::Params p = {};
+    p.in = in; p.isB = isB; p.isC = isC; p.isD = isD;
+    p.out = out; p.osB = osB; p.osC = osC; p.osD = osD;
+    p.wpack = wpack; p.bias = bias;
+    p.mode = tc::MODE_D; p.T = k;
+    p.Cin = Cin; p.Cout = Cout; p.H = H; p.W = W; p.Din = Din; p.Dout = Dout;
+    p.dil = dilation; p.act = act;
+    p.PW = W;                                   // no padding columns: positions are the plane's pixels
+    p.k_d = k; p.stride_d = stride; p.transposed = transposed;
+    p.nchunk = (Cin + 7) / 8;
+    return tc::launch(p, (Cout + 15) / 16 * 16, (long long)H * W, B * Dout, 0, k, (cudaStream_t)stream, "conv_d_tc");
 }
 
 }  // extern "C"

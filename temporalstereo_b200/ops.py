@@ -113,18 +113,21 @@ def tf32_split(w: torch.Tensor):
     return hi, rna(w - hi)
 
 
-def pack_conv_hw3_tc(w: torch.Tensor) -> torch.Tensor:
-    """[Cout, Cin, 9] (BN folded) -> the tcgen05 B-operand image [ceil(Cin/8)][tap 9][khalf 2][part 2][N][4]:
-    per (chunk, tap) a K-major 2N x 8 matrix whose rows are [tf32 hi part | tf32 lo part] of the weights."""
-    cout, cin, taps = w.shape
-    assert taps == 9
+def pack_conv_tc(w: torch.Tensor) -> torch.Tensor:
+    """[Cout, Cin, T] (BN folded; T = 9 taps ky*3+kx, or k taps along D) -> the tcgen05 B-operand image
+    [ceil(Cin/8)][tap T][khalf 2][part 2][N][4]: per (chunk, tap) a K-major 2N x 8 matrix whose rows are
+    [tf32 hi part | tf32 lo part] of the weights."""
+    cout, cin, T = w.shape
     N, nch = (cout + 15) // 16 * 16, (cin + 7) // 8
-    full = torch.zeros((N, nch * 8, 9), device=w.device, dtype=torch.float32)
+    full = torch.zeros((N, nch * 8, T), device=w.device, dtype=torch.float32)
     full[:cout, :cin] = w
     hi, lo = tf32_split(full)
-    parts = torch.stack([hi, lo])                                     # [2, N, nch*8, 9]
-    parts = parts.view(2, N, nch, 2, 4, 9)                            # [part, n, chunk, khalf, i, tap]
+    parts = torch.stack([hi, lo])                                     # [2, N, nch*8, T]
+    parts = parts.view(2, N, nch, 2, 4, T)                            # [part, n, chunk, khalf, i, tap]
     return parts.permute(2, 5, 3, 0, 1, 4).contiguous().view(-1)      # [chunk, tap, khalf, part, n, i]
+
+
+pack_conv_hw3_tc = pack_conv_tc
 
 
 def conv_hw3_tc(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Tensor], cout: int, dilation: int = 1,
@@ -139,9 +142,25 @@ def conv_hw3_tc(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Tenso
     isB, isC, isD = _view5(x)
     osB, osC, osD = _view5(out)
     _chk(wpack, bias)
-    assert wpack.numel() == _lib.load().tstereo_conv_hw3_tc_wpack_floats(Cin, cout)
+    assert wpack.numel() == _lib.load().tstereo_conv_tc_wpack_floats(Cin, cout, 9)
     _lib.call("tstereo_conv_hw3_tc", _p(x), isB, isC, isD, _p(out), osB, osC, osD, _p(wpack), _p(bias),
               B, Cin, cout, D, H, W, dilation, ACT[act], _stream())
+    return out
+
+
+def conv_d_tc(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Tensor], cout: int, k: int = 3, stride: int = 1,
+              dilation: int = 1, transposed: bool = False, act=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(k,1,1) conv along D (or its stride-2 transposed form) on the tensor cores (tcgen05, 3xTF32)."""
+    B, Cin, Din, H, W = x.shape
+    Dout = 2 * Din if transposed else (Din - 1) // stride + 1
+    if out is None:
+        out = torch.empty((B, cout, Dout, H, W), device=x.device, dtype=torch.float32)
+    isB, isC, isD = _view5(x)
+    osB, osC, osD = _view5(out)
+    _chk(wpack, bias)
+    assert wpack.numel() == _lib.load().tstereo_conv_tc_wpack_floats(Cin, cout, k)
+    _lib.call("tstereo_conv_d_tc", _p(x), isB, isC, isD, _p(out), osB, osC, osD, _p(wpack), _p(bias),
+              B, Cin, cout, Din, Dout, H, W, k, stride, dilation, int(transposed), ACT[act], _stream())
     return out
 
 
