@@ -89,6 +89,10 @@ class TEMPORALSTEREO(nn.Module):
         # stride-1 3x3 contractions on tcgen05 with error-compensated 3xTF32 operands (fp32-equivalent);
         # False keeps every contraction on the fp32 FMA pipe
         self.tensor_cores = True
+        # per-(layer shape) choice between the tensor-core and the fp32-FMA kernel: "auto" times both on the
+        # first call of a shape (outside CUDA-graph capture) and keeps the faster; "tc" / "simt" force one
+        self.plan_mode = "auto"
+        self._plan: Dict[tuple, str] = {}
         self.register_load_state_dict_post_hook(lambda m, _k: m.invalidate())
         super().train(False)
 
@@ -239,17 +243,42 @@ class TEMPORALSTEREO(nn.Module):
         return pk
 
     # ------------------------------------------------------------------ building blocks
+    def _pick(self, key, run_tc, run_simt):
+        """Plan cache (per-shape plan cache): which of the two kernels runs this layer shape."""
+        choice = self._plan.get(key) if self.plan_mode == "auto" else self.plan_mode
+        if choice is None:
+            if torch.cuda.is_current_stream_capturing():
+                choice = "tc"
+            else:
+                times = []
+                for fn in (run_tc, run_simt):
+                    fn()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(3):
+                        fn()
+                    e1.record()
+                    e1.synchronize()
+                    times.append(e0.elapsed_time(e1))
+                choice = "tc" if times[0] <= times[1] else "simt"
+                self._plan[key] = choice
+        return run_tc() if choice == "tc" else run_simt()
+
     def _hw3(self, x, k: _Packed, stride=1, dil=1, act=None, out=None):
-        """3x3 conv over (H,W): tensor cores for stride 1, fp32 FMA kernel otherwise."""
-        if k.wtc is not None and stride == 1 and self.tensor_cores:
-            return ops.conv_hw3_tc(x, k.wtc, k.b, k.cout, dil, act, out=out)
-        return ops.conv_hw3(x, k.w, k.b, k.cout, stride, dil, act, out=out)
+        """3x3 conv over (H,W): tensor cores (stride 1) or the fp32 FMA kernel, per the plan."""
+        simt = lambda: ops.conv_hw3(x, k.w, k.b, k.cout, stride, dil, act, out=out)
+        if k.wtc is None or stride != 1 or not self.tensor_cores:
+            return simt()
+        key = ("hw3", tuple(x.shape), k.cout, dil)
+        return self._pick(key, lambda: ops.conv_hw3_tc(x, k.wtc, k.b, k.cout, dil, act, out=out), simt)
 
     def _d(self, x, k: _Packed, ksz=3, stride=1, dil=1, transposed=False, act=None, out=None):
         """(k,1,1) conv along D: tensor cores when a tcgen05 operand image exists."""
-        if k.wtc is not None and self.tensor_cores:
-            return ops.conv_d_tc(x, k.wtc, k.b, k.cout, ksz, stride, dil, transposed, act, out=out)
-        return ops.conv_d(x, k.w, k.b, k.cout, ksz, stride, dil, transposed, act, out=out)
+        simt = lambda: ops.conv_d(x, k.w, k.b, k.cout, ksz, stride, dil, transposed, act, out=out)
+        if k.wtc is None or not self.tensor_cores:
+            return simt()
+        key = ("d", tuple(x.shape), k.cout, ksz, stride, dil, transposed)
+        return self._pick(key, lambda: ops.conv_d_tc(x, k.wtc, k.b, k.cout, ksz, stride, dil, transposed, act, out=out), simt)
 
     def _sep(self, x, p, stride=1, dil=1, act0="SiLU", act1="SiLU", out=None):
         """'DepthwiseConv3D': (1,3,3) conv then (3,1,1) conv, BN folded (reference module.py:111-147)."""

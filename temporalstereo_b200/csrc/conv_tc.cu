@@ -269,23 +269,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const Params p) {
             const uint32_t khalf = (uint32_t)p.NPOS * 16u;
             const int c0 = k * 8;
             const float* src = in_b + (long long)c0 * p.isC;
-#pragma unroll 2
-            for (int i = tid; i < npos; i += NPROD) {
-                const int off = pos_tbl[i];
-                float v[8];
+            // PB positions per thread per batch: all PB*8 global loads are issued before the first
+            // conversion, so one memory latency covers the whole batch
+            constexpr int PB = 4;
+            for (int i0 = tid; i0 < npos; i0 += NPROD * PB) {
+                float v[PB][8];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) v[c] = (off >= 0 && c0 + c < p.Cin) ? __ldg(src + (long long)c * p.isC + off) : 0.f;
-                uint32_t hi[8], lo[8];
+                for (int u = 0; u < PB; ++u) {
+                    const int i = i0 + u * NPROD;
+                    const int off = (i < npos) ? pos_tbl[i] : -1;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    hi[c] = f2tf32(v[c]);
-                    lo[c] = f2tf32(v[c] - __uint_as_float(hi[c]));
+                    for (int c = 0; c < 8; ++c)
+                        v[u][c] = (off >= 0 && c0 + c < p.Cin) ? __ldg(src + (long long)c * p.isC + off) : 0.f;
                 }
-                const uint32_t o = (uint32_t)i * 16u;
-                sts128(a_hi + o, hi[0], hi[1], hi[2], hi[3]);
-                sts128(a_hi + khalf + o, hi[4], hi[5], hi[6], hi[7]);
-                sts128(a_lo + o, lo[0], lo[1], lo[2], lo[3]);
-                sts128(a_lo + khalf + o, lo[4], lo[5], lo[6], lo[7]);
+#pragma unroll
+                for (int u = 0; u < PB; ++u) {
+                    const int i = i0 + u * NPROD;
+                    if (i < npos) {
+                        uint32_t hi[8], lo[8];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            hi[c] = f2tf32(v[u][c]);
+                            lo[c] = f2tf32(v[u][c] - __uint_as_float(hi[c]));
+                        }
+                        const uint32_t o = (uint32_t)i * 16u;
+                        sts128(a_hi + o, hi[0], hi[1], hi[2], hi[3]);
+                        sts128(a_hi + khalf + o, hi[4], hi[5], hi[6], hi[7]);
+                        sts128(a_lo + o, lo[0], lo[1], lo[2], lo[3]);
+                        sts128(a_lo + khalf + o, lo[4], lo[5], lo[6], lo[7]);
+                    }
+                }
             }
             fence_proxy_async();          // generic-proxy st.shared -> visible to the tensor core (async proxy)
             mbar_arrive(&full[s]);
