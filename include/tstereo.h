@@ -79,6 +79,17 @@ int tstereo_conv_hw3_tc(const float* in, long long isB, long long isC, long long
                         const float* wpack, const float* bias,
                         int B, int Cin, int Cout, int D, int H, int W,
                         int dilation, int act, void* stream);
+/* Second-generation tensor-core 3x3 conv (stride 1, dilation 1|2, Cout <= 32): 2-D tiles, the three kx taps
+ * folded into the MMA's N dimension, 3xTF32 operands (same results as tstereo_conv_hw3 to fp32 rounding).
+ * ref: layers/basic_layers.py:194-235 via aggregation/TemporalStereo/module.py:111-147, 424-492.
+ * wpack: [ceil(Cin/8)][ky 3][khalf 2][row 2N][4] floats, N = 3*CP, CP = 8|16|32 >= Cout,
+ * row = part*N + kx*CP + co (part 0 = tf32 hi, 1 = tf32 lo); tstereo_conv_hw3_tc2_wpack_floats(Cin, Cout) floats. */
+long long tstereo_conv_hw3_tc2_wpack_floats(int Cin, int Cout);
+int tstereo_conv_hw3_tc2(const float* in, long long isB, long long isC, long long isD,
+                         float* out, long long osB, long long osC, long long osD,
+                         const float* wpack, const float* bias,
+                         int B, int Cin, int Cout, int D, int H, int W,
+                         int dilation, int act, void* stream);
 int tstereo_conv_d_tc(const float* in, long long isB, long long isC, long long isD,
                       float* out, long long osB, long long osC, long long osD,
                       const float* wpack, const float* bias,

@@ -36,11 +36,12 @@ class _Node(nn.Module):
 
 
 class _Packed:
-    __slots__ = ("w", "b", "cout", "wtc")
+    __slots__ = ("w", "b", "cout", "wtc", "wtc2")
 
-    def __init__(self, w, b, cout, wtc=None):
+    def __init__(self, w, b, cout, wtc=None, wtc2=None):
         self.w, self.b, self.cout = w, b, cout
-        self.wtc = wtc          # tcgen05 (3xTF32) operand image of a 3x3 conv, or None
+        self.wtc = wtc          # tcgen05 (3xTF32) operand image of a 3x3 / (k,1,1) conv, or None
+        self.wtc2 = wtc2        # operand image of the kx-folded tcgen05 3x3 kernel (Cout <= 32), or None
 
 
 def _level_cfg(node, defaults: dict) -> dict:
@@ -184,9 +185,12 @@ class TEMPORALSTEREO(nn.Module):
         wtc = None
         is_hw = conv.endswith(".conv.0") or ".refinement." in conv or ".mask." in conv     # (1,k,k) / 2-D kernels
         tc_ok = (w.shape[2] == 9 and not transposed) if is_hw else w.shape[2] in (3, 5)
+        wtc2 = None
         if tc_ok and cout <= 64 and cin >= 8 and w.is_cuda and self.tensor_cores:
             wtc = ops.pack_conv_tc(w)
-        return _Packed(packed.contiguous(), None if bias is None else bias.contiguous(), cout, wtc)
+            if is_hw and cout <= 32:
+                wtc2 = ops.pack_conv_hw3_tc2(w)
+        return _Packed(packed.contiguous(), None if bias is None else bias.contiguous(), cout, wtc, wtc2)
 
     def _pack(self) -> Dict[str, _Packed]:
         sd = dict(self.state_dict(keep_vars=True))
@@ -243,15 +247,23 @@ class TEMPORALSTEREO(nn.Module):
         return pk
 
     # ------------------------------------------------------------------ building blocks
-    def _pick(self, key, run_tc, run_simt):
-        """Plan cache (per-shape plan cache): which of the two kernels runs this layer shape."""
-        choice = self._plan.get(key) if self.plan_mode == "auto" else self.plan_mode
+    def _pick(self, key, cands):
+        """Plan cache (per-shape plan cache): which kernel runs this layer shape.
+        `cands` maps a kernel name ("tc2", "tc", "simt") to a thunk; plan_mode "auto" times each on the first
+        call of a shape (outside CUDA-graph capture) and keeps the fastest; any other plan_mode forces that
+        kernel where it exists."""
+        names = list(cands)
+        if self.plan_mode != "auto":
+            choice = self.plan_mode if self.plan_mode in cands else names[0]
+        else:
+            choice = self._plan.get(key)
         if choice is None:
-            if torch.cuda.is_current_stream_capturing():
-                choice = "tc"
+            if torch.cuda.is_current_stream_capturing() or len(names) == 1:
+                choice = names[0]
             else:
                 times = []
-                for fn in (run_tc, run_simt):
+                for nme in names:
+                    fn = cands[nme]
                     fn()
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record()
@@ -260,17 +272,21 @@ class TEMPORALSTEREO(nn.Module):
                     e1.record()
                     e1.synchronize()
                     times.append(e0.elapsed_time(e1))
-                choice = "tc" if times[0] <= times[1] else "simt"
+                choice = names[times.index(min(times))]
                 self._plan[key] = choice
-        return run_tc() if choice == "tc" else run_simt()
+        return cands[choice]()
 
     def _hw3(self, x, k: _Packed, stride=1, dil=1, act=None, out=None):
         """3x3 conv over (H,W): tensor cores (stride 1) or the fp32 FMA kernel, per the plan."""
         simt = lambda: ops.conv_hw3(x, k.w, k.b, k.cout, stride, dil, act, out=out)
         if k.wtc is None or stride != 1 or not self.tensor_cores:
             return simt()
-        key = ("hw3", tuple(x.shape), k.cout, dil)
-        return self._pick(key, lambda: ops.conv_hw3_tc(x, k.wtc, k.b, k.cout, dil, act, out=out), simt)
+        cands = {}
+        if k.wtc2 is not None:
+            cands["tc2"] = lambda: ops.conv_hw3_tc2(x, k.wtc2, k.b, k.cout, dil, act, out=out)
+        cands["tc"] = lambda: ops.conv_hw3_tc(x, k.wtc, k.b, k.cout, dil, act, out=out)
+        cands["simt"] = simt
+        return self._pick(("hw3", tuple(x.shape), k.cout, dil), cands)
 
     def _d(self, x, k: _Packed, ksz=3, stride=1, dil=1, transposed=False, act=None, out=None):
         """(k,1,1) conv along D: tensor cores when a tcgen05 operand image exists."""
@@ -278,7 +294,8 @@ class TEMPORALSTEREO(nn.Module):
         if k.wtc is None or not self.tensor_cores:
             return simt()
         key = ("d", tuple(x.shape), k.cout, ksz, stride, dil, transposed)
-        return self._pick(key, lambda: ops.conv_d_tc(x, k.wtc, k.b, k.cout, ksz, stride, dil, transposed, act, out=out), simt)
+        return self._pick(key, {"tc": lambda: ops.conv_d_tc(x, k.wtc, k.b, k.cout, ksz, stride, dil, transposed, act, out=out),
+                                "simt": simt})
 
     def _sep(self, x, p, stride=1, dil=1, act0="SiLU", act1="SiLU", out=None):
         """'DepthwiseConv3D': (1,3,3) conv then (3,1,1) conv, BN folded (reference module.py:111-147)."""

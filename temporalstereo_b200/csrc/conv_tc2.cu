@@ -1,0 +1,372 @@
+// Tensor-core (tcgen05, sm_100a) 3x3 convolution over (H,W), second generation: 2-D tiles with the kx taps
+// folded into the MMA's N dimension  (SURVEY.md §8 rows a4-a7, a9, a12, a13).
+//
+// ref: architecture/modeling/layers/basic_layers.py:194-235 (Conv3d: conv -> BN -> act) as used by the (1,3,3)
+//      halves of aggregation/TemporalStereo/module.py:111-147 and the 2-D convs of :424-492.
+//
+// Why a second kernel: the first one (conv_tc.cu) issues one MMA pair per tap, i.e. the A operand (128
+// positions x 8 channels) is read from shared memory 18 times per chunk, and its linear position tiles stage a
+// halo of a full image row on both sides.  Here
+//   * a CTA owns a TR x (32 - 2*dil) output tile; the staged input is (TR + 2*dil) rows x 32 columns, position
+//     index = row*32 + col, so one warp-wide TMEM lane quarter is exactly one tile row;
+//   * the three kx taps are columns of the B operand: per ky ONE product
+//         P[pos][kx][co] (+)= A[pos + ky*dil*32][ch] * W[ky][kx][ch][co]
+//     (N = 3*CP), and the output is  out[x] = P[x][kx=0] + P[x+dil][kx=1] + P[x+2*dil][kx=2]  — two warp
+//     shuffles per channel in the epilogue.  A is read 6 times per chunk instead of 18;
+//   * 3xTF32 error compensation as before: D[0:2N) += A_hi*[B_hi|B_lo],  D[0:N) += A_lo*B_hi;
+//   * the tensor core's accumulate truncates, so TMEM accumulates only G chunks (3*8*G products
+//     per term) before the producer warps add the partial sums into fp32 registers; the MMA warp moves on to
+//     the next M-tile meanwhile (per-M-tile full/empty barriers instead of a second TMEM buffer);
+//   * producers prefetch the next chunk's 8 channel rows into registers before converting the current one, and
+//     the small variants run two CTAs per SM, so global-load latency overlaps the MMAs of the other CTA.
+//
+//  warps 0-7 : producers (global NCDHW fp32 -> hi/lo tf32 -> K-major SWIZZLE_NONE smem) + accumulator readers
+//              + epilogue;  warp 8 : TMEM alloc, MMA issue (one elected lane), commits.
+#include "common.cuh"
+#include "tc_ptx.cuh"
+#include <cstdint>
+#include <cstdlib>
+
+namespace tstereo {
+namespace tc2 {
+
+using namespace tcp;
+
+constexpr int NPROD = 256;
+constexpr int NTHREADS = NPROD + 32;
+constexpr int MAX_STAGES = 4;
+constexpr int MAX_MT = 4;
+constexpr size_t SMEM_MAX = 227 * 1024;
+
+struct Params {
+    const float* in;
+    long long isB, isC, isD;
+    float* out;
+    long long osB, osC, osD;
+    const float* wpack;   // [nchunk][ky 3][khalf 2][row 2N][4], row = part*N + kx*CP + co
+    const float* bias;    // [Cout] or null
+    int Cin, Cout, H, W, D;
+    int dil, act, nchunk, G, stages, tiles_x;
+};
+
+// cvt.rna.tf32.f32 without the NaN/Inf handling ptxas wraps around it (operands here are finite activations)
+__device__ __forceinline__ uint32_t tf32_rna(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
+
+template <int CP, int MT>
+struct Cfg {
+    static constexpr int N = 3 * CP;                   // columns of one part block: [kx][co]
+    static constexpr int N2 = (N + 15) / 16 * 16;      // width of the A_lo MMA (M = 128 needs N % 16 == 0)
+    static constexpr int COLS = MT * 2 * N;            // TMEM columns: per M-tile [A*B_hi (N) | A_hi*B_lo (N)]
+    static constexpr int JT = (MT + 1) / 2;            // M-tiles drained per thread (tiles j = half + 2*jj)
+    static constexpr int MINB = (JT * N <= 48) ? 2 : 1;
+    static constexpr int RPW = (4 * MT + 4 + 7) / 8;   // staged rows per producer warp (dil <= 2)
+    static constexpr uint32_t NCOLS = COLS <= 32 ? 32 : COLS <= 64 ? 64 : COLS <= 128 ? 128 : COLS <= 256 ? 256 : 512;
+    static constexpr uint32_t B_BYTES = 3u * 2u * 2u * N * 16u;
+    static_assert(2 * N <= 256 && COLS <= 512, "tile does not fit one MMA / TMEM");
+};
+
+template <int CP, int MT>
+__global__ void __launch_bounds__(NTHREADS, Cfg<CP, MT>::MINB) conv_tc2_kernel(const Params p) {
+    using C = Cfg<CP, MT>;
+    constexpr int N = C::N, JT = C::JT, RPW = C::RPW;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int SR = 4 * MT + 2 * p.dil;                 // staged rows
+    const uint32_t NPOS = (uint32_t)SR * 32u;
+    const uint32_t a_bytes = 4u * NPOS * 16u;          // [part 2][khalf 2][NPOS][16 B]
+    const uint32_t stage_bytes = a_bytes + C::B_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    uint64_t* full = bars;                         // [stages]  producers -> MMA
+    uint64_t* empty = bars + MAX_STAGES;           // [stages]  MMA -> producers
+    uint64_t* acc_full = bars + 2 * MAX_STAGES;    // [MT]      MMA -> readers (a group of G chunks accumulated)
+    uint64_t* acc_empty = acc_full + MAX_MT;       // [MT]      readers -> MMA (M-tile drained)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + MAX_MT);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int plane = blockIdx.y;
+    const int b = plane / p.D, d = plane - b * p.D;
+    const int ty = blockIdx.x / p.tiles_x, tx = blockIdx.x - ty * p.tiles_x;
+    const int VW = 32 - 2 * p.dil;                     // valid output columns of a tile
+    const int y0 = ty * 4 * MT, x0 = tx * VW;
+
+    if (tid == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full[s], NPROD + 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int j = 0; j < MT; ++j) {
+            mbar_init(&acc_full[j], 1);
+            mbar_init(&acc_empty[j], NPROD / 2);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == NPROD / 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(C::NCOLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int ngroups = (p.nchunk + p.G - 1) / p.G;
+
+    if (warp < NPROD / 32) {
+        // ===================== producers / accumulator readers =====================
+        const int quarter = warp & 3;                 // TMEM lane quarter = tile row inside an M-tile
+        const int half = warp >> 2;                   // which M-tiles this warp drains
+        const float* in_pl = p.in + (long long)b * p.isB + (long long)d * p.isD;
+        // the staged rows of this warp: r = warp + 8*u; lane = staged column
+        int off[RPW];
+#pragma unroll
+        for (int u = 0; u < RPW; ++u) {
+            const int r = warp + 8 * u;
+            const int gy = y0 - p.dil + r, gx = x0 - p.dil + lane;
+            off[u] = (r < SR && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) ? gy * p.W + gx : -1;
+        }
+        float v[RPW][8];
+        auto load_chunk = [&](int k) {
+            const float* src = in_pl + (long long)(k * 8) * p.isC;
+#pragma unroll
+            for (int u = 0; u < RPW; ++u)
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    v[u][c] = (off[u] >= 0 && k * 8 + c < p.Cin) ? __ldg(src + (long long)c * p.isC + off[u]) : 0.f;
+        };
+        float acc[JT][N];
+#pragma unroll
+        for (int jj = 0; jj < JT; ++jj)
+#pragma unroll
+            for (int n = 0; n < N; ++n) acc[jj][n] = 0.f;
+
+        auto drain = [&](int g) {
+#pragma unroll
+            for (int jj = 0; jj < JT; ++jj) {
+                const int j = half + 2 * jj;
+                if (j < MT) {
+                    mbar_wait(&acc_full[j], (uint32_t)g & 1u);
+                    tc_fence_after();
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(j * 2 * N);
+#pragma unroll
+                    for (int c0 = 0; c0 < N; c0 += 8) {
+                        uint32_t rh[8], rl[8];
+                        tmem_ld8(taddr + (uint32_t)c0, rh);
+                        tmem_ld8(taddr + (uint32_t)(N + c0), rl);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) acc[jj][c0 + c] += __uint_as_float(rh[c]) + __uint_as_float(rl[c]);
+                    }
+                    tc_fence_before();
+                    mbar_arrive(&acc_empty[j]);
+                }
+            }
+        };
+
+        load_chunk(0);
+        for (int k = 0; k < p.nchunk; ++k) {
+            const int s = k % p.stages;
+            const uint32_t ph = (uint32_t)(k / p.stages) & 1u;
+            mbar_wait(&empty[s], ph ^ 1u);
+            uint8_t* st_base = smem + (size_t)s * stage_bytes;
+            if (tid == 0) {
+                mbar_arrive_expect_tx(&full[s], C::B_BYTES);
+                bulk_g2s(st_base + a_bytes, p.wpack + (size_t)k * (C::B_BYTES / 4), C::B_BYTES, &full[s]);
+            }
+            const uint32_t a_hi = smem_u32(st_base);
+            const uint32_t khalf = NPOS * 16u;
+            const uint32_t a_lo = a_hi + 2u * khalf;
+#pragma unroll
+            for (int u = 0; u < RPW; ++u) {
+                const int r = warp + 8 * u;
+                if (r < SR) {
+                    uint32_t hi[8], lo[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        hi[c] = tf32_rna(v[u][c]);
+                        lo[c] = tf32_rna(v[u][c] - __uint_as_float(hi[c]));
+                    }
+                    const uint32_t o = (uint32_t)(r * 32 + lane) * 16u;
+                    sts128(a_hi + o, hi[0], hi[1], hi[2], hi[3]);
+                    sts128(a_hi + khalf + o, hi[4], hi[5], hi[6], hi[7]);
+                    sts128(a_lo + o, lo[0], lo[1], lo[2], lo[3]);
+                    sts128(a_lo + khalf + o, lo[4], lo[5], lo[6], lo[7]);
+                }
+            }
+            if (k + 1 < p.nchunk) load_chunk(k + 1);   // in flight across the barrier traffic and the drain below
+            fence_proxy_async();                       // generic-proxy st.shared -> visible to the tensor core
+            mbar_arrive(&full[s]);
+            if (k >= 1 && k % p.G == 0) drain(k / p.G - 1);   // group finished one chunk ago: overlaps chunk k's MMAs
+        }
+        drain(ngroups - 1);
+
+        // ===================== epilogue: kx shift-sum, bias, activation, NCDHW stores =====================
+        float* out_pl = p.out + (long long)b * p.osB + (long long)d * p.osD;
+        const int x = x0 + lane;
+        const bool xok = lane < VW && x < p.W;
+#pragma unroll
+        for (int jj = 0; jj < JT; ++jj) {
+            const int j = half + 2 * jj;
+            if (j < MT) {                                  // warp-uniform
+                const int y = y0 + 4 * j + quarter;
+                float* o = out_pl + (size_t)y * p.W + x;
+#pragma unroll
+                for (int co = 0; co < CP; ++co) {
+                    const float v1 = __shfl_down_sync(0xffffffffu, acc[jj][CP + co], p.dil);
+                    const float v2 = __shfl_down_sync(0xffffffffu, acc[jj][2 * CP + co], 2 * p.dil);
+                    if (co < p.Cout && xok && y < p.H) {
+                        const float bv = p.bias ? __ldg(p.bias + co) : 0.f;
+                        o[(long long)co * p.osC] = apply_act(acc[jj][co] + v1 + v2 + bv, p.act);
+                    }
+                }
+            }
+        }
+    } else {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc_2n = idesc_tf32(2 * N), idesc_lo = idesc_tf32(C::N2);
+        const uint32_t a_lbo = NPOS * 16u, b_lbo = 2u * N * 16u;
+        for (int k = 0; k < p.nchunk; ++k) {
+            const int s = k % p.stages;
+            const uint32_t ph = (uint32_t)(k / p.stages) & 1u;
+            const int g = k / p.G;
+            const bool first = (k % p.G) == 0;
+            const bool last = (k % p.G) == p.G - 1 || k == p.nchunk - 1;
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            const uint32_t st_base = smem_u32(smem + (size_t)s * stage_bytes);
+            const uint32_t a_part0 = st_base, a_part1 = st_base + 2u * NPOS * 16u;
+            const uint32_t b_base = st_base + a_bytes;
+#pragma unroll 1
+            for (int j = 0; j < MT; ++j) {
+                if (first && g >= 1) {
+                    mbar_wait(&acc_empty[j], (uint32_t)(g - 1) & 1u);
+                    tc_fence_after();
+                }
+                if (elect_one()) {
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(j * 2 * N);
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky) {
+                        const uint32_t aoff = (uint32_t)((4 * j + ky * p.dil) * 32) * 16u;
+                        const uint64_t bd = make_desc(b_base + (uint32_t)ky * (2u * 2u * N * 16u), b_lbo, 128u);
+                        // [A*B_hi | A_hi*B_lo] (+)= A_hi * [B_hi | B_lo]
+                        tc_mma_tf32(d_tmem, make_desc(a_part0 + aoff, a_lbo, 128u), bd, idesc_2n, (first && ky == 0) ? 0u : 1u);
+                        // first block += A_lo * B_hi
+                        tc_mma_tf32(d_tmem, make_desc(a_part1 + aoff, a_lbo, 128u), bd, idesc_lo, 1u);
+                    }
+                    if (last) tc_commit(&acc_full[j]);
+                }
+                __syncwarp();
+            }
+            if (elect_one()) tc_commit(&empty[s]);      // stage reusable once every MMA above has read it
+            __syncwarp();
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == NPROD / 32) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::NCOLS) : "memory");
+    }
+}
+
+static size_t smem_need(int stages, int SR, int N) { return (size_t)stages * ((size_t)SR * 2048 + (size_t)192 * N) + 256; }
+
+template <int CP, int MT>
+static int launch_one(const Params& p, dim3 grid, size_t smem_bytes, cudaStream_t st, const char* what) {
+    auto kern = conv_tc2_kernel<CP, MT>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
+        if (e != cudaSuccess) {
+            set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
+            return TSTEREO_E_CUDA;
+        }
+        attr_done = true;
+    }
+    kern<<<grid, NTHREADS, smem_bytes, st>>>(p);
+    return check_launch(what);
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return (e && *e) ? atoi(e) : dflt;
+}
+
+static int launch(Params& p, int CP, int planes, cudaStream_t st, const char* what) {
+    const int N = 3 * CP;
+    const int VW = 32 - 2 * p.dil;
+    p.tiles_x = (p.W + VW - 1) / VW;
+    // M-tiles per CTA: 2 or 4 (TMEM: MT*2N <= 512 columns); cost = SM-time of all waves
+    int best_mt = 0, best_stages = 0;
+    double best_cost = 1e30;
+    const int forced = env_int("TSTEREO_TC2_MT", 0);
+    for (int mt = 2; mt <= 4; mt += 2) {
+        if (mt * 2 * N > 512) continue;
+        if (forced && mt != forced) continue;
+        const int jt = (mt + 1) / 2, minb = (jt * N <= 48) ? 2 : 1;
+        const int SR = 4 * mt + 2 * p.dil;
+        const size_t budget = minb == 2 ? (size_t)112 * 1024 : SMEM_MAX;
+        int stages = 0;
+        for (int s = MAX_STAGES; s >= 2; --s)
+            if (smem_need(s, SR, N) <= budget) {
+                stages = s;
+                break;
+            }
+        if (!stages) continue;
+        const long long tiles = (long long)p.tiles_x * ((p.H + 4 * mt - 1) / (4 * mt)) * planes;
+        const long long waves = (tiles + 148 * minb - 1) / (148 * minb);
+        const double cost = (double)waves * minb * (SR + 5.0) * (stages >= 3 ? 1.0 : 1.15);
+        if (cost < best_cost) {
+            best_cost = cost;
+            best_mt = mt;
+            best_stages = stages;
+        }
+    }
+    TS_REQUIRE(best_mt > 0, "%s: no tile configuration for Cout<=%d", what, CP);
+    p.stages = best_stages;
+    p.G = env_int("TSTEREO_TC2_G", 4);
+    if (p.G < 1) p.G = 1;
+    const int SR = 4 * best_mt + 2 * p.dil;
+    const size_t smem_bytes = smem_need(p.stages, SR, N);
+    dim3 grid(p.tiles_x * ((p.H + 4 * best_mt - 1) / (4 * best_mt)), planes);
+#define TS_TC2(CC, MM) \
+    if (CP == CC && best_mt == MM) return launch_one<CC, MM>(p, grid, smem_bytes, st, what);
+    TS_TC2(8, 2) TS_TC2(8, 4) TS_TC2(16, 2) TS_TC2(16, 4) TS_TC2(32, 2)
+#undef TS_TC2
+    TS_REQUIRE(false, "%s: no kernel instance for CP=%d MT=%d", what, CP, best_mt);
+}
+
+}  // namespace tc2
+}  // namespace tstereo
+
+using namespace tstereo;
+
+extern "C" {
+
+static int tc2_cp(int Cout) { return Cout <= 8 ? 8 : Cout <= 16 ? 16 : 32; }
+
+long long tstereo_conv_hw3_tc2_wpack_floats(int Cin, int Cout) {
+    const long long N = 3 * tc2_cp(Cout), nchunk = (Cin + 7) / 8;
+    return nchunk * 3 * 2 * 2 * N * 4;
+}
+
+int tstereo_conv_hw3_tc2(const float* in, long long isB, long long isC, long long isD,
+                         float* out, long long osB, long long osC, long long osD,
+                         const float* wpack, const float* bias,
+                         int B, int Cin, int Cout, int D, int H, int W,
+                         int dilation, int act, void* stream) {
+    TS_REQUIRE(in && out && wpack, "conv_hw3_tc2: null pointer");
+    TS_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && Cout <= 32 && D > 0 && H > 0 && W > 0, "conv_hw3_tc2: bad sizes (Cout <= 32)");
+    TS_REQUIRE(dilation == 1 || dilation == 2, "conv_hw3_tc2: dilation %d unsupported", dilation);
+    TS_REQUIRE((long long)B * D <= 65535, "conv_hw3_tc2: B*D exceeds grid.y");
+    TS_REQUIRE((((size_t)wpack) & 15) == 0, "conv_hw3_tc2: packed weights must be 16-byte aligned");
+    TS_REQUIRE((long long)H * W < (1ll << 31), "conv_hw3_tc2: plane exceeds 32-bit offsets");
+    tc2::Params p = {};
+    p.in = in; p.isB = isB; p.isC = isC; p.isD = isD;
+    p.out = out; p.osB = osB; p.osC = osC; p.osD = osD;
+    p.wpack = wpack; p.bias = bias;
+    p.Cin = Cin; p.Cout = Cout; p.H = H; p.W = W; p.D = D;
+    p.dil = dilation; p.act = act;
+    p.nchunk = (Cin + 7) / 8;
+    return tc2::launch(p, tc2_cp(Cout), B * D, (cudaStream_t)stream, "conv_hw3_tc2");
+}
+
+}  // extern "C"

@@ -148,6 +148,38 @@ def conv_hw3_tc(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Tenso
     return out
 
 
+def pack_conv_hw3_tc2(w: torch.Tensor) -> torch.Tensor:
+    """[Cout, Cin, 9] (BN folded, taps ky*3+kx) -> the B-operand image of tstereo_conv_hw3_tc2:
+    [ceil(Cin/8)][ky][khalf 2][row 2N][4], row = part*N + kx*CP + co, N = 3*CP, CP = 8|16|32."""
+    cout, cin, T = w.shape
+    assert T == 9 and cout <= 32
+    CP = 8 if cout <= 8 else 16 if cout <= 16 else 32
+    nch = (cin + 7) // 8
+    full = torch.zeros((CP, nch * 8, 3, 3), device=w.device, dtype=torch.float32)
+    full[:cout, :cin] = w.reshape(cout, cin, 3, 3)
+    hi, lo = tf32_split(full)
+    parts = torch.stack([hi, lo]).view(2, CP, nch, 2, 4, 3, 3)        # [part, co, chunk, khalf, i, ky, kx]
+    return parts.permute(2, 5, 3, 0, 6, 1, 4).contiguous().view(-1)   # [chunk, ky, khalf, part, kx, co, i]
+
+
+def conv_hw3_tc2(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Tensor], cout: int, dilation: int = 1,
+                 act=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Stride-1 (1,3,3) / 3x3 conv, Cout <= 32, on the tensor cores (kx-folded tcgen05 kernel, 3xTF32)."""
+    five = x.dim() == 5
+    B, Cin = x.shape[:2]
+    D = x.shape[2] if five else 1
+    H, W = x.shape[-2:]
+    if out is None:
+        out = torch.empty((B, cout, D, H, W) if five else (B, cout, H, W), device=x.device, dtype=torch.float32)
+    isB, isC, isD = _view5(x)
+    osB, osC, osD = _view5(out)
+    _chk(wpack, bias)
+    assert wpack.numel() == _lib.load().tstereo_conv_hw3_tc2_wpack_floats(Cin, cout)
+    _lib.call("tstereo_conv_hw3_tc2", _p(x), isB, isC, isD, _p(out), osB, osC, osD, _p(wpack), _p(bias),
+              B, Cin, cout, D, H, W, dilation, ACT[act], _stream())
+    return out
+
+
 def conv_d_tc(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Tensor], cout: int, k: int = 3, stride: int = 1,
               dilation: int = 1, transposed: bool = False, act=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """(k,1,1) conv along D (or its stride-2 transposed form) on the tensor cores (tcgen05, 3xTF32)."""

@@ -163,11 +163,12 @@ def test_sequence_vs_oracle(engine):
     assert d.median() < 1e-3 and frac < 0.2, (d.median().item(), frac)
 
 
-def test_idempotent_and_batch_independent(engine):
+@pytest.mark.parametrize("plan", ["tc2", "tc", "simt"])
+def test_idempotent_and_batch_independent(engine, plan):
     """Size-independent properties: same input -> bit-identical output (no atomics on the aggregation
     path); a batch of 2 equals the two frames run separately."""
     lf, rf, li, ri = synth.synthetic_frame(128, 192, B=2, seed=5)
-    engine.plan_mode = "tc"          # fixed kernel choice: the auto plan may pick different kernels per batch size
+    engine.plan_mode = plan          # fixed kernel choice: the auto plan may pick different kernels per batch size
     a = engine(_cuda(lf), _cuda(rf), li.cuda(), ri.cuda(), {})
     b = engine(_cuda(lf), _cuda(rf), li.cuda(), ri.cuda(), {})
     for x, y in zip(a[0] + a[1], b[0] + b[1]):

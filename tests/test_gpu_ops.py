@@ -464,6 +464,61 @@ def test_conv_hw3_tc_views(ops):
     assert (buf[:, :8] == 7).all() and (buf[:, 24:] == 7).all()
 
 
+TC2_CASES = [
+    # B, Cin, Cout, D, H, W, dil, act, bias
+    (1, 8, 16, 1, 8, 16, 1, None, False),
+    (1, 16, 8, 2, 9, 20, 1, "SiLU", True),
+    (1, 44, 32, 3, 17, 30, 1, "SiLU", True),
+    (2, 304, 8, 2, 20, 37, 1, "SiLU", True),
+    (1, 352, 32, 2, 34, 60, 1, "SiLU", True),
+    (1, 304, 16, 2, 19, 61, 1, "SiLU", True),
+    (1, 128, 32, 2, 34, 60, 1, None, True),
+    (1, 32, 32, 2, 17, 30, 2, "SiLU", True),
+    (1, 13, 20, 1, 10, 12, 1, None, True),
+    (1, 64, 32, 1, 40, 240, 1, "ReLU", True),
+    (1, 8, 8, 5, 136, 240, 2, "SiLU", True),
+    (1, 16, 16, 3, 5, 3, 2, "SiLU", True),
+    (2, 32, 3, 1, 1, 1, 1, None, True),
+]
+
+
+@pytest.mark.parametrize("B,Cin,Cout,D,H,W,dil,act,bias", TC2_CASES)
+def test_conv_hw3_tc2(ops, B, Cin, Cout, D, H, W, dil, act, bias):
+    """kx-folded tcgen05 conv (2-D tiles, 3xTF32 operands) == fp64 conv to fp32 rounding."""
+    x = rnd(B, Cin, D, H, W, seed=41)
+    w = rnd(Cout, Cin, 1, 3, 3, seed=42, scale=(2.0 / (9 * Cin)) ** 0.5)
+    b = rnd(Cout, seed=43, scale=0.1) if bias else None
+    want = O._act(F.conv3d(x.double(), w.double(), None if b is None else b.double(), 1, (0, dil, dil), (1, dil, dil)), act).float()
+    wp = ops.pack_conv_hw3_tc2(w.reshape(Cout, Cin, 9).cuda())
+    got = ops.conv_hw3_tc2(x.cuda(), wp, None if b is None else b.cuda(), Cout, dil, act)
+    close(got, want, 1e-5, rtol=1e-5, what="conv_hw3_tc2")
+
+
+@pytest.mark.parametrize("mt", [2, 4])
+def test_conv_hw3_tc2_tilings(ops, mt, monkeypatch):
+    """Both M-tile counts (8- and 16-row tiles) on the same input; ragged right / bottom edges."""
+    monkeypatch.setenv("TSTEREO_TC2_MT", str(mt))
+    x = rnd(1, 24, 2, 37, 71, seed=61)
+    w = rnd(8, 24, 1, 3, 3, seed=62, scale=0.1)
+    want = F.conv3d(x.double(), w.double(), None, 1, (0, 1, 1)).float()
+    got = ops.conv_hw3_tc2(x.cuda(), ops.pack_conv_hw3_tc2(w.reshape(8, 24, 9).cuda()), None, 8, 1, None)
+    close(got, want, 1e-5, rtol=1e-5, what=f"conv_hw3_tc2 MT={mt}")
+
+
+def test_conv_hw3_tc2_views(ops):
+    """2-D input, channel-sliced input and output views (the concat buffers)."""
+    x = rnd(2, 24, 13, 21, seed=45)
+    w = rnd(16, 24, 3, 3, seed=46, scale=0.1)
+    want = F.relu(F.conv2d(x, w, None, 1, 1))
+    wp = ops.pack_conv_hw3_tc2(w.reshape(16, 24, 9).cuda())
+    buf = torch.full((2, 40, 13, 21), 7.0, device="cuda")
+    xin = torch.zeros(2, 40, 13, 21)
+    xin[:, 8:32] = x
+    ops.conv_hw3_tc2(xin.cuda()[:, 8:32], wp, None, 16, 1, "ReLU", out=buf[:, 8:24])
+    close(buf[:, 8:24], want, 1e-5, rtol=1e-5, what="tc2 conv2d slices")
+    assert (buf[:, :8] == 7).all() and (buf[:, 24:] == 7).all()
+
+
 @pytest.mark.parametrize("B,Cin,Cout,Din,hw,k,stride,dil,transposed,act", D_CASES + [
     (1, 8, 16, 5, (136, 240), 3, 1, 1, False, "SiLU"), (2, 64, 64, 6, (17, 30), 3, 2, 1, False, "SiLU"),
     (1, 32, 64, 14, (34, 60), 3, 1, 1, False, "SiLU"), (1, 16, 16, 7, (68, 120), 5, 1, 1, False, "SiLU")])
