@@ -20,6 +20,11 @@
 //   * producers prefetch the next chunk's 8 channel rows into registers before converting the current one, and
 //     the small variants run two CTAs per SM, so global-load latency overlaps the MMAs of the other CTA.
 //
+//   * two epilogue modes: ACC (above; any Cin) and DIRECT (Cin <= 8*G, i.e. one accumulation group): all three
+//     3xTF32 terms accumulate into the SAME N columns (3 MMAs per ky), TMEM holds MT*N columns, and the epilogue
+//     streams TMEM -> shuffle -> bias/act -> store without register accumulators, so two CTAs fit one SM even
+//     for Cout = 32.
+//
 //  warps 0-7 : producers (global NCDHW fp32 -> hi/lo tf32 -> K-major SWIZZLE_NONE smem) + accumulator readers
 //              + epilogue;  warp 8 : TMEM alloc, MMA issue (one elected lane), commits.
 #include "common.cuh"
@@ -40,9 +45,10 @@ constexpr size_t SMEM_MAX = 227 * 1024;
 
 struct Params {
     const float* in;
-    long long isB, isC, isD;
+    long long isB, isD;
     float* out;
-    long long osB, osC, osD;
+    long long osB, osD;
+    int isC, osC;         // channel strides (elements); < 2^31, checked by the host
     const float* wpack;   // [nchunk][ky 3][khalf 2][row 2N][4], row = part*N + kx*CP + co
     const float* bias;    // [Cout] or null
     int Cin, Cout, H, W, D;
@@ -52,22 +58,31 @@ struct Params {
 // cvt.rna.tf32.f32 without the NaN/Inf handling ptxas wraps around it (operands here are finite activations)
 __device__ __forceinline__ uint32_t tf32_rna(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
 
-template <int CP, int MT>
+// SiLU with ex2.approx / rcp.approx (~1e-6 relative): the epilogue is instruction-bound, and the full-precision
+// expf + IEEE division of silu_f cost ~50 instructions per output.
+__device__ __forceinline__ float act_fast(float x, int act) {
+    if (act == TSTEREO_ACT_SILU) return __fdividef(x, 1.0f + __expf(-x));
+    if (act == TSTEREO_ACT_RELU) return fmaxf(x, 0.0f);
+    return x;
+}
+
+template <int CP, int MT, bool DIRECT>
 struct Cfg {
     static constexpr int N = 3 * CP;                   // columns of one part block: [kx][co]
-    static constexpr int N2 = (N + 15) / 16 * 16;      // width of the A_lo MMA (M = 128 needs N % 16 == 0)
-    static constexpr int COLS = MT * 2 * N;            // TMEM columns: per M-tile [A*B_hi (N) | A_hi*B_lo (N)]
+    static constexpr int N2 = (N + 15) / 16 * 16;      // width of an N-wide MMA (M = 128 needs N % 16 == 0)
+    static constexpr int TS = DIRECT ? N2 : 2 * N;     // TMEM columns of one M-tile: ACC [A*B_hi (N) | A_hi*B_lo (N)]
+    static constexpr int COLS = MT * TS;
     static constexpr int JT = (MT + 1) / 2;            // M-tiles drained per thread (tiles j = half + 2*jj)
-    static constexpr int MINB = (JT * N <= 48) ? 2 : 1;
+    static constexpr int MINB = (DIRECT || JT * N <= 48) ? 2 : 1;
     static constexpr int RPW = (4 * MT + 4 + 7) / 8;   // staged rows per producer warp (dil <= 2)
     static constexpr uint32_t NCOLS = COLS <= 32 ? 32 : COLS <= 64 ? 64 : COLS <= 128 ? 128 : COLS <= 256 ? 256 : 512;
     static constexpr uint32_t B_BYTES = 3u * 2u * 2u * N * 16u;
     static_assert(2 * N <= 256 && COLS <= 512, "tile does not fit one MMA / TMEM");
 };
 
-template <int CP, int MT>
-__global__ void __launch_bounds__(NTHREADS, Cfg<CP, MT>::MINB) conv_tc2_kernel(const Params p) {
-    using C = Cfg<CP, MT>;
+template <int CP, int MT, bool DIRECT>
+__global__ void __launch_bounds__(NTHREADS, Cfg<CP, MT, DIRECT>::MINB) conv_tc2_kernel(const Params p) {
+    using C = Cfg<CP, MT, DIRECT>;
     constexpr int N = C::N, JT = C::JT, RPW = C::RPW;
     extern __shared__ __align__(128) uint8_t smem[];
     const int SR = 4 * MT + 2 * p.dil;                 // staged rows
@@ -127,18 +142,22 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CP, MT>::MINB) conv_tc2_kernel(c
         auto load_chunk = [&](int k) {
             const float* src = in_pl + (long long)(k * 8) * p.isC;
 #pragma unroll
-            for (int u = 0; u < RPW; ++u)
+            for (int u = 0; u < RPW; ++u) {
+                const float* su = src + off[u];
 #pragma unroll
                 for (int c = 0; c < 8; ++c)
-                    v[u][c] = (off[u] >= 0 && k * 8 + c < p.Cin) ? __ldg(src + (long long)c * p.isC + off[u]) : 0.f;
+                    v[u][c] = (off[u] >= 0 && k * 8 + c < p.Cin) ? __ldg(su + c * p.isC) : 0.f;
+            }
         };
-        float acc[JT][N];
+        constexpr int NACC = DIRECT ? 1 : N;
+        float acc[JT][NACC];
 #pragma unroll
         for (int jj = 0; jj < JT; ++jj)
 #pragma unroll
-            for (int n = 0; n < N; ++n) acc[jj][n] = 0.f;
+            for (int n = 0; n < NACC; ++n) acc[jj][n] = 0.f;
 
         auto drain = [&](int g) {
+            if constexpr (!DIRECT) {
 #pragma unroll
             for (int jj = 0; jj < JT; ++jj) {
                 const int j = half + 2 * jj;
@@ -158,6 +177,7 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CP, MT>::MINB) conv_tc2_kernel(c
                     tc_fence_before();
                     mbar_arrive(&acc_empty[j]);
                 }
+            }
             }
         };
 
@@ -182,7 +202,9 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CP, MT>::MINB) conv_tc2_kernel(c
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
                         hi[c] = tf32_rna(v[u][c]);
-                        lo[c] = tf32_rna(v[u][c] - __uint_as_float(hi[c]));
+                        // exact remainder; the tensor core ignores the 13 low mantissa bits of a tf32 operand, so
+                        // not rounding lo costs <= 2^-22 relative
+                        lo[c] = __float_as_uint(v[u][c] - __uint_as_float(hi[c]));
                     }
                     const uint32_t o = (uint32_t)(r * 32 + lane) * 16u;
                     sts128(a_hi + o, hi[0], hi[1], hi[2], hi[3]);
@@ -194,9 +216,9 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CP, MT>::MINB) conv_tc2_kernel(c
             if (k + 1 < p.nchunk) load_chunk(k + 1);   // in flight across the barrier traffic and the drain below
             fence_proxy_async();                       // generic-proxy st.shared -> visible to the tensor core
             mbar_arrive(&full[s]);
-            if (k >= 1 && k % p.G == 0) drain(k / p.G - 1);   // group finished one chunk ago: overlaps chunk k's MMAs
+            if (!DIRECT && k >= 1 && k % p.G == 0) drain(k / p.G - 1);   // group finished one chunk ago: overlaps chunk k's MMAs
         }
-        drain(ngroups - 1);
+        if (!DIRECT) drain(ngroups - 1);
 
         // ===================== epilogue: kx shift-sum, bias, activation, NCDHW stores =====================
         float* out_pl = p.out + (long long)b * p.osB + (long long)d * p.osD;
@@ -208,48 +230,85 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CP, MT>::MINB) conv_tc2_kernel(c
             if (j < MT) {                                  // warp-uniform
                 const int y = y0 + 4 * j + quarter;
                 float* o = out_pl + (size_t)y * p.W + x;
+                const bool ok = xok && y < p.H;
+                if constexpr (DIRECT) {
+                    // one accumulation group: stream TMEM -> registers 8 channels at a time
+                    mbar_wait(&acc_full[j], 0u);
+                    tc_fence_after();
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(j * C::TS);
 #pragma unroll
-                for (int co = 0; co < CP; ++co) {
-                    const float v1 = __shfl_down_sync(0xffffffffu, acc[jj][CP + co], p.dil);
-                    const float v2 = __shfl_down_sync(0xffffffffu, acc[jj][2 * CP + co], 2 * p.dil);
-                    if (co < p.Cout && xok && y < p.H) {
-                        const float bv = p.bias ? __ldg(p.bias + co) : 0.f;
-                        o[(long long)co * p.osC] = apply_act(acc[jj][co] + v1 + v2 + bv, p.act);
+                    for (int c0 = 0; c0 < CP; c0 += 8) {
+                        uint32_t r0[8], r1[8], r2[8];
+                        tmem_ld8(taddr + (uint32_t)c0, r0);
+                        tmem_ld8(taddr + (uint32_t)(CP + c0), r1);
+                        tmem_ld8(taddr + (uint32_t)(2 * CP + c0), r2);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const float v1 = __shfl_down_sync(0xffffffffu, __uint_as_float(r1[c]), p.dil);
+                            const float v2 = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[c]), 2 * p.dil);
+                            const int co = c0 + c;
+                            if (co < p.Cout && ok) {
+                                const float bv = p.bias ? __ldg(p.bias + co) : 0.f;
+                                o[co * p.osC] = act_fast(__uint_as_float(r0[c]) + v1 + v2 + bv, p.act);
+                            }
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int co = 0; co < CP; ++co) {
+                        const float v1 = __shfl_down_sync(0xffffffffu, acc[jj][CP + co], p.dil);
+                        const float v2 = __shfl_down_sync(0xffffffffu, acc[jj][2 * CP + co], 2 * p.dil);
+                        if (co < p.Cout && ok) {
+                            const float bv = p.bias ? __ldg(p.bias + co) : 0.f;
+                            o[co * p.osC] = act_fast(acc[jj][co] + v1 + v2 + bv, p.act);
+                        }
                     }
                 }
             }
         }
+        if constexpr (DIRECT) tc_fence_before();
     } else {
         // ===================== MMA issuer =====================
-        constexpr uint32_t idesc_2n = idesc_tf32(2 * N), idesc_lo = idesc_tf32(C::N2);
+        constexpr uint32_t idesc_2n = idesc_tf32(2 * N), idesc_n = idesc_tf32(C::N2);
         const uint32_t a_lbo = NPOS * 16u, b_lbo = 2u * N * 16u;
         for (int k = 0; k < p.nchunk; ++k) {
             const int s = k % p.stages;
             const uint32_t ph = (uint32_t)(k / p.stages) & 1u;
-            const int g = k / p.G;
-            const bool first = (k % p.G) == 0;
-            const bool last = (k % p.G) == p.G - 1 || k == p.nchunk - 1;
+            const int g = DIRECT ? 0 : k / p.G;
+            const bool first = DIRECT ? k == 0 : (k % p.G) == 0;
+            const bool last = DIRECT ? k == p.nchunk - 1 : ((k % p.G) == p.G - 1 || k == p.nchunk - 1);
             mbar_wait(&full[s], ph);
             tc_fence_after();
             const uint32_t st_base = smem_u32(smem + (size_t)s * stage_bytes);
-            const uint32_t a_part0 = st_base, a_part1 = st_base + 2u * NPOS * 16u;
-            const uint32_t b_base = st_base + a_bytes;
+            // descriptor start-address field is (addr >> 4): offsets add directly (no carry out of its 14 bits)
+            const uint64_t a_hi = make_desc(st_base, a_lbo, 128u);
+            const uint64_t a_lo = make_desc(st_base + 2u * NPOS * 16u, a_lbo, 128u);
+            const uint64_t b_d = make_desc(st_base + a_bytes, b_lbo, 128u);
 #pragma unroll 1
             for (int j = 0; j < MT; ++j) {
-                if (first && g >= 1) {
+                if (!DIRECT && first && g >= 1) {
                     mbar_wait(&acc_empty[j], (uint32_t)(g - 1) & 1u);
                     tc_fence_after();
                 }
                 if (elect_one()) {
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(j * 2 * N);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(j * C::TS);
 #pragma unroll
                     for (int ky = 0; ky < 3; ++ky) {
-                        const uint32_t aoff = (uint32_t)((4 * j + ky * p.dil) * 32) * 16u;
-                        const uint64_t bd = make_desc(b_base + (uint32_t)ky * (2u * 2u * N * 16u), b_lbo, 128u);
-                        // [A*B_hi | A_hi*B_lo] (+)= A_hi * [B_hi | B_lo]
-                        tc_mma_tf32(d_tmem, make_desc(a_part0 + aoff, a_lbo, 128u), bd, idesc_2n, (first && ky == 0) ? 0u : 1u);
-                        // first block += A_lo * B_hi
-                        tc_mma_tf32(d_tmem, make_desc(a_part1 + aoff, a_lbo, 128u), bd, idesc_lo, 1u);
+                        const uint64_t ad = (uint64_t)((4 * j + ky * p.dil) * 32);
+                        const uint64_t bd = b_d + (uint64_t)(ky * (2 * 2 * N));
+                        const uint32_t acc0 = (first && ky == 0) ? 0u : 1u;
+                        if constexpr (DIRECT) {
+                            // all three terms into the same N columns (B rows [0,N) = hi, [N,2N) = lo)
+                            tc_mma_tf32(d_tmem, a_hi + ad, bd, idesc_n, acc0);
+                            tc_mma_tf32(d_tmem, a_hi + ad, bd + (uint64_t)N, idesc_n, 1u);
+                            tc_mma_tf32(d_tmem, a_lo + ad, bd, idesc_n, 1u);
+                        } else {
+                            // [A*B_hi | A_hi*B_lo] (+)= A_hi * [B_hi | B_lo]
+                            tc_mma_tf32(d_tmem, a_hi + ad, bd, idesc_2n, acc0);
+                            // first block += A_lo * B_hi
+                            tc_mma_tf32(d_tmem, a_lo + ad, bd, idesc_n, 1u);
+                        }
                     }
                     if (last) tc_commit(&acc_full[j]);
                 }
@@ -269,9 +328,9 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CP, MT>::MINB) conv_tc2_kernel(c
 
 static size_t smem_need(int stages, int SR, int N) { return (size_t)stages * ((size_t)SR * 2048 + (size_t)192 * N) + 256; }
 
-template <int CP, int MT>
+template <int CP, int MT, bool DIRECT>
 static int launch_one(const Params& p, dim3 grid, size_t smem_bytes, cudaStream_t st, const char* what) {
-    auto kern = conv_tc2_kernel<CP, MT>;
+    auto kern = conv_tc2_kernel<CP, MT, DIRECT>;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
@@ -291,17 +350,23 @@ static int env_int(const char* name, int dflt) {
 }
 
 static int launch(Params& p, int CP, int planes, cudaStream_t st, const char* what) {
-    const int N = 3 * CP;
+    const int N = 3 * CP, N2 = (N + 15) / 16 * 16;
     const int VW = 32 - 2 * p.dil;
     p.tiles_x = (p.W + VW - 1) / VW;
-    // M-tiles per CTA: 2 or 4 (TMEM: MT*2N <= 512 columns); cost = SM-time of all waves
+    p.G = env_int("TSTEREO_TC2_G", 8);
+    if (p.G < 1) p.G = 1;
+    const bool direct = p.nchunk <= p.G && !env_int("TSTEREO_TC2_NODIRECT", 0);
+    // M-tiles per CTA: 2 or 4 (TMEM: MT * columns-per-tile <= 512); cost = SM-time of all waves
     int best_mt = 0, best_stages = 0;
     double best_cost = 1e30;
     const int forced = env_int("TSTEREO_TC2_MT", 0);
     for (int mt = 2; mt <= 4; mt += 2) {
-        if (mt * 2 * N > 512) continue;
+        const int cols = mt * (direct ? N2 : 2 * N);
+        if (cols > 512 || (CP == 32 && mt == 4)) continue;   // no (32, 4) instance
         if (forced && mt != forced) continue;
-        const int jt = (mt + 1) / 2, minb = (jt * N <= 48) ? 2 : 1;
+        const int jt = (mt + 1) / 2;
+        int minb = (direct || jt * N <= 48) ? 2 : 1;
+        if (cols > 256) minb = 1;                       // two CTAs need their TMEM columns side by side
         const int SR = 4 * mt + 2 * p.dil;
         const size_t budget = minb == 2 ? (size_t)112 * 1024 : SMEM_MAX;
         int stages = 0;
@@ -322,13 +387,13 @@ static int launch(Params& p, int CP, int planes, cudaStream_t st, const char* wh
     }
     TS_REQUIRE(best_mt > 0, "%s: no tile configuration for Cout<=%d", what, CP);
     p.stages = best_stages;
-    p.G = env_int("TSTEREO_TC2_G", 4);
-    if (p.G < 1) p.G = 1;
     const int SR = 4 * best_mt + 2 * p.dil;
     const size_t smem_bytes = smem_need(p.stages, SR, N);
     dim3 grid(p.tiles_x * ((p.H + 4 * best_mt - 1) / (4 * best_mt)), planes);
-#define TS_TC2(CC, MM) \
-    if (CP == CC && best_mt == MM) return launch_one<CC, MM>(p, grid, smem_bytes, st, what);
+#define TS_TC2(CC, MM)                                                                           \
+    if (CP == CC && best_mt == MM)                                                               \
+        return direct ? launch_one<CC, MM, true>(p, grid, smem_bytes, st, what)                  \
+                      : launch_one<CC, MM, false>(p, grid, smem_bytes, st, what);
     TS_TC2(8, 2) TS_TC2(8, 4) TS_TC2(16, 2) TS_TC2(16, 4) TS_TC2(32, 2)
 #undef TS_TC2
     TS_REQUIRE(false, "%s: no kernel instance for CP=%d MT=%d", what, CP, best_mt);
@@ -360,8 +425,10 @@ int tstereo_conv_hw3_tc2(const float* in, long long isB, long long isC, long lon
     TS_REQUIRE((((size_t)wpack) & 15) == 0, "conv_hw3_tc2: packed weights must be 16-byte aligned");
     TS_REQUIRE((long long)H * W < (1ll << 31), "conv_hw3_tc2: plane exceeds 32-bit offsets");
     tc2::Params p = {};
-    p.in = in; p.isB = isB; p.isC = isC; p.isD = isD;
-    p.out = out; p.osB = osB; p.osC = osC; p.osD = osD;
+    TS_REQUIRE(isC >= 0 && osC >= 0 && isC < (1ll << 31) && osC * (long long)Cout < (1ll << 31) && isC * 8 < (1ll << 31),
+               "conv_hw3_tc2: channel strides exceed 32 bits");
+    p.in = in; p.isB = isB; p.isC = (int)isC; p.isD = isD;
+    p.out = out; p.osB = osB; p.osC = (int)osC; p.osD = osD;
     p.wpack = wpack; p.bias = bias;
     p.Cin = Cin; p.Cout = Cout; p.H = H; p.W = W; p.D = D;
     p.dil = dilation; p.act = act;
