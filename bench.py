@@ -5,7 +5,7 @@
 
 One "step" = one pass of the per-frame hot path (3 cost volumes -> 3-level separable 3-D aggregation
 -> top-2 soft-argmin -> convex / UNet up-sampling) over one batch of B
-synthetic 544x960 (540x960 padded to a multiple of 16) D=192 stereo frames per GPU.  Prints ONE JSON
+synthetic 544x960 (540x960 padded to a multiple of 16) D=192 stereo frames per GPU (B = 8 by default).  Prints ONE JSON
 line on rank 0 (see DESIGN.md §measurement for every field).
 
   value      frames/s, inputs resident in HBM, whole job (all ranks), CUDA-event timed, max over ranks
@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=4, help="frames per GPU per step")
+    ap.add_argument("--batch", type=int, default=8, help="frames per GPU per step (SURVEY.md §8d: C2 at B=8)")
     ap.add_argument("--height", type=int, default=544)
     ap.add_argument("--width", type=int, default=960)
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
@@ -196,7 +196,7 @@ def main():
         dist = dist_
         dist.init_process_group("nccl", device_id=dev)
 
-    from temporalstereo_b200 import _lib, ops, synth
+    from temporalstereo_b200 import _lib, ops, shard, synth
     from temporalstereo_b200.aggregation import TEMPORALSTEREO
     lib = _lib.load()
 
@@ -219,9 +219,7 @@ def main():
         return eng(inp[0:3], inp[3:6], inp[6], inp[7], {})
 
     def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
+        shard.barrier(dist)
 
     # ---- device-resident throughput
     for i in range(max(a.warmup, 3)):
@@ -237,37 +235,45 @@ def main():
         e1.record()
         barrier()
     launches = lib.tstereo_launch_count() - n0
-    ms = e0.elapsed_time(e1)
-    if dist is not None:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    fps = world * B * a.steps / (ms * 1e-3)
+    # whole-job throughput: frames of all ranks / slowest rank's device time
+    fps, ms, _ = shard.aggregate_throughput(B * a.steps, e0.elapsed_time(e1), dist, dev)
 
-    # ---- end to end through the public module call with host buffers
-    stage = [torch.empty_like(t, device=dev) for t in host]
-    full_host = torch.empty((B, 1, H, W), dtype=torch.float32).pin_memory()
+    # ---- end to end through the public module call with host buffers: every step uploads its own inputs from
+    #      pinned host memory and downloads its full-resolution disparity.  Two staging sets: the upload of
+    #      step i+1 runs on a copy stream while step i computes (the steady state of a streaming caller).
+    stages = [[torch.empty_like(t, device=dev) for t in host] for _ in range(2)]
+    full_host = [torch.empty((B, 1, H, W), dtype=torch.float32).pin_memory() for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    main_stream = torch.cuda.current_stream(dev)
+    uploaded = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
 
-    def e2e_step():
-        for d, h in zip(stage, host):
-            d.copy_(h, non_blocking=True)
-        o = forward(stage)
-        full_host.copy_(o[0][0], non_blocking=True)
+    def upload(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[i % 2])          # the set is free once the step that read it is done
+            for d, h in zip(stages[i % 2], host):
+                d.copy_(h, non_blocking=True)
+            uploaded[i % 2].record(copy_stream)
 
-    for _ in range(3):
-        e2e_step()
+    def e2e_run(n):
+        for ev in consumed:
+            ev.record(main_stream)
+        upload(0)
+        for i in range(n):
+            if i + 1 < n:
+                upload(i + 1)
+            main_stream.wait_event(uploaded[i % 2])
+            o = forward(stages[i % 2])
+            consumed[i % 2].record(main_stream)
+            full_host[i % 2].copy_(o[0][0], non_blocking=True)
+
+    e2e_run(3)
     barrier()
     e0.record()
-    for _ in range(a.steps):
-        e2e_step()
+    e2e_run(a.steps)
     e1.record()
     barrier()
-    ms_e2e = e0.elapsed_time(e1)
-    if dist is not None:
-        t = torch.tensor([ms_e2e], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = float(t.item())
-    fps_e2e = world * B * a.steps / (ms_e2e * 1e-3)
+    fps_e2e, ms_e2e, _ = shard.aggregate_throughput(B * a.steps, e0.elapsed_time(e1), dist, dev)
 
     # ---- roofline of the cost-volume operator (block_cost: the path north_star sets the HBM target on).
     #      Dominant launch = the precise-level volume (198 of the 329 MB/frame); the three-level total

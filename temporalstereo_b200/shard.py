@@ -1,0 +1,72 @@
+"""Batch-axis sharding of stereo sequences over the GPUs of one box.
+
+The hot path has no cross-sample reduction (the only batch statistic, the splat metric's mean of the
+previous disparity, is taken over the LOCAL batch by the reference as well —
+projects/TemporalStereo/TemporalStereo.py:364, 380, 418), so sequences are independent units: each rank
+owns a contiguous slice of the batch and its own recurrent `prev_info`; there is no data-path collective.
+`torch.distributed` is used for the rendezvous, barriers and the max-over-ranks reduction of the timing only.
+The time axis is a sequential recurrence and is never sharded.
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Sequence, Tuple
+
+import torch
+
+
+def env_world() -> Tuple[int, int, int]:
+    """(rank, local_rank, world_size) from the torchrun environment (1 process when absent)."""
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")),
+            int(os.environ.get("WORLD_SIZE", "1")))
+
+
+def shard_range(total: int, world: int, rank: int) -> Tuple[int, int]:
+    """[start, stop) of the `total` sequences owned by `rank`: contiguous, sizes differ by at most one,
+    the first `total % world` ranks take the extra one (an empty range when total < world)."""
+    if world < 1 or not 0 <= rank < world or total < 0:
+        raise ValueError(f"bad shard request total={total} world={world} rank={rank}")
+    base, extra = divmod(total, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def shard_batch(tensors: Sequence[torch.Tensor], world: int, rank: int) -> List[torch.Tensor]:
+    """This rank's slice (dim 0) of every tensor of a batch; all tensors must share the batch size."""
+    sizes = {int(t.shape[0]) for t in tensors}
+    if len(sizes) != 1:
+        raise ValueError(f"tensors disagree on the batch size: {sorted(sizes)}")
+    a, b = shard_range(sizes.pop(), world, rank)
+    return [t[a:b] for t in tensors]
+
+
+def barrier(dist=None) -> None:
+    """Process-group barrier followed by a device synchronize (both sides of every timed region)."""
+    if dist is not None and dist.is_initialized():
+        dist.barrier()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+
+
+def max_over_ranks(value: float, dist=None, device="cpu") -> float:
+    """Slowest rank's value: a multi-GPU step is as slow as its slowest replica."""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(value: float, dist=None, device="cpu") -> float:
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def aggregate_throughput(units_this_rank: int, ms_this_rank: float, dist=None, device="cpu") -> Tuple[float, float, int]:
+    """Whole-job throughput: (units of all ranks) / (max time over ranks).  Returns (units/s, ms, units)."""
+    ms = max_over_ranks(ms_this_rank, dist, device)
+    units = int(round(sum_over_ranks(units_this_rank, dist, device)))
+    return units / (ms * 1e-3), ms, units
