@@ -58,12 +58,68 @@ struct Params {
 // cvt.rna.tf32.f32 without the NaN/Inf handling ptxas wraps around it (operands here are finite activations)
 __device__ __forceinline__ uint32_t tf32_rna(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
 
-// SiLU with ex2.approx / rcp.approx (~1e-6 relative): the epilogue is instruction-bound, and the full-precision
-// expf + IEEE division of silu_f cost ~50 instructions per output.
-__device__ __forceinline__ float act_fast(float x, int act) {
-    if (act == TSTEREO_ACT_SILU) return __fdividef(x, 1.0f + __expf(-x));
-    if (act == TSTEREO_ACT_RELU) return fmaxf(x, 0.0f);
-    return x;
+// Activation of the epilogue, compile-time selected (the epilogue is instruction-bound).  SiLU uses
+// ex2.approx / rcp.approx (~1e-6 relative); the full-precision expf + IEEE division of silu_f cost ~50
+// instructions per output.
+template <int ACT>
+__device__ __forceinline__ float act_t(float x) {
+    if constexpr (ACT == TSTEREO_ACT_SILU) {
+        float e, r;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+        return x * r;
+    } else if constexpr (ACT == TSTEREO_ACT_RELU) {
+        return fmaxf(x, 0.0f);
+    } else {
+        return x;
+    }
+}
+
+// kx shift-sum + bias + activation + store of 8 channels of one tile row (lane = tile column):
+// out[x] = P0[x] + P1[x + dil] + P2[x + 2*dil]
+template <int ACT>
+__device__ __forceinline__ void epi_store8(const float (&a0)[8], const float (&a1)[8], const float (&a2)[8], int dil, float* o,
+                                           int osC, const float* bias, int co0, int Cout, bool ok) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float v1 = __shfl_down_sync(0xffffffffu, a1[c], dil);
+        const float v2 = __shfl_down_sync(0xffffffffu, a2[c], 2 * dil);
+        const float r = act_t<ACT>(a0[c] + v1 + v2 + __ldg(bias + c));
+        if (ok && co0 + c < Cout) o[c * osC] = r;
+    }
+}
+template <int ACT, int CP>
+__device__ __forceinline__ void epi_direct(uint32_t taddr, int dil, float* o, int osC, const float* bias, int Cout, bool ok) {
+#pragma unroll
+    for (int c0 = 0; c0 < CP; c0 += 8) {
+        uint32_t r0[8], r1[8], r2[8];
+        tmem_ld8(taddr + (uint32_t)c0, r0);
+        tmem_ld8(taddr + (uint32_t)(CP + c0), r1);
+        tmem_ld8(taddr + (uint32_t)(2 * CP + c0), r2);
+        tmem_ld_wait();
+        float a0[8], a1[8], a2[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            a0[c] = __uint_as_float(r0[c]);
+            a1[c] = __uint_as_float(r1[c]);
+            a2[c] = __uint_as_float(r2[c]);
+        }
+        epi_store8<ACT>(a0, a1, a2, dil, o + (long long)c0 * osC, osC, bias + c0, c0, Cout, ok);
+    }
+}
+template <int ACT, int CP>
+__device__ __forceinline__ void epi_acc(const float* acc, int dil, float* o, int osC, const float* bias, int Cout, bool ok) {
+#pragma unroll
+    for (int c0 = 0; c0 < CP; c0 += 8) {
+        float a0[8], a1[8], a2[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            a0[c] = acc[c0 + c];
+            a1[c] = acc[CP + c0 + c];
+            a2[c] = acc[2 * CP + c0 + c];
+        }
+        epi_store8<ACT>(a0, a1, a2, dil, o + (long long)c0 * osC, osC, bias + c0, c0, Cout, ok);
+    }
 }
 
 template <int CP, int MT, bool DIRECT>
@@ -182,9 +238,9 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CP, MT, DIRECT>::MINB) conv_tc2_
         };
 
         load_chunk(0);
+        int s = 0, gk = 0, gdone = 0;      // stage of chunk k; chunks produced since the last group boundary; groups drained
+        uint32_t ph = 0;
         for (int k = 0; k < p.nchunk; ++k) {
-            const int s = k % p.stages;
-            const uint32_t ph = (uint32_t)(k / p.stages) & 1u;
             mbar_wait(&empty[s], ph ^ 1u);
             uint8_t* st_base = smem + (size_t)s * stage_bytes;
             if (tid == 0) {
@@ -216,9 +272,20 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CP, MT, DIRECT>::MINB) conv_tc2_
             if (k + 1 < p.nchunk) load_chunk(k + 1);   // in flight across the barrier traffic and the drain below
             fence_proxy_async();                       // generic-proxy st.shared -> visible to the tensor core
             mbar_arrive(&full[s]);
-            if (!DIRECT && k >= 1 && k % p.G == 0) drain(k / p.G - 1);   // group finished one chunk ago: overlaps chunk k's MMAs
+            if (++s == p.stages) {
+                s = 0;
+                ph ^= 1u;
+            }
+            if constexpr (!DIRECT) {
+                // a group that finished one chunk ago is drained now: overlaps chunk k's MMAs
+                if (gk == p.G) {
+                    drain(gdone++);
+                    gk = 0;
+                }
+                ++gk;
+            }
         }
-        if (!DIRECT) drain(ngroups - 1);
+        if constexpr (!DIRECT) drain(ngroups - 1);
 
         // ===================== epilogue: kx shift-sum, bias, activation, NCDHW stores =====================
         float* out_pl = p.out + (long long)b * p.osB + (long long)d * p.osD;
@@ -236,34 +303,13 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CP, MT, DIRECT>::MINB) conv_tc2_
                     mbar_wait(&acc_full[j], 0u);
                     tc_fence_after();
                     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(j * C::TS);
-#pragma unroll
-                    for (int c0 = 0; c0 < CP; c0 += 8) {
-                        uint32_t r0[8], r1[8], r2[8];
-                        tmem_ld8(taddr + (uint32_t)c0, r0);
-                        tmem_ld8(taddr + (uint32_t)(CP + c0), r1);
-                        tmem_ld8(taddr + (uint32_t)(2 * CP + c0), r2);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) {
-                            const float v1 = __shfl_down_sync(0xffffffffu, __uint_as_float(r1[c]), p.dil);
-                            const float v2 = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[c]), 2 * p.dil);
-                            const int co = c0 + c;
-                            if (co < p.Cout && ok) {
-                                const float bv = p.bias ? __ldg(p.bias + co) : 0.f;
-                                o[co * p.osC] = act_fast(__uint_as_float(r0[c]) + v1 + v2 + bv, p.act);
-                            }
-                        }
-                    }
+                    if (p.act == TSTEREO_ACT_SILU) epi_direct<TSTEREO_ACT_SILU, CP>(taddr, p.dil, o, p.osC, p.bias, p.Cout, ok);
+                    else if (p.act == TSTEREO_ACT_RELU) epi_direct<TSTEREO_ACT_RELU, CP>(taddr, p.dil, o, p.osC, p.bias, p.Cout, ok);
+                    else epi_direct<TSTEREO_ACT_NONE, CP>(taddr, p.dil, o, p.osC, p.bias, p.Cout, ok);
                 } else {
-#pragma unroll
-                    for (int co = 0; co < CP; ++co) {
-                        const float v1 = __shfl_down_sync(0xffffffffu, acc[jj][CP + co], p.dil);
-                        const float v2 = __shfl_down_sync(0xffffffffu, acc[jj][2 * CP + co], 2 * p.dil);
-                        if (co < p.Cout && ok) {
-                            const float bv = p.bias ? __ldg(p.bias + co) : 0.f;
-                            o[co * p.osC] = act_fast(acc[jj][co] + v1 + v2 + bv, p.act);
-                        }
-                    }
+                    if (p.act == TSTEREO_ACT_SILU) epi_acc<TSTEREO_ACT_SILU, CP>(acc[jj], p.dil, o, p.osC, p.bias, p.Cout, ok);
+                    else if (p.act == TSTEREO_ACT_RELU) epi_acc<TSTEREO_ACT_RELU, CP>(acc[jj], p.dil, o, p.osC, p.bias, p.Cout, ok);
+                    else epi_acc<TSTEREO_ACT_NONE, CP>(acc[jj], p.dil, o, p.osC, p.bias, p.Cout, ok);
                 }
             }
         }
@@ -272,12 +318,11 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CP, MT, DIRECT>::MINB) conv_tc2_
         // ===================== MMA issuer =====================
         constexpr uint32_t idesc_2n = idesc_tf32(2 * N), idesc_n = idesc_tf32(C::N2);
         const uint32_t a_lbo = NPOS * 16u, b_lbo = 2u * N * 16u;
+        int s = 0, g = 0, kg = 0;          // stage; accumulation group; chunk index inside the group
+        uint32_t ph = 0;
         for (int k = 0; k < p.nchunk; ++k) {
-            const int s = k % p.stages;
-            const uint32_t ph = (uint32_t)(k / p.stages) & 1u;
-            const int g = DIRECT ? 0 : k / p.G;
-            const bool first = DIRECT ? k == 0 : (k % p.G) == 0;
-            const bool last = DIRECT ? k == p.nchunk - 1 : ((k % p.G) == p.G - 1 || k == p.nchunk - 1);
+            const bool first = DIRECT ? k == 0 : kg == 0;
+            const bool last = DIRECT ? k == p.nchunk - 1 : (kg == p.G - 1 || k == p.nchunk - 1);
             mbar_wait(&full[s], ph);
             tc_fence_after();
             const uint32_t st_base = smem_u32(smem + (size_t)s * stage_bytes);
@@ -316,6 +361,14 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CP, MT, DIRECT>::MINB) conv_tc2_
             }
             if (elect_one()) tc_commit(&empty[s]);      // stage reusable once every MMA above has read it
             __syncwarp();
+            if (++s == p.stages) {
+                s = 0;
+                ph ^= 1u;
+            }
+            if (++kg == p.G) {
+                kg = 0;
+                ++g;
+            }
         }
         tc_fence_before();
     }
@@ -342,6 +395,17 @@ static int launch_one(const Params& p, dim3 grid, size_t smem_bytes, cudaStream_
     }
     kern<<<grid, NTHREADS, smem_bytes, st>>>(p);
     return check_launch(what);
+}
+
+// bias == null -> a device buffer of zeros, so the epilogue loads it unconditionally
+__device__ float g_zero_bias[64];
+static const float* zero_bias() {
+    static const float* ptr = nullptr;
+    if (!ptr) {
+        void* q = nullptr;
+        if (cudaGetSymbolAddress(&q, g_zero_bias) == cudaSuccess) ptr = (const float*)q;
+    }
+    return ptr;
 }
 
 static int env_int(const char* name, int dflt) {
@@ -386,6 +450,8 @@ static int launch(Params& p, int CP, int planes, cudaStream_t st, const char* wh
         }
     }
     TS_REQUIRE(best_mt > 0, "%s: no tile configuration for Cout<=%d", what, CP);
+    if (!p.bias) p.bias = zero_bias();
+    TS_REQUIRE(p.bias, "%s: zero-bias buffer unavailable", what);
     p.stages = best_stages;
     const int SR = 4 * best_mt + 2 * p.dil;
     const size_t smem_bytes = smem_need(p.stages, SR, N);
