@@ -79,7 +79,7 @@ int tstereo_conv_hw3_tc(const float* in, long long isB, long long isC, long long
                         const float* wpack, const float* bias,
                         int B, int Cin, int Cout, int D, int H, int W,
                         int dilation, int act, void* stream);
-/* Second-generation tensor-core 3x3 conv (stride 1, dilation 1|2, Cout <= 32): 2-D tiles, the three kx taps
+/* Second-generation tensor-core 3x3 conv (stride 1, dilation 1|2, any Cout in groups of 32): 2-D tiles, the three kx taps
  * folded into the MMA's N dimension, 3xTF32 operands (same results as tstereo_conv_hw3 to fp32 rounding).
  * ref: layers/basic_layers.py:194-235 via aggregation/TemporalStereo/module.py:111-147, 424-492.
  * wpack: [ceil(Cin/8)][ky 3][khalf 2][row 2N][4] floats, N = 3*CP, CP = 8|16|32 >= Cout,
@@ -90,6 +90,25 @@ int tstereo_conv_hw3_tc2(const float* in, long long isB, long long isC, long lon
                          const float* wpack, const float* bias,
                          int B, int Cin, int Cout, int D, int H, int W,
                          int dilation, int act, void* stream);
+/* Stride-2 3x3 conv (padding 1) and stride-2 transposed convs through the same tensor-core kernel
+ * (tstereo_conv_hw3_tc2 over a virtual tensor: input parity phases stacked on the channel axis / one output parity
+ * phase per launch).  Any Cout (groups of 32).  ref: aggregation/TemporalStereo/module.py:111-184 (stride-2
+ * "DepthwiseConv3D" halves, "DepthwiseConvTranspose3D" k3 s2 p1 op1), :424-492 (UNet stride-2 convs, 4x4 deconvs).
+ * wpack (host repack, temporalstereo_b200/ops.py pack_conv_hw3s2_tc2 / pack_deconv_hw_tc2):
+ *   s2:     per 32-channel group the tc2 image of w'[Cout][4*Cin8][3][3], virtual channel = phase*Cin8 + c,
+ *           phase = (row parity, col parity), Cin8 = Cin rounded up to 8;
+ *   deconv: [phase (py,px) 4] x per 32-channel group the tc2 image of the 3x3 shift kernel of that output phase
+ *           (k = 3: padding 1, output_padding 1;  k = 4: padding 1; both give Hout = 2*Hin). */
+long long tstereo_conv_hw3s2_tc2_wpack_floats(int Cin, int Cout);
+int tstereo_conv_hw3s2_tc2(const float* in, long long isB, long long isC, long long isD,
+                           float* out, long long osB, long long osC, long long osD,
+                           const float* wpack, const float* bias,
+                           int B, int Cin, int Cout, int D, int Hin, int Win, int act, void* stream);
+long long tstereo_deconv_hw_tc2_wpack_floats(int Cin, int Cout);
+int tstereo_deconv_hw_tc2(const float* in, long long isB, long long isC, long long isD,
+                          float* out, long long osB, long long osC, long long osD,
+                          const float* wpack, const float* bias,
+                          int B, int Cin, int Cout, int D, int Hin, int Win, int act, void* stream);
 int tstereo_conv_d_tc(const float* in, long long isB, long long isC, long long isD,
                       float* out, long long osB, long long osC, long long osD,
                       const float* wpack, const float* bias,

@@ -25,6 +25,12 @@
 //     streams TMEM -> shuffle -> bias/act -> store without register accumulators, so two CTAs fit one SM even
 //     for Cout = 32.
 //
+//   * stride-2 convolutions and stride-2 transposed convolutions run through the SAME kernel as stride-1 3x3
+//     convolutions over a virtual tensor: the input of a stride-2 conv is read as its four (row, column) parity
+//     phases stacked on the channel axis (chunk k -> phase k / cpp: element offset pr*Win + pc, row pitch 2*Win,
+//     x step 2), and a transposed conv writes one output parity phase per launch (output row pitch / x step 2);
+//     the host repacks the weights accordingly (taps that do not exist for a phase are zero).
+//
 //  warps 0-7 : producers (global NCDHW fp32 -> hi/lo tf32 -> K-major SWIZZLE_NONE smem) + accumulator readers
 //              + epilogue;  warp 8 : TMEM alloc, MMA issue (one elected lane), commits.
 #include "common.cuh"
@@ -51,7 +57,11 @@ struct Params {
     int isC, osC;         // channel strides (elements); < 2^31, checked by the host
     const float* wpack;   // [nchunk][ky 3][khalf 2][row 2N][4], row = part*N + kx*CP + co
     const float* bias;    // [Cout] or null
-    int Cin, Cout, H, W, D;
+    int Cin, Cout, H, W, D;       // Cin = real channels per input phase; H, W = grid of the (virtual) stride-1 conv
+    int Hin, Win;                 // real input plane (= H, W unless the input is phase-decomposed)
+    int isY, isX;                 // input row pitch / x step in elements (W, 1 | 2*Win, 2)
+    int osY, osX;                 // output row pitch / x step (W, 1 | 2*W.., 2 for one phase of a transposed conv)
+    int cpp;                      // chunks per input phase = ceil(Cin / 8); nchunk = phases * cpp
     int dil, act, nchunk, G, stages, tiles_x;
 };
 
@@ -187,22 +197,36 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CP, MT, DIRECT>::MINB) conv_tc2_
         const int half = warp >> 2;                   // which M-tiles this warp drains
         const float* in_pl = p.in + (long long)b * p.isB + (long long)d * p.isD;
         // the staged rows of this warp: r = warp + 8*u; lane = staged column
-        int off[RPW];
+        int off[RPW];               // element offset of (row, lane) in phase (0,0), or -1
+        int edge = 0;               // bit u: row r's odd-row phase lies below the input; bit 31: same for the column
+        {
+            const int gx = x0 - p.dil + lane;
+            if (p.isX * gx + 1 >= p.Win) edge |= 1 << 31;
 #pragma unroll
-        for (int u = 0; u < RPW; ++u) {
-            const int r = warp + 8 * u;
-            const int gy = y0 - p.dil + r, gx = x0 - p.dil + lane;
-            off[u] = (r < SR && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) ? gy * p.W + gx : -1;
+            for (int u = 0; u < RPW; ++u) {
+                const int r = warp + 8 * u;
+                const int gy = y0 - p.dil + r;
+                off[u] = (r < SR && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) ? gy * p.isY + gx * p.isX : -1;
+                if (p.isX * gy + 1 >= p.Hin) edge |= 1 << u;
+            }
         }
         float v[RPW][8];
-        auto load_chunk = [&](int k) {
-            const float* src = in_pl + (long long)(k * 8) * p.isC;
+        int l_phase = 0, l_kc = 0;  // load cursor: input phase and chunk inside the phase
+        auto load_chunk = [&]() {
+            const int pr = l_phase >> 1, pc = l_phase & 1;
+            const float* src = in_pl + (long long)(l_kc * 8) * p.isC + pr * p.Win + pc;
+            const bool col_ok = !(pc && edge < 0);
 #pragma unroll
             for (int u = 0; u < RPW; ++u) {
                 const float* su = src + off[u];
+                const bool ok = off[u] >= 0 && col_ok && !(pr && ((edge >> u) & 1));
 #pragma unroll
                 for (int c = 0; c < 8; ++c)
-                    v[u][c] = (off[u] >= 0 && k * 8 + c < p.Cin) ? __ldg(su + c * p.isC) : 0.f;
+                    v[u][c] = (ok && l_kc * 8 + c < p.Cin) ? __ldg(su + c * p.isC) : 0.f;
+            }
+            if (++l_kc == p.cpp) {
+                l_kc = 0;
+                ++l_phase;
             }
         };
         constexpr int NACC = DIRECT ? 1 : N;
@@ -237,7 +261,7 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CP, MT, DIRECT>::MINB) conv_tc2_
             }
         };
 
-        load_chunk(0);
+        load_chunk();
         int s = 0, gk = 0, gdone = 0;      // stage of chunk k; chunks produced since the last group boundary; groups drained
         uint32_t ph = 0;
         for (int k = 0; k < p.nchunk; ++k) {
@@ -269,7 +293,7 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CP, MT, DIRECT>::MINB) conv_tc2_
                     sts128(a_lo + khalf + o, lo[4], lo[5], lo[6], lo[7]);
                 }
             }
-            if (k + 1 < p.nchunk) load_chunk(k + 1);   // in flight across the barrier traffic and the drain below
+            if (k + 1 < p.nchunk) load_chunk();        // in flight across the barrier traffic and the drain below
             fence_proxy_async();                       // generic-proxy st.shared -> visible to the tensor core
             mbar_arrive(&full[s]);
             if (++s == p.stages) {
@@ -291,12 +315,13 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CP, MT, DIRECT>::MINB) conv_tc2_
         float* out_pl = p.out + (long long)b * p.osB + (long long)d * p.osD;
         const int x = x0 + lane;
         const bool xok = lane < VW && x < p.W;
+        const int xo = x * p.osX;
 #pragma unroll
         for (int jj = 0; jj < JT; ++jj) {
             const int j = half + 2 * jj;
             if (j < MT) {                                  // warp-uniform
                 const int y = y0 + 4 * j + quarter;
-                float* o = out_pl + (size_t)y * p.W + x;
+                float* o = out_pl + (long long)y * p.osY + xo;
                 const bool ok = xok && y < p.H;
                 if constexpr (DIRECT) {
                     // one accumulation group: stream TMEM -> registers 8 channels at a time
@@ -417,7 +442,8 @@ static int launch(Params& p, int CP, int planes, cudaStream_t st, const char* wh
     const int N = 3 * CP, N2 = (N + 15) / 16 * 16;
     const int VW = 32 - 2 * p.dil;
     p.tiles_x = (p.W + VW - 1) / VW;
-    p.G = env_int("TSTEREO_TC2_G", 8);
+    const int g_env = env_int("TSTEREO_TC2_G", 0);      // experiments: chunks per accumulation group (per input phase)
+    if (g_env > 0) p.G = g_env * (p.nchunk / p.cpp);
     if (p.G < 1) p.G = 1;
     const bool direct = p.nchunk <= p.G && !env_int("TSTEREO_TC2_NODIRECT", 0);
     // M-tiles per CTA: 2 or 4 (TMEM: MT * columns-per-tile <= 512); cost = SM-time of all waves
@@ -470,14 +496,44 @@ static int launch(Params& p, int CP, int planes, cudaStream_t st, const char* wh
 
 using namespace tstereo;
 
+namespace {
+
+int tc2_cp(int Cout) { return Cout <= 8 ? 8 : Cout <= 16 ? 16 : 32; }
+
+// floats of the operand image of ONE output-channel group (<= 32 channels) over `nchunk` 8-channel chunks
+long long group_floats(int nchunk, int cout_g) { return (long long)nchunk * 3 * 2 * 2 * (3 * tc2_cp(cout_g)) * 4; }
+
+// total over the groups of 32 output channels
+long long wpack_floats(int nchunk, int Cout) {
+    long long n = 0;
+    for (int c0 = 0; c0 < Cout; c0 += 32) n += group_floats(nchunk, Cout - c0 < 32 ? Cout - c0 : 32);
+    return n;
+}
+
+// One (virtual) stride-1 3x3 convolution, output channels in groups of <= 32 (the producer work is repeated per
+// group; Cout = 64 layers are rare and their inputs are L2 resident between the two launches).
+int run_groups(tc2::Params p, int Cout, int planes, cudaStream_t st, const char* what) {
+    const float* wp = p.wpack;
+    const float* bias = p.bias;
+    float* out = p.out;
+    for (int c0 = 0; c0 < Cout; c0 += 32) {
+        const int cg = Cout - c0 < 32 ? Cout - c0 : 32;
+        p.Cout = cg;
+        p.wpack = wp;
+        p.bias = bias ? bias + c0 : nullptr;
+        p.out = out + (long long)c0 * p.osC;
+        const int rc = tc2::launch(p, tc2_cp(cg), planes, st, what);
+        if (rc != TSTEREO_OK) return rc;
+        wp += group_floats(p.nchunk, cg);
+    }
+    return TSTEREO_OK;
+}
+
+}  // namespace
+
 extern "C" {
 
-static int tc2_cp(int Cout) { return Cout <= 8 ? 8 : Cout <= 16 ? 16 : 32; }
-
-long long tstereo_conv_hw3_tc2_wpack_floats(int Cin, int Cout) {
-    const long long N = 3 * tc2_cp(Cout), nchunk = (Cin + 7) / 8;
-    return nchunk * 3 * 2 * 2 * N * 4;
-}
+long long tstereo_conv_hw3_tc2_wpack_floats(int Cin, int Cout) { return wpack_floats((Cin + 7) / 8, Cout); }
 
 int tstereo_conv_hw3_tc2(const float* in, long long isB, long long isC, long long isD,
                          float* out, long long osB, long long osC, long long osD,
@@ -485,21 +541,81 @@ int tstereo_conv_hw3_tc2(const float* in, long long isB, long long isC, long lon
                          int B, int Cin, int Cout, int D, int H, int W,
                          int dilation, int act, void* stream) {
     TS_REQUIRE(in && out && wpack, "conv_hw3_tc2: null pointer");
-    TS_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && Cout <= 32 && D > 0 && H > 0 && W > 0, "conv_hw3_tc2: bad sizes (Cout <= 32)");
+    TS_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && D > 0 && H > 0 && W > 0, "conv_hw3_tc2: bad sizes");
     TS_REQUIRE(dilation == 1 || dilation == 2, "conv_hw3_tc2: dilation %d unsupported", dilation);
     TS_REQUIRE((long long)B * D <= 65535, "conv_hw3_tc2: B*D exceeds grid.y");
     TS_REQUIRE((((size_t)wpack) & 15) == 0, "conv_hw3_tc2: packed weights must be 16-byte aligned");
     TS_REQUIRE((long long)H * W < (1ll << 31), "conv_hw3_tc2: plane exceeds 32-bit offsets");
+    TS_REQUIRE(isC >= 0 && osC >= 0 && isC * 8 < (1ll << 31) && osC * 32 < (1ll << 31), "conv_hw3_tc2: channel strides exceed 32 bits");
     tc2::Params p = {};
-    TS_REQUIRE(isC >= 0 && osC >= 0 && isC < (1ll << 31) && osC * (long long)Cout < (1ll << 31) && isC * 8 < (1ll << 31),
-               "conv_hw3_tc2: channel strides exceed 32 bits");
     p.in = in; p.isB = isB; p.isC = (int)isC; p.isD = isD;
     p.out = out; p.osB = osB; p.osC = (int)osC; p.osD = osD;
     p.wpack = wpack; p.bias = bias;
-    p.Cin = Cin; p.Cout = Cout; p.H = H; p.W = W; p.D = D;
+    p.Cin = Cin; p.H = H; p.W = W; p.D = D; p.Hin = H; p.Win = W;
+    p.isY = W; p.isX = 1; p.osY = W; p.osX = 1;
     p.dil = dilation; p.act = act;
-    p.nchunk = (Cin + 7) / 8;
-    return tc2::launch(p, tc2_cp(Cout), B * D, (cudaStream_t)stream, "conv_hw3_tc2");
+    p.cpp = (Cin + 7) / 8;
+    p.nchunk = p.cpp;
+    p.G = 8;
+    return run_groups(p, Cout, B * D, (cudaStream_t)stream, "conv_hw3_tc2");
+}
+
+long long tstereo_conv_hw3s2_tc2_wpack_floats(int Cin, int Cout) { return wpack_floats(4 * ((Cin + 7) / 8), Cout); }
+
+int tstereo_conv_hw3s2_tc2(const float* in, long long isB, long long isC, long long isD,
+                           float* out, long long osB, long long osC, long long osD,
+                           const float* wpack, const float* bias,
+                           int B, int Cin, int Cout, int D, int Hin, int Win, int act, void* stream) {
+    TS_REQUIRE(in && out && wpack, "conv_hw3s2_tc2: null pointer");
+    TS_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && D > 0 && Hin > 0 && Win > 0, "conv_hw3s2_tc2: bad sizes");
+    TS_REQUIRE((long long)B * D <= 65535, "conv_hw3s2_tc2: B*D exceeds grid.y");
+    TS_REQUIRE((((size_t)wpack) & 15) == 0, "conv_hw3s2_tc2: packed weights must be 16-byte aligned");
+    TS_REQUIRE((long long)Hin * Win < (1ll << 30), "conv_hw3s2_tc2: plane exceeds 32-bit offsets");
+    TS_REQUIRE(isC >= 0 && osC >= 0 && isC * 8 < (1ll << 31) && osC * 32 < (1ll << 31), "conv_hw3s2_tc2: channel strides exceed 32 bits");
+    const int H = (Hin - 1) / 2 + 1, W = (Win - 1) / 2 + 1;
+    tc2::Params p = {};
+    p.in = in; p.isB = isB; p.isC = (int)isC; p.isD = isD;
+    p.out = out; p.osB = osB; p.osC = (int)osC; p.osD = osD;
+    p.wpack = wpack; p.bias = bias;
+    p.Cin = Cin; p.H = H; p.W = W; p.D = D; p.Hin = Hin; p.Win = Win;
+    p.isY = 2 * Win; p.isX = 2; p.osY = W; p.osX = 1;
+    p.dil = 1; p.act = act;
+    p.cpp = (Cin + 7) / 8;
+    p.nchunk = 4 * p.cpp;
+    p.G = 32;     // of a chunk's 9 taps only the 1-4 that exist for its phase are non-zero: same products per group as G = 8
+    return run_groups(p, Cout, B * D, (cudaStream_t)stream, "conv_hw3s2_tc2");
+}
+
+long long tstereo_deconv_hw_tc2_wpack_floats(int Cin, int Cout) { return 4 * wpack_floats((Cin + 7) / 8, Cout); }
+
+int tstereo_deconv_hw_tc2(const float* in, long long isB, long long isC, long long isD,
+                          float* out, long long osB, long long osC, long long osD,
+                          const float* wpack, const float* bias,
+                          int B, int Cin, int Cout, int D, int Hin, int Win, int act, void* stream) {
+    TS_REQUIRE(in && out && wpack, "deconv_hw_tc2: null pointer");
+    TS_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && D > 0 && Hin > 0 && Win > 0, "deconv_hw_tc2: bad sizes");
+    TS_REQUIRE((long long)B * D <= 65535, "deconv_hw_tc2: B*D exceeds grid.y");
+    TS_REQUIRE((((size_t)wpack) & 15) == 0, "deconv_hw_tc2: packed weights must be 16-byte aligned");
+    TS_REQUIRE((long long)Hin * Win < (1ll << 29), "deconv_hw_tc2: plane exceeds 32-bit offsets");
+    TS_REQUIRE(isC >= 0 && osC >= 0 && isC * 8 < (1ll << 31) && osC * 32 < (1ll << 31), "deconv_hw_tc2: channel strides exceed 32 bits");
+    tc2::Params p = {};
+    p.in = in; p.isB = isB; p.isC = (int)isC; p.isD = isD;
+    p.osB = osB; p.osC = (int)osC; p.osD = osD;
+    p.bias = bias;
+    p.Cin = Cin; p.H = Hin; p.W = Win; p.D = D; p.Hin = Hin; p.Win = Win;
+    p.isY = Win; p.isX = 1; p.osY = 4 * Win; p.osX = 2;      // output plane is (2*Hin) x (2*Win)
+    p.dil = 1; p.act = act;
+    p.cpp = (Cin + 7) / 8;
+    p.nchunk = p.cpp;
+    p.G = 8;
+    const long long per_phase = wpack_floats(p.nchunk, Cout);
+    for (int ph = 0; ph < 4; ++ph) {                           // output parity phase (py, px)
+        p.out = out + (long long)(ph >> 1) * 2 * Win + (ph & 1);
+        p.wpack = wpack + ph * per_phase;
+        const int rc = run_groups(p, Cout, B * D, (cudaStream_t)stream, "deconv_hw_tc2");
+        if (rc != TSTEREO_OK) return rc;
+    }
+    return TSTEREO_OK;
 }
 
 }  // extern "C"

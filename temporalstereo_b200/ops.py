@@ -148,9 +148,9 @@ def conv_hw3_tc(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Tenso
     return out
 
 
-def pack_conv_hw3_tc2(w: torch.Tensor) -> torch.Tensor:
-    """[Cout, Cin, 9] (BN folded, taps ky*3+kx) -> the B-operand image of tstereo_conv_hw3_tc2:
-    [ceil(Cin/8)][ky][khalf 2][row 2N][4], row = part*N + kx*CP + co, N = 3*CP, CP = 8|16|32."""
+def _pack_tc2_group(w: torch.Tensor) -> torch.Tensor:
+    """One output-channel group (<= 32): [Cout, Cin, 9] -> [ceil(Cin/8)][ky][khalf 2][row 2N][4],
+    row = part*N + kx*CP + co, N = 3*CP, CP = 8|16|32."""
     cout, cin, T = w.shape
     assert T == 9 and cout <= 32
     CP = 8 if cout <= 8 else 16 if cout <= 16 else 32
@@ -162,9 +162,49 @@ def pack_conv_hw3_tc2(w: torch.Tensor) -> torch.Tensor:
     return parts.permute(2, 5, 3, 0, 6, 1, 4).contiguous().view(-1)   # [chunk, ky, khalf, part, kx, co, i]
 
 
+def pack_conv_hw3_tc2(w: torch.Tensor) -> torch.Tensor:
+    """[Cout, Cin, 9] (BN folded, taps ky*3+kx) -> the B-operand image of tstereo_conv_hw3_tc2, output channels
+    in groups of 32."""
+    return torch.cat([_pack_tc2_group(w[c0:c0 + 32]) for c0 in range(0, w.shape[0], 32)])
+
+
+def pack_conv_hw3s2_tc2(w: torch.Tensor) -> torch.Tensor:
+    """Stride-2 3x3 conv (padding 1) as a stride-1 3x3 conv over the four input parity phases stacked on the
+    channel axis (tstereo_conv_hw3s2_tc2): tap k reads input 2*o + k - 1 = phase (k+1)%2 at o + {-1, 0, 0}[k]."""
+    cout, cin, T = w.shape
+    assert T == 9
+    cin8 = (cin + 7) // 8 * 8
+    w4 = w.reshape(cout, cin, 3, 3)
+    virt = torch.zeros((cout, 4, cin8, 3, 3), device=w.device, dtype=torch.float32)
+    tap = {0: (1, -1), 1: (0, 0), 2: (1, 0)}                      # k -> (parity, offset)
+    for ky, (pr, dm) in tap.items():
+        for kx, (pc, dn) in tap.items():
+            virt[:, pr * 2 + pc, :cin, dm + 1, dn + 1] = w4[:, :, ky, kx]
+    return pack_conv_hw3_tc2(virt.reshape(cout, 4 * cin8, 9))
+
+
+def pack_deconv_hw_tc2(w: torch.Tensor, k: int) -> torch.Tensor:
+    """Transposed conv (stride 2, padding 1; k=3 with output_padding 1, or k=4), w [Cout, Cin, k*k] in the
+    transposed-conv tap order (out[2i - 1 + t] += in[i] * w[t]) -> four 3x3 shift kernels, one per output parity
+    phase (tstereo_deconv_hw_tc2): out[2m + p] = sum_d in[m + d] * w[t(p, d)]."""
+    cout, cin, T = w.shape
+    assert T == k * k and k in (3, 4)
+    w4 = w.reshape(cout, cin, k, k)
+    shifts = ({0: {0: 1}, 1: {1: 0, 0: 2}} if k == 3 else {0: {0: 1, -1: 3}, 1: {1: 0, 0: 2}})   # parity -> {shift: tap}
+    packs = []
+    for py in (0, 1):
+        for px in (0, 1):
+            ph = torch.zeros((cout, cin, 3, 3), device=w.device, dtype=torch.float32)
+            for dy, ky in shifts[py].items():
+                for dx, kx in shifts[px].items():
+                    ph[:, :, dy + 1, dx + 1] = w4[:, :, ky, kx]
+            packs.append(pack_conv_hw3_tc2(ph.reshape(cout, cin, 9)))
+    return torch.cat(packs)
+
+
 def conv_hw3_tc2(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Tensor], cout: int, dilation: int = 1,
                  act=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Stride-1 (1,3,3) / 3x3 conv, Cout <= 32, on the tensor cores (kx-folded tcgen05 kernel, 3xTF32)."""
+    """Stride-1 (1,3,3) / 3x3 conv on the tensor cores (kx-folded tcgen05 kernel, 3xTF32)."""
     five = x.dim() == 5
     B, Cin = x.shape[:2]
     D = x.shape[2] if five else 1
@@ -177,6 +217,44 @@ def conv_hw3_tc2(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Tens
     assert wpack.numel() == _lib.load().tstereo_conv_hw3_tc2_wpack_floats(Cin, cout)
     _lib.call("tstereo_conv_hw3_tc2", _p(x), isB, isC, isD, _p(out), osB, osC, osD, _p(wpack), _p(bias),
               B, Cin, cout, D, H, W, dilation, ACT[act], _stream())
+    return out
+
+
+def conv_hw3s2_tc2(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Tensor], cout: int, act=None,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Stride-2 (1,3,3) / 3x3 conv, padding 1, on the tensor cores (phase-decomposed input, 3xTF32)."""
+    five = x.dim() == 5
+    B, Cin = x.shape[:2]
+    D = x.shape[2] if five else 1
+    Hin, Win = x.shape[-2:]
+    H, W = (Hin - 1) // 2 + 1, (Win - 1) // 2 + 1
+    if out is None:
+        out = torch.empty((B, cout, D, H, W) if five else (B, cout, H, W), device=x.device, dtype=torch.float32)
+    isB, isC, isD = _view5(x)
+    osB, osC, osD = _view5(out)
+    _chk(wpack, bias)
+    assert wpack.numel() == _lib.load().tstereo_conv_hw3s2_tc2_wpack_floats(Cin, cout)
+    _lib.call("tstereo_conv_hw3s2_tc2", _p(x), isB, isC, isD, _p(out), osB, osC, osD, _p(wpack), _p(bias),
+              B, Cin, cout, D, Hin, Win, ACT[act], _stream())
+    return out
+
+
+def deconv_hw_tc2(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Tensor], cout: int, act=None,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Transposed (1,k,k)/kxk conv, stride 2 (Hout = 2*Hin), on the tensor cores: one output parity phase per launch."""
+    five = x.dim() == 5
+    B, Cin = x.shape[:2]
+    D = x.shape[2] if five else 1
+    Hin, Win = x.shape[-2:]
+    if out is None:
+        shape = (B, cout, D, 2 * Hin, 2 * Win) if five else (B, cout, 2 * Hin, 2 * Win)
+        out = torch.empty(shape, device=x.device, dtype=torch.float32)
+    isB, isC, isD = _view5(x)
+    osB, osC, osD = _view5(out)
+    _chk(wpack, bias)
+    assert wpack.numel() == _lib.load().tstereo_deconv_hw_tc2_wpack_floats(Cin, cout)
+    _lib.call("tstereo_deconv_hw_tc2", _p(x), isB, isC, isD, _p(out), osB, osC, osD, _p(wpack), _p(bias),
+              B, Cin, cout, D, Hin, Win, ACT[act], _stream())
     return out
 
 

@@ -519,6 +519,80 @@ def test_conv_hw3_tc2_views(ops):
     assert (buf[:, :8] == 7).all() and (buf[:, 24:] == 7).all()
 
 
+def test_conv_hw3_tc2_cout64(ops):
+    """Cout > 32 runs as groups of 32 output channels."""
+    x = rnd(1, 64, 1, 19, 45, seed=63)
+    w = rnd(64, 64, 1, 3, 3, seed=64, scale=0.05)
+    b = rnd(64, seed=65, scale=0.1)
+    want = F.relu(F.conv3d(x.double(), w.double(), b.double(), 1, (0, 1, 1))).float()
+    got = ops.conv_hw3_tc2(x.cuda(), ops.pack_conv_hw3_tc2(w.reshape(64, 64, 9).cuda()), b.cuda(), 64, 1, "ReLU")
+    close(got, want, 1e-5, rtol=1e-5, what="conv_hw3_tc2 Cout=64")
+    x = rnd(1, 256, 1, 9, 15, seed=66)
+    w = rnd(64, 256, 1, 3, 3, seed=67, scale=0.03)
+    want = O._act(F.conv3d(x.double(), w.double(), b.double(), 1, (0, 1, 1)), "SiLU").float()
+    got = ops.conv_hw3_tc2(x.cuda(), ops.pack_conv_hw3_tc2(w.reshape(64, 256, 9).cuda()), b.cuda(), 64, 1, "SiLU")
+    close(got, want, 1e-5, rtol=1e-5, what="conv_hw3_tc2 256->64")
+
+
+S2_CASES = [
+    # B, Cin, Cout, D, Hin, Win, act
+    (1, 3, 32, 1, 32, 48, "ReLU"),
+    (2, 8, 16, 3, 17, 30, "SiLU"),
+    (1, 16, 16, 2, 9, 15, "SiLU"),
+    (1, 32, 64, 1, 34, 61, "ReLU"),
+    (1, 64, 64, 4, 17, 30, "SiLU"),
+    (1, 32, 32, 5, 68, 120, None),
+    (1, 12, 20, 1, 5, 7, None),
+    (1, 8, 8, 1, 1, 1, None),
+]
+
+
+@pytest.mark.parametrize("B,Cin,Cout,D,Hin,Win,act", S2_CASES)
+def test_conv_hw3s2_tc2(ops, B, Cin, Cout, D, Hin, Win, act):
+    """Stride-2 3x3 conv through the phase-decomposed tensor-core kernel vs fp64 (odd sizes: the odd-parity
+    phases end one row / column early)."""
+    x = rnd(B, Cin, D, Hin, Win, seed=71)
+    w = rnd(Cout, Cin, 1, 3, 3, seed=72, scale=(2.0 / (9 * Cin)) ** 0.5)
+    b = rnd(Cout, seed=73, scale=0.1)
+    want = O._act(F.conv3d(x.double(), w.double(), b.double(), (1, 2, 2), (0, 1, 1)), act).float()
+    wp = ops.pack_conv_hw3s2_tc2(w.reshape(Cout, Cin, 9).cuda())
+    got = ops.conv_hw3s2_tc2(x.cuda(), wp, b.cuda(), Cout, act)
+    assert got.shape == want.shape
+    close(got, want, 1e-5, rtol=1e-5, what="conv_hw3s2_tc2")
+
+
+@pytest.mark.parametrize("B,Cin,Cout,D,Hin,Win,k,act", [
+    (1, 32, 32, 1, 17, 30, 4, "ReLU"), (2, 32, 9, 1, 34, 60, 4, None), (1, 64, 32, 3, 9, 15, 3, None),
+    (1, 16, 8, 5, 34, 60, 3, None), (1, 8, 8, 1, 1, 1, 3, None), (1, 40, 40, 2, 5, 33, 4, "SiLU")])
+def test_deconv_hw_tc2(ops, B, Cin, Cout, D, Hin, Win, k, act):
+    """Stride-2 transposed convs (k3 p1 op1 and k4 p1) as four output-phase launches of the tensor-core kernel."""
+    x = rnd(B, Cin, D, Hin, Win, seed=74)
+    w = rnd(Cin, Cout, 1, k, k, seed=75, scale=(2.0 / (k * k * Cin)) ** 0.5)
+    b = rnd(Cout, seed=76, scale=0.1)
+    op = 1 if k == 3 else 0
+    want = O._act(F.conv_transpose3d(x.double(), w.double(), b.double(), (1, 2, 2), (0, 1, 1), (0, op, op)), act).float()
+    wp = ops.pack_deconv_hw_tc2(w.reshape(Cin, Cout, k * k).transpose(0, 1).contiguous().cuda(), k)
+    got = ops.deconv_hw_tc2(x.cuda(), wp, b.cuda(), Cout, act)
+    assert got.shape == want.shape
+    close(got, want, 1e-5, rtol=1e-5, what="deconv_hw_tc2")
+
+
+def test_conv_s2_deconv_views(ops):
+    """Channel-sliced output (the UNet concat buffers) for the stride-2 / transposed forms."""
+    x = rnd(1, 16, 12, 20, seed=77)
+    w = rnd(8, 16, 3, 3, seed=78, scale=0.1)
+    buf = torch.full((1, 24, 6, 10), 7.0, device="cuda")
+    ops.conv_hw3s2_tc2(x.cuda(), ops.pack_conv_hw3s2_tc2(w.reshape(8, 16, 9).cuda()), None, 8, "ReLU", out=buf[:, 8:16])
+    close(buf[:, 8:16], F.relu(F.conv2d(x, w, None, 2, 1)), 1e-5, rtol=1e-5, what="s2 into slice")
+    assert (buf[:, :8] == 7).all() and (buf[:, 16:] == 7).all()
+    wt = rnd(16, 8, 4, 4, seed=79, scale=0.1)
+    buf = torch.full((1, 24, 24, 40), 7.0, device="cuda")
+    ops.deconv_hw_tc2(x.cuda(), ops.pack_deconv_hw_tc2(wt.reshape(16, 8, 16).transpose(0, 1).contiguous().cuda(), 4), None, 8, None,
+                      out=buf[:, 8:16])
+    close(buf[:, 8:16], F.conv_transpose2d(x, wt, None, 2, 1), 1e-5, rtol=1e-5, what="deconv into slice")
+    assert (buf[:, :8] == 7).all() and (buf[:, 16:] == 7).all()
+
+
 @pytest.mark.parametrize("B,Cin,Cout,Din,hw,k,stride,dil,transposed,act", D_CASES + [
     (1, 8, 16, 5, (136, 240), 3, 1, 1, False, "SiLU"), (2, 64, 64, 6, (17, 30), 3, 2, 1, False, "SiLU"),
     (1, 32, 64, 14, (34, 60), 3, 1, 1, False, "SiLU"), (1, 16, 16, 7, (68, 120), 5, 1, 1, False, "SiLU")])
