@@ -36,10 +36,11 @@ class _Node(nn.Module):
 
 
 class _Packed:
-    __slots__ = ("w", "b", "cout", "wtc", "wtc2")
+    __slots__ = ("w", "b", "cout", "wtc", "wtc2", "lazy")
 
     def __init__(self, w, b, cout, wtc=None, wtc2=None):
         self.w, self.b, self.cout = w, b, cout
+        self.lazy = {}          # operand images built on first use (stride-2 / transposed tensor-core forms)
         self.wtc = wtc          # tcgen05 (3xTF32) operand image of a 3x3 / (k,1,1) conv, or None
         self.wtc2 = wtc2        # operand image of the kx-folded tcgen05 3x3 kernel (Cout <= 32), or None
 
@@ -188,7 +189,7 @@ class TEMPORALSTEREO(nn.Module):
         wtc2 = None
         if tc_ok and cout <= 64 and cin >= 8 and w.is_cuda and self.tensor_cores:
             wtc = ops.pack_conv_tc(w)
-            if is_hw and cout <= 32:
+            if is_hw:
                 wtc2 = ops.pack_conv_hw3_tc2(w)
         return _Packed(packed.contiguous(), None if bias is None else bias.contiguous(), cout, wtc, wtc2)
 
@@ -279,7 +280,14 @@ class TEMPORALSTEREO(nn.Module):
     def _hw3(self, x, k: _Packed, stride=1, dil=1, act=None, out=None):
         """3x3 conv over (H,W): tensor cores (stride 1) or the fp32 FMA kernel, per the plan."""
         simt = lambda: ops.conv_hw3(x, k.w, k.b, k.cout, stride, dil, act, out=out)
-        if k.wtc is None or stride != 1 or not self.tensor_cores:
+        if not self.tensor_cores or not k.w.is_cuda:
+            return simt()
+        if stride == 2 and dil == 1 and k.w.shape[1] == 9:
+            if "s2" not in k.lazy:      # [Cin][9][CoutP] -> [Cout][Cin][9]
+                k.lazy["s2"] = ops.pack_conv_hw3s2_tc2(k.w[:, :, :k.cout].permute(2, 0, 1).contiguous())
+            return self._pick(("hw3s2", tuple(x.shape), k.cout),
+                              {"tc2": lambda: ops.conv_hw3s2_tc2(x, k.lazy["s2"], k.b, k.cout, act, out=out), "simt": simt})
+        if k.wtc is None or stride != 1:
             return simt()
         cands = {}
         if k.wtc2 is not None:
@@ -297,6 +305,16 @@ class TEMPORALSTEREO(nn.Module):
         return self._pick(key, {"tc": lambda: ops.conv_d_tc(x, k.wtc, k.b, k.cout, ksz, stride, dil, transposed, act, out=out),
                                 "simt": simt})
 
+    def _deconv_hw(self, x, k: _Packed, ksz, act=None, out=None):
+        """Stride-2 transposed (1,k,k) / kxk conv: four tensor-core phase launches or the fp32 FMA kernel."""
+        simt = lambda: ops.deconv_hw(x, k.w, k.b, k.cout, ksz, act, out=out)
+        if not self.tensor_cores or not k.w.is_cuda or k.w.shape[0] < 8:
+            return simt()
+        if "dc" not in k.lazy:          # [Cin][k*k][CoutP] (transposed-conv tap order) -> [Cout][Cin][k*k]
+            k.lazy["dc"] = ops.pack_deconv_hw_tc2(k.w[:, :, :k.cout].permute(2, 0, 1).contiguous(), ksz)
+        return self._pick(("dc", tuple(x.shape), k.cout, ksz),
+                          {"tc2": lambda: ops.deconv_hw_tc2(x, k.lazy["dc"], k.b, k.cout, act, out=out), "simt": simt})
+
     def _sep(self, x, p, stride=1, dil=1, act0="SiLU", act1="SiLU", out=None):
         """'DepthwiseConv3D': (1,3,3) conv then (3,1,1) conv, BN folded (reference module.py:111-147)."""
         a, b = self._pk[p + ".conv.0"], self._pk[p + ".conv.1"]
@@ -306,7 +324,7 @@ class TEMPORALSTEREO(nn.Module):
     def _sep_t(self, x, p):
         """'DepthwiseConvTranspose3D' k3 s2 p1 op1, no activation (reference module.py:149-184)."""
         a, b = self._pk[p + ".conv.0"], self._pk[p + ".conv.1"]
-        y = ops.deconv_hw(x, a.w, a.b, a.cout, 3, None)
+        y = self._deconv_hw(x, a, 3)
         return self._d(y, b, 3, 2, 1, True, None)
 
     def _hourglass(self, x, p):
@@ -413,15 +431,16 @@ class TEMPORALSTEREO(nn.Module):
         cf = l4.shape[1]
         c4 = self._pk[r + ".conv4.1"].cout
         c2 = self._pk[r + ".conv2.1"].cout
-        lcat = torch.empty((B, cf + c4, H4, W4), device=dev, dtype=torch.float32)
-        rcat = torch.empty_like(lcat)
-        cat2 = torch.empty((B, 2 * c2, (H - 1) // 2 + 1, (W - 1) // 2 + 1), device=dev, dtype=torch.float32)
+        # left and right images go through the encoder as one batch of 2B (reference module.py:459-466 runs it twice)
+        lrcat = torch.empty((2 * B, cf + c4, H4, W4), device=dev, dtype=torch.float32)
+        lcat, rcat = lrcat[:B], lrcat[B:]
+        cat2lr = torch.empty((2 * B, 2 * c2, (H - 1) // 2 + 1, (W - 1) // 2 + 1), device=dev, dtype=torch.float32)
+        cat2 = cat2lr[:B]                 # [deconv4 output | left 1/2-scale features]; the right half's first c2 planes stay unused
         lcat[:, :cf].copy_(l4)
         rcat[:, :cf].copy_(r4)
-        s2l = self._conv2d(self._conv2d(left_image, r + ".conv2.0", 2), r + ".conv2.1", out=cat2[:, c2:])
-        self._conv2d(self._conv2d(s2l, r + ".conv4.0", 2), r + ".conv4.1", out=lcat[:, cf:])
-        s2r = self._conv2d(self._conv2d(right_image, r + ".conv2.0", 2), r + ".conv2.1")
-        self._conv2d(self._conv2d(s2r, r + ".conv4.0", 2), r + ".conv4.1", out=rcat[:, cf:])
+        images = torch.cat([left_image, right_image], 0)
+        self._conv2d(self._conv2d(images, r + ".conv2.0", 2), r + ".conv2.1", out=cat2lr[:, c2:])
+        self._conv2d(self._conv2d(cat2lr[:, c2:], r + ".conv4.0", 2), r + ".conv4.1", out=lrcat[:, cf:])
 
         samples_p = torch.empty((B, 5, H4, W4), device=dev, dtype=torch.float32)
         low_f, high_f = ops.range_samples(d_f, DISP_RANGE, samples_p, 0)
@@ -430,11 +449,9 @@ class TEMPORALSTEREO(nn.Module):
         d_p, c_p, o_p, top_disp, top_cost = self._heads_predict(vol, samples_p, "precise.pred_heads",
                                                                 float(self.levels["precise"]["delta"]), True)
         f = self._conv2d(self._conv2d(lcat, r + ".fuse.0"), r + ".fuse.1")
-        k = self._pk[r + ".deconv4"]
-        ops.deconv_hw(f, k.w, k.b, k.cout, 4, "ReLU", out=cat2[:, :c2])
+        self._deconv_hw(f, self._pk[r + ".deconv4"], 4, "ReLU", out=cat2[:, :c2])
         f = self._conv2d(cat2, r + ".concat")
-        k = self._pk[r + ".deconv2"]
-        logits = ops.deconv_hw(f, k.w, k.b, k.cout, 4, None)
+        logits = self._deconv_hw(f, self._pk[r + ".deconv2"], 4)
         full = ops.unet_upsample(logits, d_p)
 
         # ---- recurrent state write-back (reference precise.py:98-103)
