@@ -109,6 +109,15 @@ int tstereo_deconv_hw_tc2(const float* in, long long isB, long long isC, long lo
                           float* out, long long osB, long long osC, long long osD,
                           const float* wpack, const float* bias,
                           int B, int Cin, int Cout, int D, int Hin, int Win, int act, void* stream);
+/* (k,1,1) conv along D (same argument meaning as tstereo_conv_d_tc) through the second-generation tensor-core
+ * kernel: the k input planes are K-chunks of a 1x1 conv.  wpack: pack_conv_d_tc2 in temporalstereo_b200/ops.py,
+ * tstereo_conv_d_tc2_wpack_floats(Cin, Cout, k) floats. */
+long long tstereo_conv_d_tc2_wpack_floats(int Cin, int Cout, int k);
+int tstereo_conv_d_tc2(const float* in, long long isB, long long isC, long long isD,
+                       float* out, long long osB, long long osC, long long osD,
+                       const float* wpack, const float* bias,
+                       int B, int Cin, int Cout, int Din, int Dout, int H, int W,
+                       int k, int stride, int dilation, int transposed, int act, void* stream);
 int tstereo_conv_d_tc(const float* in, long long isB, long long isC, long long isD,
                       float* out, long long osB, long long osC, long long osD,
                       const float* wpack, const float* bias,

@@ -302,7 +302,10 @@ class TEMPORALSTEREO(nn.Module):
         if k.wtc is None or not self.tensor_cores:
             return simt()
         key = ("d", tuple(x.shape), k.cout, ksz, stride, dil, transposed)
-        return self._pick(key, {"tc": lambda: ops.conv_d_tc(x, k.wtc, k.b, k.cout, ksz, stride, dil, transposed, act, out=out),
+        if "d2" not in k.lazy:          # [Cin][k][CoutP] -> [Cout][Cin][k]
+            k.lazy["d2"] = ops.pack_conv_d_tc2(k.w[:, :, :k.cout].permute(2, 0, 1).contiguous())
+        return self._pick(key, {"tc2": lambda: ops.conv_d_tc2(x, k.lazy["d2"], k.b, k.cout, ksz, stride, dil, transposed, act, out=out),
+                                "tc": lambda: ops.conv_d_tc(x, k.wtc, k.b, k.cout, ksz, stride, dil, transposed, act, out=out),
                                 "simt": simt})
 
     def _deconv_hw(self, x, k: _Packed, ksz, act=None, out=None):

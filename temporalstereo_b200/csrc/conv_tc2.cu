@@ -30,6 +30,8 @@
 //     phases stacked on the channel axis (chunk k -> phase k / cpp: element offset pr*Win + pc, row pitch 2*Win,
 //     x step 2), and a transposed conv writes one output parity phase per launch (output row pitch / x step 2);
 //     the host repacks the weights accordingly (taps that do not exist for a phase are zero).
+//   * (k,1,1) convolutions along D use the same machinery with the k input planes as "phases" (chunk k -> plane
+//     dout*stride + (k/cpp - k_d/2)*dil, zero when outside), one ky tap (nky = 1) and no halo (dil = 0).
 //
 //  warps 0-7 : producers (global NCDHW fp32 -> hi/lo tf32 -> K-major SWIZZLE_NONE smem) + accumulator readers
 //              + epilogue;  warp 8 : TMEM alloc, MMA issue (one elected lane), commits.
@@ -55,7 +57,7 @@ struct Params {
     float* out;
     long long osB, osD;
     int isC, osC;         // channel strides (elements); < 2^31, checked by the host
-    const float* wpack;   // [nchunk][ky 3][khalf 2][row 2N][4], row = part*N + kx*CP + co
+    const float* wpack;   // [nchunk][ky nky][khalf 2][row 2N][4], row = part*N + kx*CP + co
     const float* bias;    // [Cout] or null
     int Cin, Cout, H, W, D;       // Cin = real channels per input phase; H, W = grid of the (virtual) stride-1 conv
     int Hin, Win;                 // real input plane (= H, W unless the input is phase-decomposed)
@@ -63,6 +65,8 @@ struct Params {
     int osY, osX;                 // output row pitch / x step (W, 1 | 2*W.., 2 for one phase of a transposed conv)
     int cpp;                      // chunks per input phase = ceil(Cin / 8); nchunk = phases * cpp
     int dil, act, nchunk, G, stages, tiles_x;
+    int nky;                      // ky taps of the virtual conv: 3, or 1 for the (k,1,1) convs along D
+    int kd, dstride, ddil, Din, dtrans;   // kd > 0: phases are input planes of a conv along D (p.D = Dout)
 };
 
 // cvt.rna.tf32.f32 without the NaN/Inf handling ptxas wraps around it (operands here are finite activations)
@@ -155,6 +159,7 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CP, MT, DIRECT>::MINB) conv_tc2_
     const uint32_t NPOS = (uint32_t)SR * 32u;
     const uint32_t a_bytes = 4u * NPOS * 16u;          // [part 2][khalf 2][NPOS][16 B]
     const uint32_t stage_bytes = a_bytes + C::B_BYTES;
+    const uint32_t b_bytes = (uint32_t)p.nky * (C::B_BYTES / 3u);   // weight bytes of one chunk actually used
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
     uint64_t* full = bars;                         // [stages]  producers -> MMA
     uint64_t* empty = bars + MAX_STAGES;           // [stages]  MMA -> producers
@@ -195,7 +200,7 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CP, MT, DIRECT>::MINB) conv_tc2_
         // ===================== producers / accumulator readers =====================
         const int quarter = warp & 3;                 // TMEM lane quarter = tile row inside an M-tile
         const int half = warp >> 2;                   // which M-tiles this warp drains
-        const float* in_pl = p.in + (long long)b * p.isB + (long long)d * p.isD;
+        const float* in_pl = p.in + (long long)b * p.isB + (p.kd ? 0ll : (long long)d * p.isD);
         // the staged rows of this warp: r = warp + 8*u; lane = staged column
         int off[RPW];               // element offset of (row, lane) in phase (0,0), or -1
         int edge = 0;               // bit u: row r's odd-row phase lies below the input; bit 31: same for the column
@@ -213,9 +218,25 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CP, MT, DIRECT>::MINB) conv_tc2_
         float v[RPW][8];
         int l_phase = 0, l_kc = 0;  // load cursor: input phase and chunk inside the phase
         auto load_chunk = [&]() {
-            const int pr = l_phase >> 1, pc = l_phase & 1;
-            const float* src = in_pl + (long long)(l_kc * 8) * p.isC + pr * p.Win + pc;
-            const bool col_ok = !(pc && edge < 0);
+            int pr = 0, pc = 0;
+            bool col_ok = true;
+            const float* src = in_pl + (long long)(l_kc * 8) * p.isC;
+            if (p.kd) {             // phase = tap along D: input plane of this output plane
+                int din;
+                if (p.dtrans) {     // transposed k3 s2 p1 op1: dout = 2*din - 1 + tap
+                    const int t2 = d + 1 - l_phase;
+                    din = (t2 >= 0 && (t2 & 1) == 0) ? (t2 >> 1) : -1;
+                } else {
+                    din = d * p.dstride + (l_phase - p.kd / 2) * p.ddil;
+                }
+                col_ok = din >= 0 && din < p.Din;
+                src += (long long)(col_ok ? din : 0) * p.isD;
+            } else {                // phase = (row, column) parity of a stride-2 input
+                pr = l_phase >> 1;
+                pc = l_phase & 1;
+                src += pr * p.Win + pc;
+                col_ok = !(pc && edge < 0);
+            }
 #pragma unroll
             for (int u = 0; u < RPW; ++u) {
                 const float* su = src + off[u];
@@ -268,8 +289,8 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CP, MT, DIRECT>::MINB) conv_tc2_
             mbar_wait(&empty[s], ph ^ 1u);
             uint8_t* st_base = smem + (size_t)s * stage_bytes;
             if (tid == 0) {
-                mbar_arrive_expect_tx(&full[s], C::B_BYTES);
-                bulk_g2s(st_base + a_bytes, p.wpack + (size_t)k * (C::B_BYTES / 4), C::B_BYTES, &full[s]);
+                mbar_arrive_expect_tx(&full[s], b_bytes);
+                bulk_g2s(st_base + a_bytes, p.wpack + (size_t)k * (b_bytes / 4), b_bytes, &full[s]);
             }
             const uint32_t a_hi = smem_u32(st_base);
             const uint32_t khalf = NPOS * 16u;
@@ -365,6 +386,7 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CP, MT, DIRECT>::MINB) conv_tc2_
                     const uint32_t d_tmem = tmem_base + (uint32_t)(j * C::TS);
 #pragma unroll
                     for (int ky = 0; ky < 3; ++ky) {
+                        if (ky >= p.nky) break;
                         const uint64_t ad = (uint64_t)((4 * j + ky * p.dil) * 32);
                         const uint64_t bd = b_d + (uint64_t)(ky * (2 * 2 * N));
                         const uint32_t acc0 = (first && ky == 0) ? 0u : 1u;
@@ -501,12 +523,12 @@ namespace {
 int tc2_cp(int Cout) { return Cout <= 8 ? 8 : Cout <= 16 ? 16 : 32; }
 
 // floats of the operand image of ONE output-channel group (<= 32 channels) over `nchunk` 8-channel chunks
-long long group_floats(int nchunk, int cout_g) { return (long long)nchunk * 3 * 2 * 2 * (3 * tc2_cp(cout_g)) * 4; }
+long long group_floats(int nchunk, int cout_g, int nky = 3) { return (long long)nchunk * nky * 2 * 2 * (3 * tc2_cp(cout_g)) * 4; }
 
 // total over the groups of 32 output channels
-long long wpack_floats(int nchunk, int Cout) {
+long long wpack_floats(int nchunk, int Cout, int nky = 3) {
     long long n = 0;
-    for (int c0 = 0; c0 < Cout; c0 += 32) n += group_floats(nchunk, Cout - c0 < 32 ? Cout - c0 : 32);
+    for (int c0 = 0; c0 < Cout; c0 += 32) n += group_floats(nchunk, Cout - c0 < 32 ? Cout - c0 : 32, nky);
     return n;
 }
 
@@ -524,7 +546,7 @@ int run_groups(tc2::Params p, int Cout, int planes, cudaStream_t st, const char*
         p.out = out + (long long)c0 * p.osC;
         const int rc = tc2::launch(p, tc2_cp(cg), planes, st, what);
         if (rc != TSTEREO_OK) return rc;
-        wp += group_floats(p.nchunk, cg);
+        wp += group_floats(p.nchunk, cg, p.nky);
     }
     return TSTEREO_OK;
 }
@@ -553,7 +575,7 @@ int tstereo_conv_hw3_tc2(const float* in, long long isB, long long isC, long lon
     p.wpack = wpack; p.bias = bias;
     p.Cin = Cin; p.H = H; p.W = W; p.D = D; p.Hin = H; p.Win = W;
     p.isY = W; p.isX = 1; p.osY = W; p.osX = 1;
-    p.dil = dilation; p.act = act;
+    p.dil = dilation; p.act = act; p.nky = 3;
     p.cpp = (Cin + 7) / 8;
     p.nchunk = p.cpp;
     p.G = 8;
@@ -579,7 +601,7 @@ int tstereo_conv_hw3s2_tc2(const float* in, long long isB, long long isC, long l
     p.wpack = wpack; p.bias = bias;
     p.Cin = Cin; p.H = H; p.W = W; p.D = D; p.Hin = Hin; p.Win = Win;
     p.isY = 2 * Win; p.isX = 2; p.osY = W; p.osX = 1;
-    p.dil = 1; p.act = act;
+    p.dil = 1; p.act = act; p.nky = 3;
     p.cpp = (Cin + 7) / 8;
     p.nchunk = 4 * p.cpp;
     p.G = 32;     // of a chunk's 9 taps only the 1-4 that exist for its phase are non-zero: same products per group as G = 8
@@ -604,7 +626,7 @@ int tstereo_deconv_hw_tc2(const float* in, long long isB, long long isC, long lo
     p.bias = bias;
     p.Cin = Cin; p.H = Hin; p.W = Win; p.D = D; p.Hin = Hin; p.Win = Win;
     p.isY = Win; p.isX = 1; p.osY = 4 * Win; p.osX = 2;      // output plane is (2*Hin) x (2*Win)
-    p.dil = 1; p.act = act;
+    p.dil = 1; p.act = act; p.nky = 3;
     p.cpp = (Cin + 7) / 8;
     p.nchunk = p.cpp;
     p.G = 8;
@@ -616,6 +638,40 @@ int tstereo_deconv_hw_tc2(const float* in, long long isB, long long isC, long lo
         if (rc != TSTEREO_OK) return rc;
     }
     return TSTEREO_OK;
+}
+
+long long tstereo_conv_d_tc2_wpack_floats(int Cin, int Cout, int k) { return wpack_floats(k * ((Cin + 7) / 8), Cout, 1); }
+
+int tstereo_conv_d_tc2(const float* in, long long isB, long long isC, long long isD,
+                       float* out, long long osB, long long osC, long long osD,
+                       const float* wpack, const float* bias,
+                       int B, int Cin, int Cout, int Din, int Dout, int H, int W,
+                       int k, int stride, int dilation, int transposed, int act, void* stream) {
+    TS_REQUIRE(in && out && wpack, "conv_d_tc2: null pointer");
+    TS_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && Din > 0 && Dout > 0 && H > 0 && W > 0, "conv_d_tc2: bad sizes");
+    TS_REQUIRE(k == 3 || k == 5, "conv_d_tc2: k=%d unsupported", k);
+    if (transposed) {
+        TS_REQUIRE(k == 3 && Dout == 2 * Din, "conv_d_tc2: transposed needs k=3, Dout=2*Din (got k=%d Din=%d Dout=%d)", k, Din, Dout);
+    } else {
+        TS_REQUIRE((stride == 1 || stride == 2) && (dilation == 1 || dilation == 2), "conv_d_tc2: bad stride/dilation");
+        TS_REQUIRE(Dout == (Din - 1) / stride + 1, "conv_d_tc2: Dout=%d inconsistent with Din=%d stride=%d", Dout, Din, stride);
+    }
+    TS_REQUIRE((long long)B * Dout <= 65535, "conv_d_tc2: B*Dout exceeds grid.y");
+    TS_REQUIRE((((size_t)wpack) & 15) == 0, "conv_d_tc2: packed weights must be 16-byte aligned");
+    TS_REQUIRE((long long)H * W < (1ll << 31), "conv_d_tc2: plane exceeds 32-bit offsets");
+    TS_REQUIRE(isC >= 0 && osC >= 0 && isC * 8 < (1ll << 31) && osC * 32 < (1ll << 31), "conv_d_tc2: channel strides exceed 32 bits");
+    tc2::Params p = {};
+    p.in = in; p.isB = isB; p.isC = (int)isC; p.isD = isD;
+    p.out = out; p.osB = osB; p.osC = (int)osC; p.osD = osD;
+    p.wpack = wpack; p.bias = bias;
+    p.Cin = Cin; p.H = H; p.W = W; p.D = Dout; p.Hin = H; p.Win = W;
+    p.isY = W; p.isX = 1; p.osY = W; p.osX = 1;
+    p.dil = 0; p.act = act; p.nky = 1;
+    p.kd = k; p.dstride = stride; p.ddil = dilation; p.Din = Din; p.dtrans = transposed;
+    p.cpp = (Cin + 7) / 8;
+    p.nchunk = k * p.cpp;
+    p.G = 24;     // one tap per chunk: 8 products per term and chunk, the same group size in products as G = 8 of a 3x3
+    return run_groups(p, Cout, B * Dout, (cudaStream_t)stream, "conv_d_tc2");
 }
 
 }  // extern "C"

@@ -148,18 +148,29 @@ def conv_hw3_tc(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Tenso
     return out
 
 
-def _pack_tc2_group(w: torch.Tensor) -> torch.Tensor:
-    """One output-channel group (<= 32): [Cout, Cin, 9] -> [ceil(Cin/8)][ky][khalf 2][row 2N][4],
+def _pack_tc2_group(w: torch.Tensor, nky: int = 3) -> torch.Tensor:
+    """One output-channel group (<= 32): [Cout, Cin, nky*3] -> [ceil(Cin/8)][ky nky][khalf 2][row 2N][4],
     row = part*N + kx*CP + co, N = 3*CP, CP = 8|16|32."""
     cout, cin, T = w.shape
-    assert T == 9 and cout <= 32
+    assert T == 3 * nky and cout <= 32
     CP = 8 if cout <= 8 else 16 if cout <= 16 else 32
     nch = (cin + 7) // 8
-    full = torch.zeros((CP, nch * 8, 3, 3), device=w.device, dtype=torch.float32)
-    full[:cout, :cin] = w.reshape(cout, cin, 3, 3)
+    full = torch.zeros((CP, nch * 8, nky, 3), device=w.device, dtype=torch.float32)
+    full[:cout, :cin] = w.reshape(cout, cin, nky, 3)
     hi, lo = tf32_split(full)
-    parts = torch.stack([hi, lo]).view(2, CP, nch, 2, 4, 3, 3)        # [part, co, chunk, khalf, i, ky, kx]
+    parts = torch.stack([hi, lo]).view(2, CP, nch, 2, 4, nky, 3)      # [part, co, chunk, khalf, i, ky, kx]
     return parts.permute(2, 5, 3, 0, 6, 1, 4).contiguous().view(-1)   # [chunk, ky, khalf, part, kx, co, i]
+
+
+def pack_conv_d_tc2(w: torch.Tensor) -> torch.Tensor:
+    """(k,1,1) conv along D, w [Cout, Cin, k] -> operand image of tstereo_conv_d_tc2: the k input planes are stacked
+    on the channel axis (virtual channel = tap*Cin8 + c) of a 1x1 conv (one ky tap, weights in the kx = 0 block)."""
+    cout, cin, k = w.shape
+    cin8 = (cin + 7) // 8 * 8
+    virt = torch.zeros((cout, k, cin8, 1, 3), device=w.device, dtype=torch.float32)
+    virt[:, :, :cin, 0, 0] = w.permute(0, 2, 1)
+    virt = virt.reshape(cout, k * cin8, 3)
+    return torch.cat([_pack_tc2_group(virt[c0:c0 + 32], 1) for c0 in range(0, cout, 32)])
 
 
 def pack_conv_hw3_tc2(w: torch.Tensor) -> torch.Tensor:
@@ -255,6 +266,22 @@ def deconv_hw_tc2(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Ten
     assert wpack.numel() == _lib.load().tstereo_deconv_hw_tc2_wpack_floats(Cin, cout)
     _lib.call("tstereo_deconv_hw_tc2", _p(x), isB, isC, isD, _p(out), osB, osC, osD, _p(wpack), _p(bias),
               B, Cin, cout, D, Hin, Win, ACT[act], _stream())
+    return out
+
+
+def conv_d_tc2(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Tensor], cout: int, k: int = 3, stride: int = 1,
+               dilation: int = 1, transposed: bool = False, act=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(k,1,1) conv along D (or its stride-2 transposed form) through the second-generation tensor-core kernel."""
+    B, Cin, Din, H, W = x.shape
+    Dout = 2 * Din if transposed else (Din - 1) // stride + 1
+    if out is None:
+        out = torch.empty((B, cout, Dout, H, W), device=x.device, dtype=torch.float32)
+    isB, isC, isD = _view5(x)
+    osB, osC, osD = _view5(out)
+    _chk(wpack, bias)
+    assert wpack.numel() == _lib.load().tstereo_conv_d_tc2_wpack_floats(Cin, cout, k)
+    _lib.call("tstereo_conv_d_tc2", _p(x), isB, isC, isD, _p(out), osB, osC, osD, _p(wpack), _p(bias),
+              B, Cin, cout, Din, Dout, H, W, k, stride, dilation, int(transposed), ACT[act], _stream())
     return out
 
 

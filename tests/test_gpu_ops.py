@@ -613,6 +613,38 @@ def test_conv_d_tc(ops, B, Cin, Cout, Din, hw, k, stride, dil, transposed, act):
     close(got, want, 1e-5, rtol=1e-5, what="conv_d_tc")
 
 
+@pytest.mark.parametrize("B,Cin,Cout,Din,hw,k,stride,dil,transposed,act", D_CASES + [
+    (1, 8, 16, 5, (136, 240), 3, 1, 1, False, "SiLU"), (2, 64, 64, 6, (17, 30), 3, 2, 1, False, "SiLU"),
+    (1, 32, 64, 14, (34, 60), 3, 1, 1, False, "SiLU"), (1, 16, 16, 7, (68, 120), 5, 1, 1, False, "SiLU"),
+    (1, 64, 32, 3, (9, 15), 3, 1, 1, True, None), (1, 12, 5, 4, (7, 33), 3, 1, 2, False, "SiLU")])
+def test_conv_d_tc2(ops, B, Cin, Cout, Din, hw, k, stride, dil, transposed, act):
+    """(k,1,1) conv along D through the second-generation tensor-core kernel (planes as K-chunks) vs fp64."""
+    H, W = hw
+    x = rnd(B, Cin, Din, H, W, seed=47)
+    b = rnd(Cout, seed=49, scale=0.1)
+    if transposed:
+        w = rnd(Cin, Cout, 3, 1, 1, seed=48, scale=0.1)
+        want = O._act(F.conv_transpose3d(x.double(), w.double(), b.double(), (2, 1, 1), (1, 0, 0), (1, 0, 0)), act).float()
+        wk = w.transpose(0, 1).reshape(Cout, Cin, 3)
+    else:
+        w = rnd(Cout, Cin, k, 1, 1, seed=48, scale=0.1)
+        want = O._act(F.conv3d(x.double(), w.double(), b.double(), (stride, 1, 1), (dil * (k // 2), 0, 0), (dil, 1, 1)), act).float()
+        wk = w.reshape(Cout, Cin, k)
+    got = ops.conv_d_tc2(x.cuda(), ops.pack_conv_d_tc2(wk.contiguous().cuda()), b.cuda(), Cout, k, stride, dil, transposed, act)
+    close(got, want, 1e-5, rtol=1e-5, what="conv_d_tc2")
+
+
+def test_conv_d_tc2_into_slice(ops):
+    x = rnd(1, 16, 7, 9, 14, seed=50)
+    w = rnd(16, 16, 5, 1, 1, seed=51, scale=0.1)
+    want = F.conv3d(x, w, None, 1, (2, 0, 0))
+    cat = torch.zeros(1, 64, 7, 9, 14, device="cuda")
+    cat[:, :16] = x.cuda()
+    ops.conv_d_tc2(cat[:, :16], ops.pack_conv_d_tc2(w.reshape(16, 16, 5).cuda()), None, 16, 5, 1, 1, False, None, out=cat[:, 16:32])
+    close(cat[:, 16:32], want, 1e-5, rtol=1e-5, what="conv_d_tc2 into slice")
+    assert (cat[:, 32:] == 0).all()
+
+
 def test_conv_d_tc_into_slice(ops):
     x = rnd(1, 16, 7, 9, 14, seed=50)
     w = rnd(16, 16, 5, 1, 1, seed=51, scale=0.1)
