@@ -95,6 +95,9 @@ class TEMPORALSTEREO(nn.Module):
         # first call of a shape (outside CUDA-graph capture) and keeps the faster; "tc" / "simt" force one
         self.plan_mode = "auto"
         self._plan: Dict[tuple, str] = {}
+        # run the UNet encoder on a side stream, concurrently with the coarse and fine levels
+        self.overlap_encoder = True
+        self._side: Dict[str, torch.cuda.Stream] = {}
         self.register_load_state_dict_post_hook(lambda m, _k: m.invalidate())
         super().train(False)
 
@@ -395,6 +398,12 @@ class TEMPORALSTEREO(nn.Module):
         up = ops.convex_upsample(mfeat, m3.w, m3.b, disp)
         return up, cost, off, samples
 
+    def _side_stream(self, dev) -> "torch.cuda.Stream":
+        key = str(dev)
+        if key not in self._side:
+            self._side[key] = torch.cuda.Stream(device=dev)
+        return self._side[key]
+
     def _conv2d(self, x, p, stride=1, act="ReLU", out=None):
         k = self._pk[p]
         return self._hw3(x, k, stride, 1, act, out=out)
@@ -412,6 +421,34 @@ class TEMPORALSTEREO(nn.Module):
         left_image, right_image = left_image.contiguous(), right_image.contiguous()
         dev = l4.device
         B = l4.shape[0]
+        if not all(t.is_cuda for t in (l4, l8, l16, r4, r8, r16, left_image, right_image)):
+            raise TypeError("libtstereo ops need fp32 CUDA tensors (there is no CPU fallback for the hot path)")
+
+        # ---- UNet encoder (1/2- and 1/4-scale image features, reference module.py:459-466): independent of the
+        #      coarse and fine levels, so it runs on a side stream while their small, latency-bound launches
+        #      leave most SMs idle.  Left and right images go through as one batch of 2B.
+        H4, W4 = l4.shape[-2:]
+        H, W = left_image.shape[-2:]
+        r = "precise.refinement"
+        cf = l4.shape[1]
+        c4 = self._pk[r + ".conv4.1"].cout
+        c2 = self._pk[r + ".conv2.1"].cout
+        lrcat = torch.empty((2 * B, cf + c4, H4, W4), device=dev, dtype=torch.float32)
+        lcat, rcat = lrcat[:B], lrcat[B:]
+        cat2lr = torch.empty((2 * B, 2 * c2, (H - 1) // 2 + 1, (W - 1) // 2 + 1), device=dev, dtype=torch.float32)
+        cat2 = cat2lr[:B]                 # [deconv4 output | left 1/2-scale features]; the right half's first c2 planes stay unused
+        images = torch.cat([left_image, right_image], 0)
+        main = torch.cuda.current_stream(dev)
+        side = self._side_stream(dev) if self.overlap_encoder else main
+        if side is not main:
+            side.wait_stream(main)
+        with torch.cuda.stream(side):
+            lcat[:, :cf].copy_(l4)
+            rcat[:, :cf].copy_(r4)
+            self._conv2d(self._conv2d(images, r + ".conv2.0", 2), r + ".conv2.1", out=cat2lr[:, c2:])
+            self._conv2d(self._conv2d(cat2lr[:, c2:], r + ".conv4.0", 2), r + ".conv4.1", out=lrcat[:, cf:])
+            enc_done = torch.cuda.Event()
+            enc_done.record(side)
 
         # ---- coarse (1/16): integer-shift volume over num_sample candidates
         d_c, c_c, o_c, s_c = self._memory_level("coarse", l16, r16, None, prev_info, True)
@@ -428,22 +465,10 @@ class TEMPORALSTEREO(nn.Module):
         d_f, c_f, o_f, s_f = self._memory_level("fine", l8, r8, samples, prev_info, False)
 
         # ---- precise (1/4): UNet encoder features concatenated to the backbone features
-        H4, W4 = l4.shape[-2:]
-        H, W = left_image.shape[-2:]
-        r = "precise.refinement"
-        cf = l4.shape[1]
-        c4 = self._pk[r + ".conv4.1"].cout
-        c2 = self._pk[r + ".conv2.1"].cout
-        # left and right images go through the encoder as one batch of 2B (reference module.py:459-466 runs it twice)
-        lrcat = torch.empty((2 * B, cf + c4, H4, W4), device=dev, dtype=torch.float32)
-        lcat, rcat = lrcat[:B], lrcat[B:]
-        cat2lr = torch.empty((2 * B, 2 * c2, (H - 1) // 2 + 1, (W - 1) // 2 + 1), device=dev, dtype=torch.float32)
-        cat2 = cat2lr[:B]                 # [deconv4 output | left 1/2-scale features]; the right half's first c2 planes stay unused
-        lcat[:, :cf].copy_(l4)
-        rcat[:, :cf].copy_(r4)
-        images = torch.cat([left_image, right_image], 0)
-        self._conv2d(self._conv2d(images, r + ".conv2.0", 2), r + ".conv2.1", out=cat2lr[:, c2:])
-        self._conv2d(self._conv2d(cat2lr[:, c2:], r + ".conv4.0", 2), r + ".conv4.1", out=lrcat[:, cf:])
+        if side is not main:
+            main.wait_event(enc_done)
+            for t in (images, l4, r4):            # read on the side stream: keep the allocator from reusing them early
+                t.record_stream(side)
 
         samples_p = torch.empty((B, 5, H4, W4), device=dev, dtype=torch.float32)
         low_f, high_f = ops.range_samples(d_f, DISP_RANGE, samples_p, 0)
