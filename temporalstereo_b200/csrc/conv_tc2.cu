@@ -237,13 +237,16 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CP, MT, DIRECT>::MINB) conv_tc2_
                 src += pr * p.Win + pc;
                 col_ok = !(pc && edge < 0);
             }
+            const int nvalid = p.Cin - l_kc * 8;                 // channels of this chunk that exist (>= 8: all)
 #pragma unroll
             for (int u = 0; u < RPW; ++u) {
                 const float* su = src + off[u];
                 const bool ok = off[u] >= 0 && col_ok && !(pr && ((edge >> u) & 1));
 #pragma unroll
-                for (int c = 0; c < 8; ++c)
-                    v[u][c] = (ok && l_kc * 8 + c < p.Cin) ? __ldg(su + c * p.isC) : 0.f;
+                for (int c = 0; c < 8; ++c) {
+                    v[u][c] = (ok && c < nvalid) ? __ldg(su) : 0.f;
+                    su += p.isC;
+                }
             }
             if (++l_kc == p.cpp) {
                 l_kc = 0;
