@@ -18,12 +18,12 @@ namespace tstereo {
 __global__ void __launch_bounds__(128)
 resize_add_act_kernel(const float* __restrict__ a, const float* __restrict__ skip, float* __restrict__ out,
                       int C, int Da, int Ha, int Wa, int D, int H, int W, int act) {
-    const int x = blockIdx.x * 128 + threadIdx.x;
-    const int y = blockIdx.y;
-    int z = blockIdx.z;
+    const int pix = blockIdx.x * 128 + threadIdx.x;     // linear over H*W: full CTAs whatever W is
+    int z = blockIdx.y;
     const int d = z % D;
     z /= D;  // z = b*C + c
-    if (x >= W) return;
+    if (pix >= H * W) return;
+    const int y = pix / W, x = pix - y * W;
     const LerpIdx id = ac_index(ac_scale(Da, D), d, Da);
     const LerpIdx iy = ac_index(ac_scale(Ha, H), y, Ha);
     const LerpIdx ix = ac_index(ac_scale(Wa, W), x, Wa);
@@ -147,10 +147,14 @@ merge_memory_kernel(const float* __restrict__ vol, const float* __restrict__ sam
         key[j] = v;
         ord[j] = i;
     }
-    for (int j = 0; j < N; ++j) out_samples[((size_t)b * N + j) * HW + p] = key[j];
+    // blockIdx.z splits the channels: every slice re-derives the (cheap) order, slice 0 writes the sorted candidates
+    constexpr int CG = 4;
+    const int c_lo = blockIdx.z * CG, c_hi = min(C, c_lo + CG);
+    if (blockIdx.z == 0)
+        for (int j = 0; j < N; ++j) out_samples[((size_t)b * N + j) * HW + p] = key[j];
     float mc[4];
     for (int m = 0; m < M && m < 4; ++m) mc[m] = mem_cost ? __ldg(mem_cost + ((size_t)b * M + m) * HW + p) : 0.f;
-    for (int c = 0; c < C; ++c) {
+    for (int c = c_lo; c < c_hi; ++c) {
         const float* vp = vol + ((size_t)b * C + c) * D * HW + p;
         float* op = out_vol + (long long)b * osB + (long long)c * osC + p;
         const float w = __ldg(past_w + c), bb = __ldg(past_b + c);
@@ -179,33 +183,47 @@ heads_kernel(const float* __restrict__ feat, const float* __restrict__ w, float*
     extern __shared__ float ws[];  // [2][C][9]
     for (int i = threadIdx.x; i < 2 * C * 9; i += 128) ws[i] = w[i];
     __syncthreads();
-    const int x = blockIdx.x * 128 + threadIdx.x;
-    const int y = blockIdx.y;
-    const int d = blockIdx.z % D, b = blockIdx.z / D;
-    if (x >= W) return;
+    // thread = one pixel of one (b, d) plane (linear over H*W: full CTAs whatever W is)
+    const int pix = blockIdx.x * 128 + threadIdx.x;
+    const int d = blockIdx.y % D, b = blockIdx.y / D;
+    if (pix >= H * W) return;
+    const int y = pix / W, x = pix - y * W;
     const size_t HW = (size_t)H * W;
-    float acc[2] = {0.f, 0.f};
+    // tap validity and offsets once; zero weight on the clamped (in-image) address of an outside tap
+    int toff[9];
+    float tok[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        const int gy = y + t / 3 - 1, gx = x + t % 3 - 1;
+        const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
+        toff[t] = ok ? gy * W + gx : pix;
+        tok[t] = ok ? 1.f : 0.f;
+    }
+    float res[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        for (int c = 0; c < C; ++c) {
-            const float* fp = feat + (((size_t)b * 2 * C + h * C + c) * D + d) * HW;
-            const float* wp = ws + (h * C + c) * 9;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};          // four independent chains over the channels
+        const float* fp = feat + (((size_t)b * 2 * C + h * C) * D + d) * HW;
+        const float* wp = ws + h * C * 9;
+        int c = 0;
+        for (; c + 4 <= C; c += 4) {
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-                const int gy = y + ky - 1;
-                if (gy < 0 || gy >= H) continue;
+            for (int q = 0; q < 4; ++q) {
+                const float* fq = fp + (size_t)(c + q) * D * HW;
 #pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
-                    const int gx = x + kx - 1;
-                    if (gx < 0 || gx >= W) continue;
-                    acc[h] = fmaf(__ldg(fp + (size_t)gy * W + gx), wp[ky * 3 + kx], acc[h]);
-                }
+                for (int t = 0; t < 9; ++t) acc[q] = fmaf(__ldg(fq + toff[t]) * tok[t], wp[(c + q) * 9 + t], acc[q]);
             }
         }
+        for (; c < C; ++c) {
+            const float* fq = fp + (size_t)c * D * HW;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) acc[0] = fmaf(__ldg(fq + toff[t]) * tok[t], wp[c * 9 + t], acc[0]);
+        }
+        res[h] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
     }
-    const size_t o = (((size_t)b * D + d) * H + y) * W + x;
-    cost[o] = acc[0];
-    off[o] = fminf(fmaxf(tanhf(__fdiv_rn(acc[1], 100.0f)), -1.0f), 1.0f) * delta;
+    const size_t o = ((size_t)b * D + d) * HW + pix;
+    cost[o] = res[0];
+    off[o] = fminf(fmaxf(tanhf(__fdiv_rn(res[1], 100.0f)), -1.0f), 1.0f) * delta;
 }
 
 // --------------------------------------------------------------------------- top-2 soft-argmin
@@ -408,8 +426,8 @@ int tstereo_resize_add_act(const float* a, const float* skip, float* out, int B,
                            int D, int H, int W, int act, void* stream) {
     TS_REQUIRE(a && out, "resize_add_act: null pointer");
     TS_REQUIRE(B > 0 && C > 0 && Da > 0 && Ha > 0 && Wa > 0 && D > 0 && H > 0 && W > 0, "resize_add_act: bad sizes");
-    TS_REQUIRE(H <= 65535 && (long long)B * C * D <= 65535, "resize_add_act: grid too large");
-    dim3 grid(cdiv(W, 128), H, B * C * D);
+    TS_REQUIRE((long long)B * C * D <= 65535 && (long long)H * W < (1ll << 31), "resize_add_act: grid too large");
+    dim3 grid(cdiv(H * W, 128), B * C * D);
     resize_add_act_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a, skip, out, C, Da, Ha, Wa, D, H, W, act);
     return check_launch("resize_add_act");
 }
@@ -432,7 +450,7 @@ int tstereo_merge_memory(const float* vol, const float* samples, const float* me
     TS_REQUIRE((mem_sample == nullptr) == (mem_cost == nullptr), "merge_memory: mem_sample and mem_cost must both be set or both NULL");
     TS_REQUIRE(B <= 65535, "merge_memory: B too large");
     const int HW = H * W;
-    dim3 grid(cdiv(HW, 128), B);
+    dim3 grid(cdiv(HW, 128), B, cdiv(C, 4));
     merge_memory_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(vol, samples, mem_sample, mem_cost, past_w, past_b,
                                                                out_vol, osB, osC, out_samples, C, D, M, HW);
     return check_launch("merge_memory");
@@ -442,8 +460,8 @@ int tstereo_heads(const float* feat, const float* w, float* cost, float* off, in
                   float delta, void* stream) {
     TS_REQUIRE(feat && w && cost && off, "heads: null pointer");
     TS_REQUIRE(B > 0 && C > 0 && C <= 256 && D > 0 && H > 0 && W > 0, "heads: bad sizes");
-    TS_REQUIRE(H <= 65535 && (long long)B * D <= 65535, "heads: grid too large");
-    dim3 grid(cdiv(W, 128), H, B * D);
+    TS_REQUIRE((long long)B * D <= 65535 && (long long)H * W < (1ll << 31), "heads: grid too large");
+    dim3 grid(cdiv(H * W, 128), B * D);
     heads_kernel<<<grid, 128, 2 * C * 9 * sizeof(float), (cudaStream_t)stream>>>(feat, w, cost, off, C, D, H, W, delta);
     return check_launch("heads");
 }
