@@ -316,6 +316,26 @@ def main():
     achieved = b_p / (ms_p * 1e-3) / 1e9
     cv_ms, alg_bytes = ms_p + ms_f + ms_c, b_p + b_f + b_c
 
+    # ---- the heaviest single launch of the step: the first (1,3,3) conv of the precise level (304 -> 8 channels over
+    #      the raw volume) on the tensor-core kernel.  It is HBM-bound (36 FLOP/B): algorithmic bytes =
+    #      volume read once + output written once.
+    pk_first = eng._pk["precise.init3d.0.conv.0"]
+    vols = [torch.randn(B, 304, 5, H // 4, W // 4, device=dev) for _ in range(2)]
+    out8 = torch.empty(B, 8, 5, H // 4, W // 4, device=dev)
+    ms_conv = timed(lambda i: ops.conv_hw3_tc2(vols[i % 2], pk_first.wtc2, pk_first.b, 8, 1, "SiLU", out=out8), reps)
+    b_conv = 4 * B * (304 + 8) * 5 * (H // 4) * (W // 4)
+    del vols
+
+    # DRAM traffic of the roofline kernel from the committed ncu capture (profiles/r01_traffic.json, per launch at the
+    # batch size it names); null when the bench runs at another batch size
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if int(tj.get("batch", -1)) == B and (H, W) == (544, 960):
+            traffic = tj["block_cost_precise_dram_bytes"]
+    except (OSError, ValueError, KeyError):
+        pass
+
     result = {
         "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -331,11 +351,18 @@ def main():
         "roofline": {"bound": "hbm",
                      "kernel": "block_cost_warp at the precise level (block_cost_main_kernel<1,1> + block_cost_resize_kernel)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes": b_p, "ms": ms_p,
+                     "traffic": traffic, "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of both "
+                     "kernels, profiles/r01_traffic.json", "peak_source": peak_src, "algorithmic_bytes": b_p, "ms": ms_p,
                      "all_three_levels": {"algorithmic_bytes": alg_bytes, "ms": cv_ms,
                                           "achieved": alg_bytes / (cv_ms * 1e-3) / 1e9,
                                           "frac": alg_bytes / (cv_ms * 1e-3) / 1e9 / peak},
                      "share_of_step": cv_ms / (ms / a.steps)},
+        "roofline_conv": {"bound": "hbm", "kernel": "conv_tc2_kernel<8,4,ACC>: first (1,3,3) conv of the precise level, "
+                          "304 -> 8 channels over the raw cost volume (tcgen05, 3xTF32)",
+                          "achieved": b_conv / (ms_conv * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                          "frac": b_conv / (ms_conv * 1e-3) / 1e9 / peak, "algorithmic_bytes": b_conv, "ms": ms_conv,
+                          "tflops_fp32_equiv": 2.0 * B * 304 * 8 * 9 * 5 * (H // 4) * (W // 4) / (ms_conv * 1e-3) / 1e12,
+                          "share_of_step": ms_conv / (ms / a.steps)},
     }
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cfps, med, n, thr = cpu_reference_frames(a, a.cpu_seconds)

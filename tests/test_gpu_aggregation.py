@@ -163,6 +163,38 @@ def test_sequence_vs_oracle(engine):
     assert d.median() < 1e-3 and frac < 0.2, (d.median().item(), frac)
 
 
+@pytest.mark.parametrize("num_sample,H,W,B", [(20, 128, 160, 2), (16, 96, 192, 1)])
+def test_other_disparity_ranges_temporal(num_sample, H, W, B):
+    """BASELINE configs C4 (D=320 -> 20 coarse candidates) and C5 (D=256 -> 16) at reduced resolution, temporal
+    mode on (cost memory + local map: 8 fine candidates), batch > 1."""
+    from temporalstereo_b200 import temporal
+    from temporalstereo_b200.aggregation import TEMPORALSTEREO
+    sd = synth.synthetic_state_dict(seed=0)
+    eng = TEMPORALSTEREO(coarse=dict(num_sample=num_sample))
+    eng.load_state_dict(sd, strict=True)
+    eng = eng.cuda().eval()
+    st = synth.synthetic_temporal_state(H, W, B=B)
+    pose = (st["K"], st["T_now"], st["inv_T_prev"], st["baseline"])
+    state = dict(prev_disp=st["prev_disp"], cost_memory=dict(st["cost_memory"]), local_map=st["local_map"])
+    with torch.no_grad():
+        ref_state = O.update_map({k: (dict(v) if isinstance(v, dict) else v) for k, v in state.items()}, *pose, H, W, True, 3)
+    dev_state = temporal.update_map(_cuda(state), *[p.cuda() for p in pose], H, W, True, 3)
+    lf, rf, li, ri = synth.synthetic_frame(H, W, B=B, seed=12)
+    # both sides aggregate from the oracle's warped state (the splat normalisation is discontinuous); the forward
+    # updates prev_info in place, so each side gets its own copy
+    copy = lambda st_: {k: (dict(v) if isinstance(v, dict) else v) for k, v in st_.items()}
+    dev_in = _cuda(copy(ref_state))
+    with torch.no_grad():
+        want = O.aggregation_forward(sd, lf, rf, li, ri, copy(ref_state), num_sample=num_sample)
+    out = eng(_cuda(lf), _cuda(rf), li.cuda(), ri.cuda(), dev_in)
+    assert out[2][2].shape[1] == num_sample + 2 and out[2][1].shape[1] == want[2][1].shape[1]
+    _check(out, want[:4], f"oracle D={16 * num_sample} temporal {H}x{W} B={B}")
+    # and the CUDA warp itself against the oracle's
+    for k in ("disp_sample", "cost_volume"):
+        d = (dev_state["cost_memory"][k].cpu() - ref_state["cost_memory"][k]).abs().max()
+        assert d < 2e-4, (k, d)
+
+
 @pytest.mark.parametrize("plan", ["tc2", "tc", "simt"])
 def test_idempotent_and_batch_independent(engine, plan):
     """Size-independent properties: same input -> bit-identical output (no atomics on the aggregation
