@@ -257,8 +257,9 @@ class TEMPORALSTEREO(nn.Module):
         call of a shape (outside CUDA-graph capture) and keeps the fastest; any other plan_mode forces that
         kernel where it exists."""
         names = list(cands)
-        if self.plan_mode != "auto":
-            choice = self.plan_mode if self.plan_mode in cands else names[0]
+        mode = self.plan_mode.get(key[0], "auto") if isinstance(self.plan_mode, dict) else self.plan_mode
+        if mode != "auto":
+            choice = mode if mode in cands else names[0]
         else:
             choice = self._plan.get(key)
         if choice is None:
@@ -290,13 +291,11 @@ class TEMPORALSTEREO(nn.Module):
                 k.lazy["s2"] = ops.pack_conv_hw3s2_tc2(k.w[:, :, :k.cout].permute(2, 0, 1).contiguous())
             return self._pick(("hw3s2", tuple(x.shape), k.cout),
                               {"tc2": lambda: ops.conv_hw3s2_tc2(x, k.lazy["s2"], k.b, k.cout, act, out=out), "simt": simt})
-        if k.wtc is None or stride != 1:
+        if k.wtc2 is None or stride != 1:
             return simt()
-        cands = {}
-        if k.wtc2 is not None:
-            cands["tc2"] = lambda: ops.conv_hw3_tc2(x, k.wtc2, k.b, k.cout, dil, act, out=out)
-        cands["tc"] = lambda: ops.conv_hw3_tc(x, k.wtc, k.b, k.cout, dil, act, out=out)
-        cands["simt"] = simt
+        # the first-generation kernel (ops.conv_hw3_tc) stays an operator of the library but is no plan candidate:
+        # conv_hw3_tc2 is faster on every layer shape of the model
+        cands = {"tc2": lambda: ops.conv_hw3_tc2(x, k.wtc2, k.b, k.cout, dil, act, out=out), "simt": simt}
         return self._pick(("hw3", tuple(x.shape), k.cout, dil), cands)
 
     def _d(self, x, k: _Packed, ksz=3, stride=1, dil=1, transposed=False, act=None, out=None):
@@ -308,7 +307,6 @@ class TEMPORALSTEREO(nn.Module):
         if "d2" not in k.lazy:          # [Cin][k][CoutP] -> [Cout][Cin][k]
             k.lazy["d2"] = ops.pack_conv_d_tc2(k.w[:, :, :k.cout].permute(2, 0, 1).contiguous())
         return self._pick(key, {"tc2": lambda: ops.conv_d_tc2(x, k.lazy["d2"], k.b, k.cout, ksz, stride, dil, transposed, act, out=out),
-                                "tc": lambda: ops.conv_d_tc(x, k.wtc, k.b, k.cout, ksz, stride, dil, transposed, act, out=out),
                                 "simt": simt})
 
     def _deconv_hw(self, x, k: _Packed, ksz, act=None, out=None):

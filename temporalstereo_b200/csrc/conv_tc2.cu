@@ -32,11 +32,19 @@
 //     the host repacks the weights accordingly (taps that do not exist for a phase are zero).
 //   * (k,1,1) convolutions along D use the same machinery with the k input planes as "phases" (chunk k -> plane
 //     dout*stride + (k/cpp - k_d/2)*dil, zero when outside), one ky tap (nky = 1) and no halo (dil = 0).
+//   * TMA producer variant (template flag; opt-in with TSTEREO_TC2_TMA=1, for inputs whose rows are 16-byte aligned
+//     and x-dense: every stride-1 and (k,1,1) layer of the model at 1/16 scale and above): one elected lane issues `cp.async.bulk.tensor.5d` per chunk — an
+//     (x 32, y TR+2*dil, c 8) box of the NCDHW input, out-of-image rows / columns / planes / channels zero-filled by
+//     the TMA unit — into a ring of raw fp32 stages; the 8 producer warps then only read it (conflict-free LDS),
+//     split to tf32 hi/lo and store the K-major operand.  No per-element address arithmetic, predication or
+//     register prefetch; the loads run `rs` chunks ahead.  The register path (below) remains for phase-decomposed
+//     (stride-2) inputs and unaligned widths.
 //
 //  warps 0-7 : producers (global NCDHW fp32 -> hi/lo tf32 -> K-major SWIZZLE_NONE smem) + accumulator readers
 //              + epilogue;  warp 8 : TMEM alloc, MMA issue (one elected lane), commits.
 #include "common.cuh"
 #include "tc_ptx.cuh"
+#include <cuda.h>
 #include <cstdint>
 #include <cstdlib>
 
@@ -65,6 +73,9 @@ struct Params {
     int osY, osX;                 // output row pitch / x step (W, 1 | 2*W.., 2 for one phase of a transposed conv)
     int cpp;                      // chunks per input phase = ceil(Cin / 8); nchunk = phases * cpp
     int dil, act, nchunk, G, stages, tiles_x;
+    int rs;                       // TMA variant: raw fp32 stages in flight
+    int bw;                       // TMA variant: box width in elements (32, or 36 when the halo shifts the 16-byte aligned origin)
+    int nbatch;                   // batch size (extent of the TMA view's last dimension)
     int nky;                      // ky taps of the virtual conv: 3, or 1 for the (k,1,1) convs along D
     int kd, dstride, ddil, Din, dtrans;   // kd > 0: phases are input planes of a conv along D (p.D = Dout)
 };
@@ -150,8 +161,20 @@ struct Cfg {
     static_assert(2 * N <= 256 && COLS <= 512, "tile does not fit one MMA / TMEM");
 };
 
-template <int CP, int MT, bool DIRECT>
-__global__ void __launch_bounds__(NTHREADS, Cfg<CP, MT, DIRECT>::MINB) conv_tc2_kernel(const Params p) {
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                            int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+
+constexpr int MAX_RS = 4;
+
+template <int CP, int MT, bool DIRECT, bool TMA>
+__global__ void __launch_bounds__(NTHREADS, Cfg<CP, MT, DIRECT>::MINB)
+conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
     using C = Cfg<CP, MT, DIRECT>;
     constexpr int N = C::N, JT = C::JT, RPW = C::RPW;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -165,7 +188,11 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CP, MT, DIRECT>::MINB) conv_tc2_
     uint64_t* empty = bars + MAX_STAGES;           // [stages]  MMA -> producers
     uint64_t* acc_full = bars + 2 * MAX_STAGES;    // [MT]      MMA -> readers (a group of G chunks accumulated)
     uint64_t* acc_empty = acc_full + MAX_MT;       // [MT]      readers -> MMA (M-tile drained)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + MAX_MT);
+    uint64_t* raw_full = acc_empty + MAX_MT;       // [rs]      TMA -> producers (raw fp32 chunk landed)
+    uint64_t* raw_empty = raw_full + MAX_RS;       // [rs]      producers -> TMA issuer (raw stage read)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + MAX_RS);
+    uint8_t* raw_base = reinterpret_cast<uint8_t*>(bars) + 384;    // TMA variant: [rs][c 8][row SR][x bw] fp32
+    const uint32_t raw_bytes = 32u * (uint32_t)p.bw * (uint32_t)SR;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int plane = blockIdx.y;
@@ -183,6 +210,12 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CP, MT, DIRECT>::MINB) conv_tc2_
             mbar_init(&acc_full[j], 1);
             mbar_init(&acc_empty[j], NPROD / 2);
         }
+        if constexpr (TMA) {
+            for (int i = 0; i < p.rs; ++i) {
+                mbar_init(&raw_full[i], 1);
+                mbar_init(&raw_empty[i], NPROD / 32);
+            }
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == NPROD / 32) {
@@ -196,6 +229,30 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CP, MT, DIRECT>::MINB) conv_tc2_
     const uint32_t tmem_base = *tmem_slot;
     const int ngroups = (p.nchunk + p.G - 1) / p.G;
 
+// TMA variant: the MMA warp keeps `rs` chunk loads in flight; chunk kk -> (phase, channel chunk) -> box coordinates
+    int t_issue = 0;
+    auto issue_tma = [&]() {        // MMA warp only, converged
+        const int kk = t_issue++;
+        const int rsl = kk % p.rs;
+        mbar_wait(&raw_empty[rsl], (((uint32_t)(kk / p.rs)) & 1u) ^ 1u);
+        if (elect_one()) {
+            const int phase = kk / p.cpp, kc = kk - phase * p.cpp;
+            int dd = d;
+            if (p.kd) {
+                if (p.dtrans) {         // transposed k3 s2 p1 op1: dout = 2*din - 1 + tap
+                    const int t2 = d + 1 - phase;
+                    dd = (t2 >= 0 && (t2 & 1) == 0) ? (t2 >> 1) : -1;
+                } else {
+                    dd = d * p.dstride + (phase - p.kd / 2) * p.ddil;
+                }
+                if (dd < 0 || dd >= p.Din) dd = -1;       // outside: the TMA unit fills zeros
+            }
+            mbar_arrive_expect_tx(&raw_full[rsl], raw_bytes);
+            // the box origin must be 16-byte aligned in global memory: start at the multiple of 4 below x0 - dil
+            tma_load_5d(raw_base + (size_t)rsl * raw_bytes, &tmap, &raw_full[rsl], (x0 - p.dil) & ~3, y0 - p.dil, dd, kc * 8, b);
+        }
+        __syncwarp();
+    };
     if (warp < NPROD / 32) {
         // ===================== producers / accumulator readers =====================
         const int quarter = warp & 3;                 // TMEM lane quarter = tile row inside an M-tile
@@ -285,7 +342,7 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CP, MT, DIRECT>::MINB) conv_tc2_
             }
         };
 
-        load_chunk();
+        if constexpr (!TMA) load_chunk();
         int s = 0, gk = 0, gdone = 0;      // stage of chunk k; chunks produced since the last group boundary; groups drained
         uint32_t ph = 0;
         for (int k = 0; k < p.nchunk; ++k) {
@@ -298,26 +355,53 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CP, MT, DIRECT>::MINB) conv_tc2_
             const uint32_t a_hi = smem_u32(st_base);
             const uint32_t khalf = NPOS * 16u;
             const uint32_t a_lo = a_hi + 2u * khalf;
+            if constexpr (TMA) {
+                const int rsl = k % p.rs;
+                mbar_wait(&raw_full[rsl], ((uint32_t)(k / p.rs)) & 1u);
+                const float* raw = reinterpret_cast<const float*>(raw_base + (size_t)rsl * raw_bytes) + (((x0 - p.dil) & 3) + lane);
 #pragma unroll
-            for (int u = 0; u < RPW; ++u) {
-                const int r = warp + 8 * u;
-                if (r < SR) {
-                    uint32_t hi[8], lo[8];
+                for (int u = 0; u < RPW; ++u) {
+                    const int r = warp + 8 * u;
+                    if (r < SR) {
+                        uint32_t hi[8], lo[8];
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        hi[c] = tf32_rna(v[u][c]);
-                        // exact remainder; the tensor core ignores the 13 low mantissa bits of a tf32 operand, so
-                        // not rounding lo costs <= 2^-22 relative
-                        lo[c] = __float_as_uint(v[u][c] - __uint_as_float(hi[c]));
+                        for (int c = 0; c < 8; ++c) {
+                            const float x = raw[(c * SR + r) * p.bw];
+                            hi[c] = tf32_rna(x);
+                            lo[c] = __float_as_uint(x - __uint_as_float(hi[c]));
+                        }
+                        const uint32_t o = (uint32_t)(r * 32 + lane) * 16u;
+                        sts128(a_hi + o, hi[0], hi[1], hi[2], hi[3]);
+                        sts128(a_hi + khalf + o, hi[4], hi[5], hi[6], hi[7]);
+                        sts128(a_lo + o, lo[0], lo[1], lo[2], lo[3]);
+                        sts128(a_lo + khalf + o, lo[4], lo[5], lo[6], lo[7]);
                     }
-                    const uint32_t o = (uint32_t)(r * 32 + lane) * 16u;
-                    sts128(a_hi + o, hi[0], hi[1], hi[2], hi[3]);
-                    sts128(a_hi + khalf + o, hi[4], hi[5], hi[6], hi[7]);
-                    sts128(a_lo + o, lo[0], lo[1], lo[2], lo[3]);
-                    sts128(a_lo + khalf + o, lo[4], lo[5], lo[6], lo[7]);
                 }
+                __syncwarp();
+                if (elect_one()) mbar_arrive(&raw_empty[rsl]);      // this warp has read the raw stage
+                __syncwarp();
+            } else {
+#pragma unroll
+                for (int u = 0; u < RPW; ++u) {
+                    const int r = warp + 8 * u;
+                    if (r < SR) {
+                        uint32_t hi[8], lo[8];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            hi[c] = tf32_rna(v[u][c]);
+                            // exact remainder; the tensor core ignores the 13 low mantissa bits of a tf32 operand,
+                            // so not rounding lo costs <= 2^-22 relative
+                            lo[c] = __float_as_uint(v[u][c] - __uint_as_float(hi[c]));
+                        }
+                        const uint32_t o = (uint32_t)(r * 32 + lane) * 16u;
+                        sts128(a_hi + o, hi[0], hi[1], hi[2], hi[3]);
+                        sts128(a_hi + khalf + o, hi[4], hi[5], hi[6], hi[7]);
+                        sts128(a_lo + o, lo[0], lo[1], lo[2], lo[3]);
+                        sts128(a_lo + khalf + o, lo[4], lo[5], lo[6], lo[7]);
+                    }
+                }
+                if (k + 1 < p.nchunk) load_chunk();    // in flight across the barrier traffic and the drain below
             }
-            if (k + 1 < p.nchunk) load_chunk();        // in flight across the barrier traffic and the drain below
             fence_proxy_async();                       // generic-proxy st.shared -> visible to the tensor core
             mbar_arrive(&full[s]);
             if (++s == p.stages) {
@@ -369,6 +453,8 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CP, MT, DIRECT>::MINB) conv_tc2_
         const uint32_t a_lbo = NPOS * 16u, b_lbo = 2u * N * 16u;
         int s = 0, g = 0, kg = 0;          // stage; accumulation group; chunk index inside the group
         uint32_t ph = 0;
+        if constexpr (TMA)
+            for (int i = 0; i < p.rs && i < p.nchunk; ++i) issue_tma();
         for (int k = 0; k < p.nchunk; ++k) {
             const bool first = DIRECT ? k == 0 : kg == 0;
             const bool last = DIRECT ? k == p.nchunk - 1 : (kg == p.G - 1 || k == p.nchunk - 1);
@@ -411,6 +497,8 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CP, MT, DIRECT>::MINB) conv_tc2_
             }
             if (elect_one()) tc_commit(&empty[s]);      // stage reusable once every MMA above has read it
             __syncwarp();
+            if constexpr (TMA)
+                if (t_issue < p.nchunk) issue_tma();   // raw stage of chunk k: the producers released it before full[s]
             if (++s == p.stages) {
                 s = 0;
                 ph ^= 1u;
@@ -429,11 +517,62 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<CP, MT, DIRECT>::MINB) conv_tc2_
     }
 }
 
-static size_t smem_need(int stages, int SR, int N) { return (size_t)stages * ((size_t)SR * 2048 + (size_t)192 * N) + 256; }
+static size_t smem_need(int stages, int SR, int N, int rs = 0, int bw = 36) {
+    return (size_t)stages * ((size_t)SR * 2048 + (size_t)192 * N) + 384 + (size_t)rs * 32 * bw * SR;
+}
 
-template <int CP, int MT, bool DIRECT>
-static int launch_one(const Params& p, dim3 grid, size_t smem_bytes, cudaStream_t st, const char* what) {
-    auto kern = conv_tc2_kernel<CP, MT, DIRECT>;
+static int env_int(const char* name, int dflt);
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (libtstereo does not link libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* q = nullptr;
+        cudaDriverEntryPointQueryResult res;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &res) == cudaSuccess &&
+            res == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)q;
+        cudaGetLastError();
+    }
+    return fn;
+}
+
+// (x, y, plane, c, b) view of the NCDHW input with an (bw, SR, 1, 8, 1) box; false when the view is not expressible
+// (rows not 16-byte aligned, strided x, ...) -> the register path runs instead
+static bool make_tmap(const Params& p, int SR, CUtensorMap* tm) {
+    // opt-in (TSTEREO_TC2_TMA=1): measured 8-10 % slower than the register path on B200 — the kernel is bound by the
+    // shared-memory pipe (tensor-core operand reads 41-55 % + producer stores), and the raw fp32 stage adds one more
+    // shared-memory write + read per element
+    if (!env_int("TSTEREO_TC2_TMA", 0) || p.isX != 1 || p.isY != p.W || p.Hin != p.H || p.Win != p.W) return false;
+    if ((p.W & 3) || (p.isC & 3) || (p.isD & 3) || (p.isB & 3) || (((size_t)p.in) & 15)) return false;
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    const int planes = p.kd ? p.Din : p.D;
+    const long long nb = p.nbatch;
+    // dimensions in order of increasing stride (NCDHW: x, y, plane, channel, batch)
+    const cuuint64_t dims[5] = {(cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)planes, (cuuint64_t)p.Cin, (cuuint64_t)nb};
+    // a dimension of extent 1 may carry any stride: use a legal (monotone, multiple of 16 B) placeholder
+    const cuuint64_t sY = (cuuint64_t)p.W * 4;
+    const cuuint64_t sD = planes > 1 ? (cuuint64_t)p.isD * 4 : sY * (cuuint64_t)p.H;
+    const cuuint64_t sC = (cuuint64_t)p.isC * 4;
+    const cuuint64_t sB = nb > 1 ? (cuuint64_t)p.isB * 4 : sC * (cuuint64_t)p.Cin;
+    if (sD < sY * (cuuint64_t)p.H || sC < sD * (cuuint64_t)planes || sB < sC * (cuuint64_t)p.Cin) return false;
+    const cuuint64_t strides[4] = {sY, sD, sC, sB};
+    const cuuint32_t box[5] = {(cuuint32_t)p.bw, (cuuint32_t)SR, 1, 8, 1};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(p.in), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int CP, int MT, bool DIRECT, bool TMA>
+static int launch_one(const Params& p, const CUtensorMap& tm, dim3 grid, size_t smem_bytes, cudaStream_t st, const char* what) {
+    auto kern = conv_tc2_kernel<CP, MT, DIRECT, TMA>;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
@@ -443,7 +582,7 @@ static int launch_one(const Params& p, dim3 grid, size_t smem_bytes, cudaStream_
         }
         attr_done = true;
     }
-    kern<<<grid, NTHREADS, smem_bytes, st>>>(p);
+    kern<<<grid, NTHREADS, smem_bytes, st>>>(p, tm);
     return check_launch(what);
 }
 
@@ -472,7 +611,11 @@ static int launch(Params& p, int CP, int planes, cudaStream_t st, const char* wh
     if (p.G < 1) p.G = 1;
     const bool direct = p.nchunk <= p.G && !env_int("TSTEREO_TC2_NODIRECT", 0);
     // M-tiles per CTA: 2 or 4 (TMEM: MT * columns-per-tile <= 512); cost = SM-time of all waves
-    int best_mt = 0, best_stages = 0;
+    p.nbatch = planes / p.D;
+    p.bw = p.dil ? 36 : 32;
+    CUtensorMap tm = {};
+    const bool tma_ok = make_tmap(p, 4 * 2 + 2 * p.dil, &tm);     // eligibility (the box is re-encoded for the chosen tile)
+    int best_mt = 0, best_stages = 0, best_rs = 0;
     double best_cost = 1e30;
     const int forced = env_int("TSTEREO_TC2_MT", 0);
     for (int mt = 2; mt <= 4; mt += 2) {
@@ -484,33 +627,55 @@ static int launch(Params& p, int CP, int planes, cudaStream_t st, const char* wh
         if (cols > 256) minb = 1;                       // two CTAs need their TMEM columns side by side
         const int SR = 4 * mt + 2 * p.dil;
         const size_t budget = minb == 2 ? (size_t)112 * 1024 : SMEM_MAX;
-        int stages = 0;
-        for (int s = MAX_STAGES; s >= 2; --s)
-            if (smem_need(s, SR, N) <= budget) {
-                stages = s;
-                break;
-            }
+        int stages = 0, rs = 0;
+        if (tma_ok) {       // operand stages + raw fp32 stages (1/2 the size): prefer depth on the raw side
+            static const int combos[][2] = {{3, 4}, {3, 3}, {2, 4}, {2, 3}, {3, 2}, {2, 2}};
+            for (const auto& c : combos)
+                if (smem_need(c[0], SR, N, c[1], p.bw) <= budget) {
+                    stages = c[0];
+                    rs = c[1];
+                    break;
+                }
+        }
+        if (!stages) {
+            rs = 0;
+            for (int s = MAX_STAGES; s >= 2; --s)
+                if (smem_need(s, SR, N) <= budget) {
+                    stages = s;
+                    break;
+                }
+        }
         if (!stages) continue;
         const long long tiles = (long long)p.tiles_x * ((p.H + 4 * mt - 1) / (4 * mt)) * planes;
         const long long waves = (tiles + 148 * minb - 1) / (148 * minb);
-        const double cost = (double)waves * minb * (SR + 5.0) * (stages >= 3 ? 1.0 : 1.15);
+        const double cost = (double)waves * minb * (SR + 5.0) * ((stages >= 3 || rs) ? 1.0 : 1.15);
         if (cost < best_cost) {
             best_cost = cost;
             best_mt = mt;
             best_stages = stages;
+            best_rs = rs;
         }
     }
     TS_REQUIRE(best_mt > 0, "%s: no tile configuration for Cout<=%d", what, CP);
     if (!p.bias) p.bias = zero_bias();
     TS_REQUIRE(p.bias, "%s: zero-bias buffer unavailable", what);
     p.stages = best_stages;
+    p.rs = best_rs;
     const int SR = 4 * best_mt + 2 * p.dil;
-    const size_t smem_bytes = smem_need(p.stages, SR, N);
+    bool tma = best_rs > 0;
+    if (tma && !make_tmap(p, SR, &tm)) {
+        set_error("%s: cuTensorMapEncodeTiled failed", what);
+        return TSTEREO_E_CUDA;
+    }
+    const size_t smem_bytes = smem_need(p.stages, SR, N, p.rs, p.bw);
     dim3 grid(p.tiles_x * ((p.H + 4 * best_mt - 1) / (4 * best_mt)), planes);
-#define TS_TC2(CC, MM)                                                                           \
-    if (CP == CC && best_mt == MM)                                                               \
-        return direct ? launch_one<CC, MM, true>(p, grid, smem_bytes, st, what)                  \
-                      : launch_one<CC, MM, false>(p, grid, smem_bytes, st, what);
+#define TS_TC2(CC, MM)                                                                                         \
+    if (CP == CC && best_mt == MM) {                                                                           \
+        if (direct) return tma ? launch_one<CC, MM, true, true>(p, tm, grid, smem_bytes, st, what)             \
+                               : launch_one<CC, MM, true, false>(p, tm, grid, smem_bytes, st, what);           \
+        return tma ? launch_one<CC, MM, false, true>(p, tm, grid, smem_bytes, st, what)                        \
+                   : launch_one<CC, MM, false, false>(p, tm, grid, smem_bytes, st, what);                      \
+    }
     TS_TC2(8, 2) TS_TC2(8, 4) TS_TC2(16, 2) TS_TC2(16, 4) TS_TC2(32, 2)
 #undef TS_TC2
     TS_REQUIRE(false, "%s: no kernel instance for CP=%d MT=%d", what, CP, best_mt);

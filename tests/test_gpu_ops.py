@@ -494,6 +494,26 @@ def test_conv_hw3_tc2(ops, B, Cin, Cout, D, H, W, dil, act, bias):
     close(got, want, 1e-5, rtol=1e-5, what="conv_hw3_tc2")
 
 
+@pytest.mark.parametrize("B,Cin,Cout,D,H,W,dil,act", [
+    (1, 16, 8, 2, 9, 20, 1, "SiLU"), (2, 304, 8, 2, 20, 36, 1, "SiLU"), (1, 44, 32, 3, 17, 32, 1, "SiLU"),
+    (1, 32, 32, 2, 17, 28, 2, "SiLU"), (1, 64, 32, 1, 40, 240, 1, "ReLU"), (1, 8, 8, 5, 136, 240, 2, "SiLU")])
+def test_conv_hw3_tc2_tma(ops, monkeypatch, B, Cin, Cout, D, H, W, dil, act):
+    """The TMA producer variant (cp.async.bulk.tensor.5d boxes, zero-filled halos) gives the same results."""
+    monkeypatch.setenv("TSTEREO_TC2_TMA", "1")
+    x = rnd(B, Cin, D, H, W, seed=81)
+    w = rnd(Cout, Cin, 1, 3, 3, seed=82, scale=(2.0 / (9 * Cin)) ** 0.5)
+    b = rnd(Cout, seed=83, scale=0.1)
+    want = O._act(F.conv3d(x.double(), w.double(), b.double(), 1, (0, dil, dil), (1, dil, dil)), act).float()
+    got = ops.conv_hw3_tc2(x.cuda(), ops.pack_conv_hw3_tc2(w.reshape(Cout, Cin, 9).cuda()), b.cuda(), Cout, dil, act)
+    close(got, want, 1e-5, rtol=1e-5, what="conv_hw3_tc2 (TMA)")
+    # (k,1,1) conv along D: planes outside [0, Din) are zero-filled by the TMA unit
+    xd = rnd(1, 16, 7, 9, 16, seed=84)
+    wd = rnd(16, 16, 5, 1, 1, seed=85, scale=0.1)
+    wantd = F.conv3d(xd, wd, None, 1, (2, 0, 0))
+    gotd = ops.conv_d_tc2(xd.cuda(), ops.pack_conv_d_tc2(wd.reshape(16, 16, 5).cuda()), None, 16, 5, 1, 1, False, None)
+    close(gotd, wantd, 1e-5, rtol=1e-5, what="conv_d_tc2 (TMA)")
+
+
 @pytest.mark.parametrize("mt", [2, 4])
 def test_conv_hw3_tc2_tilings(ops, mt, monkeypatch):
     """Both M-tile counts (8- and 16-row tiles) on the same input; ragged right / bottom edges."""
