@@ -83,13 +83,16 @@ int tstereo_conv_hw3_tc(const float* in, long long isB, long long isC, long long
  * folded into the MMA's N dimension, 3xTF32 operands (same results as tstereo_conv_hw3 to fp32 rounding).
  * ref: layers/basic_layers.py:194-235 via aggregation/TemporalStereo/module.py:111-147, 424-492.
  * wpack: [ceil(Cin/8)][ky 3][khalf 2][row 2N][4] floats, N = 3*CP, CP = 8|16|32 >= Cout,
- * row = part*N + kx*CP + co (part 0 = tf32 hi, 1 = tf32 lo); tstereo_conv_hw3_tc2_wpack_floats(Cin, Cout) floats. */
-long long tstereo_conv_hw3_tc2_wpack_floats(int Cin, int Cout);
+ * row = part*N + kx*CP + co (part 0 = hi, 1 = lo); tstereo_conv_hw3_tc2_wpack_floats(Cin, Cout, half) floats.
+ * half != 0 (all four tc2 entry points): operands split as fp16 hi + fp16 lo and multiplied with kind::f16 — 16 channels per
+ * chunk, each 16-byte row of the image holds 8 halves instead of 4 floats (ops.py pack_*(..., half=True)); activations must
+ * stay below 65504 in magnitude. */
+long long tstereo_conv_hw3_tc2_wpack_floats(int Cin, int Cout, int half);
 int tstereo_conv_hw3_tc2(const float* in, long long isB, long long isC, long long isD,
                          float* out, long long osB, long long osC, long long osD,
                          const float* wpack, const float* bias,
                          int B, int Cin, int Cout, int D, int H, int W,
-                         int dilation, int act, void* stream);
+                         int dilation, int act, int half, void* stream);
 /* Stride-2 3x3 conv (padding 1) and stride-2 transposed convs through the same tensor-core kernel
  * (tstereo_conv_hw3_tc2 over a virtual tensor: input parity phases stacked on the channel axis / one output parity
  * phase per launch).  Any Cout (groups of 32).  ref: aggregation/TemporalStereo/module.py:111-184 (stride-2
@@ -99,25 +102,25 @@ int tstereo_conv_hw3_tc2(const float* in, long long isB, long long isC, long lon
  *           phase = (row parity, col parity), Cin8 = Cin rounded up to 8;
  *   deconv: [phase (py,px) 4] x per 32-channel group the tc2 image of the 3x3 shift kernel of that output phase
  *           (k = 3: padding 1, output_padding 1;  k = 4: padding 1; both give Hout = 2*Hin). */
-long long tstereo_conv_hw3s2_tc2_wpack_floats(int Cin, int Cout);
+long long tstereo_conv_hw3s2_tc2_wpack_floats(int Cin, int Cout, int half);
 int tstereo_conv_hw3s2_tc2(const float* in, long long isB, long long isC, long long isD,
                            float* out, long long osB, long long osC, long long osD,
                            const float* wpack, const float* bias,
-                           int B, int Cin, int Cout, int D, int Hin, int Win, int act, void* stream);
-long long tstereo_deconv_hw_tc2_wpack_floats(int Cin, int Cout);
+                           int B, int Cin, int Cout, int D, int Hin, int Win, int act, int half, void* stream);
+long long tstereo_deconv_hw_tc2_wpack_floats(int Cin, int Cout, int half);
 int tstereo_deconv_hw_tc2(const float* in, long long isB, long long isC, long long isD,
                           float* out, long long osB, long long osC, long long osD,
                           const float* wpack, const float* bias,
-                          int B, int Cin, int Cout, int D, int Hin, int Win, int act, void* stream);
+                          int B, int Cin, int Cout, int D, int Hin, int Win, int act, int half, void* stream);
 /* (k,1,1) conv along D (same argument meaning as tstereo_conv_d_tc) through the second-generation tensor-core
  * kernel: the k input planes are K-chunks of a 1x1 conv.  wpack: pack_conv_d_tc2 in temporalstereo_b200/ops.py,
  * tstereo_conv_d_tc2_wpack_floats(Cin, Cout, k) floats. */
-long long tstereo_conv_d_tc2_wpack_floats(int Cin, int Cout, int k);
+long long tstereo_conv_d_tc2_wpack_floats(int Cin, int Cout, int k, int half);
 int tstereo_conv_d_tc2(const float* in, long long isB, long long isC, long long isD,
                        float* out, long long osB, long long osC, long long osD,
                        const float* wpack, const float* bias,
                        int B, int Cin, int Cout, int Din, int Dout, int H, int W,
-                       int k, int stride, int dilation, int transposed, int act, void* stream);
+                       int k, int stride, int dilation, int transposed, int act, int half, void* stream);
 int tstereo_conv_d_tc(const float* in, long long isB, long long isC, long long isD,
                       float* out, long long osB, long long osC, long long osD,
                       const float* wpack, const float* bias,

@@ -12,6 +12,9 @@ bias = torch.randn(Cout, device="cuda")
 if kind == "tc2":
     wp = ops.pack_conv_hw3_tc2(w)
     f = lambda: ops.conv_hw3_tc2(x, wp, bias, Cout, dil, "SiLU")
+elif kind == "f16":
+    wp = ops.pack_conv_hw3_tc2(w, True)
+    f = lambda: ops.conv_hw3_tc2(x, wp, bias, Cout, dil, "SiLU", half=True)
 else:
     wp = ops.pack_conv_hw3_tc(w)
     f = lambda: ops.conv_hw3_tc(x, wp, bias, Cout, dil, "SiLU")

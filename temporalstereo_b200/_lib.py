@@ -26,14 +26,14 @@ SIGNATURES = {
     "tstereo_conv_hw3": (I, [P, LL, LL, LL, P, LL, LL, LL, P, P, I, I, I, I, I, I, I, I, I, I, I, P]),
     "tstereo_conv_tc_wpack_floats": (LL, [I, I, I]),
     "tstereo_conv_hw3_tc": (I, [P, LL, LL, LL, P, LL, LL, LL, P, P, I, I, I, I, I, I, I, I, P]),
-    "tstereo_conv_hw3_tc2_wpack_floats": (LL, [I, I]),
-    "tstereo_conv_hw3_tc2": (I, [P, LL, LL, LL, P, LL, LL, LL, P, P, I, I, I, I, I, I, I, I, P]),
-    "tstereo_conv_hw3s2_tc2_wpack_floats": (LL, [I, I]),
-    "tstereo_conv_hw3s2_tc2": (I, [P, LL, LL, LL, P, LL, LL, LL, P, P, I, I, I, I, I, I, I, P]),
-    "tstereo_deconv_hw_tc2_wpack_floats": (LL, [I, I]),
-    "tstereo_deconv_hw_tc2": (I, [P, LL, LL, LL, P, LL, LL, LL, P, P, I, I, I, I, I, I, I, P]),
-    "tstereo_conv_d_tc2_wpack_floats": (LL, [I, I, I]),
-    "tstereo_conv_d_tc2": (I, [P, LL, LL, LL, P, LL, LL, LL, P, P, I, I, I, I, I, I, I, I, I, I, I, I, P]),
+    "tstereo_conv_hw3_tc2_wpack_floats": (LL, [I, I, I]),
+    "tstereo_conv_hw3_tc2": (I, [P, LL, LL, LL, P, LL, LL, LL, P, P, I, I, I, I, I, I, I, I, I, P]),
+    "tstereo_conv_hw3s2_tc2_wpack_floats": (LL, [I, I, I]),
+    "tstereo_conv_hw3s2_tc2": (I, [P, LL, LL, LL, P, LL, LL, LL, P, P, I, I, I, I, I, I, I, I, P]),
+    "tstereo_deconv_hw_tc2_wpack_floats": (LL, [I, I, I]),
+    "tstereo_deconv_hw_tc2": (I, [P, LL, LL, LL, P, LL, LL, LL, P, P, I, I, I, I, I, I, I, I, P]),
+    "tstereo_conv_d_tc2_wpack_floats": (LL, [I, I, I, I]),
+    "tstereo_conv_d_tc2": (I, [P, LL, LL, LL, P, LL, LL, LL, P, P, I, I, I, I, I, I, I, I, I, I, I, I, I, P]),
     "tstereo_conv_d_tc": (I, [P, LL, LL, LL, P, LL, LL, LL, P, P, I, I, I, I, I, I, I, I, I, I, I, I, P]),
     "tstereo_conv_d": (I, [P, LL, LL, LL, P, LL, LL, LL, P, P, I, I, I, I, I, I, I, I, I, I, I, P]),
     "tstereo_deconv_hw": (I, [P, LL, LL, LL, P, LL, LL, LL, P, P, I, I, I, I, I, I, I, I, P]),

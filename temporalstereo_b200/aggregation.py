@@ -95,6 +95,8 @@ class TEMPORALSTEREO(nn.Module):
         # first call of a shape (outside CUDA-graph capture) and keeps the faster; "tc" / "simt" force one
         self.plan_mode = "auto"
         self._plan: Dict[tuple, str] = {}
+        # tensor-core operand split: fp16 hi + lo (kind::f16, 16 channels per MMA; activations < 65504) or tf32 hi + lo
+        self.half_split = True
         # run the UNet encoder on a side stream, concurrently with the coarse and fine levels
         self.overlap_encoder = True
         self._side: Dict[str, torch.cuda.Stream] = {}
@@ -193,7 +195,7 @@ class TEMPORALSTEREO(nn.Module):
         if tc_ok and cout <= 64 and cin >= 8 and w.is_cuda and self.tensor_cores:
             wtc = ops.pack_conv_tc(w)
             if is_hw:
-                wtc2 = ops.pack_conv_hw3_tc2(w)
+                wtc2 = ops.pack_conv_hw3_tc2(w, self.half_split)
         return _Packed(packed.contiguous(), None if bias is None else bias.contiguous(), cout, wtc, wtc2)
 
     def _pack(self) -> Dict[str, _Packed]:
@@ -288,14 +290,15 @@ class TEMPORALSTEREO(nn.Module):
             return simt()
         if stride == 2 and dil == 1 and k.w.shape[1] == 9:
             if "s2" not in k.lazy:      # [Cin][9][CoutP] -> [Cout][Cin][9]
-                k.lazy["s2"] = ops.pack_conv_hw3s2_tc2(k.w[:, :, :k.cout].permute(2, 0, 1).contiguous())
+                k.lazy["s2"] = ops.pack_conv_hw3s2_tc2(k.w[:, :, :k.cout].permute(2, 0, 1).contiguous(), self.half_split)
             return self._pick(("hw3s2", tuple(x.shape), k.cout),
-                              {"tc2": lambda: ops.conv_hw3s2_tc2(x, k.lazy["s2"], k.b, k.cout, act, out=out), "simt": simt})
+                              {"tc2": lambda: ops.conv_hw3s2_tc2(x, k.lazy["s2"], k.b, k.cout, act, out=out, half=self.half_split),
+                               "simt": simt})
         if k.wtc2 is None or stride != 1:
             return simt()
         # the first-generation kernel (ops.conv_hw3_tc) stays an operator of the library but is no plan candidate:
         # conv_hw3_tc2 is faster on every layer shape of the model
-        cands = {"tc2": lambda: ops.conv_hw3_tc2(x, k.wtc2, k.b, k.cout, dil, act, out=out), "simt": simt}
+        cands = {"tc2": lambda: ops.conv_hw3_tc2(x, k.wtc2, k.b, k.cout, dil, act, out=out, half=self.half_split), "simt": simt}
         return self._pick(("hw3", tuple(x.shape), k.cout, dil), cands)
 
     def _d(self, x, k: _Packed, ksz=3, stride=1, dil=1, transposed=False, act=None, out=None):
@@ -305,8 +308,9 @@ class TEMPORALSTEREO(nn.Module):
             return simt()
         key = ("d", tuple(x.shape), k.cout, ksz, stride, dil, transposed)
         if "d2" not in k.lazy:          # [Cin][k][CoutP] -> [Cout][Cin][k]
-            k.lazy["d2"] = ops.pack_conv_d_tc2(k.w[:, :, :k.cout].permute(2, 0, 1).contiguous())
-        return self._pick(key, {"tc2": lambda: ops.conv_d_tc2(x, k.lazy["d2"], k.b, k.cout, ksz, stride, dil, transposed, act, out=out),
+            k.lazy["d2"] = ops.pack_conv_d_tc2(k.w[:, :, :k.cout].permute(2, 0, 1).contiguous(), self.half_split)
+        return self._pick(key, {"tc2": lambda: ops.conv_d_tc2(x, k.lazy["d2"], k.b, k.cout, ksz, stride, dil, transposed, act, out=out,
+                                                              half=self.half_split),
                                 "simt": simt})
 
     def _deconv_hw(self, x, k: _Packed, ksz, act=None, out=None):
@@ -315,9 +319,10 @@ class TEMPORALSTEREO(nn.Module):
         if not self.tensor_cores or not k.w.is_cuda or k.w.shape[0] < 8:
             return simt()
         if "dc" not in k.lazy:          # [Cin][k*k][CoutP] (transposed-conv tap order) -> [Cout][Cin][k*k]
-            k.lazy["dc"] = ops.pack_deconv_hw_tc2(k.w[:, :, :k.cout].permute(2, 0, 1).contiguous(), ksz)
+            k.lazy["dc"] = ops.pack_deconv_hw_tc2(k.w[:, :, :k.cout].permute(2, 0, 1).contiguous(), ksz, self.half_split)
         return self._pick(("dc", tuple(x.shape), k.cout, ksz),
-                          {"tc2": lambda: ops.deconv_hw_tc2(x, k.lazy["dc"], k.b, k.cout, act, out=out), "simt": simt})
+                          {"tc2": lambda: ops.deconv_hw_tc2(x, k.lazy["dc"], k.b, k.cout, act, out=out, half=self.half_split),
+                           "simt": simt})
 
     def _sep(self, x, p, stride=1, dil=1, act0="SiLU", act1="SiLU", out=None):
         """'DepthwiseConv3D': (1,3,3) conv then (3,1,1) conv, BN folded (reference module.py:111-147)."""

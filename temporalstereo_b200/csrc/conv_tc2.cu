@@ -39,6 +39,11 @@
 //     split to tf32 hi/lo and store the K-major operand.  No per-element address arithmetic, predication or
 //     register prefetch; the loads run `rs` chunks ahead.  The register path (below) remains for phase-decomposed
 //     (stride-2) inputs and unaligned widths.
+//   * F16 variant (template flag, the engine's default): operands split as fp16 hi + fp16 lo (22 mantissa bits,
+//     same three product terms) and multiplied with `kind::f16`: K = 16 channels per MMA instead of 8, i.e. half the
+//     MMAs and half the shared-memory operand traffic per channel (the kernel is shared-memory-pipe bound) at twice
+//     the tensor rate.  Measured EPE vs fp32 on the oracle: 8.0e-6 px (3xTF32: 8.6e-6).  fp16 range: activations
+//     must stay below 65504 in magnitude (the model's are O(1..100)).
 //
 //  warps 0-7 : producers (global NCDHW fp32 -> hi/lo tf32 -> K-major SWIZZLE_NONE smem) + accumulator readers
 //              + epilogue;  warp 8 : TMEM alloc, MMA issue (one elected lane), commits.
@@ -76,12 +81,35 @@ struct Params {
     int rs;                       // TMA variant: raw fp32 stages in flight
     int bw;                       // TMA variant: box width in elements (32, or 36 when the halo shifts the 16-byte aligned origin)
     int nbatch;                   // batch size (extent of the TMA view's last dimension)
+    int half;                     // operands as fp16 hi + lo (kind::f16, 16 channels per MMA) instead of tf32 hi + lo
     int nky;                      // ky taps of the virtual conv: 3, or 1 for the (k,1,1) convs along D
     int kd, dstride, ddil, Din, dtrans;   // kd > 0: phases are input planes of a conv along D (p.D = Dout)
 };
 
 // cvt.rna.tf32.f32 without the NaN/Inf handling ptxas wraps around it (operands here are finite activations)
 __device__ __forceinline__ uint32_t tf32_rna(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (fp16 operands, fp32 accumulate), M = 128, K = 16
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// instruction descriptor: D fp32, A/B fp16, both K-major, M = 128, N = n
+__host__ __device__ constexpr uint32_t idesc_f16(uint32_t n) { return (1u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24); }
+// two floats -> packed fp16x2 (low half = a)
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t h) {
+    float2 f;
+    asm("{\n\t.reg .b16 l, u;\n\tmov.b32 {l, u}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, u;\n\t}" : "=f"(f.x), "=f"(f.y) : "r"(h));
+    return f;
+}
 
 // Activation of the epilogue, compile-time selected (the epilogue is instruction-bound).  SiLU uses
 // ex2.approx / rcp.approx (~1e-6 relative); the full-precision expf + IEEE division of silu_f cost ~50
@@ -172,9 +200,10 @@ __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* t
 
 constexpr int MAX_RS = 4;
 
-template <int CP, int MT, bool DIRECT, bool TMA>
+template <int CP, int MT, bool DIRECT, bool TMA, bool F16>
 __global__ void __launch_bounds__(NTHREADS, Cfg<CP, MT, DIRECT>::MINB)
 conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
+    static_assert(!(TMA && F16), "the TMA producer stages tf32 operands only");
     using C = Cfg<CP, MT, DIRECT>;
     constexpr int N = C::N, JT = C::JT, RPW = C::RPW;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -227,7 +256,8 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int ngroups = (p.nchunk + p.G - 1) / p.G;
+    const int nmma = F16 ? (p.nchunk + 1) / 2 : p.nchunk;     // MMA chunks (16 | 8 channels); p.nchunk counts 8-channel units
+    const int ngroups = (nmma + p.G - 1) / p.G;
 
 // TMA variant: the MMA warp keeps `rs` chunk loads in flight; chunk kk -> (phase, channel chunk) -> box coordinates
     int t_issue = 0;
@@ -346,11 +376,14 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
         int s = 0, gk = 0, gdone = 0;      // stage of chunk k; chunks produced since the last group boundary; groups drained
         uint32_t ph = 0;
         for (int k = 0; k < p.nchunk; ++k) {
-            mbar_wait(&empty[s], ph ^ 1u);
+            // F16: two 8-channel units (K halves) make one MMA chunk / shared-memory stage
+            const bool first_half = !F16 || !(k & 1);
+            const bool last_half = !F16 || (k & 1) || k == p.nchunk - 1;
+            if (first_half) mbar_wait(&empty[s], ph ^ 1u);
             uint8_t* st_base = smem + (size_t)s * stage_bytes;
-            if (tid == 0) {
+            if (first_half && tid == 0) {
                 mbar_arrive_expect_tx(&full[s], b_bytes);
-                bulk_g2s(st_base + a_bytes, p.wpack + (size_t)k * (b_bytes / 4), b_bytes, &full[s]);
+                bulk_g2s(st_base + a_bytes, p.wpack + (size_t)(F16 ? k >> 1 : k) * (b_bytes / 4), b_bytes, &full[s]);
             }
             const uint32_t a_hi = smem_u32(st_base);
             const uint32_t khalf = NPOS * 16u;
@@ -380,6 +413,29 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
                 __syncwarp();
                 if (elect_one()) mbar_arrive(&raw_empty[rsl]);      // this warp has read the raw stage
                 __syncwarp();
+            } else if constexpr (F16) {
+                const uint32_t ko = (uint32_t)(k & 1) * khalf;         // K half of this unit inside the chunk
+#pragma unroll
+                for (int u = 0; u < RPW; ++u) {
+                    const int r = warp + 8 * u;
+                    if (r < SR) {
+                        uint32_t hi[4], lo[4];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            hi[c] = pack_h2(v[u][2 * c], v[u][2 * c + 1]);
+                            const float2 hf = unpack_h2(hi[c]);
+                            lo[c] = pack_h2(v[u][2 * c] - hf.x, v[u][2 * c + 1] - hf.y);
+                        }
+                        const uint32_t o = (uint32_t)(r * 32 + lane) * 16u;
+                        sts128(a_hi + ko + o, hi[0], hi[1], hi[2], hi[3]);
+                        sts128(a_lo + ko + o, lo[0], lo[1], lo[2], lo[3]);
+                        if (!(k & 1) && k == p.nchunk - 1) {            // odd number of units: the last K half is zero
+                            sts128(a_hi + khalf + o, 0u, 0u, 0u, 0u);
+                            sts128(a_lo + khalf + o, 0u, 0u, 0u, 0u);
+                        }
+                    }
+                }
+                if (k + 1 < p.nchunk) load_chunk();
             } else {
 #pragma unroll
                 for (int u = 0; u < RPW; ++u) {
@@ -402,19 +458,21 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
                 }
                 if (k + 1 < p.nchunk) load_chunk();    // in flight across the barrier traffic and the drain below
             }
-            fence_proxy_async();                       // generic-proxy st.shared -> visible to the tensor core
-            mbar_arrive(&full[s]);
-            if (++s == p.stages) {
-                s = 0;
-                ph ^= 1u;
-            }
-            if constexpr (!DIRECT) {
-                // a group that finished one chunk ago is drained now: overlaps chunk k's MMAs
-                if (gk == p.G) {
-                    drain(gdone++);
-                    gk = 0;
+            if (last_half) {
+                fence_proxy_async();                   // generic-proxy st.shared -> visible to the tensor core
+                mbar_arrive(&full[s]);
+                if (++s == p.stages) {
+                    s = 0;
+                    ph ^= 1u;
                 }
-                ++gk;
+                if constexpr (!DIRECT) {
+                    // a group that finished one chunk ago is drained now: overlaps this chunk's MMAs
+                    if (gk == p.G) {
+                        drain(gdone++);
+                        gk = 0;
+                    }
+                    ++gk;
+                }
             }
         }
         if constexpr (!DIRECT) drain(ngroups - 1);
@@ -449,15 +507,19 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
         if constexpr (DIRECT) tc_fence_before();
     } else {
         // ===================== MMA issuer =====================
-        constexpr uint32_t idesc_2n = idesc_tf32(2 * N), idesc_n = idesc_tf32(C::N2);
+        constexpr uint32_t idesc_2n = F16 ? idesc_f16(2 * N) : idesc_tf32(2 * N), idesc_n = F16 ? idesc_f16(C::N2) : idesc_tf32(C::N2);
+        auto mma = [](uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accf) {
+            if constexpr (F16) tc_mma_f16(d, a, b, idesc, accf);
+            else tc_mma_tf32(d, a, b, idesc, accf);
+        };
         const uint32_t a_lbo = NPOS * 16u, b_lbo = 2u * N * 16u;
         int s = 0, g = 0, kg = 0;          // stage; accumulation group; chunk index inside the group
         uint32_t ph = 0;
         if constexpr (TMA)
             for (int i = 0; i < p.rs && i < p.nchunk; ++i) issue_tma();
-        for (int k = 0; k < p.nchunk; ++k) {
+        for (int k = 0; k < nmma; ++k) {
             const bool first = DIRECT ? k == 0 : kg == 0;
-            const bool last = DIRECT ? k == p.nchunk - 1 : (kg == p.G - 1 || k == p.nchunk - 1);
+            const bool last = DIRECT ? k == nmma - 1 : (kg == p.G - 1 || k == nmma - 1);
             mbar_wait(&full[s], ph);
             tc_fence_after();
             const uint32_t st_base = smem_u32(smem + (size_t)s * stage_bytes);
@@ -481,14 +543,14 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
                         const uint32_t acc0 = (first && ky == 0) ? 0u : 1u;
                         if constexpr (DIRECT) {
                             // all three terms into the same N columns (B rows [0,N) = hi, [N,2N) = lo)
-                            tc_mma_tf32(d_tmem, a_hi + ad, bd, idesc_n, acc0);
-                            tc_mma_tf32(d_tmem, a_hi + ad, bd + (uint64_t)N, idesc_n, 1u);
-                            tc_mma_tf32(d_tmem, a_lo + ad, bd, idesc_n, 1u);
+                            mma(d_tmem, a_hi + ad, bd, idesc_n, acc0);
+                            mma(d_tmem, a_hi + ad, bd + (uint64_t)N, idesc_n, 1u);
+                            mma(d_tmem, a_lo + ad, bd, idesc_n, 1u);
                         } else {
                             // [A*B_hi | A_hi*B_lo] (+)= A_hi * [B_hi | B_lo]
-                            tc_mma_tf32(d_tmem, a_hi + ad, bd, idesc_2n, acc0);
+                            mma(d_tmem, a_hi + ad, bd, idesc_2n, acc0);
                             // first block += A_lo * B_hi
-                            tc_mma_tf32(d_tmem, a_lo + ad, bd, idesc_n, 1u);
+                            mma(d_tmem, a_lo + ad, bd, idesc_n, 1u);
                         }
                     }
                     if (last) tc_commit(&acc_full[j]);
@@ -570,9 +632,9 @@ static bool make_tmap(const Params& p, int SR, CUtensorMap* tm) {
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int CP, int MT, bool DIRECT, bool TMA>
+template <int CP, int MT, bool DIRECT, bool TMA, bool F16>
 static int launch_one(const Params& p, const CUtensorMap& tm, dim3 grid, size_t smem_bytes, cudaStream_t st, const char* what) {
-    auto kern = conv_tc2_kernel<CP, MT, DIRECT, TMA>;
+    auto kern = conv_tc2_kernel<CP, MT, DIRECT, TMA, F16>;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
@@ -609,12 +671,14 @@ static int launch(Params& p, int CP, int planes, cudaStream_t st, const char* wh
     const int g_env = env_int("TSTEREO_TC2_G", 0);      // experiments: chunks per accumulation group (per input phase)
     if (g_env > 0) p.G = g_env * (p.nchunk / p.cpp);
     if (p.G < 1) p.G = 1;
-    const bool direct = p.nchunk <= p.G && !env_int("TSTEREO_TC2_NODIRECT", 0);
+    const int nmma = p.half ? (p.nchunk + 1) / 2 : p.nchunk;
+    if (p.half) p.G = (p.G + 1) / 2;                     // same products per accumulation group: 16 channels per chunk
+    const bool direct = nmma <= p.G && !env_int("TSTEREO_TC2_NODIRECT", 0);
     // M-tiles per CTA: 2 or 4 (TMEM: MT * columns-per-tile <= 512); cost = SM-time of all waves
     p.nbatch = planes / p.D;
     p.bw = p.dil ? 36 : 32;
     CUtensorMap tm = {};
-    const bool tma_ok = make_tmap(p, 4 * 2 + 2 * p.dil, &tm);     // eligibility (the box is re-encoded for the chosen tile)
+    const bool tma_ok = !p.half && make_tmap(p, 4 * 2 + 2 * p.dil, &tm);   // eligibility (the box is re-encoded for the chosen tile)
     int best_mt = 0, best_stages = 0, best_rs = 0;
     double best_cost = 1e30;
     const int forced = env_int("TSTEREO_TC2_MT", 0);
@@ -671,10 +735,13 @@ static int launch(Params& p, int CP, int planes, cudaStream_t st, const char* wh
     dim3 grid(p.tiles_x * ((p.H + 4 * best_mt - 1) / (4 * best_mt)), planes);
 #define TS_TC2(CC, MM)                                                                                         \
     if (CP == CC && best_mt == MM) {                                                                           \
-        if (direct) return tma ? launch_one<CC, MM, true, true>(p, tm, grid, smem_bytes, st, what)             \
-                               : launch_one<CC, MM, true, false>(p, tm, grid, smem_bytes, st, what);           \
-        return tma ? launch_one<CC, MM, false, true>(p, tm, grid, smem_bytes, st, what)                        \
-                   : launch_one<CC, MM, false, false>(p, tm, grid, smem_bytes, st, what);                      \
+        if (p.half)                                                                                            \
+            return direct ? launch_one<CC, MM, true, false, true>(p, tm, grid, smem_bytes, st, what)           \
+                          : launch_one<CC, MM, false, false, true>(p, tm, grid, smem_bytes, st, what);         \
+        if (direct) return tma ? launch_one<CC, MM, true, true, false>(p, tm, grid, smem_bytes, st, what)      \
+                               : launch_one<CC, MM, true, false, false>(p, tm, grid, smem_bytes, st, what);    \
+        return tma ? launch_one<CC, MM, false, true, false>(p, tm, grid, smem_bytes, st, what)                 \
+                   : launch_one<CC, MM, false, false, false>(p, tm, grid, smem_bytes, st, what);               \
     }
     TS_TC2(8, 2) TS_TC2(8, 4) TS_TC2(16, 2) TS_TC2(16, 4) TS_TC2(32, 2)
 #undef TS_TC2
@@ -714,7 +781,7 @@ int run_groups(tc2::Params p, int Cout, int planes, cudaStream_t st, const char*
         p.out = out + (long long)c0 * p.osC;
         const int rc = tc2::launch(p, tc2_cp(cg), planes, st, what);
         if (rc != TSTEREO_OK) return rc;
-        wp += group_floats(p.nchunk, cg, p.nky);
+        wp += group_floats(p.half ? (p.nchunk + 1) / 2 : p.nchunk, cg, p.nky);
     }
     return TSTEREO_OK;
 }
@@ -723,13 +790,15 @@ int run_groups(tc2::Params p, int Cout, int planes, cudaStream_t st, const char*
 
 extern "C" {
 
-long long tstereo_conv_hw3_tc2_wpack_floats(int Cin, int Cout) { return wpack_floats((Cin + 7) / 8, Cout); }
+static int mma_chunks(int units, int half) { return half ? (units + 1) / 2 : units; }
+
+long long tstereo_conv_hw3_tc2_wpack_floats(int Cin, int Cout, int half) { return wpack_floats(mma_chunks((Cin + 7) / 8, half), Cout); }
 
 int tstereo_conv_hw3_tc2(const float* in, long long isB, long long isC, long long isD,
                          float* out, long long osB, long long osC, long long osD,
                          const float* wpack, const float* bias,
                          int B, int Cin, int Cout, int D, int H, int W,
-                         int dilation, int act, void* stream) {
+                         int dilation, int act, int half, void* stream) {
     TS_REQUIRE(in && out && wpack, "conv_hw3_tc2: null pointer");
     TS_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && D > 0 && H > 0 && W > 0, "conv_hw3_tc2: bad sizes");
     TS_REQUIRE(dilation == 1 || dilation == 2, "conv_hw3_tc2: dilation %d unsupported", dilation);
@@ -743,19 +812,19 @@ int tstereo_conv_hw3_tc2(const float* in, long long isB, long long isC, long lon
     p.wpack = wpack; p.bias = bias;
     p.Cin = Cin; p.H = H; p.W = W; p.D = D; p.Hin = H; p.Win = W;
     p.isY = W; p.isX = 1; p.osY = W; p.osX = 1;
-    p.dil = dilation; p.act = act; p.nky = 3;
+    p.dil = dilation; p.act = act; p.nky = 3; p.half = half != 0;
     p.cpp = (Cin + 7) / 8;
     p.nchunk = p.cpp;
     p.G = 8;
     return run_groups(p, Cout, B * D, (cudaStream_t)stream, "conv_hw3_tc2");
 }
 
-long long tstereo_conv_hw3s2_tc2_wpack_floats(int Cin, int Cout) { return wpack_floats(4 * ((Cin + 7) / 8), Cout); }
+long long tstereo_conv_hw3s2_tc2_wpack_floats(int Cin, int Cout, int half) { return wpack_floats(mma_chunks(4 * ((Cin + 7) / 8), half), Cout); }
 
 int tstereo_conv_hw3s2_tc2(const float* in, long long isB, long long isC, long long isD,
                            float* out, long long osB, long long osC, long long osD,
                            const float* wpack, const float* bias,
-                           int B, int Cin, int Cout, int D, int Hin, int Win, int act, void* stream) {
+                           int B, int Cin, int Cout, int D, int Hin, int Win, int act, int half, void* stream) {
     TS_REQUIRE(in && out && wpack, "conv_hw3s2_tc2: null pointer");
     TS_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && D > 0 && Hin > 0 && Win > 0, "conv_hw3s2_tc2: bad sizes");
     TS_REQUIRE((long long)B * D <= 65535, "conv_hw3s2_tc2: B*D exceeds grid.y");
@@ -769,19 +838,19 @@ int tstereo_conv_hw3s2_tc2(const float* in, long long isB, long long isC, long l
     p.wpack = wpack; p.bias = bias;
     p.Cin = Cin; p.H = H; p.W = W; p.D = D; p.Hin = Hin; p.Win = Win;
     p.isY = 2 * Win; p.isX = 2; p.osY = W; p.osX = 1;
-    p.dil = 1; p.act = act; p.nky = 3;
+    p.dil = 1; p.act = act; p.nky = 3; p.half = half != 0;
     p.cpp = (Cin + 7) / 8;
     p.nchunk = 4 * p.cpp;
     p.G = 32;     // of a chunk's 9 taps only the 1-4 that exist for its phase are non-zero: same products per group as G = 8
     return run_groups(p, Cout, B * D, (cudaStream_t)stream, "conv_hw3s2_tc2");
 }
 
-long long tstereo_deconv_hw_tc2_wpack_floats(int Cin, int Cout) { return 4 * wpack_floats((Cin + 7) / 8, Cout); }
+long long tstereo_deconv_hw_tc2_wpack_floats(int Cin, int Cout, int half) { return 4 * wpack_floats(mma_chunks((Cin + 7) / 8, half), Cout); }
 
 int tstereo_deconv_hw_tc2(const float* in, long long isB, long long isC, long long isD,
                           float* out, long long osB, long long osC, long long osD,
                           const float* wpack, const float* bias,
-                          int B, int Cin, int Cout, int D, int Hin, int Win, int act, void* stream) {
+                          int B, int Cin, int Cout, int D, int Hin, int Win, int act, int half, void* stream) {
     TS_REQUIRE(in && out && wpack, "deconv_hw_tc2: null pointer");
     TS_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && D > 0 && Hin > 0 && Win > 0, "deconv_hw_tc2: bad sizes");
     TS_REQUIRE((long long)B * D <= 65535, "deconv_hw_tc2: B*D exceeds grid.y");
@@ -794,11 +863,11 @@ int tstereo_deconv_hw_tc2(const float* in, long long isB, long long isC, long lo
     p.bias = bias;
     p.Cin = Cin; p.H = Hin; p.W = Win; p.D = D; p.Hin = Hin; p.Win = Win;
     p.isY = Win; p.isX = 1; p.osY = 4 * Win; p.osX = 2;      // output plane is (2*Hin) x (2*Win)
-    p.dil = 1; p.act = act; p.nky = 3;
+    p.dil = 1; p.act = act; p.nky = 3; p.half = half != 0;
     p.cpp = (Cin + 7) / 8;
     p.nchunk = p.cpp;
     p.G = 8;
-    const long long per_phase = wpack_floats(p.nchunk, Cout);
+    const long long per_phase = wpack_floats(mma_chunks(p.nchunk, p.half), Cout);
     for (int ph = 0; ph < 4; ++ph) {                           // output parity phase (py, px)
         p.out = out + (long long)(ph >> 1) * 2 * Win + (ph & 1);
         p.wpack = wpack + ph * per_phase;
@@ -808,13 +877,13 @@ int tstereo_deconv_hw_tc2(const float* in, long long isB, long long isC, long lo
     return TSTEREO_OK;
 }
 
-long long tstereo_conv_d_tc2_wpack_floats(int Cin, int Cout, int k) { return wpack_floats(k * ((Cin + 7) / 8), Cout, 1); }
+long long tstereo_conv_d_tc2_wpack_floats(int Cin, int Cout, int k, int half) { return wpack_floats(mma_chunks(k * ((Cin + 7) / 8), half), Cout, 1); }
 
 int tstereo_conv_d_tc2(const float* in, long long isB, long long isC, long long isD,
                        float* out, long long osB, long long osC, long long osD,
                        const float* wpack, const float* bias,
                        int B, int Cin, int Cout, int Din, int Dout, int H, int W,
-                       int k, int stride, int dilation, int transposed, int act, void* stream) {
+                       int k, int stride, int dilation, int transposed, int act, int half, void* stream) {
     TS_REQUIRE(in && out && wpack, "conv_d_tc2: null pointer");
     TS_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && Din > 0 && Dout > 0 && H > 0 && W > 0, "conv_d_tc2: bad sizes");
     TS_REQUIRE(k == 3 || k == 5, "conv_d_tc2: k=%d unsupported", k);
@@ -834,7 +903,7 @@ int tstereo_conv_d_tc2(const float* in, long long isB, long long isC, long long 
     p.wpack = wpack; p.bias = bias;
     p.Cin = Cin; p.H = H; p.W = W; p.D = Dout; p.Hin = H; p.Win = W;
     p.isY = W; p.isX = 1; p.osY = W; p.osX = 1;
-    p.dil = 0; p.act = act; p.nky = 1;
+    p.dil = 0; p.act = act; p.nky = 1; p.half = half != 0;
     p.kd = k; p.dstride = stride; p.ddil = dilation; p.Din = Din; p.dtrans = transposed;
     p.cpp = (Cin + 7) / 8;
     p.nchunk = k * p.cpp;

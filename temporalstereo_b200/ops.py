@@ -148,21 +148,29 @@ def conv_hw3_tc(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Tenso
     return out
 
 
-def _pack_tc2_group(w: torch.Tensor, nky: int = 3) -> torch.Tensor:
-    """One output-channel group (<= 32): [Cout, Cin, nky*3] -> [ceil(Cin/8)][ky nky][khalf 2][row 2N][4],
-    row = part*N + kx*CP + co, N = 3*CP, CP = 8|16|32."""
+def _pack_tc2_group(w: torch.Tensor, nky: int = 3, half: bool = False) -> torch.Tensor:
+    """One output-channel group (<= 32): [Cout, Cin, nky*3] -> [chunk][ky nky][khalf 2][row 2N][16 B],
+    row = part*N + kx*CP + co, N = 3*CP, CP = 8|16|32.  tf32 form: chunk = 8 channels, a 16-byte row holds 4 floats,
+    parts = tf32 hi / lo.  half form: chunk = 16 channels, a row holds 8 halves, parts = fp16 hi / lo (returned
+    reinterpreted as float32 pairs so the ABI keeps one pointer type)."""
     cout, cin, T = w.shape
     assert T == 3 * nky and cout <= 32
     CP = 8 if cout <= 8 else 16 if cout <= 16 else 32
-    nch = (cin + 7) // 8
-    full = torch.zeros((CP, nch * 8, nky, 3), device=w.device, dtype=torch.float32)
+    per = 16 if half else 8
+    nch = (cin + per - 1) // per
+    full = torch.zeros((CP, nch * per, nky, 3), device=w.device, dtype=torch.float32)
     full[:cout, :cin] = w.reshape(cout, cin, nky, 3)
+    if half:
+        hi = full.half()
+        lo = (full - hi.float()).half()
+        parts = torch.stack([hi, lo]).view(2, CP, nch, 2, 8, nky, 3)      # [part, co, chunk, khalf, i, ky, kx]
+        return parts.permute(2, 5, 3, 0, 6, 1, 4).contiguous().view(-1).view(torch.float32)
     hi, lo = tf32_split(full)
-    parts = torch.stack([hi, lo]).view(2, CP, nch, 2, 4, nky, 3)      # [part, co, chunk, khalf, i, ky, kx]
-    return parts.permute(2, 5, 3, 0, 6, 1, 4).contiguous().view(-1)   # [chunk, ky, khalf, part, kx, co, i]
+    parts = torch.stack([hi, lo]).view(2, CP, nch, 2, 4, nky, 3)          # [part, co, chunk, khalf, i, ky, kx]
+    return parts.permute(2, 5, 3, 0, 6, 1, 4).contiguous().view(-1)       # [chunk, ky, khalf, part, kx, co, i]
 
 
-def pack_conv_d_tc2(w: torch.Tensor) -> torch.Tensor:
+def pack_conv_d_tc2(w: torch.Tensor, half: bool = False) -> torch.Tensor:
     """(k,1,1) conv along D, w [Cout, Cin, k] -> operand image of tstereo_conv_d_tc2: the k input planes are stacked
     on the channel axis (virtual channel = tap*Cin8 + c) of a 1x1 conv (one ky tap, weights in the kx = 0 block)."""
     cout, cin, k = w.shape
@@ -170,16 +178,16 @@ def pack_conv_d_tc2(w: torch.Tensor) -> torch.Tensor:
     virt = torch.zeros((cout, k, cin8, 1, 3), device=w.device, dtype=torch.float32)
     virt[:, :, :cin, 0, 0] = w.permute(0, 2, 1)
     virt = virt.reshape(cout, k * cin8, 3)
-    return torch.cat([_pack_tc2_group(virt[c0:c0 + 32], 1) for c0 in range(0, cout, 32)])
+    return torch.cat([_pack_tc2_group(virt[c0:c0 + 32], 1, half) for c0 in range(0, cout, 32)])
 
 
-def pack_conv_hw3_tc2(w: torch.Tensor) -> torch.Tensor:
+def pack_conv_hw3_tc2(w: torch.Tensor, half: bool = False) -> torch.Tensor:
     """[Cout, Cin, 9] (BN folded, taps ky*3+kx) -> the B-operand image of tstereo_conv_hw3_tc2, output channels
     in groups of 32."""
-    return torch.cat([_pack_tc2_group(w[c0:c0 + 32]) for c0 in range(0, w.shape[0], 32)])
+    return torch.cat([_pack_tc2_group(w[c0:c0 + 32], 3, half) for c0 in range(0, w.shape[0], 32)])
 
 
-def pack_conv_hw3s2_tc2(w: torch.Tensor) -> torch.Tensor:
+def pack_conv_hw3s2_tc2(w: torch.Tensor, half: bool = False) -> torch.Tensor:
     """Stride-2 3x3 conv (padding 1) as a stride-1 3x3 conv over the four input parity phases stacked on the
     channel axis (tstereo_conv_hw3s2_tc2): tap k reads input 2*o + k - 1 = phase (k+1)%2 at o + {-1, 0, 0}[k]."""
     cout, cin, T = w.shape
@@ -191,10 +199,10 @@ def pack_conv_hw3s2_tc2(w: torch.Tensor) -> torch.Tensor:
     for ky, (pr, dm) in tap.items():
         for kx, (pc, dn) in tap.items():
             virt[:, pr * 2 + pc, :cin, dm + 1, dn + 1] = w4[:, :, ky, kx]
-    return pack_conv_hw3_tc2(virt.reshape(cout, 4 * cin8, 9))
+    return pack_conv_hw3_tc2(virt.reshape(cout, 4 * cin8, 9), half)
 
 
-def pack_deconv_hw_tc2(w: torch.Tensor, k: int) -> torch.Tensor:
+def pack_deconv_hw_tc2(w: torch.Tensor, k: int, half: bool = False) -> torch.Tensor:
     """Transposed conv (stride 2, padding 1; k=3 with output_padding 1, or k=4), w [Cout, Cin, k*k] in the
     transposed-conv tap order (out[2i - 1 + t] += in[i] * w[t]) -> four 3x3 shift kernels, one per output parity
     phase (tstereo_deconv_hw_tc2): out[2m + p] = sum_d in[m + d] * w[t(p, d)]."""
@@ -209,12 +217,12 @@ def pack_deconv_hw_tc2(w: torch.Tensor, k: int) -> torch.Tensor:
             for dy, ky in shifts[py].items():
                 for dx, kx in shifts[px].items():
                     ph[:, :, dy + 1, dx + 1] = w4[:, :, ky, kx]
-            packs.append(pack_conv_hw3_tc2(ph.reshape(cout, cin, 9)))
+            packs.append(pack_conv_hw3_tc2(ph.reshape(cout, cin, 9), half))
     return torch.cat(packs)
 
 
 def conv_hw3_tc2(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Tensor], cout: int, dilation: int = 1,
-                 act=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                 act=None, out: Optional[torch.Tensor] = None, half: bool = False) -> torch.Tensor:
     """Stride-1 (1,3,3) / 3x3 conv on the tensor cores (kx-folded tcgen05 kernel, 3xTF32)."""
     five = x.dim() == 5
     B, Cin = x.shape[:2]
@@ -225,14 +233,14 @@ def conv_hw3_tc2(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Tens
     isB, isC, isD = _view5(x)
     osB, osC, osD = _view5(out)
     _chk(wpack, bias)
-    assert wpack.numel() == _lib.load().tstereo_conv_hw3_tc2_wpack_floats(Cin, cout)
+    assert wpack.numel() == _lib.load().tstereo_conv_hw3_tc2_wpack_floats(Cin, cout, int(half))
     _lib.call("tstereo_conv_hw3_tc2", _p(x), isB, isC, isD, _p(out), osB, osC, osD, _p(wpack), _p(bias),
-              B, Cin, cout, D, H, W, dilation, ACT[act], _stream())
+              B, Cin, cout, D, H, W, dilation, ACT[act], int(half), _stream())
     return out
 
 
 def conv_hw3s2_tc2(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Tensor], cout: int, act=None,
-                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                   out: Optional[torch.Tensor] = None, half: bool = False) -> torch.Tensor:
     """Stride-2 (1,3,3) / 3x3 conv, padding 1, on the tensor cores (phase-decomposed input, 3xTF32)."""
     five = x.dim() == 5
     B, Cin = x.shape[:2]
@@ -244,14 +252,14 @@ def conv_hw3s2_tc2(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Te
     isB, isC, isD = _view5(x)
     osB, osC, osD = _view5(out)
     _chk(wpack, bias)
-    assert wpack.numel() == _lib.load().tstereo_conv_hw3s2_tc2_wpack_floats(Cin, cout)
+    assert wpack.numel() == _lib.load().tstereo_conv_hw3s2_tc2_wpack_floats(Cin, cout, int(half))
     _lib.call("tstereo_conv_hw3s2_tc2", _p(x), isB, isC, isD, _p(out), osB, osC, osD, _p(wpack), _p(bias),
-              B, Cin, cout, D, Hin, Win, ACT[act], _stream())
+              B, Cin, cout, D, Hin, Win, ACT[act], int(half), _stream())
     return out
 
 
 def deconv_hw_tc2(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Tensor], cout: int, act=None,
-                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                  out: Optional[torch.Tensor] = None, half: bool = False) -> torch.Tensor:
     """Transposed (1,k,k)/kxk conv, stride 2 (Hout = 2*Hin), on the tensor cores: one output parity phase per launch."""
     five = x.dim() == 5
     B, Cin = x.shape[:2]
@@ -263,14 +271,15 @@ def deconv_hw_tc2(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Ten
     isB, isC, isD = _view5(x)
     osB, osC, osD = _view5(out)
     _chk(wpack, bias)
-    assert wpack.numel() == _lib.load().tstereo_deconv_hw_tc2_wpack_floats(Cin, cout)
+    assert wpack.numel() == _lib.load().tstereo_deconv_hw_tc2_wpack_floats(Cin, cout, int(half))
     _lib.call("tstereo_deconv_hw_tc2", _p(x), isB, isC, isD, _p(out), osB, osC, osD, _p(wpack), _p(bias),
-              B, Cin, cout, D, Hin, Win, ACT[act], _stream())
+              B, Cin, cout, D, Hin, Win, ACT[act], int(half), _stream())
     return out
 
 
 def conv_d_tc2(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Tensor], cout: int, k: int = 3, stride: int = 1,
-               dilation: int = 1, transposed: bool = False, act=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+               dilation: int = 1, transposed: bool = False, act=None, out: Optional[torch.Tensor] = None,
+               half: bool = False) -> torch.Tensor:
     """(k,1,1) conv along D (or its stride-2 transposed form) through the second-generation tensor-core kernel."""
     B, Cin, Din, H, W = x.shape
     Dout = 2 * Din if transposed else (Din - 1) // stride + 1
@@ -279,9 +288,9 @@ def conv_d_tc2(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Tensor
     isB, isC, isD = _view5(x)
     osB, osC, osD = _view5(out)
     _chk(wpack, bias)
-    assert wpack.numel() == _lib.load().tstereo_conv_d_tc2_wpack_floats(Cin, cout, k)
+    assert wpack.numel() == _lib.load().tstereo_conv_d_tc2_wpack_floats(Cin, cout, k, int(half))
     _lib.call("tstereo_conv_d_tc2", _p(x), isB, isC, isD, _p(out), osB, osC, osD, _p(wpack), _p(bias),
-              B, Cin, cout, Din, Dout, H, W, k, stride, dilation, int(transposed), ACT[act], _stream())
+              B, Cin, cout, Din, Dout, H, W, k, stride, dilation, int(transposed), ACT[act], int(half), _stream())
     return out
 
 

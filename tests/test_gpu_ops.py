@@ -482,15 +482,16 @@ TC2_CASES = [
 ]
 
 
+@pytest.mark.parametrize("half", [False, True])
 @pytest.mark.parametrize("B,Cin,Cout,D,H,W,dil,act,bias", TC2_CASES)
-def test_conv_hw3_tc2(ops, B, Cin, Cout, D, H, W, dil, act, bias):
-    """kx-folded tcgen05 conv (2-D tiles, 3xTF32 operands) == fp64 conv to fp32 rounding."""
+def test_conv_hw3_tc2(ops, B, Cin, Cout, D, H, W, dil, act, bias, half):
+    """kx-folded tcgen05 conv (2-D tiles; tf32 hi+lo or fp16 hi+lo operands) == fp64 conv to fp32 rounding."""
     x = rnd(B, Cin, D, H, W, seed=41)
     w = rnd(Cout, Cin, 1, 3, 3, seed=42, scale=(2.0 / (9 * Cin)) ** 0.5)
     b = rnd(Cout, seed=43, scale=0.1) if bias else None
     want = O._act(F.conv3d(x.double(), w.double(), None if b is None else b.double(), 1, (0, dil, dil), (1, dil, dil)), act).float()
-    wp = ops.pack_conv_hw3_tc2(w.reshape(Cout, Cin, 9).cuda())
-    got = ops.conv_hw3_tc2(x.cuda(), wp, None if b is None else b.cuda(), Cout, dil, act)
+    wp = ops.pack_conv_hw3_tc2(w.reshape(Cout, Cin, 9).cuda(), half)
+    got = ops.conv_hw3_tc2(x.cuda(), wp, None if b is None else b.cuda(), Cout, dil, act, half=half)
     close(got, want, 1e-5, rtol=1e-5, what="conv_hw3_tc2")
 
 
@@ -567,16 +568,17 @@ S2_CASES = [
 ]
 
 
+@pytest.mark.parametrize("half", [False, True])
 @pytest.mark.parametrize("B,Cin,Cout,D,Hin,Win,act", S2_CASES)
-def test_conv_hw3s2_tc2(ops, B, Cin, Cout, D, Hin, Win, act):
+def test_conv_hw3s2_tc2(ops, B, Cin, Cout, D, Hin, Win, act, half):
     """Stride-2 3x3 conv through the phase-decomposed tensor-core kernel vs fp64 (odd sizes: the odd-parity
     phases end one row / column early)."""
     x = rnd(B, Cin, D, Hin, Win, seed=71)
     w = rnd(Cout, Cin, 1, 3, 3, seed=72, scale=(2.0 / (9 * Cin)) ** 0.5)
     b = rnd(Cout, seed=73, scale=0.1)
     want = O._act(F.conv3d(x.double(), w.double(), b.double(), (1, 2, 2), (0, 1, 1)), act).float()
-    wp = ops.pack_conv_hw3s2_tc2(w.reshape(Cout, Cin, 9).cuda())
-    got = ops.conv_hw3s2_tc2(x.cuda(), wp, b.cuda(), Cout, act)
+    wp = ops.pack_conv_hw3s2_tc2(w.reshape(Cout, Cin, 9).cuda(), half)
+    got = ops.conv_hw3s2_tc2(x.cuda(), wp, b.cuda(), Cout, act, half=half)
     assert got.shape == want.shape
     close(got, want, 1e-5, rtol=1e-5, what="conv_hw3s2_tc2")
 
@@ -584,15 +586,16 @@ def test_conv_hw3s2_tc2(ops, B, Cin, Cout, D, Hin, Win, act):
 @pytest.mark.parametrize("B,Cin,Cout,D,Hin,Win,k,act", [
     (1, 32, 32, 1, 17, 30, 4, "ReLU"), (2, 32, 9, 1, 34, 60, 4, None), (1, 64, 32, 3, 9, 15, 3, None),
     (1, 16, 8, 5, 34, 60, 3, None), (1, 8, 8, 1, 1, 1, 3, None), (1, 40, 40, 2, 5, 33, 4, "SiLU")])
-def test_deconv_hw_tc2(ops, B, Cin, Cout, D, Hin, Win, k, act):
+@pytest.mark.parametrize("half", [False, True])
+def test_deconv_hw_tc2(ops, B, Cin, Cout, D, Hin, Win, k, act, half):
     """Stride-2 transposed convs (k3 p1 op1 and k4 p1) as four output-phase launches of the tensor-core kernel."""
     x = rnd(B, Cin, D, Hin, Win, seed=74)
     w = rnd(Cin, Cout, 1, k, k, seed=75, scale=(2.0 / (k * k * Cin)) ** 0.5)
     b = rnd(Cout, seed=76, scale=0.1)
     op = 1 if k == 3 else 0
     want = O._act(F.conv_transpose3d(x.double(), w.double(), b.double(), (1, 2, 2), (0, 1, 1), (0, op, op)), act).float()
-    wp = ops.pack_deconv_hw_tc2(w.reshape(Cin, Cout, k * k).transpose(0, 1).contiguous().cuda(), k)
-    got = ops.deconv_hw_tc2(x.cuda(), wp, b.cuda(), Cout, act)
+    wp = ops.pack_deconv_hw_tc2(w.reshape(Cin, Cout, k * k).transpose(0, 1).contiguous().cuda(), k, half)
+    got = ops.deconv_hw_tc2(x.cuda(), wp, b.cuda(), Cout, act, half=half)
     assert got.shape == want.shape
     close(got, want, 1e-5, rtol=1e-5, what="deconv_hw_tc2")
 
@@ -637,7 +640,8 @@ def test_conv_d_tc(ops, B, Cin, Cout, Din, hw, k, stride, dil, transposed, act):
     (1, 8, 16, 5, (136, 240), 3, 1, 1, False, "SiLU"), (2, 64, 64, 6, (17, 30), 3, 2, 1, False, "SiLU"),
     (1, 32, 64, 14, (34, 60), 3, 1, 1, False, "SiLU"), (1, 16, 16, 7, (68, 120), 5, 1, 1, False, "SiLU"),
     (1, 64, 32, 3, (9, 15), 3, 1, 1, True, None), (1, 12, 5, 4, (7, 33), 3, 1, 2, False, "SiLU")])
-def test_conv_d_tc2(ops, B, Cin, Cout, Din, hw, k, stride, dil, transposed, act):
+@pytest.mark.parametrize("half", [False, True])
+def test_conv_d_tc2(ops, B, Cin, Cout, Din, hw, k, stride, dil, transposed, act, half):
     """(k,1,1) conv along D through the second-generation tensor-core kernel (planes as K-chunks) vs fp64."""
     H, W = hw
     x = rnd(B, Cin, Din, H, W, seed=47)
@@ -650,7 +654,8 @@ def test_conv_d_tc2(ops, B, Cin, Cout, Din, hw, k, stride, dil, transposed, act)
         w = rnd(Cout, Cin, k, 1, 1, seed=48, scale=0.1)
         want = O._act(F.conv3d(x.double(), w.double(), b.double(), (stride, 1, 1), (dil * (k // 2), 0, 0), (dil, 1, 1)), act).float()
         wk = w.reshape(Cout, Cin, k)
-    got = ops.conv_d_tc2(x.cuda(), ops.pack_conv_d_tc2(wk.contiguous().cuda()), b.cuda(), Cout, k, stride, dil, transposed, act)
+    got = ops.conv_d_tc2(x.cuda(), ops.pack_conv_d_tc2(wk.contiguous().cuda(), half), b.cuda(), Cout, k, stride, dil, transposed, act,
+                         half=half)
     close(got, want, 1e-5, rtol=1e-5, what="conv_d_tc2")
 
 
