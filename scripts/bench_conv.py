@@ -19,7 +19,10 @@ SHAPES = [  # name, Cin, Cout, D, H, W, dil
     ("fine fuse 64->16", 64, 16, 7, 68, 120, 1),
     ("coarse 32->32", 32, 32, 12, 34, 60, 1),
     ("coarse fuse 128->32", 128, 32, 14, 34, 60, 1),
-    ("hourglass 64->64... 32->32 @1/32", 32, 32, 6, 17, 30, 1),
+    ("hourglass 32->32 @1/32", 32, 32, 6, 17, 30, 1),
+    ("hourglass 64->64 @1/32", 64, 64, 6, 17, 30, 1),
+    ("hourglass 64->64 @1/64", 64, 64, 3, 9, 15, 1),
+    ("fine hg 32->32 @1/16", 32, 32, 3, 34, 60, 1),
 ]
 
 

@@ -198,12 +198,14 @@ __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* t
         : "memory");
 }
 
-constexpr int MAX_RS = 4;
+constexpr int MAX_RS = 8;
 
-template <int CP, int MT, bool DIRECT, bool TMA, bool F16>
+// RAW: 0 = chunks are prefetched into registers; 1 = TMA boxes into a raw fp32 ring; 2 = per-thread cp.async (zero-fill)
+// into the same ring, `rs` chunks deep — for the small, latency-bound layers (any width / alignment)
+template <int CP, int MT, bool DIRECT, int RAW, bool F16>
 __global__ void __launch_bounds__(NTHREADS, Cfg<CP, MT, DIRECT>::MINB)
 conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
-    static_assert(!(TMA && F16), "the TMA producer stages tf32 operands only");
+    constexpr bool TMA = RAW == 1, CPA = RAW == 2;
     using C = Cfg<CP, MT, DIRECT>;
     constexpr int N = C::N, JT = C::JT, RPW = C::RPW;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -221,7 +223,7 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
     uint64_t* raw_empty = raw_full + MAX_RS;       // [rs]      producers -> TMA issuer (raw stage read)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + MAX_RS);
     uint8_t* raw_base = reinterpret_cast<uint8_t*>(bars) + 384;    // TMA variant: [rs][c 8][row SR][x bw] fp32
-    const uint32_t raw_bytes = 32u * (uint32_t)p.bw * (uint32_t)SR;
+    const uint32_t raw_bytes = 32u * (uint32_t)p.bw * (uint32_t)SR;   // p.bw = 32 for the cp.async ring
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int plane = blockIdx.y;
@@ -245,6 +247,8 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
                 mbar_init(&raw_empty[i], NPROD / 32);
             }
         }
+        if constexpr (CPA)
+            for (int i = 0; i < p.rs; ++i) mbar_init(&raw_full[i], NPROD);    // one cp.async arrival per producer thread
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == NPROD / 32) {
@@ -340,6 +344,54 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
                 ++l_phase;
             }
         };
+        // cp.async ring: every thread copies its own (row, lane) x 8 channels of the next unit into the raw stage and
+        // posts one asynchronous arrival; a thread only ever reads back what it copied itself, so a stage needs no
+        // "empty" barrier.  Uses the same cursor / predicates as load_chunk.
+        int c_issue = 0;
+        auto issue_cpa = [&]() {
+            const int slot = c_issue % p.rs;
+            ++c_issue;
+            int pr = 0, pc = 0;
+            bool col_ok = true;
+            const float* src = in_pl + (long long)(l_kc * 8) * p.isC;
+            if (p.kd) {
+                int din;
+                if (p.dtrans) {
+                    const int t2 = d + 1 - l_phase;
+                    din = (t2 >= 0 && (t2 & 1) == 0) ? (t2 >> 1) : -1;
+                } else {
+                    din = d * p.dstride + (l_phase - p.kd / 2) * p.ddil;
+                }
+                col_ok = din >= 0 && din < p.Din;
+                src += (long long)(col_ok ? din : 0) * p.isD;
+            } else {
+                pr = l_phase >> 1;
+                pc = l_phase & 1;
+                src += pr * p.Win + pc;
+                col_ok = !(pc && edge < 0);
+            }
+            const int nvalid = p.Cin - l_kc * 8;
+            float* dst = reinterpret_cast<float*>(raw_base + (size_t)slot * raw_bytes) + lane;
+#pragma unroll
+            for (int u = 0; u < RPW; ++u) {
+                const int r = warp + 8 * u;
+                if (r < SR) {
+                    const float* su = src + off[u];
+                    const bool ok = off[u] >= 0 && col_ok && !(pr && ((edge >> u) & 1));
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const bool okc = ok && c < nvalid;
+                        cp_async4(dst + (c * SR + r) * 32, okc ? su : p.in, okc);
+                        su += p.isC;
+                    }
+                }
+            }
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&raw_full[slot])) : "memory");
+            if (++l_kc == p.cpp) {
+                l_kc = 0;
+                ++l_phase;
+            }
+        };
         constexpr int NACC = DIRECT ? 1 : N;
         float acc[JT][NACC];
 #pragma unroll
@@ -372,7 +424,11 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
             }
         };
 
-        if constexpr (!TMA) load_chunk();
+        if constexpr (CPA) {
+            for (int i = 0; i < p.rs && i < p.nchunk; ++i) issue_cpa();
+        } else if constexpr (!TMA) {
+            load_chunk();
+        }
         int s = 0, gk = 0, gdone = 0;      // stage of chunk k; chunks produced since the last group boundary; groups drained
         uint32_t ph = 0;
         for (int k = 0; k < p.nchunk; ++k) {
@@ -388,32 +444,23 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
             const uint32_t a_hi = smem_u32(st_base);
             const uint32_t khalf = NPOS * 16u;
             const uint32_t a_lo = a_hi + 2u * khalf;
-            if constexpr (TMA) {
+            // the unit's values: registers (v) or the raw fp32 stage (TMA / cp.async ring)
+            const float* raw = nullptr;
+            int rbw = 32;
+            if constexpr (TMA || CPA) {
                 const int rsl = k % p.rs;
                 mbar_wait(&raw_full[rsl], ((uint32_t)(k / p.rs)) & 1u);
-                const float* raw = reinterpret_cast<const float*>(raw_base + (size_t)rsl * raw_bytes) + (((x0 - p.dil) & 3) + lane);
-#pragma unroll
-                for (int u = 0; u < RPW; ++u) {
-                    const int r = warp + 8 * u;
-                    if (r < SR) {
-                        uint32_t hi[8], lo[8];
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) {
-                            const float x = raw[(c * SR + r) * p.bw];
-                            hi[c] = tf32_rna(x);
-                            lo[c] = __float_as_uint(x - __uint_as_float(hi[c]));
-                        }
-                        const uint32_t o = (uint32_t)(r * 32 + lane) * 16u;
-                        sts128(a_hi + o, hi[0], hi[1], hi[2], hi[3]);
-                        sts128(a_hi + khalf + o, hi[4], hi[5], hi[6], hi[7]);
-                        sts128(a_lo + o, lo[0], lo[1], lo[2], lo[3]);
-                        sts128(a_lo + khalf + o, lo[4], lo[5], lo[6], lo[7]);
-                    }
+                raw = reinterpret_cast<const float*>(raw_base + (size_t)rsl * raw_bytes) + lane;
+                if constexpr (TMA) {
+                    raw += (x0 - p.dil) & 3;
+                    rbw = p.bw;
                 }
-                __syncwarp();
-                if (elect_one()) mbar_arrive(&raw_empty[rsl]);      // this warp has read the raw stage
-                __syncwarp();
-            } else if constexpr (F16) {
+            }
+            auto val = [&](int u, int r, int c) -> float {
+                if constexpr (TMA || CPA) return raw[(c * SR + r) * rbw];
+                else return v[u][c];
+            };
+            if constexpr (F16) {
                 const uint32_t ko = (uint32_t)(k & 1) * khalf;         // K half of this unit inside the chunk
 #pragma unroll
                 for (int u = 0; u < RPW; ++u) {
@@ -422,9 +469,10 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
                         uint32_t hi[4], lo[4];
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
-                            hi[c] = pack_h2(v[u][2 * c], v[u][2 * c + 1]);
+                            const float xa = val(u, r, 2 * c), xb = val(u, r, 2 * c + 1);
+                            hi[c] = pack_h2(xa, xb);
                             const float2 hf = unpack_h2(hi[c]);
-                            lo[c] = pack_h2(v[u][2 * c] - hf.x, v[u][2 * c + 1] - hf.y);
+                            lo[c] = pack_h2(xa - hf.x, xb - hf.y);
                         }
                         const uint32_t o = (uint32_t)(r * 32 + lane) * 16u;
                         sts128(a_hi + ko + o, hi[0], hi[1], hi[2], hi[3]);
@@ -435,7 +483,6 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
                         }
                     }
                 }
-                if (k + 1 < p.nchunk) load_chunk();
             } else {
 #pragma unroll
                 for (int u = 0; u < RPW; ++u) {
@@ -444,10 +491,11 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
                         uint32_t hi[8], lo[8];
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
-                            hi[c] = tf32_rna(v[u][c]);
+                            const float x = val(u, r, c);
+                            hi[c] = tf32_rna(x);
                             // exact remainder; the tensor core ignores the 13 low mantissa bits of a tf32 operand,
                             // so not rounding lo costs <= 2^-22 relative
-                            lo[c] = __float_as_uint(v[u][c] - __uint_as_float(hi[c]));
+                            lo[c] = __float_as_uint(x - __uint_as_float(hi[c]));
                         }
                         const uint32_t o = (uint32_t)(r * 32 + lane) * 16u;
                         sts128(a_hi + o, hi[0], hi[1], hi[2], hi[3]);
@@ -456,7 +504,15 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
                         sts128(a_lo + khalf + o, lo[4], lo[5], lo[6], lo[7]);
                     }
                 }
-                if (k + 1 < p.nchunk) load_chunk();    // in flight across the barrier traffic and the drain below
+            }
+            if constexpr (TMA) {
+                __syncwarp();
+                if (elect_one()) mbar_arrive(&raw_empty[k % p.rs]);     // this warp has read the raw stage
+                __syncwarp();
+            } else if constexpr (CPA) {
+                if (c_issue < p.nchunk) issue_cpa();    // refill the stage this thread just read
+            } else {
+                if (k + 1 < p.nchunk) load_chunk();     // in flight across the barrier traffic and the drain below
             }
             if (last_half) {
                 fence_proxy_async();                   // generic-proxy st.shared -> visible to the tensor core
@@ -632,9 +688,9 @@ static bool make_tmap(const Params& p, int SR, CUtensorMap* tm) {
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int CP, int MT, bool DIRECT, bool TMA, bool F16>
+template <int CP, int MT, bool DIRECT, int RAW, bool F16>
 static int launch_one(const Params& p, const CUtensorMap& tm, dim3 grid, size_t smem_bytes, cudaStream_t st, const char* what) {
-    auto kern = conv_tc2_kernel<CP, MT, DIRECT, TMA, F16>;
+    auto kern = conv_tc2_kernel<CP, MT, DIRECT, RAW, F16>;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
@@ -679,7 +735,12 @@ static int launch(Params& p, int CP, int planes, cudaStream_t st, const char* wh
     p.bw = p.dil ? 36 : 32;
     CUtensorMap tm = {};
     const bool tma_ok = !p.half && make_tmap(p, 4 * 2 + 2 * p.dil, &tm);   // eligibility (the box is re-encoded for the chosen tile)
+    // cp.async ring (fp16 split only; opt-in TSTEREO_TC2_CPA=1): loads run `rs` chunks ahead without holding registers.
+    // Measured on B200: no gain on the small hourglass layers (they sit at the fixed launch + prologue + epilogue cost,
+    // ~10 us) and 5-20 % slower on the large ones (one more shared-memory round trip), so it is not the default.
+    const int cpa_env = env_int("TSTEREO_TC2_CPA", 0);
     int best_mt = 0, best_stages = 0, best_rs = 0;
+    bool best_cpa = false;
     double best_cost = 1e30;
     const int forced = env_int("TSTEREO_TC2_MT", 0);
     for (int mt = 2; mt <= 4; mt += 2) {
@@ -690,9 +751,17 @@ static int launch(Params& p, int CP, int planes, cudaStream_t st, const char* wh
         int minb = (direct || jt * N <= 48) ? 2 : 1;
         if (cols > 256) minb = 1;                       // two CTAs need their TMEM columns side by side
         const int SR = 4 * mt + 2 * p.dil;
-        const size_t budget = minb == 2 ? (size_t)112 * 1024 : SMEM_MAX;
+        const long long tiles = (long long)p.tiles_x * ((p.H + 4 * mt - 1) / (4 * mt)) * planes;
+        const bool cpa = p.half && cpa_env == 1;
+        const size_t budget = (minb == 2 && !(cpa && tiles <= 148)) ? (size_t)112 * 1024 : SMEM_MAX;
         int stages = 0, rs = 0;
-        if (tma_ok) {       // operand stages + raw fp32 stages (1/2 the size): prefer depth on the raw side
+        if (cpa) {          // two operand stages + as many raw fp32 stages as fit
+            for (int r = MAX_RS; r >= 2 && !stages; --r)
+                if (smem_need(2, SR, N, r, 32) <= budget) {
+                    stages = 2;
+                    rs = r;
+                }
+        } else if (tma_ok) {       // operand stages + raw fp32 stages (1/2 the size): prefer depth on the raw side
             static const int combos[][2] = {{3, 4}, {3, 3}, {2, 4}, {2, 3}, {3, 2}, {2, 2}};
             for (const auto& c : combos)
                 if (smem_need(c[0], SR, N, c[1], p.bw) <= budget) {
@@ -710,7 +779,6 @@ static int launch(Params& p, int CP, int planes, cudaStream_t st, const char* wh
                 }
         }
         if (!stages) continue;
-        const long long tiles = (long long)p.tiles_x * ((p.H + 4 * mt - 1) / (4 * mt)) * planes;
         const long long waves = (tiles + 148 * minb - 1) / (148 * minb);
         const double cost = (double)waves * minb * (SR + 5.0) * ((stages >= 3 || rs) ? 1.0 : 1.15);
         if (cost < best_cost) {
@@ -718,6 +786,7 @@ static int launch(Params& p, int CP, int planes, cudaStream_t st, const char* wh
             best_mt = mt;
             best_stages = stages;
             best_rs = rs;
+            best_cpa = cpa && rs > 0;
         }
     }
     TS_REQUIRE(best_mt > 0, "%s: no tile configuration for Cout<=%d", what, CP);
@@ -726,22 +795,26 @@ static int launch(Params& p, int CP, int planes, cudaStream_t st, const char* wh
     p.stages = best_stages;
     p.rs = best_rs;
     const int SR = 4 * best_mt + 2 * p.dil;
-    bool tma = best_rs > 0;
+    const bool tma = best_rs > 0 && !best_cpa;
+    if (best_cpa) p.bw = 32;
     if (tma && !make_tmap(p, SR, &tm)) {
         set_error("%s: cuTensorMapEncodeTiled failed", what);
         return TSTEREO_E_CUDA;
     }
-    const size_t smem_bytes = smem_need(p.stages, SR, N, p.rs, p.bw);
+    const size_t smem_bytes = smem_need(p.stages, SR, N, p.rs, p.bw);   // p.bw = 32 for the cp.async ring
     dim3 grid(p.tiles_x * ((p.H + 4 * best_mt - 1) / (4 * best_mt)), planes);
 #define TS_TC2(CC, MM)                                                                                         \
     if (CP == CC && best_mt == MM) {                                                                           \
+        if (p.half && best_cpa)                                                                                \
+            return direct ? launch_one<CC, MM, true, 2, true>(p, tm, grid, smem_bytes, st, what)               \
+                          : launch_one<CC, MM, false, 2, true>(p, tm, grid, smem_bytes, st, what);             \
         if (p.half)                                                                                            \
-            return direct ? launch_one<CC, MM, true, false, true>(p, tm, grid, smem_bytes, st, what)           \
-                          : launch_one<CC, MM, false, false, true>(p, tm, grid, smem_bytes, st, what);         \
-        if (direct) return tma ? launch_one<CC, MM, true, true, false>(p, tm, grid, smem_bytes, st, what)      \
-                               : launch_one<CC, MM, true, false, false>(p, tm, grid, smem_bytes, st, what);    \
-        return tma ? launch_one<CC, MM, false, true, false>(p, tm, grid, smem_bytes, st, what)                 \
-                   : launch_one<CC, MM, false, false, false>(p, tm, grid, smem_bytes, st, what);               \
+            return direct ? launch_one<CC, MM, true, 0, true>(p, tm, grid, smem_bytes, st, what)               \
+                          : launch_one<CC, MM, false, 0, true>(p, tm, grid, smem_bytes, st, what);             \
+        if (direct) return tma ? launch_one<CC, MM, true, 1, false>(p, tm, grid, smem_bytes, st, what)         \
+                               : launch_one<CC, MM, true, 0, false>(p, tm, grid, smem_bytes, st, what);        \
+        return tma ? launch_one<CC, MM, false, 1, false>(p, tm, grid, smem_bytes, st, what)                    \
+                   : launch_one<CC, MM, false, 0, false>(p, tm, grid, smem_bytes, st, what);                   \
     }
     TS_TC2(8, 2) TS_TC2(8, 4) TS_TC2(16, 2) TS_TC2(16, 4) TS_TC2(32, 2)
 #undef TS_TC2

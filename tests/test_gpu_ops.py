@@ -515,6 +515,22 @@ def test_conv_hw3_tc2_tma(ops, monkeypatch, B, Cin, Cout, D, H, W, dil, act):
     close(gotd, wantd, 1e-5, rtol=1e-5, what="conv_d_tc2 (TMA)")
 
 
+def test_conv_tc2_cp_async_ring(ops, monkeypatch):
+    """The cp.async raw-ring producer (opt-in) gives the same results: 3x3 with halo, odd width, (k,1,1) along D."""
+    monkeypatch.setenv("TSTEREO_TC2_CPA", "1")
+    x = rnd(2, 40, 3, 19, 45, seed=91)
+    w = rnd(16, 40, 1, 3, 3, seed=92, scale=0.05)
+    b = rnd(16, seed=93, scale=0.1)
+    want = O._act(F.conv3d(x.double(), w.double(), b.double(), 1, (0, 1, 1)), "SiLU").float()
+    got = ops.conv_hw3_tc2(x.cuda(), ops.pack_conv_hw3_tc2(w.reshape(16, 40, 9).cuda(), True), b.cuda(), 16, 1, "SiLU", half=True)
+    close(got, want, 1e-5, rtol=1e-5, what="conv_hw3_tc2 (cp.async ring)")
+    xd = rnd(1, 64, 6, 17, 30, seed=94)
+    wd = rnd(64, 64, 3, 1, 1, seed=95, scale=0.05)
+    wantd = F.conv3d(xd.double(), wd.double(), None, (2, 1, 1), (1, 0, 0)).float()
+    gotd = ops.conv_d_tc2(xd.cuda(), ops.pack_conv_d_tc2(wd.reshape(64, 64, 3).cuda(), True), None, 64, 3, 2, 1, False, None, half=True)
+    close(gotd, wantd, 1e-5, rtol=1e-5, what="conv_d_tc2 (cp.async ring)")
+
+
 @pytest.mark.parametrize("mt", [2, 4])
 def test_conv_hw3_tc2_tilings(ops, mt, monkeypatch):
     """Both M-tile counts (8- and 16-row tiles) on the same input; ragged right / bottom edges."""
