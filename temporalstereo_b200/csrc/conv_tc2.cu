@@ -81,6 +81,7 @@ struct Params {
     int rs;                       // TMA variant: raw fp32 stages in flight
     int bw;                       // TMA variant: box width in elements (32, or 36 when the halo shifts the 16-byte aligned origin)
     int nbatch;                   // batch size (extent of the TMA view's last dimension)
+    int fold;                     // 3: kx taps folded into N (3x3 forms); 1: single column block ((k,1,1) form)
     int half;                     // operands as fp16 hi + lo (kind::f16, 16 channels per MMA) instead of tf32 hi + lo
     int nky;                      // ky taps of the virtual conv: 3, or 1 for the (k,1,1) convs along D
     int kd, dstride, ddil, Din, dtrans;   // kd > 0: phases are input planes of a conv along D (p.D = Dout)
@@ -130,37 +131,43 @@ __device__ __forceinline__ float act_t(float x) {
 
 // kx shift-sum + bias + activation + store of 8 channels of one tile row (lane = tile column):
 // out[x] = P0[x] + P1[x + dil] + P2[x + 2*dil]
-template <int ACT>
+// FOLD = 3: the kx taps are columns of the accumulator (3x3 convs); FOLD = 1: one column block (the 1x1 / (k,1,1) form)
+template <int ACT, int FOLD>
 __device__ __forceinline__ void epi_store8(const float (&a0)[8], const float (&a1)[8], const float (&a2)[8], int dil, float* o,
                                            int osC, const float* bias, int co0, int Cout, bool ok) {
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-        const float v1 = __shfl_down_sync(0xffffffffu, a1[c], dil);
-        const float v2 = __shfl_down_sync(0xffffffffu, a2[c], 2 * dil);
-        const float r = act_t<ACT>(a0[c] + v1 + v2 + __ldg(bias + c));
+        float acc = a0[c];
+        if constexpr (FOLD == 3) {
+            acc += __shfl_down_sync(0xffffffffu, a1[c], dil);
+            acc += __shfl_down_sync(0xffffffffu, a2[c], 2 * dil);
+        }
+        const float r = act_t<ACT>(acc + __ldg(bias + c));
         if (ok && co0 + c < Cout) o[c * osC] = r;
     }
 }
-template <int ACT, int CP>
+template <int ACT, int CP, int FOLD>
 __device__ __forceinline__ void epi_direct(uint32_t taddr, int dil, float* o, int osC, const float* bias, int Cout, bool ok) {
 #pragma unroll
     for (int c0 = 0; c0 < CP; c0 += 8) {
         uint32_t r0[8], r1[8], r2[8];
         tmem_ld8(taddr + (uint32_t)c0, r0);
-        tmem_ld8(taddr + (uint32_t)(CP + c0), r1);
-        tmem_ld8(taddr + (uint32_t)(2 * CP + c0), r2);
+        if constexpr (FOLD == 3) {
+            tmem_ld8(taddr + (uint32_t)(CP + c0), r1);
+            tmem_ld8(taddr + (uint32_t)(2 * CP + c0), r2);
+        }
         tmem_ld_wait();
         float a0[8], a1[8], a2[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             a0[c] = __uint_as_float(r0[c]);
-            a1[c] = __uint_as_float(r1[c]);
-            a2[c] = __uint_as_float(r2[c]);
+            a1[c] = FOLD == 3 ? __uint_as_float(r1[c]) : 0.f;
+            a2[c] = FOLD == 3 ? __uint_as_float(r2[c]) : 0.f;
         }
-        epi_store8<ACT>(a0, a1, a2, dil, o + (long long)c0 * osC, osC, bias + c0, c0, Cout, ok);
+        epi_store8<ACT, FOLD>(a0, a1, a2, dil, o + (long long)c0 * osC, osC, bias + c0, c0, Cout, ok);
     }
 }
-template <int ACT, int CP>
+template <int ACT, int CP, int FOLD>
 __device__ __forceinline__ void epi_acc(const float* acc, int dil, float* o, int osC, const float* bias, int Cout, bool ok) {
 #pragma unroll
     for (int c0 = 0; c0 < CP; c0 += 8) {
@@ -168,16 +175,16 @@ __device__ __forceinline__ void epi_acc(const float* acc, int dil, float* o, int
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             a0[c] = acc[c0 + c];
-            a1[c] = acc[CP + c0 + c];
-            a2[c] = acc[2 * CP + c0 + c];
+            a1[c] = FOLD == 3 ? acc[(FOLD == 3 ? CP : 0) + c0 + c] : 0.f;
+            a2[c] = FOLD == 3 ? acc[(FOLD == 3 ? 2 * CP : 0) + c0 + c] : 0.f;
         }
-        epi_store8<ACT>(a0, a1, a2, dil, o + (long long)c0 * osC, osC, bias + c0, c0, Cout, ok);
+        epi_store8<ACT, FOLD>(a0, a1, a2, dil, o + (long long)c0 * osC, osC, bias + c0, c0, Cout, ok);
     }
 }
 
-template <int CP, int MT, bool DIRECT>
+template <int CP, int MT, bool DIRECT, int FOLD = 3>
 struct Cfg {
-    static constexpr int N = 3 * CP;                   // columns of one part block: [kx][co]
+    static constexpr int N = FOLD * CP;                // columns of one part block: [kx][co]
     static constexpr int N2 = (N + 15) / 16 * 16;      // width of an N-wide MMA (M = 128 needs N % 16 == 0)
     static constexpr int TS = DIRECT ? N2 : 2 * N;     // TMEM columns of one M-tile: ACC [A*B_hi (N) | A_hi*B_lo (N)]
     static constexpr int COLS = MT * TS;
@@ -202,11 +209,11 @@ constexpr int MAX_RS = 8;
 
 // RAW: 0 = chunks are prefetched into registers; 1 = TMA boxes into a raw fp32 ring; 2 = per-thread cp.async (zero-fill)
 // into the same ring, `rs` chunks deep — for the small, latency-bound layers (any width / alignment)
-template <int CP, int MT, bool DIRECT, int RAW, bool F16>
-__global__ void __launch_bounds__(NTHREADS, Cfg<CP, MT, DIRECT>::MINB)
+template <int CP, int MT, bool DIRECT, int RAW, bool F16, int FOLD>
+__global__ void __launch_bounds__(NTHREADS, Cfg<CP, MT, DIRECT, FOLD>::MINB)
 conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
     constexpr bool TMA = RAW == 1, CPA = RAW == 2;
-    using C = Cfg<CP, MT, DIRECT>;
+    using C = Cfg<CP, MT, DIRECT, FOLD>;
     constexpr int N = C::N, JT = C::JT, RPW = C::RPW;
     extern __shared__ __align__(128) uint8_t smem[];
     const int SR = 4 * MT + 2 * p.dil;                 // staged rows
@@ -550,13 +557,13 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
                     mbar_wait(&acc_full[j], 0u);
                     tc_fence_after();
                     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(j * C::TS);
-                    if (p.act == TSTEREO_ACT_SILU) epi_direct<TSTEREO_ACT_SILU, CP>(taddr, p.dil, o, p.osC, p.bias, p.Cout, ok);
-                    else if (p.act == TSTEREO_ACT_RELU) epi_direct<TSTEREO_ACT_RELU, CP>(taddr, p.dil, o, p.osC, p.bias, p.Cout, ok);
-                    else epi_direct<TSTEREO_ACT_NONE, CP>(taddr, p.dil, o, p.osC, p.bias, p.Cout, ok);
+                    if (p.act == TSTEREO_ACT_SILU) epi_direct<TSTEREO_ACT_SILU, CP, FOLD>(taddr, p.dil, o, p.osC, p.bias, p.Cout, ok);
+                    else if (p.act == TSTEREO_ACT_RELU) epi_direct<TSTEREO_ACT_RELU, CP, FOLD>(taddr, p.dil, o, p.osC, p.bias, p.Cout, ok);
+                    else epi_direct<TSTEREO_ACT_NONE, CP, FOLD>(taddr, p.dil, o, p.osC, p.bias, p.Cout, ok);
                 } else {
-                    if (p.act == TSTEREO_ACT_SILU) epi_acc<TSTEREO_ACT_SILU, CP>(acc[jj], p.dil, o, p.osC, p.bias, p.Cout, ok);
-                    else if (p.act == TSTEREO_ACT_RELU) epi_acc<TSTEREO_ACT_RELU, CP>(acc[jj], p.dil, o, p.osC, p.bias, p.Cout, ok);
-                    else epi_acc<TSTEREO_ACT_NONE, CP>(acc[jj], p.dil, o, p.osC, p.bias, p.Cout, ok);
+                    if (p.act == TSTEREO_ACT_SILU) epi_acc<TSTEREO_ACT_SILU, CP, FOLD>(acc[jj], p.dil, o, p.osC, p.bias, p.Cout, ok);
+                    else if (p.act == TSTEREO_ACT_RELU) epi_acc<TSTEREO_ACT_RELU, CP, FOLD>(acc[jj], p.dil, o, p.osC, p.bias, p.Cout, ok);
+                    else epi_acc<TSTEREO_ACT_NONE, CP, FOLD>(acc[jj], p.dil, o, p.osC, p.bias, p.Cout, ok);
                 }
             }
         }
@@ -688,9 +695,9 @@ static bool make_tmap(const Params& p, int SR, CUtensorMap* tm) {
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int CP, int MT, bool DIRECT, int RAW, bool F16>
+template <int CP, int MT, bool DIRECT, int RAW, bool F16, int FOLD = 3>
 static int launch_one(const Params& p, const CUtensorMap& tm, dim3 grid, size_t smem_bytes, cudaStream_t st, const char* what) {
-    auto kern = conv_tc2_kernel<CP, MT, DIRECT, RAW, F16>;
+    auto kern = conv_tc2_kernel<CP, MT, DIRECT, RAW, F16, FOLD>;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
@@ -721,7 +728,8 @@ static int env_int(const char* name, int dflt) {
 }
 
 static int launch(Params& p, int CP, int planes, cudaStream_t st, const char* what) {
-    const int N = 3 * CP, N2 = (N + 15) / 16 * 16;
+    const int fold = p.fold == 1 ? 1 : 3;
+    const int N = fold * CP, N2 = (N + 15) / 16 * 16;
     const int VW = 32 - 2 * p.dil;
     p.tiles_x = (p.W + VW - 1) / VW;
     const int g_env = env_int("TSTEREO_TC2_G", 0);      // experiments: chunks per accumulation group (per input phase)
@@ -745,14 +753,14 @@ static int launch(Params& p, int CP, int planes, cudaStream_t st, const char* wh
     const int forced = env_int("TSTEREO_TC2_MT", 0);
     for (int mt = 2; mt <= 4; mt += 2) {
         const int cols = mt * (direct ? N2 : 2 * N);
-        if (cols > 512 || (CP == 32 && mt == 4)) continue;   // no (32, 4) instance
+        if (cols > 512 || (CP == 32 && mt == 4 && fold == 3)) continue;   // no (32, 4) instance of the kx-folded form
         if (forced && mt != forced) continue;
         const int jt = (mt + 1) / 2;
         int minb = (direct || jt * N <= 48) ? 2 : 1;
         if (cols > 256) minb = 1;                       // two CTAs need their TMEM columns side by side
         const int SR = 4 * mt + 2 * p.dil;
         const long long tiles = (long long)p.tiles_x * ((p.H + 4 * mt - 1) / (4 * mt)) * planes;
-        const bool cpa = p.half && cpa_env == 1;
+        const bool cpa = p.half && cpa_env == 1 && fold == 3;
         const size_t budget = (minb == 2 && !(cpa && tiles <= 148)) ? (size_t)112 * 1024 : SMEM_MAX;
         int stages = 0, rs = 0;
         if (cpa) {          // two operand stages + as many raw fp32 stages as fit
@@ -803,6 +811,13 @@ static int launch(Params& p, int CP, int planes, cudaStream_t st, const char* wh
     }
     const size_t smem_bytes = smem_need(p.stages, SR, N, p.rs, p.bw);   // p.bw = 32 for the cp.async ring
     dim3 grid(p.tiles_x * ((p.H + 4 * best_mt - 1) / (4 * best_mt)), planes);
+#define TS_TC2F1(CC, MM)                                                                                       \
+    if (fold == 1 && p.half && !best_cpa && CP == CC && best_mt == MM)                                         \
+        return direct ? launch_one<CC, MM, true, 0, true, 1>(p, tm, grid, smem_bytes, st, what)                \
+                      : launch_one<CC, MM, false, 0, true, 1>(p, tm, grid, smem_bytes, st, what);
+    TS_TC2F1(8, 2) TS_TC2F1(8, 4) TS_TC2F1(16, 2) TS_TC2F1(16, 4) TS_TC2F1(32, 2) TS_TC2F1(32, 4)
+#undef TS_TC2F1
+    TS_REQUIRE(fold == 3, "%s: the single-column form needs the fp16 split and the register producer", what);
 #define TS_TC2(CC, MM)                                                                                         \
     if (CP == CC && best_mt == MM) {                                                                           \
         if (p.half && best_cpa)                                                                                \
@@ -831,12 +846,14 @@ namespace {
 int tc2_cp(int Cout) { return Cout <= 8 ? 8 : Cout <= 16 ? 16 : 32; }
 
 // floats of the operand image of ONE output-channel group (<= 32 channels) over `nchunk` 8-channel chunks
-long long group_floats(int nchunk, int cout_g, int nky = 3) { return (long long)nchunk * nky * 2 * 2 * (3 * tc2_cp(cout_g)) * 4; }
+long long group_floats(int nchunk, int cout_g, int nky = 3, int fold = 3) {
+    return (long long)nchunk * nky * 2 * 2 * (fold * tc2_cp(cout_g)) * 4;
+}
 
 // total over the groups of 32 output channels
-long long wpack_floats(int nchunk, int Cout, int nky = 3) {
+long long wpack_floats(int nchunk, int Cout, int nky = 3, int fold = 3) {
     long long n = 0;
-    for (int c0 = 0; c0 < Cout; c0 += 32) n += group_floats(nchunk, Cout - c0 < 32 ? Cout - c0 : 32, nky);
+    for (int c0 = 0; c0 < Cout; c0 += 32) n += group_floats(nchunk, Cout - c0 < 32 ? Cout - c0 : 32, nky, fold);
     return n;
 }
 
@@ -854,7 +871,7 @@ int run_groups(tc2::Params p, int Cout, int planes, cudaStream_t st, const char*
         p.out = out + (long long)c0 * p.osC;
         const int rc = tc2::launch(p, tc2_cp(cg), planes, st, what);
         if (rc != TSTEREO_OK) return rc;
-        wp += group_floats(p.half ? (p.nchunk + 1) / 2 : p.nchunk, cg, p.nky);
+        wp += group_floats(p.half ? (p.nchunk + 1) / 2 : p.nchunk, cg, p.nky, p.fold == 1 ? 1 : 3);
     }
     return TSTEREO_OK;
 }
@@ -950,7 +967,10 @@ int tstereo_deconv_hw_tc2(const float* in, long long isB, long long isC, long lo
     return TSTEREO_OK;
 }
 
-long long tstereo_conv_d_tc2_wpack_floats(int Cin, int Cout, int k, int half) { return wpack_floats(mma_chunks(k * ((Cin + 7) / 8), half), Cout, 1); }
+// the fp16 form of the (k,1,1) conv uses the single-column accumulator (N = CP); the tf32 form keeps N = 3*CP
+long long tstereo_conv_d_tc2_wpack_floats(int Cin, int Cout, int k, int half) {
+    return wpack_floats(mma_chunks(k * ((Cin + 7) / 8), half), Cout, 1, half ? 1 : 3);
+}
 
 int tstereo_conv_d_tc2(const float* in, long long isB, long long isC, long long isD,
                        float* out, long long osB, long long osC, long long osD,
@@ -976,7 +996,7 @@ int tstereo_conv_d_tc2(const float* in, long long isB, long long isC, long long 
     p.wpack = wpack; p.bias = bias;
     p.Cin = Cin; p.H = H; p.W = W; p.D = Dout; p.Hin = H; p.Win = W;
     p.isY = W; p.isX = 1; p.osY = W; p.osX = 1;
-    p.dil = 0; p.act = act; p.nky = 1; p.half = half != 0;
+    p.dil = 0; p.act = act; p.nky = 1; p.half = half != 0; p.fold = half ? 1 : 3;
     p.kd = k; p.dstride = stride; p.ddil = dilation; p.Din = Din; p.dtrans = transposed;
     p.cpp = (Cin + 7) / 8;
     p.nchunk = k * p.cpp;

@@ -148,37 +148,39 @@ def conv_hw3_tc(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Tenso
     return out
 
 
-def _pack_tc2_group(w: torch.Tensor, nky: int = 3, half: bool = False) -> torch.Tensor:
-    """One output-channel group (<= 32): [Cout, Cin, nky*3] -> [chunk][ky nky][khalf 2][row 2N][16 B],
-    row = part*N + kx*CP + co, N = 3*CP, CP = 8|16|32.  tf32 form: chunk = 8 channels, a 16-byte row holds 4 floats,
+def _pack_tc2_group(w: torch.Tensor, nky: int = 3, half: bool = False, fold: int = 3) -> torch.Tensor:
+    """One output-channel group (<= 32): [Cout, Cin, nky*fold] -> [chunk][ky nky][khalf 2][row 2N][16 B],
+    row = part*N + kx*CP + co, N = fold*CP (fold = 3 kx taps, or 1), CP = 8|16|32.  tf32 form: chunk = 8 channels, a 16-byte row holds 4 floats,
     parts = tf32 hi / lo.  half form: chunk = 16 channels, a row holds 8 halves, parts = fp16 hi / lo (returned
     reinterpreted as float32 pairs so the ABI keeps one pointer type)."""
     cout, cin, T = w.shape
-    assert T == 3 * nky and cout <= 32
+    assert T == fold * nky and cout <= 32
     CP = 8 if cout <= 8 else 16 if cout <= 16 else 32
     per = 16 if half else 8
     nch = (cin + per - 1) // per
-    full = torch.zeros((CP, nch * per, nky, 3), device=w.device, dtype=torch.float32)
-    full[:cout, :cin] = w.reshape(cout, cin, nky, 3)
+    full = torch.zeros((CP, nch * per, nky, fold), device=w.device, dtype=torch.float32)
+    full[:cout, :cin] = w.reshape(cout, cin, nky, fold)
     if half:
         hi = full.half()
         lo = (full - hi.float()).half()
-        parts = torch.stack([hi, lo]).view(2, CP, nch, 2, 8, nky, 3)      # [part, co, chunk, khalf, i, ky, kx]
+        parts = torch.stack([hi, lo]).view(2, CP, nch, 2, 8, nky, fold)   # [part, co, chunk, khalf, i, ky, kx]
         return parts.permute(2, 5, 3, 0, 6, 1, 4).contiguous().view(-1).view(torch.float32)
     hi, lo = tf32_split(full)
-    parts = torch.stack([hi, lo]).view(2, CP, nch, 2, 4, nky, 3)          # [part, co, chunk, khalf, i, ky, kx]
+    parts = torch.stack([hi, lo]).view(2, CP, nch, 2, 4, nky, fold)       # [part, co, chunk, khalf, i, ky, kx]
     return parts.permute(2, 5, 3, 0, 6, 1, 4).contiguous().view(-1)       # [chunk, ky, khalf, part, kx, co, i]
 
 
 def pack_conv_d_tc2(w: torch.Tensor, half: bool = False) -> torch.Tensor:
     """(k,1,1) conv along D, w [Cout, Cin, k] -> operand image of tstereo_conv_d_tc2: the k input planes are stacked
-    on the channel axis (virtual channel = tap*Cin8 + c) of a 1x1 conv (one ky tap, weights in the kx = 0 block)."""
+    on the channel axis (virtual channel = tap*Cin8 + c) of a 1x1 conv (one ky tap).  fp16 form: single column block
+    (N = CP); tf32 form: the kx-folded layout with the weights in the kx = 0 block."""
     cout, cin, k = w.shape
     cin8 = (cin + 7) // 8 * 8
-    virt = torch.zeros((cout, k, cin8, 1, 3), device=w.device, dtype=torch.float32)
+    fold = 1 if half else 3
+    virt = torch.zeros((cout, k, cin8, 1, fold), device=w.device, dtype=torch.float32)
     virt[:, :, :cin, 0, 0] = w.permute(0, 2, 1)
-    virt = virt.reshape(cout, k * cin8, 3)
-    return torch.cat([_pack_tc2_group(virt[c0:c0 + 32], 1, half) for c0 in range(0, cout, 32)])
+    virt = virt.reshape(cout, k * cin8, fold)
+    return torch.cat([_pack_tc2_group(virt[c0:c0 + 32], 1, half, fold) for c0 in range(0, cout, 32)])
 
 
 def pack_conv_hw3_tc2(w: torch.Tensor, half: bool = False) -> torch.Tensor:
