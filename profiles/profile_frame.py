@@ -36,7 +36,7 @@ def frame(prev):
 
 
 prev = {}
-for _ in range(2):
+for _ in range(5 if a.temporal else 2):   # temporal: the local map grows to 3 planes over the first frames (new layer shapes)
     prev = frame(prev)
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStart()
