@@ -189,9 +189,11 @@ def pack_conv_hw3_tc2(w: torch.Tensor, half: bool = False) -> torch.Tensor:
     return torch.cat([_pack_tc2_group(w[c0:c0 + 32], 3, half) for c0 in range(0, w.shape[0], 32)])
 
 
-def pack_conv_hw3s2_tc2(w: torch.Tensor, half: bool = False) -> torch.Tensor:
-    """Stride-2 3x3 conv (padding 1) as a stride-1 3x3 conv over the four input parity phases stacked on the
-    channel axis (tstereo_conv_hw3s2_tc2): tap k reads input 2*o + k - 1 = phase (k+1)%2 at o + {-1, 0, 0}[k]."""
+def virtual_weights_s2(w: torch.Tensor) -> torch.Tensor:
+    """Stride-2 3x3 conv (padding 1), w [Cout, Cin, 9] -> the weights [Cout, 4*Cin8, 3, 3] of the equivalent stride-1
+    3x3 conv (padding 1) over the four input parity phases stacked on the channel axis (virtual channel =
+    (row parity*2 + col parity)*Cin8 + c, phase image P[pr][pc](m, n) = x(2m + pr, 2n + pc)):
+    tap k reads input 2*o + k - 1 = phase (k+1)%2 at o + {-1, 0, 0}[k]."""
     cout, cin, T = w.shape
     assert T == 9
     cin8 = (cin + 7) // 8 * 8
@@ -201,26 +203,37 @@ def pack_conv_hw3s2_tc2(w: torch.Tensor, half: bool = False) -> torch.Tensor:
     for ky, (pr, dm) in tap.items():
         for kx, (pc, dn) in tap.items():
             virt[:, pr * 2 + pc, :cin, dm + 1, dn + 1] = w4[:, :, ky, kx]
-    return pack_conv_hw3_tc2(virt.reshape(cout, 4 * cin8, 9), half)
+    return virt.reshape(cout, 4 * cin8, 3, 3)
 
 
-def pack_deconv_hw_tc2(w: torch.Tensor, k: int, half: bool = False) -> torch.Tensor:
+def pack_conv_hw3s2_tc2(w: torch.Tensor, half: bool = False) -> torch.Tensor:
+    """Operand image of tstereo_conv_hw3s2_tc2 (see virtual_weights_s2)."""
+    v = virtual_weights_s2(w)
+    return pack_conv_hw3_tc2(v.reshape(v.shape[0], v.shape[1], 9), half)
+
+
+def virtual_weights_deconv(w: torch.Tensor, k: int) -> torch.Tensor:
     """Transposed conv (stride 2, padding 1; k=3 with output_padding 1, or k=4), w [Cout, Cin, k*k] in the
-    transposed-conv tap order (out[2i - 1 + t] += in[i] * w[t]) -> four 3x3 shift kernels, one per output parity
-    phase (tstereo_deconv_hw_tc2): out[2m + p] = sum_d in[m + d] * w[t(p, d)]."""
+    transposed-conv tap order (out[2i - 1 + t] += in[i] * w[t]) -> [4 (py*2+px), Cout, Cin, 3, 3]: the 3x3 shift
+    kernel (stride-1 conv, padding 1) of each output parity phase: out[2m + p] = sum_d in[m + d] * w[t(p, d)]."""
     cout, cin, T = w.shape
     assert T == k * k and k in (3, 4)
     w4 = w.reshape(cout, cin, k, k)
     shifts = ({0: {0: 1}, 1: {1: 0, 0: 2}} if k == 3 else {0: {0: 1, -1: 3}, 1: {1: 0, 0: 2}})   # parity -> {shift: tap}
-    packs = []
+    out = torch.zeros((4, cout, cin, 3, 3), device=w.device, dtype=torch.float32)
     for py in (0, 1):
         for px in (0, 1):
-            ph = torch.zeros((cout, cin, 3, 3), device=w.device, dtype=torch.float32)
             for dy, ky in shifts[py].items():
                 for dx, kx in shifts[px].items():
-                    ph[:, :, dy + 1, dx + 1] = w4[:, :, ky, kx]
-            packs.append(pack_conv_hw3_tc2(ph.reshape(cout, cin, 9), half))
-    return torch.cat(packs)
+                    out[py * 2 + px, :, :, dy + 1, dx + 1] = w4[:, :, ky, kx]
+    return out
+
+
+def pack_deconv_hw_tc2(w: torch.Tensor, k: int, half: bool = False) -> torch.Tensor:
+    """Operand image of tstereo_deconv_hw_tc2: the four phase kernels of virtual_weights_deconv, packed one after
+    the other."""
+    v = virtual_weights_deconv(w, k)
+    return torch.cat([pack_conv_hw3_tc2(v[ph].reshape(v.shape[1], v.shape[2], 9), half) for ph in range(4)])
 
 
 def conv_hw3_tc2(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Tensor], cout: int, dilation: int = 1,

@@ -1,6 +1,6 @@
 """Diagnostic: two-frame sequence, engine vs oracle, same-state and carried-state."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from oracle import oracle as O
 from temporalstereo_b200 import synth, temporal

@@ -1,7 +1,7 @@
 """CPU probe: how many operand mantissa bits do the conv contractions need for EPE < 1e-3 px?
 Rounds conv inputs and weights to `bits` explicit mantissa bits (fp32 accumulate) inside the oracle."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch, torch.nn.functional as F
 from oracle import oracle as O
 from temporalstereo_b200 import synth
