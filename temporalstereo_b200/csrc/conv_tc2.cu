@@ -100,10 +100,11 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint
 }
 // instruction descriptor: D fp32, A/B fp16, both K-major, M = 128, N = n
 __host__ __device__ constexpr uint32_t idesc_f16(uint32_t n) { return (1u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24); }
-// two floats -> packed fp16x2 (low half = a)
+// two floats -> packed fp16x2 (low half = a).  satfinite: a value beyond the fp16 range clamps to +-65504 (and its
+// lo part likewise) instead of turning the whole accumulation into inf - inf = NaN
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     uint32_t r;
-    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
     return r;
 }
 __device__ __forceinline__ float2 unpack_h2(uint32_t h) {

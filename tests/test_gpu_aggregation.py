@@ -163,6 +163,21 @@ def test_sequence_vs_oracle(engine):
     assert d.median() < 1e-3 and frac < 0.2, (d.median().item(), frac)
 
 
+def test_tf32_split_engine_vs_oracle():
+    """The tf32 hi+lo operand split (half_split = False, no fp16 range limit) through the whole engine."""
+    from temporalstereo_b200.aggregation import TEMPORALSTEREO
+    sd = synth.synthetic_state_dict(seed=0)
+    eng = TEMPORALSTEREO()
+    eng.half_split = False
+    eng.load_state_dict(sd, strict=True)
+    eng = eng.cuda().eval()
+    lf, rf, li, ri = synth.synthetic_frame(96, 160, B=2, seed=4)
+    with torch.no_grad():
+        want = O.aggregation_forward(sd, lf, rf, li, ri, {})
+    out = eng(_cuda(lf), _cuda(rf), li.cuda(), ri.cuda(), {})
+    _check(out, want[:4], "oracle single 96x160 B=2, tf32 split")
+
+
 @pytest.mark.parametrize("num_sample,H,W,B", [(20, 96, 352, 2), (16, 96, 288, 1)])
 def test_other_disparity_ranges_temporal(num_sample, H, W, B):
     """BASELINE configs C4 (D=320 -> 20 coarse candidates) and C5 (D=256 -> 16) at reduced resolution, temporal

@@ -515,6 +515,18 @@ def test_conv_hw3_tc2_tma(ops, monkeypatch, B, Cin, Cout, D, H, W, dil, act):
     close(gotd, wantd, 1e-5, rtol=1e-5, what="conv_d_tc2 (TMA)")
 
 
+def test_conv_hw3_tc2_fp16_saturates_instead_of_nan(ops):
+    """fp16 split: an activation beyond 65504 clamps (cvt.satfinite) — finite output; the tf32 split has no limit."""
+    x = rnd(1, 8, 1, 8, 32, seed=96)
+    x[0, 3, 0, 4, 7] = 3.0e5
+    w = rnd(8, 8, 1, 3, 3, seed=97, scale=0.1)
+    want = F.conv3d(x.double(), w.double(), None, 1, (0, 1, 1)).float()
+    got_h = ops.conv_hw3_tc2(x.cuda(), ops.pack_conv_hw3_tc2(w.reshape(8, 8, 9).cuda(), True), None, 8, 1, None, half=True)
+    assert torch.isfinite(got_h).all()
+    got_t = ops.conv_hw3_tc2(x.cuda(), ops.pack_conv_hw3_tc2(w.reshape(8, 8, 9).cuda(), False), None, 8, 1, None, half=False)
+    close(got_t, want, 1e-5, rtol=1e-5, what="tf32 split with a 3e5 activation")
+
+
 def test_conv_tc2_cp_async_ring(ops, monkeypatch):
     """The cp.async raw-ring producer (opt-in) gives the same results: 3x3 with halo, odd width, (k,1,1) along D."""
     monkeypatch.setenv("TSTEREO_TC2_CPA", "1")
