@@ -47,7 +47,6 @@ def parse():
     ap.add_argument("--batch", type=int, default=8, help="frames per GPU per step (SURVEY.md §8d: C2 at B=8)")
     ap.add_argument("--height", type=int, default=544)
     ap.add_argument("--width", type=int, default=960)
-    ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     return ap.parse_args()
