@@ -88,11 +88,12 @@ class TEMPORALSTEREO(nn.Module):
         self.weight_init()
         self._pk: Optional[Dict[str, _Packed]] = None
         self._const: Dict[tuple, torch.Tensor] = {}
-        # stride-1 3x3 contractions on tcgen05 with error-compensated 3xTF32 operands (fp32-equivalent);
-        # False keeps every contraction on the fp32 FMA pipe
+        # every contraction (3x3 stride 1 / 2, (k,1,1) along D, stride-2 transposed) on tcgen05 with hi+lo split operands
+        # (fp32-equivalent results); False keeps them all on the fp32 FMA pipe
         self.tensor_cores = True
         # per-(layer shape) choice between the tensor-core and the fp32-FMA kernel: "auto" times both on the
-        # first call of a shape (outside CUDA-graph capture) and keeps the faster; "tc" / "simt" force one
+        # first call of a shape (outside CUDA-graph capture) and keeps the faster; "tc2" / "simt" force one
+        # (or a dict per operator kind: "hw3", "hw3s2", "d", "dc")
         self.plan_mode = "auto"
         self._plan: Dict[tuple, str] = {}
         # tensor-core operand split: fp16 hi + lo (kind::f16, 16 channels per MMA; activations < 65504) or tf32 hi + lo
@@ -255,7 +256,7 @@ class TEMPORALSTEREO(nn.Module):
     # ------------------------------------------------------------------ building blocks
     def _pick(self, key, cands):
         """Plan cache (per-shape plan cache): which kernel runs this layer shape.
-        `cands` maps a kernel name ("tc2", "tc", "simt") to a thunk; plan_mode "auto" times each on the first
+        `cands` maps a kernel name ("tc2", "simt") to a thunk; plan_mode "auto" times each on the first
         call of a shape (outside CUDA-graph capture) and keeps the fastest; any other plan_mode forces that
         kernel where it exists."""
         names = list(cands)

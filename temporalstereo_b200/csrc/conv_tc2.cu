@@ -13,7 +13,7 @@
 //         P[pos][kx][co] (+)= A[pos + ky*dil*32][ch] * W[ky][kx][ch][co]
 //     (N = 3*CP), and the output is  out[x] = P[x][kx=0] + P[x+dil][kx=1] + P[x+2*dil][kx=2]  — two warp
 //     shuffles per channel in the epilogue.  A is read 6 times per chunk instead of 18;
-//   * 3xTF32 error compensation as before: D[0:2N) += A_hi*[B_hi|B_lo],  D[0:N) += A_lo*B_hi;
+//   * error compensation as before (operands split hi + lo): D[0:2N) += A_hi*[B_hi|B_lo],  D[0:N) += A_lo*B_hi;
 //   * the tensor core's accumulate truncates, so TMEM accumulates only G chunks (3*8*G products
 //     per term) before the producer warps add the partial sums into fp32 registers; the MMA warp moves on to
 //     the next M-tile meanwhile (per-M-tile full/empty barriers instead of a second TMEM buffer);
@@ -32,21 +32,23 @@
 //     the host repacks the weights accordingly (taps that do not exist for a phase are zero).
 //   * (k,1,1) convolutions along D use the same machinery with the k input planes as "phases" (chunk k -> plane
 //     dout*stride + (k/cpp - k_d/2)*dil, zero when outside), one ky tap (nky = 1) and no halo (dil = 0).
-//   * TMA producer variant (template flag; opt-in with TSTEREO_TC2_TMA=1, for inputs whose rows are 16-byte aligned
-//     and x-dense: every stride-1 and (k,1,1) layer of the model at 1/16 scale and above): one elected lane issues `cp.async.bulk.tensor.5d` per chunk — an
-//     (x 32, y TR+2*dil, c 8) box of the NCDHW input, out-of-image rows / columns / planes / channels zero-filled by
-//     the TMA unit — into a ring of raw fp32 stages; the 8 producer warps then only read it (conflict-free LDS),
-//     split to tf32 hi/lo and store the K-major operand.  No per-element address arithmetic, predication or
-//     register prefetch; the loads run `rs` chunks ahead.  The register path (below) remains for phase-decomposed
-//     (stride-2) inputs and unaligned widths.
+//   * producer modes (template RAW): 0 = the register path above (default: fastest on B200); 1 = TMA (opt-in
+//     TSTEREO_TC2_TMA=1, tf32 split, inputs whose rows are 16-byte aligned and x-dense): one elected lane of the MMA
+//     warp issues `cp.async.bulk.tensor.5d` per chunk — an (x 32|36, y TR+2*dil, plane 1, c 8) box of the NCDHW input
+//     whose origin is rounded down to a multiple of 4 pixels, out-of-image rows / columns / planes / channels
+//     zero-filled by the TMA unit — into a ring of raw fp32 stages which the 8 producer warps read (conflict-free
+//     LDS), split and store as the K-major operand; 2 = the same ring filled by per-thread `cp.async` (opt-in
+//     TSTEREO_TC2_CPA=1, fp16 split, any width).  DESIGN.md §5 has the measurements (both are slower than mode 0).
 //   * F16 variant (template flag, the engine's default): operands split as fp16 hi + fp16 lo (22 mantissa bits,
 //     same three product terms) and multiplied with `kind::f16`: K = 16 channels per MMA instead of 8, i.e. half the
 //     MMAs and half the shared-memory operand traffic per channel (the kernel is shared-memory-pipe bound) at twice
 //     the tensor rate.  Measured EPE vs fp32 on the oracle: 8.0e-6 px (3xTF32: 8.6e-6).  fp16 range: activations
 //     must stay below 65504 in magnitude (the model's are O(1..100)).
 //
-//  warps 0-7 : producers (global NCDHW fp32 -> hi/lo tf32 -> K-major SWIZZLE_NONE smem) + accumulator readers
-//              + epilogue;  warp 8 : TMEM alloc, MMA issue (one elected lane), commits.
+//   * FOLD = 1 (fp16 form of the (k,1,1) convs): a single accumulator column block, N = CP, no shuffles in the epilogue.
+//
+//  warps 0-7 : producers (global NCDHW fp32 -> hi/lo split -> K-major SWIZZLE_NONE smem) + accumulator readers
+//              + epilogue;  warp 8 : TMEM alloc, MMA issue (elect.sync), commits (and the TMA issue in RAW = 1).
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include <cuda.h>
