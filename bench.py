@@ -321,7 +321,7 @@ def main():
     pk_first = eng._pk["precise.init3d.0.conv.0"]
     vols = [torch.randn(B, 304, 5, H // 4, W // 4, device=dev) for _ in range(2)]
     out8 = torch.empty(B, 8, 5, H // 4, W // 4, device=dev)
-    ms_conv = timed(lambda i: ops.conv_hw3_tc2(vols[i % 2], pk_first.wtc2, pk_first.b, 8, 1, "SiLU", out=out8, half=eng.half_split), reps)
+    ms_conv = timed(lambda i: ops.conv_hw3_tc2(vols[i % 2], pk_first.tc["hw3"], pk_first.b, 8, 1, "SiLU", out=out8, half=eng.half_split), reps)
     b_conv = 4 * B * (304 + 8) * 5 * (H // 4) * (W // 4)
     del vols
 

@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define TSTEREO_VERSION 100            /* 0.1.0 */
+#define TSTEREO_VERSION 200            /* 0.2.0 */
 
 #define TSTEREO_OK            0
 #define TSTEREO_E_ARG        -1        /* bad size / null pointer / unsupported variant */
@@ -53,6 +53,33 @@ int tstereo_block_cost_shift(const float* left, const float* right, float* out, 
 int tstereo_block_cost_warp(const float* left, const float* right, const float* samples, float* out,
                             float* scratch, int B, int C, int H, int W, int S, void* stream);
 
+/* ---------------------------------------------------------------- fused cost volume -> first conv (a1-a3 + a5)
+ * ref: block_cost.py:34-58, 64-81 feeding the (1,3,3) half of init3d[0] (module.py:111-147) through coarse.py:82-83,
+ *      fine.py:102-103, precise.py:88-90.  The raw cost volume is never written (SURVEY.md section 8d "fused path").
+ *
+ * tstereo_group_cost_*: only the three group-wise terms, gvol [B, 3C/8, D, H, W] = [g0, g1, g2]
+ * (scratch as for tstereo_block_cost_*). */
+int tstereo_group_cost_shift(const float* left, const float* right, float* gvol, float* scratch,
+                             int B, int C, int H, int W, int D, void* stream);
+int tstereo_group_cost_warp(const float* left, const float* right, const float* samples, float* gvol,
+                            float* scratch, int B, int C, int H, int W, int S, void* stream);
+/* out[B,Cout,D,H,W] (strided view) = act(conv3x3(cost volume) + bias) on the tensor cores, the volume's feature channels
+ * rebuilt by the producer from the feature maps and its group channels read from gvol.
+ *   warp : virtual input channels [R warped (C) | gvol (3C/8)]; the candidate-invariant left half of the volume enters as
+ *          addL [B, Cout, H, W] = conv3x3(left, W[:, :C]) (no bias), computed once per frame by tstereo_conv_hw3_tc2;
+ *          wpack = tstereo_conv_hw3_tc2 image of W[:, C:] ([Cout][C + 3C/8][9]).
+ *   shift: virtual input channels [-(L - R_d)^2 (C) | gvol (3C/8)]; wpack = image of the whole W ([Cout][C + 3C/8][9]).
+ * tstereo_cost_conv_wpack_floats(C, Cout, half) floats. */
+long long tstereo_cost_conv_wpack_floats(int C, int Cout, int half);
+int tstereo_cost_conv_warp(const float* right, const float* samples, const float* gvol, const float* addL,
+                           float* out, long long osB, long long osC, long long osD,
+                           const float* wpack, const float* bias,
+                           int B, int C, int Cout, int S, int H, int W, int act, int half, void* stream);
+int tstereo_cost_conv_shift(const float* left, const float* right, const float* gvol,
+                            float* out, long long osB, long long osC, long long osD,
+                            const float* wpack, const float* bias,
+                            int B, int C, int Cout, int D, int H, int W, int act, int half, void* stream);
+
 /* ---------------------------------------------------------------- convolutions (a4-a7, a9, a12, a13)
  * ref: architecture/modeling/layers/basic_layers.py:194-235 (Conv3d), :340-388 (ConvTranspose3d),
  *      architecture/modeling/aggregation/TemporalStereo/module.py:111-184 (separable pairs).
@@ -68,19 +95,9 @@ int tstereo_conv_hw3(const float* in, long long isB, long long isC, long long is
                      int B, int Cin, int Cout, int D, int Hin, int Win, int Hout, int Wout,
                      int stride, int dilation, int act, void* stream);
 
-/* Tensor-core forms (tcgen05 implicit GEMM, error-compensated 3xTF32 operands: fp32-equivalent results,
- * DESIGN.md section 3) of tstereo_conv_hw3 (stride 1 only) and tstereo_conv_d, for Cout <= 64.
- * wpack holds the weights split into tf32 hi/lo parts in the MMA's shared-memory layout:
- * [ceil(Cin/8)][tap][khalf 2][part 2][N][4] with N = Cout rounded up to 16, taps = 9 (hw3: ky*3+kx) or k (d);
- * tstereo_conv_tc_wpack_floats(Cin, Cout, taps) floats, 16-byte aligned. */
-long long tstereo_conv_tc_wpack_floats(int Cin, int Cout, int taps);
-int tstereo_conv_hw3_tc(const float* in, long long isB, long long isC, long long isD,
-                        float* out, long long osB, long long osC, long long osD,
-                        const float* wpack, const float* bias,
-                        int B, int Cin, int Cout, int D, int H, int W,
-                        int dilation, int act, void* stream);
-/* Second-generation tensor-core 3x3 conv (stride 1, dilation 1|2, any Cout in groups of 32): 2-D tiles, the three kx taps
- * folded into the MMA's N dimension, 3xTF32 operands (same results as tstereo_conv_hw3 to fp32 rounding).
+/* Tensor-core 3x3 conv (tcgen05 implicit GEMM; stride 1, dilation 1|2, any Cout in groups of 32): 2-D tiles, the three kx
+ * taps folded into the MMA's N dimension, error-compensated hi+lo split operands (same results as tstereo_conv_hw3 to fp32
+ * rounding).
  * ref: layers/basic_layers.py:194-235 via aggregation/TemporalStereo/module.py:111-147, 424-492.
  * wpack: [ceil(Cin/8)][ky 3][khalf 2][row 2N][4] floats, N = 3*CP, CP = 8|16|32 >= Cout,
  * row = part*N + kx*CP + co (part 0 = hi, 1 = lo); tstereo_conv_hw3_tc2_wpack_floats(Cin, Cout, half) floats.
@@ -112,7 +129,7 @@ int tstereo_deconv_hw_tc2(const float* in, long long isB, long long isC, long lo
                           float* out, long long osB, long long osC, long long osD,
                           const float* wpack, const float* bias,
                           int B, int Cin, int Cout, int D, int Hin, int Win, int act, int half, void* stream);
-/* (k,1,1) conv along D (same argument meaning as tstereo_conv_d_tc) through the second-generation tensor-core
+/* (k,1,1) conv along D (same argument meaning as tstereo_conv_d) through the tensor-core
  * kernel: the k input planes are K-chunks of a 1x1 conv.  wpack: pack_conv_d_tc2 in temporalstereo_b200/ops.py,
  * tstereo_conv_d_tc2_wpack_floats(Cin, Cout, k) floats. */
 long long tstereo_conv_d_tc2_wpack_floats(int Cin, int Cout, int k, int half);
@@ -121,11 +138,6 @@ int tstereo_conv_d_tc2(const float* in, long long isB, long long isC, long long 
                        const float* wpack, const float* bias,
                        int B, int Cin, int Cout, int Din, int Dout, int H, int W,
                        int k, int stride, int dilation, int transposed, int act, int half, void* stream);
-int tstereo_conv_d_tc(const float* in, long long isB, long long isC, long long isD,
-                      float* out, long long osB, long long osC, long long osD,
-                      const float* wpack, const float* bias,
-                      int B, int Cin, int Cout, int Din, int Dout, int H, int W,
-                      int k, int stride, int dilation, int transposed, int act, void* stream);
 
 /* (k,1,1) convolution along D: k = 3|5, stride 1|2, dilation 1|2, padding = dilation*(k/2).
  * transposed != 0: ConvTranspose (3,1,1) stride 2, padding 1, output_padding 1 (Dout = 2*Din). */
@@ -142,6 +154,10 @@ int tstereo_deconv_hw(const float* in, long long isB, long long isC, long long i
                       const float* w, const float* bias,
                       int B, int Cin, int Cout, int D, int Hin, int Win,
                       int k, int act, void* stream);
+
+/* out[b, c, :] = in[b, c, :] for dense in [B, C, HW] and an out view with element strides (osB, osC): writes one
+ * operand of a channel concat in place (ref: torch.cat at aggregation/TemporalStereo/precise.py:86). */
+int tstereo_copy_planes(const float* in, float* out, long long osB, long long osC, int B, int C, int HW, void* stream);
 
 /* out = act( trilinear_align_corners(a -> (D,H,W)) + skip )   (module.py:285-295)
  * a [B,C,Da,Ha,Wa], skip/out [B,C,D,H,W] contiguous; skip may be NULL. */

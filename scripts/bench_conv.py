@@ -1,4 +1,4 @@
-"""Times the conv variants (fp32 FMA, tcgen05 v1, tcgen05 v2 kx-folded) on the aggregation's layer shapes and
+"""Times the conv variants (fp32 FMA, tcgen05 kx-folded) on the aggregation's layer shapes and
 prints error statistics vs fp64 for the accumulation cadence G (TSTEREO_TC2_G)."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -55,7 +55,7 @@ for name, Cin, Cout, D, H, W, dil in SHAPES:
     xs = [torch.randn(B, Cin, D, H, W, device="cuda", generator=g) for _ in range(nbuf)]
     w = torch.randn(Cout, Cin, 1, 3, 3, device="cuda", generator=g) * (2.0 / (9 * Cin)) ** 0.5
     bias = torch.randn(Cout, device="cuda", generator=g) * 0.1
-    ws, w1, w2 = pack_simt(w), ops.pack_conv_hw3_tc(w.reshape(Cout, Cin, 9)), ops.pack_conv_hw3_tc2(w.reshape(Cout, Cin, 9))
+    ws, w2 = pack_simt(w), ops.pack_conv_hw3_tc2(w.reshape(Cout, Cin, 9))
     w2h = ops.pack_conv_hw3_tc2(w.reshape(Cout, Cin, 9), True)
     out = torch.empty(B, Cout, D, H, W, device="cuda")
     i = [0]
@@ -64,7 +64,6 @@ for name, Cin, Cout, D, H, W, dil in SHAPES:
         i[0] += 1
         return xs[i[0] % nbuf]
     t_simt = timed(lambda: ops.conv_hw3(nxt(), ws, bias, Cout, 1, dil, "SiLU", out=out))
-    t_v1 = timed(lambda: ops.conv_hw3_tc(nxt(), w1, bias, Cout, dil, "SiLU", out=out))
     res = {}
     for mt in ("2", "4"):
         if Cout > 16 and mt == "4":
@@ -76,7 +75,7 @@ for name, Cin, Cout, D, H, W, dil in SHAPES:
     gflop = 2.0 * B * Cin * Cout * 9 * D * H * W / 1e9
     mb = 4.0 * B * (Cin + Cout) * D * H * W / 1e6
     best = min(res.values())
-    print(f"{name:32s} B={B} {gflop:7.2f} GFLOP {mb:7.1f} MB | fma {t_simt:7.1f} us  tc1 {t_v1:7.1f} us  tc2 " +
+    print(f"{name:32s} B={B} {gflop:7.2f} GFLOP {mb:7.1f} MB | fma {t_simt:7.1f} us  tc2 " +
           " ".join(f"MT{k}={v:7.1f}" for k, v in res.items()) +
           f" us | f16 {t_h:7.1f} us {gflop / t_h * 1e-3:6.1f} TFLOP/s {mb / t_h * 1e-3:5.2f} TB/s")
 

@@ -70,7 +70,7 @@ if "conv" in which:
         wt = pack(cout, cin, 9); bias = torch.randn(cout, device=dev)
         med, best = timeit(lambda i: ops.conv_hw3(x, wt, bias, cout, st, dl, "SiLU"))
         fl = 2 * B * cin * cout * 9 * D * h * w
-        wtc = ops.pack_conv_hw3_tc(torch.randn(cout, cin, 9, device=dev) * 0.05)
-        med_tc, _ = timeit(lambda i: ops.conv_hw3_tc(x, wtc, bias, cout, dl, "SiLU"))
+        wtc = ops.pack_conv_hw3_tc2(torch.randn(cout, cin, 9, device=dev) * 0.05, True)
+        med_tc, _ = timeit(lambda i: ops.conv_hw3_tc2(x, wtc, bias, cout, dl, "SiLU", half=True))
         print(f"conv_hw3 {name:26s} B={B} {fl/1e9:6.2f} GFLOP  fp32-FMA {med:8.1f} us ({fl/med/1e6:6.2f} TFLOP/s)   "
-              f"tcgen05 3xTF32 {med_tc:8.1f} us ({fl/med_tc/1e6:6.2f} TFLOP/s fp32-equivalent)  x{med/med_tc:.2f}")
+              f"tcgen05 fp16 hi+lo {med_tc:8.1f} us ({fl/med_tc/1e6:6.2f} TFLOP/s fp32-equivalent)  x{med/med_tc:.2f}")

@@ -23,9 +23,12 @@ SIGNATURES = {
     "tstereo_block_cost_scratch_floats": (LL, [I, I, I, I, I]),
     "tstereo_block_cost_shift": (I, [P, P, P, P, I, I, I, I, I, P]),
     "tstereo_block_cost_warp": (I, [P, P, P, P, P, I, I, I, I, I, P]),
+    "tstereo_group_cost_shift": (I, [P, P, P, P, I, I, I, I, I, P]),
+    "tstereo_group_cost_warp": (I, [P, P, P, P, P, I, I, I, I, I, P]),
+    "tstereo_cost_conv_wpack_floats": (LL, [I, I, I]),
+    "tstereo_cost_conv_warp": (I, [P, P, P, P, P, LL, LL, LL, P, P, I, I, I, I, I, I, I, I, P]),
+    "tstereo_cost_conv_shift": (I, [P, P, P, P, LL, LL, LL, P, P, I, I, I, I, I, I, I, I, P]),
     "tstereo_conv_hw3": (I, [P, LL, LL, LL, P, LL, LL, LL, P, P, I, I, I, I, I, I, I, I, I, I, I, P]),
-    "tstereo_conv_tc_wpack_floats": (LL, [I, I, I]),
-    "tstereo_conv_hw3_tc": (I, [P, LL, LL, LL, P, LL, LL, LL, P, P, I, I, I, I, I, I, I, I, P]),
     "tstereo_conv_hw3_tc2_wpack_floats": (LL, [I, I, I]),
     "tstereo_conv_hw3_tc2": (I, [P, LL, LL, LL, P, LL, LL, LL, P, P, I, I, I, I, I, I, I, I, I, P]),
     "tstereo_conv_hw3s2_tc2_wpack_floats": (LL, [I, I, I]),
@@ -34,9 +37,9 @@ SIGNATURES = {
     "tstereo_deconv_hw_tc2": (I, [P, LL, LL, LL, P, LL, LL, LL, P, P, I, I, I, I, I, I, I, I, P]),
     "tstereo_conv_d_tc2_wpack_floats": (LL, [I, I, I, I]),
     "tstereo_conv_d_tc2": (I, [P, LL, LL, LL, P, LL, LL, LL, P, P, I, I, I, I, I, I, I, I, I, I, I, I, I, P]),
-    "tstereo_conv_d_tc": (I, [P, LL, LL, LL, P, LL, LL, LL, P, P, I, I, I, I, I, I, I, I, I, I, I, I, P]),
     "tstereo_conv_d": (I, [P, LL, LL, LL, P, LL, LL, LL, P, P, I, I, I, I, I, I, I, I, I, I, I, P]),
     "tstereo_deconv_hw": (I, [P, LL, LL, LL, P, LL, LL, LL, P, P, I, I, I, I, I, I, I, I, P]),
+    "tstereo_copy_planes": (I, [P, P, LL, LL, I, I, I, P]),
     "tstereo_resize_add_act": (I, [P, P, P, I, I, I, I, I, I, I, I, I, P]),
     "tstereo_pool5": (I, [P, LL, LL, P, P, LL, LL, I, I, I, I, I, P]),
     "tstereo_merge_memory": (I, [P, P, P, P, P, P, P, LL, LL, P, I, I, I, I, I, I, P]),
@@ -92,7 +95,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)       # AttributeError if the library does not export it
         fn.restype = res
         fn.argtypes = args
-    if lib.tstereo_version() < 100:
+    if lib.tstereo_version() < 200:
         raise ImportError(f"libtstereo.so version {lib.tstereo_version()} too old")
     _lib = lib
     return lib

@@ -18,6 +18,7 @@ Inference only (the reference's history frames also run under no_grad, TemporalS
 from __future__ import annotations
 
 import math
+import warnings
 from typing import Dict, List, Optional
 
 import torch
@@ -36,13 +37,15 @@ class _Node(nn.Module):
 
 
 class _Packed:
-    __slots__ = ("w", "b", "cout", "wtc", "wtc2", "lazy")
+    """One layer's weights as the kernels read them (BatchNorm folded): `w` [Cin][taps][CoutP] + `b` for the fp32 FMA
+    kernels, `tc[kind]` the tensor-core operand images ("hw3" stride-1 3x3, "s2" stride-2 3x3, "dc" stride-2
+    transposed, "d" (k,1,1) along D, "cost" / "left" the fused cost -> first-conv pair).  Built on the CPU and
+    uploaded once per checkpoint load."""
+    __slots__ = ("w", "b", "cout", "tc")
 
-    def __init__(self, w, b, cout, wtc=None, wtc2=None):
+    def __init__(self, w, b, cout, tc=None):
         self.w, self.b, self.cout = w, b, cout
-        self.lazy = {}          # operand images built on first use (stride-2 / transposed tensor-core forms)
-        self.wtc = wtc          # tcgen05 (3xTF32) operand image of a 3x3 / (k,1,1) conv, or None
-        self.wtc2 = wtc2        # operand image of the kx-folded tcgen05 3x3 kernel (Cout <= 32), or None
+        self.tc = tc or {}
 
 
 def _level_cfg(node, defaults: dict) -> dict:
@@ -91,11 +94,17 @@ class TEMPORALSTEREO(nn.Module):
         # every contraction (3x3 stride 1 / 2, (k,1,1) along D, stride-2 transposed) on tcgen05 with hi+lo split operands
         # (fp32-equivalent results); False keeps them all on the fp32 FMA pipe
         self.tensor_cores = True
-        # per-(layer shape) choice between the tensor-core and the fp32-FMA kernel: "auto" times both on the
-        # first call of a shape (outside CUDA-graph capture) and keeps the faster; "tc2" / "simt" force one
-        # (or a dict per operator kind: "hw3", "hw3s2", "d", "dc")
+        # per-(layer shape) choice between the tensor-core and the fp32-FMA kernel: "auto" decides from the shape
+        # alone (`_rule`: deterministic, the same on every run and rank); "timed" times both on the first call of a
+        # shape and keeps the faster (experiments); "tc2" / "simt" force one (or a dict per operator kind:
+        # "hw3", "hw3s2", "d", "dc")
         self.plan_mode = "auto"
         self._plan: Dict[tuple, str] = {}
+        self._plan_times: Dict[tuple, dict] = {}
+        # the raw cost volumes never touch HBM: each level's first (1,3,3) conv rebuilds them in its producer
+        # (ops.cost_conv_*); False materialises them with ops.block_cost (the drop-in operator) first
+        self.fuse_cost = True
+        self._warned_train = False
         # tensor-core operand split: fp16 hi + lo (kind::f16, 16 channels per MMA; activations < 65504) or tf32 hi + lo
         self.half_split = True
         # run the UNet encoder on a side stream, concurrently with the coarse and fine levels
@@ -165,51 +174,80 @@ class TEMPORALSTEREO(nn.Module):
         return out
 
     def train(self, mode: bool = True):
-        if mode:
-            raise NotImplementedError("libtstereo is an inference engine: BatchNorm is folded with running statistics; "
-                                      "call .eval() (history frames in the reference run the same way, "
-                                      "projects/TemporalStereo/TemporalStereo.py:268-274)")
+        """The engine stays in folded-BatchNorm inference whatever the caller toggles: the reference trainer calls
+        `self.train()` after every history frame (projects/TemporalStereo/TemporalStereo.py:268-274) and Lightning
+        calls it around fit / validate / test, so `train(True)` must not raise.  It warns once; gradients are what
+        is not available (`forward` raises if an input requires grad while grad mode is on)."""
+        if mode and not self._warned_train:
+            self._warned_train = True
+            warnings.warn("libtstereo TEMPORALSTEREO is an inference engine (BatchNorm folded with running statistics): "
+                          "train(True) keeps it in eval mode", stacklevel=2)
         return super().train(False)
 
-    # ------------------------------------------------------------------ weight packing
-    def _fold(self, sd, conv: str, bn: Optional[str], transposed: bool = False) -> _Packed:
-        """[Cout,Cin,*k] (or [Cin,Cout,*k]) -> [Cin][taps][CoutP] with eval-mode BN folded in."""
-        w = sd[conv + ".weight"].detach().float()
+    # ------------------------------------------------------------------ weight packing (CPU; one upload)
+    @staticmethod
+    def _fold(sd, conv: str, bn: Optional[str], transposed: bool = False):
+        """[Cout,Cin,*k] (or [Cin,Cout,*k]) -> (w [Cout, Cin, taps], bias [Cout] | None) with eval-mode BN folded in."""
+        w = sd[conv + ".weight"]
         if transposed:
             w = w.transpose(0, 1)
         cout, cin = w.shape[:2]
         w = w.reshape(cout, cin, -1)
         bias = sd.get(conv + ".bias")
-        bias = bias.detach().float() if bias is not None else None
         if bn is not None:
-            s = sd[bn + ".weight"].detach().float() / torch.sqrt(sd[bn + ".running_var"].detach().float() + BN_EPS)
+            s = sd[bn + ".weight"] / torch.sqrt(sd[bn + ".running_var"] + BN_EPS)
             w = w * s.view(-1, 1, 1)
             b0 = bias if bias is not None else torch.zeros_like(s)
-            bias = (b0 - sd[bn + ".running_mean"].detach().float()) * s + sd[bn + ".bias"].detach().float()
-        coutp = (cout + 3) // 4 * 4
-        packed = torch.zeros((cin, w.shape[2], coutp), device=w.device, dtype=torch.float32)
+            bias = (b0 - sd[bn + ".running_mean"]) * s + sd[bn + ".bias"]
+        return w.contiguous(), bias
+
+    def _mk(self, w: torch.Tensor, bias: Optional[torch.Tensor], kinds=(), ksz: int = 3) -> _Packed:
+        """w [Cout, Cin, taps] (CPU) -> the FMA layout [Cin][taps][CoutP] plus the tensor-core operand images in `kinds`."""
+        cout, cin, T = w.shape
+        packed = torch.zeros((cin, T, (cout + 3) // 4 * 4), dtype=torch.float32)
         packed[:, :, :cout] = w.permute(1, 2, 0)
-        wtc = None
-        is_hw = conv.endswith(".conv.0") or ".refinement." in conv or ".mask." in conv     # (1,k,k) / 2-D kernels
-        tc_ok = (w.shape[2] == 9 and not transposed) if is_hw else w.shape[2] in (3, 5)
-        wtc2 = None
-        if tc_ok and cout <= 64 and cin >= 8 and w.is_cuda and self.tensor_cores:
-            wtc = ops.pack_conv_tc(w)
-            if is_hw:
-                wtc2 = ops.pack_conv_hw3_tc2(w, self.half_split)
-        return _Packed(packed.contiguous(), None if bias is None else bias.contiguous(), cout, wtc, wtc2)
+        tc = {}
+        if self.tensor_cores:
+            h = self.half_split
+            for kind in kinds:
+                if kind == "hw3" and cin >= 8 and T == 9:
+                    tc[kind] = ops.pack_conv_hw3_tc2(w, h)
+                elif kind == "s2" and T == 9:
+                    tc[kind] = ops.pack_conv_hw3s2_tc2(w, h)
+                elif kind == "dc" and cin >= 8:
+                    tc[kind] = ops.pack_deconv_hw_tc2(w, ksz, h)
+                elif kind == "d" and cin >= 8 and T in (3, 5):
+                    tc[kind] = ops.pack_conv_d_tc2(w, h)
+        return _Packed(packed, bias, cout, tc)
 
-    def _pack(self) -> Dict[str, _Packed]:
-        sd = dict(self.state_dict(keep_vars=True))
+    def _pack(self, dev) -> Dict[str, _Packed]:
+        """BatchNorm folding and operand packing run on the CPU; every packed tensor lands in ONE device buffer with
+        a single host-to-device copy (no device-side torch kernels: the first forward launches only libtstereo's)."""
+        sd = {k: v.detach().to("cpu", torch.float32) for k, v in self.state_dict(keep_vars=True).items()
+              if v.dtype.is_floating_point}
         pk: Dict[str, _Packed] = {}
+        fold, mk = self._fold, self._mk
 
-        def sep(p, transposed=False):
-            for i in ("0", "1"):
-                pk[f"{p}.conv.{i}"] = self._fold(sd, f"{p}.conv.{i}", f"{p}.conv.{i}.norm", transposed)
+        def sep(p, transposed=False, stride=1):
+            w0, b0 = fold(sd, f"{p}.conv.0", f"{p}.conv.0.norm", transposed)
+            pk[f"{p}.conv.0"] = mk(w0, b0, ("dc",) if transposed else (("s2",) if stride == 2 else ("hw3",)), 3)
+            w1, b1 = fold(sd, f"{p}.conv.1", f"{p}.conv.1.norm", transposed)
+            pk[f"{p}.conv.1"] = mk(w1, b1, ("d",))
 
-        def init3d(p):
+        def init3d(p, C, warp):
             sep(p + ".0")
-            for n in ("conv1", "conv2", "conv3", "conv4", "shortcut5", "shortcut6"):
+            first = pk[p + ".0.conv.0"]
+            if self.tensor_cores:           # fused cost -> first conv: virtual channels [feature half | group terms]
+                w0, _ = fold(sd, f"{p}.0.conv.0", f"{p}.0.conv.0.norm")
+                if warp:                    # [L (C) | warp(R) (C) | g (3C/8)]: the L half is hoisted out of the D loop
+                    first.tc["left"] = ops.pack_conv_hw3_tc2(w0[:, :C].contiguous(), self.half_split)
+                    first.tc["cost"] = ops.pack_conv_hw3_tc2(w0[:, C:].contiguous(), self.half_split)
+                else:                       # [-(L - R_d)^2 (C) | g (3C/8)]
+                    first.tc["cost"] = ops.pack_conv_hw3_tc2(w0, self.half_split)
+            sep(f"{p}.1.conv1", stride=2)
+            sep(f"{p}.1.conv2")
+            sep(f"{p}.1.conv3", stride=2)
+            for n in ("conv4", "shortcut5", "shortcut6"):
                 sep(f"{p}.1.{n}")
             sep(f"{p}.1.conv5", True)
             sep(f"{p}.1.conv6", True)
@@ -217,112 +255,146 @@ class TEMPORALSTEREO(nn.Module):
 
         def heads(p):
             # both (3,1,1) head convs fused into one Cout = 2C conv: [cost-head feats | offset-head feats]
-            a = self._fold(sd, f"{p}.cost_head.0", f"{p}.cost_head.0.norm")
-            b = self._fold(sd, f"{p}.off_head.0", f"{p}.off_head.0.norm")
-            c = a.cout
-            w = torch.cat([a.w[:, :, :c], b.w[:, :, :c]], 2)
-            cp = (2 * c + 3) // 4 * 4
-            wp = torch.zeros((w.shape[0], w.shape[1], cp), device=w.device)
-            wp[:, :, :2 * c] = w
-            wtc = None
-            if self.tensor_cores and w.is_cuda and 2 * c <= 64 and w.shape[0] >= 8:
-                wtc = ops.pack_conv_tc(w.permute(2, 0, 1).contiguous())            # [Cin][k][2C] -> [2C][Cin][k]
-            pk[p + ".stem"] = _Packed(wp.contiguous(), torch.cat([a.b, b.b]).contiguous(), 2 * c, wtc)
-            w1 = torch.stack([sd[f"{p}.cost_head.1.weight"].detach().float().reshape(c, 9),
-                              sd[f"{p}.off_head.1.weight"].detach().float().reshape(c, 9)])
+            wa, ba = fold(sd, f"{p}.cost_head.0", f"{p}.cost_head.0.norm")
+            wb, bb = fold(sd, f"{p}.off_head.0", f"{p}.off_head.0.norm")
+            c = wa.shape[0]
+            pk[p + ".stem"] = mk(torch.cat([wa, wb], 0), torch.cat([ba, bb]), ("d",) if 2 * c <= 64 else ())
+            w1 = torch.stack([sd[f"{p}.cost_head.1.weight"].reshape(c, 9), sd[f"{p}.off_head.1.weight"].reshape(c, 9)])
             pk[p + ".final"] = _Packed(w1.contiguous(), None, 2)
 
         for lvl in ("coarse", "fine"):
-            init3d(f"{lvl}.init3d")
-            pc = self._fold(sd, f"{lvl}.past_conv", f"{lvl}.past_conv.norm")
-            c = pc.cout
-            pk[f"{lvl}.past_conv"] = _Packed(pc.w[0, 0, :c].contiguous(), pc.b, c)
-            pk[f"{lvl}.fuse.conv_5x5"] = self._fold(sd, f"{lvl}.fuse.conv_5x5", f"{lvl}.fuse.conv_5x5.norm")
+            cfg = self.levels[lvl]
+            init3d(f"{lvl}.init3d", cfg["in_planes"], lvl == "fine")
+            w, b = fold(sd, f"{lvl}.past_conv", f"{lvl}.past_conv.norm")
+            pk[f"{lvl}.past_conv"] = _Packed(w[:, 0, 0].contiguous(), b, w.shape[0])
+            w, b = fold(sd, f"{lvl}.fuse.conv_5x5", f"{lvl}.fuse.conv_5x5.norm")
+            pk[f"{lvl}.fuse.conv_5x5"] = mk(w, b, ("d",))
             sep(f"{lvl}.fuse.conv_fuse")
             heads(f"{lvl}.pred_heads")
             m = f"{lvl}.convex_upsample.mask"
-            pk[m + ".0"] = self._fold(sd, m + ".0", m + ".1")
-            pk[m + ".3"] = _Packed(sd[m + ".3.weight"].detach().float().reshape(36, 64).contiguous(),
-                                   sd[m + ".3.bias"].detach().float().contiguous(), 36)
-        init3d("precise.init3d")
-        heads("precise.pred_heads")
+            w, b = fold(sd, m + ".0", m + ".1")
+            pk[m + ".0"] = mk(w, b, ("hw3",))
+            pk[m + ".3"] = _Packed(sd[m + ".3.weight"].reshape(36, 64).contiguous(), sd[m + ".3.bias"].contiguous(), 36)
         r = "precise.refinement"
-        for n in ("conv2.0", "conv2.1", "conv4.0", "conv4.1", "fuse.0", "fuse.1", "concat"):
-            pk[f"{r}.{n}"] = self._fold(sd, f"{r}.{n}", f"{r}.{n}.norm")
-        pk[f"{r}.deconv4"] = self._fold(sd, f"{r}.deconv4", f"{r}.deconv4.norm", True)
-        pk[f"{r}.deconv2"] = self._fold(sd, f"{r}.deconv2", None, True)
+        init3d("precise.init3d", self.levels["precise"]["in_planes"] + sd[f"{r}.conv4.1.weight"].shape[0], True)
+        heads("precise.pred_heads")
+        for n, stride in (("conv2.0", 2), ("conv2.1", 1), ("conv4.0", 2), ("conv4.1", 1), ("fuse.0", 1), ("fuse.1", 1), ("concat", 1)):
+            w, b = fold(sd, f"{r}.{n}", f"{r}.{n}.norm")
+            pk[f"{r}.{n}"] = mk(w, b, ("s2",) if stride == 2 else ("hw3",))
+        w, b = fold(sd, f"{r}.deconv4", f"{r}.deconv4.norm", True)
+        pk[f"{r}.deconv4"] = mk(w, b, ("dc",), 4)
+        w, b = fold(sd, f"{r}.deconv2", None, True)
+        pk[f"{r}.deconv2"] = mk(w, b, ("dc",), 4)
+
+        # one arena, one upload; every tensor starts 256-byte aligned (the operand images need 16)
+        items = []
+        for k in pk.values():
+            items.append((k, "w", None))
+            if k.b is not None:
+                items.append((k, "b", None))
+            items += [(k, "tc", name) for name in k.tc]
+        get = lambda k, f, n: (k.tc[n] if f == "tc" else getattr(k, f))
+        offs, total = [], 0
+        for it in items:
+            offs.append(total)
+            total += (get(*it).numel() + 63) // 64 * 64
+        host = torch.zeros((total,), dtype=torch.float32)
+        for it, o in zip(items, offs):
+            t = get(*it).contiguous().view(-1)
+            host[o:o + t.numel()] = t
+        arena = host.to(dev)
+        for (k, f, n), o in zip(items, offs):
+            t = get(k, f, n)
+            v = arena[o:o + t.numel()].view(t.shape)
+            if f == "tc":
+                k.tc[n] = v
+            else:
+                setattr(k, f, v)
+        self._arena = arena
         return pk
 
     # ------------------------------------------------------------------ building blocks
+    @staticmethod
+    def _rule(kind: str, x_shape, cout: int) -> str:
+        """Deterministic kernel choice from the layer shape alone (measured on B200, profiles/r02_plan_*.md): the
+        tensor-core kernel has a fixed cost of ~10 us per launch (TMEM allocation, barrier set-up, a serial chunk
+        pipeline per CTA), which the fp32 FMA kernels undercut on the small hourglass volumes and on the narrow
+        (k,1,1) convs whose arithmetic intensity is a few MACs per byte."""
+        cin = x_shape[1]
+        planes = x_shape[0] * (x_shape[2] if len(x_shape) == 5 else 1)
+        hw = x_shape[-2] * x_shape[-1]
+        if kind == "d":
+            return "simt" if (cin <= 16 and cout <= 16) or planes * hw < 200_000 else "tc2"
+        if kind in ("hw3", "hw3s2", "dc"):
+            return "simt" if planes * hw < 100_000 and cin * cout <= 64 * 64 and hw <= 34 * 60 else "tc2"
+        return "tc2"
+
     def _pick(self, key, cands):
-        """Plan cache (per-shape plan cache): which kernel runs this layer shape.
-        `cands` maps a kernel name ("tc2", "simt") to a thunk; plan_mode "auto" times each on the first
-        call of a shape (outside CUDA-graph capture) and keeps the fastest; any other plan_mode forces that
-        kernel where it exists."""
+        """Plan cache (per-shape plan cache): which kernel runs this layer shape.  `cands` maps a kernel
+        name ("tc2", "simt") to a thunk.  plan_mode "auto": `_rule` (shape only, deterministic); "timed": time each on
+        the first call of a shape (outside CUDA-graph capture) and keep the fastest; anything else forces that kernel
+        where it exists."""
         names = list(cands)
         mode = self.plan_mode.get(key[0], "auto") if isinstance(self.plan_mode, dict) else self.plan_mode
-        if mode != "auto":
+        if len(names) == 1:
+            choice = names[0]
+        elif mode == "auto":
+            choice = self._rule(key[0], key[1], key[2])
+            if choice not in cands:
+                choice = names[0]
+        elif mode != "timed":
             choice = mode if mode in cands else names[0]
         else:
             choice = self._plan.get(key)
-        if choice is None:
-            if torch.cuda.is_current_stream_capturing() or len(names) == 1:
-                choice = names[0]
-            else:
-                times = []
-                for nme in names:
-                    fn = cands[nme]
-                    fn()
-                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    e0.record()
-                    for _ in range(3):
+            if choice is None:
+                if torch.cuda.is_current_stream_capturing():
+                    choice = names[0]
+                else:
+                    times = {}
+                    for nme in names:
+                        fn = cands[nme]
                         fn()
-                    e1.record()
-                    e1.synchronize()
-                    times.append(e0.elapsed_time(e1))
-                choice = names[times.index(min(times))]
-                self._plan[key] = choice
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record()
+                        for _ in range(5):
+                            fn()
+                        e1.record()
+                        e1.synchronize()
+                        times[nme] = e0.elapsed_time(e1) / 5 * 1e3
+                    choice = min(times, key=times.get)
+                    self._plan[key] = choice
+                    self._plan_times[key] = times
         return cands[choice]()
 
     def _hw3(self, x, k: _Packed, stride=1, dil=1, act=None, out=None):
-        """3x3 conv over (H,W): tensor cores (stride 1) or the fp32 FMA kernel, per the plan."""
+        """3x3 conv over (H,W): tensor cores or the fp32 FMA kernel, per the plan."""
         simt = lambda: ops.conv_hw3(x, k.w, k.b, k.cout, stride, dil, act, out=out)
-        if not self.tensor_cores or not k.w.is_cuda:
-            return simt()
-        if stride == 2 and dil == 1 and k.w.shape[1] == 9:
-            if "s2" not in k.lazy:      # [Cin][9][CoutP] -> [Cout][Cin][9]
-                k.lazy["s2"] = ops.pack_conv_hw3s2_tc2(k.w[:, :, :k.cout].permute(2, 0, 1).contiguous(), self.half_split)
+        h = self.half_split
+        if stride == 2 and dil == 1 and "s2" in k.tc:
             return self._pick(("hw3s2", tuple(x.shape), k.cout),
-                              {"tc2": lambda: ops.conv_hw3s2_tc2(x, k.lazy["s2"], k.b, k.cout, act, out=out, half=self.half_split),
-                               "simt": simt})
-        if k.wtc2 is None or stride != 1:
+                              {"tc2": lambda: ops.conv_hw3s2_tc2(x, k.tc["s2"], k.b, k.cout, act, out=out, half=h), "simt": simt})
+        if stride != 1 or "hw3" not in k.tc:
             return simt()
-        # the first-generation kernel (ops.conv_hw3_tc) stays an operator of the library but is no plan candidate:
-        # conv_hw3_tc2 is faster on every layer shape of the model
-        cands = {"tc2": lambda: ops.conv_hw3_tc2(x, k.wtc2, k.b, k.cout, dil, act, out=out, half=self.half_split), "simt": simt}
-        return self._pick(("hw3", tuple(x.shape), k.cout, dil), cands)
+        return self._pick(("hw3", tuple(x.shape), k.cout, dil),
+                          {"tc2": lambda: ops.conv_hw3_tc2(x, k.tc["hw3"], k.b, k.cout, dil, act, out=out, half=h), "simt": simt})
 
     def _d(self, x, k: _Packed, ksz=3, stride=1, dil=1, transposed=False, act=None, out=None):
         """(k,1,1) conv along D: tensor cores when a tcgen05 operand image exists."""
         simt = lambda: ops.conv_d(x, k.w, k.b, k.cout, ksz, stride, dil, transposed, act, out=out)
-        if k.wtc is None or not self.tensor_cores:
+        if "d" not in k.tc:
             return simt()
         key = ("d", tuple(x.shape), k.cout, ksz, stride, dil, transposed)
-        if "d2" not in k.lazy:          # [Cin][k][CoutP] -> [Cout][Cin][k]
-            k.lazy["d2"] = ops.pack_conv_d_tc2(k.w[:, :, :k.cout].permute(2, 0, 1).contiguous(), self.half_split)
-        return self._pick(key, {"tc2": lambda: ops.conv_d_tc2(x, k.lazy["d2"], k.b, k.cout, ksz, stride, dil, transposed, act, out=out,
+        return self._pick(key, {"tc2": lambda: ops.conv_d_tc2(x, k.tc["d"], k.b, k.cout, ksz, stride, dil, transposed, act, out=out,
                                                               half=self.half_split),
                                 "simt": simt})
 
     def _deconv_hw(self, x, k: _Packed, ksz, act=None, out=None):
         """Stride-2 transposed (1,k,k) / kxk conv: four tensor-core phase launches or the fp32 FMA kernel."""
         simt = lambda: ops.deconv_hw(x, k.w, k.b, k.cout, ksz, act, out=out)
-        if not self.tensor_cores or not k.w.is_cuda or k.w.shape[0] < 8:
+        if "dc" not in k.tc:
             return simt()
-        if "dc" not in k.lazy:          # [Cin][k*k][CoutP] (transposed-conv tap order) -> [Cout][Cin][k*k]
-            k.lazy["dc"] = ops.pack_deconv_hw_tc2(k.w[:, :, :k.cout].permute(2, 0, 1).contiguous(), ksz, self.half_split)
         return self._pick(("dc", tuple(x.shape), k.cout, ksz),
-                          {"tc2": lambda: ops.deconv_hw_tc2(x, k.lazy["dc"], k.b, k.cout, act, out=out, half=self.half_split),
+                          {"tc2": lambda: ops.deconv_hw_tc2(x, k.tc["dc"], k.b, k.cout, act, out=out, half=self.half_split),
                            "simt": simt})
 
     def _sep(self, x, p, stride=1, dil=1, act0="SiLU", act1="SiLU", out=None):
@@ -350,8 +422,21 @@ class TEMPORALSTEREO(nn.Module):
         sc = self._sep(x, p + ".shortcut6", act0=None, act1=None)
         return ops.resize_add_act(o, x.shape[-3:], sc, "SiLU")
 
-    def _init3d(self, raw, p):
-        y = self._sep(raw, p + ".0")
+    def _init3d(self, left, right, samples, p):
+        """block_cost -> init3d stack (reference coarse.py:82-83, fine.py:102-103, precise.py:88-90).  `samples` is the
+        candidate tensor [B,S,H,W] (warp volume) or an int (shift volume).  With `fuse_cost` the raw volume is never
+        materialised: group-wise terms (small side kernel) + the first (1,3,3) conv rebuilding the feature half."""
+        a, b = self._pk[p + ".0.conv.0"], self._pk[p + ".0.conv.1"]
+        if self.fuse_cost and "cost" in a.tc:
+            g = ops.group_cost(left, right, samples)
+            if isinstance(samples, int):
+                y = ops.cost_conv_shift(left, right, g, a.tc["cost"], a.b, a.cout, "SiLU", half=self.half_split)
+            else:
+                addl = ops.conv_hw3_tc2(left, a.tc["left"], None, a.cout, 1, None, half=self.half_split)
+                y = ops.cost_conv_warp(right, samples, g, addl, a.tc["cost"], a.b, a.cout, "SiLU", half=self.half_split)
+        else:
+            y = self._hw3(ops.block_cost(left, right, samples), a, 1, 1, "SiLU")
+        y = self._d(y, b, 3, 1, 1, False, "SiLU")
         y = self._hourglass(y, p + ".1")
         return self._sep(y, p + ".2", dil=2)
 
@@ -365,8 +450,8 @@ class TEMPORALSTEREO(nn.Module):
     def _linspace_samples(self, B, n, H, W, device):
         key = ("lin", B, n, H, W, str(device))
         if key not in self._const:
-            s = torch.linspace(0, n - 1, n, device=device).view(1, n, 1, 1).expand(B, n, H, W).contiguous()
-            self._const[key] = s
+            s = torch.linspace(0, n - 1, n).view(1, n, 1, 1).expand(B, n, H, W).contiguous()
+            self._const[key] = s.to(device)
         return self._const[key]
 
     def _memory_level(self, lvl, left, right, samples, prev_info, coarse):
@@ -375,10 +460,9 @@ class TEMPORALSTEREO(nn.Module):
         cfg = self.levels[lvl]
         C = cfg["C"]
         B, _, H, W = left.shape
-        raw = ops.block_cost(left, right, cfg["num_sample"] if coarse else samples)
+        vol = self._init3d(left, right, cfg["num_sample"] if coarse else samples, f"{lvl}.init3d")
         if coarse:
             samples = self._linspace_samples(B, cfg["num_sample"], H, W, left.device)
-        vol = self._init3d(raw, f"{lvl}.init3d")
         D = vol.shape[2]
         ms = mv = None
         memory = prev_info.get("cost_memory", None)
@@ -388,7 +472,8 @@ class TEMPORALSTEREO(nn.Module):
                 mw = ms.shape[-1]
                 ms = ops.bilinear_resize(ms, (H, W), mul=W, div=mw)
                 mv = ops.bilinear_resize(mv, (H, W))
-            assert ms.shape == (B, 2, H, W) and mv.shape == (B, 2, H, W), "cost memory / level resolution mismatch"
+            if ms.shape != (B, 2, H, W) or mv.shape != (B, 2, H, W):
+                raise ValueError(f"cost memory {tuple(ms.shape)} does not match the {lvl} level {(B, 2, H, W)}")
         pc = self._pk[f"{lvl}.past_conv"]
         cat = torch.empty((B, 4 * C, D + 2, H, W), device=left.device, dtype=torch.float32)
         _, samples = ops.merge_memory(vol, samples, ms, mv, pc.w, pc.b, 2, out_vol=cat[:, :C])
@@ -412,14 +497,26 @@ class TEMPORALSTEREO(nn.Module):
         k = self._pk[p]
         return self._hw3(x, k, stride, 1, act, out=out)
 
+    @staticmethod
+    def _check_pyramid(l4, l8, l16, r4, r8, r16, left_image, right_image):
+        """The reference fails with a shape error on sizes that are not multiples of 16 (cat of
+        135- and 136-row tensors); the kernels write into pre-sized views, so the geometry is validated up front."""
+        B = l4.shape[0]
+        H16, W16 = l16.shape[-2:]
+        want = {"left 1/8": (l8, (2 * H16, 2 * W16)), "left 1/4": (l4, (4 * H16, 4 * W16)),
+                "left image": (left_image, (16 * H16, 16 * W16))}
+        for name, (t, hw) in want.items():
+            if tuple(t.shape[-2:]) != hw or t.shape[0] != B:
+                raise ValueError(f"{name} has shape {tuple(t.shape)}; the 1/16 features {tuple(l16.shape)} need (H, W) = {hw} "
+                                 "(input sizes must be multiples of 16: pad or resize like the reference's data pipeline)")
+        for a, b_, name in ((l4, r4, "1/4"), (l8, r8, "1/8"), (l16, r16, "1/16"), (left_image, right_image, "image")):
+            if a.shape != b_.shape:
+                raise ValueError(f"left / right {name} shapes differ: {tuple(a.shape)} vs {tuple(b_.shape)}")
+
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
-    def forward(self, left_feats: List[torch.Tensor], right_feats: List[torch.Tensor], left_image: torch.Tensor,
-                right_image: torch.Tensor, prev_info: Optional[dict] = None):
-        if prev_info is None:
-            prev_info = {}
-        if self._pk is None:
-            self._pk = self._pack()
+    def _forward(self, left_feats: List[torch.Tensor], right_feats: List[torch.Tensor], left_image: torch.Tensor,
+                 right_image: torch.Tensor, prev_info: dict):
         l4, l8, l16 = [t.contiguous() for t in left_feats]
         r4, r8, r16 = [t.contiguous() for t in right_feats]
         left_image, right_image = left_image.contiguous(), right_image.contiguous()
@@ -427,6 +524,9 @@ class TEMPORALSTEREO(nn.Module):
         B = l4.shape[0]
         if not all(t.is_cuda for t in (l4, l8, l16, r4, r8, r16, left_image, right_image)):
             raise TypeError("libtstereo ops need fp32 CUDA tensors (there is no CPU fallback for the hot path)")
+        self._check_pyramid(l4, l8, l16, r4, r8, r16, left_image, right_image)
+        if self._pk is None:
+            self._pk = self._pack(dev)
 
         # ---- UNet encoder (1/2- and 1/4-scale image features, reference module.py:459-466): independent of the
         #      coarse and fine levels, so it runs on a side stream while their small, latency-bound launches
@@ -441,15 +541,17 @@ class TEMPORALSTEREO(nn.Module):
         lcat, rcat = lrcat[:B], lrcat[B:]
         cat2lr = torch.empty((2 * B, 2 * c2, (H - 1) // 2 + 1, (W - 1) // 2 + 1), device=dev, dtype=torch.float32)
         cat2 = cat2lr[:B]                 # [deconv4 output | left 1/2-scale features]; the right half's first c2 planes stay unused
-        images = torch.cat([left_image, right_image], 0)
+        half2 = torch.empty((2 * B, c2, (H - 1) // 2 + 1, (W - 1) // 2 + 1), device=dev, dtype=torch.float32)
         main = torch.cuda.current_stream(dev)
         side = self._side_stream(dev) if self.overlap_encoder else main
         if side is not main:
             side.wait_stream(main)
         with torch.cuda.stream(side):
-            lcat[:, :cf].copy_(l4)
-            rcat[:, :cf].copy_(r4)
-            self._conv2d(self._conv2d(images, r + ".conv2.0", 2), r + ".conv2.1", out=cat2lr[:, c2:])
+            ops.copy_planes(l4, lcat[:, :cf])
+            ops.copy_planes(r4, rcat[:, :cf])
+            self._conv2d(left_image, r + ".conv2.0", 2, out=half2[:B])          # the two images meet in one 2B batch
+            self._conv2d(right_image, r + ".conv2.0", 2, out=half2[B:])
+            self._conv2d(half2, r + ".conv2.1", out=cat2lr[:, c2:])
             self._conv2d(self._conv2d(cat2lr[:, c2:], r + ".conv4.0", 2), r + ".conv4.1", out=lrcat[:, cf:])
             enc_done = torch.cuda.Event()
             enc_done.record(side)
@@ -471,13 +573,12 @@ class TEMPORALSTEREO(nn.Module):
         # ---- precise (1/4): UNet encoder features concatenated to the backbone features
         if side is not main:
             main.wait_event(enc_done)
-            for t in (images, l4, r4):            # read on the side stream: keep the allocator from reusing them early
+            for t in (left_image, right_image, l4, r4):     # read on the side stream: keep the allocator from reusing them early
                 t.record_stream(side)
 
         samples_p = torch.empty((B, 5, H4, W4), device=dev, dtype=torch.float32)
         low_f, high_f = ops.range_samples(d_f, DISP_RANGE, samples_p, 0)
-        raw = ops.block_cost(lcat, rcat, samples_p)
-        vol = self._init3d(raw, "precise.init3d")
+        vol = self._init3d(lcat, rcat, samples_p, "precise.init3d")
         d_p, c_p, o_p, top_disp, top_cost = self._heads_predict(vol, samples_p, "precise.pred_heads",
                                                                 float(self.levels["precise"]["delta"]), True)
         f = self._conv2d(self._conv2d(lcat, r + ".fuse.0"), r + ".fuse.1")
@@ -495,6 +596,16 @@ class TEMPORALSTEREO(nn.Module):
         }
         return ([full, d_p, d_f, d_c], [c_p, c_f, c_c], [samples_p, s_f, s_c], [o_p, o_f, o_c],
                 [{"low": low_f, "high": high_f}, {"low": low_c, "high": high_c}], prev_info)
+
+    def forward(self, left_feats: List[torch.Tensor], right_feats: List[torch.Tensor], left_image: torch.Tensor,
+                right_image: torch.Tensor, prev_info: Optional[dict] = None):
+        if prev_info is None:
+            prev_info = {}
+        if torch.is_grad_enabled() and any(t.requires_grad for t in list(left_feats) + list(right_feats)):
+            raise NotImplementedError("libtstereo TEMPORALSTEREO has no backward: call it under torch.no_grad() or with "
+                                      "detached features (the reference runs its history frames the same way, "
+                                      "projects/TemporalStereo/TemporalStereo.py:268-274)")
+        return self._forward(left_feats, right_feats, left_image, right_image, prev_info)
 
 
 def build_aggregation(cfg) -> nn.Module:

@@ -18,6 +18,7 @@
 //  * resize kernel: bilinear align_corners up-sampling of G1, G2 into the last 2*C/8 planes,
 //    four output columns per thread.
 #include "common.cuh"
+#include "cost_coord.cuh"
 
 namespace tstereo {
 
@@ -48,7 +49,9 @@ __device__ __forceinline__ void stg4_if(float* p, float a, float b, float c, flo
 // (inverse_warp_3d.py:46 + grid_sampler_unnormalize) lands up to ~1e-6 px off the integer row on
 // ~20 % of the rows, which would blend two rows with weights (1-eps, eps); the kernel samples the
 // nearer row only (deviation <= 2e-6 * |R|, far below the fp32 noise of the following contraction).
-template <bool WARP, bool VEC>
+// GONLY: only the three group-wise terms are produced, into a compact [B, 3G, D, H, W] volume (`out`): the form the
+// fused cost -> first-conv path uses (the L / R_d / -(L-R_d)^2 planes are rebuilt by that conv's producer).
+template <bool WARP, bool VEC, bool GONLY>
 __global__ void __launch_bounds__(128)
 block_cost_main_kernel(const float* __restrict__ L, const float* __restrict__ R,
                        const float* __restrict__ smp, float* __restrict__ out,
@@ -64,7 +67,7 @@ block_cost_main_kernel(const float* __restrict__ L, const float* __restrict__ R,
     const int x = (blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7)) * 4;       // first of the 4 pixels
     const int y = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
     const int HW = H * W;
-    const int outC = (WARP ? 2 * C : C) + 3 * G;
+    const int outC = GONLY ? 3 * G : (WARP ? 2 * C : C) + 3 * G;
     const bool rowin = y < H;
     bool pin[4];
 #pragma unroll
@@ -81,14 +84,8 @@ block_cost_main_kernel(const float* __restrict__ L, const float* __restrict__ R,
         wb[k] = 0.f;
     }
     if (WARP) {
-        // same op sequence as inverse_warp_3d.py:40-47 + ATen grid_sampler_unnormalize
-        const float Hm1 = (float)(H - 1), Wm1 = (float)(W - 1);
-        const float gyn = __fsub_rn(__fmul_rn(__fdiv_rn((float)yc, Hm1), 2.0f), 1.0f);
-        const float iy = __fmul_rn(__fdiv_rn(__fadd_rn(gyn, 1.0f), 2.0f), Hm1);
-        const float fy = floorf(iy);
-        int yn = (int)fy;
-        if (__fsub_rn(iy, fy) > 0.5f) yn += 1;    // nearer of the two rows grid_sample would blend
-        yn = min(max(yn, 0), H - 1);
+        // same op sequence as inverse_warp_3d.py:40-47 + ATen grid_sampler_unnormalize (cost_coord.cuh)
+        const int yn = warp_row(yc, H);
         const float* sp = smp + ((size_t)(b * D + d) * H + yc) * W;
         float dsp[4];
         if (VEC) {
@@ -100,25 +97,8 @@ block_cost_main_kernel(const float* __restrict__ L, const float* __restrict__ R,
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const float gx = __fadd_rn((float)(x + k), -dsp[k]);
-            const float gn = __fsub_rn(__fmul_rn(__fdiv_rn(gx, Wm1), 2.0f), 1.0f);
-            const float ix = __fmul_rn(__fdiv_rn(__fadd_rn(gn, 1.0f), 2.0f), Wm1);
-            const float fx = floorf(ix);
-            int xa = 0;
-            if (pin[k] && fx >= -1.0f && fx <= Wm1) {
-                xa = (int)fx;
-                wa[k] = __fsub_rn(fx + 1.0f, ix);
-                wb[k] = __fsub_rn(ix, fx);
-                if (xa < 0) {                     // tap 0 left of the image: read columns 0,1 as (tap1, unused)
-                    xa = 0;
-                    wa[k] = wb[k];
-                    wb[k] = 0.f;
-                } else if (xa + 1 >= W) {         // tap 1 right of the image: read columns W-2,W-1 as (unused, tap0)
-                    xa = W - 2;
-                    wb[k] = wa[k];
-                    wa[k] = 0.f;
-                }
-            }
+            int xa;
+            warp_col(x + k, dsp[k], W, pin[k], xa, wa[k], wb[k]);
             off[k] = yn * W + xa;
         }
     } else {
@@ -175,7 +155,8 @@ block_cost_main_kernel(const float* __restrict__ L, const float* __restrict__ R,
             e[k] = l[k] - rv[k];                 // 0 outside the image (l = 0, weights = 0)
             a0[k] = fmaf(e[k], e[k], a0[k]);
         }
-        if (VEC) {
+        if (GONLY) {
+        } else if (VEC) {
             if (pin[0]) {
                 if (WARP) {
                     *reinterpret_cast<float4*>(o1) = make_float4(l[0], l[1], l[2], l[3]);
@@ -213,7 +194,7 @@ block_cost_main_kernel(const float* __restrict__ L, const float* __restrict__ R,
     }
     (void)lmask;
 
-    const int base = WARP ? 2 * C : C;
+    const int base = GONLY ? 0 : (WARP ? 2 * C : C);
     const int H1 = H >> 1, W1 = W >> 1, H2 = H >> 2, W2 = W >> 2;
     float* og = out + (((size_t)b * outC + base + g) * D + d) * HW + pix;
     if (VEC) {
@@ -312,7 +293,7 @@ static inline float host_ac_scale(int in_size, int out_size) {
     return out_size > 1 ? (float)(in_size - 1) / (float)(out_size - 1) : 0.0f;   // IEEE fp32 divide == __fdiv_rn
 }
 
-static int block_cost_launch(bool warp, const float* L, const float* R, const float* smp, float* out,
+static int block_cost_launch(bool warp, bool gonly, const float* L, const float* R, const float* smp, float* out,
                              float* scratch, int B, int C, int H, int W, int D, cudaStream_t st) {
     TS_REQUIRE(L && R && out && scratch, "block_cost: null pointer");
     TS_REQUIRE(!warp || smp, "block_cost_warp: null samples");
@@ -326,7 +307,8 @@ static int block_cost_launch(bool warp, const float* L, const float* R, const fl
     float* g2 = scratch + (size_t)B * G * D * H1 * W1;
     const bool vec = (W % 4 == 0) && (((size_t)L | (size_t)out | (size_t)(smp ? smp : L)) & 15) == 0;
     dim3 grid(cdiv(W, 64), cdiv(H, 8), B * G * D);
-#define TS_BC(WP, VC) block_cost_main_kernel<WP, VC><<<grid, 128, 0, st>>>(L, R, smp, out, g1, g2, C, H, W, D)
+#define TS_BC(WP, VC) (gonly ? block_cost_main_kernel<WP, VC, true><<<grid, 128, 0, st>>>(L, R, smp, out, g1, g2, C, H, W, D) \
+                             : block_cost_main_kernel<WP, VC, false><<<grid, 128, 0, st>>>(L, R, smp, out, g1, g2, C, H, W, D))
     if (warp) {
         if (vec) TS_BC(true, true); else TS_BC(true, false);
     } else {
@@ -335,11 +317,12 @@ static int block_cost_launch(bool warp, const float* L, const float* R, const fl
 #undef TS_BC
     int rc = check_launch("block_cost_main");
     if (rc) return rc;
-    const int outC = (warp ? 2 * C : C) + 3 * G;
+    const int base = gonly ? 0 : (warp ? 2 * C : C);
+    const int outC = base + 3 * G;
     const int tx = cdiv(W, 4) <= 32 ? 32 : (cdiv(W, 4) <= 64 ? 64 : 128);
     dim3 rblock(tx, 128 / tx);
     dim3 rgrid(cdiv(cdiv(W, 4), tx), cdiv(H, (int)rblock.y), B * G);
-    block_cost_resize_kernel<<<rgrid, rblock, 0, st>>>(g1, g2, out, G, D, H, W, outC, warp ? 2 * C : C,
+    block_cost_resize_kernel<<<rgrid, rblock, 0, st>>>(g1, g2, out, G, D, H, W, outC, base,
                                                     host_ac_scale(H / 2, H), host_ac_scale(W / 2, W),
                                                     host_ac_scale(H / 4, H), host_ac_scale(W / 4, W));
     return check_launch("block_cost_resize");
@@ -356,12 +339,23 @@ long long tstereo_block_cost_scratch_floats(int B, int C, int H, int W, int D) {
 
 int tstereo_block_cost_shift(const float* left, const float* right, float* out, float* scratch,
                              int B, int C, int H, int W, int D, void* stream) {
-    return tstereo::block_cost_launch(false, left, right, nullptr, out, scratch, B, C, H, W, D, (cudaStream_t)stream);
+    return tstereo::block_cost_launch(false, false, left, right, nullptr, out, scratch, B, C, H, W, D, (cudaStream_t)stream);
 }
 
 int tstereo_block_cost_warp(const float* left, const float* right, const float* samples, float* out,
                             float* scratch, int B, int C, int H, int W, int S, void* stream) {
-    return tstereo::block_cost_launch(true, left, right, samples, out, scratch, B, C, H, W, S, (cudaStream_t)stream);
+    return tstereo::block_cost_launch(true, false, left, right, samples, out, scratch, B, C, H, W, S, (cudaStream_t)stream);
+}
+
+/* group-wise terms only (compact [B, 3C/8, D, H, W]): the side input of the fused cost -> first-conv path */
+int tstereo_group_cost_shift(const float* left, const float* right, float* gvol, float* scratch,
+                             int B, int C, int H, int W, int D, void* stream) {
+    return tstereo::block_cost_launch(false, true, left, right, nullptr, gvol, scratch, B, C, H, W, D, (cudaStream_t)stream);
+}
+
+int tstereo_group_cost_warp(const float* left, const float* right, const float* samples, float* gvol,
+                            float* scratch, int B, int C, int H, int W, int S, void* stream) {
+    return tstereo::block_cost_launch(true, true, left, right, samples, gvol, scratch, B, C, H, W, S, (cudaStream_t)stream);
 }
 
 }  // extern "C"

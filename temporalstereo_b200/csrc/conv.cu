@@ -190,20 +190,25 @@ static int launch_hw3(const float* in, long long isB, long long isC, long long i
 }
 
 // --------------------------------------------------------------------------- conv along D
-// thread = 2 pixels x COB couts for one (b, d_out); weights [Cin][K][COB] in shared memory
-// (warp-broadcast LDS.128), activations straight from global (coalesced along H*W).
-template <int K, int COB>
+// thread = PPT pixels x COB couts for one (b, d_out); weights [Cin][K][COB] in shared memory
+// (warp-broadcast LDS.128), activations straight from global (coalesced along H*W).  The loads of CIB
+// input channels x K taps are issued together before their FMAs: the layers that run here are the small
+// hourglass volumes (a few hundred CTAs at most), where one dependent load per FMA group was a pure
+// latency chain.  Small volumes use the (PPT = 1, 128 threads) form so the grid still covers the SMs.
+template <int K, int COB, int PPT>
 __global__ void __launch_bounds__(256)
 conv_d_kernel(const float* __restrict__ in, long long isB, long long isC, long long isD,
               float* __restrict__ out, long long osB, long long osC, long long osD,
               const float* __restrict__ w, const float* __restrict__ bias,
               int Cin, int Cout, int CoutP, int Din, int HW, int stride, int dil, int transposed, int act) {
     extern __shared__ __align__(16) float ws[];   // [Cin][K][COB]
+    constexpr int CIB = (COB >= 32 || PPT == 2) ? 4 : 8;   // input channels whose loads are in flight together
+    const int NT = blockDim.x;
     const int CB = (Cout + COB - 1) / COB;
     const int cb = blockIdx.z % CB, b = blockIdx.z / CB;
     const int co0 = cb * COB;
     const int dout = blockIdx.y;
-    for (int i = threadIdx.x; i < Cin * K * (COB / 4); i += 256) {
+    for (int i = threadIdx.x; i < Cin * K * (COB / 4); i += NT) {
         const int q4 = i % (COB / 4);
         const int t = i / (COB / 4);
         const int co = co0 + q4 * 4;
@@ -211,15 +216,24 @@ conv_d_kernel(const float* __restrict__ in, long long isB, long long isC, long l
         if (co < CoutP) v = *reinterpret_cast<const float4*>(w + (long long)t * CoutP + co);
         *reinterpret_cast<float4*>(ws + t * COB + q4 * 4) = v;
     }
-    __syncthreads();
 
-    const int p0 = blockIdx.x * 512 + threadIdx.x, p1 = p0 + 256;
-    const bool ok0 = p0 < HW, ok1 = p1 < HW;
-    float a0[COB], a1[COB];
+    int px[PPT];
+    bool ok[PPT];
 #pragma unroll
-    for (int q = 0; q < COB; ++q) a0[q] = a1[q] = 0.f;
+    for (int q = 0; q < PPT; ++q) {
+        px[q] = blockIdx.x * (NT * PPT) + q * NT + threadIdx.x;
+        ok[q] = px[q] < HW;
+        px[q] = min(px[q], HW - 1);              // always a legal address; the store is guarded
+    }
+    float acc[PPT][COB];
+#pragma unroll
+    for (int q = 0; q < PPT; ++q)
+#pragma unroll
+        for (int c = 0; c < COB; ++c) acc[q][c] = 0.f;
 
-    int di[K];
+    // input plane of tap k for this output plane (or -1); uniform across the CTA
+    long long doff[K];
+    bool dok[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         int v;
@@ -229,39 +243,52 @@ conv_d_kernel(const float* __restrict__ in, long long isB, long long isC, long l
         } else {
             v = dout * stride - dil * (K / 2) + k * dil;
         }
-        di[k] = (v >= 0 && v < Din) ? v : -1;
+        dok[k] = v >= 0 && v < Din;
+        doff[k] = dok[k] ? (long long)v * isD : 0ll;
     }
     const float* ib = in + (long long)b * isB;
-    for (int ci = 0; ci < Cin; ++ci) {
+    __syncthreads();
+    for (int ci0 = 0; ci0 < Cin; ci0 += CIB) {
+        float v[CIB][K][PPT];
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            if (di[k] < 0) continue;             // uniform across the CTA
-            const float* src = ib + (long long)ci * isC + (long long)di[k] * isD;
-            const float v0 = ok0 ? __ldg(src + p0) : 0.f;
-            const float v1 = ok1 ? __ldg(src + p1) : 0.f;
-            const float4* wp = reinterpret_cast<const float4*>(ws + (ci * K + k) * COB);
+        for (int u = 0; u < CIB; ++u) {
+            const bool cok = ci0 + u < Cin;
+            const float* src = ib + (long long)(cok ? ci0 + u : ci0) * isC;
 #pragma unroll
-            for (int q4 = 0; q4 < COB / 4; ++q4) {
-                const float4 t = wp[q4];
-                a0[q4 * 4 + 0] = fmaf(v0, t.x, a0[q4 * 4 + 0]);
-                a0[q4 * 4 + 1] = fmaf(v0, t.y, a0[q4 * 4 + 1]);
-                a0[q4 * 4 + 2] = fmaf(v0, t.z, a0[q4 * 4 + 2]);
-                a0[q4 * 4 + 3] = fmaf(v0, t.w, a0[q4 * 4 + 3]);
-                a1[q4 * 4 + 0] = fmaf(v1, t.x, a1[q4 * 4 + 0]);
-                a1[q4 * 4 + 1] = fmaf(v1, t.y, a1[q4 * 4 + 1]);
-                a1[q4 * 4 + 2] = fmaf(v1, t.z, a1[q4 * 4 + 2]);
-                a1[q4 * 4 + 3] = fmaf(v1, t.w, a1[q4 * 4 + 3]);
+            for (int k = 0; k < K; ++k)
+#pragma unroll
+                for (int q = 0; q < PPT; ++q) v[u][k][q] = (cok && dok[k]) ? __ldg(src + doff[k] + px[q]) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < CIB; ++u) {
+            if (ci0 + u >= Cin) break;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                if (!dok[k]) continue;           // uniform across the CTA
+                const float4* wp = reinterpret_cast<const float4*>(ws + ((ci0 + u) * K + k) * COB);
+#pragma unroll
+                for (int q4 = 0; q4 < COB / 4; ++q4) {
+                    const float4 t = wp[q4];
+#pragma unroll
+                    for (int q = 0; q < PPT; ++q) {
+                        acc[q][q4 * 4 + 0] = fmaf(v[u][k][q], t.x, acc[q][q4 * 4 + 0]);
+                        acc[q][q4 * 4 + 1] = fmaf(v[u][k][q], t.y, acc[q][q4 * 4 + 1]);
+                        acc[q][q4 * 4 + 2] = fmaf(v[u][k][q], t.z, acc[q][q4 * 4 + 2]);
+                        acc[q][q4 * 4 + 3] = fmaf(v[u][k][q], t.w, acc[q][q4 * 4 + 3]);
+                    }
+                }
             }
         }
     }
     float* ob = out + (long long)b * osB + (long long)dout * osD;
 #pragma unroll
-    for (int q = 0; q < COB; ++q) {
-        const int co = co0 + q;
+    for (int c = 0; c < COB; ++c) {
+        const int co = co0 + c;
         if (co >= Cout) continue;
         const float bv = bias ? __ldg(bias + co) : 0.f;
-        if (ok0) ob[(long long)co * osC + p0] = apply_act(a0[q] + bv, act);
-        if (ok1) ob[(long long)co * osC + p1] = apply_act(a1[q] + bv, act);
+#pragma unroll
+        for (int q = 0; q < PPT; ++q)
+            if (ok[q]) ob[(long long)co * osC + px[q]] = apply_act(acc[q][c] + bv, act);
     }
 }
 
@@ -269,31 +296,36 @@ template <int K, int COB>
 static int launch_d(const float* in, long long isB, long long isC, long long isD, float* out, long long osB,
                     long long osC, long long osD, const float* w, const float* bias, int B, int Cin, int Cout,
                     int Din, int Dout, int HW, int stride, int dil, int transposed, int act, cudaStream_t st) {
-    auto kern = conv_d_kernel<K, COB>;
     const int smem = Cin * K * COB * 4;
     TS_REQUIRE(smem <= 200 * 1024, "conv_d: weight slab of %d B does not fit shared memory", smem);
-    static int attr_max = 48 * 1024;
-    if (smem > attr_max) {
+    const int CB = cdiv(Cout, COB);
+    TS_REQUIRE(Dout <= 65535 && (long long)B * CB <= 65535, "conv_d: grid too large");
+    // 512-pixel CTAs (2 px / thread) when they already give every SM two CTAs; otherwise 128-pixel CTAs
+    const bool small = (long long)cdiv(HW, 512) * Dout * B * CB < 2 * 148;
+    auto kern = small ? conv_d_kernel<K, COB, 1> : conv_d_kernel<K, COB, 2>;
+    static int attr_max[2] = {48 * 1024, 48 * 1024};
+    if (smem > attr_max[small]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) {
             set_error("conv_d: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return TSTEREO_E_CUDA;
         }
-        attr_max = 200 * 1024;
+        attr_max[small] = 200 * 1024;
     }
-    const int CB = cdiv(Cout, COB);
-    TS_REQUIRE(Dout <= 65535 && (long long)B * CB <= 65535, "conv_d: grid too large");
-    dim3 grid(cdiv(HW, 512), Dout, B * CB);
+    const int nt = small ? 128 : 256, ppt = small ? 1 : 2;
+    dim3 grid(cdiv(HW, nt * ppt), Dout, B * CB);
     const int CoutP = (Cout + 3) & ~3;
-    kern<<<grid, 256, smem, st>>>(in, isB, isC, isD, out, osB, osC, osD, w, bias, Cin, Cout, CoutP, Din, HW, stride,
-                                  dil, transposed, act);
+    kern<<<grid, nt, smem, st>>>(in, isB, isC, isD, out, osB, osC, osD, w, bias, Cin, Cout, CoutP, Din, HW, stride,
+                                 dil, transposed, act);
     return check_launch("conv_d");
 }
 
 // --------------------------------------------------------------------------- transposed conv over (H,W)
 // stride 2, padding 1; KS=3 (output_padding 1) or KS=4.  Gather form: thread = one output row y,
-// the output column pair (2j, 2j+1), COB couts.  Row parity is uniform per warp and column parity is
-// unrolled, so the tap -> weight index is warp-uniform (broadcast LDS) and divergence-free.
+// the output column pair (2j, 2j+1), COB couts.  out[y] = sum_ky in[(y + 1 - ky) / 2] * w[ky] over the
+// ky of the parity of y + 1 (at most two input rows, warp-uniform); along x the pair reads the input
+// columns j-1, j, j+1 with compile-time tap indices.  The loads of CIB input channels are issued
+// together before their FMAs (these layers are small: latency, not throughput, is what they wait on).
 template <int KS, int COB>
 __global__ void __launch_bounds__(256)
 deconv_hw_kernel(const float* __restrict__ in, long long isB, long long isC, long long isD,
@@ -301,6 +333,7 @@ deconv_hw_kernel(const float* __restrict__ in, long long isB, long long isC, lon
                  const float* __restrict__ w, const float* __restrict__ bias,
                  int Cin, int Cout, int CoutP, int D, int Hin, int Win, int act) {
     extern __shared__ __align__(16) float ws[];   // [Cin][KS*KS][COB]
+    constexpr int CIB = 4;
     const int CB = (Cout + COB - 1) / COB;
     const int cb = blockIdx.z % CB, n = blockIdx.z / CB;
     const int b = n / D, d = n % D;
@@ -324,37 +357,68 @@ deconv_hw_kernel(const float* __restrict__ in, long long isB, long long isC, lon
 #pragma unroll
     for (int q = 0; q < COB; ++q) acc[0][q] = acc[1][q] = 0.f;
 
+    // row slots s = 0, 1: ky = kpar + 2 s, input row (y + 1 - ky) / 2
+    const int kpar = (y + 1) & 1;
+    int roff[2], kyv[2];
+    bool rok[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const int ky = kpar + 2 * s;
+        const int iy = (y + 1 - ky) >> 1;        // y + 1 - ky is even and >= -2
+        rok[s] = ky < KS && (y + 1 - ky) >= 0 && iy < Hin;
+        roff[s] = rok[s] ? iy * Win : 0;
+        kyv[s] = ky;
+    }
+    // columns j-1, j, j+1 (clamped address, zero value outside)
+    const bool cok[3] = {j >= 1, true, j + 1 < Win};
+    const int coff[3] = {max(j - 1, 0), j, min(j + 1, Win - 1)};
+
     const float* ib = in + (long long)b * isB + (long long)d * isD;
-    for (int ci = 0; ci < Cin; ++ci) {
-        const float* ip = ib + (long long)ci * isC;
+    for (int ci0 = 0; ci0 < Cin; ci0 += CIB) {
+        float v[CIB][2][3];
 #pragma unroll
-        for (int ky = 0; ky < KS; ++ky) {
-            const int ty = y + 1 - ky;             // y = iy*2 - 1 + ky
-            if (ty < 0 || (ty & 1)) continue;
-            const int iy = ty >> 1;
-            if (iy >= Hin) continue;
-            const float* row = ip + (long long)iy * Win;
+        for (int u = 0; u < CIB; ++u) {
+            const bool chok = ci0 + u < Cin;
+            const float* ip = ib + (long long)(chok ? ci0 + u : ci0) * isC;
 #pragma unroll
-            for (int px = 0; px < 2; ++px)
+            for (int s = 0; s < 2; ++s)
 #pragma unroll
-                for (int kx = 0; kx < KS; ++kx) {
-                    constexpr int dummy = 0;
-                    (void)dummy;
-                    const int tx = px + 1 - kx;      // relative to 2j; compile-time after unrolling
-                    if (tx & 1) continue;
-                    const int ix = j + (tx >= 0 ? (tx >> 1) : -((-tx) >> 1));
-                    if (ix < 0 || ix >= Win) continue;
-                    const float v = __ldg(row + ix);
-                    const float4* wp = reinterpret_cast<const float4*>(ws + (ci * KS * KS + ky * KS + kx) * COB);
-#pragma unroll
-                    for (int q4 = 0; q4 < COB / 4; ++q4) {
-                        const float4 t = wp[q4];
-                        acc[px][q4 * 4 + 0] = fmaf(v, t.x, acc[px][q4 * 4 + 0]);
-                        acc[px][q4 * 4 + 1] = fmaf(v, t.y, acc[px][q4 * 4 + 1]);
-                        acc[px][q4 * 4 + 2] = fmaf(v, t.z, acc[px][q4 * 4 + 2]);
-                        acc[px][q4 * 4 + 3] = fmaf(v, t.w, acc[px][q4 * 4 + 3]);
+                for (int c = 0; c < 3; ++c) {
+                    if (KS == 3 && c == 0) {     // a 3-tap kernel never reads column j-1
+                        v[u][s][c] = 0.f;
+                        continue;
                     }
+                    v[u][s][c] = (chok && rok[s] && cok[c]) ? __ldg(ip + roff[s] + coff[c]) : 0.f;
                 }
+        }
+#pragma unroll
+        for (int u = 0; u < CIB; ++u) {
+            if (ci0 + u >= Cin) break;
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                if (!rok[s]) continue;           // warp-uniform
+                const float* wrow = ws + ((ci0 + u) * KS * KS + kyv[s] * KS) * COB;
+#pragma unroll
+                for (int px = 0; px < 2; ++px)
+#pragma unroll
+                    for (int kx = 0; kx < KS; ++kx) {
+                        if ((px + 1 - kx) & 1) continue;         // compile-time after unrolling
+                        // input column j + (px + 1 - kx) / 2 -> slot {j-1, j, j+1}
+                        constexpr int dummy = 0;
+                        (void)dummy;
+                        const int col = 1 + (px + 1 - kx >= 0 ? (px + 1 - kx) / 2 : -((kx - px - 1) / 2));
+                        const float val = v[u][s][col];
+                        const float4* wp = reinterpret_cast<const float4*>(wrow + kx * COB);
+#pragma unroll
+                        for (int q4 = 0; q4 < COB / 4; ++q4) {
+                            const float4 t = wp[q4];
+                            acc[px][q4 * 4 + 0] = fmaf(val, t.x, acc[px][q4 * 4 + 0]);
+                            acc[px][q4 * 4 + 1] = fmaf(val, t.y, acc[px][q4 * 4 + 1]);
+                            acc[px][q4 * 4 + 2] = fmaf(val, t.z, acc[px][q4 * 4 + 2]);
+                            acc[px][q4 * 4 + 3] = fmaf(val, t.w, acc[px][q4 * 4 + 3]);
+                        }
+                    }
+            }
         }
     }
     float* ob = out + (long long)b * osB + (long long)d * osD + (long long)y * Wout + 2 * j;

@@ -1,0 +1,979 @@
+// Tensor-core (tcgen05, sm_100a) 3x3 convolution over (H,W), second generation: 2-D tiles with the kx taps
+// folded into the MMA's N dimension  (SURVEY.md §8 rows a4-a7, a9, a12, a13).
+//
+// ref: architecture/modeling/layers/basic_layers.py:194-235 (Conv3d: conv -> BN -> act) as used by the (1,3,3)
+//      halves of aggregation/TemporalStereo/module.py:111-147 and the 2-D convs of :424-492.
+//
+// Why a second kernel: the first one (conv_tc.cu) issues one MMA pair per tap, i.e. the A operand (128
+// positions x 8 channels) is read from shared memory 18 times per chunk, and its linear position tiles stage a
+// halo of a full image row on both sides.  Here
+//   * a CTA owns a TR x (32 - 2*dil) output tile; the staged input is (TR + 2*dil) rows x 32 columns, position
+//     index = row*32 + col, so one warp-wide TMEM lane quarter is exactly one tile row;
+//   * the three kx taps are columns of the B operand: per ky ONE product
+//         P[pos][kx][co] (+)= A[pos + ky*dil*32][ch] * W[ky][kx][ch][co]
+//     (N = 3*CP), and the output is  out[x] = P[x][kx=0] + P[x+dil][kx=1] + P[x+2*dil][kx=2]  — two warp
+//     shuffles per channel in the epilogue.  A is read 6 times per chunk instead of 18;
+//   * error compensation as before (operands split hi + lo): D[0:2N) += A_hi*[B_hi|B_lo],  D[0:N) += A_lo*B_hi;
+//   * the tensor core's accumulate truncates, so TMEM accumulates only G chunks (3*8*G products
+//     per term) before the producer warps add the partial sums into fp32 registers; the MMA warp moves on to
+//     the next M-tile meanwhile (per-M-tile full/empty barriers instead of a second TMEM buffer);
+//   * producers prefetch the next chunk's 8 channel rows into registers before converting the current one, and
+//     the small variants run two CTAs per SM, so global-load latency overlaps the MMAs of the other CTA.
+//
+//   * two epilogue modes: ACC (above; any Cin) and DIRECT (Cin <= 8*G, i.e. one accumulation group): all three
+//     3xTF32 terms accumulate into the SAME N columns (3 MMAs per ky), TMEM holds MT*N columns, and the epilogue
+//     streams TMEM -> shuffle -> bias/act -> store without register accumulators, so two CTAs fit one SM even
+//     for Cout = 32.
+//
+//   * stride-2 convolutions and stride-2 transposed convolutions run through the SAME kernel as stride-1 3x3
+//     convolutions over a virtual tensor: the input of a stride-2 conv is read as its four (row, column) parity
+//     phases stacked on the channel axis (chunk k -> phase k / cpp: element offset pr*Win + pc, row pitch 2*Win,
+//     x step 2), and a transposed conv writes one output parity phase per launch (output row pitch / x step 2);
+//     the host repacks the weights accordingly (taps that do not exist for a phase are zero).
+//   * (k,1,1) convolutions along D use the same machinery with the k input planes as "phases" (chunk k -> plane
+//     dout*stride + (k/cpp - k_d/2)*dil, zero when outside), one ky tap (nky = 1) and no halo (dil = 0).
+//   * producer modes (template RAW): 0 = the register path above (default: fastest on B200); 1 = TMA (opt-in
+//     TSTEREO_TC2_TMA=1, tf32 split, inputs whose rows are 16-byte aligned and x-dense): one elected lane of the MMA
+//     warp issues `cp.async.bulk.tensor.5d` per chunk — an (x 32|36, y TR+2*dil, plane 1, c 8) box of the NCDHW input
+//     whose origin is rounded down to a multiple of 4 pixels, out-of-image rows / columns / planes / channels
+//     zero-filled by the TMA unit — into a ring of raw fp32 stages which the 8 producer warps read (conflict-free
+//     LDS), split and store as the K-major operand; 2 = the same ring filled by per-thread `cp.async` (opt-in
+//     TSTEREO_TC2_CPA=1, fp16 split, any width).  DESIGN.md §5 has the measurements (both are slower than mode 0).
+//   * F16 variant (template flag, the engine's default): operands split as fp16 hi + fp16 lo (22 mantissa bits,
+//     same three product terms) and multiplied with `kind::f16`: K = 16 channels per MMA instead of 8, i.e. half the
+//     MMAs and half the shared-memory operand traffic per channel (the kernel is shared-memory-pipe bound) at twice
+//     the tensor rate.  Measured EPE vs fp32 on the oracle: 8.0e-6 px (3xTF32: 8.6e-6).  fp16 range: activations
+//     must stay below 65504 in magnitude (the model's are O(1..100)).
+//
+//   * FOLD = 1 (fp16 form of the (k,1,1) convs): a single accumulator column block, N = CP, no shuffles in the epilogue.
+//
+//  warps 0-7 : producers (global NCDHW fp32 -> hi/lo split -> K-major SWIZZLE_NONE smem) + accumulator readers
+//              + epilogue;  warp 8 : TMEM alloc, MMA issue (elect.sync), commits (and the TMA issue in RAW = 1).
+#pragma once
+#include "common.cuh"
+#include "cost_coord.cuh"
+#include "tc_ptx.cuh"
+#include <cuda.h>
+#include <cstdint>
+#include <cstdlib>
+
+namespace tstereo {
+namespace tc2 {
+
+using namespace tcp;
+
+constexpr int NPROD = 256;
+constexpr int NTHREADS = NPROD + 32;
+constexpr int MAX_STAGES = 4;
+constexpr int MAX_MT = 4;
+constexpr size_t SMEM_MAX = 227 * 1024;
+
+struct Params {
+    const float* in;
+    long long isB, isD;
+    float* out;
+    long long osB, osD;
+    int isC, osC;         // channel strides (elements); < 2^31, checked by the host
+    const float* wpack;   // [nchunk][ky nky][khalf 2][row 2N][4], row = part*N + kx*CP + co
+    const float* bias;    // [Cout] or null
+    int Cin, Cout, H, W, D;       // Cin = real channels per input phase; H, W = grid of the (virtual) stride-1 conv
+    int Hin, Win;                 // real input plane (= H, W unless the input is phase-decomposed)
+    int isY, isX;                 // input row pitch / x step in elements (W, 1 | 2*Win, 2)
+    int osY, osX;                 // output row pitch / x step (W, 1 | 2*W.., 2 for one phase of a transposed conv)
+    int cpp;                      // chunks per input phase = ceil(Cin / 8); nchunk = phases * cpp
+    int dil, act, nchunk, G, stages, tiles_x;
+    int rs;                       // TMA variant: raw fp32 stages in flight
+    int bw;                       // TMA variant: box width in elements (32, or 36 when the halo shifts the 16-byte aligned origin)
+    int nbatch;                   // batch size (extent of the TMA view's last dimension)
+    int fold;                     // 3: kx taps folded into N (3x3 forms); 1: single column block ((k,1,1) form)
+    int half;                     // operands as fp16 hi + lo (kind::f16, 16 channels per MMA) instead of tf32 hi + lo
+    int nky;                      // ky taps of the virtual conv: 3, or 1 for the (k,1,1) convs along D
+    int kd, dstride, ddil, Din, dtrans;   // kd > 0: phases are input planes of a conv along D (p.D = Dout)
+    // ---- fused cost volume -> first conv (template FUSE != 0; SURVEY.md §8d "fused path").  The virtual input is the raw
+    // cost volume, never materialised: chunks [0, wchunks) are built from the feature maps (`in` = right features
+    // [B, C, H, W]; FUSE 1: R warped by the per-pixel candidates `smp` [B, D, H, W]; FUSE 2: -(L - R shifted by d)^2 with
+    // `left` [B, C, H, W]), chunks [wchunks, nchunk) are read from the compact group-cost volume `in2` [B, C2, D, H, W].
+    // FUSE 1 adds `add` [B, Cout, H, W] (the D-invariant left-feature half of the conv, computed once) before the bias.
+    const float* smp;
+    const float* left;
+    const float* in2;
+    long long i2sB, i2sD;
+    int i2sC, C2, wchunks;
+    const float* add;
+    long long asB;
+    int asC;
+};
+
+// cvt.rna.tf32.f32 without the NaN/Inf handling ptxas wraps around it (operands here are finite activations)
+__device__ __forceinline__ uint32_t tf32_rna(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (fp16 operands, fp32 accumulate), M = 128, K = 16
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// instruction descriptor: D fp32, A/B fp16, both K-major, M = 128, N = n
+__host__ __device__ constexpr uint32_t idesc_f16(uint32_t n) { return (1u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24); }
+// two floats -> packed fp16x2 (low half = a).  satfinite: a value beyond the fp16 range clamps to +-65504 (and its
+// lo part likewise) instead of turning the whole accumulation into inf - inf = NaN
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t h) {
+    float2 f;
+    asm("{\n\t.reg .b16 l, u;\n\tmov.b32 {l, u}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, u;\n\t}" : "=f"(f.x), "=f"(f.y) : "r"(h));
+    return f;
+}
+
+// Activation of the epilogue, compile-time selected (the epilogue is instruction-bound).  SiLU uses
+// ex2.approx / rcp.approx (~1e-6 relative); the full-precision expf + IEEE division of silu_f cost ~50
+// instructions per output.
+template <int ACT>
+__device__ __forceinline__ float act_t(float x) {
+    if constexpr (ACT == TSTEREO_ACT_SILU) {
+        float e, r;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+        return x * r;
+    } else if constexpr (ACT == TSTEREO_ACT_RELU) {
+        return fmaxf(x, 0.0f);
+    } else {
+        return x;
+    }
+}
+
+// kx shift-sum + bias + activation + store of 8 channels of one tile row (lane = tile column):
+// out[x] = P0[x] + P1[x + dil] + P2[x + 2*dil]
+// FOLD = 3: the kx taps are columns of the accumulator (3x3 convs); FOLD = 1: one column block (the 1x1 / (k,1,1) form)
+template <int ACT, int FOLD>
+__device__ __forceinline__ void epi_store8(const float (&a0)[8], const float (&a1)[8], const float (&a2)[8], int dil, float* o,
+                                           int osC, const float* bias, int co0, int Cout, bool ok, const float* add = nullptr,
+                                           int asC = 0) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        float acc = a0[c];
+        if constexpr (FOLD == 3) {
+            acc += __shfl_down_sync(0xffffffffu, a1[c], dil);
+            acc += __shfl_down_sync(0xffffffffu, a2[c], 2 * dil);
+        }
+        const bool live = ok && co0 + c < Cout;
+        float pre = acc + (co0 + c < Cout ? __ldg(bias + c) : 0.f);
+        if (add) pre += live ? __ldg(add + (long long)c * asC) : 0.f;
+        const float r = act_t<ACT>(pre);
+        if (live) o[c * osC] = r;
+    }
+}
+template <int ACT, int CP, int FOLD>
+__device__ __forceinline__ void epi_direct(uint32_t taddr, int dil, float* o, int osC, const float* bias, int Cout, bool ok) {
+#pragma unroll
+    for (int c0 = 0; c0 < CP; c0 += 8) {
+        uint32_t r0[8], r1[8], r2[8];
+        tmem_ld8(taddr + (uint32_t)c0, r0);
+        if constexpr (FOLD == 3) {
+            tmem_ld8(taddr + (uint32_t)(CP + c0), r1);
+            tmem_ld8(taddr + (uint32_t)(2 * CP + c0), r2);
+        }
+        tmem_ld_wait();
+        float a0[8], a1[8], a2[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            a0[c] = __uint_as_float(r0[c]);
+            a1[c] = FOLD == 3 ? __uint_as_float(r1[c]) : 0.f;
+            a2[c] = FOLD == 3 ? __uint_as_float(r2[c]) : 0.f;
+        }
+        epi_store8<ACT, FOLD>(a0, a1, a2, dil, o + (long long)c0 * osC, osC, bias + c0, c0, Cout, ok);
+    }
+}
+template <int ACT, int CP, int FOLD>
+__device__ __forceinline__ void epi_acc(const float* acc, int dil, float* o, int osC, const float* bias, int Cout, bool ok,
+                                        const float* add = nullptr, int asC = 0) {
+#pragma unroll
+    for (int c0 = 0; c0 < CP; c0 += 8) {
+        float a0[8], a1[8], a2[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            a0[c] = acc[c0 + c];
+            a1[c] = FOLD == 3 ? acc[(FOLD == 3 ? CP : 0) + c0 + c] : 0.f;
+            a2[c] = FOLD == 3 ? acc[(FOLD == 3 ? 2 * CP : 0) + c0 + c] : 0.f;
+        }
+        epi_store8<ACT, FOLD>(a0, a1, a2, dil, o + (long long)c0 * osC, osC, bias + c0, c0, Cout, ok,
+                              add ? add + (long long)c0 * asC : nullptr, asC);
+    }
+}
+
+template <int CP, int MT, bool DIRECT, int FOLD = 3>
+struct Cfg {
+    static constexpr int N = FOLD * CP;                // columns of one part block: [kx][co]
+    static constexpr int N2 = (N + 15) / 16 * 16;      // width of an N-wide MMA (M = 128 needs N % 16 == 0)
+    static constexpr int TS = DIRECT ? N2 : 2 * N;     // TMEM columns of one M-tile: ACC [A*B_hi (N) | A_hi*B_lo (N)]
+    static constexpr int COLS = MT * TS;
+    static constexpr int JT = (MT + 1) / 2;            // M-tiles drained per thread (tiles j = half + 2*jj)
+    static constexpr int MINB = (DIRECT || JT * N <= 48) ? 2 : 1;
+    static constexpr int RPW = (4 * MT + 4 + 7) / 8;   // staged rows per producer warp (dil <= 2)
+    static constexpr uint32_t NCOLS = COLS <= 32 ? 32 : COLS <= 64 ? 64 : COLS <= 128 ? 128 : COLS <= 256 ? 256 : 512;
+    static constexpr uint32_t B_BYTES = 3u * 2u * 2u * N * 16u;
+    static_assert(2 * N <= 256 && COLS <= 512, "tile does not fit one MMA / TMEM");
+};
+
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                            int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+
+constexpr int MAX_RS = 8;
+
+// RAW: 0 = chunks are prefetched into registers; 1 = TMA boxes into a raw fp32 ring; 2 = per-thread cp.async (zero-fill)
+// into the same ring, `rs` chunks deep — for the small, latency-bound layers (any width / alignment)
+// FUSE: 0 = the input is a tensor; 1 / 2 = the input is the warp / shift cost volume built on the fly (see Params)
+template <int CP, int MT, bool DIRECT, int RAW, bool F16, int FOLD, int FUSE = 0>
+__global__ void __launch_bounds__(NTHREADS, Cfg<CP, MT, DIRECT, FOLD>::MINB)
+conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
+    static_assert(FUSE == 0 || (RAW == 0 && FOLD == 3 && !DIRECT), "the fused cost producer is the register path of the 3x3 ACC form");
+    constexpr bool TMA = RAW == 1, CPA = RAW == 2;
+    using C = Cfg<CP, MT, DIRECT, FOLD>;
+    constexpr int N = C::N, JT = C::JT, RPW = C::RPW;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int SR = 4 * MT + 2 * p.dil;                 // staged rows
+    const uint32_t NPOS = (uint32_t)SR * 32u;
+    const uint32_t a_bytes = 4u * NPOS * 16u;          // [part 2][khalf 2][NPOS][16 B]
+    const uint32_t stage_bytes = a_bytes + C::B_BYTES;
+    const uint32_t b_bytes = (uint32_t)p.nky * (C::B_BYTES / 3u);   // weight bytes of one chunk actually used
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    uint64_t* full = bars;                         // [stages]  producers -> MMA
+    uint64_t* empty = bars + MAX_STAGES;           // [stages]  MMA -> producers
+    uint64_t* acc_full = bars + 2 * MAX_STAGES;    // [MT]      MMA -> readers (a group of G chunks accumulated)
+    uint64_t* acc_empty = acc_full + MAX_MT;       // [MT]      readers -> MMA (M-tile drained)
+    uint64_t* raw_full = acc_empty + MAX_MT;       // [rs]      TMA -> producers (raw fp32 chunk landed)
+    uint64_t* raw_empty = raw_full + MAX_RS;       // [rs]      producers -> TMA issuer (raw stage read)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + MAX_RS);
+    uint8_t* raw_base = reinterpret_cast<uint8_t*>(bars) + 384;    // TMA variant: [rs][c 8][row SR][x bw] fp32
+    const uint32_t raw_bytes = 32u * (uint32_t)p.bw * (uint32_t)SR;   // p.bw = 32 for the cp.async ring
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int plane = blockIdx.y;
+    const int b = plane / p.D, d = plane - b * p.D;
+    const int ty = blockIdx.x / p.tiles_x, tx = blockIdx.x - ty * p.tiles_x;
+    const int VW = 32 - 2 * p.dil;                     // valid output columns of a tile
+    const int y0 = ty * 4 * MT, x0 = tx * VW;
+
+    if (tid == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full[s], NPROD + 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int j = 0; j < MT; ++j) {
+            mbar_init(&acc_full[j], 1);
+            mbar_init(&acc_empty[j], NPROD / 2);
+        }
+        if constexpr (TMA) {
+            for (int i = 0; i < p.rs; ++i) {
+                mbar_init(&raw_full[i], 1);
+                mbar_init(&raw_empty[i], NPROD / 32);
+            }
+        }
+        if constexpr (CPA)
+            for (int i = 0; i < p.rs; ++i) mbar_init(&raw_full[i], NPROD);    // one cp.async arrival per producer thread
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == NPROD / 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(C::NCOLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int nmma = F16 ? (p.nchunk + 1) / 2 : p.nchunk;     // MMA chunks (16 | 8 channels); p.nchunk counts 8-channel units
+    const int ngroups = (nmma + p.G - 1) / p.G;
+
+// TMA variant: the MMA warp keeps `rs` chunk loads in flight; chunk kk -> (phase, channel chunk) -> box coordinates
+    int t_issue = 0;
+    auto issue_tma = [&]() {        // MMA warp only, converged
+        const int kk = t_issue++;
+        const int rsl = kk % p.rs;
+        mbar_wait(&raw_empty[rsl], (((uint32_t)(kk / p.rs)) & 1u) ^ 1u);
+        if (elect_one()) {
+            const int phase = kk / p.cpp, kc = kk - phase * p.cpp;
+            int dd = d;
+            if (p.kd) {
+                if (p.dtrans) {         // transposed k3 s2 p1 op1: dout = 2*din - 1 + tap
+                    const int t2 = d + 1 - phase;
+                    dd = (t2 >= 0 && (t2 & 1) == 0) ? (t2 >> 1) : -1;
+                } else {
+                    dd = d * p.dstride + (phase - p.kd / 2) * p.ddil;
+                }
+                if (dd < 0 || dd >= p.Din) dd = -1;       // outside: the TMA unit fills zeros
+            }
+            mbar_arrive_expect_tx(&raw_full[rsl], raw_bytes);
+            // the box origin must be 16-byte aligned in global memory: start at the multiple of 4 below x0 - dil
+            tma_load_5d(raw_base + (size_t)rsl * raw_bytes, &tmap, &raw_full[rsl], (x0 - p.dil) & ~3, y0 - p.dil, dd, kc * 8, b);
+        }
+        __syncwarp();
+    };
+    if (warp < NPROD / 32) {
+        // ===================== producers / accumulator readers =====================
+        const int quarter = warp & 3;                 // TMEM lane quarter = tile row inside an M-tile
+        const int half = warp >> 2;                   // which M-tiles this warp drains
+        const float* in_pl = p.in + (long long)b * p.isB + (p.kd ? 0ll : (long long)d * p.isD);
+        // the staged rows of this warp: r = warp + 8*u; lane = staged column
+        int off[RPW];               // element offset of (row, lane) in phase (0,0), or -1
+        int edge = 0;               // bit u: row r's odd-row phase lies below the input; bit 31: same for the column
+        {
+            const int gx = x0 - p.dil + lane;
+            if (p.isX * gx + 1 >= p.Win) edge |= 1 << 31;
+#pragma unroll
+            for (int u = 0; u < RPW; ++u) {
+                const int r = warp + 8 * u;
+                const int gy = y0 - p.dil + r;
+                off[u] = (r < SR && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) ? gy * p.isY + gx * p.isX : -1;
+                if (p.isX * gy + 1 >= p.Hin) edge |= 1 << u;
+            }
+        }
+        // fused cost producer: per staged position the right-feature tap (offset inside a channel plane, two weights)
+        int woff[FUSE ? RPW : 1];
+        float wa[FUSE ? RPW : 1], wb[FUSE == 1 ? RPW : 1];
+        if constexpr (FUSE != 0) {
+            const int gx = x0 - p.dil + lane;
+#pragma unroll
+            for (int u = 0; u < RPW; ++u) {
+                const int r = warp + 8 * u;
+                const int gy = y0 - p.dil + r;
+                const bool inside = off[u] >= 0;
+                const int yc = min(max(gy, 0), p.H - 1), xc = min(max(gx, 0), p.W - 1);
+                if constexpr (FUSE == 1) {
+                    const float dsp = __ldg(p.smp + ((long long)(b * p.D + d) * p.H + yc) * p.W + xc);
+                    int xa;
+                    warp_col(xc, dsp, p.W, inside, xa, wa[u], wb[u]);
+                    woff[u] = warp_row(yc, p.H) * p.W + xa;
+                } else {
+                    const int xs = xc - d;                      // candidate d of the shift volume: R[x - d], zero for x < d
+                    wa[u] = (inside && xs >= 0) ? 1.f : 0.f;
+                    woff[u] = yc * p.W + max(xs, 0);
+                }
+            }
+        }
+        float v[RPW][8];
+        int l_phase = 0, l_kc = 0;  // load cursor: input phase and chunk inside the phase
+        auto load_chunk = [&]() {
+            if constexpr (FUSE != 0) {
+                if (l_kc < p.wchunks) {          // 8 channels of the feature half, rebuilt from the feature maps
+                    const float* rs = p.in + (long long)b * p.isB + (long long)(l_kc * 8) * p.isC;
+                    [[maybe_unused]] const float* ls = p.left + (long long)b * p.isB + (long long)(l_kc * 8) * p.isC;
+#pragma unroll
+                    for (int u = 0; u < RPW; ++u) {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            if constexpr (FUSE == 1) {
+                                const float ra = __ldg(rs + (long long)c * p.isC + woff[u]);
+                                const float rb = __ldg(rs + (long long)c * p.isC + woff[u] + 1);
+                                v[u][c] = fmaf(rb, wb[u], __fmul_rn(ra, wa[u]));
+                            } else {
+                                const float l = off[u] >= 0 ? __ldg(ls + (long long)c * p.isC + off[u]) : 0.f;
+                                const float e = l - __fmul_rn(__ldg(rs + (long long)c * p.isC + woff[u]), wa[u]);
+                                v[u][c] = -(e * e);
+                            }
+                        }
+                    }
+                } else {                         // 8 channels of the group-cost volume
+                    const int kc2 = l_kc - p.wchunks;
+                    const float* src = p.in2 + (long long)b * p.i2sB + (long long)d * p.i2sD + (long long)(kc2 * 8) * p.i2sC;
+                    const int nvalid = p.C2 - kc2 * 8;
+#pragma unroll
+                    for (int u = 0; u < RPW; ++u) {
+                        const float* su = src + off[u];
+                        const bool ok = off[u] >= 0;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            v[u][c] = (ok && c < nvalid) ? __ldg(su) : 0.f;
+                            su += p.i2sC;
+                        }
+                    }
+                }
+                ++l_kc;
+                return;
+            }
+            int pr = 0, pc = 0;
+            bool col_ok = true;
+            const float* src = in_pl + (long long)(l_kc * 8) * p.isC;
+            if (p.kd) {             // phase = tap along D: input plane of this output plane
+                int din;
+                if (p.dtrans) {     // transposed k3 s2 p1 op1: dout = 2*din - 1 + tap
+                    const int t2 = d + 1 - l_phase;
+                    din = (t2 >= 0 && (t2 & 1) == 0) ? (t2 >> 1) : -1;
+                } else {
+                    din = d * p.dstride + (l_phase - p.kd / 2) * p.ddil;
+                }
+                col_ok = din >= 0 && din < p.Din;
+                src += (long long)(col_ok ? din : 0) * p.isD;
+            } else {                // phase = (row, column) parity of a stride-2 input
+                pr = l_phase >> 1;
+                pc = l_phase & 1;
+                src += pr * p.Win + pc;
+                col_ok = !(pc && edge < 0);
+            }
+            const int nvalid = p.Cin - l_kc * 8;                 // channels of this chunk that exist (>= 8: all)
+#pragma unroll
+            for (int u = 0; u < RPW; ++u) {
+                const float* su = src + off[u];
+                const bool ok = off[u] >= 0 && col_ok && !(pr && ((edge >> u) & 1));
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    v[u][c] = (ok && c < nvalid) ? __ldg(su) : 0.f;
+                    su += p.isC;
+                }
+            }
+            if (++l_kc == p.cpp) {
+                l_kc = 0;
+                ++l_phase;
+            }
+        };
+        // cp.async ring: every thread copies its own (row, lane) x 8 channels of the next unit into the raw stage and
+        // posts one asynchronous arrival; a thread only ever reads back what it copied itself, so a stage needs no
+        // "empty" barrier.  Uses the same cursor / predicates as load_chunk.
+        int c_issue = 0;
+        auto issue_cpa = [&]() {
+            const int slot = c_issue % p.rs;
+            ++c_issue;
+            int pr = 0, pc = 0;
+            bool col_ok = true;
+            const float* src = in_pl + (long long)(l_kc * 8) * p.isC;
+            if (p.kd) {
+                int din;
+                if (p.dtrans) {
+                    const int t2 = d + 1 - l_phase;
+                    din = (t2 >= 0 && (t2 & 1) == 0) ? (t2 >> 1) : -1;
+                } else {
+                    din = d * p.dstride + (l_phase - p.kd / 2) * p.ddil;
+                }
+                col_ok = din >= 0 && din < p.Din;
+                src += (long long)(col_ok ? din : 0) * p.isD;
+            } else {
+                pr = l_phase >> 1;
+                pc = l_phase & 1;
+                src += pr * p.Win + pc;
+                col_ok = !(pc && edge < 0);
+            }
+            const int nvalid = p.Cin - l_kc * 8;
+            float* dst = reinterpret_cast<float*>(raw_base + (size_t)slot * raw_bytes) + lane;
+#pragma unroll
+            for (int u = 0; u < RPW; ++u) {
+                const int r = warp + 8 * u;
+                if (r < SR) {
+                    const float* su = src + off[u];
+                    const bool ok = off[u] >= 0 && col_ok && !(pr && ((edge >> u) & 1));
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const bool okc = ok && c < nvalid;
+                        cp_async4(dst + (c * SR + r) * 32, okc ? su : p.in, okc);
+                        su += p.isC;
+                    }
+                }
+            }
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&raw_full[slot])) : "memory");
+            if (++l_kc == p.cpp) {
+                l_kc = 0;
+                ++l_phase;
+            }
+        };
+        constexpr int NACC = DIRECT ? 1 : N;
+        float acc[JT][NACC];
+#pragma unroll
+        for (int jj = 0; jj < JT; ++jj)
+#pragma unroll
+            for (int n = 0; n < NACC; ++n) acc[jj][n] = 0.f;
+
+        auto drain = [&](int g) {
+            if constexpr (!DIRECT) {
+#pragma unroll
+            for (int jj = 0; jj < JT; ++jj) {
+                const int j = half + 2 * jj;
+                if (j < MT) {
+                    mbar_wait(&acc_full[j], (uint32_t)g & 1u);
+                    tc_fence_after();
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(j * 2 * N);
+#pragma unroll
+                    for (int c0 = 0; c0 < N; c0 += 8) {
+                        uint32_t rh[8], rl[8];
+                        tmem_ld8(taddr + (uint32_t)c0, rh);
+                        tmem_ld8(taddr + (uint32_t)(N + c0), rl);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) acc[jj][c0 + c] += __uint_as_float(rh[c]) + __uint_as_float(rl[c]);
+                    }
+                    tc_fence_before();
+                    mbar_arrive(&acc_empty[j]);
+                }
+            }
+            }
+        };
+
+        if constexpr (CPA) {
+            for (int i = 0; i < p.rs && i < p.nchunk; ++i) issue_cpa();
+        } else if constexpr (!TMA) {
+            load_chunk();
+        }
+        int s = 0, gk = 0, gdone = 0;      // stage of chunk k; chunks produced since the last group boundary; groups drained
+        uint32_t ph = 0;
+        for (int k = 0; k < p.nchunk; ++k) {
+            // F16: two 8-channel units (K halves) make one MMA chunk / shared-memory stage
+            const bool first_half = !F16 || !(k & 1);
+            const bool last_half = !F16 || (k & 1) || k == p.nchunk - 1;
+            if (first_half) mbar_wait(&empty[s], ph ^ 1u);
+            uint8_t* st_base = smem + (size_t)s * stage_bytes;
+            if (first_half && tid == 0) {
+                mbar_arrive_expect_tx(&full[s], b_bytes);
+                bulk_g2s(st_base + a_bytes, p.wpack + (size_t)(F16 ? k >> 1 : k) * (b_bytes / 4), b_bytes, &full[s]);
+            }
+            const uint32_t a_hi = smem_u32(st_base);
+            const uint32_t khalf = NPOS * 16u;
+            const uint32_t a_lo = a_hi + 2u * khalf;
+            // the unit's values: registers (v) or the raw fp32 stage (TMA / cp.async ring)
+            const float* raw = nullptr;
+            int rbw = 32;
+            if constexpr (TMA || CPA) {
+                const int rsl = k % p.rs;
+                mbar_wait(&raw_full[rsl], ((uint32_t)(k / p.rs)) & 1u);
+                raw = reinterpret_cast<const float*>(raw_base + (size_t)rsl * raw_bytes) + lane;
+                if constexpr (TMA) {
+                    raw += (x0 - p.dil) & 3;
+                    rbw = p.bw;
+                }
+            }
+            auto val = [&](int u, int r, int c) -> float {
+                if constexpr (TMA || CPA) return raw[(c * SR + r) * rbw];
+                else return v[u][c];
+            };
+            if constexpr (F16) {
+                const uint32_t ko = (uint32_t)(k & 1) * khalf;         // K half of this unit inside the chunk
+#pragma unroll
+                for (int u = 0; u < RPW; ++u) {
+                    const int r = warp + 8 * u;
+                    if (r < SR) {
+                        uint32_t hi[4], lo[4];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const float xa = val(u, r, 2 * c), xb = val(u, r, 2 * c + 1);
+                            hi[c] = pack_h2(xa, xb);
+                            const float2 hf = unpack_h2(hi[c]);
+                            lo[c] = pack_h2(xa - hf.x, xb - hf.y);
+                        }
+                        const uint32_t o = (uint32_t)(r * 32 + lane) * 16u;
+                        sts128(a_hi + ko + o, hi[0], hi[1], hi[2], hi[3]);
+                        sts128(a_lo + ko + o, lo[0], lo[1], lo[2], lo[3]);
+                        if (!(k & 1) && k == p.nchunk - 1) {            // odd number of units: the last K half is zero
+                            sts128(a_hi + khalf + o, 0u, 0u, 0u, 0u);
+                            sts128(a_lo + khalf + o, 0u, 0u, 0u, 0u);
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < RPW; ++u) {
+                    const int r = warp + 8 * u;
+                    if (r < SR) {
+                        uint32_t hi[8], lo[8];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const float x = val(u, r, c);
+                            hi[c] = tf32_rna(x);
+                            // exact remainder; the tensor core ignores the 13 low mantissa bits of a tf32 operand,
+                            // so not rounding lo costs <= 2^-22 relative
+                            lo[c] = __float_as_uint(x - __uint_as_float(hi[c]));
+                        }
+                        const uint32_t o = (uint32_t)(r * 32 + lane) * 16u;
+                        sts128(a_hi + o, hi[0], hi[1], hi[2], hi[3]);
+                        sts128(a_hi + khalf + o, hi[4], hi[5], hi[6], hi[7]);
+                        sts128(a_lo + o, lo[0], lo[1], lo[2], lo[3]);
+                        sts128(a_lo + khalf + o, lo[4], lo[5], lo[6], lo[7]);
+                    }
+                }
+            }
+            if constexpr (TMA) {
+                __syncwarp();
+                if (elect_one()) mbar_arrive(&raw_empty[k % p.rs]);     // this warp has read the raw stage
+                __syncwarp();
+            } else if constexpr (CPA) {
+                if (c_issue < p.nchunk) issue_cpa();    // refill the stage this thread just read
+            } else {
+                if (k + 1 < p.nchunk) load_chunk();     // in flight across the barrier traffic and the drain below
+            }
+            if (last_half) {
+                fence_proxy_async();                   // generic-proxy st.shared -> visible to the tensor core
+                mbar_arrive(&full[s]);
+                if (++s == p.stages) {
+                    s = 0;
+                    ph ^= 1u;
+                }
+                if constexpr (!DIRECT) {
+                    // a group that finished one chunk ago is drained now: overlaps this chunk's MMAs
+                    if (gk == p.G) {
+                        drain(gdone++);
+                        gk = 0;
+                    }
+                    ++gk;
+                }
+            }
+        }
+        if constexpr (!DIRECT) drain(ngroups - 1);
+
+        // ===================== epilogue: kx shift-sum, bias, activation, NCDHW stores =====================
+        float* out_pl = p.out + (long long)b * p.osB + (long long)d * p.osD;
+        const int x = x0 + lane;
+        const bool xok = lane < VW && x < p.W;
+        const int xo = x * p.osX;
+#pragma unroll
+        for (int jj = 0; jj < JT; ++jj) {
+            const int j = half + 2 * jj;
+            if (j < MT) {                                  // warp-uniform
+                const int y = y0 + 4 * j + quarter;
+                float* o = out_pl + (long long)y * p.osY + xo;
+                const bool ok = xok && y < p.H;
+                if constexpr (DIRECT) {
+                    // one accumulation group: stream TMEM -> registers 8 channels at a time
+                    mbar_wait(&acc_full[j], 0u);
+                    tc_fence_after();
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(j * C::TS);
+                    if (p.act == TSTEREO_ACT_SILU) epi_direct<TSTEREO_ACT_SILU, CP, FOLD>(taddr, p.dil, o, p.osC, p.bias, p.Cout, ok);
+                    else if (p.act == TSTEREO_ACT_RELU) epi_direct<TSTEREO_ACT_RELU, CP, FOLD>(taddr, p.dil, o, p.osC, p.bias, p.Cout, ok);
+                    else epi_direct<TSTEREO_ACT_NONE, CP, FOLD>(taddr, p.dil, o, p.osC, p.bias, p.Cout, ok);
+                } else {
+                    const float* ad = nullptr;
+                    if constexpr (FUSE == 1)
+                        if (p.add) ad = p.add + (long long)b * p.asB + (long long)min(y, p.H - 1) * p.W + min(x, p.W - 1);
+                    if (p.act == TSTEREO_ACT_SILU) epi_acc<TSTEREO_ACT_SILU, CP, FOLD>(acc[jj], p.dil, o, p.osC, p.bias, p.Cout, ok, ad, p.asC);
+                    else if (p.act == TSTEREO_ACT_RELU) epi_acc<TSTEREO_ACT_RELU, CP, FOLD>(acc[jj], p.dil, o, p.osC, p.bias, p.Cout, ok, ad, p.asC);
+                    else epi_acc<TSTEREO_ACT_NONE, CP, FOLD>(acc[jj], p.dil, o, p.osC, p.bias, p.Cout, ok, ad, p.asC);
+                }
+            }
+        }
+        if constexpr (DIRECT) tc_fence_before();
+    } else {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc_2n = F16 ? idesc_f16(2 * N) : idesc_tf32(2 * N), idesc_n = F16 ? idesc_f16(C::N2) : idesc_tf32(C::N2);
+        auto mma = [](uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accf) {
+            if constexpr (F16) tc_mma_f16(d, a, b, idesc, accf);
+            else tc_mma_tf32(d, a, b, idesc, accf);
+        };
+        const uint32_t a_lbo = NPOS * 16u, b_lbo = 2u * N * 16u;
+        int s = 0, g = 0, kg = 0;          // stage; accumulation group; chunk index inside the group
+        uint32_t ph = 0;
+        if constexpr (TMA)
+            for (int i = 0; i < p.rs && i < p.nchunk; ++i) issue_tma();
+        for (int k = 0; k < nmma; ++k) {
+            const bool first = DIRECT ? k == 0 : kg == 0;
+            const bool last = DIRECT ? k == nmma - 1 : (kg == p.G - 1 || k == nmma - 1);
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            const uint32_t st_base = smem_u32(smem + (size_t)s * stage_bytes);
+            // descriptor start-address field is (addr >> 4): offsets add directly (no carry out of its 14 bits)
+            const uint64_t a_hi = make_desc(st_base, a_lbo, 128u);
+            const uint64_t a_lo = make_desc(st_base + 2u * NPOS * 16u, a_lbo, 128u);
+            const uint64_t b_d = make_desc(st_base + a_bytes, b_lbo, 128u);
+#pragma unroll 1
+            for (int j = 0; j < MT; ++j) {
+                if (!DIRECT && first && g >= 1) {
+                    mbar_wait(&acc_empty[j], (uint32_t)(g - 1) & 1u);
+                    tc_fence_after();
+                }
+                if (elect_one()) {
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(j * C::TS);
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky) {
+                        if (ky >= p.nky) break;
+                        const uint64_t ad = (uint64_t)((4 * j + ky * p.dil) * 32);
+                        const uint64_t bd = b_d + (uint64_t)(ky * (2 * 2 * N));
+                        const uint32_t acc0 = (first && ky == 0) ? 0u : 1u;
+                        if constexpr (DIRECT) {
+                            // all three terms into the same N columns (B rows [0,N) = hi, [N,2N) = lo)
+                            mma(d_tmem, a_hi + ad, bd, idesc_n, acc0);
+                            mma(d_tmem, a_hi + ad, bd + (uint64_t)N, idesc_n, 1u);
+                            mma(d_tmem, a_lo + ad, bd, idesc_n, 1u);
+                        } else {
+                            // [A*B_hi | A_hi*B_lo] (+)= A_hi * [B_hi | B_lo]
+                            mma(d_tmem, a_hi + ad, bd, idesc_2n, acc0);
+                            // first block += A_lo * B_hi
+                            mma(d_tmem, a_lo + ad, bd, idesc_n, 1u);
+                        }
+                    }
+                    if (last) tc_commit(&acc_full[j]);
+                }
+                __syncwarp();
+            }
+            if (elect_one()) tc_commit(&empty[s]);      // stage reusable once every MMA above has read it
+            __syncwarp();
+            if constexpr (TMA)
+                if (t_issue < p.nchunk) issue_tma();   // raw stage of chunk k: the producers released it before full[s]
+            if (++s == p.stages) {
+                s = 0;
+                ph ^= 1u;
+            }
+            if (++kg == p.G) {
+                kg = 0;
+                ++g;
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == NPROD / 32) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::NCOLS) : "memory");
+    }
+}
+
+static size_t smem_need(int stages, int SR, int N, int rs = 0, int bw = 36) {
+    return (size_t)stages * ((size_t)SR * 2048 + (size_t)192 * N) + 384 + (size_t)rs * 32 * bw * SR;
+}
+
+static int env_int(const char* name, int dflt);
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (libtstereo does not link libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* q = nullptr;
+        cudaDriverEntryPointQueryResult res;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &res) == cudaSuccess &&
+            res == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)q;
+        cudaGetLastError();
+    }
+    return fn;
+}
+
+// (x, y, plane, c, b) view of the NCDHW input with an (bw, SR, 1, 8, 1) box; false when the view is not expressible
+// (rows not 16-byte aligned, strided x, ...) -> the register path runs instead
+static bool make_tmap(const Params& p, int SR, CUtensorMap* tm) {
+    // opt-in (TSTEREO_TC2_TMA=1): measured 8-10 % slower than the register path on B200 — the kernel is bound by the
+    // shared-memory pipe (tensor-core operand reads 41-55 % + producer stores), and the raw fp32 stage adds one more
+    // shared-memory write + read per element
+    if (!env_int("TSTEREO_TC2_TMA", 0) || p.isX != 1 || p.isY != p.W || p.Hin != p.H || p.Win != p.W) return false;
+    if ((p.W & 3) || (p.isC & 3) || (p.isD & 3) || (p.isB & 3) || (((size_t)p.in) & 15)) return false;
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    const int planes = p.kd ? p.Din : p.D;
+    const long long nb = p.nbatch;
+    // dimensions in order of increasing stride (NCDHW: x, y, plane, channel, batch)
+    const cuuint64_t dims[5] = {(cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)planes, (cuuint64_t)p.Cin, (cuuint64_t)nb};
+    // a dimension of extent 1 may carry any stride: use a legal (monotone, multiple of 16 B) placeholder
+    const cuuint64_t sY = (cuuint64_t)p.W * 4;
+    const cuuint64_t sD = planes > 1 ? (cuuint64_t)p.isD * 4 : sY * (cuuint64_t)p.H;
+    const cuuint64_t sC = (cuuint64_t)p.isC * 4;
+    const cuuint64_t sB = nb > 1 ? (cuuint64_t)p.isB * 4 : sC * (cuuint64_t)p.Cin;
+    if (sD < sY * (cuuint64_t)p.H || sC < sD * (cuuint64_t)planes || sB < sC * (cuuint64_t)p.Cin) return false;
+    const cuuint64_t strides[4] = {sY, sD, sC, sB};
+    const cuuint32_t box[5] = {(cuuint32_t)p.bw, (cuuint32_t)SR, 1, 8, 1};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(p.in), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int CP, int MT, bool DIRECT, int RAW, bool F16, int FOLD = 3, int FUSE = 0>
+static int launch_one(const Params& p, const CUtensorMap& tm, dim3 grid, size_t smem_bytes, cudaStream_t st, const char* what) {
+    auto kern = conv_tc2_kernel<CP, MT, DIRECT, RAW, F16, FOLD, FUSE>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
+        if (e != cudaSuccess) {
+            set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
+            return TSTEREO_E_CUDA;
+        }
+        attr_done = true;
+    }
+    kern<<<grid, NTHREADS, smem_bytes, st>>>(p, tm);
+    return check_launch(what);
+}
+
+// bias == null -> a device buffer of zeros, so the epilogue loads it unconditionally
+__device__ float g_zero_bias[64];
+static const float* zero_bias() {
+    static const float* ptr = nullptr;
+    if (!ptr) {
+        void* q = nullptr;
+        if (cudaGetSymbolAddress(&q, g_zero_bias) == cudaSuccess) ptr = (const float*)q;
+    }
+    return ptr;
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return (e && *e) ? atoi(e) : dflt;
+}
+
+template <int FUSE = 0>
+static int launch(Params& p, int CP, int planes, cudaStream_t st, const char* what) {
+    const int fold = p.fold == 1 ? 1 : 3;
+    const int N = fold * CP, N2 = (N + 15) / 16 * 16;
+    const int VW = 32 - 2 * p.dil;
+    p.tiles_x = (p.W + VW - 1) / VW;
+    const int g_env = env_int("TSTEREO_TC2_G", 0);      // experiments: chunks per accumulation group (per input phase)
+    if (g_env > 0) p.G = g_env * (p.nchunk / p.cpp);
+    if (p.G < 1) p.G = 1;
+    const int nmma = p.half ? (p.nchunk + 1) / 2 : p.nchunk;
+    if (p.half) p.G = (p.G + 1) / 2;                     // same products per accumulation group: 16 channels per chunk
+    const bool direct = FUSE == 0 && nmma <= p.G && !env_int("TSTEREO_TC2_NODIRECT", 0);
+    // M-tiles per CTA: 2 or 4 (TMEM: MT * columns-per-tile <= 512); cost = SM-time of all waves
+    p.nbatch = planes / p.D;
+    p.bw = p.dil ? 36 : 32;
+    CUtensorMap tm = {};
+    const bool tma_ok = FUSE == 0 && !p.half && make_tmap(p, 4 * 2 + 2 * p.dil, &tm);   // eligibility (the box is re-encoded for the chosen tile)
+    // cp.async ring (fp16 split only; opt-in TSTEREO_TC2_CPA=1): loads run `rs` chunks ahead without holding registers.
+    // Measured on B200: no gain on the small hourglass layers (they sit at the fixed launch + prologue + epilogue cost,
+    // ~10 us) and 5-20 % slower on the large ones (one more shared-memory round trip), so it is not the default.
+    const int cpa_env = FUSE == 0 ? env_int("TSTEREO_TC2_CPA", 0) : 0;
+    int best_mt = 0, best_stages = 0, best_rs = 0;
+    bool best_cpa = false;
+    double best_cost = 1e30;
+    const int forced = env_int("TSTEREO_TC2_MT", 0);
+    for (int mt = 2; mt <= 4; mt += 2) {
+        const int cols = mt * (direct ? N2 : 2 * N);
+        if (cols > 512 || (CP == 32 && mt == 4 && fold == 3)) continue;   // no (32, 4) instance of the kx-folded form
+        if (forced && mt != forced) continue;
+        const int jt = (mt + 1) / 2;
+        int minb = (direct || jt * N <= 48) ? 2 : 1;
+        if (cols > 256) minb = 1;                       // two CTAs need their TMEM columns side by side
+        const int SR = 4 * mt + 2 * p.dil;
+        const long long tiles = (long long)p.tiles_x * ((p.H + 4 * mt - 1) / (4 * mt)) * planes;
+        const bool cpa = p.half && cpa_env == 1 && fold == 3;
+        const size_t budget = (minb == 2 && !(cpa && tiles <= 148)) ? (size_t)112 * 1024 : SMEM_MAX;
+        int stages = 0, rs = 0;
+        if (cpa) {          // two operand stages + as many raw fp32 stages as fit
+            for (int r = MAX_RS; r >= 2 && !stages; --r)
+                if (smem_need(2, SR, N, r, 32) <= budget) {
+                    stages = 2;
+                    rs = r;
+                }
+        } else if (tma_ok) {       // operand stages + raw fp32 stages (1/2 the size): prefer depth on the raw side
+            static const int combos[][2] = {{3, 4}, {3, 3}, {2, 4}, {2, 3}, {3, 2}, {2, 2}};
+            for (const auto& c : combos)
+                if (smem_need(c[0], SR, N, c[1], p.bw) <= budget) {
+                    stages = c[0];
+                    rs = c[1];
+                    break;
+                }
+        }
+        if (!stages) {
+            rs = 0;
+            for (int s = MAX_STAGES; s >= 2; --s)
+                if (smem_need(s, SR, N) <= budget) {
+                    stages = s;
+                    break;
+                }
+        }
+        if (!stages) continue;
+        const long long waves = (tiles + 148 * minb - 1) / (148 * minb);
+        const double cost = (double)waves * minb * (SR + 5.0) * ((stages >= 3 || rs) ? 1.0 : 1.15);
+        if (cost < best_cost) {
+            best_cost = cost;
+            best_mt = mt;
+            best_stages = stages;
+            best_rs = rs;
+            best_cpa = cpa && rs > 0;
+        }
+    }
+    TS_REQUIRE(best_mt > 0, "%s: no tile configuration for Cout<=%d", what, CP);
+    if (!p.bias) p.bias = zero_bias();
+    TS_REQUIRE(p.bias, "%s: zero-bias buffer unavailable", what);
+    p.stages = best_stages;
+    p.rs = best_rs;
+    const int SR = 4 * best_mt + 2 * p.dil;
+    const bool tma = best_rs > 0 && !best_cpa;
+    if (best_cpa) p.bw = 32;
+    if (tma && !make_tmap(p, SR, &tm)) {
+        set_error("%s: cuTensorMapEncodeTiled failed", what);
+        return TSTEREO_E_CUDA;
+    }
+    const size_t smem_bytes = smem_need(p.stages, SR, N, p.rs, p.bw);   // p.bw = 32 for the cp.async ring
+    dim3 grid(p.tiles_x * ((p.H + 4 * best_mt - 1) / (4 * best_mt)), planes);
+    if constexpr (FUSE != 0) {
+        TS_REQUIRE(fold == 3 && !direct && !tma && !best_cpa, "%s: the fused cost producer runs the 3x3 ACC register form", what);
+#define TS_TC2U(CC, MM)                                                                                        \
+    if (CP == CC && best_mt == MM)                                                                             \
+        return p.half ? launch_one<CC, MM, false, 0, true, 3, FUSE>(p, tm, grid, smem_bytes, st, what)         \
+                      : launch_one<CC, MM, false, 0, false, 3, FUSE>(p, tm, grid, smem_bytes, st, what);
+        TS_TC2U(8, 2) TS_TC2U(8, 4) TS_TC2U(16, 2) TS_TC2U(16, 4) TS_TC2U(32, 2)
+#undef TS_TC2U
+        TS_REQUIRE(false, "%s: no fused kernel instance for CP=%d MT=%d", what, CP, best_mt);
+    } else {
+#define TS_TC2F1(CC, MM)                                                                                       \
+    if (fold == 1 && p.half && !best_cpa && CP == CC && best_mt == MM)                                         \
+        return direct ? launch_one<CC, MM, true, 0, true, 1>(p, tm, grid, smem_bytes, st, what)                \
+                      : launch_one<CC, MM, false, 0, true, 1>(p, tm, grid, smem_bytes, st, what);
+    TS_TC2F1(8, 2) TS_TC2F1(8, 4) TS_TC2F1(16, 2) TS_TC2F1(16, 4) TS_TC2F1(32, 2) TS_TC2F1(32, 4)
+#undef TS_TC2F1
+    TS_REQUIRE(fold == 3, "%s: the single-column form needs the fp16 split and the register producer", what);
+#define TS_TC2(CC, MM)                                                                                         \
+    if (CP == CC && best_mt == MM) {                                                                           \
+        if (p.half && best_cpa)                                                                                \
+            return direct ? launch_one<CC, MM, true, 2, true>(p, tm, grid, smem_bytes, st, what)               \
+                          : launch_one<CC, MM, false, 2, true>(p, tm, grid, smem_bytes, st, what);             \
+        if (p.half)                                                                                            \
+            return direct ? launch_one<CC, MM, true, 0, true>(p, tm, grid, smem_bytes, st, what)               \
+                          : launch_one<CC, MM, false, 0, true>(p, tm, grid, smem_bytes, st, what);             \
+        if (direct) return tma ? launch_one<CC, MM, true, 1, false>(p, tm, grid, smem_bytes, st, what)         \
+                               : launch_one<CC, MM, true, 0, false>(p, tm, grid, smem_bytes, st, what);        \
+        return tma ? launch_one<CC, MM, false, 1, false>(p, tm, grid, smem_bytes, st, what)                    \
+                   : launch_one<CC, MM, false, 0, false>(p, tm, grid, smem_bytes, st, what);                   \
+    }
+    TS_TC2(8, 2) TS_TC2(8, 4) TS_TC2(16, 2) TS_TC2(16, 4) TS_TC2(32, 2)
+#undef TS_TC2
+    TS_REQUIRE(false, "%s: no kernel instance for CP=%d MT=%d", what, CP, best_mt);
+    }
+}
+
+
+// ---- host helpers shared by the ABI translation units (conv_tc2.cu, cost_conv.cu)
+inline int tc2_cp(int Cout) { return Cout <= 8 ? 8 : Cout <= 16 ? 16 : 32; }
+
+// floats of the operand image of ONE output-channel group (<= 32 channels) over `nchunk` 8-channel chunks
+inline long long group_floats(int nchunk, int cout_g, int nky = 3, int fold = 3) {
+    return (long long)nchunk * nky * 2 * 2 * (fold * tc2_cp(cout_g)) * 4;
+}
+
+// total over the groups of 32 output channels
+inline long long wpack_floats(int nchunk, int Cout, int nky = 3, int fold = 3) {
+    long long n = 0;
+    for (int c0 = 0; c0 < Cout; c0 += 32) n += group_floats(nchunk, Cout - c0 < 32 ? Cout - c0 : 32, nky, fold);
+    return n;
+}
+
+// One (virtual) stride-1 3x3 convolution, output channels in groups of <= 32 (the producer work is repeated per
+// group; Cout = 64 layers are rare and their inputs are L2 resident between the two launches).
+template <int FUSE = 0>
+inline int run_groups(tc2::Params p, int Cout, int planes, cudaStream_t st, const char* what) {
+    const float* wp = p.wpack;
+    const float* bias = p.bias;
+    float* out = p.out;
+    for (int c0 = 0; c0 < Cout; c0 += 32) {
+        const int cg = Cout - c0 < 32 ? Cout - c0 : 32;
+        p.Cout = cg;
+        p.wpack = wp;
+        p.bias = bias ? bias + c0 : nullptr;
+        p.out = out + (long long)c0 * p.osC;
+        if (p.add) p.add += (c0 ? 32ll * p.asC : 0ll);
+        const int rc = tc2::launch<FUSE>(p, tc2_cp(cg), planes, st, what);
+        if (rc != TSTEREO_OK) return rc;
+        wp += group_floats(p.half ? (p.nchunk + 1) / 2 : p.nchunk, cg, p.nky, p.fold == 1 ? 1 : 3);
+    }
+    return TSTEREO_OK;
+}
+
+
+}  // namespace tc2
+}  // namespace tstereo

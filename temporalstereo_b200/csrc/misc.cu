@@ -13,6 +13,20 @@
 
 namespace tstereo {
 
+// --------------------------------------------------------------------------- strided plane copy
+// grid-stride over 16-byte vectors (or scalars when the plane size / alignment forbids it)
+template <typename T>
+__global__ void __launch_bounds__(256)
+copy_planes_kernel(const T* __restrict__ in, T* __restrict__ out, long long osB, long long osC, int C, int HWv, long long total) {
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const int p = (int)(i % HWv);
+        const long long pl = i / HWv;
+        const int c = (int)(pl % C);
+        const long long b = pl / C;
+        out[b * osB + c * osC + p] = in[i];
+    }
+}
+
 // --------------------------------------------------------------------------- resize + add + act
 // out = act(trilinear_ac(a) + skip).  thread = one output x; (y, d, c, b) from the grid.
 __global__ void __launch_bounds__(128)
@@ -421,6 +435,20 @@ bilinear_resize_kernel(const float* __restrict__ in, float* __restrict__ out, fl
 using namespace tstereo;
 
 extern "C" {
+
+int tstereo_copy_planes(const float* in, float* out, long long osB, long long osC, int B, int C, int HW, void* stream) {
+    TS_REQUIRE(in && out, "copy_planes: null pointer");
+    TS_REQUIRE(B > 0 && C > 0 && HW > 0 && osB >= 0 && osC >= HW, "copy_planes: bad sizes");
+    const bool vec = (HW % 4 == 0) && (osB % 4 == 0) && (osC % 4 == 0) && ((((size_t)in) | ((size_t)out)) & 15) == 0;
+    const long long total = (long long)B * C * (vec ? HW / 4 : HW);
+    const unsigned grid = (unsigned)(cdivll(total, 256) < 148 * 16 ? cdivll(total, 256) : 148 * 16);
+    if (vec)
+        copy_planes_kernel<float4><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out),
+                                                                           osB / 4, osC / 4, C, HW / 4, total);
+    else
+        copy_planes_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, osB, osC, C, HW, total);
+    return check_launch("copy_planes");
+}
 
 int tstereo_resize_add_act(const float* a, const float* skip, float* out, int B, int C, int Da, int Ha, int Wa,
                            int D, int H, int W, int act, void* stream) {

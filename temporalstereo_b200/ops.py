@@ -17,7 +17,25 @@ ACT = {None: 0, "none": 0, "SiLU": 1, "silu": 1, "ReLU": 2, "relu": 2}
 
 
 def _stream() -> int:
+    """The current stream of the current device.  libtstereo keeps per-process launch state for ONE device (function
+    attributes, the zero-bias buffer), so every tensor must live on the current device (`_chk` / `_view5` enforce it)."""
     return torch.cuda.current_stream().cuda_stream
+
+
+def _same_device(t: torch.Tensor) -> None:
+    if t.device.index != torch.cuda.current_device():
+        raise ValueError(f"libtstereo launches on the current device (cuda:{torch.cuda.current_device()}), got a tensor on "
+                         f"{t.device}: wrap the call in torch.cuda.device(...)")
+
+
+def _out(out: Optional[torch.Tensor], shape, like: torch.Tensor) -> torch.Tensor:
+    """Allocate the output, or check that a caller-provided view has exactly the computed geometry (a wrong-sized
+    `out` would be written out of bounds by the kernel)."""
+    if out is None:
+        return torch.empty(shape, device=like.device, dtype=torch.float32)
+    if tuple(out.shape) != tuple(shape):
+        raise ValueError(f"out has shape {tuple(out.shape)}, the operator produces {tuple(shape)}")
+    return out
 
 
 def _chk(*ts: Optional[torch.Tensor]) -> None:
@@ -26,6 +44,7 @@ def _chk(*ts: Optional[torch.Tensor]) -> None:
             continue
         if not t.is_cuda:
             raise TypeError("libtstereo ops need CUDA tensors (there is no CPU fallback)")
+        _same_device(t)
         if t.dtype != torch.float32:
             raise TypeError(f"libtstereo ops are fp32-only, got {t.dtype}")
         if not t.is_contiguous():
@@ -40,6 +59,7 @@ def _view5(t: torch.Tensor) -> Tuple[int, int, int]:
     """(sB, sC, sD) element strides of a [B,C,D,H,W] (or [B,C,H,W]) view whose (H,W) plane is dense."""
     if t.dtype != torch.float32 or not t.is_cuda:
         raise TypeError("libtstereo ops need fp32 CUDA tensors")
+    _same_device(t)
     if t.dim() == 4:
         B, Cc, H, W = t.shape
         sB, sC, sH, sW = t.stride()
@@ -82,6 +102,63 @@ def block_cost(left: torch.Tensor, right: torch.Tensor, disp_sample, block_cost_
     return out
 
 
+def group_cost(left: torch.Tensor, right: torch.Tensor, disp_sample) -> torch.Tensor:
+    """Only the three pooled group-wise terms of `block_cost` (block_cost.py:6-13, 64-78): [B, 3C/8, D, H, W].
+    Side input of the fused cost -> first-conv path (`cost_conv_warp` / `cost_conv_shift`)."""
+    _chk(left, right)
+    B, Cc, H, W = left.shape
+    assert right.shape == left.shape, "left / right feature shapes differ"
+    G = Cc // 8
+    D = disp_sample if isinstance(disp_sample, int) else disp_sample.shape[1]
+    out = torch.empty((B, 3 * G, D, H, W), device=left.device, dtype=torch.float32)
+    n = _lib.load().tstereo_block_cost_scratch_floats(B, Cc, H, W, D)
+    scratch = torch.empty((max(int(n), 1),), device=left.device, dtype=torch.float32)
+    if isinstance(disp_sample, int):
+        _lib.call("tstereo_group_cost_shift", _p(left), _p(right), _p(out), _p(scratch), B, Cc, H, W, D, _stream())
+    else:
+        _chk(disp_sample)
+        assert disp_sample.shape == (B, D, H, W)
+        _lib.call("tstereo_group_cost_warp", _p(left), _p(right), _p(disp_sample), _p(out), _p(scratch), B, Cc, H, W, D,
+                  _stream())
+    return out
+
+
+def cost_conv_warp(right: torch.Tensor, samples: torch.Tensor, gvol: torch.Tensor, addL: Optional[torch.Tensor],
+                   wpack: torch.Tensor, bias: Optional[torch.Tensor], cout: int, act=None,
+                   out: Optional[torch.Tensor] = None, half: bool = False) -> torch.Tensor:
+    """act(conv(1,3,3)(block_cost(left, right, samples)) + bias) without the volume (block_cost.py:47-81 ->
+    module.py:111-147): `wpack` is the tensor-core image of W[:, C:] over [warp(R) | group terms] and `addL`
+    [B, cout, H, W] = conv3x3(left, W[:, :C]) is the candidate-invariant left half."""
+    _chk(right, samples, gvol, addL, wpack, bias)
+    B, Cc, H, W = right.shape
+    S = samples.shape[1]
+    assert samples.shape == (B, S, H, W) and gvol.shape == (B, 3 * (Cc // 8), S, H, W)
+    assert addL is None or addL.shape == (B, cout, H, W)
+    out = _out(out, (B, cout, S, H, W), right)
+    osB, osC, osD = _view5(out)
+    assert wpack.numel() == _lib.load().tstereo_cost_conv_wpack_floats(Cc, cout, int(half))
+    _lib.call("tstereo_cost_conv_warp", _p(right), _p(samples), _p(gvol), _p(addL), _p(out), osB, osC, osD, _p(wpack),
+              _p(bias), B, Cc, cout, S, H, W, ACT[act], int(half), _stream())
+    return out
+
+
+def cost_conv_shift(left: torch.Tensor, right: torch.Tensor, gvol: torch.Tensor, wpack: torch.Tensor,
+                    bias: Optional[torch.Tensor], cout: int, act=None, out: Optional[torch.Tensor] = None,
+                    half: bool = False) -> torch.Tensor:
+    """act(conv(1,3,3)(block_cost(left, right, D)) + bias) without the volume (block_cost.py:34-45, 64-81 ->
+    module.py:111-147); `wpack` is the tensor-core image of the whole W over [-(L - R_d)^2 | group terms]."""
+    _chk(left, right, gvol, wpack, bias)
+    B, Cc, H, W = left.shape
+    D = gvol.shape[2]
+    assert right.shape == left.shape and gvol.shape == (B, 3 * (Cc // 8), D, H, W)
+    out = _out(out, (B, cout, D, H, W), left)
+    osB, osC, osD = _view5(out)
+    assert wpack.numel() == _lib.load().tstereo_cost_conv_wpack_floats(Cc, cout, int(half))
+    _lib.call("tstereo_cost_conv_shift", _p(left), _p(right), _p(gvol), _p(out), osB, osC, osD, _p(wpack), _p(bias),
+              B, Cc, cout, D, H, W, ACT[act], int(half), _stream())
+    return out
+
+
 # --------------------------------------------------------------------------- convolutions
 def conv_hw3(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], cout: int, stride: int = 1,
              dilation: int = 1, act=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -92,9 +169,7 @@ def conv_hw3(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], cou
     D = x.shape[2] if five else 1
     Hin, Win = x.shape[-2:]
     Hout, Wout = (Hin - 1) // stride + 1, (Win - 1) // stride + 1
-    if out is None:
-        shape = (B, cout, D, Hout, Wout) if five else (B, cout, Hout, Wout)
-        out = torch.empty(shape, device=x.device, dtype=torch.float32)
+    out = _out(out, (B, cout, D, Hout, Wout) if five else (B, cout, Hout, Wout), x)
     isB, isC, isD = _view5(x)
     osB, osC, osD = _view5(out)
     _chk(w, bias)
@@ -111,41 +186,6 @@ def tf32_split(w: torch.Tensor):
         return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
     hi = rna(w)
     return hi, rna(w - hi)
-
-
-def pack_conv_tc(w: torch.Tensor) -> torch.Tensor:
-    """[Cout, Cin, T] (BN folded; T = 9 taps ky*3+kx, or k taps along D) -> the tcgen05 B-operand image
-    [ceil(Cin/8)][tap T][khalf 2][part 2][N][4]: per (chunk, tap) a K-major 2N x 8 matrix whose rows are
-    [tf32 hi part | tf32 lo part] of the weights."""
-    cout, cin, T = w.shape
-    N, nch = (cout + 15) // 16 * 16, (cin + 7) // 8
-    full = torch.zeros((N, nch * 8, T), device=w.device, dtype=torch.float32)
-    full[:cout, :cin] = w
-    hi, lo = tf32_split(full)
-    parts = torch.stack([hi, lo])                                     # [2, N, nch*8, T]
-    parts = parts.view(2, N, nch, 2, 4, T)                            # [part, n, chunk, khalf, i, tap]
-    return parts.permute(2, 5, 3, 0, 1, 4).contiguous().view(-1)      # [chunk, tap, khalf, part, n, i]
-
-
-pack_conv_hw3_tc = pack_conv_tc
-
-
-def conv_hw3_tc(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Tensor], cout: int, dilation: int = 1,
-                act=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Stride-1 (1,3,3) / 3x3 conv on the tensor cores (tcgen05, 3xTF32), padding = dilation."""
-    five = x.dim() == 5
-    B, Cin = x.shape[:2]
-    D = x.shape[2] if five else 1
-    H, W = x.shape[-2:]
-    if out is None:
-        out = torch.empty((B, cout, D, H, W) if five else (B, cout, H, W), device=x.device, dtype=torch.float32)
-    isB, isC, isD = _view5(x)
-    osB, osC, osD = _view5(out)
-    _chk(wpack, bias)
-    assert wpack.numel() == _lib.load().tstereo_conv_tc_wpack_floats(Cin, cout, 9)
-    _lib.call("tstereo_conv_hw3_tc", _p(x), isB, isC, isD, _p(out), osB, osC, osD, _p(wpack), _p(bias),
-              B, Cin, cout, D, H, W, dilation, ACT[act], _stream())
-    return out
 
 
 def _pack_tc2_group(w: torch.Tensor, nky: int = 3, half: bool = False, fold: int = 3) -> torch.Tensor:
@@ -243,8 +283,7 @@ def conv_hw3_tc2(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Tens
     B, Cin = x.shape[:2]
     D = x.shape[2] if five else 1
     H, W = x.shape[-2:]
-    if out is None:
-        out = torch.empty((B, cout, D, H, W) if five else (B, cout, H, W), device=x.device, dtype=torch.float32)
+    out = _out(out, (B, cout, D, H, W) if five else (B, cout, H, W), x)
     isB, isC, isD = _view5(x)
     osB, osC, osD = _view5(out)
     _chk(wpack, bias)
@@ -262,8 +301,7 @@ def conv_hw3s2_tc2(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Te
     D = x.shape[2] if five else 1
     Hin, Win = x.shape[-2:]
     H, W = (Hin - 1) // 2 + 1, (Win - 1) // 2 + 1
-    if out is None:
-        out = torch.empty((B, cout, D, H, W) if five else (B, cout, H, W), device=x.device, dtype=torch.float32)
+    out = _out(out, (B, cout, D, H, W) if five else (B, cout, H, W), x)
     isB, isC, isD = _view5(x)
     osB, osC, osD = _view5(out)
     _chk(wpack, bias)
@@ -280,9 +318,7 @@ def deconv_hw_tc2(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Ten
     B, Cin = x.shape[:2]
     D = x.shape[2] if five else 1
     Hin, Win = x.shape[-2:]
-    if out is None:
-        shape = (B, cout, D, 2 * Hin, 2 * Win) if five else (B, cout, 2 * Hin, 2 * Win)
-        out = torch.empty(shape, device=x.device, dtype=torch.float32)
+    out = _out(out, (B, cout, D, 2 * Hin, 2 * Win) if five else (B, cout, 2 * Hin, 2 * Win), x)
     isB, isC, isD = _view5(x)
     osB, osC, osD = _view5(out)
     _chk(wpack, bias)
@@ -298,8 +334,7 @@ def conv_d_tc2(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Tensor
     """(k,1,1) conv along D (or its stride-2 transposed form) through the second-generation tensor-core kernel."""
     B, Cin, Din, H, W = x.shape
     Dout = 2 * Din if transposed else (Din - 1) // stride + 1
-    if out is None:
-        out = torch.empty((B, cout, Dout, H, W), device=x.device, dtype=torch.float32)
+    out = _out(out, (B, cout, Dout, H, W), x)
     isB, isC, isD = _view5(x)
     osB, osC, osD = _view5(out)
     _chk(wpack, bias)
@@ -309,29 +344,12 @@ def conv_d_tc2(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Tensor
     return out
 
 
-def conv_d_tc(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Tensor], cout: int, k: int = 3, stride: int = 1,
-              dilation: int = 1, transposed: bool = False, act=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """(k,1,1) conv along D (or its stride-2 transposed form) on the tensor cores (tcgen05, 3xTF32)."""
-    B, Cin, Din, H, W = x.shape
-    Dout = 2 * Din if transposed else (Din - 1) // stride + 1
-    if out is None:
-        out = torch.empty((B, cout, Dout, H, W), device=x.device, dtype=torch.float32)
-    isB, isC, isD = _view5(x)
-    osB, osC, osD = _view5(out)
-    _chk(wpack, bias)
-    assert wpack.numel() == _lib.load().tstereo_conv_tc_wpack_floats(Cin, cout, k)
-    _lib.call("tstereo_conv_d_tc", _p(x), isB, isC, isD, _p(out), osB, osC, osD, _p(wpack), _p(bias),
-              B, Cin, cout, Din, Dout, H, W, k, stride, dilation, int(transposed), ACT[act], _stream())
-    return out
-
-
 def conv_d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], cout: int, k: int = 3, stride: int = 1,
            dilation: int = 1, transposed: bool = False, act=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """(k,1,1) conv along D (or its stride-2 transposed form), packed weights w[Cin][k][CoutP]."""
     B, Cin, Din, H, W = x.shape
     Dout = 2 * Din if transposed else (Din - 1) // stride + 1
-    if out is None:
-        out = torch.empty((B, cout, Dout, H, W), device=x.device, dtype=torch.float32)
+    out = _out(out, (B, cout, Dout, H, W), x)
     isB, isC, isD = _view5(x)
     osB, osC, osD = _view5(out)
     _chk(w, bias)
@@ -347,14 +365,24 @@ def deconv_hw(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], co
     B, Cin = x.shape[:2]
     D = x.shape[2] if five else 1
     Hin, Win = x.shape[-2:]
-    if out is None:
-        shape = (B, cout, D, 2 * Hin, 2 * Win) if five else (B, cout, 2 * Hin, 2 * Win)
-        out = torch.empty(shape, device=x.device, dtype=torch.float32)
+    out = _out(out, (B, cout, D, 2 * Hin, 2 * Win) if five else (B, cout, 2 * Hin, 2 * Win), x)
     isB, isC, isD = _view5(x)
     osB, osC, osD = _view5(out)
     _chk(w, bias)
     _lib.call("tstereo_deconv_hw", _p(x), isB, isC, isD, _p(out), osB, osC, osD, _p(w), _p(bias),
               B, Cin, cout, D, Hin, Win, k, ACT[act], _stream())
+    return out
+
+
+def copy_planes(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """out[...] = x for a dense x [B,C,H,W] and a channel-slice view `out` of a concat buffer (the `torch.cat`s of
+    precise.py:86 are never materialised by a library call)."""
+    _chk(x)
+    B, Cc, H, W = x.shape
+    if tuple(out.shape) != tuple(x.shape):
+        raise ValueError(f"copy_planes: out {tuple(out.shape)} vs in {tuple(x.shape)}")
+    osB, osC, _ = _view5(out)
+    _lib.call("tstereo_copy_planes", _p(x), _p(out), osB, osC, B, Cc, H * W, _stream())
     return out
 
 
@@ -373,6 +401,8 @@ def resize_add_act(a: torch.Tensor, size, skip: Optional[torch.Tensor] = None, a
 def pool5(x: torch.Tensor, avg: torch.Tensor, mx: torch.Tensor) -> None:
     """avg_pool3d / max_pool3d, kernel 5, stride 1, padding 2, written into two views (module.py:416-417)."""
     B, Cc, D, H, W = x.shape
+    if tuple(avg.shape) != tuple(x.shape) or tuple(mx.shape) != tuple(x.shape):
+        raise ValueError(f"pool5 outputs must have the input's shape {tuple(x.shape)}")
     xsB, xsC, xsD = _view5(x)
     osB, osC, osD = _view5(avg)
     assert (xsD == H * W or D == 1) and (osD == H * W or D == 1) and _view5(mx) == (osB, osC, osD)
@@ -385,8 +415,9 @@ def merge_memory(vol: torch.Tensor, samples: torch.Tensor, mem_sample: Optional[
     """Temporal memory merge (coarse.py:84-105, fine.py:104-122): returns (volume [B,C,D+M,H,W], samples)."""
     _chk(vol, samples, mem_sample, mem_cost, past_w, past_b)
     B, Cc, D, H, W = vol.shape
-    if out_vol is None:
-        out_vol = torch.empty((B, Cc, D + M, H, W), device=vol.device, dtype=torch.float32)
+    out_vol = _out(out_vol, (B, Cc, D + M, H, W), vol)
+    if tuple(samples.shape) != (B, D, H, W):
+        raise ValueError(f"samples has shape {tuple(samples.shape)}, expected {(B, D, H, W)}")
     osB, osC, osD = _view5(out_vol)
     assert osD == H * W
     out_s = torch.empty((B, D + M, H, W), device=vol.device, dtype=torch.float32)
@@ -422,7 +453,9 @@ def range_samples(disp: torch.Tensor, radius: float, samples: torch.Tensor, c_of
     """low/high = disp -/+ radius and the 5 range candidates written at channel c_off of `samples`
     (aggregation/TemporalStereo/TemporalStereo.py:103-110, fine.py:78-86)."""
     _chk(disp, samples)
-    B, _, H, W = disp.shape
+    B, one, H, W = disp.shape
+    if one != 1 or samples.shape[0] != B or tuple(samples.shape[-2:]) != (H, W) or c_off + 5 > samples.shape[1]:
+        raise ValueError(f"range_samples: disp {tuple(disp.shape)} does not match samples {tuple(samples.shape)} at channel {c_off}")
     low = torch.empty_like(disp)
     high = torch.empty_like(disp)
     _lib.call("tstereo_range_samples", _p(disp), float(radius), _p(low), _p(high), _p(samples), samples.shape[1],
@@ -459,6 +492,8 @@ def bilinear_resize(x: torch.Tensor, size, mul: float = 1.0, div: float = 1.0, o
     Ho, Wo = size
     if out is None:
         out = torch.empty((B, Cc, Ho, Wo), device=x.device, dtype=torch.float32)
+    elif out.shape[0] != B or tuple(out.shape[-2:]) != (Ho, Wo) or c_off + Cc > out.shape[1]:
+        raise ValueError(f"bilinear_resize: out {tuple(out.shape)} cannot hold {Cc} channels of {(Ho, Wo)} at channel {c_off}")
     _lib.call("tstereo_bilinear_resize", _p(x), _p(out), float(mul), float(div), B, Cc, Hi, Wi, Ho, Wo,
               out.shape[1], c_off, _stream())
     return out
@@ -485,6 +520,8 @@ def reproject_disp(disp: torch.Tensor, params: torch.Tensor, want_flow: bool = T
     if want_disp and out is None:
         out = torch.empty((B, Cc, h, w), device=disp.device, dtype=torch.float32)
     ct = out.shape[1] if out is not None else Cc
+    if out is not None and (out.shape[0] != B or tuple(out.shape[-2:]) != (h, w) or c_off + Cc > ct):
+        raise ValueError(f"reproject_disp: out {tuple(out.shape)} cannot hold {Cc} channels of {(h, w)} at channel {c_off}")
     _lib.call("tstereo_reproject_disp", _p(disp), _p(params), _p(flow), _p(out if want_disp else None), ct, c_off,
               B, Cc, h, w, _stream())
     return flow, out

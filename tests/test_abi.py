@@ -64,7 +64,7 @@ def test_library_exports_every_symbol(lib):
     raw = ctypes.CDLL(_lib.LIB_PATH)
     for name in _declarations():
         assert hasattr(raw, name), name
-    assert lib.tstereo_version() == 100
+    assert lib.tstereo_version() == 200
     assert lib.tstereo_last_error() is not None
 
 

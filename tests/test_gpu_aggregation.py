@@ -229,3 +229,22 @@ def test_idempotent_and_batch_independent(engine, plan):
         for x, y in zip(a[0] + a[1], one[0] + one[1]):
             assert torch.equal(x[i:i + 1], y)
     engine.plan_mode = "auto"
+
+
+def test_materialised_cost_path_agrees_with_the_fused_one(engine):
+    """fuse_cost=False runs ops.block_cost (the drop-in operator, raw volume in HBM) + the plain first conv; the default
+    path never writes the volume.  Same math, other summation order: both within tolerance of the oracle and of each other."""
+    sd = synth.synthetic_state_dict(seed=0)
+    lf, rf, li, ri = synth.synthetic_frame(128, 192, B=2, seed=6)
+    with torch.no_grad():
+        want = O.aggregation_forward(sd, lf, rf, li, ri, {})
+    assert engine.fuse_cost
+    fused = engine(_cuda(lf), _cuda(rf), li.cuda(), ri.cuda(), {})
+    engine.fuse_cost = False
+    try:
+        plain = engine(_cuda(lf), _cuda(rf), li.cuda(), ri.cuda(), {})
+    finally:
+        engine.fuse_cost = True
+    _check(fused, want[:4], "fused cost path")
+    _check(plain, want[:4], "materialised cost path")
+    assert (fused[0][0] - plain[0][0]).abs().mean() < 1e-4

@@ -101,6 +101,85 @@ def test_block_cost_shift_vs_oracle(ops, B, C, H, W, D):
     close(out[:, C:], want[:, C:], 5e-5, rtol=1e-5, what="group terms")
 
 
+@pytest.mark.parametrize("B,C,H,W,S", [(1, 32, 34, 60, 5), (2, 16, 17, 45, 7), (1, 8, 4, 4, 2)])
+def test_group_cost_equals_the_volume_tail(ops, B, C, H, W, S):
+    """The group-only kernel is the materialising kernel minus its stores: bit-equal to the last 3C/8 channels."""
+    L, R, smp = _op_inputs(5, B, C, H, W, S)
+    full = ops.block_cost(L.cuda(), R.cuda(), smp.cuda())
+    g = ops.group_cost(L.cuda(), R.cuda(), smp.cuda())
+    assert torch.equal(g, full[:, 2 * C:])
+    full = ops.block_cost(L.cuda(), R.cuda(), S)
+    g = ops.group_cost(L.cuda(), R.cuda(), S)
+    assert torch.equal(g, full[:, C:])
+
+
+# fused cost volume -> first (1,3,3) conv: against the fp64 conv of the ORACLE's volume; tolerance = the fp32 conv's
+COST_CONV_CASES = [
+    # B, C, Cout, S, H, W
+    (1, 128, 8, 5, 24, 40),      # precise-level channel counts
+    (2, 128, 16, 8, 17, 45),     # fine level with local-map candidates, ragged tiles
+    (1, 16, 8, 3, 33, 70),       # tile tails in x (W > 2 tiles) and y
+    (1, 64, 32, 2, 9, 13),       # Cout = 32 (CP = 32 instance)
+    (1, 8, 20, 4, 12, 31),       # padded output channels, group terms = 3 channels (one partial chunk)
+]
+
+
+@pytest.mark.parametrize("half", [False, True])
+@pytest.mark.parametrize("B,C,Cout,S,H,W", COST_CONV_CASES)
+def test_cost_conv_warp(ops, B, C, Cout, S, H, W, half):
+    L, R, smp = _op_inputs(6, B, C, H, W, S)
+    smp[:, 0] = torch.round(smp[:, 0])
+    smp[:, -1] = smp[:, -1] + W                 # a fully out-of-range candidate
+    planes = 2 * C + 3 * (C // 8)
+    w = rnd(Cout, planes, 1, 3, 3, seed=61, scale=(2.0 / (9 * planes)) ** 0.5)
+    b = rnd(Cout, seed=62, scale=0.1)
+    vol = O.block_cost(L, R, smp, 3)
+    want = O._act(F.conv3d(vol.double(), w.double(), b.double(), 1, (0, 1, 1)), "SiLU").float()
+    w9 = w.reshape(Cout, planes, 9)
+    g = ops.group_cost(L.cuda(), R.cuda(), smp.cuda())
+    addl = ops.conv_hw3_tc2(L.cuda(), ops.pack_conv_hw3_tc2(w9[:, :C].contiguous(), half).cuda(), None, Cout, 1, None, half=half)
+    got = ops.cost_conv_warp(R.cuda(), smp.cuda(), g, addl, ops.pack_conv_hw3_tc2(w9[:, C:].contiguous(), half).cuda(), b.cuda(),
+                             Cout, "SiLU", half=half)
+    close(got, want, 2e-5, rtol=1e-5, what="cost_conv_warp")
+    # and against the two-step path it replaces (materialised volume -> tensor-core conv): same math, other summation order
+    two = ops.conv_hw3_tc2(ops.block_cost(L.cuda(), R.cuda(), smp.cuda()), ops.pack_conv_hw3_tc2(w9, half).cuda(), b.cuda(), Cout, 1,
+                           "SiLU", half=half)
+    close(got, two.cpu(), 2e-5, rtol=1e-5, what="fused vs materialised")
+
+
+@pytest.mark.parametrize("half", [False, True])
+@pytest.mark.parametrize("B,C,Cout,D,H,W", [(1, 256, 32, 12, 20, 36), (2, 16, 8, 20, 9, 45), (1, 64, 16, 16, 34, 60)])
+def test_cost_conv_shift(ops, B, C, Cout, D, H, W, half):
+    L, R, _ = _op_inputs(7, B, C, H, W, 1)
+    planes = C + 3 * (C // 8)
+    w = rnd(Cout, planes, 1, 3, 3, seed=63, scale=(2.0 / (9 * planes)) ** 0.5)
+    b = rnd(Cout, seed=64, scale=0.1)
+    vol = O.block_cost(L, R, D, 3)
+    want = O._act(F.conv3d(vol.double(), w.double(), b.double(), 1, (0, 1, 1)), "SiLU").float()
+    g = ops.group_cost(L.cuda(), R.cuda(), D)
+    got = ops.cost_conv_shift(L.cuda(), R.cuda(), g, ops.pack_conv_hw3_tc2(w.reshape(Cout, planes, 9), half).cuda(), b.cuda(), Cout,
+                              "SiLU", half=half)
+    close(got, want, 2e-5, rtol=1e-5, what="cost_conv_shift")
+
+
+def test_cost_conv_into_a_strided_view_and_bad_arguments(ops):
+    from temporalstereo_b200._lib import TStereoError
+    B, C, Cout, S, H, W = 1, 16, 8, 3, 12, 20
+    L, R, smp = _op_inputs(8, B, C, H, W, S)
+    planes = 2 * C + 3 * (C // 8)
+    w = rnd(Cout, planes, 9, seed=65, scale=0.05)
+    g = ops.group_cost(L.cuda(), R.cuda(), smp.cuda())
+    wp = ops.pack_conv_hw3_tc2(w[:, C:].contiguous(), True).cuda()
+    buf = torch.full((B, 24, S, H, W), 7.0, device="cuda")
+    ops.cost_conv_warp(R.cuda(), smp.cuda(), g, None, wp, None, Cout, None, out=buf[:, 8:16], half=True)
+    ref = ops.cost_conv_warp(R.cuda(), smp.cuda(), g, None, wp, None, Cout, None, half=True)
+    assert torch.equal(buf[:, 8:16], ref) and (buf[:, :8] == 7).all() and (buf[:, 16:] == 7).all()
+    with pytest.raises(ValueError):
+        ops.cost_conv_warp(R.cuda(), smp.cuda(), g, None, wp, None, Cout, None, out=buf[:, 8:17], half=True)
+    with pytest.raises((TStereoError, AssertionError)):
+        ops.cost_conv_warp(R.cuda()[:, :12].contiguous(), smp.cuda(), g, None, wp, None, Cout, None, half=True)
+
+
 def test_block_cost_rejects_bad_arguments(ops):
     from temporalstereo_b200._lib import TStereoError
     L = torch.zeros(1, 12, 8, 8, device="cuda")
@@ -422,48 +501,7 @@ def test_update_map_golden(golden_dir):
     close(got["local_map"], gm["local_map"], 2e-4, rtol=1e-5, what="local map")
 
 
-# --------------------------------------------------------------------------- tensor-core conv (tcgen05, 3xTF32)
-TC_CASES = [
-    # B, Cin, Cout, D, H, W, dil, act, bias
-    (1, 8, 16, 1, 8, 16, 1, None, False),
-    (1, 16, 8, 2, 9, 20, 1, "SiLU", True),
-    (1, 44, 32, 3, 17, 30, 1, "SiLU", True),
-    (2, 304, 8, 2, 20, 37, 1, "SiLU", True),
-    (1, 128, 32, 2, 34, 60, 1, None, True),
-    (1, 64, 64, 1, 9, 15, 1, "ReLU", True),
-    (1, 32, 32, 2, 17, 30, 2, "SiLU", True),
-    (1, 13, 36, 1, 10, 12, 1, None, True),
-    (1, 64, 32, 1, 40, 240, 1, "ReLU", True),
-    (1, 8, 8, 5, 136, 240, 2, "SiLU", True),
-]
-
-
-@pytest.mark.parametrize("B,Cin,Cout,D,H,W,dil,act,bias", TC_CASES)
-def test_conv_hw3_tc(ops, B, Cin, Cout, D, H, W, dil, act, bias):
-    """tcgen05 implicit-GEMM conv with error-compensated 3xTF32 operands == fp32 conv to ~1e-6 relative."""
-    x = rnd(B, Cin, D, H, W, seed=41)
-    w = rnd(Cout, Cin, 1, 3, 3, seed=42, scale=(2.0 / (9 * Cin)) ** 0.5)
-    b = rnd(Cout, seed=43, scale=0.1) if bias else None
-    want = O._act(F.conv3d(x.double(), w.double(), None if b is None else b.double(), 1, (0, dil, dil), (1, dil, dil)), act).float()
-    wp = ops.pack_conv_hw3_tc(w.reshape(Cout, Cin, 9).cuda())
-    got = ops.conv_hw3_tc(x.cuda(), wp, None if b is None else b.cuda(), Cout, dil, act)
-    close(got, want, 1e-5, rtol=1e-5, what="conv_hw3_tc")
-
-
-def test_conv_hw3_tc_views(ops):
-    """2-D input, channel-sliced input and output views (the concat buffers)."""
-    x = rnd(2, 24, 13, 21, seed=45)
-    w = rnd(16, 24, 3, 3, seed=46, scale=0.1)
-    want = F.relu(F.conv2d(x, w, None, 1, 1))
-    wp = ops.pack_conv_hw3_tc(w.reshape(16, 24, 9).cuda())
-    buf = torch.full((2, 40, 13, 21), 7.0, device="cuda")
-    xin = torch.zeros(2, 40, 13, 21)
-    xin[:, 8:32] = x
-    ops.conv_hw3_tc(xin.cuda()[:, 8:32], wp, None, 16, 1, "ReLU", out=buf[:, 8:24])
-    close(buf[:, 8:24], want, 1e-5, rtol=1e-5, what="tc conv2d slices")
-    assert (buf[:, :8] == 7).all() and (buf[:, 24:] == 7).all()
-
-
+# --------------------------------------------------------------------------- tensor-core convs (tcgen05, hi+lo split operands)
 TC2_CASES = [
     # B, Cin, Cout, D, H, W, dil, act, bias
     (1, 8, 16, 1, 8, 16, 1, None, False),
@@ -646,26 +684,6 @@ def test_conv_s2_deconv_views(ops):
 
 @pytest.mark.parametrize("B,Cin,Cout,Din,hw,k,stride,dil,transposed,act", D_CASES + [
     (1, 8, 16, 5, (136, 240), 3, 1, 1, False, "SiLU"), (2, 64, 64, 6, (17, 30), 3, 2, 1, False, "SiLU"),
-    (1, 32, 64, 14, (34, 60), 3, 1, 1, False, "SiLU"), (1, 16, 16, 7, (68, 120), 5, 1, 1, False, "SiLU")])
-def test_conv_d_tc(ops, B, Cin, Cout, Din, hw, k, stride, dil, transposed, act):
-    """(k,1,1) conv along D on tcgen05 (3xTF32) vs an fp64 reference, incl. stride 2, dilation 2, transposed."""
-    H, W = hw
-    x = rnd(B, Cin, Din, H, W, seed=47)
-    b = rnd(Cout, seed=49, scale=0.1)
-    if transposed:
-        w = rnd(Cin, Cout, 3, 1, 1, seed=48, scale=0.1)
-        want = O._act(F.conv_transpose3d(x.double(), w.double(), b.double(), (2, 1, 1), (1, 0, 0), (1, 0, 0)), act).float()
-        wk = w.transpose(0, 1).reshape(Cout, Cin, 3)
-    else:
-        w = rnd(Cout, Cin, k, 1, 1, seed=48, scale=0.1)
-        want = O._act(F.conv3d(x.double(), w.double(), b.double(), (stride, 1, 1), (dil * (k // 2), 0, 0), (dil, 1, 1)), act).float()
-        wk = w.reshape(Cout, Cin, k)
-    got = ops.conv_d_tc(x.cuda(), ops.pack_conv_tc(wk.contiguous().cuda()), b.cuda(), Cout, k, stride, dil, transposed, act)
-    close(got, want, 1e-5, rtol=1e-5, what="conv_d_tc")
-
-
-@pytest.mark.parametrize("B,Cin,Cout,Din,hw,k,stride,dil,transposed,act", D_CASES + [
-    (1, 8, 16, 5, (136, 240), 3, 1, 1, False, "SiLU"), (2, 64, 64, 6, (17, 30), 3, 2, 1, False, "SiLU"),
     (1, 32, 64, 14, (34, 60), 3, 1, 1, False, "SiLU"), (1, 16, 16, 7, (68, 120), 5, 1, 1, False, "SiLU"),
     (1, 64, 32, 3, (9, 15), 3, 1, 1, True, None), (1, 12, 5, 4, (7, 33), 3, 1, 2, False, "SiLU")])
 @pytest.mark.parametrize("half", [False, True])
@@ -695,15 +713,4 @@ def test_conv_d_tc2_into_slice(ops):
     cat[:, :16] = x.cuda()
     ops.conv_d_tc2(cat[:, :16], ops.pack_conv_d_tc2(w.reshape(16, 16, 5).cuda()), None, 16, 5, 1, 1, False, None, out=cat[:, 16:32])
     close(cat[:, 16:32], want, 1e-5, rtol=1e-5, what="conv_d_tc2 into slice")
-    assert (cat[:, 32:] == 0).all()
-
-
-def test_conv_d_tc_into_slice(ops):
-    x = rnd(1, 16, 7, 9, 14, seed=50)
-    w = rnd(16, 16, 5, 1, 1, seed=51, scale=0.1)
-    want = F.conv3d(x, w, None, 1, (2, 0, 0))
-    cat = torch.zeros(1, 64, 7, 9, 14, device="cuda")
-    cat[:, :16] = x.cuda()
-    ops.conv_d_tc(cat[:, :16], ops.pack_conv_tc(w.reshape(16, 16, 5).cuda()), None, 16, 5, out=cat[:, 16:32])
-    close(cat[:, 16:32], want, 1e-5, rtol=1e-5, what="conv_d_tc slice")
     assert (cat[:, 32:] == 0).all()

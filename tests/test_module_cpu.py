@@ -42,8 +42,13 @@ def test_from_config_and_registry():
     assert isinstance(m, TEMPORALSTEREO) and AGGREGATION_REGISTRY.get("TEMPORALSTEREO") is TEMPORALSTEREO
     assert m.levels["coarse"]["num_sample"] == 16
     assert not m.training
-    with pytest.raises(NotImplementedError):
+    # the reference trainer toggles eval()/train() around every history frame (projects/TemporalStereo/TemporalStereo.py:
+    # 268-274) and Lightning calls train() around fit / validate / test: it must not raise, and the engine stays in eval
+    with pytest.warns(UserWarning, match="inference engine"):
         m.train()
+    assert not m.training
+    m.eval().train(True)        # second toggle: silent
+    assert not m.training and all(not c.training for c in m.modules())
 
 
 def test_fold_matches_batchnorm():
@@ -52,7 +57,7 @@ def test_fold_matches_batchnorm():
     m = TEMPORALSTEREO()
     sd = synth.synthetic_state_dict(seed=0)
     p = "fine.init3d.2.conv.0"
-    pk = m._fold(sd, p, p + ".norm")
+    pk = m._mk(*m._fold(sd, p, p + ".norm"))
     x = torch.randn(1, 16, 2, 6, 7)
     y = F.conv3d(x, sd[p + ".weight"], None, 1, (0, 2, 2), (1, 2, 2))
     y = F.batch_norm(y, sd[p + ".norm.running_mean"], sd[p + ".norm.running_var"], sd[p + ".norm.weight"],
@@ -66,4 +71,45 @@ def test_no_cpu_fallback():
     m = TEMPORALSTEREO().eval()
     lf, rf, li, ri = synth.synthetic_frame(32, 48, B=1)
     with pytest.raises(TypeError):
+        m(lf, rf, li, ri, {})
+
+
+def test_pack_runs_on_cpu_into_one_arena():
+    """BN folding and operand packing are host work: `_pack` needs no GPU, lands every tensor in one buffer (a single
+    upload) and announces exactly the operand sizes the C ABI expects."""
+    from temporalstereo_b200 import _lib
+    lib = _lib.load()
+    m = TEMPORALSTEREO()
+    m.load_state_dict(synth.synthetic_state_dict(seed=0), strict=True)
+    pk = m._pack("cpu")
+    base, n = m._arena.data_ptr(), m._arena.numel() * 4
+    for name, k in pk.items():
+        for t in [k.w, k.b] + list(k.tc.values()):
+            if t is not None:
+                assert base <= t.data_ptr() < base + n and (t.data_ptr() - base) % 256 == 0, name
+    first = pk["precise.init3d.0.conv.0"]
+    assert set(first.tc) == {"hw3", "left", "cost"}
+    assert first.tc["cost"].numel() == lib.tstereo_cost_conv_wpack_floats(128, 8, 1)
+    assert first.tc["left"].numel() == lib.tstereo_conv_hw3_tc2_wpack_floats(128, 8, 1)
+    assert pk["coarse.init3d.0.conv.0"].tc["cost"].numel() == lib.tstereo_cost_conv_wpack_floats(256, 32, 1)
+    assert "s2" in pk["coarse.init3d.1.conv1.conv.0"].tc and "dc" in pk["fine.init3d.1.conv5.conv.0"].tc
+    assert pk["precise.refinement.deconv2"].tc["dc"].numel() == lib.tstereo_deconv_hw_tc2_wpack_floats(32, 9, 1)
+
+
+def test_forward_validates_the_pyramid_geometry():
+    """Sizes that are not multiples of 16 make the reference fail with a shape error; the engine
+    must raise too instead of writing out of bounds."""
+    m = TEMPORALSTEREO().eval()
+    lf, rf, li, ri = synth.synthetic_frame(32, 48, B=1)
+    lf = [lf[0], lf[1][..., :-1, :], lf[2]]
+    fake = lambda t: type("T", (), {})()
+    with pytest.raises(ValueError, match="multiples of 16"):
+        m._check_pyramid(lf[0], lf[1], lf[2], rf[0], rf[1], rf[2], li, ri)
+
+
+def test_forward_refuses_gradients():
+    m = TEMPORALSTEREO().eval()
+    lf, rf, li, ri = synth.synthetic_frame(32, 48, B=1)
+    lf[0].requires_grad_(True)
+    with pytest.raises(NotImplementedError, match="no backward"):
         m(lf, rf, li, ri, {})
