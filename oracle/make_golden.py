@@ -91,6 +91,30 @@ def main():
         for i, t in enumerate(offs): arrs[f"off{i}"] = t.numpy()
         save("agg_temporal_96x160.npz", **arrs)
 
+        # ---- other disparity ranges: D = 256 / 320 -> 16 / 20 coarse candidates (BASELINE configs C5 / C4), temporal
+        #      mode, batch 2.  The width keeps W/16 > num_sample (narrower images leave the far candidates without any
+        #      right-image support and their costs tie).
+        from temporalstereo_b200.synth import DEFAULT_LEVELS
+        for ns, (H, W) in {16: (96, 288), 20: (96, 352)}.items():
+            lv = {k: dict(v) for k, v in DEFAULT_LEVELS.items()}
+            lv["coarse"]["num_sample"] = ns
+            agg = ref_import.build_reference_aggregation(lv)
+            agg.load_state_dict(sd, strict=True)
+            lf, rf, li, ri = synth.synthetic_frame(H, W, B=2, seed=12)
+            st = synth.synthetic_temporal_state(H, W, B=2)
+            prev = dict(prev_disp=st["prev_disp"], cost_memory=st["cost_memory"], local_map=st["local_map"])
+            batch = {"baseline": st["baseline"], ("color_aug", 0, "l"): li, ("K", 0): st["K"],
+                     ("inv_T", -1, "l"): st["inv_T_prev"], ("T", 0, "l"): st["T_now"]}
+            _, prev = tm.update_map(batch, prev, 0)
+            arrs = {"warp_mem_sample": prev["cost_memory"]["disp_sample"].numpy(),
+                    "warp_mem_cost": prev["cost_memory"]["cost_volume"].numpy(), "warp_local_map": prev["local_map"].numpy()}
+            disps, costs, samples, offs, ranges, info = agg(lf, rf, li, ri, prev_info=prev)
+            for i, t in enumerate(disps): arrs[f"disp{i}"] = t.numpy()
+            for i, t in enumerate(costs): arrs[f"cost{i}"] = t.numpy()
+            for i, t in enumerate(samples): arrs[f"sample{i}"] = t.numpy()
+            for i, t in enumerate(offs): arrs[f"off{i}"] = t.numpy()
+            save(f"agg_temporal_ns{ns}_{H}x{W}.npz", **arrs)
+
 
 if __name__ == "__main__":
     main()

@@ -55,7 +55,11 @@ for B in (8, 1):
                      ("all simt (convs on fp32 FMA), fused off", dict(plan_mode="simt", fuse_cost=False))):
         mm = engine(**kw)
         fw(mm)
-        say(f"* {name}: {timed(lambda: fw(mm)):.0f} us")
+        t_eager = timed(lambda: fw(mm))
+        from temporalstereo_b200.graph import CapturedStep
+        step = CapturedStep(lambda: fw(mm))
+        say(f"* {name}: eager {t_eager:.0f} us, CUDA graph {timed(step.replay):.0f} us ({step.launches} kernels)")
+        del step
     del m
 
 # ---- fused vs materialised first conv per level, B = 8

@@ -48,5 +48,16 @@ def install_into_reference() -> None:
     `build_aggregation(cfg)` with `MODEL.AGGREGATION.NAME == 'TEMPORALSTEREO'` returns the B200
     engine.  Requires the reference package to be importable."""
     from architecture.modeling.aggregation import builder as ref_builder  # type: ignore
+    import architecture.modeling.aggregation  # noqa: F401  (registers the reference's own class first)
     from .aggregation import TEMPORALSTEREO
-    ref_builder.AGGREGATION_REGISTRY._obj_map["TEMPORALSTEREO"] = TEMPORALSTEREO
+    registry_map(ref_builder.AGGREGATION_REGISTRY)["TEMPORALSTEREO"] = TEMPORALSTEREO
+
+
+def registry_map(reg) -> dict:
+    """The name -> class table of a detectron2 / fvcore `Registry` (`_obj_map`) or of a stand-in with the same
+    `register()` / `get()` behaviour."""
+    for attr in ("_obj_map", "_map"):
+        m = getattr(reg, attr, None)
+        if isinstance(m, dict):
+            return m
+    raise TypeError(f"{type(reg).__name__} exposes no name table")

@@ -80,3 +80,15 @@ def test_argument_validation_needs_no_gpu(lib):
     assert b"null" in lib.tstereo_last_error()
     with pytest.raises(_lib.TStereoError):
         _lib.call("tstereo_predict_disp", None, None, None, None, None, None, 1, 4, 8, 8, None)
+
+
+def test_reference_splat_library_loads():
+    """oracle/_ref/libsoftsplat_ref.so (the reference's own splat kernel, built by oracle/build_softsplat_ref.py in the
+    build container) loads without a GPU and exports its launcher."""
+    path = os.path.join(ROOT, "oracle", "_ref", "libsoftsplat_ref.so")
+    if not os.path.exists(path):
+        if not os.path.isdir("/root/reference"):
+            pytest.skip("no reference tree and no prebuilt oracle/_ref")
+        import subprocess, sys
+        subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "build_softsplat_ref.py")], check=True)
+    assert hasattr(ctypes.CDLL(path), "softsplat_ref_launch")

@@ -71,7 +71,7 @@ def _check(out, ref, what):
     for i in (1, 2, 3):
         assert rep[f"disp{i}"][0] < EPE_TOL, f"{what}: disp{i} EPE {rep[f'disp{i}'][0]:.3e}"
     # the coarse candidate list is pure index work (sorted integers + zero memory): exact
-    assert rep["sample2"][0] == 0.0 or rep["sample2"][0] < 1e-4, f"{what}: coarse samples differ {rep['sample2']}"
+    assert rep["sample2"][0] < 2e-5, f"{what}: coarse samples differ {rep['sample2']}"      # exact in single-frame mode (asserted there)
     return rep
 
 
@@ -111,6 +111,34 @@ def test_temporal_frame_matches_reference_golden(engine, golden_dir):
     _check(out, ref, "golden temporal 96x160")
 
 
+@pytest.mark.parametrize("ns,H,W", [(16, 96, 288), (20, 96, 352)])
+def test_other_disparity_ranges_match_reference_golden(golden_dir, ns, H, W):
+    """D = 256 / 320 (16 / 20 coarse candidates, BASELINE configs C5 / C4), temporal mode, B=2, against outputs of the REAL
+    reference.  The aggregation starts from the reference's own warped state (stored in the golden), so the discontinuous
+    splat normalisation cannot leak into the comparison; the engine's warp is compared with it in the bulk."""
+    from temporalstereo_b200 import temporal
+    from temporalstereo_b200.aggregation import TEMPORALSTEREO
+    g = _load(golden_dir, f"agg_temporal_ns{ns}_{H}x{W}.npz")
+    eng = TEMPORALSTEREO(coarse=dict(num_sample=ns))
+    eng.load_state_dict(synth.synthetic_state_dict(seed=0), strict=True)
+    eng = eng.cuda().eval()
+    lf, rf, li, ri = synth.synthetic_frame(H, W, B=2, seed=12)
+    st = synth.synthetic_temporal_state(H, W, B=2)
+    own = temporal.update_map(_cuda(dict(prev_disp=st["prev_disp"], cost_memory=dict(st["cost_memory"]), local_map=st["local_map"])),
+                              st["K"].cuda(), st["T_now"].cuda(), st["inv_T_prev"].cuda(), st["baseline"].cuda(), H, W, True, 3)
+    for got, key in ((own["cost_memory"]["disp_sample"], "warp_mem_sample"), (own["cost_memory"]["cost_volume"], "warp_mem_cost"),
+                     (own["local_map"], "warp_local_map")):
+        d = (got.cpu() - g[key]).abs()
+        assert d.median() < 1e-5 and (d > 1e-3).float().mean() < 0.01, (key, d.median().item())
+    prev = _cuda(dict(prev_disp=st["prev_disp"], use_past_cost=True, local_map_size=3, local_map=g["warp_local_map"],
+                      cost_memory=dict(disp_sample=g["warp_mem_sample"], cost_volume=g["warp_mem_cost"])))
+    out = eng(_cuda(lf), _cuda(rf), li.cuda(), ri.cuda(), prev)
+    ref = ([g[f"disp{i}"] for i in range(4)], [g[f"cost{i}"] for i in range(3)],
+           [g[f"sample{i}"] for i in range(3)], [g[f"off{i}"] for i in range(3)])
+    assert out[2][2].shape[1] == ns + 2 and out[2][1].shape[1] == 10
+    _check(out, ref, f"golden temporal D={16 * ns} {H}x{W} B=2")
+
+
 @pytest.mark.parametrize("H,W,B", [(320, 576, 1), (544, 960, 1), (96, 112, 3)])
 def test_single_frame_vs_oracle(engine, H, W, B):
     """BASELINE configs C1 (320x576) and C2 (540x960 -> 544x960), plus a batched ragged case."""
@@ -119,7 +147,8 @@ def test_single_frame_vs_oracle(engine, H, W, B):
     with torch.no_grad():
         want = O.aggregation_forward(sd, lf, rf, li, ri, {})
     out = engine(_cuda(lf), _cuda(rf), li.cuda(), ri.cuda(), {})
-    _check(out, want[:4], f"oracle single {H}x{W} B={B}")
+    rep = _check(out, want[:4], f"oracle single {H}x{W} B={B}")
+    assert rep["sample2"][0] == 0.0, "single-frame coarse candidates are pure index work: exact"
     # top-2 index work: the stored memory is top-2 (sample+offset)/2 resized; compare as EPE
     d = (out[5]["cost_memory"]["disp_sample"].cpu() - want[5]["cost_memory"]["disp_sample"]).abs().mean()
     assert d < EPE_TOL, d

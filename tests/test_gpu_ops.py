@@ -468,6 +468,53 @@ def test_softsplat_vs_oracle():
     assert torch.equal((got.cpu() == 0).all(1), holes), "hole pattern (pixels nobody splats to) differs"
 
 
+def _ref_splat_lib():
+    import ctypes
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = os.path.join(root, "oracle", "_ref", "libsoftsplat_ref.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libsoftsplat_ref.so not built (python oracle/build_softsplat_ref.py, needs /root/reference)")
+    lib = ctypes.CDLL(path)
+    lib.softsplat_ref_launch.restype = ctypes.c_int
+    lib.softsplat_ref_launch.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int] * 4 + [ctypes.c_void_p]
+    return lib
+
+
+def _splat_case(i, B, C, h, w):
+    x = rnd(B, C, h, w, seed=70 + i)
+    flow = rnd(B, 2, h, w, seed=80 + i, scale=2.5)
+    flow[0, :, 0, 0] = torch.tensor([-30.0, 4.0])      # lands outside: contributes nowhere
+    flow[0, :, 1, 1] = torch.tensor([1.0, -1.0])       # exactly on a pixel centre
+    flow[0, :, 2, 2] = torch.tensor([w - 3.5, 0.25])   # straddles the right border: two corners dropped
+    metric = rnd(B, 1, h, w, seed=90 + i, scale=3.0)
+    return x, flow, metric
+
+
+def test_softsplat_vs_reference_kernel():
+    """Row a19 pinned to the reference's OWN kernel: oracle/_ref/libsoftsplat_ref.so is kernel_Softsplat_updateOutput
+    (softsplat.py:8-53) expanded by the reference's cupy_kernel (softsplat.py:179-232) and compiled with nvcc.  The packing
+    and normalisation around it follow FunctionSoftsplat 'softmax' (softsplat.py:344-356).  Both sides add with float
+    atomics, so the comparison carries a summation-order tolerance; the hole pattern must be identical."""
+    from oracle.softsplat_shapes import SHAPES
+    from temporalstereo_b200 import temporal
+    lib = _ref_splat_lib()
+    for i, (B, C, h, w) in enumerate(SHAPES):
+        x, flow, metric = _splat_case(i, B, C, h, w)
+        xg, fg, mg = x.cuda(), flow.cuda(), metric.cuda()
+        packed = torch.cat([xg * mg.exp(), mg.exp()], 1).contiguous()
+        acc = torch.zeros_like(packed)
+        rc = lib.softsplat_ref_launch(packed.data_ptr(), fg.data_ptr(), acc.data_ptr(), B, C + 1, h, w,
+                                      torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert rc == 0, f"reference kernel launch failed for shape {(B, C, h, w)}: {rc}"
+        want = (acc[:, :-1] / (acc[:, -1:] + 1e-22)).cpu()
+        got = temporal.FunctionSoftsplat(xg, fg, mg, "softmax")
+        close(got, want, 2e-5, rtol=1e-5, what=f"splat vs reference kernel {(B, C, h, w)}")
+        assert torch.equal((got.cpu() == 0).all(1), (want == 0).all(1)), "hole pattern differs from the reference kernel"
+        # and the CPU restatement the rest of the temporal tests lean on is pinned by the same kernel
+        close(O.softsplat_softmax(x, flow, metric), want, 2e-5, rtol=1e-5, what="oracle splat vs reference kernel")
+
+
 @pytest.mark.parametrize("first_frame", [False, True])
 def test_update_map_vs_oracle(golden_dir, first_frame):
     from temporalstereo_b200 import temporal

@@ -87,3 +87,21 @@ def test_temporal_matches_reference(golden_dir):
         torch.testing.assert_close(prev["local_map"], gm["local_map"], rtol=1e-5, atol=1e-4)
         out = O.aggregation_forward(sd, lf, rf, li, ri, prev)
     _check_agg(out, g)
+
+
+@pytest.mark.parametrize("ns,H,W", [(16, 96, 288), (20, 96, 352)])
+def test_other_disparity_ranges_match_reference(golden_dir, ns, H, W):
+    """D = 256 / 320 (16 / 20 coarse candidates: BASELINE configs C5 / C4), temporal mode, batch 2."""
+    g = _load(golden_dir, f"agg_temporal_ns{ns}_{H}x{W}.npz")
+    sd = synth.synthetic_state_dict(seed=0)
+    lf, rf, li, ri = synth.synthetic_frame(H, W, B=2, seed=12)
+    st = synth.synthetic_temporal_state(H, W, B=2)
+    prev = dict(prev_disp=st["prev_disp"], cost_memory=dict(st["cost_memory"]), local_map=st["local_map"])
+    with torch.no_grad():
+        prev = O.update_map(prev, st["K"], st["T_now"], st["inv_T_prev"], st["baseline"], H, W, True, 3)
+        torch.testing.assert_close(prev["cost_memory"]["disp_sample"], g["warp_mem_sample"], rtol=1e-5, atol=1e-4)
+        torch.testing.assert_close(prev["cost_memory"]["cost_volume"], g["warp_mem_cost"], rtol=1e-5, atol=1e-4)
+        torch.testing.assert_close(prev["local_map"], g["warp_local_map"], rtol=1e-5, atol=1e-4)
+        out = O.aggregation_forward(sd, lf, rf, li, ri, prev, num_sample=ns)
+    _check_agg(out, g)
+    assert out[2][2].shape[1] == ns + 2
