@@ -73,11 +73,11 @@ int tstereo_group_cost_warp(const float* left, const float* right, const float* 
 long long tstereo_cost_conv_wpack_floats(int C, int Cout, int half);
 int tstereo_cost_conv_warp(const float* right, const float* samples, const float* gvol, const float* addL,
                            float* out, long long osB, long long osC, long long osD,
-                           const float* wpack, const float* bias,
+                           const float* wpack, const float* bias, const float* oscale,
                            int B, int C, int Cout, int S, int H, int W, int act, int half, void* stream);
 int tstereo_cost_conv_shift(const float* left, const float* right, const float* gvol,
                             float* out, long long osB, long long osC, long long osD,
-                            const float* wpack, const float* bias,
+                            const float* wpack, const float* bias, const float* oscale,
                             int B, int C, int Cout, int D, int H, int W, int act, int half, void* stream);
 
 /* ---------------------------------------------------------------- convolutions (a4-a7, a9, a12, a13)
@@ -107,7 +107,7 @@ int tstereo_conv_hw3(const float* in, long long isB, long long isC, long long is
 long long tstereo_conv_hw3_tc2_wpack_floats(int Cin, int Cout, int half);
 int tstereo_conv_hw3_tc2(const float* in, long long isB, long long isC, long long isD,
                          float* out, long long osB, long long osC, long long osD,
-                         const float* wpack, const float* bias,
+                         const float* wpack, const float* bias, const float* oscale,
                          int B, int Cin, int Cout, int D, int H, int W,
                          int dilation, int act, int half, void* stream);
 /* Stride-2 3x3 conv (padding 1) and stride-2 transposed convs through the same tensor-core kernel
@@ -122,12 +122,12 @@ int tstereo_conv_hw3_tc2(const float* in, long long isB, long long isC, long lon
 long long tstereo_conv_hw3s2_tc2_wpack_floats(int Cin, int Cout, int half);
 int tstereo_conv_hw3s2_tc2(const float* in, long long isB, long long isC, long long isD,
                            float* out, long long osB, long long osC, long long osD,
-                           const float* wpack, const float* bias,
+                           const float* wpack, const float* bias, const float* oscale,
                            int B, int Cin, int Cout, int D, int Hin, int Win, int act, int half, void* stream);
 long long tstereo_deconv_hw_tc2_wpack_floats(int Cin, int Cout, int half);
 int tstereo_deconv_hw_tc2(const float* in, long long isB, long long isC, long long isD,
                           float* out, long long osB, long long osC, long long osD,
-                          const float* wpack, const float* bias,
+                          const float* wpack, const float* bias, const float* oscale,
                           int B, int Cin, int Cout, int D, int Hin, int Win, int act, int half, void* stream);
 /* (k,1,1) conv along D (same argument meaning as tstereo_conv_d) through the tensor-core
  * kernel: the k input planes are K-chunks of a 1x1 conv.  wpack: pack_conv_d_tc2 in temporalstereo_b200/ops.py,
@@ -135,7 +135,7 @@ int tstereo_deconv_hw_tc2(const float* in, long long isB, long long isC, long lo
 long long tstereo_conv_d_tc2_wpack_floats(int Cin, int Cout, int k, int half);
 int tstereo_conv_d_tc2(const float* in, long long isB, long long isC, long long isD,
                        float* out, long long osB, long long osC, long long osD,
-                       const float* wpack, const float* bias,
+                       const float* wpack, const float* bias, const float* oscale,
                        int B, int Cin, int Cout, int Din, int Dout, int H, int W,
                        int k, int stride, int dilation, int transposed, int act, int half, void* stream);
 

@@ -26,17 +26,17 @@ SIGNATURES = {
     "tstereo_group_cost_shift": (I, [P, P, P, P, I, I, I, I, I, P]),
     "tstereo_group_cost_warp": (I, [P, P, P, P, P, I, I, I, I, I, P]),
     "tstereo_cost_conv_wpack_floats": (LL, [I, I, I]),
-    "tstereo_cost_conv_warp": (I, [P, P, P, P, P, LL, LL, LL, P, P, I, I, I, I, I, I, I, I, P]),
-    "tstereo_cost_conv_shift": (I, [P, P, P, P, LL, LL, LL, P, P, I, I, I, I, I, I, I, I, P]),
+    "tstereo_cost_conv_warp": (I, [P, P, P, P, P, LL, LL, LL, P, P, P, I, I, I, I, I, I, I, I, P]),
+    "tstereo_cost_conv_shift": (I, [P, P, P, P, LL, LL, LL, P, P, P, I, I, I, I, I, I, I, I, P]),
     "tstereo_conv_hw3": (I, [P, LL, LL, LL, P, LL, LL, LL, P, P, I, I, I, I, I, I, I, I, I, I, I, P]),
     "tstereo_conv_hw3_tc2_wpack_floats": (LL, [I, I, I]),
-    "tstereo_conv_hw3_tc2": (I, [P, LL, LL, LL, P, LL, LL, LL, P, P, I, I, I, I, I, I, I, I, I, P]),
+    "tstereo_conv_hw3_tc2": (I, [P, LL, LL, LL, P, LL, LL, LL, P, P, P, I, I, I, I, I, I, I, I, I, P]),
     "tstereo_conv_hw3s2_tc2_wpack_floats": (LL, [I, I, I]),
-    "tstereo_conv_hw3s2_tc2": (I, [P, LL, LL, LL, P, LL, LL, LL, P, P, I, I, I, I, I, I, I, I, P]),
+    "tstereo_conv_hw3s2_tc2": (I, [P, LL, LL, LL, P, LL, LL, LL, P, P, P, I, I, I, I, I, I, I, I, P]),
     "tstereo_deconv_hw_tc2_wpack_floats": (LL, [I, I, I]),
-    "tstereo_deconv_hw_tc2": (I, [P, LL, LL, LL, P, LL, LL, LL, P, P, I, I, I, I, I, I, I, I, P]),
+    "tstereo_deconv_hw_tc2": (I, [P, LL, LL, LL, P, LL, LL, LL, P, P, P, I, I, I, I, I, I, I, I, P]),
     "tstereo_conv_d_tc2_wpack_floats": (LL, [I, I, I, I]),
-    "tstereo_conv_d_tc2": (I, [P, LL, LL, LL, P, LL, LL, LL, P, P, I, I, I, I, I, I, I, I, I, I, I, I, I, P]),
+    "tstereo_conv_d_tc2": (I, [P, LL, LL, LL, P, LL, LL, LL, P, P, P, I, I, I, I, I, I, I, I, I, I, I, I, I, P]),
     "tstereo_conv_d": (I, [P, LL, LL, LL, P, LL, LL, LL, P, P, I, I, I, I, I, I, I, I, I, I, I, P]),
     "tstereo_deconv_hw": (I, [P, LL, LL, LL, P, LL, LL, LL, P, P, I, I, I, I, I, I, I, I, P]),
     "tstereo_copy_planes": (I, [P, P, LL, LL, I, I, I, P]),

@@ -41,11 +41,12 @@ class _Packed:
     kernels, `tc[kind]` the tensor-core operand images ("hw3" stride-1 3x3, "s2" stride-2 3x3, "dc" stride-2
     transposed, "d" (k,1,1) along D, "cost" / "left" the fused cost -> first-conv pair).  Built on the CPU and
     uploaded once per checkpoint load."""
-    __slots__ = ("w", "b", "cout", "tc")
+    __slots__ = ("w", "b", "cout", "tc", "osc")
 
-    def __init__(self, w, b, cout, tc=None):
+    def __init__(self, w, b, cout, tc=None, osc=None):
         self.w, self.b, self.cout = w, b, cout
         self.tc = tc or {}
+        self.osc = osc          # fp16 split: 1 / the per-output-channel weight pre-scale (ops.fp16_prescale), else None
 
 
 def _level_cfg(node, defaults: dict) -> dict:
@@ -101,9 +102,11 @@ class TEMPORALSTEREO(nn.Module):
         self.plan_mode = "auto"
         self._plan: Dict[tuple, str] = {}
         self._plan_times: Dict[tuple, dict] = {}
-        # the raw cost volumes never touch HBM: each level's first (1,3,3) conv rebuilds them in its producer
-        # (ops.cost_conv_*); False materialises them with ops.block_cost (the drop-in operator) first
-        self.fuse_cost = True
+        # the raw cost volume of a level never touches HBM: its first (1,3,3) conv rebuilds it in the producer
+        # (ops.cost_conv_*).  True / False / a collection of level names.  Default: the two warp levels (fine, precise:
+        # the left half of the volume is hoisted out of the candidate loop, -23 % / -20 % measured); the coarse shift
+        # volume (34 MB per frame, nothing to hoist) is cheaper materialised with ops.block_cost (B200: 406 vs 581 us at B=8)
+        self.fuse_cost = ("fine", "precise")
         self._warned_train = False
         # tensor-core operand split: fp16 hi + lo (kind::f16, 16 channels per MMA; activations < 65504) or tf32 hi + lo
         self.half_split = True
@@ -206,19 +209,28 @@ class TEMPORALSTEREO(nn.Module):
         cout, cin, T = w.shape
         packed = torch.zeros((cin, T, (cout + 3) // 4 * 4), dtype=torch.float32)
         packed[:, :, :cout] = w.permute(1, 2, 0)
-        tc = {}
+        tc, osc = {}, None
         if self.tensor_cores:
             h = self.half_split
+            ws = w
+            if h:
+                ws, osc = ops.fp16_prescale(w)
             for kind in kinds:
                 if kind == "hw3" and cin >= 8 and T == 9:
-                    tc[kind] = ops.pack_conv_hw3_tc2(w, h)
+                    tc[kind] = ops.pack_conv_hw3_tc2(ws, h)
                 elif kind == "s2" and T == 9:
-                    tc[kind] = ops.pack_conv_hw3s2_tc2(w, h)
+                    tc[kind] = ops.pack_conv_hw3s2_tc2(ws, h)
                 elif kind == "dc" and cin >= 8:
-                    tc[kind] = ops.pack_deconv_hw_tc2(w, ksz, h)
+                    tc[kind] = ops.pack_deconv_hw_tc2(ws, ksz, h)
                 elif kind == "d" and cin >= 8 and T in (3, 5):
-                    tc[kind] = ops.pack_conv_d_tc2(w, h)
-        return _Packed(packed, bias, cout, tc)
+                    tc[kind] = ops.pack_conv_d_tc2(ws, h)
+                elif kind == "cost_warp":          # [L (C) | warp(R) (C) | g (3C/8)]: the L half is hoisted out of the D loop
+                    C = cin * 8 // 19
+                    tc["left"] = ops.pack_conv_hw3_tc2(ws[:, :C].contiguous(), h)
+                    tc["cost"] = ops.pack_conv_hw3_tc2(ws[:, C:].contiguous(), h)
+                elif kind == "cost_shift":         # [-(L - R_d)^2 (C) | g (3C/8)]
+                    tc["cost"] = ops.pack_conv_hw3_tc2(ws, h)
+        return _Packed(packed, bias, cout, tc, osc if tc else None)
 
     def _pack(self, dev) -> Dict[str, _Packed]:
         """BatchNorm folding and operand packing run on the CPU; every packed tensor lands in ONE device buffer with
@@ -234,16 +246,13 @@ class TEMPORALSTEREO(nn.Module):
             w1, b1 = fold(sd, f"{p}.conv.1", f"{p}.conv.1.norm", transposed)
             pk[f"{p}.conv.1"] = mk(w1, b1, ("d",))
 
-        def init3d(p, C, warp):
-            sep(p + ".0")
-            first = pk[p + ".0.conv.0"]
-            if self.tensor_cores:           # fused cost -> first conv: virtual channels [feature half | group terms]
-                w0, _ = fold(sd, f"{p}.0.conv.0", f"{p}.0.conv.0.norm")
-                if warp:                    # [L (C) | warp(R) (C) | g (3C/8)]: the L half is hoisted out of the D loop
-                    first.tc["left"] = ops.pack_conv_hw3_tc2(w0[:, :C].contiguous(), self.half_split)
-                    first.tc["cost"] = ops.pack_conv_hw3_tc2(w0[:, C:].contiguous(), self.half_split)
-                else:                       # [-(L - R_d)^2 (C) | g (3C/8)]
-                    first.tc["cost"] = ops.pack_conv_hw3_tc2(w0, self.half_split)
+        def init3d(p, warp):
+            # first conv: also the operand images of the fused cost -> first-conv path (virtual channels
+            # [feature half | group terms])
+            w0, b0 = fold(sd, f"{p}.0.conv.0", f"{p}.0.conv.0.norm")
+            pk[f"{p}.0.conv.0"] = mk(w0, b0, ("hw3", "cost_warp" if warp else "cost_shift"))
+            w1, b1 = fold(sd, f"{p}.0.conv.1", f"{p}.0.conv.1.norm")
+            pk[f"{p}.0.conv.1"] = mk(w1, b1, ("d",))
             sep(f"{p}.1.conv1", stride=2)
             sep(f"{p}.1.conv2")
             sep(f"{p}.1.conv3", stride=2)
@@ -264,7 +273,7 @@ class TEMPORALSTEREO(nn.Module):
 
         for lvl in ("coarse", "fine"):
             cfg = self.levels[lvl]
-            init3d(f"{lvl}.init3d", cfg["in_planes"], lvl == "fine")
+            init3d(f"{lvl}.init3d", lvl == "fine")
             w, b = fold(sd, f"{lvl}.past_conv", f"{lvl}.past_conv.norm")
             pk[f"{lvl}.past_conv"] = _Packed(w[:, 0, 0].contiguous(), b, w.shape[0])
             w, b = fold(sd, f"{lvl}.fuse.conv_5x5", f"{lvl}.fuse.conv_5x5.norm")
@@ -276,7 +285,7 @@ class TEMPORALSTEREO(nn.Module):
             pk[m + ".0"] = mk(w, b, ("hw3",))
             pk[m + ".3"] = _Packed(sd[m + ".3.weight"].reshape(36, 64).contiguous(), sd[m + ".3.bias"].contiguous(), 36)
         r = "precise.refinement"
-        init3d("precise.init3d", self.levels["precise"]["in_planes"] + sd[f"{r}.conv4.1.weight"].shape[0], True)
+        init3d("precise.init3d", True)
         heads("precise.pred_heads")
         for n, stride in (("conv2.0", 2), ("conv2.1", 1), ("conv4.0", 2), ("conv4.1", 1), ("fuse.0", 1), ("fuse.1", 1), ("concat", 1)):
             w, b = fold(sd, f"{r}.{n}", f"{r}.{n}.norm")
@@ -292,6 +301,8 @@ class TEMPORALSTEREO(nn.Module):
             items.append((k, "w", None))
             if k.b is not None:
                 items.append((k, "b", None))
+            if k.osc is not None:
+                items.append((k, "osc", None))
             items += [(k, "tc", name) for name in k.tc]
         get = lambda k, f, n: (k.tc[n] if f == "tc" else getattr(k, f))
         offs, total = [], 0
@@ -315,18 +326,23 @@ class TEMPORALSTEREO(nn.Module):
 
     # ------------------------------------------------------------------ building blocks
     @staticmethod
-    def _rule(kind: str, x_shape, cout: int) -> str:
-        """Deterministic kernel choice from the layer shape alone (measured on B200, profiles/r02_plan_*.md): the
-        tensor-core kernel has a fixed cost of ~10 us per launch (TMEM allocation, barrier set-up, a serial chunk
-        pipeline per CTA), which the fp32 FMA kernels undercut on the small hourglass volumes and on the narrow
-        (k,1,1) convs whose arithmetic intensity is a few MACs per byte."""
+    def _rule(kind: str, x_shape, cout: int, ksz: int = 3) -> str:
+        """Deterministic kernel choice from the layer shape alone, fitted to device times measured on B200 at B = 1 and
+        B = 8 (profiles/r02_plan_probe.md; `plan_mode = "timed"` re-measures).  3x3 forms: the tensor-core kernel always
+        wins.  (k,1,1) convs along D: it wins for 32 input channels, loses for <= 16 (a few MACs per byte: the fp32 FMA
+        kernel streams at HBM speed) and for 64 (two 32-channel output groups, each a 24-chunk latency chain).  Stride-2
+        transposed convs are four phase launches on the tensor cores: worth it only with enough work per launch."""
         cin = x_shape[1]
         planes = x_shape[0] * (x_shape[2] if len(x_shape) == 5 else 1)
         hw = x_shape[-2] * x_shape[-1]
         if kind == "d":
-            return "simt" if (cin <= 16 and cout <= 16) or planes * hw < 200_000 else "tc2"
-        if kind in ("hw3", "hw3s2", "dc"):
-            return "simt" if planes * hw < 100_000 and cin * cout <= 64 * 64 and hw <= 34 * 60 else "tc2"
+            if cin >= 64 or cin < 16:
+                return "simt"
+            if cin >= 32:
+                return "tc2"
+            return "tc2" if (ksz == 5 or cout > 16) else "simt"
+        if kind == "dc":
+            return "tc2" if (cin >= 64 and planes * hw >= 20000) or hw >= 30000 else "simt"
         return "tc2"
 
     def _pick(self, key, cands):
@@ -339,7 +355,7 @@ class TEMPORALSTEREO(nn.Module):
         if len(names) == 1:
             choice = names[0]
         elif mode == "auto":
-            choice = self._rule(key[0], key[1], key[2])
+            choice = self._rule(key[0], key[1], key[2], key[3] if key[0] == "d" else 3)
             if choice not in cands:
                 choice = names[0]
         elif mode != "timed":
@@ -380,11 +396,11 @@ class TEMPORALSTEREO(nn.Module):
         h = self.half_split
         if stride == 2 and dil == 1 and "s2" in k.tc:
             return self._pick(("hw3s2", tuple(x.shape), k.cout),
-                              {"tc2": lambda: ops.conv_hw3s2_tc2(x, k.tc["s2"], k.b, k.cout, act, out=out, half=h), "simt": simt})
+                              {"tc2": lambda: ops.conv_hw3s2_tc2(x, k.tc["s2"], k.b, k.cout, act, out=out, half=h, oscale=k.osc), "simt": simt})
         if stride != 1 or "hw3" not in k.tc:
             return simt()
         return self._pick(("hw3", tuple(x.shape), k.cout, dil),
-                          {"tc2": lambda: ops.conv_hw3_tc2(x, k.tc["hw3"], k.b, k.cout, dil, act, out=out, half=h), "simt": simt})
+                          {"tc2": lambda: ops.conv_hw3_tc2(x, k.tc["hw3"], k.b, k.cout, dil, act, out=out, half=h, oscale=k.osc), "simt": simt})
 
     def _d(self, x, k: _Packed, ksz=3, stride=1, dil=1, transposed=False, act=None, out=None):
         """(k,1,1) conv along D: tensor cores when a tcgen05 operand image exists."""
@@ -393,7 +409,7 @@ class TEMPORALSTEREO(nn.Module):
             return simt()
         key = ("d", tuple(x.shape), k.cout, ksz, stride, dil, transposed)
         return self._pick(key, {"tc2": lambda: ops.conv_d_tc2(x, k.tc["d"], k.b, k.cout, ksz, stride, dil, transposed, act, out=out,
-                                                              half=self.half_split),
+                                                              half=self.half_split, oscale=k.osc),
                                 "simt": simt})
 
     def _deconv_hw(self, x, k: _Packed, ksz, act=None, out=None):
@@ -402,7 +418,7 @@ class TEMPORALSTEREO(nn.Module):
         if "dc" not in k.tc:
             return simt()
         return self._pick(("dc", tuple(x.shape), k.cout, ksz),
-                          {"tc2": lambda: ops.deconv_hw_tc2(x, k.tc["dc"], k.b, k.cout, act, out=out, half=self.half_split),
+                          {"tc2": lambda: ops.deconv_hw_tc2(x, k.tc["dc"], k.b, k.cout, act, out=out, half=self.half_split, oscale=k.osc),
                            "simt": simt})
 
     def _sep(self, x, p, stride=1, dil=1, act0="SiLU", act1="SiLU", out=None):
@@ -435,13 +451,14 @@ class TEMPORALSTEREO(nn.Module):
         candidate tensor [B,S,H,W] (warp volume) or an int (shift volume).  With `fuse_cost` the raw volume is never
         materialised: group-wise terms (small side kernel) + the first (1,3,3) conv rebuilding the feature half."""
         a, b = self._pk[p + ".0.conv.0"], self._pk[p + ".0.conv.1"]
-        if self.fuse_cost and "cost" in a.tc:
+        fuse = self.fuse_cost if isinstance(self.fuse_cost, bool) else p.split(".")[0] in self.fuse_cost
+        if fuse and "cost" in a.tc:
             g = ops.group_cost(left, right, samples)
             if isinstance(samples, int):
-                y = ops.cost_conv_shift(left, right, g, a.tc["cost"], a.b, a.cout, "SiLU", half=self.half_split)
+                y = ops.cost_conv_shift(left, right, g, a.tc["cost"], a.b, a.cout, "SiLU", half=self.half_split, oscale=a.osc)
             else:
-                addl = ops.conv_hw3_tc2(left, a.tc["left"], None, a.cout, 1, None, half=self.half_split)
-                y = ops.cost_conv_warp(right, samples, g, addl, a.tc["cost"], a.b, a.cout, "SiLU", half=self.half_split)
+                addl = ops.conv_hw3_tc2(left, a.tc["left"], None, a.cout, 1, None, half=self.half_split, oscale=a.osc)
+                y = ops.cost_conv_warp(right, samples, g, addl, a.tc["cost"], a.b, a.cout, "SiLU", half=self.half_split, oscale=a.osc)
         else:
             y = self._hw3(ops.block_cost(left, right, samples), a, 1, 1, "SiLU")
         y = self._d(y, b, 3, 1, 1, False, "SiLU")

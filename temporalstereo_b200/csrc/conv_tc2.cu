@@ -14,7 +14,7 @@ long long tstereo_conv_hw3_tc2_wpack_floats(int Cin, int Cout, int half) { retur
 
 int tstereo_conv_hw3_tc2(const float* in, long long isB, long long isC, long long isD,
                          float* out, long long osB, long long osC, long long osD,
-                         const float* wpack, const float* bias,
+                         const float* wpack, const float* bias, const float* oscale,
                          int B, int Cin, int Cout, int D, int H, int W,
                          int dilation, int act, int half, void* stream) {
     TS_REQUIRE(in && out && wpack, "conv_hw3_tc2: null pointer");
@@ -27,7 +27,7 @@ int tstereo_conv_hw3_tc2(const float* in, long long isB, long long isC, long lon
     tc2::Params p = {};
     p.in = in; p.isB = isB; p.isC = (int)isC; p.isD = isD;
     p.out = out; p.osB = osB; p.osC = (int)osC; p.osD = osD;
-    p.wpack = wpack; p.bias = bias;
+    p.wpack = wpack; p.bias = bias; p.oscale = oscale;
     p.Cin = Cin; p.H = H; p.W = W; p.D = D; p.Hin = H; p.Win = W;
     p.isY = W; p.isX = 1; p.osY = W; p.osX = 1;
     p.dil = dilation; p.act = act; p.nky = 3; p.half = half != 0;
@@ -41,7 +41,7 @@ long long tstereo_conv_hw3s2_tc2_wpack_floats(int Cin, int Cout, int half) { ret
 
 int tstereo_conv_hw3s2_tc2(const float* in, long long isB, long long isC, long long isD,
                            float* out, long long osB, long long osC, long long osD,
-                           const float* wpack, const float* bias,
+                           const float* wpack, const float* bias, const float* oscale,
                            int B, int Cin, int Cout, int D, int Hin, int Win, int act, int half, void* stream) {
     TS_REQUIRE(in && out && wpack, "conv_hw3s2_tc2: null pointer");
     TS_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && D > 0 && Hin > 0 && Win > 0, "conv_hw3s2_tc2: bad sizes");
@@ -53,7 +53,7 @@ int tstereo_conv_hw3s2_tc2(const float* in, long long isB, long long isC, long l
     tc2::Params p = {};
     p.in = in; p.isB = isB; p.isC = (int)isC; p.isD = isD;
     p.out = out; p.osB = osB; p.osC = (int)osC; p.osD = osD;
-    p.wpack = wpack; p.bias = bias;
+    p.wpack = wpack; p.bias = bias; p.oscale = oscale;
     p.Cin = Cin; p.H = H; p.W = W; p.D = D; p.Hin = Hin; p.Win = Win;
     p.isY = 2 * Win; p.isX = 2; p.osY = W; p.osX = 1;
     p.dil = 1; p.act = act; p.nky = 3; p.half = half != 0;
@@ -67,7 +67,7 @@ long long tstereo_deconv_hw_tc2_wpack_floats(int Cin, int Cout, int half) { retu
 
 int tstereo_deconv_hw_tc2(const float* in, long long isB, long long isC, long long isD,
                           float* out, long long osB, long long osC, long long osD,
-                          const float* wpack, const float* bias,
+                          const float* wpack, const float* bias, const float* oscale,
                           int B, int Cin, int Cout, int D, int Hin, int Win, int act, int half, void* stream) {
     TS_REQUIRE(in && out && wpack, "deconv_hw_tc2: null pointer");
     TS_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && D > 0 && Hin > 0 && Win > 0, "deconv_hw_tc2: bad sizes");
@@ -78,7 +78,7 @@ int tstereo_deconv_hw_tc2(const float* in, long long isB, long long isC, long lo
     tc2::Params p = {};
     p.in = in; p.isB = isB; p.isC = (int)isC; p.isD = isD;
     p.osB = osB; p.osC = (int)osC; p.osD = osD;
-    p.bias = bias;
+    p.bias = bias; p.oscale = oscale;
     p.Cin = Cin; p.H = Hin; p.W = Win; p.D = D; p.Hin = Hin; p.Win = Win;
     p.isY = Win; p.isX = 1; p.osY = 4 * Win; p.osX = 2;      // output plane is (2*Hin) x (2*Win)
     p.dil = 1; p.act = act; p.nky = 3; p.half = half != 0;
@@ -102,7 +102,7 @@ long long tstereo_conv_d_tc2_wpack_floats(int Cin, int Cout, int k, int half) {
 
 int tstereo_conv_d_tc2(const float* in, long long isB, long long isC, long long isD,
                        float* out, long long osB, long long osC, long long osD,
-                       const float* wpack, const float* bias,
+                       const float* wpack, const float* bias, const float* oscale,
                        int B, int Cin, int Cout, int Din, int Dout, int H, int W,
                        int k, int stride, int dilation, int transposed, int act, int half, void* stream) {
     TS_REQUIRE(in && out && wpack, "conv_d_tc2: null pointer");
@@ -121,7 +121,7 @@ int tstereo_conv_d_tc2(const float* in, long long isB, long long isC, long long 
     tc2::Params p = {};
     p.in = in; p.isB = isB; p.isC = (int)isC; p.isD = isD;
     p.out = out; p.osB = osB; p.osC = (int)osC; p.osD = osD;
-    p.wpack = wpack; p.bias = bias;
+    p.wpack = wpack; p.bias = bias; p.oscale = oscale;
     p.Cin = Cin; p.H = H; p.W = W; p.D = Dout; p.Hin = H; p.Win = W;
     p.isY = W; p.isX = 1; p.osY = W; p.osX = 1;
     p.dil = 0; p.act = act; p.nky = 1; p.half = half != 0; p.fold = half ? 1 : 3;

@@ -76,6 +76,7 @@ struct Params {
     int isC, osC;         // channel strides (elements); < 2^31, checked by the host
     const float* wpack;   // [nchunk][ky nky][khalf 2][row 2N][4], row = part*N + kx*CP + co
     const float* bias;    // [Cout] or null
+    const float* oscale;  // [Cout] or null: per-output-channel multiplier of the accumulator (undoes the fp16 weight pre-scale)
     int Cin, Cout, H, W, D;       // Cin = real channels per input phase; H, W = grid of the (virtual) stride-1 conv
     int Hin, Win;                 // real input plane (= H, W unless the input is phase-decomposed)
     int isY, isX;                 // input row pitch / x step in elements (W, 1 | 2*Win, 2)
@@ -152,8 +153,8 @@ __device__ __forceinline__ float act_t(float x) {
 // FOLD = 3: the kx taps are columns of the accumulator (3x3 convs); FOLD = 1: one column block (the 1x1 / (k,1,1) form)
 template <int ACT, int FOLD>
 __device__ __forceinline__ void epi_store8(const float (&a0)[8], const float (&a1)[8], const float (&a2)[8], int dil, float* o,
-                                           int osC, const float* bias, int co0, int Cout, bool ok, const float* add = nullptr,
-                                           int asC = 0) {
+                                           int osC, const float* bias, int co0, int Cout, bool ok, const float* osc,
+                                           const float* add = nullptr, int asC = 0) {
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
         float acc = a0[c];
@@ -162,14 +163,16 @@ __device__ __forceinline__ void epi_store8(const float (&a0)[8], const float (&a
             acc += __shfl_down_sync(0xffffffffu, a2[c], 2 * dil);
         }
         const bool live = ok && co0 + c < Cout;
-        float pre = acc + (co0 + c < Cout ? __ldg(bias + c) : 0.f);
+        const bool cok = co0 + c < Cout;
+        float pre = fmaf(acc, (osc && cok) ? __ldg(osc + c) : 1.f, cok ? __ldg(bias + c) : 0.f);
         if (add) pre += live ? __ldg(add + (long long)c * asC) : 0.f;
         const float r = act_t<ACT>(pre);
         if (live) o[c * osC] = r;
     }
 }
 template <int ACT, int CP, int FOLD>
-__device__ __forceinline__ void epi_direct(uint32_t taddr, int dil, float* o, int osC, const float* bias, int Cout, bool ok) {
+__device__ __forceinline__ void epi_direct(uint32_t taddr, int dil, float* o, int osC, const float* bias, int Cout, bool ok,
+                                           const float* osc) {
 #pragma unroll
     for (int c0 = 0; c0 < CP; c0 += 8) {
         uint32_t r0[8], r1[8], r2[8];
@@ -186,12 +189,12 @@ __device__ __forceinline__ void epi_direct(uint32_t taddr, int dil, float* o, in
             a1[c] = FOLD == 3 ? __uint_as_float(r1[c]) : 0.f;
             a2[c] = FOLD == 3 ? __uint_as_float(r2[c]) : 0.f;
         }
-        epi_store8<ACT, FOLD>(a0, a1, a2, dil, o + (long long)c0 * osC, osC, bias + c0, c0, Cout, ok);
+        epi_store8<ACT, FOLD>(a0, a1, a2, dil, o + (long long)c0 * osC, osC, bias + c0, c0, Cout, ok, osc ? osc + c0 : nullptr);
     }
 }
 template <int ACT, int CP, int FOLD>
 __device__ __forceinline__ void epi_acc(const float* acc, int dil, float* o, int osC, const float* bias, int Cout, bool ok,
-                                        const float* add = nullptr, int asC = 0) {
+                                        const float* osc, const float* add = nullptr, int asC = 0) {
 #pragma unroll
     for (int c0 = 0; c0 < CP; c0 += 8) {
         float a0[8], a1[8], a2[8];
@@ -201,7 +204,7 @@ __device__ __forceinline__ void epi_acc(const float* acc, int dil, float* o, int
             a1[c] = FOLD == 3 ? acc[(FOLD == 3 ? CP : 0) + c0 + c] : 0.f;
             a2[c] = FOLD == 3 ? acc[(FOLD == 3 ? 2 * CP : 0) + c0 + c] : 0.f;
         }
-        epi_store8<ACT, FOLD>(a0, a1, a2, dil, o + (long long)c0 * osC, osC, bias + c0, c0, Cout, ok,
+        epi_store8<ACT, FOLD>(a0, a1, a2, dil, o + (long long)c0 * osC, osC, bias + c0, c0, Cout, ok, osc ? osc + c0 : nullptr,
                               add ? add + (long long)c0 * asC : nullptr, asC);
     }
 }
@@ -643,16 +646,16 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
                     mbar_wait(&acc_full[j], 0u);
                     tc_fence_after();
                     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(j * C::TS);
-                    if (p.act == TSTEREO_ACT_SILU) epi_direct<TSTEREO_ACT_SILU, CP, FOLD>(taddr, p.dil, o, p.osC, p.bias, p.Cout, ok);
-                    else if (p.act == TSTEREO_ACT_RELU) epi_direct<TSTEREO_ACT_RELU, CP, FOLD>(taddr, p.dil, o, p.osC, p.bias, p.Cout, ok);
-                    else epi_direct<TSTEREO_ACT_NONE, CP, FOLD>(taddr, p.dil, o, p.osC, p.bias, p.Cout, ok);
+                    if (p.act == TSTEREO_ACT_SILU) epi_direct<TSTEREO_ACT_SILU, CP, FOLD>(taddr, p.dil, o, p.osC, p.bias, p.Cout, ok, p.oscale);
+                    else if (p.act == TSTEREO_ACT_RELU) epi_direct<TSTEREO_ACT_RELU, CP, FOLD>(taddr, p.dil, o, p.osC, p.bias, p.Cout, ok, p.oscale);
+                    else epi_direct<TSTEREO_ACT_NONE, CP, FOLD>(taddr, p.dil, o, p.osC, p.bias, p.Cout, ok, p.oscale);
                 } else {
                     const float* ad = nullptr;
                     if constexpr (FUSE == 1)
                         if (p.add) ad = p.add + (long long)b * p.asB + (long long)min(y, p.H - 1) * p.W + min(x, p.W - 1);
-                    if (p.act == TSTEREO_ACT_SILU) epi_acc<TSTEREO_ACT_SILU, CP, FOLD>(acc[jj], p.dil, o, p.osC, p.bias, p.Cout, ok, ad, p.asC);
-                    else if (p.act == TSTEREO_ACT_RELU) epi_acc<TSTEREO_ACT_RELU, CP, FOLD>(acc[jj], p.dil, o, p.osC, p.bias, p.Cout, ok, ad, p.asC);
-                    else epi_acc<TSTEREO_ACT_NONE, CP, FOLD>(acc[jj], p.dil, o, p.osC, p.bias, p.Cout, ok, ad, p.asC);
+                    if (p.act == TSTEREO_ACT_SILU) epi_acc<TSTEREO_ACT_SILU, CP, FOLD>(acc[jj], p.dil, o, p.osC, p.bias, p.Cout, ok, p.oscale, ad, p.asC);
+                    else if (p.act == TSTEREO_ACT_RELU) epi_acc<TSTEREO_ACT_RELU, CP, FOLD>(acc[jj], p.dil, o, p.osC, p.bias, p.Cout, ok, p.oscale, ad, p.asC);
+                    else epi_acc<TSTEREO_ACT_NONE, CP, FOLD>(acc[jj], p.dil, o, p.osC, p.bias, p.Cout, ok, p.oscale, ad, p.asC);
                 }
             }
         }
@@ -845,6 +848,9 @@ static int launch(Params& p, int CP, int planes, cudaStream_t st, const char* wh
         const int cols = mt * (direct ? N2 : 2 * N);
         if (cols > 512 || (CP == 32 && mt == 4 && fold == 3)) continue;   // no (32, 4) instance of the kx-folded form
         if (forced && mt != forced) continue;
+        // fused cost producer: the (16, 4) instance needs 168 registers (one CTA per SM) and loses to two CTAs of (16, 2)
+        // on the gather latency (fine level, B200: 295 vs 200 us)
+        if (FUSE != 0 && !forced && CP == 16 && mt == 4) continue;
         const int jt = (mt + 1) / 2;
         int minb = (direct || jt * N <= 48) ? 2 : 1;
         if (cols > 256) minb = 1;                       // two CTAs need their TMEM columns side by side
@@ -959,12 +965,14 @@ template <int FUSE = 0>
 inline int run_groups(tc2::Params p, int Cout, int planes, cudaStream_t st, const char* what) {
     const float* wp = p.wpack;
     const float* bias = p.bias;
+    const float* oscale = p.oscale;
     float* out = p.out;
     for (int c0 = 0; c0 < Cout; c0 += 32) {
         const int cg = Cout - c0 < 32 ? Cout - c0 : 32;
         p.Cout = cg;
         p.wpack = wp;
         p.bias = bias ? bias + c0 : nullptr;
+        p.oscale = oscale ? oscale + c0 : nullptr;
         p.out = out + (long long)c0 * p.osC;
         if (p.add) p.add += (c0 ? 32ll * p.asC : 0ll);
         const int rc = tc2::launch<FUSE>(p, tc2_cp(cg), planes, st, what);

@@ -19,7 +19,7 @@ using namespace tstereo::tc2;
 namespace {
 
 int cost_conv(int fuse, const float* left, const float* right, const float* samples, const float* gvol, const float* addL,
-              float* out, long long osB, long long osC, long long osD, const float* wpack, const float* bias,
+              float* out, long long osB, long long osC, long long osD, const float* wpack, const float* bias, const float* oscale,
               int B, int C, int Cout, int D, int H, int W, int act, int half, cudaStream_t st, const char* what) {
     TS_REQUIRE(right && gvol && out && wpack, "%s: null pointer", what);
     TS_REQUIRE(fuse == 1 ? samples != nullptr : left != nullptr, "%s: missing %s", what, fuse == 1 ? "samples" : "left features");
@@ -35,7 +35,7 @@ int cost_conv(int fuse, const float* left, const float* right, const float* samp
     p.in2 = gvol; p.i2sB = (long long)G3 * D * H * W; p.i2sC = D * H * W; p.i2sD = (long long)H * W; p.C2 = G3;
     p.add = addL; p.asB = (long long)Cout * H * W; p.asC = H * W;
     p.out = out; p.osB = osB; p.osC = (int)osC; p.osD = osD;
-    p.wpack = wpack; p.bias = bias;
+    p.wpack = wpack; p.bias = bias; p.oscale = oscale;
     p.H = H; p.W = W; p.D = D; p.Hin = H; p.Win = W;
     p.isY = W; p.isX = 1; p.osY = W; p.osX = 1;
     p.dil = 1; p.act = act; p.nky = 3; p.half = half != 0;
@@ -60,17 +60,17 @@ long long tstereo_cost_conv_wpack_floats(int C, int Cout, int half) {
 
 int tstereo_cost_conv_warp(const float* right, const float* samples, const float* gvol, const float* addL,
                            float* out, long long osB, long long osC, long long osD,
-                           const float* wpack, const float* bias,
+                           const float* wpack, const float* bias, const float* oscale,
                            int B, int C, int Cout, int S, int H, int W, int act, int half, void* stream) {
-    return cost_conv(1, nullptr, right, samples, gvol, addL, out, osB, osC, osD, wpack, bias, B, C, Cout, S, H, W, act, half,
+    return cost_conv(1, nullptr, right, samples, gvol, addL, out, osB, osC, osD, wpack, bias, oscale, B, C, Cout, S, H, W, act, half,
                      (cudaStream_t)stream, "cost_conv_warp");
 }
 
 int tstereo_cost_conv_shift(const float* left, const float* right, const float* gvol,
                             float* out, long long osB, long long osC, long long osD,
-                            const float* wpack, const float* bias,
+                            const float* wpack, const float* bias, const float* oscale,
                             int B, int C, int Cout, int D, int H, int W, int act, int half, void* stream) {
-    return cost_conv(2, left, right, nullptr, gvol, nullptr, out, osB, osC, osD, wpack, bias, B, C, Cout, D, H, W, act, half,
+    return cost_conv(2, left, right, nullptr, gvol, nullptr, out, osB, osC, osD, wpack, bias, oscale, B, C, Cout, D, H, W, act, half,
                      (cudaStream_t)stream, "cost_conv_shift");
 }
 

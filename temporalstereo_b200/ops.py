@@ -125,11 +125,11 @@ def group_cost(left: torch.Tensor, right: torch.Tensor, disp_sample) -> torch.Te
 
 def cost_conv_warp(right: torch.Tensor, samples: torch.Tensor, gvol: torch.Tensor, addL: Optional[torch.Tensor],
                    wpack: torch.Tensor, bias: Optional[torch.Tensor], cout: int, act=None,
-                   out: Optional[torch.Tensor] = None, half: bool = False) -> torch.Tensor:
+                   out: Optional[torch.Tensor] = None, half: bool = False, oscale: Optional[torch.Tensor] = None) -> torch.Tensor:
     """act(conv(1,3,3)(block_cost(left, right, samples)) + bias) without the volume (block_cost.py:47-81 ->
     module.py:111-147): `wpack` is the tensor-core image of W[:, C:] over [warp(R) | group terms] and `addL`
     [B, cout, H, W] = conv3x3(left, W[:, :C]) is the candidate-invariant left half."""
-    _chk(right, samples, gvol, addL, wpack, bias)
+    _chk(right, samples, gvol, addL, wpack, bias, oscale)
     B, Cc, H, W = right.shape
     S = samples.shape[1]
     assert samples.shape == (B, S, H, W) and gvol.shape == (B, 3 * (Cc // 8), S, H, W)
@@ -138,16 +138,16 @@ def cost_conv_warp(right: torch.Tensor, samples: torch.Tensor, gvol: torch.Tenso
     osB, osC, osD = _view5(out)
     assert wpack.numel() == _lib.load().tstereo_cost_conv_wpack_floats(Cc, cout, int(half))
     _lib.call("tstereo_cost_conv_warp", _p(right), _p(samples), _p(gvol), _p(addL), _p(out), osB, osC, osD, _p(wpack),
-              _p(bias), B, Cc, cout, S, H, W, ACT[act], int(half), _stream())
+              _p(bias), _p(oscale), B, Cc, cout, S, H, W, ACT[act], int(half), _stream())
     return out
 
 
 def cost_conv_shift(left: torch.Tensor, right: torch.Tensor, gvol: torch.Tensor, wpack: torch.Tensor,
                     bias: Optional[torch.Tensor], cout: int, act=None, out: Optional[torch.Tensor] = None,
-                    half: bool = False) -> torch.Tensor:
+                    half: bool = False, oscale: Optional[torch.Tensor] = None) -> torch.Tensor:
     """act(conv(1,3,3)(block_cost(left, right, D)) + bias) without the volume (block_cost.py:34-45, 64-81 ->
     module.py:111-147); `wpack` is the tensor-core image of the whole W over [-(L - R_d)^2 | group terms]."""
-    _chk(left, right, gvol, wpack, bias)
+    _chk(left, right, gvol, wpack, bias, oscale)
     B, Cc, H, W = left.shape
     D = gvol.shape[2]
     assert right.shape == left.shape and gvol.shape == (B, 3 * (Cc // 8), D, H, W)
@@ -155,7 +155,7 @@ def cost_conv_shift(left: torch.Tensor, right: torch.Tensor, gvol: torch.Tensor,
     osB, osC, osD = _view5(out)
     assert wpack.numel() == _lib.load().tstereo_cost_conv_wpack_floats(Cc, cout, int(half))
     _lib.call("tstereo_cost_conv_shift", _p(left), _p(right), _p(gvol), _p(out), osB, osC, osD, _p(wpack), _p(bias),
-              B, Cc, cout, D, H, W, ACT[act], int(half), _stream())
+              _p(oscale), B, Cc, cout, D, H, W, ACT[act], int(half), _stream())
     return out
 
 
@@ -186,6 +186,17 @@ def tf32_split(w: torch.Tensor):
         return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
     hi = rna(w)
     return hi, rna(w - hi)
+
+
+def fp16_prescale(w: torch.Tensor):
+    """Per-output-channel power-of-two scaling of BN-folded weights [Cout, Cin, taps] for the fp16 hi+lo operand split:
+    returns (w * s, 1 / s) with max|w[c] * s[c]| in (511, 1023].  The lo half of a small weight would otherwise fall into
+    fp16's subnormal range (|w| = 1e-3 keeps 14 of 22 bits); scaled, hi + lo carries 22 bits for every weight within
+    2^-13 of its channel's largest.  The kernel multiplies the fp32 accumulator by 1 / s (exact) before the bias
+    (`oscale` of the tensor-core operators)."""
+    m = w.abs().flatten(1).amax(1).clamp_min(1e-30)
+    s = torch.exp2(torch.floor(torch.log2(1023.0 / m)))
+    return w * s.view(-1, *([1] * (w.dim() - 1))), (1.0 / s).contiguous()
 
 
 def _pack_tc2_group(w: torch.Tensor, nky: int = 3, half: bool = False, fold: int = 3) -> torch.Tensor:
@@ -277,8 +288,10 @@ def pack_deconv_hw_tc2(w: torch.Tensor, k: int, half: bool = False) -> torch.Ten
 
 
 def conv_hw3_tc2(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Tensor], cout: int, dilation: int = 1,
-                 act=None, out: Optional[torch.Tensor] = None, half: bool = False) -> torch.Tensor:
-    """Stride-1 (1,3,3) / 3x3 conv on the tensor cores (kx-folded tcgen05 kernel, 3xTF32)."""
+                 act=None, out: Optional[torch.Tensor] = None, half: bool = False,
+                 oscale: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Stride-1 (1,3,3) / 3x3 conv on the tensor cores (kx-folded tcgen05 kernel, hi+lo split operands).  `oscale` [Cout]:
+    per-output-channel multiplier applied to the accumulator before the bias (1 / the weight pre-scale of `fp16_prescale`)."""
     five = x.dim() == 5
     B, Cin = x.shape[:2]
     D = x.shape[2] if five else 1
@@ -286,15 +299,15 @@ def conv_hw3_tc2(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Tens
     out = _out(out, (B, cout, D, H, W) if five else (B, cout, H, W), x)
     isB, isC, isD = _view5(x)
     osB, osC, osD = _view5(out)
-    _chk(wpack, bias)
+    _chk(wpack, bias, oscale)
     assert wpack.numel() == _lib.load().tstereo_conv_hw3_tc2_wpack_floats(Cin, cout, int(half))
-    _lib.call("tstereo_conv_hw3_tc2", _p(x), isB, isC, isD, _p(out), osB, osC, osD, _p(wpack), _p(bias),
+    _lib.call("tstereo_conv_hw3_tc2", _p(x), isB, isC, isD, _p(out), osB, osC, osD, _p(wpack), _p(bias), _p(oscale),
               B, Cin, cout, D, H, W, dilation, ACT[act], int(half), _stream())
     return out
 
 
 def conv_hw3s2_tc2(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Tensor], cout: int, act=None,
-                   out: Optional[torch.Tensor] = None, half: bool = False) -> torch.Tensor:
+                   out: Optional[torch.Tensor] = None, half: bool = False, oscale: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Stride-2 (1,3,3) / 3x3 conv, padding 1, on the tensor cores (phase-decomposed input, 3xTF32)."""
     five = x.dim() == 5
     B, Cin = x.shape[:2]
@@ -304,15 +317,15 @@ def conv_hw3s2_tc2(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Te
     out = _out(out, (B, cout, D, H, W) if five else (B, cout, H, W), x)
     isB, isC, isD = _view5(x)
     osB, osC, osD = _view5(out)
-    _chk(wpack, bias)
+    _chk(wpack, bias, oscale)
     assert wpack.numel() == _lib.load().tstereo_conv_hw3s2_tc2_wpack_floats(Cin, cout, int(half))
-    _lib.call("tstereo_conv_hw3s2_tc2", _p(x), isB, isC, isD, _p(out), osB, osC, osD, _p(wpack), _p(bias),
+    _lib.call("tstereo_conv_hw3s2_tc2", _p(x), isB, isC, isD, _p(out), osB, osC, osD, _p(wpack), _p(bias), _p(oscale),
               B, Cin, cout, D, Hin, Win, ACT[act], int(half), _stream())
     return out
 
 
 def deconv_hw_tc2(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Tensor], cout: int, act=None,
-                  out: Optional[torch.Tensor] = None, half: bool = False) -> torch.Tensor:
+                  out: Optional[torch.Tensor] = None, half: bool = False, oscale: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Transposed (1,k,k)/kxk conv, stride 2 (Hout = 2*Hin), on the tensor cores: one output parity phase per launch."""
     five = x.dim() == 5
     B, Cin = x.shape[:2]
@@ -321,25 +334,25 @@ def deconv_hw_tc2(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Ten
     out = _out(out, (B, cout, D, 2 * Hin, 2 * Win) if five else (B, cout, 2 * Hin, 2 * Win), x)
     isB, isC, isD = _view5(x)
     osB, osC, osD = _view5(out)
-    _chk(wpack, bias)
+    _chk(wpack, bias, oscale)
     assert wpack.numel() == _lib.load().tstereo_deconv_hw_tc2_wpack_floats(Cin, cout, int(half))
-    _lib.call("tstereo_deconv_hw_tc2", _p(x), isB, isC, isD, _p(out), osB, osC, osD, _p(wpack), _p(bias),
+    _lib.call("tstereo_deconv_hw_tc2", _p(x), isB, isC, isD, _p(out), osB, osC, osD, _p(wpack), _p(bias), _p(oscale),
               B, Cin, cout, D, Hin, Win, ACT[act], int(half), _stream())
     return out
 
 
 def conv_d_tc2(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Tensor], cout: int, k: int = 3, stride: int = 1,
                dilation: int = 1, transposed: bool = False, act=None, out: Optional[torch.Tensor] = None,
-               half: bool = False) -> torch.Tensor:
-    """(k,1,1) conv along D (or its stride-2 transposed form) through the second-generation tensor-core kernel."""
+               half: bool = False, oscale: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(k,1,1) conv along D (or its stride-2 transposed form) through the tensor-core kernel."""
     B, Cin, Din, H, W = x.shape
     Dout = 2 * Din if transposed else (Din - 1) // stride + 1
     out = _out(out, (B, cout, Dout, H, W), x)
     isB, isC, isD = _view5(x)
     osB, osC, osD = _view5(out)
-    _chk(wpack, bias)
+    _chk(wpack, bias, oscale)
     assert wpack.numel() == _lib.load().tstereo_conv_d_tc2_wpack_floats(Cin, cout, k, int(half))
-    _lib.call("tstereo_conv_d_tc2", _p(x), isB, isC, isD, _p(out), osB, osC, osD, _p(wpack), _p(bias),
+    _lib.call("tstereo_conv_d_tc2", _p(x), isB, isC, isD, _p(out), osB, osC, osD, _p(wpack), _p(bias), _p(oscale),
               B, Cin, cout, Din, Dout, H, W, k, stride, dilation, int(transposed), ACT[act], int(half), _stream())
     return out
 

@@ -261,19 +261,21 @@ def test_idempotent_and_batch_independent(engine, plan):
 
 
 def test_materialised_cost_path_agrees_with_the_fused_one(engine):
-    """fuse_cost=False runs ops.block_cost (the drop-in operator, raw volume in HBM) + the plain first conv; the default
-    path never writes the volume.  Same math, other summation order: both within tolerance of the oracle and of each other."""
+    """fuse_cost=False runs ops.block_cost (the drop-in operator, raw volume in HBM) + the plain first conv at every level;
+    True never writes a raw volume; the default fuses the two warp levels.  Same math, other summation order: all within
+    tolerance of the oracle and of each other."""
     sd = synth.synthetic_state_dict(seed=0)
     lf, rf, li, ri = synth.synthetic_frame(128, 192, B=2, seed=6)
     with torch.no_grad():
         want = O.aggregation_forward(sd, lf, rf, li, ri, {})
-    assert engine.fuse_cost
-    fused = engine(_cuda(lf), _cuda(rf), li.cuda(), ri.cuda(), {})
-    engine.fuse_cost = False
+    default = engine.fuse_cost
+    assert set(default) == {"fine", "precise"}
+    outs = {}
     try:
-        plain = engine(_cuda(lf), _cuda(rf), li.cuda(), ri.cuda(), {})
+        for mode in (default, True, False):
+            engine.fuse_cost = mode
+            outs[str(mode)] = engine(_cuda(lf), _cuda(rf), li.cuda(), ri.cuda(), {})
+            _check(outs[str(mode)], want[:4], f"fuse_cost={mode}")
     finally:
-        engine.fuse_cost = True
-    _check(fused, want[:4], "fused cost path")
-    _check(plain, want[:4], "materialised cost path")
-    assert (fused[0][0] - plain[0][0]).abs().mean() < 1e-4
+        engine.fuse_cost = default
+    assert (outs["True"][0][0] - outs["False"][0][0]).abs().mean() < 1e-4

@@ -600,6 +600,29 @@ def test_conv_hw3_tc2_tma(ops, monkeypatch, B, Cin, Cout, D, H, W, dil, act):
     close(gotd, wantd, 1e-5, rtol=1e-5, what="conv_d_tc2 (TMA)")
 
 
+def test_fp16_split_small_weights_need_the_prescale(ops):
+    """BN-folded weights of magnitude 1e-3: the lo half of the fp16 split is subnormal (14 of 22 bits survive) unless the
+    weights are pre-scaled per output channel by a power of two and the accumulator is scaled back (oscale)."""
+    B, Cin, Cout, D, H, W = 1, 64, 16, 2, 20, 37
+    x = rnd(B, Cin, D, H, W, seed=71)
+    w = rnd(Cout, Cin, 1, 3, 3, seed=72, scale=1e-3)
+    w[3] *= 50.0                                     # channels of very different magnitude get their own scale
+    b = rnd(Cout, seed=73, scale=1e-3)
+    want = F.conv3d(x.double(), w.double(), b.double(), 1, (0, 1, 1)).float()
+    w9 = w.reshape(Cout, Cin, 9)
+    plain = ops.conv_hw3_tc2(x.cuda(), ops.pack_conv_hw3_tc2(w9, True).cuda(), b.cuda(), Cout, 1, None, half=True).cpu()
+    ws, inv = ops.fp16_prescale(w9)
+    assert torch.equal(torch.log2(inv), torch.log2(inv).round()), "the scale must be a power of two (exact to undo)"
+    m = ws.abs().flatten(1).amax(1)
+    assert (m > 511).all() and (m <= 1023).all()
+    scaled = ops.conv_hw3_tc2(x.cuda(), ops.pack_conv_hw3_tc2(ws, True).cuda(), b.cuda(), Cout, 1, None, half=True, oscale=inv.cuda()).cpu()
+    ref = want.abs().flatten(2).amax(2).view(1, Cout, 1, 1, 1)     # per-channel output magnitude
+    e_plain, e_scaled = ((plain - want).abs() / ref).max().item(), ((scaled - want).abs() / ref).max().item()
+    print(f"fp16 split, |w| ~ 1e-3: relative error plain {e_plain:.2e}, pre-scaled {e_scaled:.2e}")
+    assert e_scaled < 3e-6, e_scaled                 # the fp32 conv's own rounding level
+    assert e_plain > 3 * e_scaled, (e_plain, e_scaled)
+
+
 def test_conv_hw3_tc2_fp16_saturates_instead_of_nan(ops):
     """fp16 split: an activation beyond 65504 clamps (cvt.satfinite) — finite output; the tf32 split has no limit."""
     x = rnd(1, 8, 1, 8, 32, seed=96)

@@ -91,3 +91,23 @@ def test_tf32_split_is_exact_and_representable():
     for t in (hi, lo):
         assert ((t.view(torch.int32) & 0x1FFF) == 0).all(), "parts must be exactly representable in tf32"
     assert ((hi + lo) - w).abs().max() <= w.abs().max() * 2.0 ** -21
+
+
+def test_fp16_prescale_is_an_exact_power_of_two_per_channel():
+    g = torch.Generator().manual_seed(3)
+    w = torch.randn(12, 40, 9, generator=g) * torch.logspace(-5, 1, 12).view(-1, 1, 1)
+    ws, inv = ops.fp16_prescale(w)
+    assert torch.equal(torch.log2(inv), torch.log2(inv).round())
+    assert torch.equal(ws * inv.view(-1, 1, 1), w)                   # exact round trip
+    m = ws.abs().flatten(1).amax(1)
+    assert (m > 511).all() and (m <= 1023).all()
+    # hi + lo of the scaled weights reconstructs >= 21 bits of every weight within 2^-10 of its channel's largest
+    hi = ws.half()
+    lo = (ws - hi.float()).half()
+    rec = (hi.float() + lo.float())
+    big = ws.abs() > m.view(-1, 1, 1) * 2.0 ** -10
+    assert ((rec - ws).abs()[big] <= ws.abs()[big] * 2.0 ** -21).all()
+    # unscaled, the small channels lose their lo half to fp16's subnormal range
+    hi0 = w.half()
+    rec0 = hi0.float() + (w - hi0.float()).half().float()
+    assert ((rec0 - w).abs() / w.abs().clamp_min(1e-30))[0].max() > 2.0 ** -15
