@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--height", type=int, default=544)
     ap.add_argument("--width", type=int, default=960)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="launch kernel by kernel instead of replaying a CUDA graph per step")
+    ap.add_argument("--no-extras", action="store_true", help="skip the B=1 latency and C3 temporal side measurements")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     return ap.parse_args()
 
@@ -189,14 +191,17 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback for the hot path)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+
+    from temporalstereo_b200 import _lib, ops, shard, synth, temporal
+    from temporalstereo_b200.aggregation import TEMPORALSTEREO
+    from temporalstereo_b200.graph import CapturedStep
+    # pin the process next to its GPU BEFORE any pinned staging buffer is allocated (first touch decides the NUMA node)
+    numa_cpus = shard.bind_to_gpu_numa(local)
     dist = None
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
         dist.init_process_group("nccl", device_id=dev)
-
-    from temporalstereo_b200 import _lib, ops, shard, synth
-    from temporalstereo_b200.aggregation import TEMPORALSTEREO
     lib = _lib.load()
 
     H, W, B = a.height, a.width, a.batch
@@ -204,15 +209,25 @@ def main():
     eng.load_state_dict(synth.synthetic_state_dict(seed=0), strict=True)
     eng = eng.to(dev).eval()
 
-    # ---- inputs: host (pinned) master copy + NSETS device-resident sets rotated so that consecutive
-    #      steps never re-read inputs from L2 (sets differ by a horizontal roll)
+    # ---- inputs.  Host side (pinned): the fp32 feature pyramids as the backbone hands them over, and the two images in
+    #      their wire format: uint8 HWC, normalised on the device (reference data/datasets/base.py:120-127).
     lf, rf, li, ri = synth.synthetic_frame(H, W, B=B, seed=1 + rank)
-    host = [t.pin_memory() for t in (lf + rf + [li, ri])]
-    in_bytes = sum(t.numel() * 4 for t in host)
+    mean = torch.tensor(ops.IMAGENET_MEAN).view(1, 3, 1, 1)
+    std = torch.tensor(ops.IMAGENET_STD).view(1, 3, 1, 1)
+    to_u8 = lambda t: ((t * std + mean).clamp(0, 1) * 255).round().to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+    host_feats = [t.pin_memory() for t in lf + rf]
+    host_imgs = [to_u8(li).pin_memory(), to_u8(ri).pin_memory()]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host_feats + host_imgs)
+
+    # ---- device-resident sets for `value` (inputs already in HBM when the timed region starts): NSETS sets rotated so
+    #      that consecutive steps never re-read inputs from L2 (sets differ by a horizontal roll)
+    in_bytes = sum(t.numel() * 4 for t in lf + rf + [li, ri])
     nsets = max(2, -(-2 * L2_BYTES // in_bytes))
     sets = []
     for s in range(nsets):
-        sets.append([torch.roll(t.to(dev), shifts=s, dims=-1).contiguous() for t in host])
+        feats = [torch.roll(t.to(dev), shifts=s, dims=-1).contiguous() for t in lf + rf]
+        imgs = [ops.normalize_u8(torch.roll(t.to(dev), shifts=s, dims=2).contiguous()) for t in host_imgs]
+        sets.append(feats + imgs)
 
     def forward(inp):
         return eng(inp[0:3], inp[3:6], inp[6], inp[7], {})
@@ -220,9 +235,18 @@ def main():
     def barrier():
         shard.barrier(dist)
 
+    use_graph = not a.eager
+    if use_graph:
+        steps_dev = [CapturedStep(lambda inp=inp: forward(inp), device=dev) for inp in sets]
+        run_dev = lambda i: steps_dev[i % nsets].replay()
+        launches_per_step = steps_dev[0].launches
+    else:
+        run_dev = lambda i: forward(sets[i % nsets])
+        launches_per_step = None
+
     # ---- device-resident throughput
     for i in range(max(a.warmup, 3)):
-        out = forward(sets[i % nsets])
+        run_dev(i)
     barrier()
     n0 = lib.tstereo_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -230,41 +254,65 @@ def main():
         barrier()
         e0.record()
         for i in range(a.steps):
-            out = forward(sets[i % nsets])
+            run_dev(i)
         e1.record()
         barrier()
-    launches = lib.tstereo_launch_count() - n0
+    launches = launches_per_step * a.steps if use_graph else lib.tstereo_launch_count() - n0
     # whole-job throughput: frames of all ranks / slowest rank's device time
     fps, ms, _ = shard.aggregate_throughput(B * a.steps, e0.elapsed_time(e1), dist, dev)
 
-    # ---- end to end through the public module call with host buffers: every step uploads its own inputs from
-    #      pinned host memory and downloads its full-resolution disparity.  Two staging sets: the upload of
-    #      step i+1 runs on a copy stream while step i computes (the steady state of a streaming caller).
-    stages = [[torch.empty_like(t, device=dev) for t in host] for _ in range(2)]
+    # ---- end to end through the public call with HOST buffers.  Every step uploads its own inputs from pinned host
+    #      memory (features fp32, images uint8), normalises the images on the device, runs the frame and downloads its
+    #      full-resolution disparity.  Two staging sets: the upload of step i+1 (copy stream) and the download of step i-1
+    #      (its own stream) overlap the compute of step i — the steady state of a streaming caller.
+    stage_f = [[torch.empty_like(t, device=dev) for t in host_feats] for _ in range(2)]
+    stage_i = [[torch.empty_like(t, device=dev) for t in host_imgs] for _ in range(2)]
+    norm_i = [[torch.empty((B, 3, H, W), device=dev) for _ in range(2)] for _ in range(2)]
     full_host = [torch.empty((B, 1, H, W), dtype=torch.float32).pin_memory() for _ in range(2)]
-    copy_stream = torch.cuda.Stream(device=dev)
+    copy_stream, d2h_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
     main_stream = torch.cuda.current_stream(dev)
     uploaded = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
+    computed = [torch.cuda.Event() for _ in range(2)]
+    downloaded = [torch.cuda.Event() for _ in range(2)]
+
+    def frame_from_wire(k):
+        ops.normalize_u8(stage_i[k][0], out=norm_i[k][0])
+        ops.normalize_u8(stage_i[k][1], out=norm_i[k][1])
+        return eng(stage_f[k][0:3], stage_f[k][3:6], norm_i[k][0], norm_i[k][1], {})
+
+    if use_graph:
+        steps_e2e = [CapturedStep(lambda k=k: frame_from_wire(k), device=dev) for k in range(2)]
+        run_e2e = lambda k: steps_e2e[k].replay()
+    else:
+        run_e2e = frame_from_wire
 
     def upload(i):
+        k = i % 2
         with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[i % 2])          # the set is free once the step that read it is done
-            for d, h in zip(stages[i % 2], host):
+            copy_stream.wait_event(consumed[k])              # the set is free once the step that read it is done
+            for d, h in zip(stage_f[k] + stage_i[k], host_feats + host_imgs):
                 d.copy_(h, non_blocking=True)
-            uploaded[i % 2].record(copy_stream)
+            uploaded[k].record(copy_stream)
 
     def e2e_run(n):
-        for ev in consumed:
+        for ev in consumed + downloaded:
             ev.record(main_stream)
         upload(0)
         for i in range(n):
+            k = i % 2
             if i + 1 < n:
                 upload(i + 1)
-            main_stream.wait_event(uploaded[i % 2])
-            o = forward(stages[i % 2])
-            consumed[i % 2].record(main_stream)
-            full_host[i % 2].copy_(o[0][0], non_blocking=True)
+            main_stream.wait_event(uploaded[k])
+            main_stream.wait_event(downloaded[k])            # the graph's output buffer of set k was read by its last D2H
+            o = run_e2e(k)
+            consumed[k].record(main_stream)
+            computed[k].record(main_stream)
+            with torch.cuda.stream(d2h_stream):
+                d2h_stream.wait_event(computed[k])
+                full_host[k].copy_(o[0][0], non_blocking=True)
+                downloaded[k].record(d2h_stream)
+        main_stream.wait_stream(d2h_stream)
 
     e2e_run(3)
     barrier()
@@ -274,22 +322,23 @@ def main():
     barrier()
     fps_e2e, ms_e2e, _ = shard.aggregate_throughput(B * a.steps, e0.elapsed_time(e1), dist, dev)
 
-    # ---- roofline of the cost-volume operator (block_cost: the path north_star sets the HBM target on).
-    #      Dominant launch = the precise-level volume (198 of the 329 MB/frame); the three-level total
-    #      is reported beside it.  Candidates are the engine's own pattern: a piecewise-smooth disparity
-    #      +- {4,1,0} (a trained network regresses smooth maps; random-init weights do not).
+    # ---- what the upload alone can do on this box: every rank copies the same bytes from the same pinned buffers at the
+    #      same time (nothing else running).  e2e cannot beat bytes / this rate; at N > 1 the ranks share the host's
+    #      memory and PCIe fabric, which is what the N-GPU e2e scaling is bound by.
+    def h2d_only(n):
+        for _ in range(n):
+            for d, h in zip(stage_f[0] + stage_i[0], host_feats + host_imgs):
+                d.copy_(h, non_blocking=True)
+    h2d_only(2)
+    barrier()
+    e0.record()
+    h2d_only(10)
+    e1.record()
+    barrier()
+    ms_h2d = shard.max_over_ranks(e0.elapsed_time(e1), dist, dev) / 10
+    h2d_ceiling = h2d_bytes / (ms_h2d * 1e-3) / 1e9
+
     peak, peak_src = peaks()
-
-    def smooth_samples(h, w, S):
-        yy, xx = torch.meshgrid(torch.arange(h, device=dev), torch.arange(w, device=dev), indexing="ij")
-        base = 0.06 * w * (1.2 + torch.sin(xx / w * 6.0) * torch.cos(yy / h * 4.0)) + 0.3 * torch.rand(h, w, device=dev)
-        offs = torch.tensor([-4.0, -1.0, 0.0, 1.0, 4.0], device=dev)[:S]
-        return (base[None, None] + offs.view(1, S, 1, 1)).expand(B, S, h, w).contiguous()
-
-    nrot = max(2, -(-2 * L2_BYTES // (8 * B * 128 * (H // 4) * (W // 4))))
-    lcat = [torch.randn(B, 128, H // 4, W // 4, device=dev) for _ in range(nrot)]
-    rcat = [torch.randn(B, 128, H // 4, W // 4, device=dev) for _ in range(nrot)]
-    smp4, smp8 = smooth_samples(H // 4, W // 4, 5), smooth_samples(H // 8, W // 8, 5)
 
     def timed(fn, reps):
         for i in range(3):
@@ -302,38 +351,90 @@ def main():
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps
 
-    def vol_bytes(C, h, w, S, planes, warp=True):
-        return 4 * B * (2 * C * h * w + (S * h * w if warp else 0) + planes * S * h * w)
-
     reps = max(10, min(a.steps, 50))
-    b_p = vol_bytes(128, H // 4, W // 4, 5, 304)
-    b_f = vol_bytes(128, H // 8, W // 8, 5, 304)
-    b_c = vol_bytes(256, H // 16, W // 16, 12, 352, warp=False)
-    ms_p = timed(lambda i: ops.block_cost(lcat[i % nrot], rcat[i % nrot], smp4), reps)
-    ms_f = timed(lambda i: ops.block_cost(sets[i % nsets][1], sets[i % nsets][4], smp8), reps)
-    ms_c = timed(lambda i: ops.block_cost(sets[i % nsets][2], sets[i % nsets][5], 12), reps)
-    achieved = b_p / (ms_p * 1e-3) / 1e9
-    cv_ms, alg_bytes = ms_p + ms_f + ms_c, b_p + b_f + b_c
+    result_extra = {}
+    if rank == 0:
+        # ---- roofline of the cost-volume path.  Candidates are the engine's own pattern: a piecewise-smooth disparity
+        #      +- {4,1,0} (a trained network regresses smooth maps; random-init weights do not).
+        def smooth_samples(h, w, S):
+            yy, xx = torch.meshgrid(torch.arange(h, device=dev), torch.arange(w, device=dev), indexing="ij")
+            base = 0.06 * w * (1.2 + torch.sin(xx / w * 6.0) * torch.cos(yy / h * 4.0)) + 0.3 * torch.rand(h, w, device=dev)
+            offs = torch.tensor([-4.0, -1.0, 0.0, 1.0, 4.0], device=dev)[:S]
+            return (base[None, None] + offs.view(1, S, 1, 1)).expand(B, S, h, w).contiguous()
 
-    # ---- the heaviest single launch of the step: the first (1,3,3) conv of the precise level (304 -> 8 channels over
-    #      the raw volume) on the tensor-core kernel.  It is HBM-bound (36 FLOP/B): algorithmic bytes =
-    #      volume read once + output written once.
-    pk_first = eng._pk["precise.init3d.0.conv.0"]
-    vols = [torch.randn(B, 304, 5, H // 4, W // 4, device=dev) for _ in range(2)]
-    out8 = torch.empty(B, 8, 5, H // 4, W // 4, device=dev)
-    ms_conv = timed(lambda i: ops.conv_hw3_tc2(vols[i % 2], pk_first.tc["hw3"], pk_first.b, 8, 1, "SiLU", out=out8, half=eng.half_split), reps)
-    b_conv = 4 * B * (304 + 8) * 5 * (H // 4) * (W // 4)
-    del vols
+        h4, w4 = H // 4, W // 4
+        nrot = max(2, -(-2 * L2_BYTES // (8 * B * 128 * h4 * w4)))
+        lcat = [torch.randn(B, 128, h4, w4, device=dev) for _ in range(nrot)]
+        rcat = [torch.randn(B, 128, h4, w4, device=dev) for _ in range(nrot)]
+        smp4, smp8 = smooth_samples(h4, w4, 5), smooth_samples(H // 8, W // 8, 5)
+        first = eng._pk["precise.init3d.0.conv.0"]
+        hs = eng.half_split
 
-    # DRAM traffic of the roofline kernel from the committed ncu capture (profiles/r01_traffic.json, per launch at the
-    # batch size it names); null when the bench runs at another batch size
-    traffic = None
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        if int(tj.get("batch", -1)) == B and (H, W) == (544, 960):
-            traffic = tj["block_cost_precise_dram_bytes"]
-    except (OSError, ValueError, KeyError):
-        pass
+        # (1) the fused path the engine runs at the precise level: group terms -> left-half conv -> cost conv.  The raw
+        #     volume never exists; algorithmic bytes = SURVEY.md 8d "fused path": features + candidates + conv output + weights.
+        def fused(i):
+            g = ops.group_cost(lcat[i % nrot], rcat[i % nrot], smp4)
+            al = ops.conv_hw3_tc2(lcat[i % nrot], first.tc["left"], None, 8, 1, None, half=hs, oscale=first.osc)
+            return ops.cost_conv_warp(rcat[i % nrot], smp4, g, al, first.tc["cost"], first.b, 8, "SiLU", half=hs, oscale=first.osc)
+        gsteps = [CapturedStep(lambda i=i: fused(i), device=dev) for i in range(nrot)]
+        ms_fused = timed(lambda i: gsteps[i % nrot].replay(), reps)
+        g0 = ops.group_cost(lcat[0], rcat[0], smp4)
+        al0 = ops.conv_hw3_tc2(lcat[0], first.tc["left"], None, 8, 1, None, half=hs, oscale=first.osc)
+        part = {}
+        for name, fn in (("group_cost", lambda i: ops.group_cost(lcat[i % nrot], rcat[i % nrot], smp4)),
+                         ("left_conv", lambda i: ops.conv_hw3_tc2(lcat[i % nrot], first.tc["left"], None, 8, 1, None, half=hs, oscale=first.osc)),
+                         ("cost_conv", lambda i: ops.cost_conv_warp(rcat[i % nrot], smp4, g0, al0, first.tc["cost"], first.b, 8, "SiLU",
+                                                                    half=hs, oscale=first.osc))):
+            gs = CapturedStep(lambda fn=fn: [fn(i) for i in range(nrot)], device=dev)
+            part[name] = timed(lambda i: gs.replay(), max(reps // nrot, 5)) / nrot
+            del gs
+        b_fused = 4 * B * (2 * 128 * h4 * w4 + 5 * h4 * w4 + 8 * 5 * h4 * w4) + 4 * 8 * 304 * 9
+        flops_fused = 2.0 * B * 8 * 9 * 5 * h4 * w4 * (176 + 128 / 5.0)        # R + group channels per candidate, L once
+        del gsteps, g0, al0
+
+        # (2) the materialising operator (ops.block_cost, the drop-in for the reference's block_cost): the kernel the
+        #     north-star HBM target is quoted on; on the engine's path at the coarse level, and at every level with
+        #     fuse_cost=False.
+        def vol_bytes(C, h, w, S, planes, warp=True):
+            return 4 * B * (2 * C * h * w + (S * h * w if warp else 0) + planes * S * h * w)
+        b_p = vol_bytes(128, h4, w4, 5, 304)
+        b_f = vol_bytes(128, H // 8, W // 8, 5, 304)
+        b_c = vol_bytes(256, H // 16, W // 16, 12, 352, warp=False)
+        ms_p = timed(lambda i: ops.block_cost(lcat[i % nrot], rcat[i % nrot], smp4), reps)
+        ms_f = timed(lambda i: ops.block_cost(sets[i % nsets][1], sets[i % nsets][4], smp8), reps)
+        ms_c = timed(lambda i: ops.block_cost(sets[i % nsets][2], sets[i % nsets][5], 12), reps)
+        del lcat, rcat
+
+        traffic = {}
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+            if int(tj.get("batch", -1)) == B and (H, W) == (544, 960):
+                traffic = tj
+        except (OSError, ValueError, KeyError):
+            pass
+        step_ms = ms / a.steps
+        ach_fused = b_fused / (ms_fused * 1e-3) / 1e9
+        result_extra["roofline"] = {
+            "bound": "hbm", "kernel": "fused cost volume -> first conv at the precise level (group_cost + left-half conv_tc2 + "
+            "cost_conv_warp conv_tc2<8,4,ACC,FUSE=1>): the raw 198 MB/frame volume is never written",
+            "achieved": ach_fused, "peak": peak, "unit": "GB/s", "frac": ach_fused / peak,
+            "traffic": traffic.get("fused_precise_dram_bytes"), "traffic_source": traffic.get("source"),
+            "peak_source": peak_src, "algorithmic_bytes": b_fused, "ms": ms_fused, "share_of_step": ms_fused / step_ms,
+            "kernels_ms": part,
+            "tensor_bound": {"flops_3term": 3 * flops_fused, "tflops_3term": 3 * flops_fused / (ms_fused * 1e-3) / 1e12,
+                             "note": "fp16 hi+lo split = 3 MMA terms per product; bound = max(bytes / HBM, flops / tensor peak)"}}
+        result_extra["roofline_block_cost"] = {
+            "bound": "hbm", "kernel": "block_cost_warp at the precise level (block_cost_main_kernel<1,1,0> + block_cost_resize_kernel): "
+            "the materialising drop-in operator", "achieved": b_p / (ms_p * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+            "frac": b_p / (ms_p * 1e-3) / 1e9 / peak, "traffic": traffic.get("block_cost_precise_dram_bytes"),
+            "algorithmic_bytes": b_p, "ms": ms_p,
+            "all_three_levels": {"algorithmic_bytes": b_p + b_f + b_c, "ms": ms_p + ms_f + ms_c,
+                                 "achieved": (b_p + b_f + b_c) / ((ms_p + ms_f + ms_c) * 1e-3) / 1e9,
+                                 "frac": (b_p + b_f + b_c) / ((ms_p + ms_f + ms_c) * 1e-3) / 1e9 / peak}}
+
+        # ---- streaming latency (B = 1, CUDA graph) and the temporal configuration C3 (KITTI 384x1248, pose warp on)
+        if not a.no_extras:
+            result_extra.update(extras(eng, dev, timed, CapturedStep, synth, temporal))
 
     result = {
         "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
@@ -342,27 +443,20 @@ def main():
         "config": {"workload": workload_name(a), "frames_per_step_per_gpu": B,
                    "l2": f"inputs rotate over {nsets} device-resident sets ({nsets * in_bytes / 1e6:.0f} MB > 126 MB L2); "
                          "every intermediate cost volume alone exceeds L2",
-                   "parallelism": f"batch-sharded replicas x{world}, no data-path collective"},
+                   "launch": "one CUDA-graph replay per step" if use_graph else "eager (one launch per kernel)",
+                   "wire_format": "e2e uploads fp32 feature pyramids + uint8 HWC images (normalised on the device)",
+                   "parallelism": f"batch-sharded replicas x{world}, no data-path collective",
+                   "numa": f"rank pinned to {len(numa_cpus)} cores local to its GPU" if numa_cpus else "no NUMA pinning (NVML affinity unavailable)"},
         "clocks": clk.summary(),
-        "e2e": {"value": fps_e2e, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": B * H * W * 4,
-                "ms_per_step": ms_e2e / a.steps},
+        "e2e": {"value": fps_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": B * H * W * 4,
+                "ms_per_step": ms_e2e / a.steps,
+                "h2d_gbs_achieved": h2d_bytes / (ms_e2e / a.steps * 1e-3) / 1e9,
+                "h2d_gbs_ceiling": h2d_ceiling, "h2d_ceiling_ms_per_step": ms_h2d,
+                "h2d_note": f"ceiling = the same {h2d_bytes / 1e6:.0f} MB copied pinned->device by all {world} rank(s) at once with nothing "
+                            "else running (max over ranks); e2e frames/s cannot exceed frames_per_step / h2d_ceiling_ms_per_step"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm",
-                     "kernel": "block_cost_warp at the precise level (block_cost_main_kernel<1,1> + block_cost_resize_kernel)",
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of both "
-                     "kernels, profiles/r01_traffic.json", "peak_source": peak_src, "algorithmic_bytes": b_p, "ms": ms_p,
-                     "all_three_levels": {"algorithmic_bytes": alg_bytes, "ms": cv_ms,
-                                          "achieved": alg_bytes / (cv_ms * 1e-3) / 1e9,
-                                          "frac": alg_bytes / (cv_ms * 1e-3) / 1e9 / peak},
-                     "share_of_step": cv_ms / (ms / a.steps)},
-        "roofline_conv": {"bound": "hbm", "kernel": "conv_tc2_kernel<8,4,ACC>: first (1,3,3) conv of the precise level, "
-                          "304 -> 8 channels over the raw cost volume (tcgen05, 3xTF32)",
-                          "achieved": b_conv / (ms_conv * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                          "frac": b_conv / (ms_conv * 1e-3) / 1e9 / peak, "algorithmic_bytes": b_conv, "ms": ms_conv,
-                          "tflops_fp32_equiv": 2.0 * B * 304 * 8 * 9 * 5 * (H // 4) * (W // 4) / (ms_conv * 1e-3) / 1e12,
-                          "share_of_step": ms_conv / (ms / a.steps)},
     }
+    result.update(result_extra)
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cfps, med, n, thr = cpu_reference_frames(a, a.cpu_seconds)
         result["cpu_baseline"] = {"value": cfps, "unit": UNIT, "cores": thr, "kind": "port",
@@ -372,6 +466,46 @@ def main():
         print(json.dumps(result))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def extras(eng, dev, timed, CapturedStep, synth, temporal):
+    """Rank-0 side measurements beside the headline: B=1 streaming latency at C2 and the temporal configuration C3
+    (KITTI 384x1248, D=192, pose warp on, steady state: cost memory + 3-plane local map), each as one CUDA-graph replay."""
+    out = {}
+    cu = lambda t: t.to(dev)
+    lf, rf, li, ri = synth.synthetic_frame(544, 960, B=1, seed=3)
+    inp = [cu(t) for t in lf + rf + [li, ri]]
+    step = CapturedStep(lambda: eng(inp[0:3], inp[3:6], inp[6], inp[7], {}), device=dev)
+    ms1 = timed(lambda i: step.replay(), 30)
+    ms1_eager = timed(lambda i: eng(inp[0:3], inp[3:6], inp[6], inp[7], {}), 10)
+    out["latency_b1"] = {"workload": "C2 544x960 D=192, B=1, single frame", "ms_per_frame_graph": ms1, "ms_per_frame_eager": ms1_eager,
+                         "kernels": step.launches}
+    del step
+    H, W = 384, 1248
+    lf, rf, li, ri = synth.synthetic_frame(H, W, B=1, seed=4)
+    inp = [cu(t) for t in lf + rf + [li, ri]]
+    st = synth.synthetic_temporal_state(H, W, B=1)
+    pose = [cu(st[k]) for k in ("K", "T_now", "inv_T_prev", "baseline")]
+    state = {}
+    for _ in range(5):                      # the local map grows to 3 planes over the first frames
+        if "prev_disp" in state:
+            state = temporal.update_map(state, *pose, H, W, True, 3)
+        state = eng(inp[0:3], inp[3:6], inp[6], inp[7], state)[5]
+    frozen = {k: ({a_: b_.clone() for a_, b_ in v.items()} if isinstance(v, dict) else (v.clone() if torch.is_tensor(v) else v))
+              for k, v in state.items()}
+    copy = lambda s: {k: (dict(v) if isinstance(v, dict) else v) for k, v in s.items()}
+
+    def frame():
+        s = temporal.update_map(copy(frozen), *pose, H, W, True, 3)
+        return eng(inp[0:3], inp[3:6], inp[6], inp[7], s)[0][0]
+    step = CapturedStep(frame, device=dev)
+    warp = CapturedStep(lambda: temporal.update_map(copy(frozen), *pose, H, W, True, 3)["local_map"], device=dev)
+    out["temporal"] = {"workload": "C3 KITTI 384x1248 D=192, B=1, steady-state frame (update_map + aggregation, cost memory + local map)",
+                       "ms_per_frame_graph": timed(lambda i: step.replay(), 30), "kernels_per_frame": step.launches,
+                       "update_map_ms": timed(lambda i: warp.replay(), 30), "update_map_kernels": warp.launches,
+                       "frames_per_s": None}
+    out["temporal"]["frames_per_s"] = 1e3 / out["temporal"]["ms_per_frame_graph"]
+    return out
 
 
 if __name__ == "__main__":

@@ -250,6 +250,18 @@ int tstereo_splat_metric(const float* pd, float* metric, float* scratch,
 int tstereo_softsplat(const float* x, const float* flow, const float* metric, float* acc,
                       float* out, int B, int C, int h, int w, void* stream);
 
+/* ---------------------------------------------------------------- formats either side of the path
+ * Wire format of the images: uint8 HWC in (one quarter of the fp32 bytes over PCIe), ImageNet-normalised fp32 planes out,
+ * written into a view with element strides (osB, osC).  mean3 / std3 are HOST pointers to 3 floats.
+ * ref: architecture/data/datasets/base.py:120-127 (ToTensor + Normalize, same op order: bit-identical). */
+int tstereo_normalize_u8(const unsigned char* in, float* out, long long osB, long long osC, int B, int H, int W,
+                         const float* mean3, const float* std3, void* stream);
+/* On-device evaluation: acc6 (6 doubles, device) = { sum |gt - est|, mask count, #err>1, #err>2, #err>3, #err>5 } over the
+ * pixels with lb < gt < ub (bounds used when use_lb / use_ub != 0) -- a 48-byte read-back instead of two full-resolution maps.
+ * ref: architecture/data/evaluation/pixel_error.py:6-71 (calc_error), eval.py:31-35 (.clone().cpu()). */
+int tstereo_disp_error(const float* est, const float* gt, float lb, float ub, int use_lb, int use_ub, long long n,
+                       double* acc6, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,32 +28,39 @@ copy_planes_kernel(const T* __restrict__ in, T* __restrict__ out, long long osB,
 }
 
 // --------------------------------------------------------------------------- resize + add + act
-// out = act(trilinear_ac(a) + skip).  thread = one output x; (y, d, c, b) from the grid.
+// out = act(trilinear_ac(a) + skip).  thread = one output (y, x) of one (b, c); it walks all D output planes, so the
+// (y, x) source indices / weights are computed once and the per-plane work is 8 loads + 1 store.  The align_corners
+// scales are IEEE fp32 divisions done by the host (== __fdiv_rn): the first version spent ~300 instructions per output
+// on three in-kernel divisions and the index math (ncu: issue slots 80 %, DRAM 10 %).
 __global__ void __launch_bounds__(128)
 resize_add_act_kernel(const float* __restrict__ a, const float* __restrict__ skip, float* __restrict__ out,
-                      int C, int Da, int Ha, int Wa, int D, int H, int W, int act) {
+                      int Da, int Ha, int Wa, int D, int H, int W, float sd, float sy, float sx, int act) {
     const int pix = blockIdx.x * 128 + threadIdx.x;     // linear over H*W: full CTAs whatever W is
-    int z = blockIdx.y;
-    const int d = z % D;
-    z /= D;  // z = b*C + c
+    const int z = blockIdx.y;                           // b*C + c
     if (pix >= H * W) return;
     const int y = pix / W, x = pix - y * W;
-    const LerpIdx id = ac_index(ac_scale(Da, D), d, Da);
-    const LerpIdx iy = ac_index(ac_scale(Ha, H), y, Ha);
-    const LerpIdx ix = ac_index(ac_scale(Wa, W), x, Wa);
-    const float* p = a + (size_t)z * Da * Ha * Wa;
+    const LerpIdx iy = ac_index(sy, y, Ha);
+    const LerpIdx ix = ac_index(sx, x, Wa);
     const size_t pl = (size_t)Ha * Wa;
+    const float* p = a + (size_t)z * Da * pl;
+    const int o00 = iy.i0 * Wa + ix.i0, o01 = iy.i0 * Wa + ix.i1, o10 = iy.i1 * Wa + ix.i0, o11 = iy.i1 * Wa + ix.i1;
     auto plane = [&](int dd) {
         const float* q = p + dd * pl;
-        const float t0 = ix.w0 * __ldg(q + (size_t)iy.i0 * Wa + ix.i0) + ix.w1 * __ldg(q + (size_t)iy.i0 * Wa + ix.i1);
-        const float t1 = ix.w0 * __ldg(q + (size_t)iy.i1 * Wa + ix.i0) + ix.w1 * __ldg(q + (size_t)iy.i1 * Wa + ix.i1);
+        const float t0 = ix.w0 * __ldg(q + o00) + ix.w1 * __ldg(q + o01);
+        const float t1 = ix.w0 * __ldg(q + o10) + ix.w1 * __ldg(q + o11);
         return iy.w0 * t0 + iy.w1 * t1;
     };
-    float v = id.w0 * plane(id.i0);
-    if (id.w1 != 0.f) v += id.w1 * plane(id.i1);
-    const size_t o = (((size_t)z * D + d) * H + y) * W + x;
-    if (skip) v += __ldg(skip + o);
-    out[o] = apply_act(v, act);
+    size_t o = ((size_t)z * D * H + y) * W + x;
+    const size_t HW = (size_t)H * W;
+#pragma unroll 2
+    for (int d = 0; d < D; ++d) {
+        const LerpIdx id = ac_index(sd, d, Da);         // warp-uniform
+        float v = id.w0 * plane(id.i0);
+        if (id.w1 != 0.f) v += id.w1 * plane(id.i1);
+        if (skip) v += __ldg(skip + o);
+        out[o] = apply_act(v, act);
+        o += HW;
+    }
 }
 
 // --------------------------------------------------------------------------- 5x5x5 avg + max pooling
@@ -191,53 +198,87 @@ merge_memory_kernel(const float* __restrict__ vol, const float* __restrict__ sam
 
 // --------------------------------------------------------------------------- prediction heads
 // cost / offset = (1,3,3) conv, C -> 1, no bias, of the two head feature stacks.
+// thread = FOUR consecutive pixels of a row of one (b, d) plane: per channel and row it loads 6 values (one 16-byte vector
+// + the two neighbours) for 12 FMAs per head tap row, and every weight (shared memory, warp-broadcast) serves 4 pixels —
+// 2.7x fewer instructions than one pixel per thread with nine scalar loads per channel (ncu r02: that form sat at 6-10 % of
+// HBM with issue slots 30-40 %: a load-latency chain).  Outside taps are zero-filled at load time (no mask multiply).
+template <bool VEC>
 __global__ void __launch_bounds__(128)
 heads_kernel(const float* __restrict__ feat, const float* __restrict__ w, float* __restrict__ cost,
              float* __restrict__ off, int C, int D, int H, int W, float delta) {
     extern __shared__ float ws[];  // [2][C][9]
     for (int i = threadIdx.x; i < 2 * C * 9; i += 128) ws[i] = w[i];
     __syncthreads();
-    // thread = one pixel of one (b, d) plane (linear over H*W: full CTAs whatever W is)
-    const int pix = blockIdx.x * 128 + threadIdx.x;
+    const int W4 = (W + 3) >> 2;
+    const int q = blockIdx.x * 128 + threadIdx.x;       // quad index, linear over H * W4
     const int d = blockIdx.y % D, b = blockIdx.y / D;
-    if (pix >= H * W) return;
-    const int y = pix / W, x = pix - y * W;
+    if (q >= H * W4) return;
+    const int y = q / W4, x = (q - y * W4) * 4;
     const size_t HW = (size_t)H * W;
-    // tap validity and offsets once; zero weight on the clamped (in-image) address of an outside tap
-    int toff[9];
-    float tok[9];
+    // rows y-1, y, y+1: offset or -1
+    int roff[3];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-        const int gy = y + t / 3 - 1, gx = x + t % 3 - 1;
-        const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
-        toff[t] = ok ? gy * W + gx : pix;
-        tok[t] = ok ? 1.f : 0.f;
+    for (int r = 0; r < 3; ++r) {
+        const int gy = y + r - 1;
+        roff[r] = (gy >= 0 && gy < H) ? gy * W + x : -1;
     }
-    float res[2];
+    const bool lok = x >= 1, rok = x + 4 < W;
+    float acc[2][4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[h][k] = 0.f;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};          // four independent chains over the channels
         const float* fp = feat + (((size_t)b * 2 * C + h * C) * D + d) * HW;
         const float* wp = ws + h * C * 9;
-        int c = 0;
-        for (; c + 4 <= C; c += 4) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float* fq = fp + (size_t)(c + q) * D * HW;
-#pragma unroll
-                for (int t = 0; t < 9; ++t) acc[q] = fmaf(__ldg(fq + toff[t]) * tok[t], wp[(c + q) * 9 + t], acc[q]);
-            }
-        }
-        for (; c < C; ++c) {
+#pragma unroll 2
+        for (int c = 0; c < C; ++c) {
             const float* fq = fp + (size_t)c * D * HW;
+            float v[3][6];
 #pragma unroll
-            for (int t = 0; t < 9; ++t) acc[0] = fmaf(__ldg(fq + toff[t]) * tok[t], wp[c * 9 + t], acc[0]);
+            for (int r = 0; r < 3; ++r) {
+                if (roff[r] < 0) {
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) v[r][k] = 0.f;
+                    continue;
+                }
+                const float* row = fq + roff[r];
+                v[r][0] = lok ? __ldg(row - 1) : 0.f;
+                if (VEC) {
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(row));
+                    v[r][1] = t.x; v[r][2] = t.y; v[r][3] = t.z; v[r][4] = t.w;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) v[r][1 + k] = (x + k < W) ? __ldg(row + k) : 0.f;
+                }
+                v[r][5] = rok ? __ldg(row + 4) : 0.f;
+            }
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    const float wv = wp[c * 9 + r * 3 + t];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) acc[h][k] = fmaf(v[r][k + t], wv, acc[h][k]);
+                }
         }
-        res[h] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
     }
-    const size_t o = ((size_t)b * D + d) * HW + pix;
-    cost[o] = res[0];
-    off[o] = fminf(fmaxf(tanhf(__fdiv_rn(res[1], 100.0f)), -1.0f), 1.0f) * delta;
+    const size_t o = ((size_t)b * D + d) * HW + (size_t)y * W + x;
+    float offv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) offv[k] = fminf(fmaxf(tanhf(__fdiv_rn(acc[1][k], 100.0f)), -1.0f), 1.0f) * delta;
+    if (VEC) {
+        *reinterpret_cast<float4*>(cost + o) = make_float4(acc[0][0], acc[0][1], acc[0][2], acc[0][3]);
+        *reinterpret_cast<float4*>(off + o) = make_float4(offv[0], offv[1], offv[2], offv[3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (x + k < W) {
+                cost[o + k] = acc[0][k];
+                off[o + k] = offv[k];
+            }
+    }
 }
 
 // --------------------------------------------------------------------------- top-2 soft-argmin
@@ -365,28 +406,45 @@ convex_upsample_kernel(const float* __restrict__ m, const float* __restrict__ w,
 
 // --------------------------------------------------------------------------- UNet up-sampling
 // full[y,x] = sum_k softmax_k(logits) * bilinear_ac(unfold3x3(disp)[k] * W / w)
+// CTA = 128 consecutive x of one output row.  The pre-scaled low-resolution neighbourhood the CTA needs (4 rows x <= 64
+// columns) is staged once in shared memory — one IEEE division per staged value instead of 16 per thread — and the
+// align_corners scales come from the host.  (ncu r02: the per-thread form was instruction-bound, issue slots 83 %.)
+constexpr int UU_TW = 64;
 __global__ void __launch_bounds__(128)
 unet_upsample_kernel(const float* __restrict__ logits, const float* __restrict__ disp, float* __restrict__ full,
-                     int H, int W, int h, int w) {
-    const int x = blockIdx.x * 128 + threadIdx.x;
+                     int H, int W, int h, int w, float sy, float sx) {
+    __shared__ float tile[4][UU_TW];
+    const int x0 = blockIdx.x * 128;
+    const int x = x0 + threadIdx.x;
     const int y = blockIdx.y, b = blockIdx.z;
-    if (x >= W) return;
     const size_t HW = (size_t)H * W;
-    const LerpIdx iy = ac_index(ac_scale(h, H), y, h);
-    const LerpIdx ix = ac_index(ac_scale(w, W), x, w);
+    const LerpIdx iy = ac_index(sy, y, h);
+    const int xc = min(x, W - 1);
+    const LerpIdx ix = ac_index(sx, xc, w);
     const float* dp = disp + (size_t)b * h * w;
     const float mulv = (float)W, divv = (float)w;
+    // staged columns [cmin, cmin + ncol): from one left of the first pixel's i0 to two right of the last pixel's
+    const int cmin = ac_index(sx, x0, w).i0 - 1;
+    const int ncol = ac_index(sx, min(x0 + 127, W - 1), w).i0 + 2 - cmin + 1;
+    const bool staged = ncol <= UU_TW;                   // always for the model's 4x ratio; other ratios read directly
+    auto scaled = [&](int gy, int gx) {
+        return (gy >= 0 && gy < h && gx >= 0 && gx < w) ? __fdiv_rn(__fmul_rn(__ldg(dp + (size_t)gy * w + gx), mulv), divv) : 0.f;
+    };
+    if (staged) {
+        for (int i = threadIdx.x; i < 4 * ncol; i += 128) {
+            const int r = i / ncol, c = i - r * ncol;
+            tile[r][c] = scaled(iy.i0 - 1 + r, cmin + c);
+        }
+        __syncthreads();
+    }
+    if (x >= W) return;
     // 4x4 neighbourhood of the low-res disparity around (iy.i0, ix.i0), zero outside, pre-scaled
     float nb[4][4];
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int gy = iy.i0 - 1 + r, gx = ix.i0 - 1 + c;
-            nb[r][c] = (gy >= 0 && gy < h && gx >= 0 && gx < w)
-                           ? __fdiv_rn(__fmul_rn(__ldg(dp + (size_t)gy * w + gx), mulv), divv)
-                           : 0.f;
-        }
+        for (int c = 0; c < 4; ++c)
+            nb[r][c] = staged ? tile[r][ix.i0 - 1 - cmin + c] : scaled(iy.i0 - 1 + r, ix.i0 - 1 + c);
     const int dy1 = iy.i1 - iy.i0, dx1 = ix.i1 - ix.i0;  // 0 at the last row / column
     const float* lp = logits + (size_t)b * 9 * HW + (size_t)y * W + x;
     float lg[9], mxv = -INFINITY;
@@ -401,8 +459,10 @@ unet_upsample_kernel(const float* __restrict__ logits, const float* __restrict__
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
             // unfolded plane k at low-res (r, c) = disp[r+ky-1, c+kx-1]
-            const float v00 = nb[ky][kx], v01 = nb[ky][kx + dx1];
-            const float v10 = nb[ky + dy1][kx], v11 = nb[ky + dy1][kx + dx1];
+            // dx1, dy1 are 0 or 1: selects instead of dynamic register indexing (which would spill nb to local memory)
+            const float v00 = nb[ky][kx], v01 = dx1 ? nb[ky][kx + 1] : v00;
+            const float v10 = dy1 ? nb[ky + 1][kx] : v00;
+            const float v11 = dy1 ? (dx1 ? nb[ky + 1][kx + 1] : nb[ky + 1][kx]) : v01;
             const float t0 = ix.w0 * v00 + ix.w1 * v01;
             const float t1 = ix.w0 * v10 + ix.w1 * v11;
             const float v = iy.w0 * t0 + iy.w1 * t1;
@@ -454,9 +514,11 @@ int tstereo_resize_add_act(const float* a, const float* skip, float* out, int B,
                            int D, int H, int W, int act, void* stream) {
     TS_REQUIRE(a && out, "resize_add_act: null pointer");
     TS_REQUIRE(B > 0 && C > 0 && Da > 0 && Ha > 0 && Wa > 0 && D > 0 && H > 0 && W > 0, "resize_add_act: bad sizes");
-    TS_REQUIRE((long long)B * C * D <= 65535 && (long long)H * W < (1ll << 31), "resize_add_act: grid too large");
-    dim3 grid(cdiv(H * W, 128), B * C * D);
-    resize_add_act_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a, skip, out, C, Da, Ha, Wa, D, H, W, act);
+    TS_REQUIRE((long long)B * C <= 65535 && (long long)H * W < (1ll << 31), "resize_add_act: grid too large");
+    auto scale = [](int in_size, int out_size) { return out_size > 1 ? (float)(in_size - 1) / (float)(out_size - 1) : 0.0f; };
+    dim3 grid(cdiv(H * W, 128), B * C);
+    resize_add_act_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a, skip, out, Da, Ha, Wa, D, H, W, scale(Da, D), scale(Ha, H),
+                                                                  scale(Wa, W), act);
     return check_launch("resize_add_act");
 }
 
@@ -489,8 +551,10 @@ int tstereo_heads(const float* feat, const float* w, float* cost, float* off, in
     TS_REQUIRE(feat && w && cost && off, "heads: null pointer");
     TS_REQUIRE(B > 0 && C > 0 && C <= 256 && D > 0 && H > 0 && W > 0, "heads: bad sizes");
     TS_REQUIRE((long long)B * D <= 65535 && (long long)H * W < (1ll << 31), "heads: grid too large");
-    dim3 grid(cdiv(H * W, 128), B * D);
-    heads_kernel<<<grid, 128, 2 * C * 9 * sizeof(float), (cudaStream_t)stream>>>(feat, w, cost, off, C, D, H, W, delta);
+    dim3 grid(cdiv(H * ((W + 3) / 4), 128), B * D);
+    const bool vec = (W % 4 == 0) && ((((size_t)feat) | ((size_t)cost) | ((size_t)off)) & 15) == 0;
+    if (vec) heads_kernel<true><<<grid, 128, 2 * C * 9 * sizeof(float), (cudaStream_t)stream>>>(feat, w, cost, off, C, D, H, W, delta);
+    else heads_kernel<false><<<grid, 128, 2 * C * 9 * sizeof(float), (cudaStream_t)stream>>>(feat, w, cost, off, C, D, H, W, delta);
     return check_launch("heads");
 }
 
@@ -528,7 +592,8 @@ int tstereo_unet_upsample(const float* logits, const float* disp, float* full, i
     TS_REQUIRE(logits && disp && full, "unet_upsample: null pointer");
     TS_REQUIRE(B > 0 && B <= 65535 && H > 0 && H <= 65535 && W > 0 && h > 0 && w > 0, "unet_upsample: bad sizes");
     dim3 grid(cdiv(W, 128), H, B);
-    unet_upsample_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(logits, disp, full, H, W, h, w);
+    auto scale = [](int in_size, int out_size) { return out_size > 1 ? (float)(in_size - 1) / (float)(out_size - 1) : 0.0f; };
+    unet_upsample_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(logits, disp, full, H, W, h, w, scale(h, H), scale(w, W));
     return check_launch("unet_upsample");
 }
 

@@ -567,3 +567,42 @@ def softsplat(x: torch.Tensor, flow: torch.Tensor, metric: torch.Tensor) -> torc
     out = torch.empty_like(x)
     _lib.call("tstereo_softsplat", _p(x), _p(flow), _p(metric), _p(acc), _p(out), B, Cc, h, w, _stream())
     return out
+
+
+# --------------------------------------------------------------------------- formats either side of the path
+IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)      # data/datasets/base.py:60-61
+
+
+def normalize_u8(img: torch.Tensor, mean=IMAGENET_MEAN, std=IMAGENET_STD, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """uint8 [B,H,W,3] (the decoded image as it leaves PIL) -> ImageNet-normalised fp32 [B,3,H,W]: ToTensor + Normalize of
+    the reference's data pipeline (data/datasets/base.py:120-127) on the device, so images cross PCIe as bytes."""
+    import ctypes
+    if not img.is_cuda or img.dtype != torch.uint8 or img.dim() != 4 or img.shape[-1] != 3 or not img.is_contiguous():
+        raise TypeError("normalize_u8 needs a contiguous CUDA uint8 tensor [B,H,W,3]")
+    _same_device(img)
+    B, H, W, _ = img.shape
+    out = _out(out, (B, 3, H, W), img)
+    osB, osC, _ = _view5(out)
+    m, s = (ctypes.c_float * 3)(*mean), (ctypes.c_float * 3)(*std)
+    _lib.call("tstereo_normalize_u8", img.data_ptr(), _p(out), osB, osC, B, H, W, ctypes.addressof(m), ctypes.addressof(s), _stream())
+    return out
+
+
+def disp_error(est: torch.Tensor, gt: torch.Tensor, lb: Optional[float] = None, ub: Optional[float] = None) -> torch.Tensor:
+    """calc_error (data/evaluation/pixel_error.py:6-71) on the device: returns a float64 tensor
+    [sum |gt - est|, count, #>1px, #>2px, #>3px, #>5px] over lb < gt < ub; `error_dict` turns it into the reference's dict."""
+    _chk(est, gt)
+    if est.shape != gt.shape:
+        raise ValueError("disp_error: shapes differ")
+    acc = torch.empty((6,), device=est.device, dtype=torch.float64)
+    _lib.call("tstereo_disp_error", _p(est), _p(gt), float(lb or 0.0), float(ub or 0.0), int(lb is not None), int(ub is not None),
+              est.numel(), acc.data_ptr(), _stream())
+    return acc
+
+
+def error_dict(acc: torch.Tensor) -> dict:
+    """The reference's result dict (percentages and EPE) from `disp_error`'s accumulator; one 48-byte read-back."""
+    s, n, c1, c2, c3, c5 = [float(v) for v in acc.cpu()]
+    if n < 1.0:
+        return {"1px": 0.0, "2px": 0.0, "3px": 0.0, "5px": 0.0, "epe": 0.0}
+    return {"1px": 100.0 * c1 / n, "2px": 100.0 * c2 / n, "3px": 100.0 * c3 / n, "5px": 100.0 * c5 / n, "epe": s / n}

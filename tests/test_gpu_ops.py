@@ -784,3 +784,40 @@ def test_conv_d_tc2_into_slice(ops):
     ops.conv_d_tc2(cat[:, :16], ops.pack_conv_d_tc2(w.reshape(16, 16, 5).cuda()), None, 16, 5, 1, 1, False, None, out=cat[:, 16:32])
     close(cat[:, 16:32], want, 1e-5, rtol=1e-5, what="conv_d_tc2 into slice")
     assert (cat[:, 32:] == 0).all()
+
+
+# --------------------------------------------------------------------------- formats either side of the path (f3, f4)
+def test_normalize_u8_matches_totensor_normalize(ops):
+    """uint8 HWC -> normalised fp32 CHW, bit-identical to ToTensor().div(255) + Normalize.sub_(mean).div_(std)
+    (data/datasets/base.py:120-127), also into a slice of a 2B batch buffer."""
+    rng = np.random.RandomState(5)
+    img = torch.from_numpy(rng.randint(0, 256, (2, 37, 53, 3)).astype(np.uint8))
+    mean = torch.tensor(ops.IMAGENET_MEAN).view(1, 3, 1, 1)
+    std = torch.tensor(ops.IMAGENET_STD).view(1, 3, 1, 1)
+    want = (img.permute(0, 3, 1, 2).float().div(255).sub(mean)).div(std)
+    got = ops.normalize_u8(img.cuda())
+    close(got, want, 0.0, what="normalize_u8 (bit-exact)")
+    buf = torch.full((4, 3, 37, 53), 9.0, device="cuda")
+    ops.normalize_u8(img.cuda(), out=buf[2:])
+    assert torch.equal(buf[2:].cpu(), want) and (buf[:2] == 9).all()
+
+
+@pytest.mark.parametrize("lb,ub", [(None, None), (0.0, 192.0), (5.0, None)])
+def test_disp_error_matches_calc_error(ops, lb, ub):
+    """calc_error (data/evaluation/pixel_error.py:6-71) restated with torch ops vs the device reduction."""
+    gt = rnd(2, 1, 61, 97, seed=11, scale=40.0).abs()
+    est = gt + rnd(2, 1, 61, 97, seed=12, scale=2.5)
+    mask = torch.ones_like(gt, dtype=torch.bool)
+    if lb is not None:
+        mask &= gt > lb
+    if ub is not None:
+        mask &= gt < ub
+    err = (gt[mask] - est[mask]).abs()
+    want = {"epe": err.mean().item(), **{f"{k}px": 100.0 * (err > k).float().mean().item() for k in (1, 2, 3, 5)}}
+    got = ops.error_dict(ops.disp_error(est.cuda(), gt.cuda(), lb, ub))
+    assert abs(got["epe"] - want["epe"]) < 1e-5 * max(1.0, want["epe"])
+    for k in ("1px", "2px", "3px", "5px"):
+        assert abs(got[k] - want[k]) < 1e-4, (k, got[k], want[k])
+    # empty mask -> zeros, like the reference
+    z = ops.error_dict(ops.disp_error(est.cuda(), gt.cuda(), 1e9, None))
+    assert z["epe"] == 0.0 and z["1px"] == 0.0

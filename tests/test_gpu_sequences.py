@@ -78,79 +78,69 @@ def check_frame(out, want, what):
     print(what, "EPE", f"{(disps[0].cpu() - rd[0]).abs().mean().item():.2e}", "top-2 mismatches (decided/raw/pixels):", ", ".join(rep))
 
 
-def _perturbed(state, eps, seed):
-    """The recurrent state with every tensor moved by eps-scale noise (the size of the engine-vs-oracle differences)."""
-    g = torch.Generator().manual_seed(seed)
-    out = {}
-    for k, v in state.items():
-        if isinstance(v, dict):
-            out[k] = {a: b + eps * torch.randn(b.shape, generator=g) for a, b in v.items()}
-        elif torch.is_tensor(v) and v.is_floating_point():
-            out[k] = v + eps * torch.randn(v.shape, generator=g)
-        else:
-            out[k] = v
-    return out
+def _cpu(x):
+    if torch.is_tensor(x):
+        return x.detach().cpu()
+    if isinstance(x, dict):
+        return {k: _cpu(v) for k, v in x.items()}
+    return x
 
 
-def _sequence(H, W, B, num_sample, T, seed0=40, sensitivity=True):
-    """Oracle chain over T frames carrying ITS state.  Per frame the engine is checked
-      (1) from the oracle's previous state (same-state comparison: EPE, exact index work) — one discontinuous flip cannot
-          hide later frames;
-      (2) from its OWN previous-frame output state (one frame of carried state).  The reference algorithm amplifies
-          state differences (top-2 selection and the splat's x / (norm + 1e-22) are discontinuous), so the bound is the
-          ORACLE's own sensitivity: the same frame re-run in the oracle from its state perturbed by 1e-5 (px / cost
-          units, the size of the engine's deviations) moves a measured fraction of pixels by > 0.01 px; the engine's
-          carried-state fraction must stay within 2x of that."""
+def _sequence(H, W, B, num_sample, T, seed0=40, engine_chain=True):
+    """Two chains over T frames.
+
+      A  the ORACLE carries its state; per frame the engine starts from the oracle's previous state (same-state comparison:
+         EPE, exact index work), so one discontinuous flip cannot hide later frames.
+      B  the ENGINE carries its OWN state through all T frames (update_map + forward on the device, nothing reset); per
+         frame the oracle is evaluated from a CPU copy of that same engine state and must agree to the same bar.  Every step
+         of the engine's trajectory is thereby a step the reference would have taken from the same state.
+
+    The two trajectories themselves drift apart (printed, not asserted): the reference algorithm amplifies 1e-5-level state
+    differences through its discontinuities (top-2 selection, the splat's x / (norm + 1e-22)) — the oracle re-run from its
+    own state plus 1e-5 noise moves a few per cent of the pixels by more than 0.01 px as well."""
     from temporalstereo_b200 import temporal
     sd = synth.synthetic_state_dict(seed=0)
     eng = _engine(num_sample)
     st = synth.synthetic_temporal_state(H, W, B=B)
     pose = (st["K"], st["T_now"], st["inv_T_prev"], st["baseline"])
     dpose = [p.cuda() for p in pose]
-    ref_state, own_state, prev_ref_state = {}, {}, {}
+    ref_state, own_state = {}, {}
     for t in range(T):
         lf, rf, li, ri = synth.synthetic_frame(H, W, B=B, seed=seed0 + t)
+        dl, dr, dli, dri = _cuda(lf), _cuda(rf), li.cuda(), ri.cuda()
+        # ---- chain A
         dev_in = _cuda(_copy(ref_state))
-        prev_ref_state = _copy(ref_state)
         if t:
             with torch.no_grad():
                 ref_state = O.update_map(ref_state, *pose, H, W, True, 3)
-            dev_in = temporal.update_map(dev_in, *dpose, H, W, True, 3)
-            own_state = temporal.update_map(own_state, *dpose, H, W, True, 3)
-            # the engine's own warp against the oracle's, in the bulk (the splat's normalisation is discontinuous where
-            # almost nothing lands; tests/test_gpu_ops.py pins the per-pixel values against the reference's kernel)
-            for k in ("disp_sample", "cost_volume"):
-                d = (dev_in["cost_memory"][k].cpu() - ref_state["cost_memory"][k]).abs()
-                assert d.median() < 1e-5 and (d > 1e-3).float().mean() < 0.01, (t, k, d.median().item())
-            d = (dev_in["local_map"].cpu() - ref_state["local_map"]).abs()
-            assert d.median() < 1e-5 and (d > 1e-3).float().mean() < 0.01
+            warped = temporal.update_map(dev_in, *dpose, H, W, True, 3)
+            # the engine's warp against the oracle's, in the bulk (the splat's normalisation is discontinuous where almost
+            # nothing lands; tests/test_gpu_ops.py pins the per-pixel values against the reference's own kernel)
+            for got, want_ in ((warped["cost_memory"]["disp_sample"], ref_state["cost_memory"]["disp_sample"]),
+                               (warped["cost_memory"]["cost_volume"], ref_state["cost_memory"]["cost_volume"]),
+                               (warped["local_map"], ref_state["local_map"])):
+                d = (got.cpu() - want_).abs()
+                assert d.median() < 1e-5 and (d > 1e-3).float().mean() < 0.01, (t, d.median().item())
             dev_in = _cuda(_copy(ref_state))
         with torch.no_grad():
             want = O.aggregation_forward(sd, lf, rf, li, ri, _copy(ref_state), num_sample=num_sample)
-        out = eng(_cuda(lf), _cuda(rf), li.cuda(), ri.cuda(), dev_in)
+        out = eng(dl, dr, dli, dri, dev_in)
         n_fine = (min(t, 3) if t else 0) + 5 + 2
         assert out[2][1].shape[1] == n_fine == want[2][1].shape[1], "fine candidates: local map + 5 range + 2 memory"
-        check_frame(out, want, f"{H}x{W} D={16 * num_sample} B={B} frame {t}")
-        if t:
-            own = eng(_cuda(lf), _cuda(rf), li.cuda(), ri.cuda(), own_state)
-            d = (own[0][0].cpu() - want[0][0]).abs()
-            frac = (d > 1e-2).float().mean().item()
-            msg = f"  one frame of carried state, frame {t}: median |d| {d.median().item():.2e} px, > 0.01 px: {100 * frac:.2f} %"
-            assert d.median() < 1e-3, (t, d.median().item())
-            if sensitivity:
-                with torch.no_grad():
-                    pert = O.update_map(_perturbed(prev_ref_state, 1e-5, 100 + t), *pose, H, W, True, 3)
-                    self_out = O.aggregation_forward(sd, lf, rf, li, ri, pert, num_sample=num_sample)
-                sd_ = (self_out[0][0] - want[0][0]).abs()
-                self_frac = (sd_ > 1e-2).float().mean().item()
-                msg += f";  oracle re-run from its state + 1e-5 noise: median {sd_.median().item():.2e}, > 0.01 px: {100 * self_frac:.2f} %"
-                print(msg)
-                assert frac <= 2.0 * self_frac + 0.005, (t, frac, self_frac)
-            else:
-                print(msg)
-        # next frame's own state = the engine's output state of THIS frame (computed from the oracle's state)
-        own_state = out[5]
+        check_frame(out, want, f"A {H}x{W} D={16 * num_sample} B={B} frame {t}")
         ref_state = want[5]
+        # ---- chain B
+        if engine_chain:
+            if t:
+                own_state = temporal.update_map(own_state, *dpose, H, W, True, 3)
+            snapshot = _cpu(_copy(own_state))                     # the state the engine aggregates from, for the oracle
+            own = eng(dl, dr, dli, dri, own_state)
+            own_state = own[5]
+            with torch.no_grad():
+                want_b = O.aggregation_forward(sd, lf, rf, li, ri, snapshot, num_sample=num_sample)
+            check_frame(own, want_b, f"B {H}x{W} D={16 * num_sample} B={B} frame {t} (engine-carried state)")
+            d = (own[0][0].cpu() - want[0][0]).abs()
+            print(f"  chains A/B apart at frame {t}: median {d.median().item():.2e} px, > 0.01 px: {100 * (d > 1e-2).float().mean().item():.2f} %")
 
 
 def test_c4_tartanair_sequence_t5():
@@ -161,7 +151,7 @@ def test_c4_tartanair_sequence_t5():
 def test_c5_1080p_temporal():
     """BASELINE config C5 at its stated shape: 1088x1920 (1080 padded to x16), D=256, T=3 -> the three distinct frame kinds
     (no state / first warp / local map growing), B=2."""
-    _sequence(1088, 1920, 2, 16, 3, sensitivity=False)
+    _sequence(1088, 1920, 2, 16, 3, engine_chain=False)
 
 
 def test_captured_step_replays_bit_identically():
