@@ -250,6 +250,21 @@ int tstereo_splat_metric(const float* pd, float* metric, float* scratch,
 int tstereo_softsplat(const float* x, const float* flow, const float* metric, float* acc,
                       float* out, int B, int C, int h, int w, void* stream);
 
+/* Fused temporal warp: the whole of update_map in three launches (prep: down-sample prev_disp + partial sums + zeroed
+ * accumulators; splat: pose, flow, metric, re-projection of the stored top-2 samples and of the local-map stack, softmax
+ * splat of both groups; normalise).  ref: projects/TemporalStereo/TemporalStereo.py:326-461.
+ *   prev_disp [B,1,Hf,Wf]; K, T_now, inv_T_prev [B,4,4]; baseline [B];
+ *   mem_sample / mem_cost [B,M,h,w] -> out_sample / out_cost [B,M,h,w]          (all four NULL: no cost memory)
+ *   local_map [B,n_lm_in,h,w] (NULL when n_lm_in == 0) -> out_lm [B,n_lm_out,h,w], n_lm_out <= n_lm_in + 1: the warped
+ *   stack [prev_disp at 1/8, local_map][:n_lm_out]                               (n_lm_out == 0, out_lm NULL: no local map)
+ *   scratch: tstereo_update_map_scratch_floats(B, h, w, M, n_lm_out) floats, 8-byte aligned. */
+long long tstereo_update_map_scratch_floats(int B, int h, int w, int M, int n_lm_out);
+int tstereo_update_map(const float* prev_disp, int Hf, int Wf, const float* K, const float* T_now, const float* inv_T_prev,
+                       const float* baseline, const float* mem_sample, const float* mem_cost, int M,
+                       const float* local_map, int n_lm_in, int n_lm_out,
+                       float* out_sample, float* out_cost, float* out_lm, float* scratch,
+                       int B, int h, int w, void* stream);
+
 /* ---------------------------------------------------------------- formats either side of the path
  * Wire format of the images: uint8 HWC in (one quarter of the fp32 bytes over PCIe), ImageNet-normalised fp32 planes out,
  * written into a view with element strides (osB, osC).  mean3 / std3 are HOST pointers to 3 floats.

@@ -55,6 +55,8 @@ SIGNATURES = {
     "tstereo_reproject_disp": (I, [P, P, P, P, I, I, I, I, I, I, P]),
     "tstereo_project_to_3d": (I, [P, P, P, P, I, I, I, I, P]),
     "tstereo_splat_metric": (I, [P, P, P, I, I, I, I, P]),
+    "tstereo_update_map_scratch_floats": (LL, [I, I, I, I, I]),
+    "tstereo_update_map": (I, [P, I, I, P, P, P, P, P, P, I, P, I, I, P, P, P, P, I, I, I, P]),
     "tstereo_softsplat": (I, [P, P, P, P, P, I, I, I, I, P]),
 }
 

@@ -49,7 +49,9 @@ __device__ __forceinline__ void stg4_if(float* p, float a, float b, float c, flo
 // (inverse_warp_3d.py:46 + grid_sampler_unnormalize) lands up to ~1e-6 px off the integer row on
 // ~20 % of the rows, which would blend two rows with weights (1-eps, eps); the kernel samples the
 // nearer row only (deviation <= 2e-6 * |R|, far below the fp32 noise of the following contraction).
-template <bool WARP, bool VEC>
+// GONLY: only the three group-wise terms are produced, into a compact [B, 3G, D, H, W] volume (`out`): the form the
+// fused cost -> first-conv path uses (the L / R_d / -(L-R_d)^2 planes are rebuilt by that conv's producer).
+template <bool WARP, bool VEC, bool GONLY>
 __global__ void __launch_bounds__(128)
 block_cost_main_kernel(const float* __restrict__ L, const float* __restrict__ R,
                        const float* __restrict__ smp, float* __restrict__ out,
@@ -65,7 +67,7 @@ block_cost_main_kernel(const float* __restrict__ L, const float* __restrict__ R,
     const int x = (blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7)) * 4;       // first of the 4 pixels
     const int y = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
     const int HW = H * W;
-    const int outC = (WARP ? 2 * C : C) + 3 * G;
+    const int outC = GONLY ? 3 * G : (WARP ? 2 * C : C) + 3 * G;
     const bool rowin = y < H;
     bool pin[4];
 #pragma unroll
@@ -153,7 +155,8 @@ block_cost_main_kernel(const float* __restrict__ L, const float* __restrict__ R,
             e[k] = l[k] - rv[k];                 // 0 outside the image (l = 0, weights = 0)
             a0[k] = fmaf(e[k], e[k], a0[k]);
         }
-        if (VEC) {
+        if (GONLY) {
+        } else if (VEC) {
             if (pin[0]) {
                 if (WARP) {
                     *reinterpret_cast<float4*>(o1) = make_float4(l[0], l[1], l[2], l[3]);
@@ -191,7 +194,7 @@ block_cost_main_kernel(const float* __restrict__ L, const float* __restrict__ R,
     }
     (void)lmask;
 
-    const int base = WARP ? 2 * C : C;
+    const int base = GONLY ? 0 : (WARP ? 2 * C : C);
     const int H1 = H >> 1, W1 = W >> 1, H2 = H >> 2, W2 = W >> 2;
     float* og = out + (((size_t)b * outC + base + g) * D + d) * HW + pix;
     if (VEC) {
@@ -208,96 +211,6 @@ block_cost_main_kernel(const float* __restrict__ L, const float* __restrict__ R,
         if (x + 3 < W) p1[1] = -a1[1];
     }
     if ((y & 3) == 0 && y + 3 < H && x + 3 < W) g2[(pl * H2 + (y >> 2)) * W2 + (x >> 2)] = -a2;
-}
-
-// Group-wise terms only, into a compact [B, 3G, D, H, W] volume (the side input of the fused cost -> first-conv path; the
-// L / R_d / -(L-R_d)^2 planes are rebuilt by that conv's producer): same arithmetic, in the same order, as
-// block_cost_main_kernel (bit-identical group terms), laid out for the load path instead of the store path.
-//   lane = x (32 consecutive pixels: every right-feature gather of a warp touches one or two 128-byte lines instead of
-//   four rows x strided columns), thread = 4 consecutive rows x 8 channels, and the thread walks ALL D candidates with its
-//   32 left-feature values held in registers (read once instead of D times).  2x2 / 4x4 pooled differences: x pairs by
-//   shfl.xor 1 / 2, y pairs in-thread.  (The store-oriented layout of the kernel above, minus its volume stores, was
-//   L1-wavefront bound at 86 %: 254 us at the 1/4 level of C2, B = 8.)
-template <bool WARP>
-__global__ void __launch_bounds__(128)
-group_cost_kernel(const float* __restrict__ L, const float* __restrict__ R, const float* __restrict__ smp,
-                  float* __restrict__ out, float* __restrict__ g1, float* __restrict__ g2, int C, int H, int W, int D) {
-    const int G = C >> 3;
-    const int g = blockIdx.z % G, b = blockIdx.z / G;
-    const int x = blockIdx.x * 32 + threadIdx.x;
-    const int y0 = (blockIdx.y * 4 + threadIdx.y) * 4;
-    const int HW = H * W;
-    const bool colin = x < W;
-    const int xc = min(x, W - 1);
-    bool pin[4];
-    int yc[4], rrow[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        pin[r] = colin && (y0 + r < H);
-        yc[r] = min(y0 + r, H - 1);
-        rrow[r] = (WARP ? warp_row(yc[r], H) : yc[r]) * W;
-    }
-    const float* Lp = L + ((size_t)b * C + g * 8) * HW;
-    const float* Rp = R + ((size_t)b * C + g * 8) * HW;
-    float l[8][4];
-#pragma unroll
-    for (int c = 0; c < 8; ++c)
-#pragma unroll
-        for (int r = 0; r < 4; ++r) l[c][r] = pin[r] ? __ldg(Lp + (size_t)c * HW + yc[r] * W + xc) : 0.f;
-
-    const int H1 = H >> 1, W1 = W >> 1, H2 = H >> 2, W2 = W >> 2;
-    const size_t plane0 = ((size_t)b * G + g) * D;
-    float* og = out + (((size_t)b * 3 * G + g) * D) * HW;
-    for (int d = 0; d < D; ++d) {
-        int off[4];
-        float wa[4], wb[4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            if (WARP) {
-                const float dsp = __ldg(smp + ((size_t)(b * D + d) * H + yc[r]) * W + xc);
-                int xa;
-                warp_col(xc, dsp, W, pin[r], xa, wa[r], wb[r]);
-                off[r] = rrow[r] + xa;
-            } else {
-                const int xs = xc - d;
-                wa[r] = (pin[r] && xs >= 0) ? 1.f : 0.f;
-                wb[r] = 0.f;
-                off[r] = rrow[r] + max(xs, 0);
-            }
-        }
-        float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[2] = {0.f, 0.f}, a2 = 0.f;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const float* rc = Rp + (size_t)c * HW;
-            float pa[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                float rv;
-                if (WARP) rv = fmaf(__ldg(rc + off[r] + 1), wb[r], __fmul_rn(__ldg(rc + off[r]), wa[r]));
-                else rv = __fmul_rn(__ldg(rc + off[r]), wa[r]);
-                const float e = l[c][r] - rv;            // 0 outside the image (l = 0, weights = 0)
-                a0[r] = fmaf(e, e, a0[r]);
-                pa[r] = e + __shfl_xor_sync(0xffffffffu, e, 1);           // x pair
-            }
-            const float s01 = pa[0] + pa[1], s23 = pa[2] + pa[3];       // 2x2 sums of the two row pairs
-            const float ma = s01 * 0.25f, mb = s23 * 0.25f;
-            a1[0] = fmaf(ma, ma, a1[0]);
-            a1[1] = fmaf(mb, mb, a1[1]);
-            const float q01 = s01 + __shfl_xor_sync(0xffffffffu, s01, 2);  // the neighbouring x pair
-            const float q23 = s23 + __shfl_xor_sync(0xffffffffu, s23, 2);
-            const float mq = (q01 + q23) * 0.0625f;
-            a2 = fmaf(mq, mq, a2);
-        }
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-            if (pin[r]) og[(size_t)d * HW + (size_t)(y0 + r) * W + x] = -a0[r];
-        const size_t pl = plane0 + d;
-        if ((x & 1) == 0 && x + 1 < W) {
-            if (y0 + 1 < H) g1[(pl * H1 + (y0 >> 1)) * W1 + (x >> 1)] = -a1[0];
-            if (y0 + 3 < H) g1[(pl * H1 + (y0 >> 1) + 1) * W1 + (x >> 1)] = -a1[1];
-        }
-        if ((x & 3) == 0 && x + 3 < W && y0 + 3 < H) g2[(pl * H2 + (y0 >> 2)) * W2 + (x >> 2)] = -a2;
-    }
 }
 
 // out planes [base+G+g] and [base+2G+g] <- bilinear_align_corners(G1), (G2)   (block_cost.py:74)
@@ -393,21 +306,15 @@ static int block_cost_launch(bool warp, bool gonly, const float* L, const float*
     float* g1 = scratch;
     float* g2 = scratch + (size_t)B * G * D * H1 * W1;
     const bool vec = (W % 4 == 0) && (((size_t)L | (size_t)out | (size_t)(smp ? smp : L)) & 15) == 0;
-    if (gonly) {
-        TS_REQUIRE((long long)B * G <= 65535, "group_cost: B*C/8 exceeds grid.z");
-        dim3 ggrid(cdiv(W, 32), cdiv(H, 16), B * G), gblock(32, 4);
-        if (warp) group_cost_kernel<true><<<ggrid, gblock, 0, st>>>(L, R, smp, out, g1, g2, C, H, W, D);
-        else group_cost_kernel<false><<<ggrid, gblock, 0, st>>>(L, R, smp, out, g1, g2, C, H, W, D);
-    } else {
     dim3 grid(cdiv(W, 64), cdiv(H, 8), B * G * D);
-#define TS_BC(WP, VC) block_cost_main_kernel<WP, VC><<<grid, 128, 0, st>>>(L, R, smp, out, g1, g2, C, H, W, D)
+#define TS_BC(WP, VC) (gonly ? block_cost_main_kernel<WP, VC, true><<<grid, 128, 0, st>>>(L, R, smp, out, g1, g2, C, H, W, D) \
+                             : block_cost_main_kernel<WP, VC, false><<<grid, 128, 0, st>>>(L, R, smp, out, g1, g2, C, H, W, D))
     if (warp) {
         if (vec) TS_BC(true, true); else TS_BC(true, false);
     } else {
         if (vec) TS_BC(false, true); else TS_BC(false, false);
     }
 #undef TS_BC
-    }
     int rc = check_launch("block_cost_main");
     if (rc) return rc;
     const int base = gonly ? 0 : (warp ? 2 * C : C);

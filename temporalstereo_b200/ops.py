@@ -559,6 +559,31 @@ def splat_metric(pd: torch.Tensor) -> torch.Tensor:
     return metric
 
 
+def update_map_fused(prev_disp: torch.Tensor, K: torch.Tensor, T_now: torch.Tensor, inv_T_prev: torch.Tensor,
+                     baseline: torch.Tensor, mem_sample: Optional[torch.Tensor], mem_cost: Optional[torch.Tensor],
+                     local_map: Optional[torch.Tensor], n_lm_out: int, hw: Tuple[int, int]):
+    """The whole temporal warp in three launches (TemporalStereo.py:326-461): returns (warped samples, warped costs,
+    warped local map), each None when its input group is absent.  `hw` = the 1/8-scale size of the state."""
+    _chk(prev_disp, K, T_now, inv_T_prev, baseline, mem_sample, mem_cost, local_map)
+    B, _, Hf, Wf = prev_disp.shape
+    h, w = hw
+    M = mem_sample.shape[1] if mem_sample is not None else 0
+    n_in = local_map.shape[1] if local_map is not None else 0
+    if mem_sample is not None:
+        assert mem_sample.shape == (B, M, h, w) and mem_cost.shape == (B, M, h, w)
+    if local_map is not None:
+        assert local_map.shape == (B, n_in, h, w)
+    dev = prev_disp.device
+    out_s = torch.empty((B, M, h, w), device=dev, dtype=torch.float32) if M else None
+    out_c = torch.empty((B, M, h, w), device=dev, dtype=torch.float32) if M else None
+    out_l = torch.empty((B, n_lm_out, h, w), device=dev, dtype=torch.float32) if n_lm_out else None
+    n = _lib.load().tstereo_update_map_scratch_floats(B, h, w, M, n_lm_out)
+    scratch = torch.empty((int(n),), device=dev, dtype=torch.float32)
+    _lib.call("tstereo_update_map", _p(prev_disp), Hf, Wf, _p(K), _p(T_now), _p(inv_T_prev), _p(baseline), _p(mem_sample),
+              _p(mem_cost), M, _p(local_map), n_in, n_lm_out, _p(out_s), _p(out_c), _p(out_l), _p(scratch), B, h, w, _stream())
+    return out_s, out_c, out_l
+
+
 def softsplat(x: torch.Tensor, flow: torch.Tensor, metric: torch.Tensor) -> torch.Tensor:
     _chk(x, flow, metric)
     B, Cc, h, w = x.shape

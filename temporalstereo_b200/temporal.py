@@ -54,17 +54,38 @@ def project_to_3d(depth: torch.Tensor, K: torch.Tensor, inv_K: Optional[torch.Te
 
 def update_map(prev_info: dict, K: torch.Tensor, T_now: torch.Tensor, inv_T_prev: torch.Tensor,
                baseline: torch.Tensor, full_h: int, full_w: int, use_past_cost: bool = True,
-               local_map_size: int = 3, with_previous: bool = True) -> dict:
-    """Fused temporal warp (reference projects/TemporalStereo/TemporalStereo.py:326-461): re-projects
-    the previous disparity, the stored top-2 samples/costs and the local map into the current camera
-    and softmax-splats them.  Mutates and returns `prev_info`."""
+               local_map_size: int = 3, with_previous: bool = True, fused: bool = True) -> dict:
+    """Temporal warp (reference projects/TemporalStereo/TemporalStereo.py:326-461): re-projects the previous
+    disparity, the stored top-2 samples/costs and the local map into the current camera and softmax-splats them.
+    Mutates and returns `prev_info`.  `fused` (default): three launches for the whole warp (ops.update_map_fused);
+    otherwise — or when the cost memory and the local map live at different resolutions — the per-stage operators
+    (pose_prep / reproject_disp / splat_metric / softsplat: the drop-ins of project_to_3d and FunctionSoftsplat)."""
     if not with_previous:
         return prev_info
     prev_disp = prev_info["prev_disp"].detach().contiguous().float()
     K = K.contiguous().float()
     T_now, inv_T_prev = T_now.contiguous().float(), inv_T_prev.contiguous().float()
     baseline = baseline.float().reshape(-1).contiguous()
+    memory = prev_info.get("cost_memory", None) if use_past_cost else None
+    lm = prev_info.get("local_map", None) if local_map_size > 0 else None
+    hw_mem = tuple(memory["disp_sample"].shape[-2:]) if memory is not None else None
+    hw_lm = (tuple(lm.shape[-2:]) if lm is not None else (full_h // 8, full_w // 8)) if local_map_size > 0 else None
+    if fused and (hw_mem is None or hw_lm is None or hw_mem == hw_lm) and (hw_mem or hw_lm):
+        n_out = min((lm.shape[1] if lm is not None else 0) + 1, local_map_size) if local_map_size > 0 else 0
+        ds = memory["disp_sample"].detach().contiguous() if memory is not None else None
+        cv = memory["cost_volume"].detach().contiguous() if memory is not None else None
+        ws, wc, wl = ops.update_map_fused(prev_disp, K, T_now, inv_T_prev, baseline, ds, cv,
+                                          lm.contiguous() if lm is not None else None, n_out, hw_mem or hw_lm)
+        prev_info["cost_memory"] = {"disp_sample": ws, "cost_volume": wc} if memory is not None else None
+        prev_info["use_past_cost"] = use_past_cost
+        if local_map_size > 0:
+            prev_info["local_map"] = wl
+            prev_info["local_map_size"] = local_map_size
+        return prev_info
+    return _update_map_staged(prev_info, prev_disp, K, T_now, inv_T_prev, baseline, full_h, full_w, use_past_cost, local_map_size)
 
+
+def _update_map_staged(prev_info, prev_disp, K, T_now, inv_T_prev, baseline, full_h, full_w, use_past_cost, local_map_size):
     def state_at(h, w):
         params = ops.pose_prep(K, T_now, inv_T_prev, baseline, full_w / w)
         pd = ops.bilinear_resize(prev_disp, (h, w), mul=w, div=prev_disp.shape[-1])

@@ -59,23 +59,27 @@ def top2_mismatches(cost, ref_cost, margin=MARGIN):
 def check_frame(out, want, what):
     disps, costs, samples, offs = out[:4]
     rd, rc, rs, ro = want[:4]
-    for i, (a, b) in enumerate(zip(disps, rd)):
+    epes = [(a.cpu() - b).abs().mean().item() for a, b in zip(disps, rd)]
+    rep, bad_total = [], 0
+    for i, lvl in enumerate(("precise", "fine", "coarse")):
+        bad, raw, n = top2_mismatches(costs[i], rc[i])
+        bad_total += bad
+        rep.append(f"{lvl} {bad}/{raw}/{n} (max |dcost| {(costs[i].cpu() - rc[i]).abs().max().item():.1e})")
+    print(what, "EPE full/precise/fine/coarse", " ".join(f"{e:.2e}" for e in epes),
+          "| top-2 mismatches (decided/raw/pixels):", ", ".join(rep), flush=True)
+    for a, b in zip(disps, rd):
         assert tuple(a.shape) == tuple(b.shape)
-        epe = (a.cpu() - b).abs().mean().item()
-        assert epe < EPE_TOL, f"{what}: disp{i} EPE {epe:.3e} px"
     # coarse candidates = sorted [integers 0..Dc-1 | two memory samples]: the integer entries (index work) must be exact
     # everywhere and sit at the same sorted positions; the memory entries are bilinear re-samplings (fp32 rounding)
     got_s, ref_s = samples[2].cpu(), rs[2]
     integral = ref_s == ref_s.round()
     assert torch.equal(got_s[integral], ref_s[integral]), f"{what}: coarse candidate list differs"
     assert (got_s - ref_s).abs().max() < 2e-5, f"{what}: coarse memory candidates differ"
-    rep = []
-    for i, lvl in enumerate(("precise", "fine", "coarse")):
-        bad, raw, n = top2_mismatches(costs[i], rc[i])
-        rep.append(f"{lvl} {bad}/{raw}/{n}")
-        assert bad == 0, f"{what}: {bad} top-2 index mismatches at the {lvl} level outside the tie margin ({raw} incl. ties of {n})"
+    assert bad_total == 0, f"{what}: top-2 index mismatches outside the tie margin: {rep}"
+    for i in range(3):
         assert (costs[i].cpu() - rc[i]).abs().max() < 2e-3
-    print(what, "EPE", f"{(disps[0].cpu() - rd[0]).abs().mean().item():.2e}", "top-2 mismatches (decided/raw/pixels):", ", ".join(rep))
+    for i, e in enumerate(epes):
+        assert e < EPE_TOL, f"{what}: disp{i} EPE {e:.3e} px"
 
 
 def _cpu(x):
