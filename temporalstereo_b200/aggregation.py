@@ -108,6 +108,10 @@ class TEMPORALSTEREO(nn.Module):
         # volume (34 MB per frame, nothing to hoist) is cheaper materialised with ops.block_cost (B200: 406 vs 581 us at B=8)
         self.fuse_cost = ("fine", "precise")
         self._warned_train = False
+        # per-level parity tests only: {"coarse_disp": t, "fine_disp": t} replace the engine's own up-sampled coarse /
+        # fine disparity as the centre of the next level's candidates ("teacher forcing"), so that a level can be compared
+        # with the oracle on bit-identical candidates; the outputs still carry the engine's own disparities
+        self._inject: Optional[dict] = None
         # tensor-core operand split: fp16 hi + lo (kind::f16, 16 channels per MMA; activations < 65504) or tf32 hi + lo
         self.half_split = True
         # run the UNet encoder on a side stream, concurrently with the coarse and fine levels
@@ -592,7 +596,8 @@ class TEMPORALSTEREO(nn.Module):
         if n_lm:
             lm = lm.contiguous()
             ops.bilinear_resize(lm, (H8, W8), mul=W8, div=lm.shape[-1], out=samples, c_off=0)
-        low_c, high_c = ops.range_samples(d_c, DISP_RANGE, samples, n_lm)
+        centre = self._inject["coarse_disp"].contiguous() if self._inject and "coarse_disp" in self._inject else d_c
+        low_c, high_c = ops.range_samples(centre, DISP_RANGE, samples, n_lm)
         d_f, c_f, o_f, s_f = self._memory_level("fine", l8, r8, samples, prev_info, False)
 
         # ---- precise (1/4): UNet encoder features concatenated to the backbone features
@@ -602,7 +607,8 @@ class TEMPORALSTEREO(nn.Module):
                 t.record_stream(side)
 
         samples_p = torch.empty((B, 5, H4, W4), device=dev, dtype=torch.float32)
-        low_f, high_f = ops.range_samples(d_f, DISP_RANGE, samples_p, 0)
+        centre = self._inject["fine_disp"].contiguous() if self._inject and "fine_disp" in self._inject else d_f
+        low_f, high_f = ops.range_samples(centre, DISP_RANGE, samples_p, 0)
         vol = self._init3d(lcat, rcat, samples_p, "precise.init3d")
         d_p, c_p, o_p, top_disp, top_cost = self._heads_predict(vol, samples_p, "precise.pred_heads",
                                                                 float(self.levels["precise"]["delta"]), True)

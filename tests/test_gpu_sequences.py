@@ -4,12 +4,15 @@
   C4  TartanAir 480x640, D=320 (20 coarse candidates), T=5 sequence, B>=2
   C5  1088x1920 (1080x1920 padded), D=256 (16 candidates), temporal frame, B=2
 
-Index work is checked as index work: the coarse candidate list must be exact everywhere, and the top-2 selection of every
-level must pick the same two candidates as the oracle wherever the oracle's decision is not within rounding of a tie
-(margin between the 2nd and 3rd best cost > MARGIN); regressed disparity within 1e-3 px EPE (north_star).
+Index work is checked as index work: the coarse candidate list must be exact, and the top-2 selection of every level
+must pick the same two candidates as the oracle wherever the oracle's decision is not within rounding of a tie (margin
+between the 2nd and 3rd best cost > MARGIN); regressed disparity within 1e-3 px EPE (north_star).  Pixels whose candidate
+SORT is itself decided by < 1e-4 px between a memory plane and a regular plane (see `sort_tie_masks`) are excluded with
+their receptive field and their share of the image is reported (a fraction of a per cent).
 """
 import pytest
 import torch
+import torch.nn.functional as F
 
 from oracle import oracle as O
 from temporalstereo_b200 import synth
@@ -41,43 +44,82 @@ def _engine(num_sample):
     return eng.cuda().eval()
 
 
-def top2_mismatches(cost, ref_cost, margin=MARGIN):
-    """Pixels whose top-2 candidate SET differs from the oracle's, counted only where the oracle's 2nd and 3rd best
-    costs are more than `margin` apart (otherwise the choice is a rounding-level tie in the reference itself)."""
+def top2_mismatches(cost, ref_cost, keep, margin=MARGIN):
+    """Pixels (inside `keep`) whose top-2 candidate SET differs from the oracle's, counted only where the oracle's 2nd and
+    3rd best costs are more than `margin` apart (otherwise the choice is a rounding-level tie in the reference itself)."""
     ref_top = torch.topk(ref_cost, k=min(3, ref_cost.shape[1]), dim=1)
     got_top = torch.topk(cost.cpu(), k=2, dim=1)
     a = torch.sort(ref_top.indices[:, :2], dim=1).values
     b = torch.sort(got_top.indices, dim=1).values
-    differs = (a != b).any(1)
+    differs = (a != b).any(1) & keep
     if ref_cost.shape[1] > 2:
         decided = (ref_top.values[:, 1] - ref_top.values[:, 2]) > margin
     else:
         decided = torch.ones_like(differs)
-    return int((differs & decided).sum()), int(differs.sum()), differs.numel()
+    return int((differs & decided).sum()), int(differs.sum()), int(keep.sum())
 
 
-def check_frame(out, want, what):
+def _dilate(m, r):
+    return F.max_pool2d(m.float().unsqueeze(1), 2 * r + 1, 1, r).squeeze(1) > 0
+
+
+def sort_tie_masks(ref_samples, has_memory, tol=1e-4):
+    """Where the reference's candidate SORT is decided by less than `tol`.
+
+    merge_memory concatenates the level's candidates with the two memory samples and sorts them (coarse.py:100-104,
+    fine.py:118-122); the volume planes follow the permutation.  A memory plane (past_conv of a stored cost) and a regular
+    plane have unrelated contents, so when a memory sample lands within rounding of another candidate the order of two
+    DIFFERENT planes hangs on the last bits of the previous level's disparity — a discontinuity of the reference algorithm
+    (the fp64 oracle flips there against the fp32 one as well), not something a kernel can match.  Returns per-level keep
+    masks (precise, fine, coarse, full) that exclude those pixels and the receptive field they feed (pool5 / 3x3 convs:
+    radius 6 at the level, doubled by each up-sampling)."""
+    s_p, s_f, s_c = ref_samples
+
+    def near(s):
+        d = s[:, 1:] - s[:, :-1]                     # sorted ascending
+        t = d < tol
+        if not has_memory:                           # the two zero samples of single-frame mode tie EXACTLY on both sides
+            t &= d > 0
+        return t.any(1)
+    tie_c = _dilate(near(s_c), 6)
+    up = lambda m: F.interpolate(m.float().unsqueeze(1), scale_factor=2, mode="nearest").squeeze(1) > 0
+    tie_f = _dilate(near(s_f) | _dilate(up(tie_c), 2), 6)
+    tie_p = _dilate(up(tie_f), 6)
+    tie_full = _dilate(F.interpolate(tie_p.float().unsqueeze(1), scale_factor=4, mode="nearest").squeeze(1) > 0, 4)
+    return ~tie_p, ~tie_f, ~tie_c, ~tie_full
+
+
+def check_frame(out, want, what, has_memory, strict=False):
+    """strict: nothing excluded (used when the levels run on the oracle's candidates: the sorts cannot flip)."""
     disps, costs, samples, offs = out[:4]
     rd, rc, rs, ro = want[:4]
-    epes = [(a.cpu() - b).abs().mean().item() for a, b in zip(disps, rd)]
+    keep_p, keep_f, keep_c, keep_full = sort_tie_masks(rs, has_memory, tol=-1.0 if strict else 1e-4)
+    keeps = [keep_p, keep_f, keep_c]
+    dkeep = [keep_full, keep_p, keep_p, keep_f]          # disps: full, precise (1/4), fine up-sampled (1/4), coarse up-sampled (1/8)
+    excluded = 1.0 - keep_full.float().mean().item()
+    epes = [((a.cpu() - b).abs()[:, 0][k]).mean().item() for a, b, k in zip(disps, rd, dkeep)]
     rep, bad_total = [], 0
     for i, lvl in enumerate(("precise", "fine", "coarse")):
-        bad, raw, n = top2_mismatches(costs[i], rc[i])
+        bad, raw, n = top2_mismatches(costs[i], rc[i], keeps[i])
         bad_total += bad
-        rep.append(f"{lvl} {bad}/{raw}/{n} (max |dcost| {(costs[i].cpu() - rc[i]).abs().max().item():.1e})")
+        dc = (costs[i].cpu() - rc[i]).abs().amax(1)[keeps[i]].max().item()
+        rep.append(f"{lvl} {bad}/{raw}/{n} (max |dcost| {dc:.1e})")
+        assert dc < 2e-3, f"{what}: {lvl} costs differ by {dc:.2e} away from any sort tie"
     print(what, "EPE full/precise/fine/coarse", " ".join(f"{e:.2e}" for e in epes),
-          "| top-2 mismatches (decided/raw/pixels):", ", ".join(rep), flush=True)
+          "| top-2 mismatches (decided/raw/pixels):", ", ".join(rep), f"| sort-tie neighbourhoods excluded: {100 * excluded:.2f} % of the image",
+          flush=True)
     for a, b in zip(disps, rd):
         assert tuple(a.shape) == tuple(b.shape)
     # coarse candidates = sorted [integers 0..Dc-1 | two memory samples]: the integer entries (index work) must be exact
     # everywhere and sit at the same sorted positions; the memory entries are bilinear re-samplings (fp32 rounding)
     got_s, ref_s = samples[2].cpu(), rs[2]
-    integral = ref_s == ref_s.round()
+    integral = (ref_s == ref_s.round()) & keep_c.unsqueeze(1)
     assert torch.equal(got_s[integral], ref_s[integral]), f"{what}: coarse candidate list differs"
-    assert (got_s - ref_s).abs().max() < 2e-5, f"{what}: coarse memory candidates differ"
+    assert (got_s - ref_s).abs().amax(1)[keep_c].max() < 2e-5, f"{what}: coarse memory candidates differ"
     assert bad_total == 0, f"{what}: top-2 index mismatches outside the tie margin: {rep}"
-    for i in range(3):
-        assert (costs[i].cpu() - rc[i]).abs().max() < 2e-3
+    if strict:
+        assert excluded == 0.0
+        assert torch.equal(samples[2].cpu(), rs[2]) or has_memory, f"{what}: single-frame coarse candidates must be bit-exact"
     for i, e in enumerate(epes):
         assert e < EPE_TOL, f"{what}: disp{i} EPE {e:.3e} px"
 
@@ -128,10 +170,19 @@ def _sequence(H, W, B, num_sample, T, seed0=40, engine_chain=True):
             dev_in = _cuda(_copy(ref_state))
         with torch.no_grad():
             want = O.aggregation_forward(sd, lf, rf, li, ri, _copy(ref_state), num_sample=num_sample)
+        # (1) level by level on bit-identical candidates: the engine's fine / precise levels are centred on the ORACLE's
+        #     up-sampled coarse / fine disparities, so no candidate sort can flip: strict everywhere, nothing excluded
+        eng._inject = {"coarse_disp": want[0][3].cuda(), "fine_disp": want[0][2].cuda()}
+        try:
+            forced = eng(dl, dr, dli, dri, _cuda(_copy(ref_state)))
+        finally:
+            eng._inject = None
+        check_frame(forced, want, f"A {H}x{W} D={16 * num_sample} B={B} frame {t} (levels on the oracle's candidates)", t > 0, strict=True)
+        # (2) end to end, each level centred on the engine's own previous level
         out = eng(dl, dr, dli, dri, dev_in)
         n_fine = (min(t, 3) if t else 0) + 5 + 2
         assert out[2][1].shape[1] == n_fine == want[2][1].shape[1], "fine candidates: local map + 5 range + 2 memory"
-        check_frame(out, want, f"A {H}x{W} D={16 * num_sample} B={B} frame {t}")
+        check_frame(out, want, f"A {H}x{W} D={16 * num_sample} B={B} frame {t} (end to end)", t > 0)
         ref_state = want[5]
         # ---- chain B
         if engine_chain:
@@ -142,7 +193,7 @@ def _sequence(H, W, B, num_sample, T, seed0=40, engine_chain=True):
             own_state = own[5]
             with torch.no_grad():
                 want_b = O.aggregation_forward(sd, lf, rf, li, ri, snapshot, num_sample=num_sample)
-            check_frame(own, want_b, f"B {H}x{W} D={16 * num_sample} B={B} frame {t} (engine-carried state)")
+            check_frame(own, want_b, f"B {H}x{W} D={16 * num_sample} B={B} frame {t} (engine-carried state)", t > 0)
             d = (own[0][0].cpu() - want[0][0]).abs()
             print(f"  chains A/B apart at frame {t}: median {d.median().item():.2e} px, > 0.01 px: {100 * (d > 1e-2).float().mean().item():.2f} %")
 
