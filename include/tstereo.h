@@ -103,7 +103,10 @@ int tstereo_conv_hw3(const float* in, long long isB, long long isC, long long is
  * row = part*N + kx*CP + co (part 0 = hi, 1 = lo); tstereo_conv_hw3_tc2_wpack_floats(Cin, Cout, half) floats.
  * half != 0 (all four tc2 entry points): operands split as fp16 hi + fp16 lo and multiplied with kind::f16 — 16 channels per
  * chunk, each 16-byte row of the image holds 8 halves instead of 4 floats (ops.py pack_*(..., half=True)); activations must
- * stay below 65504 in magnitude. */
+ * stay below 65504 in magnitude.  half == 2: the same fp16 image, but only the A_hi * B_hi product is issued (11-bit
+ * operands, one MMA term instead of three) -- for layers whose measured sensitivity allows it (the UNet
+ * decoder after the top-2 selection).
+ * oscale [Cout] or NULL: multiplier of the accumulator before the bias (1 / the weight pre-scale of ops.fp16_prescale). */
 long long tstereo_conv_hw3_tc2_wpack_floats(int Cin, int Cout, int half);
 int tstereo_conv_hw3_tc2(const float* in, long long isB, long long isC, long long isD,
                          float* out, long long osB, long long osC, long long osD,

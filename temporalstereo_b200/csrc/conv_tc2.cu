@@ -30,7 +30,7 @@ int tstereo_conv_hw3_tc2(const float* in, long long isB, long long isC, long lon
     p.wpack = wpack; p.bias = bias; p.oscale = oscale;
     p.Cin = Cin; p.H = H; p.W = W; p.D = D; p.Hin = H; p.Win = W;
     p.isY = W; p.isX = 1; p.osY = W; p.osX = 1;
-    p.dil = dilation; p.act = act; p.nky = 3; p.half = half != 0;
+    p.dil = dilation; p.act = act; p.nky = 3; p.half = half != 0; p.terms = half == 2 ? 1 : 3;
     p.cpp = (Cin + 7) / 8;
     p.nchunk = p.cpp;
     p.G = 8;
@@ -56,7 +56,7 @@ int tstereo_conv_hw3s2_tc2(const float* in, long long isB, long long isC, long l
     p.wpack = wpack; p.bias = bias; p.oscale = oscale;
     p.Cin = Cin; p.H = H; p.W = W; p.D = D; p.Hin = Hin; p.Win = Win;
     p.isY = 2 * Win; p.isX = 2; p.osY = W; p.osX = 1;
-    p.dil = 1; p.act = act; p.nky = 3; p.half = half != 0;
+    p.dil = 1; p.act = act; p.nky = 3; p.half = half != 0; p.terms = half == 2 ? 1 : 3;
     p.cpp = (Cin + 7) / 8;
     p.nchunk = 4 * p.cpp;
     p.G = 32;     // of a chunk's 9 taps only the 1-4 that exist for its phase are non-zero: same products per group as G = 8
@@ -81,7 +81,7 @@ int tstereo_deconv_hw_tc2(const float* in, long long isB, long long isC, long lo
     p.bias = bias; p.oscale = oscale;
     p.Cin = Cin; p.H = Hin; p.W = Win; p.D = D; p.Hin = Hin; p.Win = Win;
     p.isY = Win; p.isX = 1; p.osY = 4 * Win; p.osX = 2;      // output plane is (2*Hin) x (2*Win)
-    p.dil = 1; p.act = act; p.nky = 3; p.half = half != 0;
+    p.dil = 1; p.act = act; p.nky = 3; p.half = half != 0; p.terms = half == 2 ? 1 : 3;
     p.cpp = (Cin + 7) / 8;
     p.nchunk = p.cpp;
     p.G = 8;
@@ -124,7 +124,7 @@ int tstereo_conv_d_tc2(const float* in, long long isB, long long isC, long long 
     p.wpack = wpack; p.bias = bias; p.oscale = oscale;
     p.Cin = Cin; p.H = H; p.W = W; p.D = Dout; p.Hin = H; p.Win = W;
     p.isY = W; p.isX = 1; p.osY = W; p.osX = 1;
-    p.dil = 0; p.act = act; p.nky = 1; p.half = half != 0; p.fold = half ? 1 : 3;
+    p.dil = 0; p.act = act; p.nky = 1; p.half = half != 0; p.terms = half == 2 ? 1 : 3; p.fold = half ? 1 : 3;
     p.kd = k; p.dstride = stride; p.ddil = dilation; p.Din = Din; p.dtrans = transposed;
     p.cpp = (Cin + 7) / 8;
     p.nchunk = k * p.cpp;

@@ -88,6 +88,7 @@ struct Params {
     int nbatch;                   // batch size (extent of the TMA view's last dimension)
     int fold;                     // 3: kx taps folded into N (3x3 forms); 1: single column block ((k,1,1) form)
     int half;                     // operands as fp16 hi + lo (kind::f16, 16 channels per MMA) instead of tf32 hi + lo
+    int terms;                    // 3: error-compensated hi+lo products; 1 (fp16, DIRECT only): A_hi * B_hi alone (11-bit operands)
     int nky;                      // ky taps of the virtual conv: 3, or 1 for the (k,1,1) convs along D
     int kd, dstride, ddil, Din, dtrans;   // kd > 0: phases are input planes of a conv along D (p.D = Dout)
     // ---- fused cost volume -> first conv (template FUSE != 0; SURVEY.md §8d "fused path").  The virtual input is the raw
@@ -562,17 +563,20 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
                 for (int u = 0; u < RPW; ++u) {
                     const int r = warp + 8 * u;
                     if (r < SR) {
-                        uint32_t hi[4], lo[4];
+                        uint32_t hi[4];
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            const float xa = val(u, r, 2 * c), xb = val(u, r, 2 * c + 1);
-                            hi[c] = pack_h2(xa, xb);
-                            const float2 hf = unpack_h2(hi[c]);
-                            lo[c] = pack_h2(xa - hf.x, xb - hf.y);
-                        }
+                        for (int c = 0; c < 4; ++c) hi[c] = pack_h2(val(u, r, 2 * c), val(u, r, 2 * c + 1));
                         const uint32_t o = (uint32_t)(r * 32 + lane) * 16u;
                         sts128(a_hi + ko + o, hi[0], hi[1], hi[2], hi[3]);
-                        sts128(a_lo + ko + o, lo[0], lo[1], lo[2], lo[3]);
+                        if (p.terms == 3) {                             // uniform: the single-term form needs no lo half
+                            uint32_t lo[4];
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                const float2 hf = unpack_h2(hi[c]);
+                                lo[c] = pack_h2(val(u, r, 2 * c) - hf.x, val(u, r, 2 * c + 1) - hf.y);
+                            }
+                            sts128(a_lo + ko + o, lo[0], lo[1], lo[2], lo[3]);
+                        }
                         if (!(k & 1) && k == p.nchunk - 1) {            // odd number of units: the last K half is zero
                             sts128(a_hi + khalf + o, 0u, 0u, 0u, 0u);
                             sts128(a_lo + khalf + o, 0u, 0u, 0u, 0u);
@@ -699,8 +703,10 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
                         if constexpr (DIRECT) {
                             // all three terms into the same N columns (B rows [0,N) = hi, [N,2N) = lo)
                             mma(d_tmem, a_hi + ad, bd, idesc_n, acc0);
-                            mma(d_tmem, a_hi + ad, bd + (uint64_t)N, idesc_n, 1u);
-                            mma(d_tmem, a_lo + ad, bd, idesc_n, 1u);
+                            if (p.terms == 3) {
+                                mma(d_tmem, a_hi + ad, bd + (uint64_t)N, idesc_n, 1u);
+                                mma(d_tmem, a_lo + ad, bd, idesc_n, 1u);
+                            }
                         } else {
                             // [A*B_hi | A_hi*B_lo] (+)= A_hi * [B_hi | B_lo]
                             mma(d_tmem, a_hi + ad, bd, idesc_2n, acc0);
@@ -830,6 +836,11 @@ static int launch(Params& p, int CP, int planes, cudaStream_t st, const char* wh
     if (p.G < 1) p.G = 1;
     const int nmma = p.half ? (p.nchunk + 1) / 2 : p.nchunk;
     if (p.half) p.G = (p.G + 1) / 2;                     // same products per accumulation group: 16 channels per chunk
+    if (p.terms != 1) p.terms = 3;
+    if (p.terms == 1) {
+        TS_REQUIRE(p.half && FUSE == 0, "%s: the single-term form is an fp16 variant of the plain convolutions", what);
+        p.G = nmma;                                      // 11-bit operands: nothing to gain from short TMEM accumulation groups
+    }
     const bool direct = FUSE == 0 && nmma <= p.G && !env_int("TSTEREO_TC2_NODIRECT", 0);
     // M-tiles per CTA: 2 or 4 (TMEM: MT * columns-per-tile <= 512); cost = SM-time of all waves
     p.nbatch = planes / p.D;

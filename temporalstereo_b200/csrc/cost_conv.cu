@@ -38,7 +38,7 @@ int cost_conv(int fuse, const float* left, const float* right, const float* samp
     p.wpack = wpack; p.bias = bias; p.oscale = oscale;
     p.H = H; p.W = W; p.D = D; p.Hin = H; p.Win = W;
     p.isY = W; p.isX = 1; p.osY = W; p.osX = 1;
-    p.dil = 1; p.act = act; p.nky = 3; p.half = half != 0;
+    p.dil = 1; p.act = act; p.nky = 3; p.half = half != 0; p.terms = 3;
     p.wchunks = C / 8;
     p.Cin = C + G3;
     p.cpp = p.wchunks + (G3 + 7) / 8;

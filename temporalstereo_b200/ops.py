@@ -300,7 +300,7 @@ def conv_hw3_tc2(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Tens
     isB, isC, isD = _view5(x)
     osB, osC, osD = _view5(out)
     _chk(wpack, bias, oscale)
-    assert wpack.numel() == _lib.load().tstereo_conv_hw3_tc2_wpack_floats(Cin, cout, int(half))
+    assert wpack.numel() == _lib.load().tstereo_conv_hw3_tc2_wpack_floats(Cin, cout, int(bool(half)))
     _lib.call("tstereo_conv_hw3_tc2", _p(x), isB, isC, isD, _p(out), osB, osC, osD, _p(wpack), _p(bias), _p(oscale),
               B, Cin, cout, D, H, W, dilation, ACT[act], int(half), _stream())
     return out
@@ -318,7 +318,7 @@ def conv_hw3s2_tc2(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Te
     isB, isC, isD = _view5(x)
     osB, osC, osD = _view5(out)
     _chk(wpack, bias, oscale)
-    assert wpack.numel() == _lib.load().tstereo_conv_hw3s2_tc2_wpack_floats(Cin, cout, int(half))
+    assert wpack.numel() == _lib.load().tstereo_conv_hw3s2_tc2_wpack_floats(Cin, cout, int(bool(half)))
     _lib.call("tstereo_conv_hw3s2_tc2", _p(x), isB, isC, isD, _p(out), osB, osC, osD, _p(wpack), _p(bias), _p(oscale),
               B, Cin, cout, D, Hin, Win, ACT[act], int(half), _stream())
     return out
@@ -335,7 +335,7 @@ def deconv_hw_tc2(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Ten
     isB, isC, isD = _view5(x)
     osB, osC, osD = _view5(out)
     _chk(wpack, bias, oscale)
-    assert wpack.numel() == _lib.load().tstereo_deconv_hw_tc2_wpack_floats(Cin, cout, int(half))
+    assert wpack.numel() == _lib.load().tstereo_deconv_hw_tc2_wpack_floats(Cin, cout, int(bool(half)))
     _lib.call("tstereo_deconv_hw_tc2", _p(x), isB, isC, isD, _p(out), osB, osC, osD, _p(wpack), _p(bias), _p(oscale),
               B, Cin, cout, D, Hin, Win, ACT[act], int(half), _stream())
     return out

@@ -279,3 +279,28 @@ def test_materialised_cost_path_agrees_with_the_fused_one(engine):
     finally:
         engine.fuse_cost = default
     assert (outs["True"][0][0] - outs["False"][0][0]).abs().mean() < 1e-4
+
+
+def test_decoder_single_term_precision(engine):
+    """The UNet decoder runs one fp16 MMA term (engine.decoder_single_term): measured on the oracle at 7.6e-5 px EPE
+    (tests/tools/precision_probe_decoder.py).  On the GPU: both settings within 1e-3 px of the oracle, every output other
+    than the full-resolution disparity bit-identical between them."""
+    sd = synth.synthetic_state_dict(seed=0)
+    lf, rf, li, ri = synth.synthetic_frame(128, 192, B=2, seed=9)
+    with torch.no_grad():
+        want = O.aggregation_forward(sd, lf, rf, li, ri, {})
+    assert engine.decoder_single_term
+    fast = engine(_cuda(lf), _cuda(rf), li.cuda(), ri.cuda(), {})
+    engine.decoder_single_term = False
+    try:
+        exact = engine(_cuda(lf), _cuda(rf), li.cuda(), ri.cuda(), {})
+    finally:
+        engine.decoder_single_term = True
+    _check(fast, want[:4], "decoder single-term")
+    _check(exact, want[:4], "decoder 3-term")
+    for a, b in zip(fast[0][1:] + fast[1] + fast[2] + fast[3], exact[0][1:] + exact[1] + exact[2] + exact[3]):
+        assert torch.equal(a, b)
+    d = (fast[0][0] - exact[0][0]).abs()
+    e3 = (exact[0][0].cpu() - want[0][0]).abs().mean().item()
+    print(f"decoder single-term vs 3-term: EPE {d.mean().item():.2e} max {d.max().item():.2e}; 3-term vs oracle {e3:.2e}")
+    assert d.mean() < 5e-4

@@ -821,3 +821,28 @@ def test_disp_error_matches_calc_error(ops, lb, ub):
     # empty mask -> zeros, like the reference
     z = ops.error_dict(ops.disp_error(est.cuda(), gt.cuda(), 1e9, None))
     assert z["epe"] == 0.0 and z["1px"] == 0.0
+
+
+@pytest.mark.parametrize("Cin,Cout,H,W", [(128, 32, 34, 60), (64, 32, 40, 52), (32, 9, 20, 37)])
+def test_single_term_fp16_convs(ops, Cin, Cout, H, W):
+    """half=2: one MMA term (A_hi * B_hi): fp16-rounded operands, fp32 accumulate — the UNet decoder's precision.  Against
+    the fp64 conv of the fp16-ROUNDED operands it is exact to accumulation rounding; against the fp32 conv it carries the
+    operand rounding (2^-11 relative per product)."""
+    x = rnd(2, Cin, H, W, seed=81)
+    w = rnd(Cout, Cin, 3, 3, seed=82, scale=(2.0 / (9 * Cin)) ** 0.5)
+    b = rnd(Cout, seed=83, scale=0.1)
+    ws, inv = ops.fp16_prescale(w.reshape(Cout, Cin, 9))
+    got = ops.conv_hw3_tc2(x.cuda(), ops.pack_conv_hw3_tc2(ws, True).cuda(), b.cuda(), Cout, 1, "ReLU", half=2, oscale=inv.cuda())
+    xr = x.half().double()
+    wr = (ws.half().double() * inv.double().view(-1, 1, 1)).reshape(Cout, Cin, 3, 3)
+    close(got, F.relu(F.conv2d(xr, wr, b.double(), 1, 1)).float(), 2e-5, rtol=1e-5, what="single-term conv vs rounded-operand reference")
+    full = F.relu(F.conv2d(x.double(), w.double(), b.double(), 1, 1)).float()
+    err = (got.cpu() - full).abs().max().item()
+    assert 1e-6 < err < 5e-3, err
+    # transposed 4x4 (deconv4 / deconv2 of the decoder)
+    wt = rnd(Cin, Cout, 4, 4, seed=84, scale=(2.0 / (16 * Cin)) ** 0.5)
+    wk = wt.reshape(Cin, Cout, 16).transpose(0, 1).contiguous()
+    wks, inv = ops.fp16_prescale(wk)
+    got = ops.deconv_hw_tc2(x.cuda(), ops.pack_deconv_hw_tc2(wks, 4, True).cuda(), b.cuda(), Cout, None, half=2, oscale=inv.cuda())
+    wtr = (wks.half().double() * inv.double().view(-1, 1, 1)).transpose(0, 1).reshape(Cin, Cout, 4, 4)
+    close(got, F.conv_transpose2d(xr, wtr, b.double(), 2, 1).float(), 2e-5, rtol=1e-5, what="single-term deconv vs rounded-operand reference")

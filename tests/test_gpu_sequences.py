@@ -63,37 +63,52 @@ def _dilate(m, r):
     return F.max_pool2d(m.float().unsqueeze(1), 2 * r + 1, 1, r).squeeze(1) > 0
 
 
-def sort_tie_masks(ref_samples, has_memory, tol=1e-4):
-    """Where the reference's candidate SORT is decided by less than `tol`.
+def sort_tie_masks(ref_samples, state, tol=2e-5):
+    """Where the reference's candidate SORT is decided by less than `tol` between a memory plane and a regular plane.
 
     merge_memory concatenates the level's candidates with the two memory samples and sorts them (coarse.py:100-104,
     fine.py:118-122); the volume planes follow the permutation.  A memory plane (past_conv of a stored cost) and a regular
-    plane have unrelated contents, so when a memory sample lands within rounding of another candidate the order of two
-    DIFFERENT planes hangs on the last bits of the previous level's disparity — a discontinuity of the reference algorithm
-    (the fp64 oracle flips there against the fp32 one as well), not something a kernel can match.  Returns per-level keep
-    masks (precise, fine, coarse, full) that exclude those pixels and the receptive field they feed (pool5 / 3x3 convs:
-    radius 6 at the level, doubled by each up-sampling)."""
+    plane have unrelated contents, so when a memory sample lands within rounding of another candidate (the engine's
+    up-sampled coarse disparity differs from the oracle's by ~4e-6 px) the order of two DIFFERENT planes hangs on the last
+    bits of the previous level's output — a discontinuity of the reference algorithm (the fp64 oracle flips there against
+    the fp32 one as well), not something a kernel can match.  Returns keep masks (precise, fine, coarse, full) that
+    exclude those pixels and the receptive field they feed (pool5 + two 3x3 convs + convex up-sampling: radius 6 at the
+    level, carried through each x2 up-sampling; the precise hourglass adds its own)."""
     s_p, s_f, s_c = ref_samples
+    B, _, Hc, Wc = s_c.shape
+    memory = state.get("cost_memory") if state.get("use_past_cost", False) else None
 
-    def near(s):
-        d = s[:, 1:] - s[:, :-1]                     # sorted ascending
-        t = d < tol
-        if not has_memory:                           # the two zero samples of single-frame mode tie EXACTLY on both sides
-            t &= d > 0
-        return t.any(1)
-    tie_c = _dilate(near(s_c), 6)
+    def ties(sorted_s, ms):
+        """ms [B,2,h,w]: a memory sample within tol of a candidate that is not (one of) the memory samples themselves"""
+        t = torch.zeros(sorted_s.shape[0], *sorted_s.shape[-2:], dtype=torch.bool)
+        for k in range(ms.shape[1]):
+            v = ms[:, k:k + 1]
+            near_all = ((sorted_s - v).abs() < tol).sum(1)
+            near_mem = ((ms - v).abs() < tol).sum(1)
+            t |= near_all > near_mem
+        return t
+    if memory is None:
+        ms_f = torch.zeros(B, 2, *s_f.shape[-2:])
+        tie_c = torch.zeros(B, Hc, Wc, dtype=torch.bool)          # zeros against the integer candidate 0: exact on both sides
+    else:
+        ms_f = memory["disp_sample"]
+        ms_c = F.interpolate(ms_f * Wc / ms_f.shape[-1], size=(Hc, Wc), mode="bilinear", align_corners=True)
+        tie_c = ties(s_c, ms_c)
+    tie_c = _dilate(tie_c, 6)
     up = lambda m: F.interpolate(m.float().unsqueeze(1), scale_factor=2, mode="nearest").squeeze(1) > 0
-    tie_f = _dilate(near(s_f) | _dilate(up(tie_c), 2), 6)
-    tie_p = _dilate(up(tie_f), 6)
+    tie_f = _dilate(ties(s_f, ms_f) | _dilate(up(tie_c), 2), 6)
+    tie_p = _dilate(up(tie_f), 12)
     tie_full = _dilate(F.interpolate(tie_p.float().unsqueeze(1), scale_factor=4, mode="nearest").squeeze(1) > 0, 4)
     return ~tie_p, ~tie_f, ~tie_c, ~tie_full
 
 
-def check_frame(out, want, what, has_memory, strict=False):
-    """strict: nothing excluded (used when the levels run on the oracle's candidates: the sorts cannot flip)."""
+def check_frame(out, want, what, state, strict=False):
+    """`state`: the recurrent state the frame was computed from.  strict: nothing excluded (used when the levels run on
+    the oracle's candidates: the sorts cannot flip)."""
     disps, costs, samples, offs = out[:4]
     rd, rc, rs, ro = want[:4]
-    keep_p, keep_f, keep_c, keep_full = sort_tie_masks(rs, has_memory, tol=-1.0 if strict else 1e-4)
+    has_memory = state.get("cost_memory") is not None and state.get("use_past_cost", False)
+    keep_p, keep_f, keep_c, keep_full = sort_tie_masks(rs, state, tol=-1.0 if strict else 2e-5)
     keeps = [keep_p, keep_f, keep_c]
     dkeep = [keep_full, keep_p, keep_p, keep_f]          # disps: full, precise (1/4), fine up-sampled (1/4), coarse up-sampled (1/8)
     excluded = 1.0 - keep_full.float().mean().item()
@@ -168,6 +183,7 @@ def _sequence(H, W, B, num_sample, T, seed0=40, engine_chain=True):
                 d = (got.cpu() - want_).abs()
                 assert d.median() < 1e-5 and (d > 1e-3).float().mean() < 0.01, (t, d.median().item())
             dev_in = _cuda(_copy(ref_state))
+        ref_in = _copy(ref_state)                                   # the state this frame is computed from (read-only copy)
         with torch.no_grad():
             want = O.aggregation_forward(sd, lf, rf, li, ri, _copy(ref_state), num_sample=num_sample)
         # (1) level by level on bit-identical candidates: the engine's fine / precise levels are centred on the ORACLE's
@@ -177,12 +193,12 @@ def _sequence(H, W, B, num_sample, T, seed0=40, engine_chain=True):
             forced = eng(dl, dr, dli, dri, _cuda(_copy(ref_state)))
         finally:
             eng._inject = None
-        check_frame(forced, want, f"A {H}x{W} D={16 * num_sample} B={B} frame {t} (levels on the oracle's candidates)", t > 0, strict=True)
+        check_frame(forced, want, f"A {H}x{W} D={16 * num_sample} B={B} frame {t} (levels on the oracle's candidates)", ref_in, strict=True)
         # (2) end to end, each level centred on the engine's own previous level
         out = eng(dl, dr, dli, dri, dev_in)
         n_fine = (min(t, 3) if t else 0) + 5 + 2
         assert out[2][1].shape[1] == n_fine == want[2][1].shape[1], "fine candidates: local map + 5 range + 2 memory"
-        check_frame(out, want, f"A {H}x{W} D={16 * num_sample} B={B} frame {t} (end to end)", t > 0)
+        check_frame(out, want, f"A {H}x{W} D={16 * num_sample} B={B} frame {t} (end to end)", ref_in)
         ref_state = want[5]
         # ---- chain B
         if engine_chain:
@@ -192,8 +208,8 @@ def _sequence(H, W, B, num_sample, T, seed0=40, engine_chain=True):
             own = eng(dl, dr, dli, dri, own_state)
             own_state = own[5]
             with torch.no_grad():
-                want_b = O.aggregation_forward(sd, lf, rf, li, ri, snapshot, num_sample=num_sample)
-            check_frame(own, want_b, f"B {H}x{W} D={16 * num_sample} B={B} frame {t} (engine-carried state)", t > 0)
+                want_b = O.aggregation_forward(sd, lf, rf, li, ri, _copy(snapshot), num_sample=num_sample)
+            check_frame(own, want_b, f"B {H}x{W} D={16 * num_sample} B={B} frame {t} (engine-carried state)", snapshot)
             d = (own[0][0].cpu() - want[0][0]).abs()
             print(f"  chains A/B apart at frame {t}: median {d.median().item():.2e} px, > 0.01 px: {100 * (d > 1e-2).float().mean().item():.2f} %")
 
