@@ -5,6 +5,8 @@ previous disparity, is taken over the LOCAL batch by the reference as well —
 projects/TemporalStereo/TemporalStereo.py:364, 380, 418), so sequences are independent units: each rank
 owns a contiguous slice of the batch and its own recurrent `prev_info`; there is no data-path collective.
 `torch.distributed` is used for the rendezvous, barriers and the max-over-ranks reduction of the timing only.
+The engine is inference-only, so the training collective of SURVEY.md §8e (one flat gradient all-reduce) has no
+producer here and is not shipped.
 The time axis is a sequential recurrence and is never sharded.
 """
 from __future__ import annotations
@@ -94,41 +96,3 @@ def aggregate_throughput(units_this_rank: int, ms_this_rank: float, dist=None, d
     ms = max_over_ranks(ms_this_rank, dist, device)
     units = int(round(sum_over_ranks(units_this_rank, dist, device)))
     return units / (ms * 1e-3), ms, units
-
-
-class GradAllReducer:
-    """The one collective of a data-parallel training step: every gradient is packed into ONE flat
-    fp32 buffer, all-reduced once (sum, then / world) and scattered back.  Parameters that received no gradient
-    (the reference's `fine.phi`, fine.py:33) are skipped on every rank alike — ranks must agree on which parameters
-    have gradients, as with DistributedDataParallel without unused-parameter detection.  BatchNorm statistics stay
-    local to a rank (no SyncBN collective; a documented deviation from the reference default, config.py:76).
-
-    The aggregation engine of this repository is inference-only; the reducer is for the trainable modules around it
-    (backbone, losses) when sequences are sharded on the batch axis.
-    """
-
-    def __init__(self, params, dist=None):
-        self.params = [p for p in params]
-        self.dist = dist
-        self._flat = None
-
-    def __call__(self) -> int:
-        """All-reduce the gradients in place; returns the number of elements sent (0 without a process group)."""
-        grads = [p.grad for p in self.params if p.grad is not None]
-        if not grads or self.dist is None or not self.dist.is_initialized() or self.dist.get_world_size() == 1:
-            return 0
-        n = sum(g.numel() for g in grads)
-        dev = grads[0].device
-        if self._flat is None or self._flat.numel() != n or self._flat.device != dev:
-            self._flat = torch.empty(n, dtype=torch.float32, device=dev)
-        o = 0
-        for g in grads:
-            self._flat[o:o + g.numel()].copy_(g.reshape(-1))
-            o += g.numel()
-        self.dist.all_reduce(self._flat, op=self.dist.ReduceOp.SUM)         # the single collective
-        self._flat.div_(self.dist.get_world_size())
-        o = 0
-        for g in grads:
-            g.copy_(self._flat[o:o + g.numel()].view_as(g))
-            o += g.numel()
-        return n

@@ -77,54 +77,6 @@ def _worker(rank, world, port, total, out):
         dist.destroy_process_group()
 
 
-def _grad_worker(rank, world, port, out):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
-                      LOCAL_RANK=str(rank))
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    try:
-        torch.manual_seed(0)                                     # same weights on every rank
-        net = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3, padding=1), torch.nn.ReLU(), torch.nn.Conv2d(4, 1, 1))
-        phi = torch.nn.Parameter(torch.zeros(1))                 # a parameter that never gets a gradient (fine.phi)
-        g = torch.Generator().manual_seed(1)
-        x = torch.randn(4, 3, 8, 8, generator=g)
-        y = torch.randn(4, 1, 8, 8, generator=g)
-        # reference: the whole batch on one process
-        ref = [p.detach().clone() for p in net.parameters()]
-        loss = torch.nn.functional.mse_loss(net(x), y)
-        want = torch.autograd.grad(loss, list(net.parameters()))
-        for p, r in zip(net.parameters(), ref):
-            assert torch.equal(p, r)
-        # sharded: each rank its slice of the batch, then ONE all-reduce of the flat gradient buffer
-        xs, ys = shard.shard_batch([x, y], world, rank)
-        torch.nn.functional.mse_loss(net(xs), ys).backward()
-        calls = []
-        orig = dist.all_reduce
-        dist.all_reduce = lambda *a, **k: (calls.append(1), orig(*a, **k))[1]
-        n = shard.GradAllReducer(list(net.parameters()) + [phi], dist)()
-        dist.all_reduce = orig
-        assert len(calls) == 1, "exactly one collective per step"
-        assert n == sum(p.numel() for p in net.parameters()) and phi.grad is None
-        for p, w in zip(net.parameters(), want):                 # equal shards: mean of shard means == full-batch mean
-            assert torch.allclose(p.grad, w, atol=1e-6), (p.grad - w).abs().max()
-        if rank == 0:
-            out.put("ok")
-    finally:
-        dist.destroy_process_group()
-
-
-def test_single_gradient_allreduce_gloo():
-    world, port = 2, _free_port()
-    ctx = mp.get_context("spawn")
-    out = ctx.Queue()
-    procs = [ctx.Process(target=_grad_worker, args=(r, world, port, out)) for r in range(world)]
-    for p in procs:
-        p.start()
-    for p in procs:
-        p.join(timeout=120)
-    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
-    assert out.get(timeout=5) == "ok"
-
-
 @pytest.mark.parametrize("total", [5, 16])
 def test_two_rank_gloo_sharding(total):
     world, port = 2, _free_port()
