@@ -97,7 +97,7 @@ def sort_tie_masks(ref_samples, state, tol=1e-4):
     tie_c = _dilate(tie_c, 6)
     up = lambda m: F.interpolate(m.float().unsqueeze(1), scale_factor=2, mode="nearest").squeeze(1) > 0
     tie_f = _dilate(ties(s_f, ms_f) | _dilate(up(tie_c), 2), 6)
-    tie_p = _dilate(up(tie_f), 12)
+    tie_p = _dilate(up(tie_f), 40)            # + the precise hourglass (two stride-2 stages) and the dilated convs
     tie_full = _dilate(F.interpolate(tie_p.float().unsqueeze(1), scale_factor=4, mode="nearest").squeeze(1) > 0, 4)
     return ~tie_p, ~tie_f, ~tie_c, ~tie_full
 
@@ -112,12 +112,12 @@ def check_frame(out, want, what, state, strict=False):
     keeps = [keep_p, keep_f, keep_c]
     dkeep = [keep_full, keep_p, keep_p, keep_f]          # disps: full, precise (1/4), fine up-sampled (1/4), coarse up-sampled (1/8)
     excluded = 1.0 - keep_full.float().mean().item()
-    epes = [((a.cpu() - b).abs()[:, 0][k]).mean().item() for a, b, k in zip(disps, rd, dkeep)]
+    epes = [((a.cpu() - b).abs()[:, 0][k]).mean().item() if k.any() else 0.0 for a, b, k in zip(disps, rd, dkeep)]
     rep, bad_total = [], 0
     for i, lvl in enumerate(("precise", "fine", "coarse")):
         bad, raw, n = top2_mismatches(costs[i], rc[i], keeps[i])
         bad_total += bad
-        dc = (costs[i].cpu() - rc[i]).abs().amax(1)[keeps[i]].max().item()
+        dc = (costs[i].cpu() - rc[i]).abs().amax(1)[keeps[i]].max().item() if keeps[i].any() else 0.0
         rep.append(f"{lvl} {bad}/{raw}/{n} (max |dcost| {dc:.1e})")
         assert dc < 2e-3, f"{what}: {lvl} costs differ by {dc:.2e} away from any sort tie"
     print(what, "EPE full/precise/fine/coarse", " ".join(f"{e:.2e}" for e in epes),
@@ -205,11 +205,18 @@ def _sequence(H, W, B, num_sample, T, seed0=40, engine_chain=True):
             if t:
                 own_state = temporal.update_map(own_state, *dpose, H, W, True, 3)
             snapshot = _cpu(_copy(own_state))                     # the state the engine aggregates from, for the oracle
-            own = eng(dl, dr, dli, dri, own_state)
-            own_state = own[5]
             with torch.no_grad():
                 want_b = O.aggregation_forward(sd, lf, rf, li, ri, _copy(snapshot), num_sample=num_sample)
-            check_frame(own, want_b, f"B {H}x{W} D={16 * num_sample} B={B} frame {t} (engine-carried state)", snapshot)
+            eng._inject = {"coarse_disp": want_b[0][3].cuda(), "fine_disp": want_b[0][2].cuda()}
+            try:
+                forced = eng(dl, dr, dli, dri, _cuda(_copy(snapshot)))
+            finally:
+                eng._inject = None
+            check_frame(forced, want_b, f"B {H}x{W} D={16 * num_sample} B={B} frame {t} (engine-carried state, levels on the oracle's candidates)",
+                        snapshot, strict=True)
+            own = eng(dl, dr, dli, dri, own_state)                # the natural run: this is what is carried forward
+            own_state = own[5]
+            check_frame(own, want_b, f"B {H}x{W} D={16 * num_sample} B={B} frame {t} (engine-carried state, end to end)", snapshot)
             d = (own[0][0].cpu() - want[0][0]).abs()
             print(f"  chains A/B apart at frame {t}: median {d.median().item():.2e} px, > 0.01 px: {100 * (d > 1e-2).float().mean().item():.2f} %")
 
