@@ -367,9 +367,11 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
             }
         }
         float v[RPW][8];
+        unsigned v_ok = 0xffffffffu;    // bit u: row u of the chunk held in v is real data (else: zero it when it is packed)
         int l_phase = 0, l_kc = 0;  // load cursor: input phase and chunk inside the phase
         auto load_chunk = [&]() {
             if constexpr (FUSE != 0) {
+                v_ok = 0xffffffffu;
                 if (l_kc < p.wchunks) {          // 8 channels of the feature half, rebuilt from the feature maps
                     const float* rs = p.in + (long long)b * p.isB + (long long)(l_kc * 8) * p.isC;
                     [[maybe_unused]] const float* ls = p.left + (long long)b * p.isB + (long long)(l_kc * 8) * p.isC;
@@ -426,14 +428,38 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
                 col_ok = !(pc && edge < 0);
             }
             const int nvalid = p.Cin - l_kc * 8;                 // channels of this chunk that exist (>= 8: all)
+            if (nvalid >= 8) {
+                // Full chunk (warp-uniform branch): unconditional loads at 32-bit offsets from the chunk's base — a padding
+                // position reads element 0 of the plane instead — and a per-row validity bit that zeroes the PACKED operand
+                // at conversion time.  The predicated zero-fill form below costs ~9 instructions per load (64-bit index
+                // increment, LEA pair, ISETP, two R2UR to re-materialise the descriptor under the predicate, a zero MOV:
+                // ncu r02 source view, issue slots 57 %); this one ~3.  The zeroing must not touch v here: writing a load's
+                // destination register would wait for the load and serialise the prefetch.
+                v_ok = 0u;
+                // the chunk's base as an opaque 64-bit register: one IMAD.WIDE.U32 (base + 4 * offset) per load; left to
+                // itself ptxas keeps the base as a uniform element index and spends IADD3 + IMAD.X + LEA + LEA.HI.X on each
+                unsigned long long srcv;
+                asm("mov.u64 %0, %1;" : "=l"(srcv) : "l"(src));
+                const float* sv = reinterpret_cast<const float*>(srcv);
 #pragma unroll
-            for (int u = 0; u < RPW; ++u) {
-                const float* su = src + off[u];
-                const bool ok = off[u] >= 0 && col_ok && !(pr && ((edge >> u) & 1));
+                for (int u = 0; u < RPW; ++u) {
+                    const bool ok = off[u] >= 0 && col_ok && !(pr && ((edge >> u) & 1));
+                    const unsigned o = ok ? (unsigned)off[u] : 0u;
+                    v_ok |= (ok ? 1u : 0u) << u;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    v[u][c] = (ok && c < nvalid) ? __ldg(su) : 0.f;
-                    su += p.isC;
+                    for (int c = 0; c < 8; ++c) v[u][c] = __ldg(sv + (o + (unsigned)(c * p.isC)));
+                }
+            } else {
+                v_ok = 0xffffffffu;
+#pragma unroll
+                for (int u = 0; u < RPW; ++u) {
+                    const float* su = src + off[u];
+                    const bool ok = off[u] >= 0 && col_ok && !(pr && ((edge >> u) & 1));
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        v[u][c] = (ok && c < nvalid) ? __ldg(su) : 0.f;
+                        su += p.isC;
+                    }
                 }
             }
             if (++l_kc == p.cpp) {
@@ -563,11 +589,13 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
                 for (int u = 0; u < RPW; ++u) {
                     const int r = warp + 8 * u;
                     if (r < SR) {
+                        const bool live = (TMA || CPA) ? true : ((v_ok >> u) & 1u) != 0u;
                         uint32_t hi[4];
 #pragma unroll
                         for (int c = 0; c < 4; ++c) hi[c] = pack_h2(val(u, r, 2 * c), val(u, r, 2 * c + 1));
                         const uint32_t o = (uint32_t)(r * 32 + lane) * 16u;
-                        sts128(a_hi + ko + o, hi[0], hi[1], hi[2], hi[3]);
+                        if (live) sts128(a_hi + ko + o, hi[0], hi[1], hi[2], hi[3]);
+                        else sts128(a_hi + ko + o, 0u, 0u, 0u, 0u);
                         if (p.terms == 3) {                             // uniform: the single-term form needs no lo half
                             uint32_t lo[4];
 #pragma unroll
@@ -575,7 +603,8 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
                                 const float2 hf = unpack_h2(hi[c]);
                                 lo[c] = pack_h2(val(u, r, 2 * c) - hf.x, val(u, r, 2 * c + 1) - hf.y);
                             }
-                            sts128(a_lo + ko + o, lo[0], lo[1], lo[2], lo[3]);
+                            if (live) sts128(a_lo + ko + o, lo[0], lo[1], lo[2], lo[3]);
+                            else sts128(a_lo + ko + o, 0u, 0u, 0u, 0u);
                         }
                         if (!(k & 1) && k == p.nchunk - 1) {            // odd number of units: the last K half is zero
                             sts128(a_hi + khalf + o, 0u, 0u, 0u, 0u);
@@ -596,6 +625,10 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
                             // exact remainder; the tensor core ignores the 13 low mantissa bits of a tf32 operand,
                             // so not rounding lo costs <= 2^-22 relative
                             lo[c] = __float_as_uint(x - __uint_as_float(hi[c]));
+                        }
+                        if (!(TMA || CPA) && !((v_ok >> u) & 1u)) {
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) hi[c] = lo[c] = 0u;
                         }
                         const uint32_t o = (uint32_t)(r * 32 + lane) * 16u;
                         sts128(a_hi + o, hi[0], hi[1], hi[2], hi[3]);
