@@ -56,6 +56,7 @@
 #include <cuda.h>
 #include <cstdint>
 #include <cstdlib>
+#include <type_traits>
 
 namespace tstereo {
 namespace tc2 {
@@ -366,12 +367,20 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
                 }
             }
         }
-        float v[RPW][8];
-        unsigned v_ok = 0xffffffffu;    // bit u: row u of the chunk held in v is real data (else: zero it when it is packed)
+        // NB = 2 (DIRECT register-producer instances: 80-91 registers, room under the 112 of two CTAs per SM): the loads of
+        // unit k+1 are issued BEFORE unit k is converted, into the other register buffer — with one buffer a unit's loads
+        // could only be issued after the previous unit's conversion and each unit paid a full memory latency, hidden by
+        // nothing but the other warps (ncu r02: 21 % of the stall samples on the first F2FP after the loads).
+        constexpr int NB = (DIRECT && RAW == 0 && FUSE == 0) ? 2 : 1;
+        float v[NB][RPW][8];
+        unsigned v_ok[NB];              // bit u: row u of the unit held in v[.] is real data (else: zero it when it is packed)
+#pragma unroll
+        for (int i = 0; i < NB; ++i) v_ok[i] = 0xffffffffu;
         int l_phase = 0, l_kc = 0;  // load cursor: input phase and chunk inside the phase
-        auto load_chunk = [&]() {
+        auto load_chunk = [&](auto BUFC) {
+            constexpr int BUF = decltype(BUFC)::value;
             if constexpr (FUSE != 0) {
-                v_ok = 0xffffffffu;
+                v_ok[BUF] = 0xffffffffu;
                 if (l_kc < p.wchunks) {          // 8 channels of the feature half, rebuilt from the feature maps
                     const float* rs = p.in + (long long)b * p.isB + (long long)(l_kc * 8) * p.isC;
                     [[maybe_unused]] const float* ls = p.left + (long long)b * p.isB + (long long)(l_kc * 8) * p.isC;
@@ -382,11 +391,11 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
                             if constexpr (FUSE == 1) {
                                 const float ra = __ldg(rs + (long long)c * p.isC + woff[u]);
                                 const float rb = __ldg(rs + (long long)c * p.isC + woff[u] + 1);
-                                v[u][c] = fmaf(rb, wb[u], __fmul_rn(ra, wa[u]));
+                                v[BUF][u][c] = fmaf(rb, wb[u], __fmul_rn(ra, wa[u]));
                             } else {
                                 const float l = off[u] >= 0 ? __ldg(ls + (long long)c * p.isC + off[u]) : 0.f;
                                 const float e = l - __fmul_rn(__ldg(rs + (long long)c * p.isC + woff[u]), wa[u]);
-                                v[u][c] = -(e * e);
+                                v[BUF][u][c] = -(e * e);
                             }
                         }
                     }
@@ -400,7 +409,7 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
                         const bool ok = off[u] >= 0;
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
-                            v[u][c] = (ok && c < nvalid) ? __ldg(su) : 0.f;
+                            v[BUF][u][c] = (ok && c < nvalid) ? __ldg(su) : 0.f;
                             su += p.i2sC;
                         }
                     }
@@ -435,7 +444,7 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
                 // increment, LEA pair, ISETP, two R2UR to re-materialise the descriptor under the predicate, a zero MOV:
                 // ncu r02 source view, issue slots 57 %); this one ~3.  The zeroing must not touch v here: writing a load's
                 // destination register would wait for the load and serialise the prefetch.
-                v_ok = 0u;
+                v_ok[BUF] = 0u;
                 // the chunk's base as an opaque 64-bit register: one IMAD.WIDE.U32 (base + 4 * offset) per load; left to
                 // itself ptxas keeps the base as a uniform element index and spends IADD3 + IMAD.X + LEA + LEA.HI.X on each
                 unsigned long long srcv;
@@ -445,19 +454,19 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
                 for (int u = 0; u < RPW; ++u) {
                     const bool ok = off[u] >= 0 && col_ok && !(pr && ((edge >> u) & 1));
                     const unsigned o = ok ? (unsigned)off[u] : 0u;
-                    v_ok |= (ok ? 1u : 0u) << u;
+                    v_ok[BUF] |= (ok ? 1u : 0u) << u;
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) v[u][c] = __ldg(sv + (o + (unsigned)(c * p.isC)));
+                    for (int c = 0; c < 8; ++c) v[BUF][u][c] = __ldg(sv + (o + (unsigned)(c * p.isC)));
                 }
             } else {
-                v_ok = 0xffffffffu;
+                v_ok[BUF] = 0xffffffffu;
 #pragma unroll
                 for (int u = 0; u < RPW; ++u) {
                     const float* su = src + off[u];
                     const bool ok = off[u] >= 0 && col_ok && !(pr && ((edge >> u) & 1));
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
-                        v[u][c] = (ok && c < nvalid) ? __ldg(su) : 0.f;
+                        v[BUF][u][c] = (ok && c < nvalid) ? __ldg(su) : 0.f;
                         su += p.isC;
                     }
                 }
@@ -550,11 +559,15 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
         if constexpr (CPA) {
             for (int i = 0; i < p.rs && i < p.nchunk; ++i) issue_cpa();
         } else if constexpr (!TMA) {
-            load_chunk();
+            load_chunk(std::integral_constant<int, 0>{});
         }
         int s = 0, gk = 0, gdone = 0;      // stage of chunk k; chunks produced since the last group boundary; groups drained
         uint32_t ph = 0;
-        for (int k = 0; k < p.nchunk; ++k) {
+        auto step = [&](int k, auto BUFC) {
+            constexpr int BUF = decltype(BUFC)::value;
+            if constexpr (NB == 2) {        // unit k+1 goes in flight now, into the other buffer (whose unit k-1 is already packed)
+                if (k + 1 < p.nchunk) load_chunk(std::integral_constant<int, 1 - BUF>{});
+            }
             // F16: two 8-channel units (K halves) make one MMA chunk / shared-memory stage
             const bool first_half = !F16 || !(k & 1);
             const bool last_half = !F16 || (k & 1) || k == p.nchunk - 1;
@@ -581,7 +594,7 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
             }
             auto val = [&](int u, int r, int c) -> float {
                 if constexpr (TMA || CPA) return raw[(c * SR + r) * rbw];
-                else return v[u][c];
+                else return v[BUF][u][c];
             };
             if constexpr (F16) {
                 const uint32_t ko = (uint32_t)(k & 1) * khalf;         // K half of this unit inside the chunk
@@ -589,7 +602,7 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
                 for (int u = 0; u < RPW; ++u) {
                     const int r = warp + 8 * u;
                     if (r < SR) {
-                        const bool live = (TMA || CPA) ? true : ((v_ok >> u) & 1u) != 0u;
+                        const bool live = (TMA || CPA) ? true : ((v_ok[BUF] >> u) & 1u) != 0u;
                         uint32_t hi[4];
 #pragma unroll
                         for (int c = 0; c < 4; ++c) hi[c] = pack_h2(val(u, r, 2 * c), val(u, r, 2 * c + 1));
@@ -626,7 +639,7 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
                             // so not rounding lo costs <= 2^-22 relative
                             lo[c] = __float_as_uint(x - __uint_as_float(hi[c]));
                         }
-                        if (!(TMA || CPA) && !((v_ok >> u) & 1u)) {
+                        if (!(TMA || CPA) && !((v_ok[BUF] >> u) & 1u)) {
 #pragma unroll
                             for (int c = 0; c < 8; ++c) hi[c] = lo[c] = 0u;
                         }
@@ -644,8 +657,8 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
                 __syncwarp();
             } else if constexpr (CPA) {
                 if (c_issue < p.nchunk) issue_cpa();    // refill the stage this thread just read
-            } else {
-                if (k + 1 < p.nchunk) load_chunk();     // in flight across the barrier traffic and the drain below
+            } else if constexpr (NB == 1) {
+                if (k + 1 < p.nchunk) load_chunk(std::integral_constant<int, 0>{});   // in flight across the barrier traffic and the drain below
             }
             if (last_half) {
                 fence_proxy_async();                   // generic-proxy st.shared -> visible to the tensor core
@@ -663,6 +676,14 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
                     ++gk;
                 }
             }
+        };
+        if constexpr (NB == 2) {
+            for (int k = 0; k < p.nchunk; k += 2) {
+                step(k, std::integral_constant<int, 0>{});
+                if (k + 1 < p.nchunk) step(k + 1, std::integral_constant<int, 1>{});
+            }
+        } else {
+            for (int k = 0; k < p.nchunk; ++k) step(k, std::integral_constant<int, 0>{});
         }
         if constexpr (!DIRECT) drain(ngroups - 1);
 
