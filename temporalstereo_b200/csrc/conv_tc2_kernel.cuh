@@ -84,6 +84,8 @@ struct Params {
     int osY, osX;                 // output row pitch / x step (W, 1 | 2*W.., 2 for one phase of a transposed conv)
     int cpp;                      // chunks per input phase = ceil(Cin / 8); nchunk = phases * cpp
     int dil, act, nchunk, G, stages, tiles_x;
+    int tiles_y, nplanes;         // tiles along y; B * D planes: a launch covers tiles_x * tiles_y * nplanes tiles
+    int persist;                  // MULTI instances: grid.x CTAs walk the tiles with stride grid.x (0: one tile per CTA)
     int rs;                       // TMA variant: raw fp32 stages in flight
     int bw;                       // TMA variant: box width in elements (32, or 36 when the halo shifts the 16-byte aligned origin)
     int nbatch;                   // batch size (extent of the TMA view's last dimension)
@@ -264,11 +266,26 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
     const uint32_t raw_bytes = 32u * (uint32_t)p.bw * (uint32_t)SR;   // p.bw = 32 for the cp.async ring
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int plane = blockIdx.y;
-    const int b = plane / p.D, d = plane - b * p.D;
-    const int ty = blockIdx.x / p.tiles_x, tx = blockIdx.x - ty * p.tiles_x;
     const int VW = 32 - 2 * p.dil;                     // valid output columns of a tile
-    const int y0 = ty * 4 * MT, x0 = tx * VW;
+    // MULTI (DIRECT register-producer instances): a CTA walks tiles t0, t0 + grid.x, ... — barriers, TMEM and the
+    // operand ring are set up once, the first loads of tile t+1 are in flight while tile t's epilogue runs.  Every other
+    // instance keeps one tile per CTA (grid = tiles of a plane x planes).
+    constexpr bool MULTI = DIRECT && RAW == 0 && FUSE == 0;
+    const int tiles_pp = p.tiles_x * p.tiles_y;
+    const int T = tiles_pp * p.nplanes;                // < 2^31 (checked by the host)
+    const int t_first = MULTI ? (int)blockIdx.x : (int)blockIdx.y * tiles_pp + (int)blockIdx.x;
+    const int t_stride = MULTI ? (int)gridDim.x : T;
+    int b, d, y0, x0;
+    auto set_tile = [&](int t) {
+        const int plane = t / tiles_pp;
+        const int rem = t - plane * tiles_pp;
+        const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+        b = plane / p.D;
+        d = plane - b * p.D;
+        y0 = ty * 4 * MT;
+        x0 = tx * VW;
+    };
+    set_tile(t_first);
 
     if (tid == 0) {
         for (int s = 0; s < p.stages; ++s) {
@@ -329,11 +346,16 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
         // ===================== producers / accumulator readers =====================
         const int quarter = warp & 3;                 // TMEM lane quarter = tile row inside an M-tile
         const int half = warp >> 2;                   // which M-tiles this warp drains
-        const float* in_pl = p.in + (long long)b * p.isB + (p.kd ? 0ll : (long long)d * p.isD);
+        const float* in_pl;
         // the staged rows of this warp: r = warp + 8*u; lane = staged column
         int off[RPW];               // element offset of (row, lane) in phase (0,0), or -1
-        int edge = 0;               // bit u: row r's odd-row phase lies below the input; bit 31: same for the column
-        {
+        int edge;                   // bit u: row r's odd-row phase lies below the input; bit 31: same for the column
+        int l_phase, l_kc;          // load cursor: input phase and chunk inside the phase
+        auto setup_tile = [&]() {   // per-tile producer state from (b, d, y0, x0)
+            in_pl = p.in + (long long)b * p.isB + (p.kd ? 0ll : (long long)d * p.isD);
+            edge = 0;
+            l_phase = 0;
+            l_kc = 0;
             const int gx = x0 - p.dil + lane;
             if (p.isX * gx + 1 >= p.Win) edge |= 1 << 31;
 #pragma unroll
@@ -343,7 +365,8 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
                 off[u] = (r < SR && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) ? gy * p.isY + gx * p.isX : -1;
                 if (p.isX * gy + 1 >= p.Hin) edge |= 1 << u;
             }
-        }
+        };
+        setup_tile();
         // fused cost producer: per staged position the right-feature tap (offset inside a channel plane, two weights)
         int woff[FUSE ? RPW : 1];
         float wa[FUSE ? RPW : 1], wb[FUSE == 1 ? RPW : 1];
@@ -371,12 +394,11 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
         // unit k+1 are issued BEFORE unit k is converted, into the other register buffer — with one buffer a unit's loads
         // could only be issued after the previous unit's conversion and each unit paid a full memory latency, hidden by
         // nothing but the other warps (ncu r02: 21 % of the stall samples on the first F2FP after the loads).
-        constexpr int NB = (DIRECT && RAW == 0 && FUSE == 0) ? 2 : 1;
+        constexpr int NB = (DIRECT && RAW == 0 && FUSE == 0 && RPW <= 2) ? 2 : 1;   // RPW = 3 (MT = 4): no room for 24 more registers
         float v[NB][RPW][8];
         unsigned v_ok[NB];              // bit u: row u of the unit held in v[.] is real data (else: zero it when it is packed)
 #pragma unroll
         for (int i = 0; i < NB; ++i) v_ok[i] = 0xffffffffu;
-        int l_phase = 0, l_kc = 0;  // load cursor: input phase and chunk inside the phase
         auto load_chunk = [&](auto BUFC) {
             constexpr int BUF = decltype(BUFC)::value;
             if constexpr (FUSE != 0) {
@@ -677,6 +699,8 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
                 }
             }
         };
+        uint32_t it = 0;                 // tiles this CTA has finished: parity of the per-tile accumulator barriers
+        for (int t = t_first; t < T; t += t_stride, ++it) {
         if constexpr (NB == 2) {
             for (int k = 0; k < p.nchunk; k += 2) {
                 step(k, std::integral_constant<int, 0>{});
@@ -692,21 +716,35 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
         const int x = x0 + lane;
         const bool xok = lane < VW && x < p.W;
         const int xo = x * p.osX;
+        const int ey0 = y0;
+        if constexpr (MULTI) {
+            // the next tile's first unit goes in flight before this tile's epilogue (buffer 0 is free: every unit of this
+            // tile has been packed); the epilogue below works from the coordinates saved above
+            if (t_stride < T - t) {
+                set_tile(t + t_stride);
+                setup_tile();
+                load_chunk(std::integral_constant<int, 0>{});
+            }
+        }
 #pragma unroll
         for (int jj = 0; jj < JT; ++jj) {
             const int j = half + 2 * jj;
             if (j < MT) {                                  // warp-uniform
-                const int y = y0 + 4 * j + quarter;
+                const int y = ey0 + 4 * j + quarter;
                 float* o = out_pl + (long long)y * p.osY + xo;
                 const bool ok = xok && y < p.H;
                 if constexpr (DIRECT) {
                     // one accumulation group: stream TMEM -> registers 8 channels at a time
-                    mbar_wait(&acc_full[j], 0u);
+                    mbar_wait(&acc_full[j], it & 1u);
                     tc_fence_after();
                     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(j * C::TS);
                     if (p.act == TSTEREO_ACT_SILU) epi_direct<TSTEREO_ACT_SILU, CP, FOLD>(taddr, p.dil, o, p.osC, p.bias, p.Cout, ok, p.oscale);
                     else if (p.act == TSTEREO_ACT_RELU) epi_direct<TSTEREO_ACT_RELU, CP, FOLD>(taddr, p.dil, o, p.osC, p.bias, p.Cout, ok, p.oscale);
                     else epi_direct<TSTEREO_ACT_NONE, CP, FOLD>(taddr, p.dil, o, p.osC, p.bias, p.Cout, ok, p.oscale);
+                    if constexpr (MULTI) {                 // M-tile j of the accumulator is free for the next tile's MMAs
+                        tc_fence_before();
+                        mbar_arrive(&acc_empty[j]);
+                    }
                 } else {
                     const float* ad = nullptr;
                     if constexpr (FUSE == 1)
@@ -717,6 +755,7 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
                 }
             }
         }
+        }   // tiles
         if constexpr (DIRECT) tc_fence_before();
     } else {
         // ===================== MMA issuer =====================
@@ -730,6 +769,8 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
         uint32_t ph = 0;
         if constexpr (TMA)
             for (int i = 0; i < p.rs && i < p.nchunk; ++i) issue_tma();
+        uint32_t it = 0;                 // tiles finished (MULTI): parity of acc_empty
+        for (int t = t_first; t < T; t += t_stride, ++it)
         for (int k = 0; k < nmma; ++k) {
             const bool first = DIRECT ? k == 0 : kg == 0;
             const bool last = DIRECT ? k == nmma - 1 : (kg == p.G - 1 || k == nmma - 1);
@@ -744,6 +785,10 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
             for (int j = 0; j < MT; ++j) {
                 if (!DIRECT && first && g >= 1) {
                     mbar_wait(&acc_empty[j], (uint32_t)(g - 1) & 1u);
+                    tc_fence_after();
+                }
+                if (MULTI && first && it >= 1) {          // the previous tile's epilogue has read M-tile j out of TMEM
+                    mbar_wait(&acc_empty[j], (it - 1u) & 1u);
                     tc_fence_after();
                 }
                 if (elect_one()) {
@@ -971,7 +1016,19 @@ static int launch(Params& p, int CP, int planes, cudaStream_t st, const char* wh
         return TSTEREO_E_CUDA;
     }
     const size_t smem_bytes = smem_need(p.stages, SR, N, p.rs, p.bw);   // p.bw = 32 for the cp.async ring
-    dim3 grid(p.tiles_x * ((p.H + 4 * best_mt - 1) / (4 * best_mt)), planes);
+    p.tiles_y = (p.H + 4 * best_mt - 1) / (4 * best_mt);
+    p.nplanes = planes;
+    dim3 grid(p.tiles_x * p.tiles_y, planes);
+    // MULTI instances (DIRECT, register producer): resident CTAs walk the tiles — 2 per SM (TSTEREO_TC2_PERSIST=0: one tile
+    // per CTA, the same kernel with grid.x = tiles)
+    const bool multi = FUSE == 0 && direct && !tma && !best_cpa;
+    if (multi) {
+        const long long T = (long long)grid.x * planes;
+        const long long want = (long long)148 * 2 * (env_int("TSTEREO_TC2_PERSIST", 1) > 0 ? env_int("TSTEREO_TC2_PERSIST", 1) : 1);
+        p.persist = env_int("TSTEREO_TC2_PERSIST", 1) != 0;
+        TS_REQUIRE(T < (1ll << 31), "%s: too many tiles", what);
+        grid = dim3((unsigned)((p.persist && T > want) ? want : T), 1);
+    }
     if constexpr (FUSE != 0) {
         TS_REQUIRE(fold == 3 && !direct && !tma && !best_cpa, "%s: the fused cost producer runs the 3x3 ACC register form", what);
 #define TS_TC2U(CC, MM)                                                                                        \
