@@ -142,6 +142,52 @@ int tstereo_conv_d_tc2(const float* in, long long isB, long long isC, long long 
                        int B, int Cin, int Cout, int Din, int Dout, int H, int W,
                        int k, int stride, int dilation, int transposed, int act, int half, void* stream);
 
+/* ---- S-format ("split") activations: the TMA-fed form of the tensor-core convolutions (round 2).
+ * An S-format tensor holds the fp16 hi / lo halves of an fp32 activation x (hi = fp16(x), lo = fp16(x - hi): exactly the
+ * operand split the tensor-core kernels compute from fp32 inputs), laid out [B][D][part][C8][H][W][8 channels] with
+ * C8 = ceil(C / 8) and zero padding channels, so that one K-chunk of the implicit GEMM's A operand is ONE TMA box
+ * (cp.async.bulk.tensor) from global memory straight into the K-major shared-memory stage: no producer warps, no
+ * per-consumer conversion.  The epilogue of the producing layer writes it (the split is computed once per element).
+ * Results are bit-identical to the fp32-input entry points above (same operand values, same MMA order).
+ * ref: the same reference layers as the _tc2 entry points (layers/basic_layers.py:194-235, 340-388). */
+typedef struct tstereo_split {
+    void* ptr;                   /* fp16 bit patterns */
+    long long sB, sD, sP, sC8;   /* element (fp16) strides: batch, plane, part (hi -> lo), 8-channel chunk; [H][W][8] is dense */
+    int C8;                      /* 8-channel chunks addressable from ptr */
+    int parts;                   /* 2: hi + lo;  1: hi only (inputs / outputs of the single-term form, half == 2) */
+    int nb;                      /* as an output: only batches [0, nb) are written (0: all) */
+} tstereo_split;
+
+/* fp32 [B, C, D, H, W] view (dense H*W plane) -> S-format (for activations produced by a non-convolution kernel or by
+ * the caller, e.g. the backbone features). */
+int tstereo_split_pack(const float* in, long long isB, long long isC, long long isD, const tstereo_split* sout,
+                       int B, int C, int D, int H, int W, void* stream);
+
+/* The four tensor-core convolutions with S-format operands.  Arguments as in the _tc2 forms (same packed weights), plus
+ *   sin  : S-format input, or NULL (the fp32 input `in` is converted by the kernel's producer warps);
+ *   sout : S-format output written by the epilogue, or NULL;  `out` (fp32) may be NULL when sout is given.
+ * half must be 1 or 2.  Stride-2 convolutions read the four parity phases of an S-format input through the TMA map's
+ * element strides; transposed convolutions write one output parity phase per launch into either format. */
+int tstereo_conv_hw3_s(const float* in, long long isB, long long isC, long long isD, const tstereo_split* sin,
+                       float* out, long long osB, long long osC, long long osD, const tstereo_split* sout,
+                       const float* wpack, const float* bias, const float* oscale,
+                       int B, int Cin, int Cout, int D, int H, int W,
+                       int dilation, int act, int half, void* stream);
+int tstereo_conv_hw3s2_s(const float* in, long long isB, long long isC, long long isD, const tstereo_split* sin,
+                         float* out, long long osB, long long osC, long long osD, const tstereo_split* sout,
+                         const float* wpack, const float* bias, const float* oscale,
+                         int B, int Cin, int Cout, int D, int Hin, int Win, int act, int half, void* stream);
+int tstereo_deconv_hw_s(const float* in, long long isB, long long isC, long long isD, const tstereo_split* sin,
+                        float* out, long long osB, long long osC, long long osD, const tstereo_split* sout,
+                        const float* wpack, const float* bias, const float* oscale,
+                        int B, int Cin, int Cout, int D, int Hin, int Win, int act, int half, void* stream);
+int tstereo_conv_d_s(const float* in, long long isB, long long isC, long long isD, const tstereo_split* sin,
+                     float* out, long long osB, long long osC, long long osD, const tstereo_split* sout,
+                     const float* wpack, const float* bias, const float* oscale,
+                     int B, int Cin, int Cout, int Din, int Dout, int H, int W,
+                     int k, int stride, int dilation, int transposed, int act, int half, void* stream);
+
+
 /* (k,1,1) convolution along D: k = 3|5, stride 1|2, dilation 1|2, padding = dilation*(k/2).
  * transposed != 0: ConvTranspose (3,1,1) stride 2, padding 1, output_padding 1 (Dout = 2*Din). */
 int tstereo_conv_d(const float* in, long long isB, long long isC, long long isD,

@@ -37,6 +37,11 @@ SIGNATURES = {
     "tstereo_deconv_hw_tc2": (I, [P, LL, LL, LL, P, LL, LL, LL, P, P, P, I, I, I, I, I, I, I, I, P]),
     "tstereo_conv_d_tc2_wpack_floats": (LL, [I, I, I, I]),
     "tstereo_conv_d_tc2": (I, [P, LL, LL, LL, P, LL, LL, LL, P, P, P, I, I, I, I, I, I, I, I, I, I, I, I, I, P]),
+    "tstereo_split_pack": (I, [P, LL, LL, LL, P, I, I, I, I, I, P]),
+    "tstereo_conv_hw3_s": (I, [P, LL, LL, LL, P, P, LL, LL, LL, P, P, P, P, I, I, I, I, I, I, I, I, I, P]),
+    "tstereo_conv_hw3s2_s": (I, [P, LL, LL, LL, P, P, LL, LL, LL, P, P, P, P, I, I, I, I, I, I, I, I, P]),
+    "tstereo_deconv_hw_s": (I, [P, LL, LL, LL, P, P, LL, LL, LL, P, P, P, P, I, I, I, I, I, I, I, I, P]),
+    "tstereo_conv_d_s": (I, [P, LL, LL, LL, P, P, LL, LL, LL, P, P, P, P, I, I, I, I, I, I, I, I, I, I, I, I, I, P]),
     "tstereo_conv_d": (I, [P, LL, LL, LL, P, LL, LL, LL, P, P, I, I, I, I, I, I, I, I, I, I, I, P]),
     "tstereo_deconv_hw": (I, [P, LL, LL, LL, P, LL, LL, LL, P, P, I, I, I, I, I, I, I, I, P]),
     "tstereo_copy_planes": (I, [P, P, LL, LL, I, I, I, P]),
@@ -59,6 +64,13 @@ SIGNATURES = {
     "tstereo_update_map": (I, [P, I, I, P, P, P, P, P, P, I, P, I, I, P, P, P, P, I, I, I, P]),
     "tstereo_softsplat": (I, [P, P, P, P, P, I, I, I, I, P]),
 }
+
+
+
+class SplitStruct(C.Structure):
+    """`tstereo_split` of include/tstereo.h: an S-format (fp16 hi / lo) activation."""
+    _fields_ = [("ptr", P), ("sB", LL), ("sD", LL), ("sP", LL), ("sC8", LL), ("C8", I), ("parts", I), ("nb", I)]
+
 
 _lib = None
 

@@ -119,6 +119,11 @@ class TEMPORALSTEREO(nn.Module):
         self._inject: Optional[dict] = None
         # tensor-core operand split: fp16 hi + lo (kind::f16, 16 channels per MMA; activations < 65504) or tf32 hi + lo
         self.half_split = True
+        # S-format activations between tensor-core convolutions (include/tstereo.h `tstereo_split`): the epilogue of a
+        # layer writes the fp16 hi / lo halves its consumer's MMAs need, laid out so that the consumer stages a K-chunk
+        # with one TMA box (no producer warps, no per-tile conversion).  Bit-identical results (tests/test_gpu_split.py);
+        # needs the fp16 operand split.  False: every convolution reads and writes fp32 NC(D)HW
+        self.split_format = True
         # run the UNet encoder on a side stream, concurrently with the coarse and fine levels
         self.overlap_encoder = True
         self._side: Dict[str, torch.cuda.Stream] = {}
@@ -574,20 +579,46 @@ class TEMPORALSTEREO(nn.Module):
         c2 = self._pk[r + ".conv2.1"].cout
         lrcat = torch.empty((2 * B, cf + c4, H4, W4), device=dev, dtype=torch.float32)
         lcat, rcat = lrcat[:B], lrcat[B:]
-        cat2lr = torch.empty((2 * B, 2 * c2, (H - 1) // 2 + 1, (W - 1) // 2 + 1), device=dev, dtype=torch.float32)
-        cat2 = cat2lr[:B]                 # [deconv4 output | left 1/2-scale features]; the right half's first c2 planes stay unused
-        half2 = torch.empty((2 * B, c2, (H - 1) // 2 + 1, (W - 1) // 2 + 1), device=dev, dtype=torch.float32)
+        if not (self.split_format and self.half_split and self.tensor_cores):
+            cat2lr = torch.empty((2 * B, 2 * c2, (H - 1) // 2 + 1, (W - 1) // 2 + 1), device=dev, dtype=torch.float32)
+            cat2 = cat2lr[:B]             # [deconv4 output | left 1/2-scale features]; the right half's first c2 planes stay unused
+            half2 = torch.empty((2 * B, c2, (H - 1) // 2 + 1, (W - 1) // 2 + 1), device=dev, dtype=torch.float32)
         main = torch.cuda.current_stream(dev)
         side = self._side_stream(dev) if self.overlap_encoder else main
         if side is not main:
             side.wait_stream(main)
+        sfmt = self.split_format and self.half_split and self.tensor_cores
+        single = self.decoder_single_term
+        if sfmt:        # allocated on the main stream (like lrcat): the decoder reads them there after the encoder's event
+            H2, W2 = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+            s_half2 = ops.Split(2 * B, c2, 1, H2, W2, 2, device=dev, five=False)
+            s_cat2 = ops.Split(2 * B, 2 * c2, 1, H2, W2, 2, device=dev, five=False)
+            s_q = ops.Split(2 * B, c4, 1, H4, W4, 2, device=dev, five=False)
+            s_lcat = ops.Split(B, cf + c4, 1, H4, W4, 1 if single else 2, device=dev, five=False)
         with torch.cuda.stream(side):
             ops.copy_planes(l4, lcat[:, :cf])
             ops.copy_planes(r4, rcat[:, :cf])
-            self._conv2d(left_image, r + ".conv2.0", 2, out=half2[:B])          # the two images meet in one 2B batch
-            self._conv2d(right_image, r + ".conv2.0", 2, out=half2[B:])
-            self._conv2d(half2, r + ".conv2.1", out=cat2lr[:, c2:])
-            self._conv2d(self._conv2d(cat2lr[:, c2:], r + ".conv4.0", 2), r + ".conv4.1", out=lrcat[:, cf:])
+            if sfmt:
+                # S-format chain: image -> conv2.0 -> conv2.1 -> conv4.0 -> conv4.1; only conv4.1 also writes fp32 (the
+                # 1/4-scale features of the precise cost volume).  s_cat2 = [deconv4 output | conv2.1 output] is the
+                # decoder's concat buffer, s_lcat = [left backbone features | left conv4.1 output] the input of fuse.0
+                pk = self._pk
+                k = pk[r + ".conv2.0"]
+                ops.conv_hw3s2_s(left_image, k.tc["s2"], k.b, k.cout, "ReLU", oscale=k.osc, sout=s_half2.batches(0, B))
+                ops.conv_hw3s2_s(right_image, k.tc["s2"], k.b, k.cout, "ReLU", oscale=k.osc, sout=s_half2.batches(B, 2 * B))
+                k = pk[r + ".conv2.1"]
+                ops.conv_hw3_s(s_half2, k.tc["hw3"], k.b, k.cout, 1, "ReLU", oscale=k.osc, sout=s_cat2.channels(c2, 2 * c2))
+                k = pk[r + ".conv4.0"]
+                ops.conv_hw3s2_s(s_cat2.channels(c2, 2 * c2), k.tc["s2"], k.b, k.cout, "ReLU", oscale=k.osc, sout=s_q)
+                k = pk[r + ".conv4.1"]
+                ops.conv_hw3_s(s_q, k.tc["hw3"], k.b, k.cout, 1, "ReLU", out=lrcat[:, cf:], oscale=k.osc,
+                               sout=s_lcat.channels(cf, cf + c4), nb=B)
+                ops.split_pack(l4, out=s_lcat.channels(0, cf))
+            else:
+                self._conv2d(left_image, r + ".conv2.0", 2, out=half2[:B])          # the two images meet in one 2B batch
+                self._conv2d(right_image, r + ".conv2.0", 2, out=half2[B:])
+                self._conv2d(half2, r + ".conv2.1", out=cat2lr[:, c2:])
+                self._conv2d(self._conv2d(cat2lr[:, c2:], r + ".conv4.0", 2), r + ".conv4.1", out=lrcat[:, cf:])
             enc_done = torch.cuda.Event()
             enc_done.record(side)
 
@@ -618,10 +649,30 @@ class TEMPORALSTEREO(nn.Module):
         vol = self._init3d(lcat, rcat, samples_p, "precise.init3d")
         d_p, c_p, o_p, top_disp, top_cost = self._heads_predict(vol, samples_p, "precise.pred_heads",
                                                                 float(self.levels["precise"]["delta"]), True)
-        f = self._conv2d(self._conv2d(lcat, r + ".fuse.0", single=True), r + ".fuse.1", single=True)
-        self._deconv_hw(f, self._pk[r + ".deconv4"], 4, "ReLU", out=cat2[:, :c2], single=True)
-        f = self._conv2d(cat2, r + ".concat", single=True)
-        logits = self._deconv_hw(f, self._pk[r + ".deconv2"], 4, single=True)
+        if sfmt:
+            # decoder on S-format activations (hi half only when it runs single-term MMAs); deconv2 writes the fp32 logits
+            pk = self._pk
+            h, np_ = (2, 1) if single else (1, 2)
+            cfz = pk[r + ".fuse.0"].cout
+            s_f0 = ops.Split(B, cfz, 1, H4, W4, np_, device=dev, five=False)
+            s_f1 = ops.Split(B, pk[r + ".fuse.1"].cout, 1, H4, W4, np_, device=dev, five=False)
+            s_cc = ops.Split(B, pk[r + ".concat"].cout, 1, H2, W2, np_, device=dev, five=False)
+            k = pk[r + ".fuse.0"]
+            ops.conv_hw3_s(s_lcat, k.tc["hw3"], k.b, k.cout, 1, "ReLU", half=h, oscale=k.osc, sout=s_f0)
+            k = pk[r + ".fuse.1"]
+            ops.conv_hw3_s(s_f0, k.tc["hw3"], k.b, k.cout, 1, "ReLU", half=h, oscale=k.osc, sout=s_f1)
+            k = pk[r + ".deconv4"]
+            up = s_cat2.batches(0, B).channels(0, c2)
+            ops.deconv_hw_s(s_f1, k.tc["dc"], k.b, k.cout, "ReLU", half=h, oscale=k.osc, sout=up.hi() if single else up)
+            k = pk[r + ".concat"]
+            ops.conv_hw3_s(s_cat2.batches(0, B), k.tc["hw3"], k.b, k.cout, 1, "ReLU", half=h, oscale=k.osc, sout=s_cc)
+            k = pk[r + ".deconv2"]
+            logits, _ = ops.deconv_hw_s(s_cc, k.tc["dc"], k.b, k.cout, None, half=h, oscale=k.osc)
+        else:
+            f = self._conv2d(self._conv2d(lcat, r + ".fuse.0", single=True), r + ".fuse.1", single=True)
+            self._deconv_hw(f, self._pk[r + ".deconv4"], 4, "ReLU", out=cat2[:, :c2], single=True)
+            f = self._conv2d(cat2, r + ".concat", single=True)
+            logits = self._deconv_hw(f, self._pk[r + ".deconv2"], 4, single=True)
         full = ops.unet_upsample(logits, d_p)
 
         # ---- recurrent state write-back (reference precise.py:98-103)

@@ -39,6 +39,12 @@
 //     zero-filled by the TMA unit — into a ring of raw fp32 stages which the 8 producer warps read (conflict-free
 //     LDS), split and store as the K-major operand; 2 = the same ring filled by per-thread `cp.async` (opt-in
 //     TSTEREO_TC2_CPA=1, fp16 split, any width).  DESIGN.md §5 has the measurements (both are slower than mode 0).
+//     3 = SPLIT (round 2, the fastest form): the input is an "S-format" tensor — the fp16 hi / lo halves of the fp32
+//     activation, laid out [.. part][8-channel chunk][H][W][8] by the epilogue of the layer that produced it — so a
+//     K-chunk of the A operand is one TMA box `cp.async.bulk.tensor.5d` straight into the K-major stage (zero padding by
+//     the TMA unit's out-of-bounds fill): no producer warps at all; warp 9 issues the boxes + the weight bulk copy,
+//     warp 8 the MMAs, warps 0-7 only drain / run the epilogue.  The split is computed ONCE per element by the
+//     producing epilogue instead of once per consumer tile (halo included) in front of every MMA.
 //   * F16 variant (template flag, the engine's default): operands split as fp16 hi + fp16 lo (22 mantissa bits,
 //     same three product terms) and multiplied with `kind::f16`: K = 16 channels per MMA instead of 8, i.e. half the
 //     MMAs and half the shared-memory operand traffic per channel (the kernel is shared-memory-pipe bound) at twice
@@ -65,7 +71,8 @@ using namespace tcp;
 
 constexpr int NPROD = 256;
 constexpr int NTHREADS = NPROD + 32;
-constexpr int MAX_STAGES = 4;
+constexpr int nthreads(int raw) { return NPROD + 32 + (raw == 3 ? 32 : 0); }   // SPLIT: one more warp issues the TMA boxes
+constexpr int MAX_STAGES = 8;
 constexpr int MAX_MT = 4;
 constexpr size_t SMEM_MAX = 227 * 1024;
 
@@ -107,6 +114,14 @@ struct Params {
     const float* add;
     long long asB;
     int asC;
+    // ---- S-format ("split") tensors: fp16 hi / lo halves of an fp32 activation, [B][D][part][C8][H][W][8 channels]
+    // (strides in fp16 elements; the [H][W][8] block is dense).  Input (template RAW = 3): read through the two TMA maps
+    // (hi, lo), s_sx = 2: the four parity phases of a stride-2 conv through the map's element strides.  Output (any
+    // instance): `outs` != null -> the epilogue also (or only: out == null) writes the split result for batches < s_nb.
+    int s_in, s_sx;
+    unsigned short* outs;
+    long long ossB, ossD, ossP, ossC8;
+    int s_parts, s_nb;
 };
 
 // cvt.rna.tf32.f32 without the NaN/Inf handling ptxas wraps around it (operands here are finite activations)
@@ -152,13 +167,27 @@ __device__ __forceinline__ float act_t(float x) {
     }
 }
 
+// Where the epilogue of one lane (= one output position) writes: fp32 NC(D)HW and / or the S-format halves.
+struct EpiOut {
+    float* o;                 // fp32: address of channel 0 at this position, or null
+    int osC;
+    unsigned short* so;       // S-format: the hi vector (8 channels) of chunk 0 at this position, or null
+    long long so_lo;          // element offset hi -> lo vector (0: hi only)
+    long long so_c8;          // element stride between 8-channel chunks
+    bool sok;                 // this lane writes the S-format (position inside the image, batch < s_nb)
+};
+__device__ __forceinline__ void stg128(void* ptr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 // kx shift-sum + bias + activation + store of 8 channels of one tile row (lane = tile column):
 // out[x] = P0[x] + P1[x + dil] + P2[x + 2*dil]
 // FOLD = 3: the kx taps are columns of the accumulator (3x3 convs); FOLD = 1: one column block (the 1x1 / (k,1,1) form)
 template <int ACT, int FOLD>
-__device__ __forceinline__ void epi_store8(const float (&a0)[8], const float (&a1)[8], const float (&a2)[8], int dil, float* o,
-                                           int osC, const float* bias, int co0, int Cout, bool ok, const float* osc,
+__device__ __forceinline__ void epi_store8(const float (&a0)[8], const float (&a1)[8], const float (&a2)[8], int dil, const EpiOut& eo,
+                                           int c0, const float* bias, int Cout, bool ok, const float* osc,
                                            const float* add = nullptr, int asC = 0) {
+    float res[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
         float acc = a0[c];
@@ -166,16 +195,32 @@ __device__ __forceinline__ void epi_store8(const float (&a0)[8], const float (&a
             acc += __shfl_down_sync(0xffffffffu, a1[c], dil);
             acc += __shfl_down_sync(0xffffffffu, a2[c], 2 * dil);
         }
-        const bool live = ok && co0 + c < Cout;
-        const bool cok = co0 + c < Cout;
-        float pre = fmaf(acc, (osc && cok) ? __ldg(osc + c) : 1.f, cok ? __ldg(bias + c) : 0.f);
-        if (add) pre += live ? __ldg(add + (long long)c * asC) : 0.f;
-        const float r = act_t<ACT>(pre);
-        if (live) o[c * osC] = r;
+        const bool live = ok && c0 + c < Cout;
+        const bool cok = c0 + c < Cout;
+        float pre = fmaf(acc, (osc && cok) ? __ldg(osc + c0 + c) : 1.f, cok ? __ldg(bias + c0 + c) : 0.f);
+        if (add) pre += live ? __ldg(add + (long long)(c0 + c) * asC) : 0.f;
+        res[c] = act_t<ACT>(pre);
+        if (eo.o && live) eo.o[(c0 + c) * eo.osC] = res[c];
+    }
+    if (eo.so && c0 < Cout) {   // the S-format of this 8-channel chunk (chunks beyond Cout do not exist in the output): hi = fp16(x), lo = fp16(x - hi); padding channels are 0
+        uint32_t hi[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) hi[i] = pack_h2(res[2 * i], res[2 * i + 1]);
+        unsigned short* sp = eo.so + (long long)(c0 >> 3) * eo.so_c8;
+        if (eo.sok) stg128(sp, hi[0], hi[1], hi[2], hi[3]);
+        if (eo.so_lo) {
+            uint32_t lo[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 hf = unpack_h2(hi[i]);
+                lo[i] = pack_h2(res[2 * i] - hf.x, res[2 * i + 1] - hf.y);
+            }
+            if (eo.sok) stg128(sp + eo.so_lo, lo[0], lo[1], lo[2], lo[3]);
+        }
     }
 }
 template <int ACT, int CP, int FOLD>
-__device__ __forceinline__ void epi_direct(uint32_t taddr, int dil, float* o, int osC, const float* bias, int Cout, bool ok,
+__device__ __forceinline__ void epi_direct(uint32_t taddr, int dil, const EpiOut& eo, const float* bias, int Cout, bool ok,
                                            const float* osc) {
 #pragma unroll
     for (int c0 = 0; c0 < CP; c0 += 8) {
@@ -193,11 +238,11 @@ __device__ __forceinline__ void epi_direct(uint32_t taddr, int dil, float* o, in
             a1[c] = FOLD == 3 ? __uint_as_float(r1[c]) : 0.f;
             a2[c] = FOLD == 3 ? __uint_as_float(r2[c]) : 0.f;
         }
-        epi_store8<ACT, FOLD>(a0, a1, a2, dil, o + (long long)c0 * osC, osC, bias + c0, c0, Cout, ok, osc ? osc + c0 : nullptr);
+        epi_store8<ACT, FOLD>(a0, a1, a2, dil, eo, c0, bias, Cout, ok, osc);
     }
 }
 template <int ACT, int CP, int FOLD>
-__device__ __forceinline__ void epi_acc(const float* acc, int dil, float* o, int osC, const float* bias, int Cout, bool ok,
+__device__ __forceinline__ void epi_acc(const float* acc, int dil, const EpiOut& eo, const float* bias, int Cout, bool ok,
                                         const float* osc, const float* add = nullptr, int asC = 0) {
 #pragma unroll
     for (int c0 = 0; c0 < CP; c0 += 8) {
@@ -208,8 +253,7 @@ __device__ __forceinline__ void epi_acc(const float* acc, int dil, float* o, int
             a1[c] = FOLD == 3 ? acc[(FOLD == 3 ? CP : 0) + c0 + c] : 0.f;
             a2[c] = FOLD == 3 ? acc[(FOLD == 3 ? 2 * CP : 0) + c0 + c] : 0.f;
         }
-        epi_store8<ACT, FOLD>(a0, a1, a2, dil, o + (long long)c0 * osC, osC, bias + c0, c0, Cout, ok, osc ? osc + c0 : nullptr,
-                              add ? add + (long long)c0 * asC : nullptr, asC);
+        epi_store8<ACT, FOLD>(a0, a1, a2, dil, eo, c0, bias, Cout, ok, osc, add, asC);
     }
 }
 
@@ -242,16 +286,18 @@ constexpr int MAX_RS = 8;
 // into the same ring, `rs` chunks deep — for the small, latency-bound layers (any width / alignment)
 // FUSE: 0 = the input is a tensor; 1 / 2 = the input is the warp / shift cost volume built on the fly (see Params)
 template <int CP, int MT, bool DIRECT, int RAW, bool F16, int FOLD, int FUSE = 0>
-__global__ void __launch_bounds__(NTHREADS, Cfg<CP, MT, DIRECT, FOLD>::MINB)
-conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
+__global__ void __launch_bounds__(nthreads(RAW), Cfg<CP, MT, DIRECT, FOLD>::MINB)
+conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_lo) {
     static_assert(FUSE == 0 || (RAW == 0 && FOLD == 3 && !DIRECT), "the fused cost producer is the register path of the 3x3 ACC form");
-    constexpr bool TMA = RAW == 1, CPA = RAW == 2;
+    static_assert(RAW != 3 || F16, "the S-format input is the fp16 split");
+    constexpr bool TMA = RAW == 1, CPA = RAW == 2, SPLIT = RAW == 3;
     using C = Cfg<CP, MT, DIRECT, FOLD>;
     constexpr int N = C::N, JT = C::JT, RPW = C::RPW;
     extern __shared__ __align__(128) uint8_t smem[];
     const int SR = 4 * MT + 2 * p.dil;                 // staged rows
     const uint32_t NPOS = (uint32_t)SR * 32u;
-    const uint32_t a_bytes = 4u * NPOS * 16u;          // [part 2][khalf 2][NPOS][16 B]
+    // [part 2][khalf 2][NPOS][16 B]; the single-term SPLIT form stages the hi part only
+    const uint32_t a_bytes = ((SPLIT && p.terms != 3) ? 2u : 4u) * NPOS * 16u;
     const uint32_t stage_bytes = a_bytes + C::B_BYTES;
     const uint32_t b_bytes = (uint32_t)p.nky * (C::B_BYTES / 3u);   // weight bytes of one chunk actually used
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
@@ -270,7 +316,7 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
     // MULTI (DIRECT register-producer instances): a CTA walks tiles t0, t0 + grid.x, ... — barriers, TMEM and the
     // operand ring are set up once, the first loads of tile t+1 are in flight while tile t's epilogue runs.  Every other
     // instance keeps one tile per CTA (grid = tiles of a plane x planes).
-    constexpr bool MULTI = DIRECT && RAW == 0 && FUSE == 0;
+    constexpr bool MULTI = DIRECT && (RAW == 0 || RAW == 3) && FUSE == 0;
     const int tiles_pp = p.tiles_x * p.tiles_y;
     const int T = tiles_pp * p.nplanes;                // < 2^31 (checked by the host)
     const int t_first = MULTI ? (int)blockIdx.x : (int)blockIdx.y * tiles_pp + (int)blockIdx.x;
@@ -289,7 +335,7 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
 
     if (tid == 0) {
         for (int s = 0; s < p.stages; ++s) {
-            mbar_init(&full[s], NPROD + 1);
+            mbar_init(&full[s], SPLIT ? 1 : NPROD + 1);
             mbar_init(&empty[s], 1);
         }
         for (int j = 0; j < MT; ++j) {
@@ -366,7 +412,7 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
                 if (p.isX * gy + 1 >= p.Hin) edge |= 1 << u;
             }
         };
-        setup_tile();
+        if constexpr (!SPLIT) setup_tile();
         // fused cost producer: per staged position the right-feature tap (offset inside a channel plane, two weights)
         int woff[FUSE ? RPW : 1];
         float wa[FUSE ? RPW : 1], wb[FUSE == 1 ? RPW : 1];
@@ -580,7 +626,7 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
 
         if constexpr (CPA) {
             for (int i = 0; i < p.rs && i < p.nchunk; ++i) issue_cpa();
-        } else if constexpr (!TMA) {
+        } else if constexpr (!TMA && !SPLIT) {
             load_chunk(std::integral_constant<int, 0>{});
         }
         int s = 0, gk = 0, gdone = 0;      // stage of chunk k; chunks produced since the last group boundary; groups drained
@@ -701,7 +747,12 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
         };
         uint32_t it = 0;                 // tiles this CTA has finished: parity of the per-tile accumulator barriers
         for (int t = t_first; t < T; t += t_stride, ++it) {
-        if constexpr (NB == 2) {
+        if constexpr (SPLIT) {
+            // nothing to produce: the TMA warp fills the operand stages; these warps only drain the accumulator groups
+            set_tile(t);
+            if constexpr (!DIRECT)
+                for (int g = 0; g + 1 < ngroups; ++g) drain(g);
+        } else if constexpr (NB == 2) {
             for (int k = 0; k < p.nchunk; k += 2) {
                 step(k, std::integral_constant<int, 0>{});
                 if (k + 1 < p.nchunk) step(k + 1, std::integral_constant<int, 1>{});
@@ -712,12 +763,14 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
         if constexpr (!DIRECT) drain(ngroups - 1);
 
         // ===================== epilogue: kx shift-sum, bias, activation, NCDHW stores =====================
-        float* out_pl = p.out + (long long)b * p.osB + (long long)d * p.osD;
+        float* out_pl = p.out ? p.out + (long long)b * p.osB + (long long)d * p.osD : nullptr;
+        unsigned short* outs_pl = p.outs ? p.outs + (long long)b * p.ossB + (long long)d * p.ossD : nullptr;
+        const bool s_batch = b < p.s_nb;
         const int x = x0 + lane;
         const bool xok = lane < VW && x < p.W;
         const int xo = x * p.osX;
         const int ey0 = y0;
-        if constexpr (MULTI) {
+        if constexpr (MULTI && !SPLIT) {
             // the next tile's first unit goes in flight before this tile's epilogue (buffer 0 is free: every unit of this
             // tile has been packed); the epilogue below works from the coordinates saved above
             if (t_stride < T - t) {
@@ -731,16 +784,23 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
             const int j = half + 2 * jj;
             if (j < MT) {                                  // warp-uniform
                 const int y = ey0 + 4 * j + quarter;
-                float* o = out_pl + (long long)y * p.osY + xo;
                 const bool ok = xok && y < p.H;
+                const long long pos = (long long)y * p.osY + xo;
+                EpiOut eo;
+                eo.o = out_pl ? out_pl + pos : nullptr;
+                eo.osC = p.osC;
+                eo.so = outs_pl ? outs_pl + pos * 8 : nullptr;
+                eo.so_lo = p.s_parts == 2 ? p.ossP : 0ll;
+                eo.so_c8 = p.ossC8;
+                eo.sok = ok && s_batch;
                 if constexpr (DIRECT) {
                     // one accumulation group: stream TMEM -> registers 8 channels at a time
                     mbar_wait(&acc_full[j], it & 1u);
                     tc_fence_after();
                     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(j * C::TS);
-                    if (p.act == TSTEREO_ACT_SILU) epi_direct<TSTEREO_ACT_SILU, CP, FOLD>(taddr, p.dil, o, p.osC, p.bias, p.Cout, ok, p.oscale);
-                    else if (p.act == TSTEREO_ACT_RELU) epi_direct<TSTEREO_ACT_RELU, CP, FOLD>(taddr, p.dil, o, p.osC, p.bias, p.Cout, ok, p.oscale);
-                    else epi_direct<TSTEREO_ACT_NONE, CP, FOLD>(taddr, p.dil, o, p.osC, p.bias, p.Cout, ok, p.oscale);
+                    if (p.act == TSTEREO_ACT_SILU) epi_direct<TSTEREO_ACT_SILU, CP, FOLD>(taddr, p.dil, eo, p.bias, p.Cout, ok, p.oscale);
+                    else if (p.act == TSTEREO_ACT_RELU) epi_direct<TSTEREO_ACT_RELU, CP, FOLD>(taddr, p.dil, eo, p.bias, p.Cout, ok, p.oscale);
+                    else epi_direct<TSTEREO_ACT_NONE, CP, FOLD>(taddr, p.dil, eo, p.bias, p.Cout, ok, p.oscale);
                     if constexpr (MULTI) {                 // M-tile j of the accumulator is free for the next tile's MMAs
                         tc_fence_before();
                         mbar_arrive(&acc_empty[j]);
@@ -749,15 +809,15 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
                     const float* ad = nullptr;
                     if constexpr (FUSE == 1)
                         if (p.add) ad = p.add + (long long)b * p.asB + (long long)min(y, p.H - 1) * p.W + min(x, p.W - 1);
-                    if (p.act == TSTEREO_ACT_SILU) epi_acc<TSTEREO_ACT_SILU, CP, FOLD>(acc[jj], p.dil, o, p.osC, p.bias, p.Cout, ok, p.oscale, ad, p.asC);
-                    else if (p.act == TSTEREO_ACT_RELU) epi_acc<TSTEREO_ACT_RELU, CP, FOLD>(acc[jj], p.dil, o, p.osC, p.bias, p.Cout, ok, p.oscale, ad, p.asC);
-                    else epi_acc<TSTEREO_ACT_NONE, CP, FOLD>(acc[jj], p.dil, o, p.osC, p.bias, p.Cout, ok, p.oscale, ad, p.asC);
+                    if (p.act == TSTEREO_ACT_SILU) epi_acc<TSTEREO_ACT_SILU, CP, FOLD>(acc[jj], p.dil, eo, p.bias, p.Cout, ok, p.oscale, ad, p.asC);
+                    else if (p.act == TSTEREO_ACT_RELU) epi_acc<TSTEREO_ACT_RELU, CP, FOLD>(acc[jj], p.dil, eo, p.bias, p.Cout, ok, p.oscale, ad, p.asC);
+                    else epi_acc<TSTEREO_ACT_NONE, CP, FOLD>(acc[jj], p.dil, eo, p.bias, p.Cout, ok, p.oscale, ad, p.asC);
                 }
             }
         }
         }   // tiles
         if constexpr (DIRECT) tc_fence_before();
-    } else {
+    } else if (warp == NPROD / 32) {
         // ===================== MMA issuer =====================
         constexpr uint32_t idesc_2n = F16 ? idesc_f16(2 * N) : idesc_tf32(2 * N), idesc_n = F16 ? idesc_f16(C::N2) : idesc_tf32(C::N2);
         auto mma = [](uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accf) {
@@ -831,6 +891,63 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
             }
         }
         tc_fence_before();
+    } else if constexpr (SPLIT) {
+        // ===================== TMA issuer (SPLIT): one box per 8-channel unit and part + the weight image per stage =====================
+        const uint32_t unit_bytes = NPOS * 16u;
+        const int nparts = p.terms == 3 ? 2 : 1;
+        int s = 0;
+        uint32_t ph = 0;
+        for (int t = t_first; t < T; t += t_stride) {
+            set_tile(t);
+            for (int k = 0; k < nmma; ++k) {
+                mbar_wait(&empty[s], ph ^ 1u);
+                if (elect_one()) {
+                    uint8_t* st_base = smem + (size_t)s * stage_bytes;
+                    mbar_arrive_expect_tx(&full[s], 2u * (uint32_t)nparts * unit_bytes + b_bytes);
+                    bulk_g2s(st_base + a_bytes, p.wpack + (size_t)k * (b_bytes / 4), b_bytes, &full[s]);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int u = 2 * k + h;            // 8-channel unit = K half h of MMA chunk k
+                        int phase = u / p.cpp, kc = u - phase * p.cpp;
+                        if (u >= p.nchunk) {                // odd number of units: the last K half is a box of zeros
+                            phase = 0;
+                            kc = p.cpp;
+                        }
+                        int c0, c1, c2, c3, c4;
+                        if (p.s_sx == 2) {                  // map (ch 8, x, y, c8, plane), element strides (1, 2, 2, 1, 1)
+                            c0 = 0;
+                            c1 = 2 * (x0 - 1) + (phase & 1);
+                            c2 = 2 * (y0 - 1) + (phase >> 1);
+                            c3 = kc;
+                            c4 = b * p.D + d;
+                        } else {                            // map (x*8 + ch, y, c8, plane d, b)
+                            int dd = d;
+                            if (p.kd) {
+                                if (p.dtrans) {             // transposed k3 s2 p1 op1: dout = 2*din - 1 + tap
+                                    const int t2 = d + 1 - phase;
+                                    dd = (t2 >= 0 && (t2 & 1) == 0) ? (t2 >> 1) : -1;
+                                } else {
+                                    dd = d * p.dstride + (phase - p.kd / 2) * p.ddil;
+                                }
+                                if (dd < 0 || dd >= p.Din) dd = -1;      // outside: the TMA unit fills zeros
+                            }
+                            c0 = (x0 - p.dil) * 8;
+                            c1 = y0 - p.dil;
+                            c2 = kc;
+                            c3 = dd;
+                            c4 = b;
+                        }
+                        tma_load_5d(st_base + (size_t)h * unit_bytes, &tmap, &full[s], c0, c1, c2, c3, c4);
+                        if (nparts == 2) tma_load_5d(st_base + (size_t)(2 + h) * unit_bytes, &tmap_lo, &full[s], c0, c1, c2, c3, c4);
+                    }
+                }
+                __syncwarp();
+                if (++s == p.stages) {
+                    s = 0;
+                    ph ^= 1u;
+                }
+            }
+        }
     }
     __syncthreads();
     if (warp == NPROD / 32) {
@@ -839,8 +956,8 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap) {
     }
 }
 
-static size_t smem_need(int stages, int SR, int N, int rs = 0, int bw = 36) {
-    return (size_t)stages * ((size_t)SR * 2048 + (size_t)192 * N) + 384 + (size_t)rs * 32 * bw * SR;
+static size_t smem_need(int stages, int SR, int N, int rs = 0, int bw = 36, int a_units = 4) {
+    return (size_t)stages * ((size_t)SR * 512 * a_units + (size_t)192 * N) + 384 + (size_t)rs * 32 * bw * SR;
 }
 
 static int env_int(const char* name, int dflt);
@@ -892,8 +1009,48 @@ static bool make_tmap(const Params& p, int SR, CUtensorMap* tm) {
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// S-format input [B][D][part][C8][H][W][8] fp16 (strides in elements) as a TMA view; one map per part (hi, lo).
+//   stride 1: (x*8 + ch, y, c8, d, b), box (256, SR, 1, 1, 1): a box row is 32 positions x 8 channels = the K-major stage row
+//   stride 2: (ch, x, y, c8, plane b*D + d), box (8, 64, 2*SR, 1, 1) walked with element strides (1, 2, 2, 1, 1)
+struct SIn {
+    const unsigned short* ptr;
+    long long sB, sD, sP, sC8;
+    int C8, parts;
+};
+static bool make_tmap_s(const SIn& si, int part, int B, int D, int H, int W, int SR, int sx, CUtensorMap* tm) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    const unsigned short* base = si.ptr + (part ? si.sP : 0ll);
+    if ((((size_t)base) & 15) || (si.sB & 7) || (si.sD & 7) || (si.sC8 & 7)) return false;
+    const cuuint64_t sY = (cuuint64_t)W * 16;
+    const cuuint64_t sC = (cuuint64_t)si.sC8 * 2;
+    // a dimension of extent 1 may carry any stride: use a legal placeholder
+    const cuuint64_t sDb = D > 1 ? (cuuint64_t)si.sD * 2 : sC * (cuuint64_t)si.C8;
+    const cuuint64_t sBb = B > 1 ? (cuuint64_t)si.sB * 2 : sDb * (cuuint64_t)D;
+    if (sx == 1) {
+        const cuuint64_t dims[5] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)si.C8, (cuuint64_t)D, (cuuint64_t)B};
+        const cuuint64_t strides[4] = {sY, sC, sDb, sBb};
+        const cuuint32_t box[5] = {256, (cuuint32_t)SR, 1, 1, 1};
+        const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        return fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT16, 5, const_cast<unsigned short*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
+    // stride 2: batch and plane merge into one dimension, which needs sB == D * sD
+    if (B > 1 && D > 1 && si.sB != (long long)D * si.sD) return false;
+    const cuuint64_t sPl = (B * D > 1) ? (D > 1 ? (cuuint64_t)si.sD * 2 : (cuuint64_t)si.sB * 2) : sC * (cuuint64_t)si.C8;
+    const cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)si.C8, (cuuint64_t)B * D};
+    const cuuint64_t strides[4] = {16, sY, sC, sPl};
+    const cuuint32_t box[5] = {8, 64, (cuuint32_t)(2 * SR), 1, 1};
+    const cuuint32_t estr[5] = {1, 2, 2, 1, 1};
+    return fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT16, 5, const_cast<unsigned short*>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int CP, int MT, bool DIRECT, int RAW, bool F16, int FOLD = 3, int FUSE = 0>
-static int launch_one(const Params& p, const CUtensorMap& tm, dim3 grid, size_t smem_bytes, cudaStream_t st, const char* what) {
+static int launch_one(const Params& p, const CUtensorMap& tm, const CUtensorMap& tm2, dim3 grid, size_t smem_bytes, cudaStream_t st,
+                      const char* what) {
     auto kern = conv_tc2_kernel<CP, MT, DIRECT, RAW, F16, FOLD, FUSE>;
     static bool attr_done = false;
     if (!attr_done) {
@@ -904,7 +1061,7 @@ static int launch_one(const Params& p, const CUtensorMap& tm, dim3 grid, size_t 
         }
         attr_done = true;
     }
-    kern<<<grid, NTHREADS, smem_bytes, st>>>(p, tm);
+    kern<<<grid, nthreads(RAW), smem_bytes, st>>>(p, tm, tm2);
     return check_launch(what);
 }
 
@@ -925,7 +1082,7 @@ static int env_int(const char* name, int dflt) {
 }
 
 template <int FUSE = 0>
-static int launch(Params& p, int CP, int planes, cudaStream_t st, const char* what) {
+static int launch(Params& p, int CP, int planes, cudaStream_t st, const char* what, const SIn* sin = nullptr) {
     const int fold = p.fold == 1 ? 1 : 3;
     const int N = fold * CP, N2 = (N + 15) / 16 * 16;
     const int VW = 32 - 2 * p.dil;
@@ -941,15 +1098,24 @@ static int launch(Params& p, int CP, int planes, cudaStream_t st, const char* wh
         p.G = nmma;                                      // 11-bit operands: nothing to gain from short TMEM accumulation groups
     }
     const bool direct = FUSE == 0 && nmma <= p.G && !env_int("TSTEREO_TC2_NODIRECT", 0);
+    const bool split = FUSE == 0 && sin != nullptr;
+    if (split) {
+        TS_REQUIRE(p.half, "%s: the S-format input is the fp16 split", what);
+        TS_REQUIRE(sin->parts == 2 || p.terms == 1, "%s: a hi-only S-format input serves the single-term form only", what);
+        TS_REQUIRE(sin->C8 >= p.cpp, "%s: S-format input has %d chunks, the layer needs %d", what, sin->C8, p.cpp);
+    }
+    p.s_in = split;
+    const int a_units = (split && p.terms != 3) ? 2 : 4;
     // M-tiles per CTA: 2 or 4 (TMEM: MT * columns-per-tile <= 512); cost = SM-time of all waves
     p.nbatch = planes / p.D;
     p.bw = p.dil ? 36 : 32;
     CUtensorMap tm = {};
-    const bool tma_ok = FUSE == 0 && !p.half && make_tmap(p, 4 * 2 + 2 * p.dil, &tm);   // eligibility (the box is re-encoded for the chosen tile)
+    CUtensorMap tm2 = {};
+    const bool tma_ok = FUSE == 0 && !split && !p.half && make_tmap(p, 4 * 2 + 2 * p.dil, &tm);   // eligibility (the box is re-encoded for the chosen tile)
     // cp.async ring (fp16 split only; opt-in TSTEREO_TC2_CPA=1): loads run `rs` chunks ahead without holding registers.
     // Measured on B200: no gain on the small hourglass layers (they sit at the fixed launch + prologue + epilogue cost,
     // ~10 us) and 5-20 % slower on the large ones (one more shared-memory round trip), so it is not the default.
-    const int cpa_env = FUSE == 0 ? env_int("TSTEREO_TC2_CPA", 0) : 0;
+    const int cpa_env = (FUSE == 0 && !split) ? env_int("TSTEREO_TC2_CPA", 0) : 0;
     int best_mt = 0, best_stages = 0, best_rs = 0;
     bool best_cpa = false;
     double best_cost = 1e30;
@@ -986,8 +1152,8 @@ static int launch(Params& p, int CP, int planes, cudaStream_t st, const char* wh
         }
         if (!stages) {
             rs = 0;
-            for (int s = MAX_STAGES; s >= 2; --s)
-                if (smem_need(s, SR, N) <= budget) {
+            for (int s = split ? MAX_STAGES : 4; s >= 2; --s)
+                if (smem_need(s, SR, N, 0, 36, a_units) <= budget) {
                     stages = s;
                     break;
                 }
@@ -1015,13 +1181,19 @@ static int launch(Params& p, int CP, int planes, cudaStream_t st, const char* wh
         set_error("%s: cuTensorMapEncodeTiled failed", what);
         return TSTEREO_E_CUDA;
     }
-    const size_t smem_bytes = smem_need(p.stages, SR, N, p.rs, p.bw);   // p.bw = 32 for the cp.async ring
+    if (split) {
+        const int Dm = p.kd ? p.Din : p.D;
+        TS_REQUIRE(make_tmap_s(*sin, 0, p.nbatch, Dm, p.Hin, p.Win, SR, p.s_sx, &tm) &&
+                       (p.terms != 3 || make_tmap_s(*sin, 1, p.nbatch, Dm, p.Hin, p.Win, SR, p.s_sx, &tm2)),
+                   "%s: the S-format input is not expressible as a TMA view (alignment / strides)", what);
+    }
+    const size_t smem_bytes = smem_need(p.stages, SR, N, p.rs, p.bw, a_units);   // p.bw = 32 for the cp.async ring
     p.tiles_y = (p.H + 4 * best_mt - 1) / (4 * best_mt);
     p.nplanes = planes;
     dim3 grid(p.tiles_x * p.tiles_y, planes);
     // MULTI instances (DIRECT, register producer): resident CTAs walk the tiles — 2 per SM (TSTEREO_TC2_PERSIST=0: one tile
     // per CTA, the same kernel with grid.x = tiles)
-    const bool multi = FUSE == 0 && direct && !tma && !best_cpa;
+    const bool multi = FUSE == 0 && direct && !tma && !best_cpa;   // register producer or SPLIT
     if (multi) {
         const long long T = (long long)grid.x * planes;
         const long long want = (long long)148 * 2 * (env_int("TSTEREO_TC2_PERSIST", 1) > 0 ? env_int("TSTEREO_TC2_PERSIST", 1) : 1);
@@ -1033,31 +1205,39 @@ static int launch(Params& p, int CP, int planes, cudaStream_t st, const char* wh
         TS_REQUIRE(fold == 3 && !direct && !tma && !best_cpa, "%s: the fused cost producer runs the 3x3 ACC register form", what);
 #define TS_TC2U(CC, MM)                                                                                        \
     if (CP == CC && best_mt == MM)                                                                             \
-        return p.half ? launch_one<CC, MM, false, 0, true, 3, FUSE>(p, tm, grid, smem_bytes, st, what)         \
-                      : launch_one<CC, MM, false, 0, false, 3, FUSE>(p, tm, grid, smem_bytes, st, what);
+        return p.half ? launch_one<CC, MM, false, 0, true, 3, FUSE>(p, tm, tm2, grid, smem_bytes, st, what)    \
+                      : launch_one<CC, MM, false, 0, false, 3, FUSE>(p, tm, tm2, grid, smem_bytes, st, what);
         TS_TC2U(8, 2) TS_TC2U(8, 4) TS_TC2U(16, 2) TS_TC2U(16, 4) TS_TC2U(32, 2)
 #undef TS_TC2U
         TS_REQUIRE(false, "%s: no fused kernel instance for CP=%d MT=%d", what, CP, best_mt);
     } else {
+#define TS_TC2S(CC, MM, FF)                                                                                    \
+    if (split && fold == FF && CP == CC && best_mt == MM)                                                      \
+        return direct ? launch_one<CC, MM, true, 3, true, FF>(p, tm, tm2, grid, smem_bytes, st, what)          \
+                      : launch_one<CC, MM, false, 3, true, FF>(p, tm, tm2, grid, smem_bytes, st, what);
+    TS_TC2S(8, 2, 3) TS_TC2S(8, 4, 3) TS_TC2S(16, 2, 3) TS_TC2S(16, 4, 3) TS_TC2S(32, 2, 3)
+    TS_TC2S(8, 2, 1) TS_TC2S(8, 4, 1) TS_TC2S(16, 2, 1) TS_TC2S(16, 4, 1) TS_TC2S(32, 2, 1) TS_TC2S(32, 4, 1)
+#undef TS_TC2S
+    TS_REQUIRE(!split, "%s: no S-format kernel instance for CP=%d MT=%d fold=%d", what, CP, best_mt, fold);
 #define TS_TC2F1(CC, MM)                                                                                       \
     if (fold == 1 && p.half && !best_cpa && CP == CC && best_mt == MM)                                         \
-        return direct ? launch_one<CC, MM, true, 0, true, 1>(p, tm, grid, smem_bytes, st, what)                \
-                      : launch_one<CC, MM, false, 0, true, 1>(p, tm, grid, smem_bytes, st, what);
+        return direct ? launch_one<CC, MM, true, 0, true, 1>(p, tm, tm2, grid, smem_bytes, st, what)           \
+                      : launch_one<CC, MM, false, 0, true, 1>(p, tm, tm2, grid, smem_bytes, st, what);
     TS_TC2F1(8, 2) TS_TC2F1(8, 4) TS_TC2F1(16, 2) TS_TC2F1(16, 4) TS_TC2F1(32, 2) TS_TC2F1(32, 4)
 #undef TS_TC2F1
     TS_REQUIRE(fold == 3, "%s: the single-column form needs the fp16 split and the register producer", what);
 #define TS_TC2(CC, MM)                                                                                         \
     if (CP == CC && best_mt == MM) {                                                                           \
         if (p.half && best_cpa)                                                                                \
-            return direct ? launch_one<CC, MM, true, 2, true>(p, tm, grid, smem_bytes, st, what)               \
-                          : launch_one<CC, MM, false, 2, true>(p, tm, grid, smem_bytes, st, what);             \
+            return direct ? launch_one<CC, MM, true, 2, true>(p, tm, tm2, grid, smem_bytes, st, what)          \
+                          : launch_one<CC, MM, false, 2, true>(p, tm, tm2, grid, smem_bytes, st, what);        \
         if (p.half)                                                                                            \
-            return direct ? launch_one<CC, MM, true, 0, true>(p, tm, grid, smem_bytes, st, what)               \
-                          : launch_one<CC, MM, false, 0, true>(p, tm, grid, smem_bytes, st, what);             \
-        if (direct) return tma ? launch_one<CC, MM, true, 1, false>(p, tm, grid, smem_bytes, st, what)         \
-                               : launch_one<CC, MM, true, 0, false>(p, tm, grid, smem_bytes, st, what);        \
-        return tma ? launch_one<CC, MM, false, 1, false>(p, tm, grid, smem_bytes, st, what)                    \
-                   : launch_one<CC, MM, false, 0, false>(p, tm, grid, smem_bytes, st, what);                   \
+            return direct ? launch_one<CC, MM, true, 0, true>(p, tm, tm2, grid, smem_bytes, st, what)          \
+                          : launch_one<CC, MM, false, 0, true>(p, tm, tm2, grid, smem_bytes, st, what);        \
+        if (direct) return tma ? launch_one<CC, MM, true, 1, false>(p, tm, tm2, grid, smem_bytes, st, what)    \
+                               : launch_one<CC, MM, true, 0, false>(p, tm, tm2, grid, smem_bytes, st, what);   \
+        return tma ? launch_one<CC, MM, false, 1, false>(p, tm, tm2, grid, smem_bytes, st, what)               \
+                   : launch_one<CC, MM, false, 0, false>(p, tm, tm2, grid, smem_bytes, st, what);              \
     }
     TS_TC2(8, 2) TS_TC2(8, 4) TS_TC2(16, 2) TS_TC2(16, 4) TS_TC2(32, 2)
 #undef TS_TC2
@@ -1084,20 +1264,22 @@ inline long long wpack_floats(int nchunk, int Cout, int nky = 3, int fold = 3) {
 // One (virtual) stride-1 3x3 convolution, output channels in groups of <= 32 (the producer work is repeated per
 // group; Cout = 64 layers are rare and their inputs are L2 resident between the two launches).
 template <int FUSE = 0>
-inline int run_groups(tc2::Params p, int Cout, int planes, cudaStream_t st, const char* what) {
+inline int run_groups(tc2::Params p, int Cout, int planes, cudaStream_t st, const char* what, const SIn* sin = nullptr) {
     const float* wp = p.wpack;
     const float* bias = p.bias;
     const float* oscale = p.oscale;
     float* out = p.out;
+    unsigned short* outs = p.outs;
     for (int c0 = 0; c0 < Cout; c0 += 32) {
         const int cg = Cout - c0 < 32 ? Cout - c0 : 32;
         p.Cout = cg;
         p.wpack = wp;
         p.bias = bias ? bias + c0 : nullptr;
         p.oscale = oscale ? oscale + c0 : nullptr;
-        p.out = out + (long long)c0 * p.osC;
+        p.out = out ? out + (long long)c0 * p.osC : nullptr;
+        p.outs = outs ? outs + (long long)(c0 / 8) * p.ossC8 : nullptr;
         if (p.add) p.add += (c0 ? 32ll * p.asC : 0ll);
-        const int rc = tc2::launch<FUSE>(p, tc2_cp(cg), planes, st, what);
+        const int rc = tc2::launch<FUSE>(p, tc2_cp(cg), planes, st, what, sin);
         if (rc != TSTEREO_OK) return rc;
         wp += group_floats(p.half ? (p.nchunk + 1) / 2 : p.nchunk, cg, p.nky, p.fold == 1 ? 1 : 3);
     }

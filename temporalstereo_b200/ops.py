@@ -357,6 +357,192 @@ def conv_d_tc2(x: torch.Tensor, wpack: torch.Tensor, bias: Optional[torch.Tensor
     return out
 
 
+# --------------------------------------------------------------------------- S-format (TMA-fed) convolutions
+class Split:
+    """S-format activation (include/tstereo.h `tstereo_split`): the fp16 hi / lo halves of an fp32 tensor [B, C, D, H, W],
+    stored [B][D][part][C8][H][W][8] so that the tensor-core convolutions stage a K-chunk with one TMA box.  `parts` = 1
+    keeps the hi half only (operands of the single-term form).  `t` is the backing fp16 tensor (possibly a chunk slice
+    of a larger one: channel concatenation is a slice of the C8 axis)."""
+
+    def __init__(self, B: int, C: int, D: int, H: int, W: int, parts: int = 2, device=None, t: Optional[torch.Tensor] = None,
+                 five: bool = True):
+        self.C, self.five = C, five
+        c8 = (C + 7) // 8
+        if t is None:
+            t = torch.empty((B, D, parts, c8, H, W, 8), device=device, dtype=torch.float16)
+        if tuple(t.shape) != (B, D, parts, c8, H, W, 8) or t.dtype != torch.float16:
+            raise ValueError(f"S-format backing tensor has shape {tuple(t.shape)}, expected {(B, D, parts, c8, H, W, 8)}")
+        if not t.is_cuda:
+            raise TypeError("libtstereo ops need CUDA tensors (there is no CPU fallback)")
+        _same_device(t)
+        if t.stride()[4:] != (W * 8, 8, 1):
+            raise ValueError("the [H][W][8] block of an S-format tensor must be dense")
+        self.t = t
+
+    @property
+    def shape(self):
+        B, D, _, _, H, W, _ = self.t.shape
+        return (B, self.C, D, H, W) if self.five else (B, self.C, H, W)
+
+    @property
+    def parts(self) -> int:
+        return self.t.shape[2]
+
+    def channels(self, c0: int, c1: int) -> "Split":
+        """Channels [c0, c1) (multiples of 8) as an S-format view: the operand of a concatenation."""
+        assert c0 % 8 == 0 and (c1 % 8 == 0 or c1 == self.C) and 0 <= c0 < c1 <= self.C
+        B, D, P_, _, H, W, _ = self.t.shape
+        return Split(B, c1 - c0, D, H, W, P_, t=self.t[:, :, :, c0 // 8:(c1 + 7) // 8], five=self.five)
+
+    def batches(self, b0: int, b1: int) -> "Split":
+        B, D, P_, _, H, W, _ = self.t.shape
+        return Split(b1 - b0, self.C, D, H, W, P_, t=self.t[b0:b1], five=self.five)
+
+    def hi(self) -> "Split":
+        """The hi half alone (what a single-term consumer reads, what a single-term producer needs to write)."""
+        B, D, _, _, H, W, _ = self.t.shape
+        return Split(B, self.C, D, H, W, 1, t=self.t[:, :, :1], five=self.five)
+
+    def struct(self, nb: int = 0) -> "_lib.SplitStruct":
+        sB, sD, sP, sC8 = self.t.stride()[:4]
+        return _lib.SplitStruct(self.t.data_ptr(), sB, sD, sP if self.parts == 2 else 0, sC8, self.t.shape[3], self.parts, nb)
+
+    def float(self) -> torch.Tensor:
+        """hi (+ lo) as an fp32 [B, C, (D,) H, W] tensor (tests / debugging)."""
+        v = self.t.float().sum(2)                                  # [B, D, C8, H, W, 8]
+        B, D, C8, H, W, _ = v.shape
+        v = v.permute(0, 2, 5, 1, 3, 4).reshape(B, C8 * 8, D, H, W)[:, :self.C]
+        return v.contiguous() if self.five else v[:, :, 0].contiguous()
+
+
+def _sref(s: Optional[Split], nb: int = 0):
+    import ctypes
+    if s is None:
+        return None, None
+    st = s.struct(nb)
+    return st, ctypes.byref(st)
+
+
+def split_pack(x: torch.Tensor, parts: int = 2, out: Optional[Split] = None) -> Split:
+    """fp32 [B, C, (D,) H, W] view -> S-format."""
+    five = x.dim() == 5
+    B, Cc = x.shape[:2]
+    D = x.shape[2] if five else 1
+    H, W = x.shape[-2:]
+    if out is None:
+        out = Split(B, Cc, D, H, W, parts, device=x.device, five=five)
+    if out.shape != tuple(x.shape):
+        raise ValueError(f"S-format output has shape {out.shape}, the input {tuple(x.shape)}")
+    isB, isC, isD = _view5(x)
+    keep, ref = _sref(out)
+    _lib.call("tstereo_split_pack", _p(x), isB, isC, isD, ref, B, Cc, D, H, W, _stream())
+    return out
+
+
+def _s_io(x, out, sout, out_shape, want_f32, nb=0):
+    """Common argument handling of the `_s` operators: x is a torch tensor or a Split; returns the ABI pieces."""
+    xs = x if isinstance(x, Split) else None
+    if xs is None:
+        isB, isC, isD = _view5(x)
+        xp = _p(x)
+        like = x
+    else:
+        isB = isC = isD = 0
+        xp = None
+        like = xs.t
+    if sout is not None:
+        # nb: only the leading nb batches are written, so the S-format output may hold fewer than B (but at least nb)
+        if sout.shape[1:] != tuple(out_shape[1:]) or not (sout.shape[0] == out_shape[0] or (nb and sout.shape[0] >= nb)):
+            raise ValueError(f"S-format output has shape {sout.shape}, the operator produces {tuple(out_shape)}"
+                             + (f" (batches [0, {nb}))" if nb else ""))
+    if out is None and (want_f32 or sout is None):
+        out = torch.empty(out_shape, device=like.device, dtype=torch.float32)
+    if out is not None:
+        if tuple(out.shape) != tuple(out_shape):
+            raise ValueError(f"out has shape {tuple(out.shape)}, the operator produces {tuple(out_shape)}")
+        osB, osC, osD = _view5(out)
+    else:
+        osB = osC = osD = 0
+    return xs, xp, (isB, isC, isD), out, (osB, osC, osD)
+
+
+def conv_hw3_s(x, wpack: torch.Tensor, bias: Optional[torch.Tensor], cout: int, dilation: int = 1, act=None,
+               out: Optional[torch.Tensor] = None, half: int = 1, oscale: Optional[torch.Tensor] = None,
+               sout: Optional[Split] = None, want_f32: bool = False, nb: int = 0):
+    """`conv_hw3_tc2` with S-format operands: `x` may be a Split (staged by TMA), `sout` a Split written by the epilogue
+    (batches [0, nb) only when nb > 0); the fp32 output is produced when `out` is given, `want_f32`, or there is no `sout`.
+    Returns (fp32 output or None, sout)."""
+    shp = x.shape
+    five = len(shp) == 5
+    B, Cin = shp[:2]
+    D = shp[2] if five else 1
+    H, W = shp[-2:]
+    xs, xp, (isB, isC, isD), out, (osB, osC, osD) = _s_io(x, out, sout, (B, cout, D, H, W) if five else (B, cout, H, W), want_f32, nb)
+    _chk(wpack, bias, oscale)
+    assert wpack.numel() == _lib.load().tstereo_conv_hw3_tc2_wpack_floats(Cin, cout, 1)
+    k1, r1 = _sref(xs)
+    k2, r2 = _sref(sout, nb)
+    _lib.call("tstereo_conv_hw3_s", xp, isB, isC, isD, r1, _p(out), osB, osC, osD, r2, _p(wpack), _p(bias), _p(oscale),
+              B, Cin, cout, D, H, W, dilation, ACT[act], int(half), _stream())
+    return out, sout
+
+
+def conv_hw3s2_s(x, wpack: torch.Tensor, bias: Optional[torch.Tensor], cout: int, act=None, out: Optional[torch.Tensor] = None,
+                 half: int = 1, oscale: Optional[torch.Tensor] = None, sout: Optional[Split] = None, want_f32: bool = False,
+                 nb: int = 0):
+    """`conv_hw3s2_tc2` with S-format operands (see conv_hw3_s)."""
+    shp = x.shape
+    five = len(shp) == 5
+    B, Cin = shp[:2]
+    D = shp[2] if five else 1
+    Hin, Win = shp[-2:]
+    H, W = (Hin - 1) // 2 + 1, (Win - 1) // 2 + 1
+    xs, xp, (isB, isC, isD), out, (osB, osC, osD) = _s_io(x, out, sout, (B, cout, D, H, W) if five else (B, cout, H, W), want_f32, nb)
+    _chk(wpack, bias, oscale)
+    assert wpack.numel() == _lib.load().tstereo_conv_hw3s2_tc2_wpack_floats(Cin, cout, 1)
+    k1, r1 = _sref(xs)
+    k2, r2 = _sref(sout, nb)
+    _lib.call("tstereo_conv_hw3s2_s", xp, isB, isC, isD, r1, _p(out), osB, osC, osD, r2, _p(wpack), _p(bias), _p(oscale),
+              B, Cin, cout, D, Hin, Win, ACT[act], int(half), _stream())
+    return out, sout
+
+
+def deconv_hw_s(x, wpack: torch.Tensor, bias: Optional[torch.Tensor], cout: int, act=None, out: Optional[torch.Tensor] = None,
+                half: int = 1, oscale: Optional[torch.Tensor] = None, sout: Optional[Split] = None, want_f32: bool = False,
+                nb: int = 0):
+    """`deconv_hw_tc2` with S-format operands (see conv_hw3_s)."""
+    shp = x.shape
+    five = len(shp) == 5
+    B, Cin = shp[:2]
+    D = shp[2] if five else 1
+    Hin, Win = shp[-2:]
+    xs, xp, (isB, isC, isD), out, (osB, osC, osD) = _s_io(
+        x, out, sout, (B, cout, D, 2 * Hin, 2 * Win) if five else (B, cout, 2 * Hin, 2 * Win), want_f32, nb)
+    _chk(wpack, bias, oscale)
+    assert wpack.numel() == _lib.load().tstereo_deconv_hw_tc2_wpack_floats(Cin, cout, 1)
+    k1, r1 = _sref(xs)
+    k2, r2 = _sref(sout, nb)
+    _lib.call("tstereo_deconv_hw_s", xp, isB, isC, isD, r1, _p(out), osB, osC, osD, r2, _p(wpack), _p(bias), _p(oscale),
+              B, Cin, cout, D, Hin, Win, ACT[act], int(half), _stream())
+    return out, sout
+
+
+def conv_d_s(x, wpack: torch.Tensor, bias: Optional[torch.Tensor], cout: int, k: int = 3, stride: int = 1, dilation: int = 1,
+             transposed: bool = False, act=None, out: Optional[torch.Tensor] = None, half: int = 1,
+             oscale: Optional[torch.Tensor] = None, sout: Optional[Split] = None, want_f32: bool = False, nb: int = 0):
+    """`conv_d_tc2` with S-format operands (see conv_hw3_s)."""
+    B, Cin, Din, H, W = x.shape
+    Dout = 2 * Din if transposed else (Din - 1) // stride + 1
+    xs, xp, (isB, isC, isD), out, (osB, osC, osD) = _s_io(x, out, sout, (B, cout, Dout, H, W), want_f32, nb)
+    _chk(wpack, bias, oscale)
+    assert wpack.numel() == _lib.load().tstereo_conv_d_tc2_wpack_floats(Cin, cout, k, 1)
+    k1, r1 = _sref(xs)
+    k2, r2 = _sref(sout, nb)
+    _lib.call("tstereo_conv_d_s", xp, isB, isC, isD, r1, _p(out), osB, osC, osD, r2, _p(wpack), _p(bias), _p(oscale),
+              B, Cin, cout, Din, Dout, H, W, k, stride, dilation, int(transposed), ACT[act], int(half), _stream())
+    return out, sout
+
+
 def conv_d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], cout: int, k: int = 3, stride: int = 1,
            dilation: int = 1, transposed: bool = False, act=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """(k,1,1) conv along D (or its stride-2 transposed form), packed weights w[Cin][k][CoutP]."""
