@@ -404,8 +404,32 @@ class TEMPORALSTEREO(nn.Module):
                     self._plan_times[key] = times
         return cands[choice]()
 
-    def _hw3(self, x, k: _Packed, stride=1, dil=1, act=None, out=None, single=False):
-        """3x3 conv over (H,W): tensor cores or the fp32 FMA kernel, per the plan.  single: one fp16 MMA term."""
+    def _sfmt(self) -> bool:
+        """S-format activations between the tensor-core convolutions (see `split_format`)."""
+        return bool(self.split_format and self.half_split and self.tensor_cores)
+
+    @staticmethod
+    def _new_split(shape, like, parts=2) -> "ops.Split":
+        five = len(shape) == 5
+        B, C = shape[:2]
+        D = shape[2] if five else 1
+        dev = like.t.device if isinstance(like, ops.Split) else like.device
+        return ops.Split(B, C, D, shape[-2], shape[-1], parts, device=dev, five=five)
+
+    def _hw3(self, x, k: _Packed, stride=1, dil=1, act=None, out=None, single=False, fmt="f"):
+        """3x3 conv over (H,W): tensor cores or the fp32 FMA kernel, per the plan.  single: one fp16 MMA term.
+        `x` is an fp32 tensor or an S-format `ops.Split`; fmt "s" returns the result as a Split (S-format mode only)."""
+        if isinstance(x, ops.Split) or fmt == "s":
+            h = 2 if (single and self.decoder_single_term) else 1
+            shp = tuple(x.shape)
+            if stride == 2:
+                oshp = shp[:1] + (k.cout,) + shp[2:-2] + ((shp[-2] - 1) // 2 + 1, (shp[-1] - 1) // 2 + 1)
+                so = self._new_split(oshp, x) if fmt == "s" else None
+                f, _ = ops.conv_hw3s2_s(x, k.tc["s2"], k.b, k.cout, act, out=out, half=h, oscale=k.osc, sout=so)
+            else:
+                so = self._new_split(shp[:1] + (k.cout,) + shp[2:], x) if fmt == "s" else None
+                f, _ = ops.conv_hw3_s(x, k.tc["hw3"], k.b, k.cout, dil, act, out=out, half=h, oscale=k.osc, sout=so)
+            return so if fmt == "s" else f
         simt = lambda: ops.conv_hw3(x, k.w, k.b, k.cout, stride, dil, act, out=out)
         h = 2 if (single and self.half_split and self.decoder_single_term) else self.half_split
         if stride == 2 and dil == 1 and "s2" in k.tc:
@@ -416,8 +440,14 @@ class TEMPORALSTEREO(nn.Module):
         return self._pick(("hw3", tuple(x.shape), k.cout, dil),
                           {"tc2": lambda: ops.conv_hw3_tc2(x, k.tc["hw3"], k.b, k.cout, dil, act, out=out, half=h, oscale=k.osc), "simt": simt})
 
-    def _d(self, x, k: _Packed, ksz=3, stride=1, dil=1, transposed=False, act=None, out=None):
-        """(k,1,1) conv along D: tensor cores when a tcgen05 operand image exists."""
+    def _d(self, x, k: _Packed, ksz=3, stride=1, dil=1, transposed=False, act=None, out=None, fmt="f"):
+        """(k,1,1) conv along D: tensor cores when a tcgen05 operand image exists.  S-format operands as in `_hw3`."""
+        if isinstance(x, ops.Split) or fmt == "s":
+            B, _, Din, H, W = x.shape
+            Dout = 2 * Din if transposed else (Din - 1) // stride + 1
+            so = self._new_split((B, k.cout, Dout, H, W), x) if fmt == "s" else None
+            f, _ = ops.conv_d_s(x, k.tc["d"], k.b, k.cout, ksz, stride, dil, transposed, act, out=out, half=1, oscale=k.osc, sout=so)
+            return so if fmt == "s" else f
         simt = lambda: ops.conv_d(x, k.w, k.b, k.cout, ksz, stride, dil, transposed, act, out=out)
         if "d" not in k.tc:
             return simt()
@@ -426,8 +456,15 @@ class TEMPORALSTEREO(nn.Module):
                                                               half=self.half_split, oscale=k.osc),
                                 "simt": simt})
 
-    def _deconv_hw(self, x, k: _Packed, ksz, act=None, out=None, single=False):
-        """Stride-2 transposed (1,k,k) / kxk conv: four tensor-core phase launches or the fp32 FMA kernel."""
+    def _deconv_hw(self, x, k: _Packed, ksz, act=None, out=None, single=False, fmt="f"):
+        """Stride-2 transposed (1,k,k) / kxk conv: four tensor-core phase launches or the fp32 FMA kernel.  S-format
+        operands as in `_hw3`."""
+        if isinstance(x, ops.Split) or fmt == "s":
+            h = 2 if (single and self.decoder_single_term) else 1
+            shp = tuple(x.shape)
+            so = self._new_split(shp[:1] + (k.cout,) + shp[2:-2] + (2 * shp[-2], 2 * shp[-1]), x) if fmt == "s" else None
+            f, _ = ops.deconv_hw_s(x, k.tc["dc"], k.b, k.cout, act, out=out, half=h, oscale=k.osc, sout=so)
+            return so if fmt == "s" else f
         simt = lambda: ops.deconv_hw(x, k.w, k.b, k.cout, ksz, act, out=out)
         if "dc" not in k.tc:
             return simt()
@@ -436,32 +473,37 @@ class TEMPORALSTEREO(nn.Module):
                           {"tc2": lambda: ops.deconv_hw_tc2(x, k.tc["dc"], k.b, k.cout, act, out=out, half=h, oscale=k.osc),
                            "simt": simt})
 
-    def _sep(self, x, p, stride=1, dil=1, act0="SiLU", act1="SiLU", out=None):
-        """'DepthwiseConv3D': (1,3,3) conv then (3,1,1) conv, BN folded (reference module.py:111-147)."""
+    def _sep(self, x, p, stride=1, dil=1, act0="SiLU", act1="SiLU", out=None, fmt="f"):
+        """'DepthwiseConv3D': (1,3,3) conv then (3,1,1) conv, BN folded (reference module.py:111-147).  In S-format mode
+        the intermediate never exists in fp32."""
         a, b = self._pk[p + ".conv.0"], self._pk[p + ".conv.1"]
-        y = self._hw3(x, a, stride, dil, act0)
-        return self._d(y, b, 3, stride, dil, False, act1, out=out)
+        y = self._hw3(x, a, stride, dil, act0, fmt="s" if self._sfmt() else "f")
+        return self._d(y, b, 3, stride, dil, False, act1, out=out, fmt=fmt)
 
-    def _sep_t(self, x, p):
+    def _sep_t(self, x, p, fmt="f"):
         """'DepthwiseConvTranspose3D' k3 s2 p1 op1, no activation (reference module.py:149-184)."""
         a, b = self._pk[p + ".conv.0"], self._pk[p + ".conv.1"]
-        y = self._deconv_hw(x, a, 3)
-        return self._d(y, b, 3, 2, 1, True, None)
+        y = self._deconv_hw(x, a, 3, fmt="s" if self._sfmt() else "f")
+        return self._d(y, b, 3, 2, 1, True, None, fmt=fmt)
 
     def _hourglass(self, x, p):
-        """ResidualBlock3D (reference module.py:271-297)."""
-        o = self._sep(x, p + ".conv1", stride=2)
-        pre = self._sep(o, p + ".conv2")
-        o = self._sep(pre, p + ".conv3", stride=2)
-        o = self._sep(o, p + ".conv4", act0=None, act1="SiLU")
+        """ResidualBlock3D (reference module.py:271-297).  S-format mode: `x` and the result are `ops.Split`s; only the
+        operands of the two resize + add + SiLU kernels exist in fp32."""
+        sf = self._sfmt()
+        m = "s" if sf else "f"
+        o = self._sep(x, p + ".conv1", stride=2, fmt=m)
+        pre = self._sep(o, p + ".conv2", fmt=m)
+        o = self._sep(pre, p + ".conv3", stride=2, fmt=m)
+        o = self._sep(o, p + ".conv4", act0=None, act1="SiLU", fmt=m)
         o = self._sep_t(o, p + ".conv5")
         sc = self._sep(pre, p + ".shortcut5", act0=None, act1=None)
         o = ops.resize_add_act(o, pre.shape[-3:], sc, "SiLU")
-        o = self._sep_t(o, p + ".conv6")
+        o = self._sep_t(ops.split_pack(o) if sf else o, p + ".conv6")
         sc = self._sep(x, p + ".shortcut6", act0=None, act1=None)
-        return ops.resize_add_act(o, x.shape[-3:], sc, "SiLU")
+        o = ops.resize_add_act(o, x.shape[-3:], sc, "SiLU")
+        return ops.split_pack(o) if sf else o
 
-    def _init3d(self, left, right, samples, p):
+    def _init3d(self, left, right, samples, p, out_fmt="f"):
         """block_cost -> init3d stack (reference coarse.py:82-83, fine.py:102-103, precise.py:88-90).  `samples` is the
         candidate tensor [B,S,H,W] (warp volume) or an int (shift volume).  With `fuse_cost` the raw volume is never
         materialised: group-wise terms (small side kernel) + the first (1,3,3) conv rebuilding the feature half."""
@@ -476,9 +518,9 @@ class TEMPORALSTEREO(nn.Module):
                 y = ops.cost_conv_warp(right, samples, g, addl, a.tc["cost"], a.b, a.cout, "SiLU", half=self.half_split, oscale=a.osc)
         else:
             y = self._hw3(ops.block_cost(left, right, samples), a, 1, 1, "SiLU")
-        y = self._d(y, b, 3, 1, 1, False, "SiLU")
+        y = self._d(y, b, 3, 1, 1, False, "SiLU", fmt="s" if self._sfmt() else "f")
         y = self._hourglass(y, p + ".1")
-        return self._sep(y, p + ".2", dil=2)
+        return self._sep(y, p + ".2", dil=2, fmt=out_fmt if self._sfmt() else "f")
 
     def _heads_predict(self, vol, samples, p, delta, want_top=False):
         st, fin = self._pk[p + ".stem"], self._pk[p + ".final"]
@@ -520,7 +562,7 @@ class TEMPORALSTEREO(nn.Module):
         c5 = self._pk[f"{lvl}.fuse.conv_5x5"]
         self._d(cat[:, :C], c5, 5, 1, 1, False, "SiLU", out=cat[:, C:2 * C])
         ops.pool5(cat[:, :C], cat[:, 2 * C:3 * C], cat[:, 3 * C:])
-        vol = self._sep(cat, f"{lvl}.fuse.conv_fuse", act0=None, act1=None)
+        vol = self._sep(cat, f"{lvl}.fuse.conv_fuse", act0=None, act1=None, fmt="s" if self._sfmt() else "f")
         disp, cost, off, _, _ = self._heads_predict(vol, samples, f"{lvl}.pred_heads", float(cfg["delta"]))
         m0, m3 = self._pk[f"{lvl}.convex_upsample.mask.0"], self._pk[f"{lvl}.convex_upsample.mask.3"]
         mfeat = self._hw3(left, m0, 1, 1, "SiLU")
@@ -646,7 +688,7 @@ class TEMPORALSTEREO(nn.Module):
         samples_p = torch.empty((B, 5, H4, W4), device=dev, dtype=torch.float32)
         centre = self._inject["fine_disp"].contiguous() if self._inject and "fine_disp" in self._inject else d_f
         low_f, high_f = ops.range_samples(centre, DISP_RANGE, samples_p, 0)
-        vol = self._init3d(lcat, rcat, samples_p, "precise.init3d")
+        vol = self._init3d(lcat, rcat, samples_p, "precise.init3d", out_fmt="s")
         d_p, c_p, o_p, top_disp, top_cost = self._heads_predict(vol, samples_p, "precise.pred_heads",
                                                                 float(self.levels["precise"]["delta"]), True)
         if sfmt:
