@@ -214,6 +214,12 @@ int tstereo_resize_add_act(const float* a, const float* skip, float* out,
                            int B, int C, int Da, int Ha, int Wa, int D, int H, int W,
                            int act, void* stream);
 
+/* The same operator writing the S-format (`tstereo_split`, declared with the tensor-core convolutions above)
+ * that the consumer convolution stages by TMA; values are the fp16 hi / lo split of tstereo_resize_add_act's result. */
+int tstereo_resize_add_act_s(const float* a, const float* skip, const tstereo_split* sout,
+                             int B, int C, int Da, int Ha, int Wa, int D, int H, int W,
+                             int act, void* stream);
+
 /* avg_pool3d and max_pool3d, kernel 5, stride 1, padding 2 (module.py:416-417).
  * x [B,C,D,H,W] view with strides; results written to two channel slices (strided views). D <= 24. */
 int tstereo_pool5(const float* x, long long xsB, long long xsC,

@@ -47,7 +47,8 @@ def timed(fns, reps=5):
 
 
 print(f"B = {B}; us per launch (graph replay, inputs rotate beyond L2)")
-print(f"{'layer':40s} {'fp32 in':>9s} {'S in':>9s} {'S in+out':>9s} {'S->S only':>9s}  MB(fp32 io)")
+MODES = [{}, {"TSTEREO_TC2_MT": "2"}, {"TSTEREO_TC2_MT": "2", "TSTEREO_TC2_WRES": "0"}, {"TSTEREO_TC2_WRES": "0"}]
+print(f"{'layer':40s} {'fp32 in':>9s} {'S->S':>9s} {'S->S mt2':>9s} {'mt2 nowr':>9s} {'nowres':>9s} {'S->S+f32':>9s}  MB(fp32 io)")
 for name, kind, Cin, Cout, mul, D, H, W, dil, act, half in SHAPES:
     gen = torch.Generator(device="cuda").manual_seed(0)
     Bn = B * mul
@@ -86,9 +87,15 @@ for name, kind, Cin, Cout, mul, D, H, W, dil, act, half in SHAPES:
     out = torch.empty(*oshp, device="cuda")
     so = ops.Split(Bn, Cout, D, Ho, Wo, parts, device="cuda", five=five)
     t0 = timed([(lambda x=x: f32(x, out)) for x in xs])
-    t1 = timed([(lambda s=s: sfn(s, out, None)) for s in ss])
+    cols = []
+    for env in MODES:
+        for k_ in ("TSTEREO_TC2_MT", "TSTEREO_TC2_WRES"):
+            os.environ.pop(k_, None)
+        os.environ.update(env)
+        cols.append(timed([(lambda s=s: sfn(s, None, so)) for s in ss]))
+    for k_ in ("TSTEREO_TC2_MT", "TSTEREO_TC2_WRES"):
+        os.environ.pop(k_, None)
     t2 = timed([(lambda s=s: sfn(s, out, so)) for s in ss])
-    t3 = timed([(lambda s=s: sfn(s, None, so)) for s in ss])
     same = torch.equal(f32(xs[0], torch.empty_like(out)), sfn(ss[0], torch.empty_like(out), None)[0])
     mb = (xs[0].numel() + out.numel()) * 4 / 1e6
-    print(f"{name:40s} {t0:9.1f} {t1:9.1f} {t2:9.1f} {t3:9.1f}  {mb:8.1f}  {'bit-identical' if same else 'DIFFERENT'}", flush=True)
+    print(f"{name:40s} {t0:9.1f} " + " ".join(f"{c:9.1f}" for c in cols) + f" {t2:9.1f}  {mb:8.1f}  {'bit-identical' if same else 'DIFFERENT'}", flush=True)

@@ -46,6 +46,7 @@ SIGNATURES = {
     "tstereo_deconv_hw": (I, [P, LL, LL, LL, P, LL, LL, LL, P, P, I, I, I, I, I, I, I, I, P]),
     "tstereo_copy_planes": (I, [P, P, LL, LL, I, I, I, P]),
     "tstereo_resize_add_act": (I, [P, P, P, I, I, I, I, I, I, I, I, I, P]),
+    "tstereo_resize_add_act_s": (I, [P, P, P, I, I, I, I, I, I, I, I, I, P]),
     "tstereo_pool5": (I, [P, LL, LL, P, P, LL, LL, I, I, I, I, I, P]),
     "tstereo_merge_memory": (I, [P, P, P, P, P, P, P, LL, LL, P, I, I, I, I, I, I, P]),
     "tstereo_heads": (I, [P, P, P, P, I, I, I, I, I, F, P]),

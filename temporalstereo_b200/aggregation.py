@@ -497,11 +497,11 @@ class TEMPORALSTEREO(nn.Module):
         o = self._sep(o, p + ".conv4", act0=None, act1="SiLU", fmt=m)
         o = self._sep_t(o, p + ".conv5")
         sc = self._sep(pre, p + ".shortcut5", act0=None, act1=None)
-        o = ops.resize_add_act(o, pre.shape[-3:], sc, "SiLU")
-        o = self._sep_t(ops.split_pack(o) if sf else o, p + ".conv6")
+        raa = ops.resize_add_act_s if sf else ops.resize_add_act
+        o = raa(o, pre.shape[-3:], sc, "SiLU")
+        o = self._sep_t(o, p + ".conv6")
         sc = self._sep(x, p + ".shortcut6", act0=None, act1=None)
-        o = ops.resize_add_act(o, x.shape[-3:], sc, "SiLU")
-        return ops.split_pack(o) if sf else o
+        return raa(o, x.shape[-3:], sc, "SiLU")
 
     def _init3d(self, left, right, samples, p, out_fmt="f"):
         """block_cost -> init3d stack (reference coarse.py:82-83, fine.py:102-103, precise.py:88-90).  `samples` is the
@@ -633,6 +633,7 @@ class TEMPORALSTEREO(nn.Module):
         single = self.decoder_single_term
         if sfmt:        # allocated on the main stream (like lrcat): the decoder reads them there after the encoder's event
             H2, W2 = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+            s_img = ops.Split(2 * B, left_image.shape[1], 1, H, W, 2, device=dev, five=False)
             s_half2 = ops.Split(2 * B, c2, 1, H2, W2, 2, device=dev, five=False)
             s_cat2 = ops.Split(2 * B, 2 * c2, 1, H2, W2, 2, device=dev, five=False)
             s_q = ops.Split(2 * B, c4, 1, H4, W4, 2, device=dev, five=False)
@@ -645,9 +646,12 @@ class TEMPORALSTEREO(nn.Module):
                 # 1/4-scale features of the precise cost volume).  s_cat2 = [deconv4 output | conv2.1 output] is the
                 # decoder's concat buffer, s_lcat = [left backbone features | left conv4.1 output] the input of fuse.0
                 pk = self._pk
+                # the two images meet in one 2B batch of S-format pixels (3 channels + 5 zeros per 16-byte vector), so
+                # conv2.0 is ONE TMA-fed launch instead of two register-producer launches over strided fp32 loads
+                ops.split_pack(left_image, out=s_img.batches(0, B))
+                ops.split_pack(right_image, out=s_img.batches(B, 2 * B))
                 k = pk[r + ".conv2.0"]
-                ops.conv_hw3s2_s(left_image, k.tc["s2"], k.b, k.cout, "ReLU", oscale=k.osc, sout=s_half2.batches(0, B))
-                ops.conv_hw3s2_s(right_image, k.tc["s2"], k.b, k.cout, "ReLU", oscale=k.osc, sout=s_half2.batches(B, 2 * B))
+                ops.conv_hw3s2_s(s_img, k.tc["s2"], k.b, k.cout, "ReLU", oscale=k.osc, sout=s_half2)
                 k = pk[r + ".conv2.1"]
                 ops.conv_hw3_s(s_half2, k.tc["hw3"], k.b, k.cout, 1, "ReLU", oscale=k.osc, sout=s_cat2.channels(c2, 2 * c2))
                 k = pk[r + ".conv4.0"]

@@ -1,6 +1,7 @@
 // Shared helpers for libtstereo.so kernels (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <cstdint>
 #include <cstdio>
 #include <cstdarg>
 #include "../../include/tstereo.h"
@@ -53,6 +54,25 @@ __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// ---- S-format (fp16 hi / lo split, include/tstereo.h `tstereo_split`) helpers
+// two floats -> packed fp16x2 (low half = a).  satfinite: a value beyond the fp16 range clamps to +-65504 (and its
+// lo part likewise) instead of turning the whole accumulation into inf - inf = NaN
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t h) {
+    float2 f;
+    asm("{\n\t.reg .b16 l, u;\n\tmov.b32 {l, u}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, u;\n\t}" : "=f"(f.x), "=f"(f.y) : "r"(h));
+    return f;
+}
+
+__device__ __forceinline__ void stg128(void* ptr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 
 // ATen's align_corners source index: scale = (in-1)/(out-1) in float, src = scale*dst
 // (aten/src/ATen/native/UpSample.h area_pixel_compute_scale / guard_index_and_lambda).

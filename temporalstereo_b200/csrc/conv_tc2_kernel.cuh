@@ -73,6 +73,7 @@ constexpr int NPROD = 256;
 constexpr int NTHREADS = NPROD + 32;
 constexpr int nthreads(int raw) { return NPROD + 32 + (raw == 3 ? 32 : 0); }   // SPLIT: one more warp issues the TMA boxes
 constexpr int MAX_STAGES = 8;
+constexpr int BAR_BYTES = 640;   // barriers + TMEM slot (<= 384 B) + the CTA's bias / output-scale vectors (2 x 32 floats)
 constexpr int MAX_MT = 4;
 constexpr size_t SMEM_MAX = 227 * 1024;
 
@@ -119,6 +120,7 @@ struct Params {
     // (hi, lo), s_sx = 2: the four parity phases of a stride-2 conv through the map's element strides.  Output (any
     // instance): `outs` != null -> the epilogue also (or only: out == null) writes the split result for batches < s_nb.
     int s_in, s_sx;
+    int wres;                     // SPLIT, resident CTAs: the whole weight image (nmma chunks) is loaded into shared memory once
     unsigned short* outs;
     long long ossB, ossD, ossP, ossC8;
     int s_parts, s_nb;
@@ -137,19 +139,6 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint
 }
 // instruction descriptor: D fp32, A/B fp16, both K-major, M = 128, N = n
 __host__ __device__ constexpr uint32_t idesc_f16(uint32_t n) { return (1u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24); }
-// two floats -> packed fp16x2 (low half = a).  satfinite: a value beyond the fp16 range clamps to +-65504 (and its
-// lo part likewise) instead of turning the whole accumulation into inf - inf = NaN
-__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
-    uint32_t r;
-    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
-    return r;
-}
-__device__ __forceinline__ float2 unpack_h2(uint32_t h) {
-    float2 f;
-    asm("{\n\t.reg .b16 l, u;\n\tmov.b32 {l, u}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, u;\n\t}" : "=f"(f.x), "=f"(f.y) : "r"(h));
-    return f;
-}
-
 // Activation of the epilogue, compile-time selected (the epilogue is instruction-bound).  SiLU uses
 // ex2.approx / rcp.approx (~1e-6 relative); the full-precision expf + IEEE division of silu_f cost ~50
 // instructions per output.
@@ -176,10 +165,6 @@ struct EpiOut {
     long long so_c8;          // element stride between 8-channel chunks
     bool sok;                 // this lane writes the S-format (position inside the image, batch < s_nb)
 };
-__device__ __forceinline__ void stg128(void* ptr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-
 // kx shift-sum + bias + activation + store of 8 channels of one tile row (lane = tile column):
 // out[x] = P0[x] + P1[x + dil] + P2[x + 2*dil]
 // FOLD = 3: the kx taps are columns of the accumulator (3x3 convs); FOLD = 1: one column block (the 1x1 / (k,1,1) form)
@@ -187,6 +172,12 @@ template <int ACT, int FOLD>
 __device__ __forceinline__ void epi_store8(const float (&a0)[8], const float (&a1)[8], const float (&a2)[8], int dil, const EpiOut& eo,
                                            int c0, const float* bias, int Cout, bool ok, const float* osc,
                                            const float* add = nullptr, int asC = 0) {
+    // bias / osc: the CTA's shared-memory copies (zero / one padded to 32 channels)
+    float bv[8], sv[8];
+    *reinterpret_cast<float4*>(bv) = *reinterpret_cast<const float4*>(bias + c0);
+    *reinterpret_cast<float4*>(bv + 4) = *reinterpret_cast<const float4*>(bias + c0 + 4);
+    *reinterpret_cast<float4*>(sv) = *reinterpret_cast<const float4*>(osc + c0);
+    *reinterpret_cast<float4*>(sv + 4) = *reinterpret_cast<const float4*>(osc + c0 + 4);
     float res[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
@@ -196,11 +187,14 @@ __device__ __forceinline__ void epi_store8(const float (&a0)[8], const float (&a
             acc += __shfl_down_sync(0xffffffffu, a2[c], 2 * dil);
         }
         const bool live = ok && c0 + c < Cout;
-        const bool cok = c0 + c < Cout;
-        float pre = fmaf(acc, (osc && cok) ? __ldg(osc + c0 + c) : 1.f, cok ? __ldg(bias + c0 + c) : 0.f);
+        float pre = fmaf(acc, sv[c], bv[c]);
         if (add) pre += live ? __ldg(add + (long long)(c0 + c) * asC) : 0.f;
         res[c] = act_t<ACT>(pre);
-        if (eo.o && live) eo.o[(c0 + c) * eo.osC] = res[c];
+    }
+    if (eo.o) {                 // warp-uniform branch: an S-format-only layer skips the eight predicated stores and their address math
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            if (ok && c0 + c < Cout) eo.o[(c0 + c) * eo.osC] = res[c];
     }
     if (eo.so && c0 < Cout) {   // the S-format of this 8-channel chunk (chunks beyond Cout do not exist in the output): hi = fp16(x), lo = fp16(x - hi); padding channels are 0
         uint32_t hi[4];
@@ -298,17 +292,23 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap, const 
     const uint32_t NPOS = (uint32_t)SR * 32u;
     // [part 2][khalf 2][NPOS][16 B]; the single-term SPLIT form stages the hi part only
     const uint32_t a_bytes = ((SPLIT && p.terms != 3) ? 2u : 4u) * NPOS * 16u;
-    const uint32_t stage_bytes = a_bytes + C::B_BYTES;
     const uint32_t b_bytes = (uint32_t)p.nky * (C::B_BYTES / 3u);   // weight bytes of one chunk actually used
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    const bool wres = SPLIT && p.wres;                              // weights resident: a stage holds the A operand only
+    const uint32_t stage_bytes = a_bytes + (wres ? 0u : C::B_BYTES);
+    const int nmma_w = (p.nchunk + 1) / 2;
+    uint8_t* wbase = smem + (size_t)p.stages * stage_bytes;         // [nmma][b_bytes] when resident
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wbase + (wres ? (size_t)nmma_w * b_bytes : 0));
     uint64_t* full = bars;                         // [stages]  producers -> MMA
     uint64_t* empty = bars + MAX_STAGES;           // [stages]  MMA -> producers
     uint64_t* acc_full = bars + 2 * MAX_STAGES;    // [MT]      MMA -> readers (a group of G chunks accumulated)
     uint64_t* acc_empty = acc_full + MAX_MT;       // [MT]      readers -> MMA (M-tile drained)
     uint64_t* raw_full = acc_empty + MAX_MT;       // [rs]      TMA -> producers (raw fp32 chunk landed)
     uint64_t* raw_empty = raw_full + MAX_RS;       // [rs]      producers -> TMA issuer (raw stage read)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + MAX_RS);
-    uint8_t* raw_base = reinterpret_cast<uint8_t*>(bars) + 384;    // TMA variant: [rs][c 8][row SR][x bw] fp32
+    uint64_t* wfull = raw_empty + MAX_RS;          // resident weights landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
+    float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 384);   // [32] bias, 0 beyond Cout
+    float* s_osc = s_bias + 32;                                                         // [32] accumulator scale, 1 when absent
+    uint8_t* raw_base = reinterpret_cast<uint8_t*>(bars) + BAR_BYTES;    // TMA variant: [rs][c 8][row SR][x bw] fp32
     const uint32_t raw_bytes = 32u * (uint32_t)p.bw * (uint32_t)SR;   // p.bw = 32 for the cp.async ring
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -333,6 +333,13 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap, const 
     };
     set_tile(t_first);
 
+    // the epilogue's per-channel constants, staged once: 16 predicated scalar loads per 8 channels and output row (each with
+    // its descriptor re-materialisation: ncu r02, ~20 of the epilogue's ~47 instructions per channel) become four LDS.128
+    if (tid < 32) {
+        const bool cok = tid < p.Cout;
+        s_bias[tid] = cok ? __ldg(p.bias + tid) : 0.f;
+        s_osc[tid] = (cok && p.oscale) ? __ldg(p.oscale + tid) : 1.f;
+    }
     if (tid == 0) {
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(&full[s], SPLIT ? 1 : NPROD + 1);
@@ -350,6 +357,7 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap, const 
         }
         if constexpr (CPA)
             for (int i = 0; i < p.rs; ++i) mbar_init(&raw_full[i], NPROD);    // one cp.async arrival per producer thread
+        if constexpr (SPLIT) mbar_init(wfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == NPROD / 32) {
@@ -798,9 +806,9 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap, const 
                     mbar_wait(&acc_full[j], it & 1u);
                     tc_fence_after();
                     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(j * C::TS);
-                    if (p.act == TSTEREO_ACT_SILU) epi_direct<TSTEREO_ACT_SILU, CP, FOLD>(taddr, p.dil, eo, p.bias, p.Cout, ok, p.oscale);
-                    else if (p.act == TSTEREO_ACT_RELU) epi_direct<TSTEREO_ACT_RELU, CP, FOLD>(taddr, p.dil, eo, p.bias, p.Cout, ok, p.oscale);
-                    else epi_direct<TSTEREO_ACT_NONE, CP, FOLD>(taddr, p.dil, eo, p.bias, p.Cout, ok, p.oscale);
+                    if (p.act == TSTEREO_ACT_SILU) epi_direct<TSTEREO_ACT_SILU, CP, FOLD>(taddr, p.dil, eo, s_bias, p.Cout, ok, s_osc);
+                    else if (p.act == TSTEREO_ACT_RELU) epi_direct<TSTEREO_ACT_RELU, CP, FOLD>(taddr, p.dil, eo, s_bias, p.Cout, ok, s_osc);
+                    else epi_direct<TSTEREO_ACT_NONE, CP, FOLD>(taddr, p.dil, eo, s_bias, p.Cout, ok, s_osc);
                     if constexpr (MULTI) {                 // M-tile j of the accumulator is free for the next tile's MMAs
                         tc_fence_before();
                         mbar_arrive(&acc_empty[j]);
@@ -809,9 +817,9 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap, const 
                     const float* ad = nullptr;
                     if constexpr (FUSE == 1)
                         if (p.add) ad = p.add + (long long)b * p.asB + (long long)min(y, p.H - 1) * p.W + min(x, p.W - 1);
-                    if (p.act == TSTEREO_ACT_SILU) epi_acc<TSTEREO_ACT_SILU, CP, FOLD>(acc[jj], p.dil, eo, p.bias, p.Cout, ok, p.oscale, ad, p.asC);
-                    else if (p.act == TSTEREO_ACT_RELU) epi_acc<TSTEREO_ACT_RELU, CP, FOLD>(acc[jj], p.dil, eo, p.bias, p.Cout, ok, p.oscale, ad, p.asC);
-                    else epi_acc<TSTEREO_ACT_NONE, CP, FOLD>(acc[jj], p.dil, eo, p.bias, p.Cout, ok, p.oscale, ad, p.asC);
+                    if (p.act == TSTEREO_ACT_SILU) epi_acc<TSTEREO_ACT_SILU, CP, FOLD>(acc[jj], p.dil, eo, s_bias, p.Cout, ok, s_osc, ad, p.asC);
+                    else if (p.act == TSTEREO_ACT_RELU) epi_acc<TSTEREO_ACT_RELU, CP, FOLD>(acc[jj], p.dil, eo, s_bias, p.Cout, ok, s_osc, ad, p.asC);
+                    else epi_acc<TSTEREO_ACT_NONE, CP, FOLD>(acc[jj], p.dil, eo, s_bias, p.Cout, ok, s_osc, ad, p.asC);
                 }
             }
         }
@@ -829,6 +837,7 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap, const 
         uint32_t ph = 0;
         if constexpr (TMA)
             for (int i = 0; i < p.rs && i < p.nchunk; ++i) issue_tma();
+        if (wres) mbar_wait(wfull, 0u);
         uint32_t it = 0;                 // tiles finished (MULTI): parity of acc_empty
         for (int t = t_first; t < T; t += t_stride, ++it)
         for (int k = 0; k < nmma; ++k) {
@@ -840,7 +849,7 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap, const 
             // descriptor start-address field is (addr >> 4): offsets add directly (no carry out of its 14 bits)
             const uint64_t a_hi = make_desc(st_base, a_lbo, 128u);
             const uint64_t a_lo = make_desc(st_base + 2u * NPOS * 16u, a_lbo, 128u);
-            const uint64_t b_d = make_desc(st_base + a_bytes, b_lbo, 128u);
+            const uint64_t b_d = make_desc(wres ? smem_u32(wbase) + (uint32_t)k * b_bytes : st_base + a_bytes, b_lbo, 128u);
 #pragma unroll 1
             for (int j = 0; j < MT; ++j) {
                 if (!DIRECT && first && g >= 1) {
@@ -897,14 +906,21 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap, const 
         const int nparts = p.terms == 3 ? 2 : 1;
         int s = 0;
         uint32_t ph = 0;
+        if (wres && t_first < T) {
+            if (elect_one()) {
+                mbar_arrive_expect_tx(wfull, (uint32_t)nmma * b_bytes);
+                for (int k = 0; k < nmma; ++k) bulk_g2s(wbase + (size_t)k * b_bytes, p.wpack + (size_t)k * (b_bytes / 4), b_bytes, wfull);
+            }
+            __syncwarp();
+        }
         for (int t = t_first; t < T; t += t_stride) {
             set_tile(t);
             for (int k = 0; k < nmma; ++k) {
                 mbar_wait(&empty[s], ph ^ 1u);
                 if (elect_one()) {
                     uint8_t* st_base = smem + (size_t)s * stage_bytes;
-                    mbar_arrive_expect_tx(&full[s], 2u * (uint32_t)nparts * unit_bytes + b_bytes);
-                    bulk_g2s(st_base + a_bytes, p.wpack + (size_t)k * (b_bytes / 4), b_bytes, &full[s]);
+                    mbar_arrive_expect_tx(&full[s], 2u * (uint32_t)nparts * unit_bytes + (wres ? 0u : b_bytes));
+                    if (!wres) bulk_g2s(st_base + a_bytes, p.wpack + (size_t)k * (b_bytes / 4), b_bytes, &full[s]);
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const int u = 2 * k + h;            // 8-channel unit = K half h of MMA chunk k
@@ -956,8 +972,9 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap, const 
     }
 }
 
-static size_t smem_need(int stages, int SR, int N, int rs = 0, int bw = 36, int a_units = 4) {
-    return (size_t)stages * ((size_t)SR * 512 * a_units + (size_t)192 * N) + 384 + (size_t)rs * 32 * bw * SR;
+static size_t smem_need(int stages, int SR, int N, int rs = 0, int bw = 36, int a_units = 4, size_t wres_bytes = 0) {
+    return (size_t)stages * ((size_t)SR * 512 * a_units + (wres_bytes ? 0 : (size_t)192 * N)) + wres_bytes + BAR_BYTES +
+           (size_t)rs * 32 * bw * SR;
 }
 
 static int env_int(const char* name, int dflt);
@@ -1116,13 +1133,18 @@ static int launch(Params& p, int CP, int planes, cudaStream_t st, const char* wh
     // Measured on B200: no gain on the small hourglass layers (they sit at the fixed launch + prologue + epilogue cost,
     // ~10 us) and 5-20 % slower on the large ones (one more shared-memory round trip), so it is not the default.
     const int cpa_env = (FUSE == 0 && !split) ? env_int("TSTEREO_TC2_CPA", 0) : 0;
-    int best_mt = 0, best_stages = 0, best_rs = 0;
-    bool best_cpa = false;
+    int best_mt = 0, best_stages = 0, best_rs = 0, best_minb = 2;
+    bool best_cpa = false, best_wres = false;
+    // SPLIT + DIRECT (resident CTAs walking many tiles): keep the whole weight image in shared memory when that leaves
+    // room for >= 3 operand stages — the per-tile weight reload is otherwise 30-65 % of the L2 -> SM traffic
+    const size_t wres_bytes = (split && direct && env_int("TSTEREO_TC2_WRES", 1)) ? (size_t)nmma * p.nky * 64 * N : 0;
     double best_cost = 1e30;
     const int forced = env_int("TSTEREO_TC2_MT", 0);
     for (int mt = 2; mt <= 4; mt += 2) {
         const int cols = mt * (direct ? N2 : 2 * N);
-        if (cols > 512 || (CP == 32 && mt == 4 && fold == 3)) continue;   // no (32, 4) instance of the kx-folded form
+        // no (32, 4) instance of the kx-folded form: one CTA per SM (384 TMEM columns) measured slower than two CTAs of (32, 2)
+        // in every producer mode (SPLIT: 141 vs 129 us on the UNet 32 -> 32 conv) — the epilogue needs the second CTA's warps
+        if (cols > 512 || (CP == 32 && mt == 4 && fold == 3)) continue;
         if (forced && mt != forced) continue;
         // fused cost producer: the (16, 4) instance needs 168 registers (one CTA per SM) and loses to two CTAs of (16, 2)
         // on the gather latency (fine level, B200: 295 vs 200 us)
@@ -1150,6 +1172,15 @@ static int launch(Params& p, int CP, int planes, cudaStream_t st, const char* wh
                     break;
                 }
         }
+        bool wres = false;
+        if (!stages && wres_bytes) {
+            for (int s = MAX_STAGES; s >= 3; --s)
+                if (smem_need(s, SR, N, 0, 36, a_units, wres_bytes) <= budget) {
+                    stages = s;
+                    wres = true;
+                    break;
+                }
+        }
         if (!stages) {
             rs = 0;
             for (int s = split ? MAX_STAGES : 4; s >= 2; --s)
@@ -1167,6 +1198,8 @@ static int launch(Params& p, int CP, int planes, cudaStream_t st, const char* wh
             best_stages = stages;
             best_rs = rs;
             best_cpa = cpa && rs > 0;
+            best_wres = wres;
+            best_minb = minb;
         }
     }
     TS_REQUIRE(best_mt > 0, "%s: no tile configuration for Cout<=%d", what, CP);
@@ -1174,6 +1207,7 @@ static int launch(Params& p, int CP, int planes, cudaStream_t st, const char* wh
     TS_REQUIRE(p.bias, "%s: zero-bias buffer unavailable", what);
     p.stages = best_stages;
     p.rs = best_rs;
+    p.wres = best_wres;
     const int SR = 4 * best_mt + 2 * p.dil;
     const bool tma = best_rs > 0 && !best_cpa;
     if (best_cpa) p.bw = 32;
@@ -1187,7 +1221,7 @@ static int launch(Params& p, int CP, int planes, cudaStream_t st, const char* wh
                        (p.terms != 3 || make_tmap_s(*sin, 1, p.nbatch, Dm, p.Hin, p.Win, SR, p.s_sx, &tm2)),
                    "%s: the S-format input is not expressible as a TMA view (alignment / strides)", what);
     }
-    const size_t smem_bytes = smem_need(p.stages, SR, N, p.rs, p.bw, a_units);   // p.bw = 32 for the cp.async ring
+    const size_t smem_bytes = smem_need(p.stages, SR, N, p.rs, p.bw, a_units, best_wres ? wres_bytes : 0);   // p.bw = 32 for the cp.async ring
     p.tiles_y = (p.H + 4 * best_mt - 1) / (4 * best_mt);
     p.nplanes = planes;
     dim3 grid(p.tiles_x * p.tiles_y, planes);
@@ -1196,7 +1230,7 @@ static int launch(Params& p, int CP, int planes, cudaStream_t st, const char* wh
     const bool multi = FUSE == 0 && direct && !tma && !best_cpa;   // register producer or SPLIT
     if (multi) {
         const long long T = (long long)grid.x * planes;
-        const long long want = (long long)148 * 2 * (env_int("TSTEREO_TC2_PERSIST", 1) > 0 ? env_int("TSTEREO_TC2_PERSIST", 1) : 1);
+        const long long want = (long long)148 * best_minb * (env_int("TSTEREO_TC2_PERSIST", 1) > 0 ? env_int("TSTEREO_TC2_PERSIST", 1) : 1);
         p.persist = env_int("TSTEREO_TC2_PERSIST", 1) != 0;
         TS_REQUIRE(T < (1ll << 31), "%s: too many tiles", what);
         grid = dim3((unsigned)((p.persist && T > want) ? want : T), 1);
@@ -1272,14 +1306,17 @@ inline int run_groups(tc2::Params p, int Cout, int planes, cudaStream_t st, cons
     unsigned short* outs = p.outs;
     for (int c0 = 0; c0 < Cout; c0 += 32) {
         const int cg = Cout - c0 < 32 ? Cout - c0 : 32;
-        p.Cout = cg;
-        p.wpack = wp;
-        p.bias = bias ? bias + c0 : nullptr;
-        p.oscale = oscale ? oscale + c0 : nullptr;
-        p.out = out ? out + (long long)c0 * p.osC : nullptr;
-        p.outs = outs ? outs + (long long)(c0 / 8) * p.ossC8 : nullptr;
-        if (p.add) p.add += (c0 ? 32ll * p.asC : 0ll);
-        const int rc = tc2::launch<FUSE>(p, tc2_cp(cg), planes, st, what, sin);
+        // a fresh copy per group: launch() rewrites fields (G halves for the fp16 split, tile / stage choices) — reusing
+        // one Params made the second group of a 64-channel layer fall out of the DIRECT form (G 8 -> 4 -> 2)
+        tc2::Params q = p;
+        q.Cout = cg;
+        q.wpack = wp;
+        q.bias = bias ? bias + c0 : nullptr;
+        q.oscale = oscale ? oscale + c0 : nullptr;
+        q.out = out ? out + (long long)c0 * p.osC : nullptr;
+        q.outs = outs ? outs + (long long)(c0 / 8) * p.ossC8 : nullptr;
+        if (p.add) q.add = p.add + (long long)c0 * p.asC;
+        const int rc = tc2::launch<FUSE>(q, tc2_cp(cg), planes, st, what, sin);
         if (rc != TSTEREO_OK) return rc;
         wp += group_floats(p.half ? (p.nchunk + 1) / 2 : p.nchunk, cg, p.nky, p.fold == 1 ? 1 : 3);
     }

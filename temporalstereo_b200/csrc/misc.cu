@@ -63,6 +63,58 @@ resize_add_act_kernel(const float* __restrict__ a, const float* __restrict__ ski
     }
 }
 
+// The same operator writing the S-format (fp16 hi / lo split) its consumer convolution stages by TMA: thread = one output
+// (y, x) of one (b, 8-channel chunk); it walks the D planes and the chunk's 8 channels (each channel's loads are
+// coalesced across the warp) and stores the two 16-byte vectors of the position.
+__global__ void __launch_bounds__(128)
+resize_add_act_s_kernel(const float* __restrict__ a, const float* __restrict__ skip, unsigned short* __restrict__ so,
+                        long long sB, long long sD, long long sP, long long sC8, int parts, int C,
+                        int Da, int Ha, int Wa, int D, int H, int W, float sd, float sy, float sx, int act) {
+    const int pix = blockIdx.x * 128 + threadIdx.x;
+    const int C8 = (C + 7) >> 3;
+    const int b = blockIdx.y / C8, c8 = blockIdx.y - b * C8;
+    if (pix >= H * W) return;
+    const int y = pix / W, x = pix - y * W;
+    const LerpIdx iy = ac_index(sy, y, Ha);
+    const LerpIdx ix = ac_index(sx, x, Wa);
+    const size_t pl = (size_t)Ha * Wa, HW = (size_t)H * W;
+    const int o00 = iy.i0 * Wa + ix.i0, o01 = iy.i0 * Wa + ix.i1, o10 = iy.i1 * Wa + ix.i0, o11 = iy.i1 * Wa + ix.i1;
+    const int nc = min(8, C - c8 * 8);
+    const float* pa = a + ((size_t)b * C + (size_t)c8 * 8) * Da * pl;
+    const float* ps = skip ? skip + ((size_t)b * C + (size_t)c8 * 8) * D * HW + pix : nullptr;
+    unsigned short* dst = so + b * sB + c8 * sC8 + (long long)pix * 8;
+    for (int d = 0; d < D; ++d) {
+        const LerpIdx id = ac_index(sd, d, Da);         // warp-uniform
+        float v[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            v[c] = 0.f;
+            if (c < nc) {
+                const float* p = pa + (size_t)c * Da * pl;
+                auto plane = [&](int dd) {
+                    const float* q = p + dd * pl;
+                    const float t0 = ix.w0 * __ldg(q + o00) + ix.w1 * __ldg(q + o01);
+                    const float t1 = ix.w0 * __ldg(q + o10) + ix.w1 * __ldg(q + o11);
+                    return iy.w0 * t0 + iy.w1 * t1;
+                };
+                float r = id.w0 * plane(id.i0);
+                if (id.w1 != 0.f) r += id.w1 * plane(id.i1);
+                if (ps) r += __ldg(ps + ((size_t)c * D + d) * HW);
+                v[c] = apply_act(r, act);
+            }
+        }
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            hi[j] = pack_h2(v[2 * j], v[2 * j + 1]);
+            const float2 hf = unpack_h2(hi[j]);
+            lo[j] = pack_h2(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
+        }
+        stg128(dst + d * sD, hi[0], hi[1], hi[2], hi[3]);
+        if (parts == 2) stg128(dst + d * sD + sP, lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
 // --------------------------------------------------------------------------- 5x5x5 avg + max pooling
 // CTA = one (b, c) and an 8 x 32 tile of (H, W); it walks all D planes once.  Per plane: halo tile
 // -> shared, horizontal 5-tap pass -> shared, vertical 5-tap pass -> registers; a 5-deep register
@@ -520,6 +572,22 @@ int tstereo_resize_add_act(const float* a, const float* skip, float* out, int B,
     resize_add_act_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a, skip, out, Da, Ha, Wa, D, H, W, scale(Da, D), scale(Ha, H),
                                                                   scale(Wa, W), act);
     return check_launch("resize_add_act");
+}
+
+int tstereo_resize_add_act_s(const float* a, const float* skip, const tstereo_split* sout, int B, int C, int Da, int Ha, int Wa,
+                             int D, int H, int W, int act, void* stream) {
+    TS_REQUIRE(a && sout && sout->ptr, "resize_add_act_s: null pointer");
+    TS_REQUIRE(B > 0 && C > 0 && Da > 0 && Ha > 0 && Wa > 0 && D > 0 && H > 0 && W > 0, "resize_add_act_s: bad sizes");
+    TS_REQUIRE((long long)B * ((C + 7) / 8) <= 65535 && (long long)H * W < (1ll << 28), "resize_add_act_s: grid too large");
+    TS_REQUIRE((sout->parts == 1 || sout->parts == 2) && sout->C8 >= (C + 7) / 8, "resize_add_act_s: bad S-format output");
+    TS_REQUIRE((((size_t)sout->ptr) & 15) == 0 && (sout->sB & 7) == 0 && (sout->sD & 7) == 0 && (sout->sP & 7) == 0 && (sout->sC8 & 7) == 0,
+               "resize_add_act_s: S-format output must be 16-byte aligned");
+    auto scale = [](int in_size, int out_size) { return out_size > 1 ? (float)(in_size - 1) / (float)(out_size - 1) : 0.0f; };
+    dim3 grid(cdiv(H * W, 128), B * ((C + 7) / 8));
+    resize_add_act_s_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a, skip, (unsigned short*)sout->ptr, sout->sB, sout->sD, sout->sP,
+                                                                    sout->sC8, sout->parts, C, Da, Ha, Wa, D, H, W, scale(Da, D),
+                                                                    scale(Ha, H), scale(Wa, W), act);
+    return check_launch("resize_add_act_s");
 }
 
 int tstereo_pool5(const float* x, long long xsB, long long xsC, float* avg, float* mx, long long osB, long long osC,

@@ -597,6 +597,19 @@ def resize_add_act(a: torch.Tensor, size, skip: Optional[torch.Tensor] = None, a
     return out
 
 
+def resize_add_act_s(a: torch.Tensor, size, skip: Optional[torch.Tensor] = None, act=None, parts: int = 2) -> "Split":
+    """`resize_add_act` with the result in S-format (the operand layout of the TMA-fed convolutions)."""
+    _chk(a, skip)
+    B, Cc, Da, Ha, Wa = a.shape
+    D, H, W = size
+    out = Split(B, Cc, D, H, W, parts, device=a.device)
+    if skip is not None:
+        assert tuple(skip.shape) == out.shape
+    keep, ref = _sref(out)
+    _lib.call("tstereo_resize_add_act_s", _p(a), _p(skip), ref, B, Cc, Da, Ha, Wa, D, H, W, ACT[act], _stream())
+    return out
+
+
 def pool5(x: torch.Tensor, avg: torch.Tensor, mx: torch.Tensor) -> None:
     """avg_pool3d / max_pool3d, kernel 5, stride 1, padding 2, written into two views (module.py:416-417)."""
     B, Cc, D, H, W = x.shape

@@ -231,3 +231,16 @@ def test_split_rejects_bad_arguments(ops):
         ops.conv_hw3_s(x, wp, None, 8, 1, None, sout=ops.Split(1, 8, 1, 8, 15, 2, device="cuda", five=False))
     with pytest.raises(TStereoError):       # S-format input needs the fp16 split
         ops.conv_hw3_s(ops.split_pack(x), wp, None, 8, 1, None, half=0)
+
+
+@pytest.mark.parametrize("src,dst,C", [((6, 18, 30), (6, 17, 30), 64), ((4, 10, 16), (3, 9, 15), 8), ((6, 18, 30), (5, 17, 30), 12),
+                                       ((2, 5, 7), (2, 5, 7), 16)])
+@pytest.mark.parametrize("parts", [1, 2])
+def test_resize_add_act_s(ops, src, dst, C, parts):
+    """resize + add + SiLU writing S-format == split_pack of the fp32 operator's result (bit for bit)."""
+    a = rnd(2, C, *src, seed=181).cuda()
+    skip = rnd(2, C, *dst, seed=182).cuda()
+    want = ops.split_pack(ops.resize_add_act(a, dst, skip, "SiLU"), parts)
+    got = ops.resize_add_act_s(a, dst, skip, "SiLU", parts)
+    same_split(got, want, "resize_add_act_s")
+    same_split(ops.resize_add_act_s(a, dst, None, None, parts), ops.split_pack(ops.resize_add_act(a, dst, None, None), parts), "no skip")
