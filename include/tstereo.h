@@ -80,6 +80,21 @@ int tstereo_cost_conv_shift(const float* left, const float* right, const float* 
                             const float* wpack, const float* bias, const float* oscale,
                             int B, int C, int Cout, int D, int H, int W, int act, int half, void* stream);
 
+/* "Tap projection" form of the warp levels' first conv (the engine's default for the fine / precise levels, round 2).
+ * The warp is a per-position lerp of two columns of R, the same for every channel, so the channel contraction commutes
+ * with it:  sum_c W[co,c,t] * Rw[c,d,p] = wa * T[t,co,y,xa] + wb * T[t,co,y,xa+1]  with  T[t*Cout+co] = sum_c W[co,C+c,t] * R[c]
+ * ONE 1x1 convolution of the right features per frame (tstereo_conv_d_tc2, k = 1).  This entry point does the rest:
+ *   out[b,co,d,y,x] = act( bias[co] + addL[b,co,y,x] + gconv[b,co,d,y,x]
+ *                          + sum_{ky,kx} lerp_x( T[b,(ky*3+kx)*Cout+co, y+ky-1, .]  at  (x+kx-1) - samples[b,d,y+ky-1,x+kx-1] ) )
+ * T [B, 9*Cout, H, W]; gconv [B, Cout, S, H, W] = the (1,3,3) conv over the group-wise channels (tstereo_group_cost_warp),
+ * no bias / activation, or NULL; addL as in tstereo_cost_conv_warp, or NULL.  `out` (strided fp32) and / or `sout` (S-format,
+ * declared below with the tensor-core convolutions).  Cout = 8 | 16 | 32.
+ * ref: block_cost.py:47-58 -> module.py:111-147 (zero padding of the VOLUME: neighbours outside the image contribute 0). */
+struct tstereo_split;
+int tstereo_cost_taps(const float* T, const float* samples, const float* gconv, const float* addL, const float* bias,
+                      float* out, long long osB, long long osC, long long osD, const struct tstereo_split* sout,
+                      int B, int Cout, int S, int H, int W, int act, void* stream);
+
 /* ---------------------------------------------------------------- convolutions (a4-a7, a9, a12, a13)
  * ref: architecture/modeling/layers/basic_layers.py:194-235 (Conv3d), :340-388 (ConvTranspose3d),
  *      architecture/modeling/aggregation/TemporalStereo/module.py:111-184 (separable pairs).

@@ -28,6 +28,7 @@ SIGNATURES = {
     "tstereo_cost_conv_wpack_floats": (LL, [I, I, I]),
     "tstereo_cost_conv_warp": (I, [P, P, P, P, P, LL, LL, LL, P, P, P, I, I, I, I, I, I, I, I, P]),
     "tstereo_cost_conv_shift": (I, [P, P, P, P, LL, LL, LL, P, P, P, I, I, I, I, I, I, I, I, P]),
+    "tstereo_cost_taps": (I, [P, P, P, P, P, P, LL, LL, LL, P, I, I, I, I, I, I, P]),
     "tstereo_conv_hw3": (I, [P, LL, LL, LL, P, LL, LL, LL, P, P, I, I, I, I, I, I, I, I, I, I, I, P]),
     "tstereo_conv_hw3_tc2_wpack_floats": (LL, [I, I, I]),
     "tstereo_conv_hw3_tc2": (I, [P, LL, LL, LL, P, LL, LL, LL, P, P, P, I, I, I, I, I, I, I, I, I, P]),

@@ -107,6 +107,12 @@ class TEMPORALSTEREO(nn.Module):
         # the left half of the volume is hoisted out of the candidate loop, -23 % / -20 % measured); the coarse shift
         # volume (34 MB per frame, nothing to hoist) is cheaper materialised with ops.block_cost (B200: 406 vs 581 us at B=8)
         self.fuse_cost = ("fine", "precise")
+        # how a fused warp level's first conv runs: "taps" — the channel contraction of the right half commutes with the
+        # warp (a per-position lerp shared by all channels), so it is done ONCE per frame as a 1x1 conv (T = 9 taps x Cout
+        # channels) and each candidate only gathers / lerps T (ops.cost_taps) next to a 3x3 conv over the group-wise
+        # channels; "producer" — the tensor-core conv's producer rebuilds the warped right features per candidate
+        # (ops.cost_conv_warp; B200, precise level B = 8: 545 us against ~150 us for projection + gather + group conv)
+        self.cost_form = "taps"
         # the UNet decoder (fuse -> deconv4 -> concat -> deconv2: the mask logits of the final convex up-sampling, after
         # the last top-2 selection) runs single-term fp16 MMAs: measured on the oracle, rounding its operands to fp16 moves
         # the full-resolution disparity by 7.6e-5 px EPE (max 8e-4) and nothing else (tests/tools/precision_probe_decoder.py);
@@ -242,6 +248,13 @@ class TEMPORALSTEREO(nn.Module):
                     C = cin * 8 // 19
                     tc["left"] = ops.pack_conv_hw3_tc2(ws[:, :C].contiguous(), h)
                     tc["cost"] = ops.pack_conv_hw3_tc2(ws[:, C:].contiguous(), h)
+                    if h and cout in (8, 16, 32):
+                        # tap-projection form (ops.cost_taps): T = 1x1 conv of R with the right-half weights, one output
+                        # channel per (tap, co), its own per-channel fp16 pre-scale; the group-wise channels keep a 3x3 conv
+                        wt, osc_t = ops.fp16_prescale(ops.tap_projection_weights(w[:, C:2 * C].contiguous()))
+                        tc["taps"] = ops.pack_conv_d_tc2(wt, True)
+                        tc["taps_osc"] = osc_t
+                        tc["gconv"] = ops.pack_conv_hw3_tc2(ws[:, 2 * C:].contiguous(), True)
                 elif kind == "cost_shift":         # [-(L - R_d)^2 (C) | g (3C/8)]
                     tc["cost"] = ops.pack_conv_hw3_tc2(ws, h)
         return _Packed(packed, bias, cout, tc, osc if tc else None)
@@ -503,7 +516,7 @@ class TEMPORALSTEREO(nn.Module):
         sc = self._sep(x, p + ".shortcut6", act0=None, act1=None)
         return raa(o, x.shape[-3:], sc, "SiLU")
 
-    def _init3d(self, left, right, samples, p, out_fmt="f"):
+    def _init3d(self, left, right, samples, p, out_fmt="f", s_left=None, s_right=None):
         """block_cost -> init3d stack (reference coarse.py:82-83, fine.py:102-103, precise.py:88-90).  `samples` is the
         candidate tensor [B,S,H,W] (warp volume) or an int (shift volume).  With `fuse_cost` the raw volume is never
         materialised: group-wise terms (small side kernel) + the first (1,3,3) conv rebuilding the feature half."""
@@ -513,6 +526,27 @@ class TEMPORALSTEREO(nn.Module):
             g = ops.group_cost(left, right, samples)
             if isinstance(samples, int):
                 y = ops.cost_conv_shift(left, right, g, a.tc["cost"], a.b, a.cout, "SiLU", half=self.half_split, oscale=a.osc)
+            elif self.cost_form == "taps" and "taps" in a.tc:
+                B_, C_, H_, W_ = right.shape
+                sf = self._sfmt()
+                if sf:
+                    # both feature maps in S-format (given by the caller when a producer already wrote them): the left-half
+                    # conv and the 9*Cout-channel projection (3-5 output groups, each a pass over the input) are TMA-fed
+                    sl = s_left if s_left is not None else ops.split_pack(left)
+                    sr = s_right if s_right is not None else ops.split_pack(right)
+                    addl, _ = ops.conv_hw3_s(sl, a.tc["left"], None, a.cout, 1, None, half=1, oscale=a.osc)
+                    sr5 = ops.Split(B_, C_, 1, H_, W_, sr.parts, t=sr.t, five=True)
+                    T, _ = ops.conv_d_s(sr5, a.tc["taps"], None, 9 * a.cout, 1, 1, 1, False, None, half=1, oscale=a.tc["taps_osc"])
+                    T = T.view(B_, 9 * a.cout, H_, W_)
+                else:
+                    addl = ops.conv_hw3_tc2(left, a.tc["left"], None, a.cout, 1, None, half=True, oscale=a.osc)
+                    T = ops.conv_d_tc2(right.unsqueeze(2), a.tc["taps"], None, 9 * a.cout, 1, 1, 1, False, None, half=True,
+                                       oscale=a.tc["taps_osc"]).view(B_, 9 * a.cout, H_, W_)
+                gc = ops.conv_hw3_tc2(g, a.tc["gconv"], None, a.cout, 1, None, half=True, oscale=a.osc)
+                so = self._new_split((B_, a.cout, samples.shape[1], H_, W_), right) if sf else None
+                y, so = ops.cost_taps(T, samples, gc, addl, a.b, a.cout, "SiLU", sout=so)
+                if sf:
+                    y = so
             else:
                 addl = ops.conv_hw3_tc2(left, a.tc["left"], None, a.cout, 1, None, half=self.half_split, oscale=a.osc)
                 y = ops.cost_conv_warp(right, samples, g, addl, a.tc["cost"], a.b, a.cout, "SiLU", half=self.half_split, oscale=a.osc)
@@ -637,14 +671,14 @@ class TEMPORALSTEREO(nn.Module):
             s_half2 = ops.Split(2 * B, c2, 1, H2, W2, 2, device=dev, five=False)
             s_cat2 = ops.Split(2 * B, 2 * c2, 1, H2, W2, 2, device=dev, five=False)
             s_q = ops.Split(2 * B, c4, 1, H4, W4, 2, device=dev, five=False)
-            s_lcat = ops.Split(B, cf + c4, 1, H4, W4, 1 if single else 2, device=dev, five=False)
+            s_lrcat = ops.Split(2 * B, cf + c4, 1, H4, W4, 2, device=dev, five=False)      # S-format of lrcat (both images)
         with torch.cuda.stream(side):
             ops.copy_planes(l4, lcat[:, :cf])
             ops.copy_planes(r4, rcat[:, :cf])
             if sfmt:
                 # S-format chain: image -> conv2.0 -> conv2.1 -> conv4.0 -> conv4.1; only conv4.1 also writes fp32 (the
                 # 1/4-scale features of the precise cost volume).  s_cat2 = [deconv4 output | conv2.1 output] is the
-                # decoder's concat buffer, s_lcat = [left backbone features | left conv4.1 output] the input of fuse.0
+                # decoder's concat buffer, s_lrcat = [backbone features | conv4.1 output] of both images: the input of fuse.0 and of the precise cost path
                 pk = self._pk
                 # the two images meet in one 2B batch of S-format pixels (3 channels + 5 zeros per 16-byte vector), so
                 # conv2.0 is ONE TMA-fed launch instead of two register-producer launches over strided fp32 loads
@@ -658,8 +692,9 @@ class TEMPORALSTEREO(nn.Module):
                 ops.conv_hw3s2_s(s_cat2.channels(c2, 2 * c2), k.tc["s2"], k.b, k.cout, "ReLU", oscale=k.osc, sout=s_q)
                 k = pk[r + ".conv4.1"]
                 ops.conv_hw3_s(s_q, k.tc["hw3"], k.b, k.cout, 1, "ReLU", out=lrcat[:, cf:], oscale=k.osc,
-                               sout=s_lcat.channels(cf, cf + c4), nb=B)
-                ops.split_pack(l4, out=s_lcat.channels(0, cf))
+                               sout=s_lrcat.channels(cf, cf + c4))
+                ops.split_pack(l4, out=s_lrcat.batches(0, B).channels(0, cf))
+                ops.split_pack(r4, out=s_lrcat.batches(B, 2 * B).channels(0, cf))
             else:
                 self._conv2d(left_image, r + ".conv2.0", 2, out=half2[:B])          # the two images meet in one 2B batch
                 self._conv2d(right_image, r + ".conv2.0", 2, out=half2[B:])
@@ -692,7 +727,8 @@ class TEMPORALSTEREO(nn.Module):
         samples_p = torch.empty((B, 5, H4, W4), device=dev, dtype=torch.float32)
         centre = self._inject["fine_disp"].contiguous() if self._inject and "fine_disp" in self._inject else d_f
         low_f, high_f = ops.range_samples(centre, DISP_RANGE, samples_p, 0)
-        vol = self._init3d(lcat, rcat, samples_p, "precise.init3d", out_fmt="s")
+        vol = self._init3d(lcat, rcat, samples_p, "precise.init3d", out_fmt="s",
+                           s_left=s_lrcat.batches(0, B) if sfmt else None, s_right=s_lrcat.batches(B, 2 * B) if sfmt else None)
         d_p, c_p, o_p, top_disp, top_cost = self._heads_predict(vol, samples_p, "precise.pred_heads",
                                                                 float(self.levels["precise"]["delta"]), True)
         if sfmt:
@@ -704,7 +740,7 @@ class TEMPORALSTEREO(nn.Module):
             s_f1 = ops.Split(B, pk[r + ".fuse.1"].cout, 1, H4, W4, np_, device=dev, five=False)
             s_cc = ops.Split(B, pk[r + ".concat"].cout, 1, H2, W2, np_, device=dev, five=False)
             k = pk[r + ".fuse.0"]
-            ops.conv_hw3_s(s_lcat, k.tc["hw3"], k.b, k.cout, 1, "ReLU", half=h, oscale=k.osc, sout=s_f0)
+            ops.conv_hw3_s(s_lrcat.batches(0, B), k.tc["hw3"], k.b, k.cout, 1, "ReLU", half=h, oscale=k.osc, sout=s_f0)
             k = pk[r + ".fuse.1"]
             ops.conv_hw3_s(s_f0, k.tc["hw3"], k.b, k.cout, 1, "ReLU", half=h, oscale=k.osc, sout=s_f1)
             k = pk[r + ".deconv4"]

@@ -1,6 +1,7 @@
 // Version / error plumbing of the C ABI (include/tstereo.h).
 #include "common.cuh"
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 
 namespace tstereo {
@@ -13,6 +14,10 @@ void set_error(const char* fmt, ...) {
 }
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+bool pdl_enabled() {           // read at every launch: tests and benches flip TSTEREO_PDL inside one process
+    const char* e = getenv("TSTEREO_PDL");
+    return !(e && *e == '0');
+}
 }  // namespace tstereo
 
 extern "C" {

@@ -57,6 +57,7 @@ block_cost_main_kernel(const float* __restrict__ L, const float* __restrict__ R,
                        const float* __restrict__ smp, float* __restrict__ out,
                        float* __restrict__ g1, float* __restrict__ g2,
                        int C, int H, int W, int D) {
+    pdl_sync();
     const int G = C >> 3;
     int z = blockIdx.z;
     const int d = z % D;
@@ -220,6 +221,7 @@ __global__ void __launch_bounds__(128)
 block_cost_resize_kernel(const float* __restrict__ g1, const float* __restrict__ g2, float* __restrict__ out,
                          int G, int D, int H, int W, int outC, int base,
                          float sy1, float sx1, float sy2, float sx2) {
+    pdl_sync();
     // blockDim = (TX, 128 / TX): TX = 32 | 64 | 128 threads along x (4 columns each), the rest along y
     const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
@@ -307,8 +309,8 @@ static int block_cost_launch(bool warp, bool gonly, const float* L, const float*
     float* g2 = scratch + (size_t)B * G * D * H1 * W1;
     const bool vec = (W % 4 == 0) && (((size_t)L | (size_t)out | (size_t)(smp ? smp : L)) & 15) == 0;
     dim3 grid(cdiv(W, 64), cdiv(H, 8), B * G * D);
-#define TS_BC(WP, VC) (gonly ? block_cost_main_kernel<WP, VC, true><<<grid, 128, 0, st>>>(L, R, smp, out, g1, g2, C, H, W, D) \
-                             : block_cost_main_kernel<WP, VC, false><<<grid, 128, 0, st>>>(L, R, smp, out, g1, g2, C, H, W, D))
+#define TS_BC(WP, VC) (gonly ? launch_k(block_cost_main_kernel<WP, VC, true>, dim3(grid), dim3(128), 0, st, L, R, smp, out, g1, g2, C, H, W, D) \
+                             : launch_k(block_cost_main_kernel<WP, VC, false>, dim3(grid), dim3(128), 0, st, L, R, smp, out, g1, g2, C, H, W, D))
     if (warp) {
         if (vec) TS_BC(true, true); else TS_BC(true, false);
     } else {
@@ -322,7 +324,7 @@ static int block_cost_launch(bool warp, bool gonly, const float* L, const float*
     const int tx = cdiv(W, 4) <= 32 ? 32 : (cdiv(W, 4) <= 64 ? 64 : 128);
     dim3 rblock(tx, 128 / tx);
     dim3 rgrid(cdiv(cdiv(W, 4), tx), cdiv(H, (int)rblock.y), B * G);
-    block_cost_resize_kernel<<<rgrid, rblock, 0, st>>>(g1, g2, out, G, D, H, W, outC, base,
+    launch_k(block_cost_resize_kernel, dim3(rgrid), dim3(rblock), 0, st, g1, g2, out, G, D, H, W, outC, base,
                                                     host_ac_scale(H / 2, H), host_ac_scale(W / 2, W),
                                                     host_ac_scale(H / 4, H), host_ac_scale(W / 4, W));
     return check_launch("block_cost_resize");

@@ -21,6 +21,31 @@ inline int check_launch(const char* what) {
     return TSTEREO_OK;
 }
 
+// ---- programmatic dependent launch (PDL): every hot-path kernel starts with pdl_sync() — it lets the NEXT kernel of the
+// stream be scheduled right away (its CTAs run their prologue: barrier init, TMEM allocation, index math) and then waits
+// until the PREVIOUS kernel has completed and flushed its writes, before touching any dependent memory.  launch_k() sets
+// the matching launch attribute (TSTEREO_PDL=0: plain stream order).  Captured into a CUDA graph the edges become
+// programmatic dependencies: the ~1-2 us launch gap between the ~160 dependent kernels of a frame overlaps their tails.
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_sync() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 #define TS_REQUIRE(cond, ...)                 \
     do {                                      \
         if (!(cond)) {                        \

@@ -46,6 +46,7 @@ conv_hw3_kernel(const float* __restrict__ in, long long isB, long long isC, long
                 float* __restrict__ out, long long osB, long long osC, long long osD,
                 const float* __restrict__ w, const float* __restrict__ bias,
                 int Cin, int Cout, int CoutP, int D, int Hin, int Win, int Hout, int Wout, int act) {
+    pdl_sync();
     using Cfg = HW3Cfg<Q, NCG, P, S, DIL>;
     extern __shared__ __align__(16) float smem[];
     float* in_s = smem;                           // [2][CK][IH][IWP]
@@ -184,7 +185,7 @@ static int launch_hw3(const float* in, long long isB, long long isC, long long i
     TS_REQUIRE(gz <= 65535, "conv_hw3: B*D*cout_blocks = %lld exceeds grid.z", gz);
     dim3 grid(cdiv(Wout, 32), cdiv(Hout, Cfg::TH), (unsigned)gz);
     const int CoutP = (Cout + 3) & ~3;
-    kern<<<grid, 256, Cfg::SMEM_BYTES, st>>>(in, isB, isC, isD, out, osB, osC, osD, w, bias, Cin, Cout, CoutP, D, Hin,
+    launch_k(kern, dim3(grid), dim3(256), Cfg::SMEM_BYTES, st, in, isB, isC, isD, out, osB, osC, osD, w, bias, Cin, Cout, CoutP, D, Hin,
                                              Win, Hout, Wout, act);
     return check_launch("conv_hw3");
 }
@@ -201,6 +202,7 @@ conv_d_kernel(const float* __restrict__ in, long long isB, long long isC, long l
               float* __restrict__ out, long long osB, long long osC, long long osD,
               const float* __restrict__ w, const float* __restrict__ bias,
               int Cin, int Cout, int CoutP, int Din, int HW, int stride, int dil, int transposed, int act) {
+    pdl_sync();
     extern __shared__ __align__(16) float ws[];   // [Cin][K][COB]
     constexpr int CIB = (COB >= 32 || PPT == 2) ? 4 : 8;   // input channels whose loads are in flight together
     const int NT = blockDim.x;
@@ -315,7 +317,7 @@ static int launch_d(const float* in, long long isB, long long isC, long long isD
     const int nt = small ? 128 : 256, ppt = small ? 1 : 2;
     dim3 grid(cdiv(HW, nt * ppt), Dout, B * CB);
     const int CoutP = (Cout + 3) & ~3;
-    kern<<<grid, nt, smem, st>>>(in, isB, isC, isD, out, osB, osC, osD, w, bias, Cin, Cout, CoutP, Din, HW, stride,
+    launch_k(kern, dim3(grid), dim3(nt), smem, st, in, isB, isC, isD, out, osB, osC, osD, w, bias, Cin, Cout, CoutP, Din, HW, stride,
                                  dil, transposed, act);
     return check_launch("conv_d");
 }
@@ -332,6 +334,7 @@ deconv_hw_kernel(const float* __restrict__ in, long long isB, long long isC, lon
                  float* __restrict__ out, long long osB, long long osC, long long osD,
                  const float* __restrict__ w, const float* __restrict__ bias,
                  int Cin, int Cout, int CoutP, int D, int Hin, int Win, int act) {
+    pdl_sync();
     extern __shared__ __align__(16) float ws[];   // [Cin][KS*KS][COB]
     constexpr int CIB = 4;
     const int CB = (Cout + COB - 1) / COB;
@@ -455,7 +458,7 @@ static int launch_deconv(const float* in, long long isB, long long isC, long lon
     TS_REQUIRE(gz <= 65535, "deconv_hw: grid.z too large");
     dim3 grid(cdiv(Win, 64), cdiv(2 * Hin, 4), (unsigned)gz), block(64, 4);
     const int CoutP = (Cout + 3) & ~3;
-    kern<<<grid, block, smem, st>>>(in, isB, isC, isD, out, osB, osC, osD, w, bias, Cin, Cout, CoutP, D, Hin, Win,
+    launch_k(kern, dim3(grid), dim3(block), smem, st, in, isB, isC, isD, out, osB, osC, osD, w, bias, Cin, Cout, CoutP, D, Hin, Win,
                                     act);
     return check_launch("deconv_hw");
 }

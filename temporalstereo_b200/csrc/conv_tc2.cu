@@ -138,7 +138,7 @@ int conv_d_impl(const float* in, long long isB, long long isC, long long isD, co
                 int k, int stride, int dilation, int transposed, int act, int half, void* stream, const char* what) {
     TS_REQUIRE(wpack, "%s: null pointer", what);
     TS_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && Din > 0 && Dout > 0 && H > 0 && W > 0, "%s: bad sizes", what);
-    TS_REQUIRE(k == 3 || k == 5, "%s: k=%d unsupported", what, k);
+    TS_REQUIRE(k == 1 || k == 3 || k == 5, "%s: k=%d unsupported", what, k);   // k = 1: a 1x1x1 channel contraction
     if (transposed) {
         TS_REQUIRE(k == 3 && Dout == 2 * Din, "%s: transposed needs k=3, Dout=2*Din (got k=%d Din=%d Dout=%d)", what, k, Din, Dout);
     } else {
@@ -170,6 +170,7 @@ int conv_d_impl(const float* in, long long isB, long long isC, long long isD, co
 // the two 16-byte stores are each coalesced across the warp
 __global__ void split_pack_kernel(const float* __restrict__ in, long long isB, long long isC, long long isD, unsigned short* __restrict__ so,
                                   long long sB, long long sD, long long sP, long long sC8, int parts, int C, int D, int HW, long long total) {
+    pdl_sync();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int C8 = (C + 7) / 8;
@@ -293,7 +294,7 @@ int tstereo_split_pack(const float* in, long long isB, long long isC, long long 
     TS_REQUIRE((long long)H * W < (1ll << 28), "split_pack: plane too large");
     const long long total = (long long)B * D * ((C + 7) / 8) * H * W;
     const int threads = 256;
-    split_pack_kernel<<<(unsigned)cdivll(total, threads), threads, 0, (cudaStream_t)stream>>>(
+    launch_k(split_pack_kernel, dim3((unsigned)cdivll(total, threads)), dim3(threads), 0, (cudaStream_t)stream, 
         in, isB, isC, isD, (unsigned short*)sout->ptr, sout->sB, sout->sD, sout->sP, sout->sC8, sout->parts, C, D, H * W, total);
     return check_launch("split_pack");
 }

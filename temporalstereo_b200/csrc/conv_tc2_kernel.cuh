@@ -275,12 +275,20 @@ __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* t
 }
 
 constexpr int MAX_RS = 8;
+// The fused cost producer holds 48 gathers (3 staged rows x 8 channels x 2 taps) per thread in flight next to the 48
+// accumulators of the ACC form: under the 96-register cap of two CTAs per SM ptxas serialises the gathers (and spills)
+// (measured on B200, precise level B = 8: one CTA per SM with 168 registers, no spills and double-buffered gathers runs
+// 654 us against 545 us for two spilling CTAs — the second CTA's eight producer warps matter more; default off)
+#ifndef TS_FUSE_ONE_CTA
+#define TS_FUSE_ONE_CTA 0
+#endif
+constexpr bool FUSE_ONE_CTA = TS_FUSE_ONE_CTA != 0;
 
 // RAW: 0 = chunks are prefetched into registers; 1 = TMA boxes into a raw fp32 ring; 2 = per-thread cp.async (zero-fill)
 // into the same ring, `rs` chunks deep — for the small, latency-bound layers (any width / alignment)
 // FUSE: 0 = the input is a tensor; 1 / 2 = the input is the warp / shift cost volume built on the fly (see Params)
 template <int CP, int MT, bool DIRECT, int RAW, bool F16, int FOLD, int FUSE = 0>
-__global__ void __launch_bounds__(nthreads(RAW), Cfg<CP, MT, DIRECT, FOLD>::MINB)
+__global__ void __launch_bounds__(nthreads(RAW), (FUSE != 0 && FUSE_ONE_CTA) ? 1 : Cfg<CP, MT, DIRECT, FOLD>::MINB)
 conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_lo) {
     static_assert(FUSE == 0 || (RAW == 0 && FOLD == 3 && !DIRECT), "the fused cost producer is the register path of the 3x3 ACC form");
     static_assert(RAW != 3 || F16, "the S-format input is the fp16 split");
@@ -368,6 +376,9 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap, const 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    // everything above (barriers, TMEM, the layer's constants) overlapped the previous kernel's tail; its outputs are
+    // visible from here on (common.cuh pdl_sync)
+    pdl_sync();
     const uint32_t tmem_base = *tmem_slot;
     const int nmma = F16 ? (p.nchunk + 1) / 2 : p.nchunk;     // MMA chunks (16 | 8 channels); p.nchunk counts 8-channel units
     const int ngroups = (nmma + p.G - 1) / p.G;
@@ -448,7 +459,7 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap, const 
         // unit k+1 are issued BEFORE unit k is converted, into the other register buffer — with one buffer a unit's loads
         // could only be issued after the previous unit's conversion and each unit paid a full memory latency, hidden by
         // nothing but the other warps (ncu r02: 21 % of the stall samples on the first F2FP after the loads).
-        constexpr int NB = (DIRECT && RAW == 0 && FUSE == 0 && RPW <= 2) ? 2 : 1;   // RPW = 3 (MT = 4): no room for 24 more registers
+        constexpr int NB = (RAW == 0 && ((RPW <= 2 && DIRECT && FUSE == 0) || (FUSE != 0 && FUSE_ONE_CTA))) ? 2 : 1;   // RPW = 3 (MT = 4) at two CTAs per SM: no room for 24 more registers
         float v[NB][RPW][8];
         unsigned v_ok[NB];              // bit u: row u of the unit held in v[.] is real data (else: zero it when it is packed)
 #pragma unroll
@@ -457,20 +468,26 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap, const 
             constexpr int BUF = decltype(BUFC)::value;
             if constexpr (FUSE != 0) {
                 v_ok[BUF] = 0xffffffffu;
+                // loads at 32-bit offsets from an opaque 64-bit base (one IMAD.WIDE.U32 per address; left to itself ptxas keeps
+                // the base as a uniform element index and spends ~6 more integer instructions per load: ncu r02, 23 % of the
+                // fused kernel's 3.0e8 warp instructions were address arithmetic); extents are checked by the host
                 if (l_kc < p.wchunks) {          // 8 channels of the feature half, rebuilt from the feature maps
-                    const float* rs = p.in + (long long)b * p.isB + (long long)(l_kc * 8) * p.isC;
+                    unsigned long long rsv;
+                    asm("mov.u64 %0, %1;" : "=l"(rsv) : "l"(p.in + (long long)b * p.isB + (long long)(l_kc * 8) * p.isC));
+                    const float* rs = reinterpret_cast<const float*>(rsv);
                     [[maybe_unused]] const float* ls = p.left + (long long)b * p.isB + (long long)(l_kc * 8) * p.isC;
 #pragma unroll
                     for (int u = 0; u < RPW; ++u) {
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
                             if constexpr (FUSE == 1) {
-                                const float ra = __ldg(rs + (long long)c * p.isC + woff[u]);
-                                const float rb = __ldg(rs + (long long)c * p.isC + woff[u] + 1);
+                                const float* t = rs + ((unsigned)woff[u] + (unsigned)(c * p.isC));
+                                const float ra = __ldg(t);
+                                const float rb = __ldg(t + 1);
                                 v[BUF][u][c] = fmaf(rb, wb[u], __fmul_rn(ra, wa[u]));
                             } else {
                                 const float l = off[u] >= 0 ? __ldg(ls + (long long)c * p.isC + off[u]) : 0.f;
-                                const float e = l - __fmul_rn(__ldg(rs + (long long)c * p.isC + woff[u]), wa[u]);
+                                const float e = l - __fmul_rn(__ldg(rs + ((unsigned)woff[u] + (unsigned)(c * p.isC))), wa[u]);
                                 v[BUF][u][c] = -(e * e);
                             }
                         }
@@ -479,14 +496,29 @@ conv_tc2_kernel(const Params p, const __grid_constant__ CUtensorMap tmap, const 
                     const int kc2 = l_kc - p.wchunks;
                     const float* src = p.in2 + (long long)b * p.i2sB + (long long)d * p.i2sD + (long long)(kc2 * 8) * p.i2sC;
                     const int nvalid = p.C2 - kc2 * 8;
+                    if (nvalid >= 8) {           // full chunk: unconditional loads, padding positions zeroed when the unit is packed
+                        unsigned long long sv64;
+                        asm("mov.u64 %0, %1;" : "=l"(sv64) : "l"(src));
+                        const float* sv = reinterpret_cast<const float*>(sv64);
+                        v_ok[BUF] = 0u;
 #pragma unroll
-                    for (int u = 0; u < RPW; ++u) {
-                        const float* su = src + off[u];
-                        const bool ok = off[u] >= 0;
+                        for (int u = 0; u < RPW; ++u) {
+                            const bool ok = off[u] >= 0;
+                            const unsigned o = ok ? (unsigned)off[u] : 0u;
+                            v_ok[BUF] |= (ok ? 1u : 0u) << u;
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) {
-                            v[BUF][u][c] = (ok && c < nvalid) ? __ldg(su) : 0.f;
-                            su += p.i2sC;
+                            for (int c = 0; c < 8; ++c) v[BUF][u][c] = __ldg(sv + (o + (unsigned)(c * p.i2sC)));
+                        }
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < RPW; ++u) {
+                            const float* su = src + off[u];
+                            const bool ok = off[u] >= 0;
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) {
+                                v[BUF][u][c] = (ok && c < nvalid) ? __ldg(su) : 0.f;
+                                su += p.i2sC;
+                            }
                         }
                     }
                 }
@@ -1078,7 +1110,7 @@ static int launch_one(const Params& p, const CUtensorMap& tm, const CUtensorMap&
         }
         attr_done = true;
     }
-    kern<<<grid, nthreads(RAW), smem_bytes, st>>>(p, tm, tm2);
+    launch_k(kern, grid, dim3(nthreads(RAW)), smem_bytes, st, p, tm, tm2);
     return check_launch(what);
 }
 
@@ -1151,6 +1183,7 @@ static int launch(Params& p, int CP, int planes, cudaStream_t st, const char* wh
         if (FUSE != 0 && !forced && CP == 16 && mt == 4) continue;
         const int jt = (mt + 1) / 2;
         int minb = (direct || jt * N <= 48) ? 2 : 1;
+        if (FUSE != 0 && FUSE_ONE_CTA) minb = 1;
         if (cols > 256) minb = 1;                       // two CTAs need their TMEM columns side by side
         const int SR = 4 * mt + 2 * p.dil;
         const long long tiles = (long long)p.tiles_x * ((p.H + 4 * mt - 1) / (4 * mt)) * planes;

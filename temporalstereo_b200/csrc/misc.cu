@@ -18,6 +18,7 @@ namespace tstereo {
 template <typename T>
 __global__ void __launch_bounds__(256)
 copy_planes_kernel(const T* __restrict__ in, T* __restrict__ out, long long osB, long long osC, int C, int HWv, long long total) {
+    pdl_sync();
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
         const int p = (int)(i % HWv);
         const long long pl = i / HWv;
@@ -35,6 +36,7 @@ copy_planes_kernel(const T* __restrict__ in, T* __restrict__ out, long long osB,
 __global__ void __launch_bounds__(128)
 resize_add_act_kernel(const float* __restrict__ a, const float* __restrict__ skip, float* __restrict__ out,
                       int Da, int Ha, int Wa, int D, int H, int W, float sd, float sy, float sx, int act) {
+    pdl_sync();
     const int pix = blockIdx.x * 128 + threadIdx.x;     // linear over H*W: full CTAs whatever W is
     const int z = blockIdx.y;                           // b*C + c
     if (pix >= H * W) return;
@@ -70,6 +72,7 @@ __global__ void __launch_bounds__(128)
 resize_add_act_s_kernel(const float* __restrict__ a, const float* __restrict__ skip, unsigned short* __restrict__ so,
                         long long sB, long long sD, long long sP, long long sC8, int parts, int C,
                         int Da, int Ha, int Wa, int D, int H, int W, float sd, float sy, float sx, int act) {
+    pdl_sync();
     const int pix = blockIdx.x * 128 + threadIdx.x;
     const int C8 = (C + 7) >> 3;
     const int b = blockIdx.y / C8, c8 = blockIdx.y - b * C8;
@@ -122,6 +125,7 @@ resize_add_act_s_kernel(const float* __restrict__ a, const float* __restrict__ s
 __global__ void __launch_bounds__(256)
 pool5_kernel(const float* __restrict__ x, long long xsB, long long xsC, float* __restrict__ avg,
              float* __restrict__ mx, long long osB, long long osC, int C, int D, int H, int W) {
+    pdl_sync();
     __shared__ float tile[12][36];
     __shared__ float hs[12][32], hm[12][32];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -198,6 +202,7 @@ merge_memory_kernel(const float* __restrict__ vol, const float* __restrict__ sam
                     const float* __restrict__ past_w, const float* __restrict__ past_b,
                     float* __restrict__ out_vol, long long osB, long long osC, float* __restrict__ out_samples,
                     int C, int D, int M, int HW) {
+    pdl_sync();
     const int p = blockIdx.x * 128 + threadIdx.x;
     const int b = blockIdx.y;
     if (p >= HW) return;
@@ -258,6 +263,7 @@ template <bool VEC>
 __global__ void __launch_bounds__(128)
 heads_kernel(const float* __restrict__ feat, const float* __restrict__ w, float* __restrict__ cost,
              float* __restrict__ off, int C, int D, int H, int W, float delta) {
+    pdl_sync();
     extern __shared__ float ws[];  // [2][C][9]
     for (int i = threadIdx.x; i < 2 * C * 9; i += 128) ws[i] = w[i];
     __syncthreads();
@@ -338,6 +344,7 @@ __global__ void __launch_bounds__(128)
 predict_disp_kernel(const float* __restrict__ cost, const float* __restrict__ samples, const float* __restrict__ off,
                     float* __restrict__ disp, float* __restrict__ top_disp, float* __restrict__ top_cost,
                     int D, int HW) {
+    pdl_sync();
     const int p = blockIdx.x * 128 + threadIdx.x;
     const int b = blockIdx.y;
     if (p >= HW) return;
@@ -377,6 +384,7 @@ predict_disp_kernel(const float* __restrict__ cost, const float* __restrict__ sa
 __global__ void __launch_bounds__(256)
 range_samples_kernel(const float* __restrict__ disp, float radius, float* __restrict__ low, float* __restrict__ high,
                      float* __restrict__ samples, int S_total, int c_off, int HW, long long total) {
+    pdl_sync();
     const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
     if (i >= total) return;
     const int p = (int)(i % HW);
@@ -398,6 +406,7 @@ range_samples_kernel(const float* __restrict__ disp, float radius, float* __rest
 __global__ void __launch_bounds__(128)
 convex_upsample_kernel(const float* __restrict__ m, const float* __restrict__ w, const float* __restrict__ bias,
                        const float* __restrict__ disp, float* __restrict__ out, int H, int W) {
+    pdl_sync();
     __shared__ __align__(16) float ws[64 * 36];  // [ci][36]
     __shared__ float bs[36];
     for (int i = threadIdx.x; i < 36 * 64; i += 128) {
@@ -465,6 +474,7 @@ constexpr int UU_TW = 64;
 __global__ void __launch_bounds__(128)
 unet_upsample_kernel(const float* __restrict__ logits, const float* __restrict__ disp, float* __restrict__ full,
                      int H, int W, int h, int w, float sy, float sx) {
+    pdl_sync();
     __shared__ float tile[4][UU_TW];
     const int x0 = blockIdx.x * 128;
     const int x = x0 + threadIdx.x;
@@ -529,6 +539,7 @@ unet_upsample_kernel(const float* __restrict__ logits, const float* __restrict__
 __global__ void __launch_bounds__(128)
 bilinear_resize_kernel(const float* __restrict__ in, float* __restrict__ out, float mul, float div, int C, int Hi,
                        int Wi, int Ho, int Wo, int C_total, int c_off) {
+    pdl_sync();
     const int x = blockIdx.x * 128 + threadIdx.x;
     const int y = blockIdx.y;
     const int c = blockIdx.z % C, b = blockIdx.z / C;
@@ -555,10 +566,10 @@ int tstereo_copy_planes(const float* in, float* out, long long osB, long long os
     const long long total = (long long)B * C * (vec ? HW / 4 : HW);
     const unsigned grid = (unsigned)(cdivll(total, 256) < 148 * 16 ? cdivll(total, 256) : 148 * 16);
     if (vec)
-        copy_planes_kernel<float4><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out),
+        launch_k(copy_planes_kernel<float4>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out),
                                                                            osB / 4, osC / 4, C, HW / 4, total);
     else
-        copy_planes_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, osB, osC, C, HW, total);
+        launch_k(copy_planes_kernel<float>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, in, out, osB, osC, C, HW, total);
     return check_launch("copy_planes");
 }
 
@@ -569,7 +580,7 @@ int tstereo_resize_add_act(const float* a, const float* skip, float* out, int B,
     TS_REQUIRE((long long)B * C <= 65535 && (long long)H * W < (1ll << 31), "resize_add_act: grid too large");
     auto scale = [](int in_size, int out_size) { return out_size > 1 ? (float)(in_size - 1) / (float)(out_size - 1) : 0.0f; };
     dim3 grid(cdiv(H * W, 128), B * C);
-    resize_add_act_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a, skip, out, Da, Ha, Wa, D, H, W, scale(Da, D), scale(Ha, H),
+    launch_k(resize_add_act_kernel, dim3(grid), dim3(128), 0, (cudaStream_t)stream, a, skip, out, Da, Ha, Wa, D, H, W, scale(Da, D), scale(Ha, H),
                                                                   scale(Wa, W), act);
     return check_launch("resize_add_act");
 }
@@ -584,7 +595,7 @@ int tstereo_resize_add_act_s(const float* a, const float* skip, const tstereo_sp
                "resize_add_act_s: S-format output must be 16-byte aligned");
     auto scale = [](int in_size, int out_size) { return out_size > 1 ? (float)(in_size - 1) / (float)(out_size - 1) : 0.0f; };
     dim3 grid(cdiv(H * W, 128), B * ((C + 7) / 8));
-    resize_add_act_s_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a, skip, (unsigned short*)sout->ptr, sout->sB, sout->sD, sout->sP,
+    launch_k(resize_add_act_s_kernel, dim3(grid), dim3(128), 0, (cudaStream_t)stream, a, skip, (unsigned short*)sout->ptr, sout->sB, sout->sD, sout->sP,
                                                                     sout->sC8, sout->parts, C, Da, Ha, Wa, D, H, W, scale(Da, D),
                                                                     scale(Ha, H), scale(Wa, W), act);
     return check_launch("resize_add_act_s");
@@ -596,7 +607,7 @@ int tstereo_pool5(const float* x, long long xsB, long long xsC, float* avg, floa
     TS_REQUIRE(B > 0 && C > 0 && D > 0 && H > 0 && W > 0, "pool5: bad sizes");
     TS_REQUIRE((long long)B * C <= 65535 && cdiv(H, 8) <= 65535, "pool5: grid too large");
     dim3 grid(cdiv(W, 32), cdiv(H, 8), B * C);
-    pool5_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, xsB, xsC, avg, mx, osB, osC, C, D, H, W);
+    launch_k(pool5_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, x, xsB, xsC, avg, mx, osB, osC, C, D, H, W);
     return check_launch("pool5");
 }
 
@@ -609,7 +620,7 @@ int tstereo_merge_memory(const float* vol, const float* samples, const float* me
     TS_REQUIRE(B <= 65535, "merge_memory: B too large");
     const int HW = H * W;
     dim3 grid(cdiv(HW, 128), B, cdiv(C, 4));
-    merge_memory_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(vol, samples, mem_sample, mem_cost, past_w, past_b,
+    launch_k(merge_memory_kernel, dim3(grid), dim3(128), 0, (cudaStream_t)stream, vol, samples, mem_sample, mem_cost, past_w, past_b,
                                                                out_vol, osB, osC, out_samples, C, D, M, HW);
     return check_launch("merge_memory");
 }
@@ -621,8 +632,8 @@ int tstereo_heads(const float* feat, const float* w, float* cost, float* off, in
     TS_REQUIRE((long long)B * D <= 65535 && (long long)H * W < (1ll << 31), "heads: grid too large");
     dim3 grid(cdiv(H * ((W + 3) / 4), 128), B * D);
     const bool vec = (W % 4 == 0) && ((((size_t)feat) | ((size_t)cost) | ((size_t)off)) & 15) == 0;
-    if (vec) heads_kernel<true><<<grid, 128, 2 * C * 9 * sizeof(float), (cudaStream_t)stream>>>(feat, w, cost, off, C, D, H, W, delta);
-    else heads_kernel<false><<<grid, 128, 2 * C * 9 * sizeof(float), (cudaStream_t)stream>>>(feat, w, cost, off, C, D, H, W, delta);
+    if (vec) launch_k(heads_kernel<true>, dim3(grid), dim3(128), 2 * C * 9 * sizeof(float), (cudaStream_t)stream, feat, w, cost, off, C, D, H, W, delta);
+    else launch_k(heads_kernel<false>, dim3(grid), dim3(128), 2 * C * 9 * sizeof(float), (cudaStream_t)stream, feat, w, cost, off, C, D, H, W, delta);
     return check_launch("heads");
 }
 
@@ -632,7 +643,7 @@ int tstereo_predict_disp(const float* cost, const float* samples, const float* o
     TS_REQUIRE(B > 0 && B <= 65535 && D >= 2 && H > 0 && W > 0, "predict_disp: need D >= 2 (D=%d)", D);
     const int HW = H * W;
     dim3 grid(cdiv(HW, 128), B);
-    predict_disp_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(cost, samples, off, disp, top_disp, top_cost, D, HW);
+    launch_k(predict_disp_kernel, dim3(grid), dim3(128), 0, (cudaStream_t)stream, cost, samples, off, disp, top_disp, top_cost, D, HW);
     return check_launch("predict_disp");
 }
 
@@ -641,7 +652,7 @@ int tstereo_range_samples(const float* disp, float radius, float* low, float* hi
     TS_REQUIRE(disp && samples, "range_samples: null pointer");
     TS_REQUIRE(B > 0 && H > 0 && W > 0 && c_off >= 0 && c_off + 5 <= S_total, "range_samples: bad sizes");
     const long long total = (long long)B * H * W;
-    range_samples_kernel<<<(unsigned)cdivll(total, 256), 256, 0, (cudaStream_t)stream>>>(disp, radius, low, high, samples,
+    launch_k(range_samples_kernel, dim3((unsigned)cdivll(total, 256)), dim3(256), 0, (cudaStream_t)stream, disp, radius, low, high, samples,
                                                                                        S_total, c_off, H * W, total);
     return check_launch("range_samples");
 }
@@ -651,7 +662,7 @@ int tstereo_convex_upsample(const float* m, const float* w, const float* b, cons
     TS_REQUIRE(m && w && b && disp && out, "convex_upsample: null pointer");
     TS_REQUIRE(B > 0 && B <= 65535 && H > 0 && H <= 65535 && W > 0, "convex_upsample: bad sizes");
     dim3 grid(cdiv(W, 128), H, B);
-    convex_upsample_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(m, w, b, disp, out, H, W);
+    launch_k(convex_upsample_kernel, dim3(grid), dim3(128), 0, (cudaStream_t)stream, m, w, b, disp, out, H, W);
     return check_launch("convex_upsample");
 }
 
@@ -661,7 +672,7 @@ int tstereo_unet_upsample(const float* logits, const float* disp, float* full, i
     TS_REQUIRE(B > 0 && B <= 65535 && H > 0 && H <= 65535 && W > 0 && h > 0 && w > 0, "unet_upsample: bad sizes");
     dim3 grid(cdiv(W, 128), H, B);
     auto scale = [](int in_size, int out_size) { return out_size > 1 ? (float)(in_size - 1) / (float)(out_size - 1) : 0.0f; };
-    unet_upsample_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(logits, disp, full, H, W, h, w, scale(h, H), scale(w, W));
+    launch_k(unet_upsample_kernel, dim3(grid), dim3(128), 0, (cudaStream_t)stream, logits, disp, full, H, W, h, w, scale(h, H), scale(w, W));
     return check_launch("unet_upsample");
 }
 
@@ -672,7 +683,7 @@ int tstereo_bilinear_resize(const float* in, float* out, float mul, float div, i
                "bilinear_resize: bad sizes");
     TS_REQUIRE(Ho <= 65535 && (long long)B * C <= 65535, "bilinear_resize: grid too large");
     dim3 grid(cdiv(Wo, 128), Ho, B * C);
-    bilinear_resize_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(in, out, mul, div, C, Hi, Wi, Ho, Wo, C_total, c_off);
+    launch_k(bilinear_resize_kernel, dim3(grid), dim3(128), 0, (cudaStream_t)stream, in, out, mul, div, C, Hi, Wi, Ho, Wo, C_total, c_off);
     return check_launch("bilinear_resize");
 }
 

@@ -160,6 +160,43 @@ def cost_conv_shift(left: torch.Tensor, right: torch.Tensor, gvol: torch.Tensor,
 
 
 # --------------------------------------------------------------------------- convolutions
+def tap_projection_weights(w_r: torch.Tensor) -> torch.Tensor:
+    """Right-feature part of a warp level's first-conv weights [Cout, C, 9] -> the [9*Cout, C, 1] weights of the 1x1 conv
+    whose output is T[t*Cout + co] = sum_c w[co, c, t] * R[c] (see `cost_taps`)."""
+    cout, C, T = w_r.shape
+    assert T == 9
+    return w_r.permute(2, 0, 1).reshape(9 * cout, C, 1).contiguous()
+
+
+def cost_taps(T: torch.Tensor, samples: torch.Tensor, gconv: Optional[torch.Tensor], addL: Optional[torch.Tensor],
+              bias: torch.Tensor, cout: int, act=None, out: Optional[torch.Tensor] = None, sout: Optional["Split"] = None,
+              want_f32: bool = False):
+    """Tap-projection form of the warp levels' first (1,3,3) conv: act(bias + addL + gconv + sum over the 3x3 neighbours of
+    the x-lerp of T at the neighbour's warp taps) — T [B, 9*cout, H, W] is the 1x1 projection of the right features
+    (`tap_projection_weights`), the same for every candidate.  Returns (fp32 [B, cout, S, H, W] or None, sout)."""
+    B, S, H, W = samples.shape
+    _chk(T, samples, gconv, addL, bias)
+    if tuple(T.shape) != (B, 9 * cout, H, W):
+        raise ValueError(f"T has shape {tuple(T.shape)}, expected {(B, 9 * cout, H, W)}")
+    if gconv is not None and tuple(gconv.shape) != (B, cout, S, H, W):
+        raise ValueError(f"gconv has shape {tuple(gconv.shape)}, expected {(B, cout, S, H, W)}")
+    if addL is not None and tuple(addL.shape) != (B, cout, H, W):
+        raise ValueError(f"addL has shape {tuple(addL.shape)}, expected {(B, cout, H, W)}")
+    if sout is not None and sout.shape != (B, cout, S, H, W):
+        raise ValueError(f"S-format output has shape {sout.shape}, the operator produces {(B, cout, S, H, W)}")
+    if out is None and (want_f32 or sout is None):
+        out = torch.empty((B, cout, S, H, W), device=T.device, dtype=torch.float32)
+    osB = osC = osD = 0
+    if out is not None:
+        if tuple(out.shape) != (B, cout, S, H, W):
+            raise ValueError(f"out has shape {tuple(out.shape)}, the operator produces {(B, cout, S, H, W)}")
+        osB, osC, osD = _view5(out)
+    keep, ref = _sref(sout)
+    _lib.call("tstereo_cost_taps", _p(T), _p(samples), _p(gconv), _p(addL), _p(bias), _p(out), osB, osC, osD, ref,
+              B, cout, S, H, W, ACT[act], _stream())
+    return out, sout
+
+
 def conv_hw3(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], cout: int, stride: int = 1,
              dilation: int = 1, act=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """(1,3,3) / 3x3 conv, padding = dilation, packed weights w[Cin][9][CoutP]

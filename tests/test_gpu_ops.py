@@ -147,6 +147,42 @@ def test_cost_conv_warp(ops, B, C, Cout, S, H, W, half):
     close(got, two.cpu(), 2e-5, rtol=1e-5, what="fused vs materialised")
 
 
+@pytest.mark.parametrize("B,C,Cout,S,H,W", COST_CONV_CASES[:4] + [(1, 128, 8, 5, 136, 240)])
+def test_cost_taps(ops, B, C, Cout, S, H, W):
+    """Tap-projection form of the warp levels' first conv (1x1 projection of R once per frame + per-candidate gather / lerp
+    + 3x3 conv over the group-wise channels) against the fp64 conv of the ORACLE's volume, and against the producer form."""
+    L, R, smp = _op_inputs(6, B, C, H, W, S)
+    smp[:, 0] = torch.round(smp[:, 0])
+    smp[:, -1] = smp[:, -1] + W                 # a fully out-of-range candidate
+    planes = 2 * C + 3 * (C // 8)
+    w = rnd(Cout, planes, 1, 3, 3, seed=61, scale=(2.0 / (9 * planes)) ** 0.5)
+    b = rnd(Cout, seed=62, scale=0.1)
+    vol = O.block_cost(L, R, smp, 3)
+    want = O._act(F.conv3d(vol.double(), w.double(), b.double(), 1, (0, 1, 1)), "SiLU").float()
+    w9 = w.reshape(Cout, planes, 9)
+    Lc, Rc, sc = L.cuda(), R.cuda(), smp.cuda()
+    g = ops.group_cost(Lc, Rc, sc)
+    addl = ops.conv_hw3_tc2(Lc, ops.pack_conv_hw3_tc2(w9[:, :C].contiguous(), True).cuda(), None, Cout, 1, None, half=True)
+    wt, osc_t = ops.fp16_prescale(ops.tap_projection_weights(w9[:, C:2 * C].contiguous()))
+    T = ops.conv_d_tc2(Rc.unsqueeze(2), ops.pack_conv_d_tc2(wt, True).cuda(), None, 9 * Cout, 1, 1, 1, False, None, half=True,
+                       oscale=osc_t.cuda()).view(B, 9 * Cout, H, W)
+    gc = ops.conv_hw3_tc2(g, ops.pack_conv_hw3_tc2(w9[:, 2 * C:].contiguous(), True).cuda(), None, Cout, 1, None, half=True)
+    so = ops.Split(B, Cout, S, H, W, 2, device="cuda")
+    got, _ = ops.cost_taps(T, sc, gc, addl, b.cuda(), Cout, "SiLU", sout=so, want_f32=True)
+    # the 136x240 case: with these white-noise features the group-wise channels reach |g| ~ 30 and the materialising
+    # kernel's fp32 evaluation of them differs from the oracle's by up to 8e-4 (3e-5 relative; every GPU form — taps,
+    # producer, materialised — then sits 1.2e-4 from the oracle and within 1e-5 of each other, scripts/diag_taps.py)
+    close(got, want, 2e-5 if H * W < 10000 else 2e-4, rtol=1e-5, what="cost_taps")
+    assert torch.equal(so.t.view(torch.int16), ops.split_pack(got).t.view(torch.int16))
+    prod = ops.cost_conv_warp(Rc, sc, g, addl, ops.pack_conv_hw3_tc2(w9[:, C:].contiguous(), True).cuda(), b.cuda(), Cout, "SiLU", half=True)
+    close(got, prod.cpu(), 2e-5, rtol=1e-5, what="taps vs producer form")
+    # into a strided view; without the optional addends
+    buf = torch.full((B, Cout + 8, S, H, W), 7.0, device="cuda")
+    ops.cost_taps(T, sc, None, None, b.cuda(), Cout, None, out=buf[:, 8:])
+    ref, _ = ops.cost_taps(T, sc, None, None, b.cuda(), Cout, None)
+    assert torch.equal(buf[:, 8:], ref) and (buf[:, :8] == 7).all()
+
+
 @pytest.mark.parametrize("half", [False, True])
 @pytest.mark.parametrize("B,C,Cout,D,H,W", [(1, 256, 32, 12, 20, 36), (2, 16, 8, 20, 9, 45), (1, 64, 16, 16, 34, 60)])
 def test_cost_conv_shift(ops, B, C, Cout, D, H, W, half):

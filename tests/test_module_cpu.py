@@ -88,7 +88,7 @@ def test_pack_runs_on_cpu_into_one_arena():
             if t is not None:
                 assert base <= t.data_ptr() < base + n and (t.data_ptr() - base) % 256 == 0, name
     first = pk["precise.init3d.0.conv.0"]
-    assert set(first.tc) == {"hw3", "left", "cost"}
+    assert set(first.tc) == {"hw3", "left", "cost", "taps", "taps_osc", "gconv"}
     assert first.tc["cost"].numel() == lib.tstereo_cost_conv_wpack_floats(128, 8, 1)
     assert first.tc["left"].numel() == lib.tstereo_conv_hw3_tc2_wpack_floats(128, 8, 1)
     assert pk["coarse.init3d.0.conv.0"].tc["cost"].numel() == lib.tstereo_cost_conv_wpack_floats(256, 32, 1)
