@@ -63,6 +63,13 @@ int tstereo_group_cost_shift(const float* left, const float* right, float* gvol,
                              int B, int C, int H, int W, int D, void* stream);
 int tstereo_group_cost_warp(const float* left, const float* right, const float* samples, float* gvol,
                             float* scratch, int B, int C, int H, int W, int S, void* stream);
+/* Shift volume in the layout its consumer stages by TMA: the C cost planes -(L - R_d)^2 as S-format chunks [0, C/8) of
+ * `sout` (struct tstereo_split, declared with the tensor-core convolutions below; needs both parts) + the compact group terms
+ * `gvol` [B, 3C/8, D, H, W] (appended as chunks [C/8, ...) with tstereo_split_pack).  ref: block_cost.py:34-45, 64-81. */
+struct tstereo_split;
+int tstereo_block_cost_shift_s(const float* left, const float* right, const struct tstereo_split* sout, float* gvol,
+                               float* scratch, int B, int C, int H, int W, int D, void* stream);
+
 /* out[B,Cout,D,H,W] (strided view) = act(conv3x3(cost volume) + bias) on the tensor cores, the volume's feature channels
  * rebuilt by the producer from the feature maps and its group channels read from gvol.
  *   warp : virtual input channels [R warped (C) | gvol (3C/8)]; the candidate-invariant left half of the volume enters as

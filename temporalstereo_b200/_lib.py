@@ -24,6 +24,7 @@ SIGNATURES = {
     "tstereo_block_cost_shift": (I, [P, P, P, P, I, I, I, I, I, P]),
     "tstereo_block_cost_warp": (I, [P, P, P, P, P, I, I, I, I, I, P]),
     "tstereo_group_cost_shift": (I, [P, P, P, P, I, I, I, I, I, P]),
+    "tstereo_block_cost_shift_s": (I, [P, P, P, P, P, I, I, I, I, I, P]),
     "tstereo_group_cost_warp": (I, [P, P, P, P, P, I, I, I, I, I, P]),
     "tstereo_cost_conv_wpack_floats": (LL, [I, I, I]),
     "tstereo_cost_conv_warp": (I, [P, P, P, P, P, LL, LL, LL, P, P, P, I, I, I, I, I, I, I, I, P]),

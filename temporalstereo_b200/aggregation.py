@@ -550,6 +550,9 @@ class TEMPORALSTEREO(nn.Module):
             else:
                 addl = ops.conv_hw3_tc2(left, a.tc["left"], None, a.cout, 1, None, half=self.half_split, oscale=a.osc)
                 y = ops.cost_conv_warp(right, samples, g, addl, a.tc["cost"], a.b, a.cout, "SiLU", half=self.half_split, oscale=a.osc)
+        elif self._sfmt() and isinstance(samples, int) and left.shape[1] % 64 == 0:
+            # materialised shift volume (coarse level), written in the S-format its only consumer stages by TMA
+            y = self._hw3(ops.block_cost_shift_s(left, right, samples), a, 1, 1, "SiLU", fmt="s")
         else:
             y = self._hw3(ops.block_cost(left, right, samples), a, 1, 1, "SiLU")
         y = self._d(y, b, 3, 1, 1, False, "SiLU", fmt="s" if self._sfmt() else "f")
@@ -599,7 +602,7 @@ class TEMPORALSTEREO(nn.Module):
         vol = self._sep(cat, f"{lvl}.fuse.conv_fuse", act0=None, act1=None, fmt="s" if self._sfmt() else "f")
         disp, cost, off, _, _ = self._heads_predict(vol, samples, f"{lvl}.pred_heads", float(cfg["delta"]))
         m0, m3 = self._pk[f"{lvl}.convex_upsample.mask.0"], self._pk[f"{lvl}.convex_upsample.mask.3"]
-        mfeat = self._hw3(left, m0, 1, 1, "SiLU")
+        mfeat = self._hw3(ops.split_pack(left) if self._sfmt() else left, m0, 1, 1, "SiLU")
         up = ops.convex_upsample(mfeat, m3.w, m3.b, disp)
         return up, cost, off, samples
 

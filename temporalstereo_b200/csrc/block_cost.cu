@@ -51,12 +51,16 @@ __device__ __forceinline__ void stg4_if(float* p, float a, float b, float c, flo
 // nearer row only (deviation <= 2e-6 * |R|, far below the fp32 noise of the following contraction).
 // GONLY: only the three group-wise terms are produced, into a compact [B, 3G, D, H, W] volume (`out`): the form the
 // fused cost -> first-conv path uses (the L / R_d / -(L-R_d)^2 planes are rebuilt by that conv's producer).
-template <bool WARP, bool VEC, bool GONLY>
+// SOUT (with GONLY, shift form): the C cost planes are ALSO produced, as the S-format (fp16 hi / lo split, chunk = this
+// thread's group of 8 channels: the thread holds all 8 channels of its 4 pixels) that the first conv stages by TMA — the
+// materialised coarse volume in the layout its only consumer reads, same bytes as fp32.
+template <bool WARP, bool VEC, bool GONLY, bool SOUT = false>
 __global__ void __launch_bounds__(128)
 block_cost_main_kernel(const float* __restrict__ L, const float* __restrict__ R,
                        const float* __restrict__ smp, float* __restrict__ out,
                        float* __restrict__ g1, float* __restrict__ g2,
-                       int C, int H, int W, int D) {
+                       int C, int H, int W, int D, unsigned short* __restrict__ so = nullptr, long long ssB = 0,
+                       long long ssD = 0, long long ssP = 0, long long ssC8 = 0) {
     pdl_sync();
     const int G = C >> 3;
     int z = blockIdx.z;
@@ -128,6 +132,7 @@ block_cost_main_kernel(const float* __restrict__ L, const float* __restrict__ R,
 #define TS_BC_UNROLL 8
 #endif
     constexpr int kUnroll = TS_BC_UNROLL;     // channels whose loads are in flight together
+    [[maybe_unused]] float sv[SOUT ? 8 : 1][4];
 #pragma unroll kUnroll
     for (int c = 0; c < 8; ++c) {
         float l[4], rv[4];
@@ -155,6 +160,10 @@ block_cost_main_kernel(const float* __restrict__ L, const float* __restrict__ R,
         for (int k = 0; k < 4; ++k) {
             e[k] = l[k] - rv[k];                 // 0 outside the image (l = 0, weights = 0)
             a0[k] = fmaf(e[k], e[k], a0[k]);
+        }
+        if constexpr (SOUT) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) sv[c][k] = WARP ? rv[k] : -(e[k] * e[k]);
         }
         if (GONLY) {
         } else if (VEC) {
@@ -194,6 +203,23 @@ block_cost_main_kernel(const float* __restrict__ L, const float* __restrict__ R,
         o1 += chs;
     }
     (void)lmask;
+    if constexpr (SOUT) {
+        unsigned short* sp = so + b * ssB + d * ssD + g * ssC8 + (long long)pix * 8;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                hi[j] = pack_h2(sv[2 * j][k], sv[2 * j + 1][k]);
+                const float2 hf = unpack_h2(hi[j]);
+                lo[j] = pack_h2(sv[2 * j][k] - hf.x, sv[2 * j + 1][k] - hf.y);
+            }
+            if (pin[k]) {
+                stg128(sp + k * 8, hi[0], hi[1], hi[2], hi[3]);
+                stg128(sp + k * 8 + ssP, lo[0], lo[1], lo[2], lo[3]);
+            }
+        }
+    }
 
     const int base = GONLY ? 0 : (WARP ? 2 * C : C);
     const int H1 = H >> 1, W1 = W >> 1, H2 = H >> 2, W2 = W >> 2;
@@ -296,7 +322,7 @@ static inline float host_ac_scale(int in_size, int out_size) {
 }
 
 static int block_cost_launch(bool warp, bool gonly, const float* L, const float* R, const float* smp, float* out,
-                             float* scratch, int B, int C, int H, int W, int D, cudaStream_t st) {
+                             float* scratch, int B, int C, int H, int W, int D, cudaStream_t st, const tstereo_split* sout = nullptr) {
     TS_REQUIRE(L && R && out && scratch, "block_cost: null pointer");
     TS_REQUIRE(!warp || smp, "block_cost_warp: null samples");
     TS_REQUIRE(B > 0 && D > 0 && C > 0 && C % 8 == 0, "block_cost: C=%d must be a positive multiple of 8 (B=%d D=%d)", C, B, D);
@@ -309,9 +335,21 @@ static int block_cost_launch(bool warp, bool gonly, const float* L, const float*
     float* g2 = scratch + (size_t)B * G * D * H1 * W1;
     const bool vec = (W % 4 == 0) && (((size_t)L | (size_t)out | (size_t)(smp ? smp : L)) & 15) == 0;
     dim3 grid(cdiv(W, 64), cdiv(H, 8), B * G * D);
-#define TS_BC(WP, VC) (gonly ? launch_k(block_cost_main_kernel<WP, VC, true>, dim3(grid), dim3(128), 0, st, L, R, smp, out, g1, g2, C, H, W, D) \
-                             : launch_k(block_cost_main_kernel<WP, VC, false>, dim3(grid), dim3(128), 0, st, L, R, smp, out, g1, g2, C, H, W, D))
-    if (warp) {
+#define TS_BC(WP, VC) (gonly ? launch_k(block_cost_main_kernel<WP, VC, true>, dim3(grid), dim3(128), 0, st, L, R, smp, out, g1, g2, C, H, W, D, \
+                                        (unsigned short*)nullptr, 0ll, 0ll, 0ll, 0ll)                                                        \
+                             : launch_k(block_cost_main_kernel<WP, VC, false>, dim3(grid), dim3(128), 0, st, L, R, smp, out, g1, g2, C, H, W, D, \
+                                        (unsigned short*)nullptr, 0ll, 0ll, 0ll, 0ll))
+    if (sout) {
+        TS_REQUIRE(!warp && gonly, "block_cost: the S-format cost planes belong to the shift form with compact group terms");
+        TS_REQUIRE(sout->ptr && sout->parts == 2 && sout->C8 >= G, "block_cost: bad S-format output");
+        TS_REQUIRE((((size_t)sout->ptr) & 15) == 0 && (sout->sB & 7) == 0 && (sout->sD & 7) == 0 && (sout->sP & 7) == 0 && (sout->sC8 & 7) == 0,
+                   "block_cost: S-format output must be 16-byte aligned");
+        unsigned short* sp = (unsigned short*)sout->ptr;
+        if (vec) launch_k(block_cost_main_kernel<false, true, true, true>, dim3(grid), dim3(128), 0, st, L, R, smp, out, g1, g2, C, H, W, D, sp,
+                          sout->sB, sout->sD, sout->sP, sout->sC8);
+        else launch_k(block_cost_main_kernel<false, false, true, true>, dim3(grid), dim3(128), 0, st, L, R, smp, out, g1, g2, C, H, W, D, sp,
+                      sout->sB, sout->sD, sout->sP, sout->sC8);
+    } else if (warp) {
         if (vec) TS_BC(true, true); else TS_BC(true, false);
     } else {
         if (vec) TS_BC(false, true); else TS_BC(false, false);
@@ -353,6 +391,14 @@ int tstereo_block_cost_warp(const float* left, const float* right, const float* 
 int tstereo_group_cost_shift(const float* left, const float* right, float* gvol, float* scratch,
                              int B, int C, int H, int W, int D, void* stream) {
     return tstereo::block_cost_launch(false, true, left, right, nullptr, gvol, scratch, B, C, H, W, D, (cudaStream_t)stream);
+}
+
+/* shift volume for a TMA-fed first conv: the C cost planes -(L - R_d)^2 as S-format chunks [0, C/8) of `sout` + the compact
+ * group terms `gvol` (to be appended as chunks [C/8, C/8 + 3C/64) with tstereo_split_pack) */
+int tstereo_block_cost_shift_s(const float* left, const float* right, const tstereo_split* sout, float* gvol, float* scratch,
+                               int B, int C, int H, int W, int D, void* stream) {
+    TS_REQUIRE(sout, "block_cost_shift_s: null S-format output");
+    return tstereo::block_cost_launch(false, true, left, right, nullptr, gvol, scratch, B, C, H, W, D, (cudaStream_t)stream, sout);
 }
 
 int tstereo_group_cost_warp(const float* left, const float* right, const float* samples, float* gvol,

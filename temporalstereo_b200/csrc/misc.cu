@@ -66,8 +66,9 @@ resize_add_act_kernel(const float* __restrict__ a, const float* __restrict__ ski
 }
 
 // The same operator writing the S-format (fp16 hi / lo split) its consumer convolution stages by TMA: thread = one output
-// (y, x) of one (b, 8-channel chunk); it walks the D planes and the chunk's 8 channels (each channel's loads are
-// coalesced across the warp) and stores the two 16-byte vectors of the position.
+// (d, y, x) of one (b, 8-channel chunk); it walks the chunk's 8 channels (each channel's loads are coalesced across the
+// warp) and stores the two 16-byte vectors of the position.  (One thread per plane: walking D inside the thread as the
+// fp32 kernel does left 8 x fewer threads with 8 x the serial work — 368 us per step against 224 for the fp32 form.)
 __global__ void __launch_bounds__(128)
 resize_add_act_s_kernel(const float* __restrict__ a, const float* __restrict__ skip, unsigned short* __restrict__ so,
                         long long sB, long long sD, long long sP, long long sC8, int parts, int C,
@@ -86,7 +87,8 @@ resize_add_act_s_kernel(const float* __restrict__ a, const float* __restrict__ s
     const float* pa = a + ((size_t)b * C + (size_t)c8 * 8) * Da * pl;
     const float* ps = skip ? skip + ((size_t)b * C + (size_t)c8 * 8) * D * HW + pix : nullptr;
     unsigned short* dst = so + b * sB + c8 * sC8 + (long long)pix * 8;
-    for (int d = 0; d < D; ++d) {
+    {
+        const int d = blockIdx.z;
         const LerpIdx id = ac_index(sd, d, Da);         // warp-uniform
         float v[8];
 #pragma unroll
@@ -589,12 +591,12 @@ int tstereo_resize_add_act_s(const float* a, const float* skip, const tstereo_sp
                              int D, int H, int W, int act, void* stream) {
     TS_REQUIRE(a && sout && sout->ptr, "resize_add_act_s: null pointer");
     TS_REQUIRE(B > 0 && C > 0 && Da > 0 && Ha > 0 && Wa > 0 && D > 0 && H > 0 && W > 0, "resize_add_act_s: bad sizes");
-    TS_REQUIRE((long long)B * ((C + 7) / 8) <= 65535 && (long long)H * W < (1ll << 28), "resize_add_act_s: grid too large");
+    TS_REQUIRE((long long)B * ((C + 7) / 8) <= 65535 && D <= 65535 && (long long)H * W < (1ll << 28), "resize_add_act_s: grid too large");
     TS_REQUIRE((sout->parts == 1 || sout->parts == 2) && sout->C8 >= (C + 7) / 8, "resize_add_act_s: bad S-format output");
     TS_REQUIRE((((size_t)sout->ptr) & 15) == 0 && (sout->sB & 7) == 0 && (sout->sD & 7) == 0 && (sout->sP & 7) == 0 && (sout->sC8 & 7) == 0,
                "resize_add_act_s: S-format output must be 16-byte aligned");
     auto scale = [](int in_size, int out_size) { return out_size > 1 ? (float)(in_size - 1) / (float)(out_size - 1) : 0.0f; };
-    dim3 grid(cdiv(H * W, 128), B * ((C + 7) / 8));
+    dim3 grid(cdiv(H * W, 128), B * ((C + 7) / 8), D);
     launch_k(resize_add_act_s_kernel, dim3(grid), dim3(128), 0, (cudaStream_t)stream, a, skip, (unsigned short*)sout->ptr, sout->sB, sout->sD, sout->sP,
                                                                     sout->sC8, sout->parts, C, Da, Ha, Wa, D, H, W, scale(Da, D),
                                                                     scale(Ha, H), scale(Wa, W), act);

@@ -123,6 +123,26 @@ def group_cost(left: torch.Tensor, right: torch.Tensor, disp_sample) -> torch.Te
     return out
 
 
+def block_cost_shift_s(left: torch.Tensor, right: torch.Tensor, D: int) -> "Split":
+    """The shift cost volume of `block_cost(left, right, D)` as an S-format tensor [B, C + 3C/8, D, H, W] (fp16 hi / lo split
+    of the fp32 volume), the layout the TMA-fed first conv reads: the C cost planes come straight from the cost kernel, the
+    3C/8 group-wise planes through `split_pack` of the compact group volume.  C/8 + 3C/64 chunks (C a multiple of 64)."""
+    _chk(left, right)
+    B, Cc, H, W = left.shape
+    assert right.shape == left.shape, "left / right feature shapes differ"
+    G = Cc // 8
+    if (3 * G) % 8:
+        raise ValueError(f"block_cost_shift_s needs C a multiple of 64 (3C/8 group planes must fill whole chunks), got C={Cc}")
+    vol = Split(B, Cc + 3 * G, D, H, W, 2, device=left.device)
+    gv = torch.empty((B, 3 * G, D, H, W), device=left.device, dtype=torch.float32)
+    n = _lib.load().tstereo_block_cost_scratch_floats(B, Cc, H, W, D)
+    scratch = torch.empty((max(int(n), 1),), device=left.device, dtype=torch.float32)
+    keep, ref = _sref(vol.channels(0, Cc))
+    _lib.call("tstereo_block_cost_shift_s", _p(left), _p(right), ref, _p(gv), _p(scratch), B, Cc, H, W, D, _stream())
+    split_pack(gv, out=vol.channels(Cc, Cc + 3 * G))
+    return vol
+
+
 def cost_conv_warp(right: torch.Tensor, samples: torch.Tensor, gvol: torch.Tensor, addL: Optional[torch.Tensor],
                    wpack: torch.Tensor, bias: Optional[torch.Tensor], cout: int, act=None,
                    out: Optional[torch.Tensor] = None, half: bool = False, oscale: Optional[torch.Tensor] = None) -> torch.Tensor:

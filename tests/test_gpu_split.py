@@ -244,3 +244,12 @@ def test_resize_add_act_s(ops, src, dst, C, parts):
     got = ops.resize_add_act_s(a, dst, skip, "SiLU", parts)
     same_split(got, want, "resize_add_act_s")
     same_split(ops.resize_add_act_s(a, dst, None, None, parts), ops.split_pack(ops.resize_add_act(a, dst, None, None), parts), "no skip")
+
+
+@pytest.mark.parametrize("B,C,H,W,D", [(1, 256, 20, 36, 12), (2, 64, 9, 13, 20), (1, 64, 34, 60, 16)])
+def test_block_cost_shift_s(ops, B, C, H, W, D):
+    """The coarse shift volume written directly in S-format == split_pack of the materialising operator's fp32 volume."""
+    L, R = rnd(B, C, H, W, seed=191).cuda(), rnd(B, C, H, W, seed=192).cuda()
+    want = ops.split_pack(ops.block_cost(L, R, D))
+    got = ops.block_cost_shift_s(L, R, D)
+    same_split(got, want, "block_cost_shift_s")
