@@ -370,27 +370,51 @@ def main():
         first = eng._pk["precise.init3d.0.conv.0"]
         hs = eng.half_split
 
-        # (1) the fused path the engine runs at the precise level: group terms -> left-half conv -> cost conv.  The raw
-        #     volume never exists; algorithmic bytes = SURVEY.md 8d "fused path": features + candidates + conv output + weights.
+        # (1) the path the engine runs at the precise level (eng._first_conv): group terms, left-half conv, the 1x1
+        #     "tap projection" of the right features (once per frame), the 3x3 conv over the group-wise channels, and the
+        #     per-candidate gather / lerp kernel.  The raw volume never exists; algorithmic bytes = SURVEY.md 8d "fused
+        #     path": features + candidates + conv output + weights.
+        key = "precise.init3d"
         def fused(i):
-            g = ops.group_cost(lcat[i % nrot], rcat[i % nrot], smp4)
-            al = ops.conv_hw3_tc2(lcat[i % nrot], first.tc["left"], None, 8, 1, None, half=hs, oscale=first.osc)
-            return ops.cost_conv_warp(rcat[i % nrot], smp4, g, al, first.tc["cost"], first.b, 8, "SiLU", half=hs, oscale=first.osc)
+            return eng._first_conv(lcat[i % nrot], rcat[i % nrot], smp4, key)
         gsteps = [CapturedStep(lambda i=i: fused(i), device=dev) for i in range(nrot)]
         ms_fused = timed(lambda i: gsteps[i % nrot].replay(), reps)
-        g0 = ops.group_cost(lcat[0], rcat[0], smp4)
-        al0 = ops.conv_hw3_tc2(lcat[0], first.tc["left"], None, 8, 1, None, half=hs, oscale=first.osc)
+        sf = eng._sfmt() and eng.cost_form == "taps" and "taps" in first.tc
         part = {}
-        for name, fn in (("group_cost", lambda i: ops.group_cost(lcat[i % nrot], rcat[i % nrot], smp4)),
-                         ("left_conv", lambda i: ops.conv_hw3_tc2(lcat[i % nrot], first.tc["left"], None, 8, 1, None, half=hs, oscale=first.osc)),
-                         ("cost_conv", lambda i: ops.cost_conv_warp(rcat[i % nrot], smp4, g0, al0, first.tc["cost"], first.b, 8, "SiLU",
-                                                                    half=hs, oscale=first.osc))):
-            gs = CapturedStep(lambda fn=fn: [fn(i) for i in range(nrot)], device=dev)
-            part[name] = timed(lambda i: gs.replay(), max(reps // nrot, 5)) / nrot
-            del gs
+        if sf:
+            sl0, sr0 = ops.split_pack(lcat[0]), ops.split_pack(rcat[0])
+            sr5 = ops.Split(B, 128, 1, h4, w4, 2, t=sr0.t, five=True)
+            g0 = ops.group_cost(lcat[0], rcat[0], smp4)
+            al0, _ = ops.conv_hw3_s(sl0, first.tc["left"], None, 8, 1, None, half=1, oscale=first.osc)
+            T0, _ = ops.conv_d_s(sr5, first.tc["taps"], None, 72, 1, 1, 1, False, None, half=1, oscale=first.tc["taps_osc"])
+            T0 = T0.view(B, 72, h4, w4)
+            gc0 = ops.conv_hw3_tc2(g0, first.tc["gconv"], None, 8, 1, None, half=True, oscale=first.osc)
+            so0 = ops.Split(B, 8, 5, h4, w4, 2, device=dev)
+            pieces = (("group_cost", lambda i: ops.group_cost(lcat[i % nrot], rcat[i % nrot], smp4)),
+                      ("split_pack_LR", lambda i: (ops.split_pack(lcat[i % nrot], out=sl0), ops.split_pack(rcat[i % nrot], out=sr0))),
+                      ("left_conv", lambda i: ops.conv_hw3_s(sl0, first.tc["left"], None, 8, 1, None, half=1, oscale=first.osc)),
+                      ("tap_projection", lambda i: ops.conv_d_s(sr5, first.tc["taps"], None, 72, 1, 1, 1, False, None, half=1,
+                                                                oscale=first.tc["taps_osc"])),
+                      ("group_conv", lambda i: ops.conv_hw3_tc2(g0, first.tc["gconv"], None, 8, 1, None, half=True, oscale=first.osc)),
+                      ("cost_taps", lambda i: ops.cost_taps(T0, smp4, gc0, al0, first.b, 8, "SiLU", sout=so0)))
+            for name, fn in pieces:
+                gs = CapturedStep(lambda fn=fn: [fn(i) for i in range(nrot)], device=dev)
+                part[name] = timed(lambda i: gs.replay(), max(reps // nrot, 5)) / nrot
+                del gs
+            del sl0, sr0, sr5, T0, gc0, so0, al0
+        # the producer form it replaced (ops.cost_conv_warp: the conv's producer warps rebuild the warped right features
+        # per candidate), timed beside it
+        g0 = ops.group_cost(lcat[0], rcat[0], smp4)
+        alp = ops.conv_hw3_tc2(lcat[0], first.tc["left"], None, 8, 1, None, half=hs, oscale=first.osc)
+        gs = CapturedStep(lambda: [ops.cost_conv_warp(rcat[i % nrot], smp4, g0, alp, first.tc["cost"], first.b, 8, "SiLU", half=hs,
+                                                      oscale=first.osc) for i in range(nrot)], device=dev)
+        part["producer_form_cost_conv (not on the default path)"] = timed(lambda i: gs.replay(), max(reps // nrot, 5)) / nrot
+        del gs, g0, alp
         b_fused = 4 * B * (2 * 128 * h4 * w4 + 5 * h4 * w4 + 8 * 5 * h4 * w4) + 4 * 8 * 304 * 9
-        flops_fused = 2.0 * B * 8 * 9 * 5 * h4 * w4 * (176 + 128 / 5.0)        # R + group channels per candidate, L once
-        del gsteps, g0, al0
+        # MACs actually issued: left 3x3 (128 -> 8) and tap projection (128 -> 72, 1x1) once per frame; group conv (48 -> 8, 3x3)
+        # per candidate; the gather adds 2 * 9 * 8 fp32 FMAs per output position on the CUDA cores
+        flops_fused = 2.0 * B * h4 * w4 * (128 * 9 * 8 + 128 * 72 + 5 * 48 * 9 * 8)
+        del gsteps
 
         # (2) the materialising operator (ops.block_cost, the drop-in for the reference's block_cost): the kernel the
         #     north-star HBM target is quoted on; on the engine's path at the coarse level, and at every level with
@@ -415,14 +439,16 @@ def main():
         step_ms = ms / a.steps
         ach_fused = b_fused / (ms_fused * 1e-3) / 1e9
         result_extra["roofline"] = {
-            "bound": "hbm", "kernel": "fused cost volume -> first conv at the precise level (group_cost + left-half conv_tc2 + "
-            "cost_conv_warp conv_tc2<8,4,ACC,FUSE=1>): the raw 198 MB/frame volume is never written",
+            "bound": "hbm", "kernel": "cost volume -> first conv at the precise level, as the engine runs it (group_cost + left-half "
+            "conv + 1x1 tap projection of the right features + 3x3 conv over the group-wise channels + cost_taps gather/lerp): the raw "
+            "198 MB/frame volume is never written",
             "achieved": ach_fused, "peak": peak, "unit": "GB/s", "frac": ach_fused / peak,
             "traffic": traffic.get("fused_precise_dram_bytes"), "traffic_source": traffic.get("source"),
             "peak_source": peak_src, "algorithmic_bytes": b_fused, "ms": ms_fused, "share_of_step": ms_fused / step_ms,
             "kernels_ms": part,
             "tensor_bound": {"flops_3term": 3 * flops_fused, "tflops_3term": 3 * flops_fused / (ms_fused * 1e-3) / 1e12,
-                             "note": "fp16 hi+lo split = 3 MMA terms per product; bound = max(bytes / HBM, flops / tensor peak)"}}
+                             "note": "tensor-core MACs actually issued (the channel contraction of the right half is hoisted out of the "
+                                     "candidate loop), fp16 hi+lo split = 3 MMA terms per product; bound = max(bytes / HBM, flops / tensor peak)"}}
         result_extra["roofline_block_cost"] = {
             "bound": "hbm", "kernel": "block_cost_warp at the precise level (block_cost_main_kernel<1,1,0> + block_cost_resize_kernel): "
             "the materialising drop-in operator", "achieved": b_p / (ms_p * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",

@@ -516,11 +516,12 @@ class TEMPORALSTEREO(nn.Module):
         sc = self._sep(x, p + ".shortcut6", act0=None, act1=None)
         return raa(o, x.shape[-3:], sc, "SiLU")
 
-    def _init3d(self, left, right, samples, p, out_fmt="f", s_left=None, s_right=None):
-        """block_cost -> init3d stack (reference coarse.py:82-83, fine.py:102-103, precise.py:88-90).  `samples` is the
-        candidate tensor [B,S,H,W] (warp volume) or an int (shift volume).  With `fuse_cost` the raw volume is never
-        materialised: group-wise terms (small side kernel) + the first (1,3,3) conv rebuilding the feature half."""
-        a, b = self._pk[p + ".0.conv.0"], self._pk[p + ".0.conv.1"]
+    def _first_conv(self, left, right, samples, p, s_left=None, s_right=None):
+        """block_cost -> the first (1,3,3) conv + BN + SiLU of a level's init3d (reference block_cost.py:16-83 feeding
+        module.py:111-147 through coarse.py:82-83, fine.py:102-103, precise.py:88-90).  `samples` is the candidate tensor
+        [B,S,H,W] (warp volume) or an int (shift volume).  With `fuse_cost` the raw volume is never materialised (see
+        `cost_form`).  Returns fp32 [B,C,D,H,W] or, in S-format mode, an `ops.Split`.  (bench.py times this function.)"""
+        a = self._pk[p + ".0.conv.0"]
         fuse = self.fuse_cost if isinstance(self.fuse_cost, bool) else p.split(".")[0] in self.fuse_cost
         if fuse and "cost" in a.tc:
             g = ops.group_cost(left, right, samples)
@@ -555,6 +556,12 @@ class TEMPORALSTEREO(nn.Module):
             y = self._hw3(ops.block_cost_shift_s(left, right, samples), a, 1, 1, "SiLU", fmt="s")
         else:
             y = self._hw3(ops.block_cost(left, right, samples), a, 1, 1, "SiLU")
+        return y
+
+    def _init3d(self, left, right, samples, p, out_fmt="f", s_left=None, s_right=None):
+        """block_cost -> init3d stack (reference coarse.py:82-83, fine.py:102-103, precise.py:88-90)."""
+        b = self._pk[p + ".0.conv.1"]
+        y = self._first_conv(left, right, samples, p, s_left, s_right)
         y = self._d(y, b, 3, 1, 1, False, "SiLU", fmt="s" if self._sfmt() else "f")
         y = self._hourglass(y, p + ".1")
         return self._sep(y, p + ".2", dil=2, fmt=out_fmt if self._sfmt() else "f")

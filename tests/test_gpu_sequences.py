@@ -137,6 +137,14 @@ def check_frame(out, want, what, state, strict=False):
     keep_p, keep_f, keep_c, keep_full = sort_tie_masks(rs, state, tol=-1.0 if strict else 1e-4, flip_c=flip_c, flip_f=flip_f)
     keeps = [keep_p, keep_f, keep_c]
     dkeep = [keep_full, keep_p, keep_p, keep_f]          # disps: full, precise (1/4), fine up-sampled (1/4), coarse up-sampled (1/8)
+    if not strict:
+        # a tie-margin flip of the precise level's own selection moves that pixel's precise disparity and the 3x3 (x4)
+        # neighbourhood of the full-resolution one; with ~1 % of the image left after the sort-tie exclusion a single such
+        # pixel would carry the mean
+        flip_p = top2_tie_flips(costs[0], rc[0])
+        if flip_p.any():
+            dkeep[1] = keep_p & ~flip_p
+            dkeep[0] = keep_full & ~_dilate(F.interpolate(_dilate(flip_p, 1).float().unsqueeze(1), scale_factor=4, mode="nearest").squeeze(1) > 0, 4)
     excluded = 1.0 - keep_full.float().mean().item()
     epes = [((a.cpu() - b).abs()[:, 0][k]).mean().item() if k.any() else 0.0 for a, b, k in zip(disps, rd, dkeep)]
     rep, bad_total = [], 0
