@@ -531,6 +531,37 @@ def extras(eng, dev, timed, CapturedStep, synth, temporal):
                        "update_map_ms": timed(lambda i: warp.replay(), 30), "update_map_kernels": warp.launches,
                        "frames_per_s": None}
     out["temporal"]["frames_per_s"] = 1e3 / out["temporal"]["ms_per_frame_graph"]
+    del step, warp
+
+    # ---- BASELINE configs C4 / C5 at their stated shapes and per-GPU batch (B=4/GPU): a whole sequence,
+    #      frame by frame with the state carried (update_map + aggregation), each distinct frame kind one CUDA-graph replay
+    from temporalstereo_b200.aggregation import TEMPORALSTEREO
+    for tag, (Hs, Ws, ns, Tn, Bs) in (("C4", (480, 640, 20, 5, 4)), ("C5", (1088, 1920, 16, 3, 4))):
+        e2 = TEMPORALSTEREO(coarse=dict(num_sample=ns))
+        e2.load_state_dict(synth.synthetic_state_dict(seed=0), strict=True)
+        e2 = e2.to(dev).eval()
+        lf, rf, li, ri = synth.synthetic_frame(Hs, Ws, B=Bs, seed=5)
+        inp = [cu(t) for t in lf + rf + [li, ri]]
+        st = synth.synthetic_temporal_state(Hs, Ws, B=Bs)
+        pose = [cu(st[k]) for k in ("K", "T_now", "inv_T_prev", "baseline")]
+        steps, state = [], {}
+        for t in range(Tn):                  # frame kinds: no state / first warp / local map growing
+            snap = {k: ({a_: b_.clone() for a_, b_ in v.items()} if isinstance(v, dict) else (v.clone() if torch.is_tensor(v) else v))
+                    for k, v in state.items()}
+
+            def frame(snap=snap, t=t):
+                s = copy(snap)
+                if t:
+                    s = temporal.update_map(s, *pose, Hs, Ws, True, 3)
+                return e2(inp[0:3], inp[3:6], inp[6], inp[7], s)
+            state = frame()[5]
+            steps.append(CapturedStep(lambda frame=frame: frame()[0][0], device=dev))
+        ms_seq = timed(lambda i: [g.replay() for g in steps], 5)
+        out["sequence_" + tag] = {"workload": f"{tag}: {Hs}x{Ws} D={16 * ns}, sequence T={Tn}, B={Bs}/GPU, pose warp on, state carried",
+                                  "ms_per_sequence": ms_seq, "frames_per_s": Bs * Tn / (ms_seq * 1e-3),
+                                  "kernels_per_sequence": sum(g.launches for g in steps)}
+        del steps, e2, state
+        torch.cuda.empty_cache()
     return out
 
 

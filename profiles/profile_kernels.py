@@ -41,19 +41,40 @@ state = {"prev_disp": st["prev_disp"].cuda(), "cost_memory": {k: v.cuda() for k,
 pose = [st[k].cuda() for k in ("K", "T_now", "inv_T_prev", "baseline")]
 
 
+sl, sr = ops.split_pack(L), ops.split_pack(R)
+sr5 = ops.Split(B, 128, 1, h4, w4, 2, t=sr.t, five=True)
+x2s = ops.split_pack(torch.randn(2 * B, 32, H // 2, W // 2, device=dev))                   # UNet conv2.1 input (both images)
+x2o = ops.Split(2 * B, 32, 1, H // 2, W // 2, 2, device=dev, five=False)
+c21 = eng._pk["precise.refinement.conv2.1"]
+xcs = ops.split_pack(x2, 1)                                                               # decoder concat input, hi half only
+xco = ops.Split(B, 32, 1, H // 2, W // 2, 1, device=dev, five=False)
+
+
 def run():
+    # ---- the engine's first-conv path at the precise level (eng._first_conv, "taps" form)
     g = ops.group_cost(L, R, smp)                                                         # block_cost_main (group terms) + resize
-    al = ops.conv_hw3_tc2(L, first.tc["left"], None, 8, 1, None, half=hs, oscale=first.osc)
-    ops.cost_conv_warp(R, smp, g, al, first.tc["cost"], first.b, 8, "SiLU", half=hs, oscale=first.osc)
-    v = ops.block_cost(L, R, smp)                                                         # the materialising operator
+    ops.split_pack(L, out=sl)
+    ops.split_pack(R, out=sr)
+    al, _ = ops.conv_hw3_s(sl, first.tc["left"], None, 8, 1, None, half=1, oscale=first.osc)          # left half, once per frame
+    T, _ = ops.conv_d_s(sr5, first.tc["taps"], None, 72, 1, 1, 1, False, None, half=1, oscale=first.tc["taps_osc"])   # 3 launches
+    gc = ops.conv_hw3_tc2(g, first.tc["gconv"], None, 8, 1, None, half=True, oscale=first.osc)
+    ops.cost_taps(T.view(B, 72, h4, w4), smp, gc, al, first.b, 8, "SiLU", sout=ops.Split(B, 8, 5, h4, w4, 2, device=dev))
+    # ---- the producer form it replaced
+    alp = ops.conv_hw3_tc2(L, first.tc["left"], None, 8, 1, None, half=hs, oscale=first.osc)
+    ops.cost_conv_warp(R, smp, g, alp, first.tc["cost"], first.b, 8, "SiLU", half=hs, oscale=first.osc)
+    # ---- the materialising operator + conv over the volume
+    v = ops.block_cost(L, R, smp)
     ops.conv_hw3_tc2(v, first.tc["hw3"], first.b, 8, 1, "SiLU", half=hs, oscale=first.osc)
     del v
+    # ---- S-format (TMA-fed) convolutions: UNet 32 -> 32 at 1/2 scale (3-term, S in / S out), decoder concat 64 -> 32 (1-term)
+    ops.conv_hw3_s(x2s, c21.tc["hw3"], c21.b, 32, 1, "ReLU", half=1, oscale=c21.osc, sout=x2o)
+    ops.conv_hw3_s(xcs, cc.tc["hw3"], cc.b, 32, 1, "ReLU", half=2, oscale=cc.osc, sout=xco)
+    ops.conv_hw3_tc2(x2, cc.tc["hw3"], cc.b, 32, 1, "ReLU", half=2, oscale=cc.osc)        # the same layer, fp32 in / out (register producer)
+    # ---- streaming kernels
     ops.heads(feat_p, w_p, 1.0)
-    ops.resize_add_act(a6, (5, h4, w4), sk6, "SiLU")
+    ops.resize_add_act_s(a6, (5, h4, w4), sk6, "SiLU")
     ops.unet_upsample(lg, dp)
     ops.pool5(vol, av, mx)
-    ops.conv_hw3_tc2(x2, cc.tc["hw3"], cc.b, 32, 1, "ReLU", half=2, oscale=cc.osc)        # decoder concat conv, single-term
-    ops.conv_hw3_tc2(x2, cc.tc["hw3"], cc.b, 32, 1, "ReLU", half=1, oscale=cc.osc)        # the same, 3-term
     temporal.update_map({k: (dict(v) if isinstance(v, dict) else v) for k, v in state.items()}, *pose, 384, 1248, True, 3)
 
 

@@ -537,8 +537,15 @@ class TEMPORALSTEREO(nn.Module):
                     sr = s_right if s_right is not None else ops.split_pack(right)
                     addl, _ = ops.conv_hw3_s(sl, a.tc["left"], None, a.cout, 1, None, half=1, oscale=a.osc)
                     sr5 = ops.Split(B_, C_, 1, H_, W_, sr.parts, t=sr.t, five=True)
-                    T, _ = ops.conv_d_s(sr5, a.tc["taps"], None, 9 * a.cout, 1, 1, 1, False, None, half=1, oscale=a.tc["taps_osc"])
-                    T = T.view(B_, 9 * a.cout, H_, W_)
+                    # 9*Cout outputs = 3-5 groups of 32, each a pass over the input: sub-batches whose S-format features
+                    # (4 bytes per element) stay L2-resident, so only the first pass of a sub-batch reads DRAM
+                    nb = max(1, min(B_, int(64e6 // (C_ * H_ * W_ * 4))))
+                    T5 = torch.empty((B_, 9 * a.cout, 1, H_, W_), device=right.device, dtype=torch.float32)
+                    for b0 in range(0, B_, nb):
+                        b1 = min(B_, b0 + nb)
+                        ops.conv_d_s(sr5.batches(b0, b1), a.tc["taps"], None, 9 * a.cout, 1, 1, 1, False, None, out=T5[b0:b1], half=1,
+                                     oscale=a.tc["taps_osc"])
+                    T = T5.view(B_, 9 * a.cout, H_, W_)
                 else:
                     addl = ops.conv_hw3_tc2(left, a.tc["left"], None, a.cout, 1, None, half=True, oscale=a.osc)
                     T = ops.conv_d_tc2(right.unsqueeze(2), a.tc["taps"], None, 9 * a.cout, 1, 1, 1, False, None, half=True,

@@ -25,6 +25,10 @@ class CapturedStep:
     def __init__(self, fn: Callable[[], Any], warmup: int = 1, device=None):
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         lib = _lib.load()
+        # the graph's kernels hold raw pointers into every tensor `fn` closes over (its input buffers): keep the callable —
+        # and with it those tensors — alive as long as the graph.  (A caller that dropped them got replays over recycled
+        # memory, and an illegal address once torch.cuda.empty_cache() unmapped the segment.)
+        self._fn = fn
         with torch.cuda.device(dev):
             cur = torch.cuda.current_stream(dev)
             side = torch.cuda.Stream(device=dev)
