@@ -132,6 +132,8 @@ class TEMPORALSTEREO(nn.Module):
         self.split_format = True
         # run the UNet encoder on a side stream, concurrently with the coarse and fine levels
         self.overlap_encoder = True
+        # independent branches inside a level (hourglass shortcuts, mask conv, left / projection convs) on a second side stream
+        self.overlap_branches = True
         self._side: Dict[str, torch.cuda.Stream] = {}
         self.register_load_state_dict_post_hook(lambda m, _k: m.invalidate())
         super().train(False)
@@ -504,17 +506,27 @@ class TEMPORALSTEREO(nn.Module):
         operands of the two resize + add + SiLU kernels exist in fp32."""
         sf = self._sfmt()
         m = "s" if sf else "f"
+        dev = x.t.device if isinstance(x, ops.Split) else x.device
+        # the two shortcuts depend on x / pre only: they run beside the down-up chain (outputs allocated before the fork)
+        c6 = self._pk[p + ".shortcut6.conv.1"].cout
+        sc6 = torch.empty((x.shape[0], c6) + tuple(x.shape[2:]), device=dev, dtype=torch.float32)
+        with self._branch(dev) as br6:
+            self._sep(x, p + ".shortcut6", act0=None, act1=None, out=sc6)
         o = self._sep(x, p + ".conv1", stride=2, fmt=m)
         pre = self._sep(o, p + ".conv2", fmt=m)
+        c5 = self._pk[p + ".shortcut5.conv.1"].cout
+        sc5 = torch.empty((pre.shape[0], c5) + tuple(pre.shape[2:]), device=dev, dtype=torch.float32)
+        with self._branch(dev) as br5:            # same side stream: queued behind shortcut6
+            self._sep(pre, p + ".shortcut5", act0=None, act1=None, out=sc5)
         o = self._sep(pre, p + ".conv3", stride=2, fmt=m)
         o = self._sep(o, p + ".conv4", act0=None, act1="SiLU", fmt=m)
         o = self._sep_t(o, p + ".conv5")
-        sc = self._sep(pre, p + ".shortcut5", act0=None, act1=None)
         raa = ops.resize_add_act_s if sf else ops.resize_add_act
-        o = raa(o, pre.shape[-3:], sc, "SiLU")
+        br5.join()
+        o = raa(o, pre.shape[-3:], sc5, "SiLU")
         o = self._sep_t(o, p + ".conv6")
-        sc = self._sep(x, p + ".shortcut6", act0=None, act1=None)
-        return raa(o, x.shape[-3:], sc, "SiLU")
+        br6.join()
+        return raa(o, x.shape[-3:], sc6, "SiLU")
 
     def _first_conv(self, left, right, samples, p, s_left=None, s_right=None):
         """block_cost -> the first (1,3,3) conv + BN + SiLU of a level's init3d (reference block_cost.py:16-83 feeding
@@ -524,38 +536,45 @@ class TEMPORALSTEREO(nn.Module):
         a = self._pk[p + ".0.conv.0"]
         fuse = self.fuse_cost if isinstance(self.fuse_cost, bool) else p.split(".")[0] in self.fuse_cost
         if fuse and "cost" in a.tc:
-            g = ops.group_cost(left, right, samples)
             if isinstance(samples, int):
+                g = ops.group_cost(left, right, samples)
                 y = ops.cost_conv_shift(left, right, g, a.tc["cost"], a.b, a.cout, "SiLU", half=self.half_split, oscale=a.osc)
             elif self.cost_form == "taps" and "taps" in a.tc:
                 B_, C_, H_, W_ = right.shape
                 sf = self._sfmt()
-                if sf:
-                    # both feature maps in S-format (given by the caller when a producer already wrote them): the left-half
-                    # conv and the 9*Cout-channel projection (3-5 output groups, each a pass over the input) are TMA-fed
-                    sl = s_left if s_left is not None else ops.split_pack(left)
-                    sr = s_right if s_right is not None else ops.split_pack(right)
-                    addl, _ = ops.conv_hw3_s(sl, a.tc["left"], None, a.cout, 1, None, half=1, oscale=a.osc)
-                    sr5 = ops.Split(B_, C_, 1, H_, W_, sr.parts, t=sr.t, five=True)
-                    # 9*Cout outputs = 3-5 groups of 32, each a pass over the input: sub-batches whose S-format features
-                    # (4 bytes per element) stay L2-resident, so only the first pass of a sub-batch reads DRAM
-                    nb = max(1, min(B_, int(64e6 // (C_ * H_ * W_ * 4))))
-                    T5 = torch.empty((B_, 9 * a.cout, 1, H_, W_), device=right.device, dtype=torch.float32)
-                    for b0 in range(0, B_, nb):
-                        b1 = min(B_, b0 + nb)
-                        ops.conv_d_s(sr5.batches(b0, b1), a.tc["taps"], None, 9 * a.cout, 1, 1, 1, False, None, out=T5[b0:b1], half=1,
-                                     oscale=a.tc["taps_osc"])
-                    T = T5.view(B_, 9 * a.cout, H_, W_)
-                else:
-                    addl = ops.conv_hw3_tc2(left, a.tc["left"], None, a.cout, 1, None, half=True, oscale=a.osc)
-                    T = ops.conv_d_tc2(right.unsqueeze(2), a.tc["taps"], None, 9 * a.cout, 1, 1, 1, False, None, half=True,
-                                       oscale=a.tc["taps_osc"]).view(B_, 9 * a.cout, H_, W_)
+                addl = torch.empty((B_, a.cout, H_, W_), device=right.device, dtype=torch.float32)
+                T5 = torch.empty((B_, 9 * a.cout, 1, H_, W_), device=right.device, dtype=torch.float32)
+                T = T5.view(B_, 9 * a.cout, H_, W_)
+                # the left-half conv and the projection depend on the features only: beside the group terms (the branch's
+                # outputs are allocated above, before the fork)
+                with self._branch(right.device) as br:
+                    if sf:
+                        # both feature maps in S-format (given by the caller when a producer already wrote them): the left-half
+                        # conv and the 9*Cout-channel projection (3-5 output groups, each a pass over the input) are TMA-fed
+                        sl = s_left if s_left is not None else ops.split_pack(left)
+                        sr = s_right if s_right is not None else ops.split_pack(right)
+                        ops.conv_hw3_s(sl, a.tc["left"], None, a.cout, 1, None, out=addl, half=1, oscale=a.osc)
+                        sr5 = ops.Split(B_, C_, 1, H_, W_, sr.parts, t=sr.t, five=True)
+                        # 9*Cout outputs = 3-5 groups of 32, each a pass over the input: sub-batches whose S-format features
+                        # (4 bytes per element) stay L2-resident, so only the first pass of a sub-batch reads DRAM
+                        nb = max(1, min(B_, int(64e6 // (C_ * H_ * W_ * 4))))
+                        for b0 in range(0, B_, nb):
+                            b1 = min(B_, b0 + nb)
+                            ops.conv_d_s(sr5.batches(b0, b1), a.tc["taps"], None, 9 * a.cout, 1, 1, 1, False, None, out=T5[b0:b1], half=1,
+                                         oscale=a.tc["taps_osc"])
+                    else:
+                        ops.conv_hw3_tc2(left, a.tc["left"], None, a.cout, 1, None, out=addl, half=True, oscale=a.osc)
+                        ops.conv_d_tc2(right.unsqueeze(2), a.tc["taps"], None, 9 * a.cout, 1, 1, 1, False, None, out=T5, half=True,
+                                       oscale=a.tc["taps_osc"])
+                g = ops.group_cost(left, right, samples)
                 gc = ops.conv_hw3_tc2(g, a.tc["gconv"], None, a.cout, 1, None, half=True, oscale=a.osc)
+                br.join()
                 so = self._new_split((B_, a.cout, samples.shape[1], H_, W_), right) if sf else None
                 y, so = ops.cost_taps(T, samples, gc, addl, a.b, a.cout, "SiLU", sout=so)
                 if sf:
                     y = so
             else:
+                g = ops.group_cost(left, right, samples)
                 addl = ops.conv_hw3_tc2(left, a.tc["left"], None, a.cout, 1, None, half=self.half_split, oscale=a.osc)
                 y = ops.cost_conv_warp(right, samples, g, addl, a.tc["cost"], a.b, a.cout, "SiLU", half=self.half_split, oscale=a.osc)
         elif self._sfmt() and isinstance(samples, int) and left.shape[1] % 64 == 0:
@@ -593,6 +612,11 @@ class TEMPORALSTEREO(nn.Module):
         cfg = self.levels[lvl]
         C = cfg["C"]
         B, _, H, W = left.shape
+        # the convex up-sampling's mask conv reads the left features only: beside the whole level
+        m0, m3 = self._pk[f"{lvl}.convex_upsample.mask.0"], self._pk[f"{lvl}.convex_upsample.mask.3"]
+        mfeat = torch.empty((B, m0.cout, H, W), device=left.device, dtype=torch.float32)
+        with self._branch(left.device) as br_mask:
+            self._hw3(ops.split_pack(left) if self._sfmt() else left, m0, 1, 1, "SiLU", out=mfeat)
         vol = self._init3d(left, right, cfg["num_sample"] if coarse else samples, f"{lvl}.init3d")
         if coarse:
             samples = self._linspace_samples(B, cfg["num_sample"], H, W, left.device)
@@ -611,20 +635,58 @@ class TEMPORALSTEREO(nn.Module):
         cat = torch.empty((B, 4 * C, D + 2, H, W), device=left.device, dtype=torch.float32)
         _, samples = ops.merge_memory(vol, samples, ms, mv, pc.w, pc.b, 2, out_vol=cat[:, :C])
         c5 = self._pk[f"{lvl}.fuse.conv_5x5"]
+        with self._branch(left.device) as br_pool:          # both read the merged volume, write their own channel slices of `cat`
+            ops.pool5(cat[:, :C], cat[:, 2 * C:3 * C], cat[:, 3 * C:])
         self._d(cat[:, :C], c5, 5, 1, 1, False, "SiLU", out=cat[:, C:2 * C])
-        ops.pool5(cat[:, :C], cat[:, 2 * C:3 * C], cat[:, 3 * C:])
+        br_pool.join()
         vol = self._sep(cat, f"{lvl}.fuse.conv_fuse", act0=None, act1=None, fmt="s" if self._sfmt() else "f")
         disp, cost, off, _, _ = self._heads_predict(vol, samples, f"{lvl}.pred_heads", float(cfg["delta"]))
-        m0, m3 = self._pk[f"{lvl}.convex_upsample.mask.0"], self._pk[f"{lvl}.convex_upsample.mask.3"]
-        mfeat = self._hw3(ops.split_pack(left) if self._sfmt() else left, m0, 1, 1, "SiLU")
+        br_mask.join()
         up = ops.convex_upsample(mfeat, m3.w, m3.b, disp)
         return up, cost, off, samples
 
-    def _side_stream(self, dev) -> "torch.cuda.Stream":
-        key = str(dev)
+    def _side_stream(self, dev, n: int = 0) -> "torch.cuda.Stream":
+        key = f"{dev}/{n}"
         if key not in self._side:
             self._side[key] = torch.cuda.Stream(device=dev)
         return self._side[key]
+
+    class _Branch:
+        """`with self._branch(dev) as br: ...` runs the block on a second side stream, forked from the current stream; `br.join()`
+        makes the current stream wait for it.  Most launches of the 3-D levels fill a fraction of the 148 SMs and sit on
+        their fixed latency, so independent branches (the hourglass shortcuts, the mask conv, the left / projection convs
+        of the first conv) overlap for free; captured into the CUDA graph they become parallel branches.  Contract: every
+        tensor the branch hands back is allocated by the CALLER before the fork (`out=`), like the encoder's buffers, so
+        the caching allocator never recycles it under the other stream; temporaries inside the block live and die on the
+        side stream."""
+
+        def __init__(self, eng, dev):
+            self.main = torch.cuda.current_stream(dev)
+            self.side = eng._side_stream(dev, 1) if eng.overlap_branches else self.main
+            self.ctx = None
+            self.done = None
+
+        def __enter__(self):
+            if self.side is not self.main:
+                self.side.wait_stream(self.main)
+                self.ctx = torch.cuda.stream(self.side)
+                self.ctx.__enter__()
+            return self
+
+        def __exit__(self, *exc):
+            if self.ctx is not None:
+                self.done = torch.cuda.Event()
+                self.done.record(self.side)
+                self.ctx.__exit__(*exc)
+            return False
+
+        def join(self):
+            if self.done is not None:
+                self.main.wait_event(self.done)
+                self.done = None
+
+    def _branch(self, dev):
+        return TEMPORALSTEREO._Branch(self, dev)
 
     def _conv2d(self, x, p, stride=1, act="ReLU", out=None, single=False):
         k = self._pk[p]
@@ -689,6 +751,13 @@ class TEMPORALSTEREO(nn.Module):
             s_cat2 = ops.Split(2 * B, 2 * c2, 1, H2, W2, 2, device=dev, five=False)
             s_q = ops.Split(2 * B, c4, 1, H4, W4, 2, device=dev, five=False)
             s_lrcat = ops.Split(2 * B, cf + c4, 1, H4, W4, 2, device=dev, five=False)      # S-format of lrcat (both images)
+            # the decoder (mask logits of the final up-sampling) depends on the encoder only, not on any level: it follows the
+            # encoder on the side stream, beside the three levels (hi half only when it runs single-term MMAs)
+            h_dec, np_ = (2, 1) if single else (1, 2)
+            s_f0 = ops.Split(B, self._pk[r + ".fuse.0"].cout, 1, H4, W4, np_, device=dev, five=False)
+            s_f1 = ops.Split(B, self._pk[r + ".fuse.1"].cout, 1, H4, W4, np_, device=dev, five=False)
+            s_cc = ops.Split(B, self._pk[r + ".concat"].cout, 1, H2, W2, np_, device=dev, five=False)
+            logits = torch.empty((B, self._pk[r + ".deconv2"].cout, H, W), device=dev, dtype=torch.float32)
         with torch.cuda.stream(side):
             ops.copy_planes(l4, lcat[:, :cf])
             ops.copy_planes(r4, rcat[:, :cf])
@@ -719,6 +788,21 @@ class TEMPORALSTEREO(nn.Module):
                 self._conv2d(self._conv2d(cat2lr[:, c2:], r + ".conv4.0", 2), r + ".conv4.1", out=lrcat[:, cf:])
             enc_done = torch.cuda.Event()
             enc_done.record(side)
+            if sfmt:
+                pk, h = self._pk, h_dec
+                k = pk[r + ".fuse.0"]
+                ops.conv_hw3_s(s_lrcat.batches(0, B), k.tc["hw3"], k.b, k.cout, 1, "ReLU", half=h, oscale=k.osc, sout=s_f0)
+                k = pk[r + ".fuse.1"]
+                ops.conv_hw3_s(s_f0, k.tc["hw3"], k.b, k.cout, 1, "ReLU", half=h, oscale=k.osc, sout=s_f1)
+                k = pk[r + ".deconv4"]
+                up = s_cat2.batches(0, B).channels(0, c2)
+                ops.deconv_hw_s(s_f1, k.tc["dc"], k.b, k.cout, "ReLU", half=h, oscale=k.osc, sout=up.hi() if single else up)
+                k = pk[r + ".concat"]
+                ops.conv_hw3_s(s_cat2.batches(0, B), k.tc["hw3"], k.b, k.cout, 1, "ReLU", half=h, oscale=k.osc, sout=s_cc)
+                k = pk[r + ".deconv2"]
+                ops.deconv_hw_s(s_cc, k.tc["dc"], k.b, k.cout, None, out=logits, half=h, oscale=k.osc)
+                dec_done = torch.cuda.Event()
+                dec_done.record(side)
 
         # ---- coarse (1/16): integer-shift volume over num_sample candidates
         d_c, c_c, o_c, s_c = self._memory_level("coarse", l16, r16, None, prev_info, True)
@@ -749,24 +833,8 @@ class TEMPORALSTEREO(nn.Module):
         d_p, c_p, o_p, top_disp, top_cost = self._heads_predict(vol, samples_p, "precise.pred_heads",
                                                                 float(self.levels["precise"]["delta"]), True)
         if sfmt:
-            # decoder on S-format activations (hi half only when it runs single-term MMAs); deconv2 writes the fp32 logits
-            pk = self._pk
-            h, np_ = (2, 1) if single else (1, 2)
-            cfz = pk[r + ".fuse.0"].cout
-            s_f0 = ops.Split(B, cfz, 1, H4, W4, np_, device=dev, five=False)
-            s_f1 = ops.Split(B, pk[r + ".fuse.1"].cout, 1, H4, W4, np_, device=dev, five=False)
-            s_cc = ops.Split(B, pk[r + ".concat"].cout, 1, H2, W2, np_, device=dev, five=False)
-            k = pk[r + ".fuse.0"]
-            ops.conv_hw3_s(s_lrcat.batches(0, B), k.tc["hw3"], k.b, k.cout, 1, "ReLU", half=h, oscale=k.osc, sout=s_f0)
-            k = pk[r + ".fuse.1"]
-            ops.conv_hw3_s(s_f0, k.tc["hw3"], k.b, k.cout, 1, "ReLU", half=h, oscale=k.osc, sout=s_f1)
-            k = pk[r + ".deconv4"]
-            up = s_cat2.batches(0, B).channels(0, c2)
-            ops.deconv_hw_s(s_f1, k.tc["dc"], k.b, k.cout, "ReLU", half=h, oscale=k.osc, sout=up.hi() if single else up)
-            k = pk[r + ".concat"]
-            ops.conv_hw3_s(s_cat2.batches(0, B), k.tc["hw3"], k.b, k.cout, 1, "ReLU", half=h, oscale=k.osc, sout=s_cc)
-            k = pk[r + ".deconv2"]
-            logits, _ = ops.deconv_hw_s(s_cc, k.tc["dc"], k.b, k.cout, None, half=h, oscale=k.osc)
+            if side is not main:
+                main.wait_event(dec_done)
         else:
             f = self._conv2d(self._conv2d(lcat, r + ".fuse.0", single=True), r + ".fuse.1", single=True)
             self._deconv_hw(f, self._pk[r + ".deconv4"], 4, "ReLU", out=cat2[:, :c2], single=True)
