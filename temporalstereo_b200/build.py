@@ -55,6 +55,20 @@ def _stale(target: str, deps) -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile and link in-tree.  Serialised across processes with a file lock (every rank of a torchrun job calls
+    `_lib.load()` at once), and the library is linked to a temporary name and renamed into place, so no process can ever
+    dlopen a half-written libtstereo.so."""
+    import fcntl
+    os.makedirs(OBJ, exist_ok=True)
+    with open(os.path.join(OBJ, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force: bool, verbose: bool) -> str:
     nvcc = _nvcc()
     os.makedirs(OBJ, exist_ok=True)
     srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
@@ -84,7 +98,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 if verbose and log:
                     print(log, file=sys.stderr)
     if force or jobs or _stale(LIB, objs):
-        run([nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+        tmp = LIB + f".tmp{os.getpid()}"
+        run([nvcc, "-shared", "-o", tmp] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+        os.replace(tmp, LIB)
     with open(idfile, "w") as f:
         f.write(sid)
     return LIB

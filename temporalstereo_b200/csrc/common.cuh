@@ -60,6 +60,20 @@ __host__ __device__ inline long long cdivll(long long a, long long b) { return (
 // x * sigmoid(x); full-precision expf so the result tracks the fp32 reference to ~1 ulp.
 __device__ __forceinline__ float silu_f(float x) { return __fdiv_rn(x, 1.0f + expf(-x)); }
 
+// SiLU with ex2.approx / rcp.approx (~1e-6 relative, the form the tensor-core epilogues use): ~6 instructions instead of
+// the ~50 of the full-precision expf + IEEE division
+__device__ __forceinline__ float silu_fast(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return x * r;
+}
+__device__ __forceinline__ float apply_act_fast(float x, int act) {
+    if (act == TSTEREO_ACT_SILU) return silu_fast(x);
+    if (act == TSTEREO_ACT_RELU) return fmaxf(x, 0.0f);
+    return x;
+}
+
 __device__ __forceinline__ float apply_act(float x, int act) {
     if (act == TSTEREO_ACT_SILU) return silu_f(x);
     if (act == TSTEREO_ACT_RELU) return fmaxf(x, 0.0f);

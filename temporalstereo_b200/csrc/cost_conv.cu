@@ -121,7 +121,7 @@ cost_taps_kernel(const float* __restrict__ T, const float* __restrict__ smp, con
         }
     }
 #pragma unroll
-    for (int co = 0; co < COUT; ++co) acc[co] = apply_act(acc[co], act);
+    for (int co = 0; co < COUT; ++co) acc[co] = apply_act_fast(acc[co], act);   // the conv epilogue's SiLU (ex2 / rcp approx)
     if (out) {
         float* o = out + (long long)b * osB + (long long)d * osD + pix;
 #pragma unroll

@@ -105,7 +105,7 @@ resize_add_act_s_kernel(const float* __restrict__ a, const float* __restrict__ s
                 float r = id.w0 * plane(id.i0);
                 if (id.w1 != 0.f) r += id.w1 * plane(id.i1);
                 if (ps) r += __ldg(ps + ((size_t)c * D + d) * HW);
-                v[c] = apply_act(r, act);
+                v[c] = apply_act_fast(r, act);      // the S-format consumers are tensor-core convs: same SiLU as their epilogues
             }
         }
         uint32_t hi[4], lo[4];

@@ -304,3 +304,32 @@ def test_decoder_single_term_precision(engine):
     e3 = (exact[0][0].cpu() - want[0][0]).abs().mean().item()
     print(f"decoder single-term vs 3-term: EPE {d.mean().item():.2e} max {d.max().item():.2e}; 3-term vs oracle {e3:.2e}")
     assert d.mean() < 5e-4
+
+
+def test_streams_and_forms_agree(engine):
+    """Engine switches that must not change results: the side streams (UNet encoder / decoder, the independent branches of a
+    level) only reorder launches -> bit-identical outputs, also under repetition (a stream race would show up as a
+    difference); the S-format (`split_format`) and the two forms of the warp levels' first conv (`cost_form`) change the
+    summation order only -> every variant within the oracle tolerances."""
+    sd = synth.synthetic_state_dict(seed=0)
+    lf, rf, li, ri = synth.synthetic_frame(128, 192, B=2, seed=11)
+    with torch.no_grad():
+        want = O.aggregation_forward(sd, lf, rf, li, ri, {})
+    args = (_cuda(lf), _cuda(rf), li.cuda(), ri.cuda())
+    base = engine(*args, {})
+    _check(base, want[:4], "default")
+    assert engine.overlap_encoder and engine.overlap_branches and engine.split_format and engine.cost_form == "taps"
+    try:
+        for enc, br in ((False, False), (True, False), (False, True), (True, True), (True, True)):
+            engine.overlap_encoder, engine.overlap_branches = enc, br
+            out = engine(*args, {})
+            for x, y in zip(base[0] + base[1] + base[2] + base[3], out[0] + out[1] + out[2] + out[3]):
+                assert torch.equal(x, y), (enc, br)
+        engine.cost_form = "producer"
+        _check(engine(*args, {}), want[:4], "cost_form=producer")
+        engine.cost_form = "taps"
+        engine.split_format = False
+        _check(engine(*args, {}), want[:4], "split_format=False")
+    finally:
+        engine.overlap_encoder = engine.overlap_branches = engine.split_format = True
+        engine.cost_form = "taps"
