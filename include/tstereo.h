@@ -354,6 +354,18 @@ int tstereo_normalize_u8(const unsigned char* in, float* out, long long osB, lon
 int tstereo_disp_error(const float* est, const float* gt, float lb, float ub, int use_lb, int use_ub, long long n,
                        double* acc6, void* stream);
 
+/* ---------------------------------------------------------------- training losses, forward only
+ * ref: architecture/modeling/losses/smooth_l1_loss.py:49-74, warsserstein_distance_loss.py:53-81 (loss_per_level).
+ * gt [B,1,Hg,Wg] is scaled (gt / (Wg/W)) and adaptively pooled (average: dense, max: sparse) onto the level's (H, W) grid;
+ * valid where start_disp < gt_s < max_disp / (Wg/W).  acc2 (2 doubles, device): [sum, number of valid pixels] —
+ *   smooth L1:    loss = sum / count                     (0 when no pixel is valid)
+ *   Wasserstein:  loss = sum / (B*H*W),  sum over valid pixels of  sum_d (softmax_d(cost) + 0.25) * |off_d + sample_d - gt_s| */
+int tstereo_loss_smooth_l1(const float* est, const float* gt, int B, int H, int W, int Hg, int Wg, float max_disp, float start_disp,
+                           int sparse, double* acc2, void* stream);
+int tstereo_loss_wasserstein(const float* cost, const float* off, const float* samples, const float* gt, int B, int D, int H, int W,
+                             int Hg, int Wg, float max_disp, float start_disp, int sparse, double* acc2, void* stream);
+
+
 #ifdef __cplusplus
 }
 #endif

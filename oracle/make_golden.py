@@ -115,6 +115,40 @@ def main():
             for i, t in enumerate(offs): arrs[f"off{i}"] = t.numpy()
             save(f"agg_temporal_ns{ns}_{H}x{W}.npz", **arrs)
 
+        # ---- f2: the two loss terms, forward, from the reference's own classes (dense and sparse ground truth, the three
+        #      level resolutions of a 96x160 frame, a case without any valid pixel) ----
+        from architecture.modeling.losses.smooth_l1_loss import DispSmoothL1Loss
+        from architecture.modeling.losses.warsserstein_distance_loss import WarssersteinDistanceLoss
+        arrs = {}
+        for tag, sparse in (("dense", False), ("sparse", True)):
+            est, costs, offs, smps, gt = loss_inputs(sparse)
+            l1 = DispSmoothL1Loss(max_disp=192, start_disp=0, global_weight=1.0, weights=None, sparse=sparse)(est, gt)
+            wa = WarssersteinDistanceLoss(max_disp=192, start_disp=0, global_weight=1.0, weights=None, sparse=sparse)(costs, offs, smps, gt)
+            for k, v in {**l1, **wa}.items():
+                arrs[f"{tag}_{k}"] = v.numpy()
+            none = torch.zeros_like(gt)                       # no valid pixel: both fall back to a masked mean (= 0)
+            arrs[f"{tag}_l1_none"] = DispSmoothL1Loss(max_disp=192, sparse=sparse)(est[1], none)["l1_loss_lvl0"].numpy()
+        save("losses_96x160.npz", **arrs)
+
+
+def loss_inputs(sparse: bool, H: int = 96, W: int = 160, B: int = 2, seed: int = 30):
+    """Seeded inputs of the loss goldens (regenerated by the tests): disparities / costs / offsets / samples at full, 1/4,
+    1/8 and 1/16 resolution and a ground truth with out-of-range and (sparse: 70 % zero) invalid pixels."""
+    rng = np.random.RandomState(seed)
+    f32 = lambda a: torch.from_numpy(np.asarray(a, dtype=np.float32))
+    gt = rng.uniform(-5.0, 230.0, (B, 1, H, W))
+    if sparse:
+        gt = gt * (rng.uniform(0, 1, gt.shape) > 0.7)
+    gt = f32(gt)
+    est = [f32(rng.uniform(0.0, 200.0 / s, (B, 1, H // s, W // s))) for s in (1, 4, 4, 8)]
+    costs, offs, smps = [], [], []
+    for s, D in ((4, 5), (8, 10), (16, 14)):
+        shp = (B, D, H // s, W // s)
+        costs.append(f32(rng.standard_normal(shp) * 2.0))
+        offs.append(f32(rng.uniform(-1.0, 1.0, shp)))
+        smps.append(f32(np.sort(rng.uniform(0.0, 192.0 / s, shp), axis=1)))
+    return est, costs, offs, smps, gt
+
 
 if __name__ == "__main__":
     main()

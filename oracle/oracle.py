@@ -427,3 +427,34 @@ def update_map(prev_info: dict, K, T_now, inv_T_prev, baseline, full_h: int, ful
         prev_info["local_map"] = lm.detach()
         prev_info["local_map_size"] = local_map_size
     return prev_info
+
+
+# --------------------------------------------------------------------------- training losses, forward
+def _scaled_gt(gt, H: int, W: int, max_disp: float, start_disp: float, sparse: bool):
+    """gt / scale, adaptive pooling onto the level's grid, validity mask (smooth_l1_loss.py:50-63 ==
+    warsserstein_distance_loss.py:57-69)."""
+    scale = 1.0
+    g = gt
+    if gt.shape[-2] != H or gt.shape[-1] != W:
+        scale = gt.shape[-1] / (W * 1.0)
+        g = (F.adaptive_max_pool2d if sparse else F.adaptive_avg_pool2d)(gt / scale, (H, W))
+    mask = (g > start_disp) & (g < (max_disp / scale))
+    return g, mask
+
+
+def smooth_l1_loss_level(est, gt, max_disp=192, start_disp=0, sparse=False):
+    """DispSmoothL1Loss.loss_per_level (losses/smooth_l1_loss.py:49-74)."""
+    g, mask = _scaled_gt(gt, est.shape[-2], est.shape[-1], max_disp, start_disp, sparse)
+    if mask.sum() < 1.0:
+        return (torch.abs(est - g) * mask.float()).mean()
+    return F.smooth_l1_loss(est[mask], g[mask], reduction="mean")
+
+
+def wasserstein_loss_level(cost, off, sample, gt, max_disp=192, start_disp=0, sparse=False):
+    """WarssersteinDistanceLoss.loss_per_level (losses/warsserstein_distance_loss.py:53-81)."""
+    prob = torch.softmax(cost, dim=1)
+    g, mask = _scaled_gt(gt, cost.shape[-2], cost.shape[-1], max_disp, start_disp, sparse)
+    if mask.sum() < 1.0:
+        return (prob * torch.abs(off + sample - g) * mask.float()).sum(dim=1).mean()
+    return ((prob * 1.0 + 0.25) * torch.abs(off + sample - g) * mask.float()).sum(dim=1).mean()
+

@@ -59,6 +59,8 @@ SIGNATURES = {
     "tstereo_bilinear_resize": (I, [P, P, F, F, I, I, I, I, I, I, I, I, P]),
     "tstereo_normalize_u8": (I, [P, P, LL, LL, I, I, I, P, P, P]),
     "tstereo_disp_error": (I, [P, P, F, F, I, I, LL, P, P]),
+    "tstereo_loss_smooth_l1": (I, [P, P, I, I, I, I, I, F, F, I, P, P]),
+    "tstereo_loss_wasserstein": (I, [P, P, P, P, I, I, I, I, I, I, F, F, I, P, P]),
     "tstereo_pose_prep": (I, [P, P, P, P, F, P, I, P]),
     "tstereo_reproject_disp": (I, [P, P, P, P, I, I, I, I, I, I, P]),
     "tstereo_project_to_3d": (I, [P, P, P, P, I, I, I, I, P]),

@@ -881,6 +881,31 @@ def disp_error(est: torch.Tensor, gt: torch.Tensor, lb: Optional[float] = None, 
     return acc
 
 
+def loss_smooth_l1(est: torch.Tensor, gt: torch.Tensor, max_disp: float = 192, start_disp: float = 0, sparse: bool = False) -> torch.Tensor:
+    """`DispSmoothL1Loss.loss_per_level` (losses/smooth_l1_loss.py:49-74) on the device, forward only: a 0-dim float32 tensor."""
+    _chk(est, gt)
+    B, _, H, W = est.shape
+    Hg, Wg = gt.shape[-2:]
+    acc = torch.empty((2,), device=est.device, dtype=torch.float64)
+    _lib.call("tstereo_loss_smooth_l1", _p(est), _p(gt), B, H, W, Hg, Wg, float(max_disp), float(start_disp), int(bool(sparse)),
+              acc.data_ptr(), _stream())
+    return (acc[0] / acc[1].clamp_min(1.0)).float()
+
+
+def loss_wasserstein(cost: torch.Tensor, off: torch.Tensor, samples: torch.Tensor, gt: torch.Tensor, max_disp: float = 192,
+                     start_disp: float = 0, sparse: bool = False) -> torch.Tensor:
+    """`WarssersteinDistanceLoss.loss_per_level` (losses/warsserstein_distance_loss.py:53-81) on the device, forward only."""
+    _chk(cost, off, samples, gt)
+    B, D, H, W = cost.shape
+    if off.shape != cost.shape or samples.shape != cost.shape:
+        raise ValueError(f"cost {tuple(cost.shape)}, offsets {tuple(off.shape)} and samples {tuple(samples.shape)} must agree")
+    Hg, Wg = gt.shape[-2:]
+    acc = torch.empty((2,), device=cost.device, dtype=torch.float64)
+    _lib.call("tstereo_loss_wasserstein", _p(cost), _p(off), _p(samples), _p(gt), B, D, H, W, Hg, Wg, float(max_disp),
+              float(start_disp), int(bool(sparse)), acc.data_ptr(), _stream())
+    return (acc[0] / float(B * H * W)).float()
+
+
 def error_dict(acc: torch.Tensor) -> dict:
     """The reference's result dict (percentages and EPE) from `disp_error`'s accumulator; one 48-byte read-back."""
     s, n, c1, c2, c3, c5 = [float(v) for v in acc.cpu()]

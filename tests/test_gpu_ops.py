@@ -882,3 +882,27 @@ def test_single_term_fp16_convs(ops, Cin, Cout, H, W):
     got = ops.deconv_hw_tc2(x.cuda(), ops.pack_deconv_hw_tc2(wks, 4, True).cuda(), b.cuda(), Cout, None, half=2, oscale=inv.cuda())
     wtr = (wks.half().double() * inv.double().view(-1, 1, 1)).transpose(0, 1).reshape(Cin, Cout, 4, 4)
     close(got, F.conv_transpose2d(xr, wtr, b.double(), 2, 1).float(), 2e-5, rtol=1e-5, what="single-term deconv vs rounded-operand reference")
+
+
+# --------------------------------------------------------------------------- losses, forward (f2)
+@pytest.mark.parametrize("sparse", [False, True])
+def test_losses_forward(ops, sparse):
+    """On-device smooth-L1 and Wasserstein loss terms (one launch per level, gt scaled + pooled in the kernel) vs the oracle,
+    and through the reference-shaped classes; fp32 sums in another order: 2e-6 relative."""
+    from oracle.make_golden import loss_inputs
+    from temporalstereo_b200.losses import DispSmoothL1Loss, WarssersteinDistanceLoss
+    est, costs, offs, smps, gt = loss_inputs(sparse)
+    for i, e in enumerate(est):
+        want = float(O.smooth_l1_loss_level(e, gt, 192, 0, sparse))
+        got = float(ops.loss_smooth_l1(e.cuda(), gt.cuda(), 192, 0, sparse))
+        assert abs(got - want) <= 2e-6 * max(1.0, abs(want)), (i, got, want)
+    for i, (c, o, s) in enumerate(zip(costs, offs, smps)):
+        want = float(O.wasserstein_loss_level(c, o, s, gt, 192, 0, sparse))
+        got = float(ops.loss_wasserstein(c.cuda(), o.cuda(), s.cuda(), gt.cuda(), 192, 0, sparse))
+        assert abs(got - want) <= 2e-6 * max(1.0, abs(want)), (i, got, want)
+    assert float(ops.loss_smooth_l1(est[1].cuda(), torch.zeros_like(gt).cuda(), 192, 0, sparse)) == 0.0
+    d1 = DispSmoothL1Loss(192, 0, 0.5, [1.0, 0.7, 0.5, 0.3], sparse)([e.cuda() for e in est], gt.cuda())
+    assert set(d1) == {f"l1_loss_lvl{i}" for i in range(4)}
+    assert abs(float(d1["l1_loss_lvl1"]) - 0.5 * 0.7 * float(O.smooth_l1_loss_level(est[1], gt, 192, 0, sparse))) < 1e-4
+    d2 = WarssersteinDistanceLoss(192, 0, 1.0, None, sparse)([c.cuda() for c in costs], [o.cuda() for o in offs], [s.cuda() for s in smps], gt.cuda())
+    assert set(d2) == {f"wars_loss_lvl{i}" for i in range(3)}

@@ -105,3 +105,19 @@ def test_other_disparity_ranges_match_reference(golden_dir, ns, H, W):
         out = O.aggregation_forward(sd, lf, rf, li, ri, prev, num_sample=ns)
     _check_agg(out, g)
     assert out[2][2].shape[1] == ns + 2
+
+
+def test_losses_match_reference_golden(golden_dir):
+    """f2 (forward): the oracle's restatement of the two loss terms against values computed by the reference's own classes
+    (oracle/make_golden.py, inputs regenerated from the same seeds)."""
+    from oracle.make_golden import loss_inputs
+    g = np.load(os.path.join(golden_dir, "losses_96x160.npz"))
+    for tag, sparse in (("dense", False), ("sparse", True)):
+        est, costs, offs, smps, gt = loss_inputs(sparse)
+        for i, e in enumerate(est):
+            got = O.smooth_l1_loss_level(e, gt, 192, 0, sparse)
+            np.testing.assert_allclose(got.numpy(), g[f"{tag}_l1_loss_lvl{i}"], rtol=1e-6, atol=0)
+        for i, (c, o, s) in enumerate(zip(costs, offs, smps)):
+            got = O.wasserstein_loss_level(c, o, s, gt, 192, 0, sparse)
+            np.testing.assert_allclose(got.numpy(), g[f"{tag}_wars_loss_lvl{i}"], rtol=1e-6, atol=0)
+        assert float(O.smooth_l1_loss_level(est[1], torch.zeros_like(gt), 192, 0, sparse)) == float(g[f"{tag}_l1_none"]) == 0.0
