@@ -458,6 +458,30 @@ def main():
                                  "achieved": (b_p + b_f + b_c) / ((ms_p + ms_f + ms_c) * 1e-3) / 1e9,
                                  "frac": (b_p + b_f + b_c) / ((ms_p + ms_f + ms_c) * 1e-3) / 1e9 / peak}}
 
+        # ---- the kernel most of the step runs on: the TMA-fed S-format tensor-core convolution, on its largest layer (UNet
+        #      conv2.1, 32 -> 32 at 1/2 scale, both images of the B frames), S-format in and out.  HBM-bound: algorithmic
+        #      bytes = 4 B per element in + out (fp16 hi + lo); ncu evidence (tensor pipe, shared-memory pipe, DRAM bytes) in
+        #      profiles/r02_ncu_kernels.txt row 15.
+        if eng._sfmt():
+            c21 = eng._pk["precise.refinement.conv2.1"]
+            h2, w2 = H // 2, W // 2
+            nrc = max(2, -(-2 * L2_BYTES // (2 * B * 32 * h2 * w2 * 4)))
+            xs_ = [ops.split_pack(torch.randn(2 * B, 32, h2, w2, device=dev)) for _ in range(nrc)]
+            so_ = ops.Split(2 * B, 32, 1, h2, w2, 2, device=dev, five=False)
+            gs = CapturedStep(lambda: [ops.conv_hw3_s(x_, c21.tc["hw3"], c21.b, 32, 1, "ReLU", half=1, oscale=c21.osc, sout=so_)
+                                       for x_ in xs_], device=dev)
+            ms_c = timed(lambda i: gs.replay(), max(reps // nrc, 5)) / nrc
+            b_conv = 2 * (2 * B * 32 * h2 * w2 * 4)
+            result_extra["roofline_conv"] = {
+                "bound": "hbm", "kernel": "conv_tc2_kernel<32,2,DIRECT,RAW=3 (S-format in via TMA),F16,FOLD=3>: UNet conv2.1 32->32 3x3 at "
+                "1/2 scale, 2B images, S-format in and out, 3-term fp16 split", "achieved": b_conv / (ms_c * 1e-3) / 1e9, "peak": peak,
+                "unit": "GB/s", "frac": b_conv / (ms_c * 1e-3) / 1e9 / peak, "algorithmic_bytes": b_conv, "ms": ms_c,
+                "traffic": traffic.get("split_conv_unet_conv21_dram_bytes"),
+                "tflops_fp16_issued": 3 * 2.0 * 2 * B * h2 * w2 * 32 * 32 * 9 / (ms_c * 1e-3) / 1e12,
+                "note": "ncu: tensor pipe 52 % active, shared-memory pipe ~96 % busy (tensor-core operand reads 61 % + TMA fills / "
+                        "epilogue 35 %), DRAM 49 % of peak: the SWIZZLE_NONE K-major operand form reads A (4 KB) + B (3 KB) per 128x96x16 MMA"}
+            del gs, xs_, so_
+
         # ---- streaming latency (B = 1, CUDA graph) and the temporal configuration C3 (KITTI 384x1248, pose warp on)
         if not a.no_extras:
             result_extra.update(extras(eng, dev, timed, CapturedStep, synth, temporal))
